@@ -1,0 +1,151 @@
+// Shared device/host helpers for libast_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/ast_b200.h"
+
+#define AST_CHECK_LAUNCH()                                   \
+  do {                                                       \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) return (int)e__;                 \
+  } while (0)
+
+#define AST_CUDA(call)                                       \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return (int)e__;                 \
+  } while (0)
+
+namespace ast {
+
+constexpr int kWarp = 32;
+
+// ---- Welford / Chan running moments (count, mean, M2), fp32 --------------------------------
+struct Moments {
+  float n, mean, m2;
+};
+
+__device__ __forceinline__ Moments moments_merge(Moments a, Moments b) {
+  // Chan et al. pairwise combination; safe for empty operands.
+  float n = a.n + b.n;
+  if (n == 0.f) return Moments{0.f, 0.f, 0.f};
+  float d = b.mean - a.mean;
+  float fb = b.n / n;
+  Moments r;
+  r.n = n;
+  r.mean = a.mean + d * fb;
+  r.m2 = a.m2 + b.m2 + d * d * a.n * fb;
+  return r;
+}
+
+__device__ __forceinline__ Moments moments_warp_reduce(Moments m) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Moments o;
+    o.n = __shfl_xor_sync(0xffffffffu, m.n, off);
+    o.mean = __shfl_xor_sync(0xffffffffu, m.mean, off);
+    o.m2 = __shfl_xor_sync(0xffffffffu, m.m2, off);
+    m = moments_merge(m, o);
+  }
+  return m;
+}
+
+// Per-thread streaming Welford over V interleaved lanes that share one count: one reciprocal
+// per vector, three FMAs-class ops per element.
+template <int V>
+struct WelfordLanes {
+  float n;
+  float mean[V];
+  float m2[V];
+  __device__ __forceinline__ void init() {
+    n = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { mean[j] = 0.f; m2[j] = 0.f; }
+  }
+  __device__ __forceinline__ void push(const float (&x)[V]) {
+    n += 1.f;
+    float rn = __frcp_rn(n);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float d = x[j] - mean[j];
+      mean[j] = fmaf(d, rn, mean[j]);
+      m2[j] = fmaf(d, x[j] - mean[j], m2[j]);
+    }
+  }
+  __device__ __forceinline__ Moments fold() const {
+    Moments r{n, mean[0], m2[0]};
+#pragma unroll
+    for (int j = 1; j < V; ++j) r = moments_merge(r, Moments{n, mean[j], m2[j]});
+    return r;
+  }
+};
+
+// ---- vector I/O ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Element-type traits for 16-byte vectors: fp32 -> 4 lanes, bf16 -> 8 lanes.
+template <bool BF16>
+struct Vec16;
+template <>
+struct Vec16<false> {
+  static constexpr int V = 4;
+  using elem = float;
+  __device__ static __forceinline__ void unpack(uint4 u, float (&x)[4]) {
+    x[0] = __uint_as_float(u.x); x[1] = __uint_as_float(u.y);
+    x[2] = __uint_as_float(u.z); x[3] = __uint_as_float(u.w);
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&x)[4]) {
+    return make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]),
+                      __float_as_uint(x[3]));
+  }
+  __device__ static __forceinline__ float load1(const void* p, int64_t i) {
+    return reinterpret_cast<const float*>(p)[i];
+  }
+  __device__ static __forceinline__ void store1(void* p, int64_t i, float v) {
+    reinterpret_cast<float*>(p)[i] = v;
+  }
+};
+template <>
+struct Vec16<true> {
+  static constexpr int V = 8;
+  using elem = __nv_bfloat16;
+  __device__ static __forceinline__ void unpack(uint4 u, float (&x)[8]) {
+    x[0] = bf16lo(u.x); x[1] = bf16hi(u.x); x[2] = bf16lo(u.y); x[3] = bf16hi(u.y);
+    x[4] = bf16lo(u.z); x[5] = bf16hi(u.z); x[6] = bf16lo(u.w); x[7] = bf16hi(u.w);
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&x)[8]) {
+    return make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                      pack_bf16(x[6], x[7]));
+  }
+  __device__ static __forceinline__ float load1(const void* p, int64_t i) {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  }
+  __device__ static __forceinline__ void store1(void* p, int64_t i, float v) {
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  }
+};
+
+__host__ __device__ __forceinline__ bool aligned16(const void* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+}  // namespace ast

@@ -1,0 +1,400 @@
+// K2: 3x3 stride-1 convolution as an implicit GEMM on tcgen05 / TMEM, operands fed by TMA.
+//
+// Reference work replaced (paths relative to /root/reference):
+//   VGG-19 features   models.py:186-240  nn.Conv2d(k3, zero pad 1, bias) + ReLU + MaxPool2d(2,2)
+//   classic decoder   models.py:598-628  ReflectionPad2d(1) + Conv2d(k3) + ReLU + Upsample(x2)
+//
+// Data layout: activations are bf16 [N][H+2][W+2][C] with a one-pixel halo that already holds the
+// padding of the consuming conv (zeros for VGG, the reflection for the decoder), so a 3x3 tap is a
+// plain shifted box.  GEMM view: M = output pixels (tile = 8 rows x 16 cols = 128), N = Cout
+// (BN = 64/128/256 per CTA), K = 9 taps x Cin in steps of 64 channels.
+//   A (128 x 64)  one 4-D TMA box {64 ch, 16 w, 8 h, 1 n} at (cb*64, w0+kw, h0+kh, n): pixel rows of
+//                 128 B, 128B-swizzled -> exactly the canonical K-major SW128 UMMA operand.
+//   B (BN x 64)   one 3-D TMA box {64 ci, BN co, 1 tap} of the packed weights [9][Cout][Cin].
+//   D (128 x BN)  fp32 in TMEM, double buffered (2*BN columns) so the epilogue of tile i overlaps
+//                 the MMAs of tile i+1.
+// Warp roles (256 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias -> ReLU
+// -> {plain | 2x2 max-pool via shuffles | nearest x2 upsample} -> bf16 -> global, plus the
+// reflection halo of the output when the next layer is a decoder conv).
+#include "tc.cuh"
+
+namespace ast {
+namespace tc {
+
+static EncodeTiledFn g_encode = nullptr;
+
+EncodeTiledFn get_encode_tiled() {
+  if (g_encode) return g_encode;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return g_encode;
+}
+
+int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return AST_E_NODRIVER;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : AST_E_SHAPE;
+}
+
+constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W, KBLK = 64;
+constexpr int A_STAGE_BYTES = TILE_M * KBLK * 2;  // 16 KB
+constexpr int kConvThreads = 256;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * KBLK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // multiple of 1024
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);  // 192 KB of operands
+  static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
+};
+
+struct ConvParams {
+  int N, H, W, Cin, Cout;
+  int Ho, Wo;
+  int relu, halo, tap_prerelu;
+  int tiles_w, tiles_h, n_blocks, num_tiles;
+  const float* bias;
+  __nv_bfloat16* out;
+  float* tap;
+};
+
+// Output coordinates (unpadded grid, -1 and Xo are the halo) that conv coordinate x feeds.
+template <int EPI>
+__device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)[4]) {
+  int n = 0;
+  if (EPI == AST_EPI_PLAIN) {
+    t[n++] = x;
+  } else if (EPI == AST_EPI_UP2) {
+    t[n++] = 2 * x;
+    t[n++] = 2 * x + 1;
+  } else {
+    t[n++] = x >> 1;
+  }
+  if (reflect) {  // ReflectionPad2d(1) of the OUTPUT grid: index -1 <- 1, index Xo <- Xo-2
+    const int m = n;
+    for (int i = 0; i < m; ++i) {
+      if (t[i] == 1) t[n++] = -1;
+      if (t[i] == Xo - 2) t[n++] = Xo;
+    }
+  }
+  return n;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B operands need 1024 B alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int cblocks = p.Cin / KBLK;
+  const int ksteps = 9 * cblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nb = t % p.n_blocks; t /= p.n_blocks;
+        const int twi = t % p.tiles_w; t /= p.tiles_w;
+        const int thi = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        const int h0 = thi * TILE_H, w0 = twi * TILE_W;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kh = tap / 3, kw = tap - 3 * kh;
+          for (int cb = 0; cb < cblocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            const uint32_t a_dst = base + stage * C::STAGE_BYTES;
+            tma_load_4d(a_dst, &tmA, full_bar(stage), cb * KBLK, w0 + kw, h0 + kh, n);
+            tma_load_3d(a_dst + A_STAGE_BYTES, &tmB, full_bar(stage), cb * KBLK, nb * BN, tap);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = base + stage * C::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < KBLK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle atom
+            const uint64_t adesc = make_sdesc_k128(a_addr + k * 32);
+            const uint64_t bdesc = make_sdesc_k128(b_addr + k * 32);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int e = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32e, 32e+32)
+    const int hl = 2 * e + (lane >> 4);
+    const int wl = lane & 15;
+    const bool reflect = p.halo == AST_HALO_REFLECT;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int nb = t % p.n_blocks; t /= p.n_blocks;
+      const int twi = t % p.tiles_w; t /= p.tiles_w;
+      const int thi = t % p.tiles_h;
+      const int n = t / p.tiles_h;
+      const int h = thi * TILE_H + hl, w = twi * TILE_W + wl;
+      const bool in_img = (h < p.H) && (w < p.W);
+
+      int rows[4], cols[4], nr = 0, nc = 0;
+      bool owner;
+      if (EPI == AST_EPI_POOL2) {
+        owner = ((hl & 1) == 0) && ((wl & 1) == 0) && ((h >> 1) < p.Ho) && ((w >> 1) < p.Wo);
+      } else {
+        owner = in_img;
+      }
+      if (owner) {
+        nr = out_targets<EPI>(h, p.Ho, reflect, rows);
+        nc = out_targets<EPI>(w, p.Wo, reflect, cols);
+      }
+
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN + chunk * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const int ch0 = nb * BN + chunk * 32;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[i + 0] = __uint_as_float(v[i + 0]) + b.x;
+          f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
+          f[i + 2] = __uint_as_float(v[i + 2]) + b.z;
+          f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+        }
+        if (p.tap && p.tap_prerelu && in_img) {
+          float* tp = p.tap + (((int64_t)n * p.Cout + ch0) * p.H + h) * p.W + w;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.tap && !p.tap_prerelu && in_img) {
+          float* tp = p.tap + (((int64_t)n * p.Cout + ch0) * p.H + h) * p.W + w;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+        if (EPI == AST_EPI_POOL2) {
+          // 2x2 max: partner along w is lane^1, along h is lane^16 (tile rows are 16 wide).
+          // max commutes with the (monotonic) bf16 rounding, so pool the packed values.
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+            uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+            a = __hmax2_nan(a, *reinterpret_cast<__nv_bfloat162*>(&o1));
+            uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
+            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, 16);
+            a = __hmax2_nan(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
+            pk[i] = *reinterpret_cast<uint32_t*>(&a);
+          }
+        }
+        if (p.out) {
+          for (int ri = 0; ri < nr; ++ri) {
+            for (int ci = 0; ci < nc; ++ci) {
+              __nv_bfloat16* o = p.out +
+                  (((int64_t)n * (p.Ho + 2) + (rows[ri] + 1)) * (p.Wo + 2) + (cols[ci] + 1)) * p.Cout + ch0;
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+              o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              o4[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+              o4[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
+                     int sm_count, cudaStream_t s) {
+  using C = Cfg<BN>;
+  auto kern = conv3x3_tc_kernel<BN, EPI>;
+  static bool attr_done = false;  // per (BN, EPI) instantiation
+  if (!attr_done) {
+    AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  kern<<<grid, kConvThreads, C::SMEM_BYTES, s>>>(tmA, tmB, p);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BN>
+static int launch_tc_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const ConvParams& p, int sm_count, cudaStream_t s) {
+  switch (epi) {
+    case AST_EPI_PLAIN: return launch_tc<BN, AST_EPI_PLAIN>(tmA, tmB, p, sm_count, s);
+    case AST_EPI_POOL2: return launch_tc<BN, AST_EPI_POOL2>(tmA, tmB, p, sm_count, s);
+    case AST_EPI_UP2: return launch_tc<BN, AST_EPI_UP2>(tmA, tmB, p, sm_count, s);
+  }
+  return AST_E_BADARG;
+}
+
+bool tc_supported(const ast_conv_desc* d) {
+  return d->Cin % 64 == 0 && d->Cout % 64 == 0 && d->H >= 2 && d->W >= 2;
+}
+
+int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const float* bias, void* out,
+               float* tap, cudaStream_t s) {
+  if (!tc_supported(d)) return AST_E_SHAPE;
+  if (!aligned16(in) || !aligned16(wpk) || (out && !aligned16(out)) || (bias && !aligned16(bias)))
+    return AST_E_ALIGN;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    AST_CUDA(cudaGetDevice(&dev));
+    AST_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  ConvParams p = {};
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->H : d->H);
+  p.Wo = d->epilogue == AST_EPI_POOL2 ? d->W / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->W : d->W);
+  p.relu = d->relu; p.halo = d->halo; p.tap_prerelu = d->tap_prerelu;
+  p.tiles_w = (d->W + TILE_W - 1) / TILE_W;
+  p.tiles_h = (d->H + TILE_H - 1) / TILE_H;
+  p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.tap = tap;
+
+  // N-block: the widest that still gives every SM a tile (a wide N amortises the A-operand
+  // shared-memory reads of each MMA); narrow blocks only when the problem is small.
+  const int64_t sp_tiles = (int64_t)d->N * p.tiles_h * p.tiles_w;
+  int BN = 64;
+  if (d->Cout % 256 == 0 && sp_tiles * (d->Cout / 256) >= sm_count) BN = 256;
+  else if (d->Cout % 128 == 0 && sp_tiles * (d->Cout / 128) >= sm_count) BN = 128;
+  if (d->impl >= 64 && d->impl <= 256 && d->Cout % d->impl == 0) BN = d->impl;  // tuning override
+  if (BN != 64 && BN != 128 && BN != 256) return AST_E_SHAPE;
+  p.n_blocks = d->Cout / BN;
+  const int64_t nt = sp_tiles * p.n_blocks;
+  if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
+  p.num_tiles = (int)nt;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W + 2, (uint64_t)d->H + 2, (uint64_t)d->N};
+    const uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)(d->W + 2) * d->Cin * 2,
+                             (uint64_t)(d->H + 2) * (d->W + 2) * d->Cin * 2};
+    const uint32_t box[4] = {KBLK, TILE_W, TILE_H, 1};
+    int r = encode_bf16_map(&tmA, in, 4, dims, str, box);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, 9};
+    const uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout * d->Cin * 2};
+    const uint32_t box[3] = {KBLK, (uint32_t)BN, 1};
+    int r = encode_bf16_map(&tmB, wpk, 3, dims, str, box);
+    if (r) return r;
+  }
+  switch (BN) {
+    case 256: return launch_tc_epi<256>(d->epilogue, tmA, tmB, p, sm_count, s);
+    case 128: return launch_tc_epi<128>(d->epilogue, tmA, tmB, p, sm_count, s);
+    default: return launch_tc_epi<64>(d->epilogue, tmA, tmB, p, sm_count, s);
+  }
+}
+
+}  // namespace tc
+}  // namespace ast

@@ -1,0 +1,249 @@
+// K3: loss kernels -- Huber (content loss) and Gram matrix, forward + backward.
+//
+// Reference arithmetic replaced (paths relative to /root/reference):
+//   compute_content_loss  losses.py:124-126   F.huber_loss(inp, tgt): delta 1, mean
+//   gram_matrix           losses.py:105-109   bmm(X, X^T) / (C*H*W)
+//   compute_style_loss    losses.py:128-139   composes the two with channel_stats (adain.cu)
+#include "common.cuh"
+
+namespace ast {
+
+constexpr int kLThreads = 256;
+constexpr int kHuberMaxBlocks = 1024;
+
+__device__ __forceinline__ float huber1(float d) {
+  float a = fabsf(d);
+  return a < 1.f ? 0.5f * d * d : a - 0.5f;
+}
+
+// stage 1: per-block partial sums (fixed assignment -> deterministic)
+__global__ void __launch_bounds__(kLThreads) huber_partial_kernel(const float* __restrict__ inp,
+                                                                  const float* __restrict__ tgt,
+                                                                  float* __restrict__ partial,
+                                                                  int64_t n) {
+  __shared__ float s_red[kLThreads / 32];
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * kLThreads;
+  const bool vec = aligned16(inp) && aligned16(tgt);
+  const int64_t nvec = vec ? n / 4 : 0;
+  for (int64_t i = (int64_t)blockIdx.x * kLThreads + threadIdx.x; i < nvec; i += stride) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(inp) + i);
+    float4 b = __ldg(reinterpret_cast<const float4*>(tgt) + i);
+    acc += huber1(a.x - b.x) + huber1(a.y - b.y) + huber1(a.z - b.z) + huber1(a.w - b.w);
+  }
+  for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * kLThreads + threadIdx.x; i < n; i += stride)
+    acc += huber1(inp[i] - tgt[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int w = 0; w < kLThreads / 32; ++w) r += s_red[w];
+    partial[blockIdx.x] = r;
+  }
+}
+
+// stage 2: one block folds the partials in a fixed order
+__global__ void __launch_bounds__(kLThreads) huber_final_kernel(const float* __restrict__ partial,
+                                                                int nblocks, float* loss,
+                                                                float scale_over_n) {
+  __shared__ float s_red[kLThreads / 32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += kLThreads) acc += partial[i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int w = 0; w < kLThreads / 32; ++w) r += s_red[w];
+    loss[0] = r * scale_over_n;
+  }
+}
+
+__global__ void __launch_bounds__(kLThreads) huber_bwd_kernel(const float* __restrict__ inp,
+                                                              const float* __restrict__ tgt,
+                                                              const float* __restrict__ g_loss,
+                                                              float* __restrict__ g_inp, int64_t n,
+                                                              float scale_over_n) {
+  const float g = g_loss[0] * scale_over_n;
+  const int64_t stride = (int64_t)gridDim.x * kLThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kLThreads + threadIdx.x; i < n; i += stride) {
+    float d = inp[i] - tgt[i];
+    g_inp[i] = g * fminf(fmaxf(d, -1.f), 1.f);
+  }
+}
+
+// ---- Gram: G[b] = X X^T / (C*HW) ---------------------------------------------------------------
+// 64x64 output tile per CTA, 4x4 per thread, K chunks of 32 through shared memory, split-K over HW
+// with fp32 atomics into a pre-zeroed G.  Only tiles with tj >= ti are computed; the mirror is
+// written in the same pass.
+constexpr int GT = 64, GK = 32;
+
+__global__ void __launch_bounds__(256) gram_fwd_kernel(const float* __restrict__ x,
+                                                       float* __restrict__ g, int C, int64_t HW,
+                                                       int64_t k_per_split, float scale) {
+  __shared__ float sA[GK][GT + 4];
+  __shared__ float sB[GK][GT + 4];
+  const int b = blockIdx.z;
+  const int tiles = (C + GT - 1) / GT;
+  // decode upper-triangular tile index
+  int t = blockIdx.x, ti = 0;
+  while (t >= tiles - ti) { t -= tiles - ti; ++ti; }
+  const int tj = ti + t;
+  const int64_t k0 = (int64_t)blockIdx.y * k_per_split;
+  const int64_t k1 = (k0 + k_per_split < HW) ? k0 + k_per_split : HW;
+  const float* xb = x + (int64_t)b * C * HW;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int64_t kk = k0; kk < k1; kk += GK) {
+    // 64 rows x 32 k per operand; 256 threads -> 8 elements each
+    for (int e = threadIdx.x; e < GT * GK; e += 256) {
+      int r = e / GK, k = e % GK;
+      int64_t kg = kk + k;
+      int ra = ti * GT + r, rb = tj * GT + r;
+      sA[k][r] = (ra < C && kg < k1) ? xb[(int64_t)ra * HW + kg] : 0.f;
+      sB[k][r] = (rb < C && kg < k1) ? xb[(int64_t)rb * HW + kg] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; bb[i] = sB[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* gb = g + (int64_t)b * C * C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = ti * GT + ty * 4 + i, c = tj * GT + tx * 4 + j;
+      if (r < C && c < C) {
+        float v = acc[i][j] * scale;
+        atomicAdd(&gb[(int64_t)r * C + c], v);
+        if (ti != tj) atomicAdd(&gb[(int64_t)c * C + r], v);
+      }
+    }
+}
+
+// gx[b] = S X * scale, S = gG + gG^T (C x C), X (C x HW): tile 64 rows x 64 cols of HW per CTA.
+__global__ void __launch_bounds__(256) gram_bwd_kernel(const float* __restrict__ x,
+                                                       const float* __restrict__ gg,
+                                                       float* __restrict__ gx, int C, int64_t HW,
+                                                       float scale) {
+  __shared__ float sS[GK][GT + 4];  // S^T chunk: [k][row]
+  __shared__ float sX[GK][GT + 4];  // X chunk:   [k][col]
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * GT;
+  const int64_t c0 = (int64_t)blockIdx.x * GT;
+  const float* xb = x + (int64_t)b * C * HW;
+  const float* gb = gg + (int64_t)b * C * C;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int kk = 0; kk < C; kk += GK) {
+    for (int e = threadIdx.x; e < GT * GK; e += 256) {
+      int k = e / GT, r = e % GT;  // S[r0+r][kk+k] = gG[r][k] + gG[k][r]
+      int rg = r0 + r, kg = kk + k;
+      sS[k][r] = (rg < C && kg < C) ? gb[(int64_t)rg * C + kg] + gb[(int64_t)kg * C + rg] : 0.f;
+      int64_t cg = c0 + r;  // reuse r as column index: coalesced along HW
+      sX[k][r] = (kg < C && cg < HW) ? xb[(int64_t)kg * HW + cg] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sS[k][ty * 4 + i]; bb[i] = sX[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* ob = gx + (int64_t)b * C * HW;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = r0 + ty * 4 + i;
+      int64_t c = c0 + tx * 4 + j;
+      if (r < C && c < HW) ob[(int64_t)r * HW + c] = acc[i][j] * scale;
+    }
+}
+
+}  // namespace ast
+
+using namespace ast;
+
+static int huber_blocks(int64_t n) {
+  int64_t b = (n + (int64_t)kLThreads * 16 - 1) / ((int64_t)kLThreads * 16);
+  if (b < 1) b = 1;
+  if (b > kHuberMaxBlocks) b = kHuberMaxBlocks;
+  return (int)b;
+}
+
+extern "C" size_t ast_huber_ws_bytes(int64_t) { return kHuberMaxBlocks * sizeof(float); }
+
+extern "C" int ast_huber_fwd(const float* inp, const float* tgt, float* loss, int64_t n,
+                             float scale, void* ws, size_t ws_bytes, void* stream) {
+  if (!inp || !tgt || !loss || !ws || n <= 0) return AST_E_BADARG;
+  if (ws_bytes < kHuberMaxBlocks * sizeof(float)) return AST_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = huber_blocks(n);
+  huber_partial_kernel<<<nb, kLThreads, 0, s>>>(inp, tgt, (float*)ws, n);
+  AST_CHECK_LAUNCH();
+  huber_final_kernel<<<1, kLThreads, 0, s>>>((const float*)ws, nb, loss, scale / (float)n);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_huber_bwd(const float* inp, const float* tgt, const float* g_loss, float* g_inp,
+                             int64_t n, float scale, void* stream) {
+  if (!inp || !tgt || !g_loss || !g_inp || n <= 0) return AST_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t nb = (n + kLThreads * 4 - 1) / (kLThreads * 4);
+  if (nb > 148 * 16) nb = 148 * 16;
+  huber_bwd_kernel<<<(unsigned)nb, kLThreads, 0, s>>>(inp, tgt, g_loss, g_inp, n, scale / (float)n);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_gram_fwd(const float* x, float* g, int B, int C, int64_t HW, void* stream) {
+  if (!x || !g || B <= 0 || C <= 0 || HW <= 0) return AST_E_BADARG;
+  if (B > 65535) return AST_E_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  AST_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)B * C * C, s));
+  const int tiles = (C + GT - 1) / GT;
+  const int ntri = tiles * (tiles + 1) / 2;
+  // split K so that the grid fills the machine (~4 CTAs per SM), chunks multiple of GK
+  int64_t want = (4 * 148 + (int64_t)ntri * B - 1) / ((int64_t)ntri * B);
+  int64_t chunks = (HW + GK - 1) / GK;
+  if (want > chunks) want = chunks;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  int64_t k_per_split = ((chunks + want - 1) / want) * GK;
+  int splits = (int)((HW + k_per_split - 1) / k_per_split);
+  dim3 grid(ntri, splits, B);
+  gram_fwd_kernel<<<grid, 256, 0, s>>>(x, g, C, HW, k_per_split, 1.f / ((float)C * (float)HW));
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_gram_bwd(const float* x, const float* gg, float* gx, int B, int C, int64_t HW,
+                            void* stream) {
+  if (!x || !gg || !gx || B <= 0 || C <= 0 || HW <= 0) return AST_E_BADARG;
+  if (B > 65535 || (C + GT - 1) / GT > 65535) return AST_E_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)((HW + GT - 1) / GT), (C + GT - 1) / GT, B);
+  gram_bwd_kernel<<<grid, 256, 0, s>>>(x, gg, gx, C, HW, 1.f / ((float)C * (float)HW));
+  AST_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,289 @@
+// Native-layout (bf16 [N][H+2][W+2][C], one-pixel halo) helpers:
+//   * converters to / from the reference's NCHW fp32 tensors (the drop-in boundary),
+//   * K1n: AdaIN (models.py:43-51 + alpha blend models.py:471) evaluated directly on the native
+//     layout between the encoder's last conv and the decoder's first, same fp32 Welford / Chan
+//     arithmetic as K1 (adain.cu).
+#include "common.cuh"
+
+namespace ast {
+
+__device__ __forceinline__ int halo_targets(int x, int X, bool reflect, int (&t)[3]) {
+  int n = 0;
+  t[n++] = x;
+  if (reflect) {
+    if (x == 1) t[n++] = -1;
+    if (x == X - 2) t[n++] = X;
+  }
+  return n;
+}
+
+// ---- NCHW fp32 -> native ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_native_kernel(const float* __restrict__ src,
+                                                             __nv_bfloat16* __restrict__ dst, int N,
+                                                             int C, int H, int W, int reflect) {
+  __shared__ float tile[32][33];  // [c][w]
+  const int ctiles = (C + 31) / 32;
+  const int n = blockIdx.z / ctiles, c0 = (blockIdx.z % ctiles) * 32;
+  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < 32; c += 8) {
+    const int cc = c0 + c, ww = w0 + tx;
+    tile[c][tx] = (cc < C && ww < W) ? src[(((int64_t)n * C + cc) * H + h) * W + ww] : 0.f;
+  }
+  __syncthreads();
+  int rows[3];
+  const int nr = halo_targets(h, H, reflect != 0, rows);
+  for (int wl = ty; wl < 32; wl += 8) {
+    const int ww = w0 + wl, cc = c0 + tx;
+    if (ww >= W || cc >= C) continue;
+    const __nv_bfloat16 v = __float2bfloat16_rn(tile[tx][wl]);
+    int cols[3];
+    const int nc = halo_targets(ww, W, reflect != 0, cols);
+    for (int ri = 0; ri < nr; ++ri)
+      for (int ci = 0; ci < nc; ++ci)
+        dst[(((int64_t)n * (H + 2) + rows[ri] + 1) * (W + 2) + cols[ci] + 1) * C + cc] = v;
+  }
+}
+
+// ---- native -> NCHW fp32 ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) native_to_nchw_kernel(const __nv_bfloat16* __restrict__ src,
+                                                             float* __restrict__ dst, int N, int C,
+                                                             int H, int W) {
+  __shared__ float tile[32][33];  // [w][c]
+  const int ctiles = (C + 31) / 32;
+  const int n = blockIdx.z / ctiles, c0 = (blockIdx.z % ctiles) * 32;
+  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int wl = ty; wl < 32; wl += 8) {
+    const int ww = w0 + wl, cc = c0 + tx;
+    tile[wl][tx] = (ww < W && cc < C)
+                       ? __bfloat162float(src[(((int64_t)n * (H + 2) + h + 1) * (W + 2) + ww + 1) * C + cc])
+                       : 0.f;
+  }
+  __syncthreads();
+  for (int c = ty; c < 32; c += 8) {
+    const int cc = c0 + c, ww = w0 + tx;
+    if (cc < C && ww < W) dst[(((int64_t)n * C + cc) * H + h) * W + ww] = tile[tx][c];
+  }
+}
+
+// ---- K1n: AdaIN on the native layout -------------------------------------------------------------
+constexpr int kNThreads = 256;
+constexpr int kMaxChunks = 32;
+
+// Stage 1: per (map q, image n, pixel chunk) Welford moments of every channel.
+// grid = (chunks, N, 1 + K); thread -> 8 consecutive channels of one pixel group.
+struct NativeStatArgs {
+  const __nv_bfloat16* maps[1 + AST_MAX_STYLES];
+  int H[1 + AST_MAX_STYLES], W[1 + AST_MAX_STYLES];
+  float* partial;  // [(1+K)][N][chunks][C][3]
+  int N, C, chunks;
+};
+
+__global__ void __launch_bounds__(kNThreads) native_stats_kernel(const NativeStatArgs a) {
+  extern __shared__ float s_part[];  // [groups][C][3]
+  const int q = blockIdx.z, n = blockIdx.y, chunk = blockIdx.x;
+  const int cvecs = a.C / 8;
+  const int groups = kNThreads / cvecs;
+  const int g = threadIdx.x / cvecs, v = threadIdx.x % cvecs;
+  const int H = a.H[q], W = a.W[q];
+  const int64_t npix = (int64_t)H * W;
+  const int64_t per = (npix + a.chunks - 1) / a.chunks;
+  const int64_t p0 = chunk * per, p1 = (p0 + per < npix) ? p0 + per : npix;
+  WelfordLanes<8> wl;
+  wl.init();
+  if (g < groups) {
+    const __nv_bfloat16* base = a.maps[q] + (int64_t)n * (H + 2) * (W + 2) * a.C + v * 8;
+    for (int64_t p = p0 + g; p < p1; p += groups) {
+      const int h = (int)(p / W), w = (int)(p % W);
+      const uint4 u = ld_stream_u4(base + ((int64_t)(h + 1) * (W + 2) + (w + 1)) * a.C);
+      float x[8];
+      Vec16<true>::unpack(u, x);
+      wl.push(x);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float* sp = s_part + ((int64_t)g * a.C + v * 8 + j) * 3;
+      sp[0] = wl.n; sp[1] = wl.mean[j]; sp[2] = wl.m2[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.C; c += kNThreads) {
+    Moments m{s_part[c * 3], s_part[c * 3 + 1], s_part[c * 3 + 2]};
+    for (int gg = 1; gg < groups; ++gg) {
+      const float* sp = s_part + ((int64_t)gg * a.C + c) * 3;
+      m = moments_merge(m, Moments{sp[0], sp[1], sp[2]});
+    }
+    float* o = a.partial + ((((int64_t)q * a.N + n) * a.chunks + chunk) * a.C + c) * 3;
+    o[0] = m.n; o[1] = m.mean; o[2] = m.m2;
+  }
+}
+
+// Stage 2: merge chunks, build the per-(n,c) affine (mu_c, 1/sigma_c, A, B).
+struct NativeCoefArgs {
+  const float* partial;
+  float4* coef;  // [N][C]
+  float style_w[AST_MAX_STYLES];
+  int N, C, chunks, K;
+  float eps;
+  unsigned flags;
+};
+
+__global__ void __launch_bounds__(kNThreads) native_coef_kernel(const NativeCoefArgs a) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * kNThreads + threadIdx.x;
+  if (c >= a.C) return;
+  float mu = 0.f, rsig = 0.f, A = 0.f, B = 0.f;
+  for (int q = 0; q <= a.K; ++q) {
+    Moments m{0.f, 0.f, 0.f};
+    for (int ch = 0; ch < a.chunks; ++ch) {
+      const float* pp = a.partial + ((((int64_t)q * a.N + n) * a.chunks + ch) * a.C + c) * 3;
+      m = moments_merge(m, Moments{pp[0], pp[1], pp[2]});
+    }
+    const float denom = (a.flags & AST_F_BIASED) ? m.n : m.n - 1.f;
+    const float sig = sqrtf(m.m2 / denom + a.eps);
+    if (q == 0) {
+      mu = m.mean;
+      rsig = 1.f / sig;
+    } else if (a.flags & AST_F_CANONICAL) {
+      A = fmaf(a.style_w[q - 1], sig, A);
+      B = fmaf(a.style_w[q - 1], m.mean, B);
+    } else {  // models.py:44: style_std := mean(style), style_mean := std(style)
+      A = fmaf(a.style_w[q - 1], m.mean, A);
+      B = fmaf(a.style_w[q - 1], sig, B);
+    }
+  }
+  a.coef[(int64_t)n * a.C + c] = make_float4(mu, rsig, A, B);
+}
+
+// Stage 3: apply + alpha blend, write interior and (optionally) the reflection halo.
+__global__ void __launch_bounds__(kNThreads)
+native_apply_kernel(const __nv_bfloat16* __restrict__ content, const float4* __restrict__ coef,
+                    __nv_bfloat16* __restrict__ out, int N, int C, int H, int W, float alpha,
+                    int reflect) {
+  const int cvecs = C / 8;
+  const int64_t total = (int64_t)N * H * W * cvecs;
+  const bool blend = alpha != 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * kNThreads + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * kNThreads) {
+    const int v = (int)(i % cvecs);
+    int64_t r = i / cvecs;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    const int64_t img = (int64_t)n * (H + 2) * (W + 2);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(
+        content + ((img + (int64_t)(h + 1) * (W + 2) + (w + 1)) * C + v * 8)));
+    float x[8];
+    Vec16<true>::unpack(u, x);
+    const float4* cf = coef + (int64_t)n * C + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 k = __ldg(cf + j);
+      const float t = (x[j] - k.x) * k.y;   // models.py:47
+      float y = fmaf(t, k.z, k.w);          // models.py:50
+      if (blend) y = fmaf(alpha, y, (1.f - alpha) * x[j]);  // models.py:471
+      x[j] = y;
+    }
+    const uint4 o = Vec16<true>::pack(x);
+    int rows[3], cols[3];
+    const int nr = halo_targets(h, H, reflect != 0, rows);
+    const int nc = halo_targets(w, W, reflect != 0, cols);
+    for (int ri = 0; ri < nr; ++ri)
+      for (int ci = 0; ci < nc; ++ci)
+        *reinterpret_cast<uint4*>(out + ((img + (int64_t)(rows[ri] + 1) * (W + 2) + (cols[ci] + 1)) * C + v * 8)) = o;
+  }
+}
+
+static int native_chunks(int N, int64_t hw) {
+  int64_t c = (2 * 148 + N - 1) / N;
+  if (c > kMaxChunks) c = kMaxChunks;
+  if (c > hw / 32) c = hw / 32;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+}  // namespace ast
+
+using namespace ast;
+
+extern "C" int ast_nchw_to_native(const float* nchw, void* native, int N, int C, int H, int W,
+                                  int halo, void* stream) {
+  if (!nchw || !native || N <= 0 || C <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  if (halo == AST_HALO_REFLECT && (H < 2 || W < 2)) return AST_E_SHAPE;
+  const int ctiles = (C + 31) / 32;
+  if ((int64_t)N * ctiles > 65535 || H > 65535) return AST_E_SHAPE;
+  dim3 grid((W + 31) / 32, H, N * ctiles);
+  nchw_to_native_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      nchw, reinterpret_cast<__nv_bfloat16*>(native), N, C, H, W, halo == AST_HALO_REFLECT);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_native_to_nchw(const void* native, float* nchw, int N, int C, int H, int W,
+                                  void* stream) {
+  if (!nchw || !native || N <= 0 || C <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  const int ctiles = (C + 31) / 32;
+  if ((int64_t)N * ctiles > 65535 || H > 65535) return AST_E_SHAPE;
+  dim3 grid((W + 31) / 32, H, N * ctiles);
+  native_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(native), nchw, N, C, H, W);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" size_t ast_adain_native_ws_bytes(int N, int C, int K) {
+  if (N <= 0 || C <= 0 || K < 0) return 0;
+  return (size_t)(1 + K) * N * kMaxChunks * C * 3 * sizeof(float) + (size_t)N * C * sizeof(float4);
+}
+
+extern "C" int ast_adain_native_fwd(const void* content, const void* const* styles,
+                                    const float* style_w, int K, void* out, int N, int C, int H,
+                                    int W, int Hs, int Ws, float alpha, float eps, unsigned flags,
+                                    int halo, void* ws, size_t ws_bytes, void* stream) {
+  if (!content || !out || !ws || N <= 0 || C <= 0 || H <= 0 || W <= 0 || K < 1) return AST_E_BADARG;
+  if (!styles || !style_w || Hs <= 0 || Ws <= 0) return AST_E_BADARG;
+  if (K > AST_MAX_STYLES) return AST_E_TOOMANY;
+  if (C % 8 != 0 || C / 8 > kNThreads) return AST_E_SHAPE;
+  if (halo == AST_HALO_REFLECT && (H < 2 || W < 2)) return AST_E_SHAPE;
+  if (ws_bytes < ast_adain_native_ws_bytes(N, C, K)) return AST_E_WORKSPACE;
+  if (!aligned16(content) || !aligned16(out) || !aligned16(ws)) return AST_E_ALIGN;
+  if (N > 65535) return AST_E_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t hw_min = ((int64_t)H * W < (int64_t)Hs * Ws) ? (int64_t)H * W : (int64_t)Hs * Ws;
+  const int chunks = native_chunks(N, hw_min);
+
+  float* partial = reinterpret_cast<float*>(ws);
+  float4* coef = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) +
+                                           (size_t)(1 + K) * N * kMaxChunks * C * 3 * sizeof(float));
+  NativeStatArgs sa = {};
+  sa.maps[0] = reinterpret_cast<const __nv_bfloat16*>(content);
+  sa.H[0] = H; sa.W[0] = W;
+  for (int k = 0; k < K; ++k) {
+    if (!styles[k] || !aligned16(styles[k])) return AST_E_BADARG;
+    sa.maps[1 + k] = reinterpret_cast<const __nv_bfloat16*>(styles[k]);
+    sa.H[1 + k] = Hs; sa.W[1 + k] = Ws;
+  }
+  sa.partial = partial; sa.N = N; sa.C = C; sa.chunks = chunks;
+  const int groups = kNThreads / (C / 8);
+  const size_t smem = (size_t)groups * C * 3 * sizeof(float);
+  if (smem > 48 * 1024) return AST_E_SHAPE;
+  native_stats_kernel<<<dim3(chunks, N, 1 + K), kNThreads, smem, s>>>(sa);
+  AST_CHECK_LAUNCH();
+
+  NativeCoefArgs ca = {};
+  ca.partial = partial; ca.coef = coef; ca.N = N; ca.C = C; ca.chunks = chunks; ca.K = K;
+  ca.eps = eps; ca.flags = flags;
+  for (int k = 0; k < K; ++k) ca.style_w[k] = style_w[k];
+  native_coef_kernel<<<dim3((C + kNThreads - 1) / kNThreads, N), kNThreads, 0, s>>>(ca);
+  AST_CHECK_LAUNCH();
+
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  int64_t nb = (total + kNThreads - 1) / kNThreads;
+  if (nb > 148 * 16) nb = 148 * 16;
+  native_apply_kernel<<<(unsigned)nb, kNThreads, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(content), coef, reinterpret_cast<__nv_bfloat16*>(out), N,
+      C, H, W, alpha, halo == AST_HALO_REFLECT);
+  AST_CHECK_LAUNCH();
+  return 0;
+}

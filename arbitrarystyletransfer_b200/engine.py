@@ -1,0 +1,230 @@
+"""Native-layout execution of the classic VGG-19 relu4_1 -> AdaIN -> mirrored decoder path
+(reference pieces: models.py:186-240 encoder, models.py:43-51 AdaIN,
+models.py:471 alpha blend, models.py:598-628 decoder spec).
+
+Activations live between layers as bf16 [N][H+2][W+2][C] whose one-pixel halo already holds the
+padding of the consuming conv (zeros inside VGG, the reflection inside the decoder), so every
+3x3 tap of the tcgen05 implicit-GEMM kernel is one shifted TMA box.  fp32 NCHW exists only at the
+boundary: images in, image out, and optional feature taps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib as L
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # models.py:189
+IMAGENET_STD = (0.229, 0.224, 0.225)    # models.py:190
+
+# torchvision VGG-19 configuration 'E' (what models.py:192 instantiates), 'M' = MaxPool2d(2, 2)
+VGG19_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M",
+             512, 512, 512, 512, "M", 512, 512, 512, 512, "M")
+# (cin, cout, relu, upsample_after) of the 9 decoder convs, models.py:598-628 / conf.py:9
+DECODER_SPEC = ((512, 256, True, True), (256, 256, True, False), (256, 256, True, False),
+                (256, 256, True, False), (256, 128, True, True), (128, 128, True, False),
+                (128, 64, True, True), (64, 64, True, False), (64, 3, False, False))
+
+
+def vgg_layer_plan(n_convs: int):
+    """[(cin, cout, pool_after)] for the first ``n_convs`` VGG-19 convs."""
+    plan, cin = [], 3
+    cfg = list(VGG19_CFG)
+    i = 0
+    while i < len(cfg) and len(plan) < n_convs:
+        v = cfg[i]
+        if v != "M":
+            pool = i + 1 < len(cfg) and cfg[i + 1] == "M"
+            plan.append((cin, v, pool))
+            cin = v
+        i += 1
+    return plan
+
+
+def native_empty(N, H, W, Cc, device, zero_halo: bool):
+    """bf16 [N][H+2][W+2][C]; ``zero_halo`` buffers are zero-filled once and only ever written in
+    their interior, so the halo keeps VGG's zero padding."""
+    shape = (N, H + 2, W + 2, Cc)
+    if zero_halo:
+        return torch.zeros(shape, device=device, dtype=torch.bfloat16)
+    return torch.empty(shape, device=device, dtype=torch.bfloat16)
+
+
+def pack_conv_weight(w: torch.Tensor, flip: bool = False) -> torch.Tensor:
+    """OIHW fp32 -> bf16 [9][Cout][Cin] (or the data-gradient form when ``flip``)."""
+    lib = L.load()
+    L.require_cuda(w)
+    w = w.detach().float().contiguous()
+    co, ci = w.shape[:2]
+    out = torch.empty((9, ci, co) if flip else (9, co, ci), device=w.device, dtype=torch.bfloat16)
+    L.check(lib.ast_pack_conv_weight(w.data_ptr(), out.data_ptr(), co, ci, int(flip),
+                                     L.stream_ptr(w.device)), "ast_pack_conv_weight")
+    return out
+
+
+def conv3x3(x_native: torch.Tensor, wpk: torch.Tensor, bias, out_native, *, N, H, W, cin, cout,
+            relu=True, epilogue=L.EPI_PLAIN, halo=L.HALO_KEEP, impl=L.CONV_AUTO, tap=None,
+            tap_prerelu=True):
+    lib = L.load()
+    d = L.ConvDesc(N, H, W, cin, cout, int(relu), epilogue, halo, impl, int(tap_prerelu))
+    L.check(lib.ast_conv3x3_fwd(C.byref(d), x_native.data_ptr(), wpk.data_ptr(), L.ptr(bias),
+                                L.ptr(out_native), L.ptr(tap), L.stream_ptr(x_native.device)),
+            "ast_conv3x3_fwd")
+    return out_native
+
+
+def nchw_to_native(x: torch.Tensor, reflect: bool, out=None) -> torch.Tensor:
+    lib = L.load()
+    L.require_cuda(x)
+    x = x.float().contiguous()
+    N, Cc, H, W = x.shape
+    if out is None:
+        out = native_empty(N, H, W, Cc, x.device, zero_halo=not reflect)
+    L.check(lib.ast_nchw_to_native(x.data_ptr(), out.data_ptr(), N, Cc, H, W,
+                                   L.HALO_REFLECT if reflect else L.HALO_KEEP,
+                                   L.stream_ptr(x.device)), "ast_nchw_to_native")
+    return out
+
+
+def native_to_nchw(x_native: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    N, Hp, Wp, Cc = x_native.shape
+    out = torch.empty(N, Cc, Hp - 2, Wp - 2, device=x_native.device, dtype=torch.float32)
+    L.check(lib.ast_native_to_nchw(x_native.data_ptr(), out.data_ptr(), N, Cc, Hp - 2, Wp - 2,
+                                   L.stream_ptr(x_native.device)), "ast_native_to_nchw")
+    return out
+
+
+class _Buffers:
+    """Shape-keyed cache of activation buffers (torch's caching allocator owns the memory)."""
+
+    def __init__(self):
+        self._b = {}
+
+    def get(self, key, N, H, W, Cc, device, zero_halo):
+        k = (key, N, H, W, Cc, str(device), zero_halo)
+        t = self._b.get(k)
+        if t is None:
+            t = native_empty(N, H, W, Cc, device, zero_halo)
+            self._b[k] = t
+        return t
+
+    def clear(self):
+        self._b.clear()
+
+
+class StyleTransferEngine:
+    """Forward engine for configs 1 / 4 / 5: images (N,3,H,W) fp32 in [0,1] -> stylised images.
+
+    ``vgg_w/vgg_b``: the first 9 VGG-19 conv weights / biases (OIHW fp32) -> relu4_1;
+    ``dec_w/dec_b``: the 9 classic-decoder convs.  Weights are packed to bf16 [9][Cout][Cin] once.
+    """
+
+    def __init__(self, vgg_w: Sequence[torch.Tensor], vgg_b, dec_w, dec_b, device="cuda",
+                 conv_impl: int = L.CONV_AUTO):
+        L.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.AstError("StyleTransferEngine needs a CUDA device (no CPU fallback)")
+        self.impl = conv_impl
+        self.plan = vgg_layer_plan(9)
+        dev = self.device
+        self.vgg_w0 = vgg_w[0].detach().to(dev, torch.float32).contiguous()
+        self.vgg_b = [b.detach().to(dev, torch.float32).contiguous() for b in vgg_b[:9]]
+        self.vgg_wpk = [None] + [pack_conv_weight(w.to(dev)) for w in vgg_w[1:9]]
+        self.dec_b = [b.detach().to(dev, torch.float32).contiguous() for b in dec_b]
+        self.dec_wpk = [pack_conv_weight(w.to(dev)) for w in dec_w[:8]] + [None]
+        self.dec_w_last = dec_w[8].detach().to(dev, torch.float32).contiguous()
+        self._mean = L.float_array(IMAGENET_MEAN)
+        self._std = L.float_array(IMAGENET_STD)
+        self.buf = _Buffers()
+        self._ws = None
+
+    # ---- encoder: models.py:230-240 with content_layers=['relu_9'] ------------------------------
+    def encode(self, img: torch.Tensor, key: str = "c") -> torch.Tensor:
+        """(N,3,H,W) fp32 -> relu4_1 in native layout bf16 [N][H/8+2][W/8+2][512] (zero halo)."""
+        lib = L.load()
+        L.require_cuda(img)
+        img = img.float().contiguous()
+        N, c3, H, W = img.shape
+        if c3 != 3:
+            raise L.AstError("images must have 3 channels")
+        dev = img.device
+        st = L.stream_ptr(dev)
+        x = self.buf.get("enc0", N, H, W, 64, dev, True)
+        L.check(lib.ast_conv3x3_first(img.data_ptr(), self.vgg_w0.data_ptr(),
+                                      self.vgg_b[0].data_ptr(), self._mean, self._std,
+                                      x.data_ptr(), None, 1, N, H, W, 64, st), "ast_conv3x3_first")
+        h, w = H, W
+        for i in range(1, 9):
+            cin, cout, pool = self.plan[i]
+            ho, wo = (h // 2, w // 2) if pool else (h, w)
+            last = i == 8
+            y = self.buf.get(f"enc{i}" + (key if last else ""), N, ho, wo, cout, dev, True)
+            conv3x3(x, self.vgg_wpk[i], self.vgg_b[i], y, N=N, H=h, W=w, cin=cin, cout=cout,
+                    relu=True, epilogue=L.EPI_POOL2 if pool else L.EPI_PLAIN, halo=L.HALO_KEEP,
+                    impl=self.impl)
+            x, h, w = y, ho, wo
+        return x
+
+    # ---- AdaIN on the native layout ---------------------------------------------------------------
+    def adain(self, fc: torch.Tensor, fs: Sequence[torch.Tensor], weights, alpha=1.0,
+              canonical=False) -> torch.Tensor:
+        lib = L.load()
+        N, Hp, Wp, Cc = fc.shape
+        K = len(fs)
+        Hs, Ws = fs[0].shape[1] - 2, fs[0].shape[2] - 2
+        wsb = lib.ast_adain_native_ws_bytes(N, Cc, K)
+        if self._ws is None or self._ws.numel() < wsb or self._ws.device != fc.device:
+            self._ws = torch.empty(wsb, device=fc.device, dtype=torch.uint8)
+        out = self.buf.get("adain", N, Hp - 2, Wp - 2, Cc, fc.device, False)
+        sp = (C.c_void_p * K)(*[s.data_ptr() for s in fs])
+        L.check(lib.ast_adain_native_fwd(fc.data_ptr(), sp, L.float_array(weights), K,
+                                         out.data_ptr(), N, Cc, Hp - 2, Wp - 2, Hs, Ws,
+                                         float(alpha), 0.0, L.F_CANONICAL if canonical else 0,
+                                         L.HALO_REFLECT, self._ws.data_ptr(), self._ws.numel(),
+                                         L.stream_ptr(fc.device)), "ast_adain_native_fwd")
+        return out
+
+    # ---- decoder: models.py:598-628 ------------------------------------------------------------------
+    def decode(self, t: torch.Tensor, clamp01: bool = False, out: torch.Tensor | None = None):
+        """native bf16 [N][h+2][w+2][512] with reflection halo -> (N,3,8h,8w) fp32."""
+        lib = L.load()
+        N, hp, wp, _ = t.shape
+        h, w = hp - 2, wp - 2
+        dev = t.device
+        x = t
+        for i in range(8):
+            cin, cout, relu, up = DECODER_SPEC[i]
+            ho, wo = (2 * h, 2 * w) if up else (h, w)
+            y = self.buf.get(f"dec{i}", N, ho, wo, cout, dev, False)
+            conv3x3(x, self.dec_wpk[i], self.dec_b[i], y, N=N, H=h, W=w, cin=cin, cout=cout,
+                    relu=relu, epilogue=L.EPI_UP2 if up else L.EPI_PLAIN, halo=L.HALO_REFLECT,
+                    impl=self.impl)
+            x, h, w = y, ho, wo
+        if out is None:
+            out = torch.empty(N, 3, h, w, device=dev, dtype=torch.float32)
+        L.check(lib.ast_conv3x3_last(x.data_ptr(), self.dec_w_last.data_ptr(),
+                                     self.dec_b[8].data_ptr(), out.data_ptr(), N, h, w, 64, 3,
+                                     int(clamp01), L.stream_ptr(dev)), "ast_conv3x3_last")
+        return out
+
+    # ---- full path ------------------------------------------------------------------------------
+    def stylize(self, content: torch.Tensor, styles, alpha: float = 1.0, style_weights=None,
+                canonical: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+        """content (N,3,H,W); styles: tensor (N,3,Hs,Ws) or list of K such tensors."""
+        if isinstance(styles, torch.Tensor):
+            styles = [styles]
+        K = len(styles)
+        if style_weights is None:
+            style_weights = [1.0 / K] * K
+        fc = self.encode(content, "c")
+        fs = [self.encode(s, f"s{k}") for k, s in enumerate(styles)]
+        t = self.adain(fc, fs, style_weights, alpha, canonical)
+        return self.decode(t, out=out)
+
+    def launches_per_stylize(self, K: int = 1) -> int:
+        """Kernels of libast_b200 launched by one stylize() call (for bench.py's gpu_launches)."""
+        return (1 + K) * 9 + 3 + 9

@@ -1,0 +1,229 @@
+"""Thin functional layer over the C ABI: one Python function (or autograd.Function) per kernel
+family.  Tensors in and out are the reference's own convention -- NCHW, fp32, contiguous, CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _flags(t: torch.Tensor, canonical=False, biased=False) -> int:
+    f = 0
+    if canonical:
+        f |= L.F_CANONICAL
+    if biased:
+        f |= L.F_BIASED
+    if t.dtype == torch.bfloat16:
+        f |= L.F_BF16
+    elif t.dtype != torch.float32:
+        raise L.AstError(f"only fp32 / bf16 tensors are supported, got {t.dtype}")
+    return f
+
+
+# ------------------------------------------------------------------------------------------
+# K1: fused AdaIN                      reference: models.py:43-51 (+ :471 alpha blend)
+# ------------------------------------------------------------------------------------------
+def adain_forward(content: torch.Tensor, styles: Sequence[torch.Tensor],
+                  weights: Sequence[float] | None = None, alpha: float = 1.0,
+                  canonical: bool = False, eps: float = 0.0, out: torch.Tensor | None = None,
+                  return_stats: bool = False):
+    """out = alpha * ((c - mu_c)/sigma_c * A + B) + (1 - alpha) * c with
+    (A, B) = sum_k w_k (mu_s, sigma_s)  [reference, swapped as models.py:44]  or (sigma_s, mu_s)
+    [canonical].  One pass over HBM; statistics in fp32 (Welford / Chan)."""
+    lib = L.load()
+    if isinstance(styles, torch.Tensor):
+        styles = [styles]
+    K = len(styles)
+    if K < 1:
+        raise L.AstError("adain_forward needs at least one style map")
+    if K > L.MAX_STYLES:
+        raise L.AstError(f"at most {L.MAX_STYLES} style maps are supported, got {K}")
+    L.require_cuda(content, *styles)
+    if content.dim() != 4:
+        raise L.AstError("content_map must be 4-D (N, C, H, W)")
+    content = _c(content)
+    styles = [_c(s) for s in styles]
+    N, Cc, H, W = content.shape
+    for s in styles:
+        if s.dim() != 4 or s.shape[0] != N or s.shape[1] != Cc or s.dtype != content.dtype:
+            raise L.AstError("style maps must be (N, C, Hs, Ws) with the content's N, C and dtype")
+    if weights is None:
+        weights = [1.0 / K] * K
+    if len(weights) != K:
+        raise L.AstError("one interpolation weight per style map is required")
+    if out is None:
+        out = torch.empty_like(content)
+    stats = (torch.empty(N * Cc, 2 + 2 * K, device=content.device, dtype=torch.float32)
+             if return_stats else None)
+    sp = (C.c_void_p * K)(*[s.data_ptr() for s in styles])
+    shw = (C.c_int64 * K)(*[s.shape[2] * s.shape[3] for s in styles])
+    rc = lib.ast_adain_fwd(content.data_ptr(), sp, shw, L.float_array(weights), K, out.data_ptr(),
+                           L.ptr(stats), N, Cc, H * W, float(alpha), float(eps),
+                           _flags(content, canonical), L.stream_ptr(content.device))
+    L.check(rc, "ast_adain_fwd")
+    return (out, stats) if return_stats else out
+
+
+# ------------------------------------------------------------------------------------------
+# channel_stats                          reference: model_util.py:3-8, models.py:54-62
+# ------------------------------------------------------------------------------------------
+class _ChannelStats(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps, biased):
+        lib = L.load()
+        L.require_cuda(x)
+        x = _c(x)
+        N, Cc = x.shape[:2]
+        HW = x[0, 0].numel()
+        mean = torch.empty(N, Cc, device=x.device, dtype=torch.float32)
+        std = torch.empty(N, Cc, device=x.device, dtype=torch.float32)
+        fl = _flags(x, biased=biased)
+        L.check(lib.ast_channel_stats_fwd(x.data_ptr(), mean.data_ptr(), std.data_ptr(), N * Cc, HW,
+                                          float(eps), fl, L.stream_ptr(x.device)),
+                "ast_channel_stats_fwd")
+        ctx.save_for_backward(x, mean, std)
+        ctx.fl = fl
+        return mean, std
+
+    @staticmethod
+    def backward(ctx, g_mean, g_std):
+        lib = L.load()
+        x, mean, std = ctx.saved_tensors
+        N, Cc = x.shape[:2]
+        HW = x[0, 0].numel()
+        gx = torch.empty_like(x)
+        gm = _c(g_mean.float()) if g_mean is not None else None
+        gs = _c(g_std.float()) if g_std is not None else None
+        L.check(lib.ast_channel_stats_bwd(x.data_ptr(), mean.data_ptr(), std.data_ptr(), L.ptr(gm),
+                                          L.ptr(gs), gx.data_ptr(), N * Cc, HW, ctx.fl,
+                                          L.stream_ptr(x.device)), "ast_channel_stats_bwd")
+        return gx, None, None
+
+
+def channel_stats_flat(x: torch.Tensor, eps: float = 0.0, biased: bool = False):
+    """(mean, std) as (N, C) fp32 tensors; std = sqrt(var + eps), unbiased unless ``biased``."""
+    if x.dim() < 3:
+        raise L.AstError("channel statistics need a tensor of at least 3 dimensions")
+    return _ChannelStats.apply(x, eps, biased)
+
+
+# ------------------------------------------------------------------------------------------
+# mean_variance_norm                                          reference: models.py:64-68
+# ------------------------------------------------------------------------------------------
+class _MVN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        lib = L.load()
+        L.require_cuda(x)
+        x = _c(x)
+        N, Cc = x.shape[:2]
+        HW = x[0, 0].numel()
+        y = torch.empty_like(x)
+        stats = torch.empty(N * Cc, 2, device=x.device, dtype=torch.float32)
+        fl = _flags(x)
+        L.check(lib.ast_mvn_fwd(x.data_ptr(), y.data_ptr(), stats.data_ptr(), N * Cc, HW, float(eps),
+                                fl, L.stream_ptr(x.device)), "ast_mvn_fwd")
+        ctx.save_for_backward(x, stats)
+        ctx.fl = fl
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.load()
+        x, stats = ctx.saved_tensors
+        N, Cc = x.shape[:2]
+        HW = x[0, 0].numel()
+        gy = _c(gy.to(x.dtype))
+        gx = torch.empty_like(x)
+        L.check(lib.ast_mvn_bwd(x.data_ptr(), gy.data_ptr(), stats.data_ptr(), gx.data_ptr(), N * Cc,
+                                HW, ctx.fl, L.stream_ptr(x.device)), "ast_mvn_bwd")
+        return gx, None
+
+
+def mean_variance_norm(feat: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    return _MVN.apply(feat, eps)
+
+
+# ------------------------------------------------------------------------------------------
+# K3: Huber / Gram                                           reference: losses.py:105-139
+# ------------------------------------------------------------------------------------------
+class _Huber(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, tgt, scale):
+        lib = L.load()
+        L.require_cuda(inp, tgt)
+        if inp.shape != tgt.shape:
+            raise L.AstError(f"huber_loss shapes differ: {tuple(inp.shape)} vs {tuple(tgt.shape)}")
+        inp = _c(inp.float())
+        tgt = _c(tgt.float())
+        n = inp.numel()
+        loss = torch.empty((), device=inp.device, dtype=torch.float32)
+        wsb = lib.ast_huber_ws_bytes(n)
+        ws = torch.empty(wsb, device=inp.device, dtype=torch.uint8)
+        L.check(lib.ast_huber_fwd(inp.data_ptr(), tgt.data_ptr(), loss.data_ptr(), n, float(scale),
+                                  ws.data_ptr(), wsb, L.stream_ptr(inp.device)), "ast_huber_fwd")
+        ctx.save_for_backward(inp, tgt)
+        ctx.scale = float(scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        inp, tgt = ctx.saved_tensors
+        g = _c(g.float().reshape(1))
+        gi = torch.empty_like(inp) if ctx.needs_input_grad[0] else None
+        gt = None
+        if gi is not None:
+            L.check(lib.ast_huber_bwd(inp.data_ptr(), tgt.data_ptr(), g.data_ptr(), gi.data_ptr(),
+                                      inp.numel(), ctx.scale, L.stream_ptr(inp.device)),
+                    "ast_huber_bwd")
+        if ctx.needs_input_grad[1]:
+            gt = torch.empty_like(tgt)
+            L.check(lib.ast_huber_bwd(tgt.data_ptr(), inp.data_ptr(), g.data_ptr(), gt.data_ptr(),
+                                      inp.numel(), ctx.scale, L.stream_ptr(inp.device)),
+                    "ast_huber_bwd")
+        return gi, gt, None
+
+
+def huber_loss(inp: torch.Tensor, tgt: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """scale * F.huber_loss(inp, tgt) (delta 1, mean) as a 0-dim tensor with autograd history."""
+    return _Huber.apply(inp, tgt, scale)
+
+
+class _Gram(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = L.load()
+        L.require_cuda(x)
+        if x.dim() != 4:
+            raise L.AstError("gram_matrix expects (B, C, H, W)")
+        x = _c(x.float())
+        B, Cc, H, W = x.shape
+        g = torch.empty(B, Cc, Cc, device=x.device, dtype=torch.float32)
+        L.check(lib.ast_gram_fwd(x.data_ptr(), g.data_ptr(), B, Cc, H * W, L.stream_ptr(x.device)),
+                "ast_gram_fwd")
+        ctx.save_for_backward(x)
+        return g
+
+    @staticmethod
+    def backward(ctx, gg):
+        lib = L.load()
+        (x,) = ctx.saved_tensors
+        B, Cc, H, W = x.shape
+        gg = _c(gg.float())
+        gx = torch.empty_like(x)
+        L.check(lib.ast_gram_bwd(x.data_ptr(), gg.data_ptr(), gx.data_ptr(), B, Cc, H * W,
+                                 L.stream_ptr(x.device)), "ast_gram_bwd")
+        return gx
+
+
+def gram_matrix(x: torch.Tensor) -> torch.Tensor:
+    return _Gram.apply(x)

@@ -1,0 +1,32 @@
+"""Drop-in for the hot-path part of the reference's losses.py (losses.py:105-139).
+
+Same names, argument meaning and return convention (0-dim tensors with autograd history); the
+device work is libast_b200's Huber / Gram / channel-statistics kernels."""
+from __future__ import annotations
+
+import torch
+
+from . import functional as Fn
+from .model_util import channel_stats
+
+
+def gram_matrix(tensor: torch.Tensor) -> torch.Tensor:
+    """X X^T / (C*H*W), X = (B, C, H*W) -- losses.py:105-109."""
+    return Fn.gram_matrix(tensor)
+
+
+def compute_content_loss(inp: torch.Tensor, tgt: torch.Tensor) -> torch.Tensor:
+    """F.huber_loss(inp, tgt): delta 1, mean reduction -- losses.py:124-126."""
+    return Fn.huber_loss(inp, tgt)
+
+
+def compute_style_loss(t_cs_map: torch.Tensor, style_map: torch.Tensor) -> torch.Tensor:
+    """1.25 huber(mean) + 1.25 huber(std) + 10 huber(gram) -- losses.py:128-139."""
+    enc_mean, enc_std = channel_stats(t_cs_map)
+    style_mean, style_std = channel_stats(style_map)
+    mean_loss = Fn.huber_loss(enc_mean, style_mean, 1.25)
+    std_loss = Fn.huber_loss(enc_std, style_std, 1.25)
+    g_c = gram_matrix(t_cs_map)
+    g_s = gram_matrix(style_map)
+    gram_loss = Fn.huber_loss(g_c, g_s, 10.0)
+    return mean_loss + std_loss + gram_loss

@@ -1,0 +1,281 @@
+"""Drop-in for the AdaIN hot-path part of the reference's models.py.
+
+Same class / function names, constructor and ``forward`` signatures, return conventions and
+state-dict keys as the reference (paths relative to /root/reference):
+  AdaIN                models.py:37-51     (incl. the swapped style-statistics unpack at :44)
+  calc_mean_std        models.py:54-62
+  mean_variance_norm   models.py:64-68
+  PretrainedEncoder    models.py:186-240   (VGG-19 features, taps by name, early return)
+  ClassicDecoder       models.py:598-628   (the commented nn.Sequential spec, same key indices)
+Parameters stay ordinary fp32 OIHW ``nn.Parameter``s, so optimisers, clipping and checkpoints
+written for the reference work unchanged; packed bf16 kernel weights are derived caches that are
+rebuilt whenever a parameter's version counter changes.  All device work goes through
+libast_b200.so; CPU tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import engine as E
+from . import functional as Fn
+from .model_util import channel_stats  # re-exported like the reference's star import
+
+__all__ = ["AdaIN", "calc_mean_std", "mean_variance_norm", "PretrainedEncoder", "ClassicDecoder",
+           "StyleTransferNet", "channel_stats"]
+
+
+class AdaIN(nn.Module):
+    """models.py:37-51.  ``forward(content_map, style_map)``.
+
+    The reference binds ``style_std, style_mean = channel_stats(style_map)`` (models.py:44), i.e.
+    it scales by the style MEAN and shifts by the style STD; that is the default here.
+    ``canonical=True`` gives the Huang & Belongie form.  ``alpha`` / multi-style interpolation
+    (models.py:471 and BASELINE config 5) are fused into the same kernel pass."""
+
+    def __init__(self, canonical: bool = False):
+        super().__init__()
+        self.canonical = canonical
+
+    def forward(self, content_map, style_map, alpha: float = 1.0, style_weights=None):
+        styles = list(style_map) if isinstance(style_map, (list, tuple)) else [style_map]
+        if torch.is_grad_enabled() and (content_map.requires_grad or any(s.requires_grad for s in styles)):
+            return _adain_autograd(content_map, styles, style_weights, alpha, self.canonical)
+        return Fn.adain_forward(content_map, styles, style_weights, alpha, self.canonical)
+
+
+def _adain_autograd(content, styles, weights, alpha, canonical):
+    """Differentiable composition out of the differentiable kernels (MVN with eps = 0 and
+    channel statistics); used only when a feature map requires grad."""
+    K = len(styles)
+    weights = weights or [1.0 / K] * K
+    z = Fn.mean_variance_norm(content, eps=0.0)
+    A = B = None
+    for w, s in zip(weights, styles):
+        m, sd = channel_stats(s)
+        a, b = (sd, m) if canonical else (m, sd)
+        A = w * a if A is None else A + w * a
+        B = w * b if B is None else B + w * b
+    t = z * A + B
+    if alpha != 1.0:
+        t = alpha * t + (1 - alpha) * content
+    return t
+
+
+def calc_mean_std(feat, eps=1e-5):
+    """models.py:54-62: unbiased var + eps -> sqrt; mean.  Returns (mean, std), each (N,C,1,1)."""
+    size = feat.size()
+    assert (len(size) == 4)
+    N, C = size[:2]
+    mean, std = Fn.channel_stats_flat(feat, eps=eps, biased=False)
+    return mean.view(N, C, 1, 1).to(feat.dtype), std.view(N, C, 1, 1).to(feat.dtype)
+
+
+def mean_variance_norm(feat):
+    """models.py:64-68: (feat - mean) / sqrt(var + 1e-5), one fused pass, differentiable."""
+    assert feat.dim() == 4
+    return Fn.mean_variance_norm(feat, eps=1e-5)
+
+
+class _Named(nn.Module):
+    """Placeholder for the non-parametric VGG layers (norm / relu / pool); keeps ModuleList
+    indices -- and therefore state-dict keys -- identical to the reference."""
+
+    def __init__(self, name):
+        super().__init__()
+        self.name = name
+
+
+class _WeightCache:
+    def __init__(self):
+        self._c = {}
+
+    def packed(self, p: torch.Tensor, flip=False):
+        key = (id(p), flip)
+        ver = (p.data_ptr(), p._version, str(p.device))
+        hit = self._c.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, E.pack_conv_weight(p, flip))
+            self._c[key] = hit
+        return hit[1]
+
+
+class PretrainedEncoder(nn.Module):
+    """models.py:186-240.  VGG-19 ``features`` behind ImageNet normalisation; layers are named
+    conv_i / relu_i / pool_i (i = running conv index); ``forward`` returns the outputs of the
+    layers named in ``content_layers`` in network order and stops once all are collected.
+
+    The reference hard-codes ``pretrained=True`` (models.py:192); there is no network here, so
+    weights are torchvision's default VGG init and ``load_state_dict`` accepts the reference's
+    keys (``_vgg_layers.{1,3,6,...}.{weight,bias}``)."""
+
+    def __init__(self, content_layers=['conv_1', 'conv_3', 'conv_5', 'conv_9', 'conv_13', 'relu_15']):
+        super().__init__()
+        self._content_layers = set(content_layers)
+        layers = [_Named("norm")]
+        cin, i = 3, 0
+        for v in E.VGG19_CFG:
+            if v == "M":
+                layers.append(_Named(f"pool_{i}"))
+            else:
+                i += 1
+                conv = nn.Conv2d(cin, v, kernel_size=3, padding=1)
+                nn.init.kaiming_normal_(conv.weight, mode="fan_out", nonlinearity="relu")
+                nn.init.constant_(conv.bias, 0)
+                conv.name = f"conv_{i}"
+                layers.append(conv)
+                layers.append(_Named(f"relu_{i}"))
+                cin = v
+        self._vgg_layers = nn.ModuleList(layers)
+        self._cache = _WeightCache()
+        self._buf = E._Buffers()
+        self.conv_impl = L.CONV_AUTO
+
+    def _convs(self):
+        return [m for m in self._vgg_layers if isinstance(m, nn.Conv2d)]
+
+    def forward(self, x):
+        lib = L.load()
+        L.require_cuda(x)
+        wanted = self._content_layers
+        names = [m.name for m in self._vgg_layers]
+        last_needed = max((k for k, nm in enumerate(names) if nm in wanted), default=-1)
+        if last_needed < 0:
+            return []
+        x = x.float().contiguous()
+        N, _, H, W = x.shape
+        dev = x.device
+        st = L.stream_ptr(dev)
+        outs = []
+        convs = self._convs()
+        cur, h, w, c = None, H, W, 3
+        k = 1  # index into _vgg_layers (0 is the norm layer, fused into conv_1)
+        ci = 0
+        while k <= last_needed:
+            conv = self._vgg_layers[k]
+            assert isinstance(conv, nn.Conv2d)
+            cname, rname = names[k], names[k + 1]
+            has_pool = k + 2 < len(names) and names[k + 2].startswith("pool_")
+            pname = names[k + 2] if has_pool else None
+            want_c, want_r = cname in wanted, rname in wanted
+            if want_c and want_r:
+                raise L.AstError("tapping both conv_i and relu_i of the same layer is not supported")
+            cout = conv.out_channels
+            tap = (torch.empty(N, cout, h, w, device=dev, dtype=torch.float32)
+                   if (want_c or want_r) else None)
+            more = last_needed > k + 1  # anything after this conv+relu pair?
+            fuse_pool = has_pool and more
+            ho, wo = (h // 2, w // 2) if fuse_pool else (h, w)
+            out = self._buf.get(f"v{ci}", N, ho, wo, cout, dev, True) if more else None
+            if ci == 0:
+                mean, std = L.float_array(E.IMAGENET_MEAN), L.float_array(E.IMAGENET_STD)
+                L.check(lib.ast_conv3x3_first(x.data_ptr(), conv.weight.data_ptr(),
+                                              conv.bias.data_ptr(), mean, std, L.ptr(out),
+                                              L.ptr(tap), int(want_c), N, h, w, cout, st),
+                        "ast_conv3x3_first")
+                if fuse_pool:
+                    raise L.AstError("VGG-19 never pools right after conv_1")
+            else:
+                E.conv3x3(cur, self._cache.packed(conv.weight), conv.bias, out, N=N, H=h, W=w,
+                          cin=c, cout=cout, relu=True,
+                          epilogue=L.EPI_POOL2 if fuse_pool else L.EPI_PLAIN, halo=L.HALO_KEEP,
+                          impl=self.conv_impl, tap=tap, tap_prerelu=want_c)
+            if tap is not None:
+                outs.append(tap)
+            cur, h, w, c = out, ho, wo, cout
+            ci += 1
+            k += 2
+            if fuse_pool:
+                if pname in wanted:
+                    outs.append(E.native_to_nchw(cur))
+                k += 1
+        return outs
+
+
+class ClassicDecoder(nn.Sequential):
+    """The classic mirrored decoder the reference keeps as a commented ``nn.Sequential``
+    (models.py:598-628; channel list conf.py:9): [ReflectionPad2d(1), Conv2d(3x3), ReLU] x 9 (no
+    ReLU after the last), nearest x2 upsample after convs 1, 5 and 7.  The module list is built
+    exactly as that spec so the state-dict keys ('1.weight', '5.weight', ...) match; ``forward``
+    runs the tcgen05 kernels on the native layout instead of calling the sub-modules."""
+
+    def __init__(self, exporting: bool = False):
+        mods = []
+        for cin, cout, relu, up in E.DECODER_SPEC:
+            mods.append(nn.ReflectionPad2d((1, 1, 1, 1)))
+            mods.append(nn.Conv2d(cin, cout, (3, 3)))
+            if relu:
+                mods.append(nn.ReLU())
+            if up:
+                mods.append(nn.Upsample(scale_factor=2, mode='nearest'))
+        super().__init__(*mods)
+        self.exporting = exporting
+        self._cache = _WeightCache()
+        self._buf = E._Buffers()
+        self.conv_impl = L.CONV_AUTO
+
+    def _convs(self):
+        return [m for m in self if isinstance(m, nn.Conv2d)]
+
+    def forward(self, x):
+        """x: (N, 512, h, w) fp32 NCHW features -> (N, 3, 8h, 8w) fp32 image."""
+        L.require_cuda(x)
+        t = E.nchw_to_native(x, reflect=True)
+        return self.forward_native(t)
+
+    def forward_native(self, t):
+        lib = L.load()
+        N, hp, wp, _ = t.shape
+        h, w = hp - 2, wp - 2
+        dev = t.device
+        convs = self._convs()
+        cur = t
+        for i in range(8):
+            cin, cout, relu, up = E.DECODER_SPEC[i]
+            ho, wo = (2 * h, 2 * w) if up else (h, w)
+            y = self._buf.get(f"d{i}", N, ho, wo, cout, dev, False)
+            E.conv3x3(cur, self._cache.packed(convs[i].weight), convs[i].bias, y, N=N, H=h, W=w,
+                      cin=cin, cout=cout, relu=relu, epilogue=L.EPI_UP2 if up else L.EPI_PLAIN,
+                      halo=L.HALO_REFLECT, impl=self.conv_impl)
+            cur, h, w = y, ho, wo
+        out = torch.empty(N, 3, h, w, device=dev, dtype=torch.float32)
+        last = convs[8]
+        L.check(lib.ast_conv3x3_last(cur.data_ptr(), last.weight.data_ptr(), last.bias.data_ptr(),
+                                     out.data_ptr(), N, h, w, 64, 3, int(self.exporting),
+                                     L.stream_ptr(dev)), "ast_conv3x3_last")
+        return out
+
+
+class StyleTransferNet(nn.Module):
+    """f = relu4_1(img) ('relu_9'); t = AdaIN(f_c, f_s); alpha blend
+    (models.py:471); img = decoder(t).  ``forward(content, style, alpha=1.0)`` like AST.forward
+    (models.py:425).  Inference runs end to end in the native layout (StyleTransferEngine)."""
+
+    def __init__(self, encoder: PretrainedEncoder | None = None, decoder: ClassicDecoder | None = None,
+                 canonical: bool = False):
+        super().__init__()
+        self._enc = encoder if encoder is not None else PretrainedEncoder(['relu_9'])
+        self._dec = decoder if decoder is not None else ClassicDecoder()
+        self.ada_in = AdaIN(canonical)
+        self._engine = None
+        self._engine_ver = None
+
+    def engine(self) -> E.StyleTransferEngine:
+        convs = self._enc._convs()[:9]
+        dconvs = self._dec._convs()
+        params = [c.weight for c in convs] + [c.bias for c in convs] + \
+                 [c.weight for c in dconvs] + [c.bias for c in dconvs]
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        if self._engine is None or ver != self._engine_ver:
+            dev = convs[0].weight.device
+            self._engine = E.StyleTransferEngine([c.weight for c in convs], [c.bias for c in convs],
+                                                 [c.weight for c in dconvs], [c.bias for c in dconvs],
+                                                 device=dev)
+            self._engine_ver = ver
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, content_img, style_img, alpha: float = 1.0, style_weights=None):
+        return self.engine().stylize(content_img, style_img, alpha=alpha,
+                                     style_weights=style_weights, canonical=self.ada_in.canonical)

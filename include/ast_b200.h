@@ -1,0 +1,192 @@
+/*
+ * ast_b200.h -- C ABI of libast_b200.so: hand-written sm_100a kernels for the AdaIN
+ * style-transfer hot path of rwickman/ArbitraryStyleTransfer.
+ *
+ * The reference has no FFI: its hot path is Python calling ATen.  Each
+ * entry point below therefore cites the reference Python function (path relative to
+ * /root/reference, file:line) whose device work it replaces.  The Python host side
+ * (arbitrarystyletransfer_b200/*.py) mirrors the reference's call surface and binds these
+ * symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - return 0 on success, >0 = cudaError_t, <0 = AST_E_* argument/shape error;
+ *   - never throws, never allocates device memory, never synchronises the device;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *   - device pointers are borrowed for the duration of the enqueued work; host arrays
+ *     (style pointer lists, weights) are copied into kernel parameters before returning;
+ *   - tensors are contiguous.  "NCHW fp32" is the reference's own layout; "NHWC16 padded"
+ *     is the native inter-layer layout: bf16 [N][H+2][W+2][C] with a one-pixel halo that holds
+ *     zeros (VGG, zero padding) or the reflection of the interior (decoder, ReflectionPad2d(1)).
+ */
+#ifndef AST_B200_H_
+#define AST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AST_ABI_VERSION 1
+
+/* error codes (negative) */
+#define AST_E_BADARG   (-1)  /* null pointer / non-positive size */
+#define AST_E_SHAPE    (-2)  /* shape not supported by this kernel */
+#define AST_E_ALIGN    (-3)  /* pointer not aligned as required */
+#define AST_E_TOOMANY  (-4)  /* K > AST_MAX_STYLES */
+#define AST_E_NODRIVER (-5)  /* CUDA driver entry point (TMA descriptor encode) unavailable */
+#define AST_E_WORKSPACE (-6) /* workspace too small */
+
+#define AST_MAX_STYLES 8
+
+/* flags for the statistics / AdaIN family */
+#define AST_F_CANONICAL 0x1u /* scale = sigma_s, shift = mu_s (paper).  Default 0 = the
+                                reference's swapped unpack at models.py:44:
+                                scale = mu_s, shift = sigma_s. */
+#define AST_F_BIASED    0x2u /* divide M2 by HW instead of HW-1 (default: unbiased, as
+                                torch.std / torch.var in model_util.py:5, models.py:59) */
+#define AST_F_BF16      0x4u /* tensors are bf16 instead of fp32 (stats stay fp32) */
+
+int ast_abi_version(void);
+const char* ast_error_string(int code);
+/* SM count / compute capability of the current device; returns 0 or a cudaError_t. */
+int ast_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  fused AdaIN: per-(n,c) Welford mean/variance of content and K style maps, affine
+ * re-normalisation, K-style mix and alpha blend in one pass over HBM.
+ * Replaces AdaIN.forward (models.py:43-51) + channel_stats x2 (model_util.py:3-8) + the
+ * alpha blend `t = alpha*t + (1-alpha)*content_map` (models.py:471).
+ *   content : [N][C][HW]          styles[k] : [N][C][style_hw[k]]      out : [N][C][HW]
+ *   style_w : K host floats (mix weights; K=1,w=1 is the reference)
+ *   stats   : optional device [N*C][2+2K] fp32 = mu_c, sigma_c, (mu_s, sigma_s) x K
+ *   eps     : added to the variance before sqrt (0 for the reference AdaIN)
+ * out may alias content.  Algorithmic HBM bytes: (1 + K + 1) * N*C*HW * sizeof(elem).
+ * ------------------------------------------------------------------------------------- */
+int ast_adain_fwd(const void* content, const void* const* styles, const int64_t* style_hw,
+                  const float* style_w, int K, void* out, float* stats,
+                  int N, int C, int64_t HW, float alpha, float eps, unsigned flags,
+                  void* stream);
+
+/* channel_stats (model_util.py:3-8) / calc_mean_std (models.py:54-62): x [rows][HW] ->
+ * mean[rows], std[rows] (std = sqrt(var + eps)). */
+int ast_channel_stats_fwd(const void* x, float* mean, float* std_, int64_t rows, int64_t HW,
+                          float eps, unsigned flags, void* stream);
+/* backward of the above: gx = g_mean/HW + g_std * (x - mean) / ((HW-1|HW) * std).
+ * g_mean / g_std may be NULL (treated as zero). */
+int ast_channel_stats_bwd(const void* x, const float* mean, const float* std_,
+                          const float* g_mean, const float* g_std, void* gx,
+                          int64_t rows, int64_t HW, unsigned flags, void* stream);
+
+/* mean_variance_norm (models.py:64-68): y = (x - mean) / sqrt(var_unbiased + eps).
+ * stats: optional device [rows][2] fp32 (mean, std) saved for the backward.  y may alias x. */
+int ast_mvn_fwd(const void* x, void* y, float* stats, int64_t rows, int64_t HW,
+                float eps, unsigned flags, void* stream);
+/* backward: gx = (gy - mean(gy))/std - y * sum(gy*y) / ((HW-1|HW) * std), with y recomputed
+ * from x and the saved stats. */
+int ast_mvn_bwd(const void* x, const void* gy, const float* stats, void* gx,
+                int64_t rows, int64_t HW, unsigned flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  losses.
+ * ------------------------------------------------------------------------------------- */
+/* compute_content_loss = F.huber_loss(inp, tgt), delta 1, mean (losses.py:124-126).
+ * Writes scale * mean(huber) to loss[0] (device fp32; overwritten).
+ * ws: device workspace of >= ast_huber_ws_bytes(n) bytes. */
+size_t ast_huber_ws_bytes(int64_t n);
+int ast_huber_fwd(const float* inp, const float* tgt, float* loss, int64_t n, float scale,
+                  void* ws, size_t ws_bytes, void* stream);
+/* g_inp = g_loss[0] * scale / n * clamp(inp - tgt, -1, 1). */
+int ast_huber_bwd(const float* inp, const float* tgt, const float* g_loss, float* g_inp,
+                  int64_t n, float scale, void* stream);
+
+/* gram_matrix (losses.py:105-109): G[b] = X[b] X[b]^T / (C*HW), X fp32 [B][C][HW] -> [B][C][C] */
+int ast_gram_fwd(const float* x, float* g, int B, int C, int64_t HW, void* stream);
+/* gx[b] = (gG[b] + gG[b]^T) X[b] / (C*HW) */
+int ast_gram_bwd(const float* x, const float* gg, float* gx, int B, int C, int64_t HW,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  3x3 convolutions (stride 1) on the native layout.
+ * Replaces, for VGG-19 (models.py:186-240): nn.Conv2d(k3, zero pad 1, bias) + nn.ReLU +
+ * nn.MaxPool2d(2,2); for the classic decoder (models.py:598-628): nn.ReflectionPad2d(1) +
+ * nn.Conv2d(k3, p0, bias) + nn.ReLU + nn.Upsample(x2, nearest).
+ * ------------------------------------------------------------------------------------- */
+
+/* epilogue placement */
+#define AST_EPI_PLAIN 0 /* out[h][w]                          (Ho,Wo) = (H,W)      */
+#define AST_EPI_POOL2 1 /* 2x2/2 max pool of relu(conv)       (Ho,Wo) = (H/2,W/2)  */
+#define AST_EPI_UP2   2 /* nearest x2 upsample of relu(conv)  (Ho,Wo) = (2H,2W)    */
+/* halo written by the epilogue into the padded output */
+#define AST_HALO_KEEP    0 /* interior only (halo keeps the caller's zeros: next conv zero-pads) */
+#define AST_HALO_REFLECT 1 /* also write the ReflectionPad2d(1) halo of the output grid */
+/* implementation selector */
+#define AST_CONV_AUTO   0 /* tcgen05 implicit GEMM when Cin%64==0 && Cout%64==0, else direct */
+#define AST_CONV_TC     1 /* force tcgen05 (AST_E_SHAPE if unsupported) */
+#define AST_CONV_DIRECT 2 /* CUDA-core direct kernel (odd shapes; on-device cross-check) */
+
+typedef struct ast_conv_desc {
+  int N, H, W;        /* conv input = conv output spatial size (stride 1, 3x3, pad 1)      */
+  int Cin, Cout;
+  int relu;           /* fuse ReLU                                                           */
+  int epilogue;       /* AST_EPI_*                                                           */
+  int halo;           /* AST_HALO_*                                                          */
+  int impl;           /* AST_CONV_*                                                          */
+  int tap_prerelu;    /* if tap != NULL: 1 = tap holds conv+bias before ReLU, 0 = after     */
+} ast_conv_desc;
+
+/* in  : bf16 [N][H+2][W+2][Cin] (halo already holds the padding of this conv)
+ * wpk : bf16 packed weights [9][Cout][Cin] (ast_pack_conv_weight)
+ * bias: fp32 [Cout] (may be NULL)
+ * out : bf16 [N][Ho+2][Wo+2][Cout] or NULL
+ * tap : optional fp32 NCHW [N][Cout][H][W] copy of the (pre- or post-ReLU) conv output at
+ *       conv resolution, for callers that need reference-layout feature maps. */
+int ast_conv3x3_fwd(const ast_conv_desc* d, const void* in, const void* wpk, const float* bias,
+                    void* out, float* tap, void* stream);
+
+/* OIHW fp32 [Cout][Cin][3][3] -> bf16 [9][Cout][Cin] (tap = kh*3+kw).
+ * flip=1 additionally rotates the taps by 180 degrees and swaps the O/I roles, producing the
+ * data-gradient weights: out is [9][Cin][Cout'] i.e. a conv from Cout channels to Cin. */
+int ast_pack_conv_weight(const float* w_oihw, void* wpk, int Cout, int Cin, int flip,
+                         void* stream);
+
+/* First VGG layer: Normalization (models.py:129-131) + conv_1 (3->Cout, zero pad) + ReLU from
+ * the reference's NCHW fp32 image straight into the native layout.
+ *   img : fp32 [N][3][H][W]; w : fp32 OIHW [Cout][3][3][3]; bias fp32 [Cout]
+ *   mean/std : 3 host floats each (NULL = no normalisation)
+ *   out : bf16 [N][H+2][W+2][Cout] (interior only); tap as in ast_conv3x3_fwd. */
+int ast_conv3x3_first(const float* img, const float* w, const float* bias, const float* mean,
+                      const float* std_, void* out, float* tap, int tap_prerelu,
+                      int N, int H, int W, int Cout, void* stream);
+
+/* Last decoder layer: reflect-padded native input -> NCHW fp32 image, no ReLU.
+ *   in : bf16 [N][H+2][W+2][Cin]; w : fp32 OIHW [Cout][Cin][3][3]; out fp32 [N][Cout][H][W]
+ *   clamp01 != 0 applies Hardtanh(0,1) (Decoder.last_act when exporting, models.py:304,315) */
+int ast_conv3x3_last(const void* in, const float* w, const float* bias, float* out,
+                     int N, int H, int W, int Cin, int Cout, int clamp01, void* stream);
+
+/* layout converters between the reference layout and the native one.
+ * nchw fp32 [N][C][H][W] <-> bf16 [N][H+2][W+2][C]; `halo` as AST_HALO_*. */
+int ast_nchw_to_native(const float* nchw, void* native, int N, int C, int H, int W, int halo,
+                       void* stream);
+int ast_native_to_nchw(const void* native, float* nchw, int N, int C, int H, int W,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K1n  AdaIN on the native layout (in-pipeline form of K1; same arithmetic).
+ *   content : bf16 [N][H+2][W+2][C]; styles[k] : bf16 [N][Hs+2][Ws+2][C]
+ *   out     : bf16 [N][H+2][W+2][C], halo per `halo`
+ *   ws      : >= ast_adain_native_ws_bytes(N, C, K) bytes
+ * ------------------------------------------------------------------------------------- */
+size_t ast_adain_native_ws_bytes(int N, int C, int K);
+int ast_adain_native_fwd(const void* content, const void* const* styles, const float* style_w,
+                         int K, void* out, int N, int C, int H, int W, int Hs, int Ws,
+                         float alpha, float eps, unsigned flags, int halo,
+                         void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AST_B200_H_ */

@@ -1,0 +1,176 @@
+"""Generate tests/golden/*.npz by EXECUTING THE GENUINE REFERENCE CODE (read from /root/reference
+at run time through oracle/ref_loader.py) on seeded inputs.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (the GPU box has no /root/reference):
+    python -m oracle.make_golden
+The fixtures pin oracle/restate.py (tests/test_oracle_golden.py) and, through it, the CUDA path
+(tests/test_gpu_*.py).  Every file records the torch / torchvision versions that produced it,
+because the arithmetic below the reference lives in ATen / torchvision (unpinned by the
+reference, which has no requirements file).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_loader, restate as R  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _versions():
+    import torchvision
+    return {"torch_version": np.array(torch.__version__), "torchvision_version": np.array(torchvision.__version__)}
+
+
+def _t(seed, *shape, scale=1.0, shift=0.0, relu=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(*shape, generator=g) * scale + shift
+    return torch.relu(x) if relu else x
+
+
+def golden_stats_adain(M, mu, out):
+    """AdaIN / channel_stats / calc_mean_std / mean_variance_norm from the genuine reference."""
+    cases = {
+        "a": ((2, 8, 7, 9), (2, 8, 5, 6)),        # ragged, HW not a multiple of 4
+        "b": ((1, 16, 32, 32), (1, 16, 32, 32)),  # cfg-1 spatial size, few channels
+        "c": ((3, 4, 1, 2), (3, 4, 2, 1)),        # HW = 2: smallest size with a finite unbiased std
+        "d": ((1, 6, 64, 48), (1, 6, 16, 80)),    # different content / style sizes
+    }
+    for k, (cs, ss) in cases.items():
+        c = _t(10 + ord(k), *cs, scale=3.0, shift=1.0, relu=True)
+        s = _t(20 + ord(k), *ss, scale=2.0, shift=3.0)
+        out[f"adain_{k}_content"] = c.numpy()
+        out[f"adain_{k}_style"] = s.numpy()
+        with torch.no_grad():
+            out[f"adain_{k}_out"] = M.AdaIN()(c, s).numpy()                  # models.py:43-51
+            m, sd = mu.channel_stats(c)                                      # model_util.py:3-8
+            out[f"adain_{k}_cmean"], out[f"adain_{k}_cstd"] = m.numpy(), sd.numpy()
+            m, sd = M.calc_mean_std(c)                                       # models.py:54-62
+            out[f"adain_{k}_cms_mean"], out[f"adain_{k}_cms_std"] = m.numpy(), sd.numpy()
+            out[f"adain_{k}_mvn"] = M.mean_variance_norm(c).numpy()          # models.py:64-68
+            t = M.AdaIN()(c, s)
+            out[f"adain_{k}_blend06"] = (0.6 * t + (1 - 0.6) * c).numpy()     # models.py:471
+    # a dead (constant) channel: the reference divides 0/0 (no epsilon) -> NaN
+    c = _t(31, 1, 3, 4, 4)
+    c[:, 1] = 0.0
+    s = _t(32, 1, 3, 4, 4)
+    with torch.no_grad():
+        out["adain_dead_content"], out["adain_dead_style"] = c.numpy(), s.numpy()
+        out["adain_dead_out"] = M.AdaIN()(c, s).numpy()
+    # backward of mean_variance_norm and channel_stats (autograd of the reference functions)
+    c = _t(41, 2, 5, 6, 7, scale=2.0, shift=0.5).requires_grad_(True)
+    gy = _t(42, 2, 5, 6, 7)
+    M.mean_variance_norm(c).backward(gy)
+    out["mvn_bwd_x"], out["mvn_bwd_gy"], out["mvn_bwd_gx"] = c.detach().numpy(), gy.numpy(), c.grad.numpy()
+    c2 = c.detach().clone().requires_grad_(True)
+    m, sd = mu.channel_stats(c2)
+    gm, gs = _t(43, 2, 5, 1, 1), _t(44, 2, 5, 1, 1)
+    (m * gm).sum().add((sd * gs).sum()).backward()
+    out["cs_bwd_gm"], out["cs_bwd_gs"], out["cs_bwd_gx"] = gm.numpy(), gs.numpy(), c2.grad.numpy()
+
+
+def golden_losses(Ls, out):
+    """compute_content_loss / gram_matrix / compute_style_loss values and input gradients."""
+    a = _t(51, 2, 6, 9, 11, scale=1.5).requires_grad_(True)
+    b = _t(52, 2, 6, 9, 11, scale=1.5, shift=0.3)
+    out["loss_a"], out["loss_b"] = a.detach().numpy(), b.numpy()
+    l = Ls.compute_content_loss(a, b)                                     # losses.py:124-126
+    l.backward()
+    out["content_loss"], out["content_loss_ga"] = l.detach().numpy(), a.grad.numpy()
+    a.grad = None
+    g = Ls.gram_matrix(a)                                                 # losses.py:105-109
+    out["gram_a"] = g.detach().numpy()
+    gg = _t(53, 2, 6, 6)
+    (g * gg).sum().backward()
+    out["gram_gg"], out["gram_ga"] = gg.numpy(), a.grad.numpy()
+    a.grad = None
+    l = Ls.compute_style_loss(a, b)                                       # losses.py:128-139
+    l.backward()
+    out["style_loss"], out["style_loss_ga"] = l.detach().numpy(), a.grad.numpy()
+
+
+def golden_networks(M, out):
+    """Genuine PretrainedEncoder (models.py:186-240) and the commented classic decoder
+    (models.py:598-628) with the seeded synthetic weight recipe of oracle/restate.py."""
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+
+    def load_vgg(enc):
+        convs = [l for l in enc._vgg_layers if isinstance(l, torch.nn.Conv2d)]
+        assert len(convs) == 16
+        with torch.no_grad():
+            for c, w, b in zip(convs, vw, vb):
+                c.weight.copy_(w)
+                c.bias.copy_(b)
+
+    enc_default = M.PretrainedEncoder().eval()
+    load_vgg(enc_default)
+    enc_r9 = M.PretrainedEncoder(['relu_9']).eval()
+    load_vgg(enc_r9)
+    dec = ref_loader.build_reference_classic_decoder()
+    dconvs = [l for l in dec if isinstance(l, torch.nn.Conv2d)]
+    with torch.no_grad():
+        for c, w, b in zip(dconvs, dw, db):
+            c.weight.copy_(w)
+            c.bias.copy_(b)
+    out["vgg_state_keys"] = np.array(sorted(enc_default.state_dict().keys()))
+    out["dec_state_keys"] = np.array(sorted(dec.state_dict().keys()))
+
+    x = R.rand_image(1, 32, 61)
+    with torch.no_grad():
+        taps = enc_default(x)
+    out["vgg_x32"] = x.numpy()
+    for i, t in enumerate(taps):
+        out[f"vgg_x32_tap{i}"] = t.numpy()
+    # config-1 shaped run at reduced size (64x64) and the real config 1 (256x256, summary + crop)
+    adain = M.AdaIN()
+    for size, tag in ((64, "s64"), (256, "cfg1")):
+        c, s = R.rand_image(1, size, 101), R.rand_image(1, size, 102)
+        with torch.no_grad():
+            fc, fs = enc_r9(c)[0], enc_r9(s)[0]
+            t = adain(fc, fs)
+            img = dec(t)
+        if size == 64:
+            out[f"{tag}_fc"], out[f"{tag}_t"], out[f"{tag}_img"] = fc.numpy(), t.numpy(), img.numpy()
+        else:
+            out[f"{tag}_img_crop"] = img[:, :, 96:160, 96:160].numpy()
+            out[f"{tag}_img_sub4"] = img[:, :, ::4, ::4].numpy()
+            out[f"{tag}_img_stats"] = np.array([img.mean().item(), img.std().item(),
+                                                img.min().item(), img.max().item()])
+            out[f"{tag}_fc_sub"] = fc[:, ::8, ::2, ::2].numpy()
+    # decoder alone on a tiny feature map
+    f = _t(71, 1, 512, 4, 4, scale=1.0, shift=0.5, relu=True)
+    with torch.no_grad():
+        out["dec_in"], out["dec_out"] = f.numpy(), dec(f).numpy()
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("reference tree not present: golden vectors can only be made in the build container")
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    M = ref_loader.load_reference_models()
+    mu = ref_loader.load_reference_module("model_util")
+    Ls = ref_loader.load_reference_module("losses")
+    os.makedirs(OUT, exist_ok=True)
+    for name, fn, args in (("stats_adain", golden_stats_adain, (M, mu)),
+                           ("losses", golden_losses, (Ls,)),
+                           ("networks", golden_networks, (M,))):
+        d = dict(_versions())
+        fn(*args, d)
+        path = os.path.join(OUT, f"{name}.npz")
+        np.savez_compressed(path, **d)
+        print(f"wrote {path}: {len(d)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

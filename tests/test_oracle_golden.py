@@ -1,0 +1,128 @@
+"""The CPU oracle (oracle/restate.py) against golden vectors produced by the GENUINE reference code
+(oracle/make_golden.py, executed in the build container).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+
+CASES = ["a", "b", "c", "d"]
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def same(a, b):
+    """bit-exact, NaN == NaN (dead channels give 0/0 in the reference: models.py:47)."""
+    return np.array_equal(a.detach().numpy(), np.asarray(b), equal_nan=True)
+
+
+@pytest.mark.parametrize("k", CASES)
+def test_channel_stats_and_adain(golden_stats, k):
+    g = golden_stats
+    c, s = T(g[f"adain_{k}_content"]), T(g[f"adain_{k}_style"])
+    m, sd = R.channel_stats(c)
+    assert same(m, g[f"adain_{k}_cmean"])
+    assert same(sd, g[f"adain_{k}_cstd"])
+    assert same(R.adain(c, s), g[f"adain_{k}_out"])
+    # fp64 numpy restatement agrees with the fp32 reference to fp32 rounding
+    m64, sd64 = R.channel_stats_np(c.numpy())
+    np.testing.assert_allclose(m64, g[f"adain_{k}_cmean"], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(sd64, g[f"adain_{k}_cstd"], rtol=2e-6, atol=1e-6)
+    # K = 1 multi-style form == the reference AdaIN (models.py:43-51), up to fp32 re-association
+    np.testing.assert_allclose(R.adain_multi(c, [s], [1.0]).numpy(), g[f"adain_{k}_out"],
+                               rtol=1e-5, atol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(R.adain_multi(c, [s], [1.0], alpha=0.6).numpy(),
+                               g[f"adain_{k}_blend06"], rtol=1e-5, atol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize("k", CASES)
+def test_calc_mean_std_mvn(golden_stats, k):
+    g = golden_stats
+    c = T(g[f"adain_{k}_content"])
+    m, sd = R.calc_mean_std(c)
+    assert same(m, g[f"adain_{k}_cms_mean"])
+    assert same(sd, g[f"adain_{k}_cms_std"])
+    assert same(R.mean_variance_norm(c), g[f"adain_{k}_mvn"])
+
+
+def test_dead_channel_is_nan_like_reference(golden_stats):
+    g = golden_stats
+    out = R.adain(T(g["adain_dead_content"]), T(g["adain_dead_style"])).numpy()
+    ref = g["adain_dead_out"]
+    assert np.isnan(ref[:, 1]).all()            # the reference has no epsilon: 0/0
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    np.testing.assert_array_equal(out[~np.isnan(out)], ref[~np.isnan(ref)])
+
+
+def test_swapped_statistics(golden_stats):
+    """models.py:44 binds (style_std, style_mean) = channel_stats(style) = (mean, std)."""
+    g = golden_stats
+    c, s = T(g["adain_b_content"]), T(g["adain_b_style"])
+    out = T(g["adain_b_out"])
+    m, sd = R.channel_stats(out)
+    sm, ssd = R.channel_stats(s)
+    # per-channel std of the output = |mean(style)|, per-channel mean = std(style)
+    torch.testing.assert_close(sd, sm.abs(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(m, ssd, rtol=1e-4, atol=1e-4)
+    assert not torch.allclose(out, R.adain_canonical(c, s), atol=1e-2)
+
+
+def test_backward_goldens(golden_stats):
+    g = golden_stats
+    x = T(g["mvn_bwd_x"]).clone().requires_grad_(True)
+    R.mean_variance_norm(x).backward(T(g["mvn_bwd_gy"]))
+    torch.testing.assert_close(x.grad, T(g["mvn_bwd_gx"]), rtol=1e-6, atol=1e-6)
+    x2 = T(g["mvn_bwd_x"]).clone().requires_grad_(True)
+    m, sd = R.channel_stats(x2)
+    ((m * T(g["cs_bwd_gm"])).sum() + (sd * T(g["cs_bwd_gs"])).sum()).backward()
+    torch.testing.assert_close(x2.grad, T(g["cs_bwd_gx"]), rtol=1e-6, atol=1e-6)
+
+
+def test_losses(golden_losses):
+    g = golden_losses
+    a, b = T(g["loss_a"]).clone().requires_grad_(True), T(g["loss_b"])
+    l = R.compute_content_loss(a, b)
+    assert l.item() == pytest.approx(float(g["content_loss"]), rel=1e-6)
+    assert l.item() == pytest.approx(R.huber_np(a.detach().numpy(), b.numpy()), rel=1e-5)
+    l.backward()
+    torch.testing.assert_close(a.grad, T(g["content_loss_ga"]))
+    a.grad = None
+    gm = R.gram_matrix(a)
+    torch.testing.assert_close(gm.detach(), T(g["gram_a"]), rtol=1e-6, atol=1e-7)
+    (gm * T(g["gram_gg"])).sum().backward()
+    torch.testing.assert_close(a.grad, T(g["gram_ga"]), rtol=1e-5, atol=1e-7)
+    a.grad = None
+    l = R.compute_style_loss(a, b)
+    assert l.item() == pytest.approx(float(g["style_loss"]), rel=1e-6)
+    l.backward()
+    torch.testing.assert_close(a.grad, T(g["style_loss_ga"]), rtol=1e-5, atol=1e-8)
+
+
+def test_vgg_taps_and_decoder(golden_networks):
+    g = golden_networks
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+    with torch.no_grad():
+        taps = R.vgg_forward(T(g["vgg_x32"]), vw, vb)
+        assert len(taps) == 6
+        for i, t in enumerate(taps):
+            torch.testing.assert_close(t, T(g[f"vgg_x32_tap{i}"]), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(R.decoder_forward(T(g["dec_in"]), dw, db), T(g["dec_out"]),
+                                   rtol=1e-5, atol=1e-5)
+
+
+def test_stylize_64(golden_networks):
+    g = golden_networks
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+    c, s = R.rand_image(1, 64, 101), R.rand_image(1, 64, 102)
+    with torch.no_grad():
+        fc = R.vgg_relu4_1(c, vw, vb)
+        torch.testing.assert_close(fc, T(g["s64_fc"]), rtol=1e-5, atol=1e-5)
+        img = R.stylize(c, s, vw, vb, dw, db)
+    assert torch.isfinite(img).all()
+    assert R.psnr(img, T(g["s64_img"])) > 80.0
