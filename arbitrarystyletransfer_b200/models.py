@@ -279,3 +279,26 @@ class StyleTransferNet(nn.Module):
     def forward(self, content_img, style_img, alpha: float = 1.0, style_weights=None):
         return self.engine().stylize(content_img, style_img, alpha=alpha,
                                      style_weights=style_weights, canonical=self.ada_in.canonical)
+
+
+@torch.no_grad()
+def calibrate_encoder_bias(enc: PretrainedEncoder, n_convs: int = 9, size: int = 128,
+                           seed: int = 1234) -> None:
+    """Synthetic-weight helper (no reference counterpart: the reference downloads pretrained
+    weights, models.py:192).  With random-init VGG weights tens of relu4_1 channels are dead and
+    the epsilon-free AdaIN (models.py:47) turns them into NaN; this sets, conv by conv,
+    ``bias_c = -mean(pre-activation_c)`` on a seeded uniform batch so every channel stays alive
+    (SURVEY.md section 8d).  Runs on the GPU through this package's own encoder taps."""
+    dev = enc._convs()[0].weight.device
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(2, 3, size, size, generator=g).to(dev)
+    saved = enc._content_layers
+    try:
+        for i, conv in enumerate(enc._convs()[:n_convs]):
+            conv.bias.zero_()
+            enc._content_layers = {f"conv_{i + 1}"}
+            pre = enc(x)[0]
+            m, _ = Fn.channel_stats_flat(pre.transpose(0, 1).reshape(1, pre.shape[1], -1, 1))
+            conv.bias.copy_(-m.view(-1))
+    finally:
+        enc._content_layers = saved

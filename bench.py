@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the AdaIN style-transfer hot path (BASELINE.json metric: stylised img/s @512x512,
+VGG-19 relu4_1 -> AdaIN -> mirrored decoder forward; AdaIN HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic content/style pairs
+(BASELINE config 4: 512x512, 32 pairs per GPU, batch-sharded with no collective -> weak scaling).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "stylized_img_per_s_512x512_vgg19_adain_fwd"
+UNIT = "img/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="content/style pairs per GPU per step")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="pairs timed on the CPU arm (0 = auto: about 10-30 s of CPU work)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers-out", default="", help="write the per-layer timing table (JSON) here")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                          ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows if len(r) > col):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows),
+                "reasons": reasons}
+
+
+def flops_per_image(size: int) -> float:
+    """Algorithmic FLOPs of one stylised image: 2 encoders to relu4_1 + 1 decoder, 2*Cout*Cin*9*Ho*Wo
+    per conv in the reference formulation."""
+    from arbitrarystyletransfer_b200.engine import DECODER_SPEC, vgg_layer_plan
+    enc, h = 0.0, size
+    for cin, cout, pool in vgg_layer_plan(9):
+        enc += 2.0 * cout * cin * 9 * h * h
+        if pool:
+            h //= 2
+    dec = 0.0
+    for cin, cout, _, up in DECODER_SPEC:
+        dec += 2.0 * cout * cin * 9 * h * h
+        if up:
+            h *= 2
+    return 2 * enc + dec
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU path (oracle port), all host threads
+# ------------------------------------------------------------------------------------------
+def cpu_reference(size: int, pairs: int, warm: int = 1):
+    """Time oracle.restate.stylize (the CPU restatement of models.py:186-240 + 43-51 + 598-628 --
+    the reference is pure Python/ATen with no compilable sources, so kind = 'port') on `pairs`
+    512x512 pairs, one at a time as the reference's batch-1 preview path does (train.py:380-385)."""
+    from oracle import restate as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+    c, s = R.rand_image(1, size, 401), R.rand_image(1, size, 402)
+    with torch.no_grad():
+        for _ in range(warm):
+            R.stylize(c, s, vw, vb, dw, db)
+        t0 = time.perf_counter()
+        for _ in range(pairs):
+            R.stylize(c, s, vw, vb, dw, db)
+        dt = time.perf_counter() - t0
+    return {"value": pairs / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{pairs} sequential {size}x{size} content/style pairs (batch 1, fp32, "
+                      f"torch {torch.__version__} CPU, oracle/restate.py stylize), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs = args.cpu_sample or 2
+    # warm-up steps then K timed steps, each a bounded sample of `pairs` images
+    from oracle import restate as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+    c, s = R.rand_image(pairs, args.size, 401), R.rand_image(pairs, args.size, 402)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            R.stylize(c[:1], s[:1], vw, vb, dw, db)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            R.stylize(c, s, vw, vb, dw, db)
+        dt = time.perf_counter() - t0
+    v = pairs * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE config 4: VGG-19 relu4_1 -> AdaIN -> decoder forward at "
+                                   f"{args.size}x{args.size}, alpha=1.0; bounded sample of {pairs} pairs per step "
+                                   "on the host cores (reference CPU path)",
+                       "batch_per_step": pairs, "size": args.size},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} steps x {pairs} pairs at {args.size}x{args.size}, "
+                                       f"oracle/restate.py stylize (CPU restatement of the reference: it has "
+                                       f"no compilable sources), {dt:.1f} s"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------
+def build_engine(device):
+    """Random-init weights of the named architecture (no checkpoints offline): torchvision-style VGG
+    init + seeded decoder init, with the bias calibration that keeps all relu4_1 channels alive."""
+    from arbitrarystyletransfer_b200 import models as M
+    torch.manual_seed(0)
+    enc = M.PretrainedEncoder(['relu_9']).to(device)
+    M.calibrate_encoder_bias(enc)
+    torch.manual_seed(1)
+    dec = M.ClassicDecoder().to(device)
+    net = M.StyleTransferNet(enc, dec)
+    return net.engine()
+
+
+def time_layers(eng, N, size, reps=5):
+    """CUDA-event duration of every conv launch of one stylise pass (on the launching stream),
+    for the roofline of the dominant kernel family (conv3x3_tc_kernel)."""
+    from arbitrarystyletransfer_b200 import _lib as L, engine as E
+    dev = eng.device
+    rows = []
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return ts[len(ts) // 2]
+
+    h = size
+    x = eng.buf.get("enc0", N, h, h, 64, dev, True)
+    for i in range(1, 9):
+        cin, cout, pool = eng.plan[i]
+        ho = h // 2 if pool else h
+        y = eng.buf.get(f"enc{i}" + ("c" if i == 8 else ""), N, ho, ho, cout, dev, True)
+        ms = timed(lambda: E.conv3x3(x, eng.vgg_wpk[i], eng.vgg_b[i], y, N=N, H=h, W=h, cin=cin,
+                                     cout=cout, relu=True,
+                                     epilogue=L.EPI_POOL2 if pool else L.EPI_PLAIN, halo=L.HALO_KEEP))
+        rows.append({"layer": f"enc_conv{i + 1}", "cin": cin, "cout": cout, "hw": h, "epi": "pool" if pool else "plain",
+                     "ms": ms, "flops": 2.0 * cout * cin * 9 * h * h * N, "per_step": 2})
+        x, h = y, ho
+    x = eng.buf.get("adain", N, h, h, 512, dev, False)
+    for i in range(8):
+        cin, cout, relu, up = E.DECODER_SPEC[i]
+        ho = 2 * h if up else h
+        y = eng.buf.get(f"dec{i}", N, ho, ho, cout, dev, False)
+        ms = timed(lambda: E.conv3x3(x, eng.dec_wpk[i], eng.dec_b[i], y, N=N, H=h, W=h, cin=cin,
+                                     cout=cout, relu=relu,
+                                     epilogue=L.EPI_UP2 if up else L.EPI_PLAIN, halo=L.HALO_REFLECT))
+        rows.append({"layer": f"dec_conv{i + 1}", "cin": cin, "cout": cout, "hw": h, "epi": "up" if up else "plain",
+                     "ms": ms, "flops": 2.0 * cout * cin * 9 * h * h * N, "per_step": 1})
+        x, h = y, ho
+    for r in rows:
+        r["tflops"] = r["flops"] / (r["ms"] * 1e-3) / 1e12
+    return rows
+
+
+def time_adain_k1(N, reps=10):
+    """Standalone K1 (fused AdaIN, NCHW fp32) at the config-4 per-GPU shape (N,512,64,64)."""
+    from arbitrarystyletransfer_b200 import functional as Fn
+    c = torch.relu(torch.randn(N, 512, 64, 64, device="cuda") * 3 + 1)
+    s = torch.randn(N, 512, 64, 64, device="cuda") * 2 + 3
+    out = torch.empty_like(c)
+    for _ in range(3):
+        Fn.adain_forward(c, [s], out=out)
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        Fn.adain_forward(c, [s], out=out)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    ms = ts[len(ts) // 2]
+    return 3.0 * c.numel() * 4, ms
+
+
+def run_native(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, S = args.batch, args.size
+    eng = build_engine(dev)
+    g = torch.Generator().manual_seed(401 + rank)
+    # host-side pinned inputs (e2e leg) and their device-resident copies (value leg)
+    c_host = torch.rand(N, 3, S, S, generator=g).pin_memory()
+    s_host = torch.rand(N, 3, S, S, generator=g).pin_memory()
+    c_dev, s_dev = c_host.to(dev), s_host.to(dev)
+    out_dev = torch.empty(N, 3, S, S, device=dev)
+    out_host = torch.empty(N, 3, S, S).pin_memory()
+
+    def step_resident():
+        eng.stylize(c_dev, s_dev, alpha=1.0, out=out_dev)
+
+    def step_e2e():
+        c = c_host.to(dev, non_blocking=True)
+        s = s_host.to(dev, non_blocking=True)
+        eng.stylize(c, s, alpha=1.0, out=out_dev)
+        out_host.copy_(out_dev, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    finite = bool(torch.isfinite(out_dev).all().item())
+
+    value = world * N * args.steps / (ms * 1e-3)
+    e2e = world * N * args.steps / (ms_e2e * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 4: batch stylisation inference, VGG-19 relu4_1 -> AdaIN -> "
+                                   f"mirrored decoder forward at {S}x{S}, alpha=1.0, {N} content/style pairs per GPU "
+                                   "per step, batch-sharded, no collective",
+                       "batch_per_gpu": N, "global_batch": N * world, "size": S,
+                       "parallelism": f"shard{world}", "weights": "random-init (seeded) + bias calibration",
+                       "l2": "inputs and activations per step (>1 GB) exceed the 126 MB L2; no flush needed",
+                       "output_finite": finite},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * c_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": eng.launches_per_stylize(1) * args.steps,
+            "clocks": clk.summary()}
+
+    if rank == 0:
+        pk = peaks()
+        rows = time_layers(eng, N, S)
+        conv_ms = sum(r["ms"] * r["per_step"] for r in rows)
+        conv_flops = sum(r["flops"] * r["per_step"] for r in rows)
+        n_launch = sum(r["per_step"] for r in rows)
+        ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, 24 launches/step)",
+                            "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                            "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                            "flops_per_launch_avg": conv_flops / n_launch,
+                            "ms_per_launch_avg": conv_ms / n_launch,
+                            "share_of_step": conv_ms / (ms / args.steps),
+                            "whole_step_tflops": flops_per_image(S) * N / (ms / args.steps * 1e-3) / 1e12}
+        ab, ams = time_adain_k1(N)
+        gbs = ab / (ams * 1e-3) / 1e9
+        line["adain_roofline"] = {"bound": "hbm", "kernel": "adain_cached_kernel (K1, NCHW fp32, (N,512,64,64))",
+                                  "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                  "frac": gbs / pk["hbm_gbs"], "bytes_per_launch": ab, "ms_per_launch": ams,
+                                  "traffic": None, "peak_source": pk["source"]}
+        if args.layers_out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
+            json.dump(rows, open(args.layers_out, "w"), indent=1)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(S, args.cpu_sample or 8)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

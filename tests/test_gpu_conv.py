@@ -1,0 +1,167 @@
+"""K2 parity: tcgen05 implicit-GEMM conv (and the CUDA-core kernels) vs the CPU oracle arithmetic
+(torch fp32 conv on bf16-rounded operands = what models.py:186-240 / 598-628 compute, at the
+storage precision of the native layout).  Tolerance: one bf16 ulp (2^-8 relative) on outputs that
+sit on a rounding boundary, i.e. rtol 8e-3 elementwise and < 2e-3 relative L2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import bf16r, oracle_conv_native, native_to_padded_nchw, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(N, H, W, cin, cout, relu, epi, halo_reflect, impl, seed=0, with_tap=None):
+    from arbitrarystyletransfer_b200 import _lib as L, engine as E
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(N, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    pad_mode = "reflect" if halo_reflect else "zeros"
+    exp, pre, post = oracle_conv_native(x, w, b, relu, epi, pad_mode)
+    dev = "cuda"
+    xin = E.nchw_to_native(x.to(dev), reflect=halo_reflect)
+    wpk = E.pack_conv_weight(w.to(dev))
+    Ho, Wo = (H // 2, W // 2) if epi == 1 else ((2 * H, 2 * W) if epi == 2 else (H, W))
+    out = torch.full((N, Ho + 2, Wo + 2, cout), 7.0, device=dev, dtype=torch.bfloat16)
+    tap = None
+    if with_tap is not None:
+        tap = torch.full((N, cout, H, W), -99.0, device=dev, dtype=torch.float32)
+    E.conv3x3(xin, wpk, b.to(dev), out, N=N, H=H, W=W, cin=cin, cout=cout, relu=relu, epilogue=epi,
+              halo=L.HALO_REFLECT if halo_reflect else L.HALO_KEEP, impl=impl, tap=tap,
+              tap_prerelu=bool(with_tap == "pre"))
+    torch.cuda.synchronize()
+    got = native_to_padded_nchw(out).cpu()
+    inner = got[:, :, 1:-1, 1:-1]
+    assert rel_err(inner, exp) < 2e-3, f"interior rel err {rel_err(inner, exp)}"
+    torch.testing.assert_close(inner, exp, rtol=8e-3, atol=2e-3)
+    if halo_reflect:
+        torch.testing.assert_close(got, F.pad(exp, (1, 1, 1, 1), mode="reflect"), rtol=8e-3, atol=2e-3)
+    else:  # halo untouched
+        assert (got[:, :, 0, :] == 7.0).all() and (got[:, :, :, -1] == 7.0).all()
+    if tap is not None:
+        ref = pre if with_tap == "pre" else post
+        torch.testing.assert_close(tap.cpu(), ref, rtol=2e-3, atol=2e-3)
+    return inner, exp
+
+
+SHAPES_TC = [
+    # N, H, W, cin, cout
+    (1, 16, 16, 64, 64),
+    (2, 8, 16, 64, 128),
+    (1, 32, 32, 128, 256),
+    (1, 24, 40, 64, 64),      # partial tiles in both directions
+    (1, 12, 20, 128, 128),    # 96/160-pixel images at /8 (conf.py:4 img_sizes)
+    (1, 16, 32, 256, 512),
+    (3, 10, 18, 64, 256),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES_TC)
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_tc_conv_zero_pad(shape, epi):
+    from arbitrarystyletransfer_b200 import _lib as L
+    N, H, W, cin, cout = shape
+    _run(N, H, W, cin, cout, True, epi, False, L.CONV_TC, seed=epi)
+
+
+@pytest.mark.parametrize("shape", SHAPES_TC[:5])
+@pytest.mark.parametrize("epi", [0, 2])
+def test_tc_conv_reflect_halo(shape, epi):
+    from arbitrarystyletransfer_b200 import _lib as L
+    N, H, W, cin, cout = shape
+    _run(N, H, W, cin, cout, True, epi, True, L.CONV_TC, seed=3 + epi)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_tc_conv_forced_n_block(bn):
+    _run(2, 16, 32, 128, 256, True, 0, True, bn, seed=11)
+
+
+def test_tc_conv_no_relu_and_taps():
+    from arbitrarystyletransfer_b200 import _lib as L
+    _run(1, 16, 16, 64, 64, False, 0, False, L.CONV_TC, seed=5, with_tap="pre")
+    _run(1, 16, 32, 64, 128, True, 1, False, L.CONV_TC, seed=6, with_tap="pre")
+    _run(1, 16, 16, 128, 64, True, 0, False, L.CONV_TC, seed=7, with_tap="post")
+
+
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_direct_conv(epi):
+    from arbitrarystyletransfer_b200 import _lib as L
+    _run(1, 6, 10, 16, 24, True, epi, epi != 1, L.CONV_DIRECT, seed=20 + epi)
+    _run(2, 8, 8, 64, 64, True, epi, False, L.CONV_DIRECT, seed=30 + epi, with_tap="pre")
+
+
+def test_tc_matches_direct_bitwise_mostly():
+    """Same operands, same fp32 accumulate: the two device kernels agree to fp32 re-association."""
+    from arbitrarystyletransfer_b200 import _lib as L
+    a, _ = _run(1, 16, 16, 64, 64, True, 0, False, L.CONV_TC, seed=9)
+    b, _ = _run(1, 16, 16, 64, 64, True, 0, False, L.CONV_DIRECT, seed=9)
+    assert (a != b).float().mean().item() < 0.02   # only rounding-boundary flips
+
+
+def test_many_tiles_persistent_loop():
+    """More tiles than SMs and > 2 tiles per CTA: exercises stage / accumulator phase wrap."""
+    from arbitrarystyletransfer_b200 import _lib as L
+    _run(4, 64, 96, 64, 64, True, 1, False, L.CONV_TC, seed=12)
+    _run(2, 64, 64, 128, 128, True, 0, True, L.CONV_TC, seed=13)
+
+
+def test_first_and_last_layers():
+    from arbitrarystyletransfer_b200 import _lib as L, engine as E
+    from oracle import restate as R
+    lib = L.load()
+    g = torch.Generator().manual_seed(1)
+    N, H, W = 2, 20, 28
+    img = torch.rand(N, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(64, generator=g) * 0.1
+    mean = torch.tensor(R.IMAGENET_MEAN).view(-1, 1, 1)
+    std = torch.tensor(R.IMAGENET_STD).view(-1, 1, 1)
+    pre = F.conv2d((img - mean) / std, w, b, padding=1)
+    out = torch.zeros(N, H + 2, W + 2, 64, device="cuda", dtype=torch.bfloat16)
+    tap = torch.empty(N, 64, H, W, device="cuda")
+    L.check(lib.ast_conv3x3_first(img.cuda().data_ptr(), w.cuda().data_ptr(), b.cuda().data_ptr(),
+                                  L.float_array(R.IMAGENET_MEAN), L.float_array(R.IMAGENET_STD),
+                                  out.data_ptr(), tap.data_ptr(), 1, N, H, W, 64, L.stream_ptr()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(tap.cpu(), pre, rtol=1e-4, atol=1e-4)
+    got = native_to_padded_nchw(out).cpu()
+    torch.testing.assert_close(got[:, :, 1:-1, 1:-1], bf16r(F.relu(pre)), rtol=8e-3, atol=1e-3)
+    assert (got[:, :, 0] == 0).all() and (got[:, :, :, 0] == 0).all()
+    # last layer: reflect-padded native input -> NCHW fp32
+    x = bf16r(torch.randn(N, 64, H, W, generator=g))
+    wl = torch.randn(3, 64, 3, 3, generator=g) * 0.05
+    bl = torch.randn(3, generator=g) * 0.1
+    exp = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), wl, bl)
+    xin = E.nchw_to_native(x.cuda(), reflect=True)
+    o = torch.empty(N, 3, H, W, device="cuda")
+    L.check(lib.ast_conv3x3_last(xin.data_ptr(), wl.cuda().data_ptr(), bl.cuda().data_ptr(),
+                                 o.data_ptr(), N, H, W, 64, 3, 0, L.stream_ptr()))
+    torch.testing.assert_close(o.cpu(), exp, rtol=1e-4, atol=1e-4)
+    L.check(lib.ast_conv3x3_last(xin.data_ptr(), wl.cuda().data_ptr(), bl.cuda().data_ptr(),
+                                 o.data_ptr(), N, H, W, 64, 3, 1, L.stream_ptr()))
+    torch.testing.assert_close(o.cpu(), exp.clamp(0, 1), rtol=1e-4, atol=1e-4)
+
+
+def test_layout_roundtrip():
+    from arbitrarystyletransfer_b200 import engine as E
+    g = torch.Generator().manual_seed(2)
+    x = bf16r(torch.randn(2, 40, 9, 13, generator=g))
+    for reflect in (False, True):
+        t = E.nchw_to_native(x.cuda(), reflect=reflect)
+        assert torch.equal(E.native_to_nchw(t).cpu(), x)
+        full = native_to_padded_nchw(t).cpu()
+        ref = F.pad(x, (1, 1, 1, 1), mode="reflect" if reflect else "constant")
+        assert torch.equal(full, ref)
+
+
+def test_conv_argument_errors():
+    from arbitrarystyletransfer_b200 import _lib as L, engine as E
+    x = torch.zeros(1, 10, 10, 48, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(9, 64, 48, device="cuda", dtype=torch.bfloat16)
+    o = torch.zeros(1, 10, 10, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(L.AstError):  # Cin % 64 != 0 cannot take the tensor-core path
+        E.conv3x3(x, w, None, o, N=1, H=8, W=8, cin=48, cout=64, impl=L.CONV_TC)
+    with pytest.raises(L.AstError):  # reflect halo of a 1-pixel output
+        E.conv3x3(x, w, None, o, N=1, H=1, W=8, cin=48, cout=64, halo=L.HALO_REFLECT, impl=L.CONV_DIRECT)

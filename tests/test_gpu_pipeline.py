@@ -1,0 +1,124 @@
+"""End-to-end parity of the classic VGG relu4_1 -> AdaIN -> decoder path (configs 1, 4-shaped, 5-shaped)
+against golden outputs of the genuine reference and the CPU oracle.  north_star tolerance for the
+bf16 pipeline: relative L2 <= 1e-2 and PSNR >= 40 dB (range = max(ref) - min(ref))."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def weights():
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+    return vw, vb, dw, db
+
+
+@pytest.fixture(scope="module")
+def engine(weights):
+    from arbitrarystyletransfer_b200.engine import StyleTransferEngine
+    vw, vb, dw, db = weights
+    return StyleTransferEngine(vw[:9], vb[:9], dw, db, device="cuda")
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def test_stylize_64_vs_reference_golden(engine, golden_networks):
+    g = golden_networks
+    c, s = R.rand_image(1, 64, 101).cuda(), R.rand_image(1, 64, 102).cuda()
+    from arbitrarystyletransfer_b200 import engine as E
+    fc = E.native_to_nchw(engine.encode(c)).cpu()
+    assert rel_l2(fc, T(g["s64_fc"])) < 1e-2
+    img = engine.stylize(c, s).cpu()
+    ref = T(g["s64_img"])
+    assert torch.isfinite(img).all()
+    assert rel_l2(img, ref) < 1e-2
+    assert R.psnr(img, ref) >= 40.0
+
+
+def test_config1_256_vs_reference_golden(engine, golden_networks):
+    g = golden_networks
+    c, s = R.rand_image(1, 256, 101).cuda(), R.rand_image(1, 256, 102).cuda()
+    img = engine.stylize(c, s, alpha=1.0).cpu()
+    crop, sub = T(g["cfg1_img_crop"]), T(g["cfg1_img_sub4"])
+    assert R.psnr(img[:, :, 96:160, 96:160], crop) >= 40.0
+    assert R.psnr(img[:, :, ::4, ::4], sub) >= 40.0
+    assert rel_l2(img[:, :, ::4, ::4], sub) < 1e-2
+    st = g["cfg1_img_stats"]
+    assert img.mean().item() == pytest.approx(st[0], abs=2e-3)
+    assert img.std().item() == pytest.approx(st[1], rel=2e-2)
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.5])
+def test_batch_and_alpha_vs_oracle(engine, weights, alpha):
+    vw, vb, dw, db = weights
+    c, s = R.rand_image(3, 96, 401), R.rand_image(3, 96, 402)     # ragged: 96/8 = 12 (partial tiles)
+    with torch.no_grad():
+        ref = R.stylize(c, s, vw, vb, dw, db, alpha=alpha)
+    img = engine.stylize(c.cuda(), s.cuda(), alpha=alpha).cpu()
+    assert R.psnr(img, ref) >= 40.0 and rel_l2(img, ref) < 1e-2
+
+
+def test_multi_style_interpolation_vs_oracle(engine, weights):
+    vw, vb, dw, db = weights
+    c = R.rand_image(1, 128, 501)
+    styles = [R.rand_image(1, 128, 502 + k) for k in range(4)]
+    w = [0.4, 0.3, 0.2, 0.1]
+    with torch.no_grad():
+        ref = R.stylize(c, styles, vw, vb, dw, db, alpha=0.6, style_weights=w)
+    img = engine.stylize(c.cuda(), [s.cuda() for s in styles], alpha=0.6, style_weights=w).cpu()
+    assert R.psnr(img, ref) >= 40.0 and rel_l2(img, ref) < 1e-2
+
+
+def test_size_independent_properties_512(engine):
+    """Full-size (512x512) checks that need no oracle run: batch-order equivariance, alpha = 0
+    reproduces decoder(relu4_1(content)) regardless of the style, determinism."""
+    c, s = R.rand_image(2, 512, 11).cuda(), R.rand_image(2, 512, 12).cuda()
+    a = engine.stylize(c, s).clone()
+    b = engine.stylize(c.flip(0), s.flip(0)).flip(0)
+    assert torch.equal(a, b)
+    assert torch.equal(a, engine.stylize(c, s))
+    z1 = engine.stylize(c, s, alpha=0.0).clone()
+    z2 = engine.stylize(c, s.flip(0), alpha=0.0)
+    torch.testing.assert_close(z1, z2, rtol=0, atol=0)
+
+
+def test_modules_drop_in(weights, golden_networks):
+    """The nn.Module surface: state-dict keys of the reference, taps by name, NCHW fp32 in/out."""
+    from arbitrarystyletransfer_b200 import models as M
+    vw, vb, dw, db = weights
+    g = golden_networks
+    enc = M.PretrainedEncoder().cuda()
+    assert sorted(enc.state_dict().keys()) == list(g["vgg_state_keys"])
+    dec = M.ClassicDecoder().cuda()
+    assert sorted(dec.state_dict().keys()) == list(g["dec_state_keys"])
+    with torch.no_grad():
+        for conv, w, b in zip(enc._convs(), vw, vb):
+            conv.weight.copy_(w); conv.bias.copy_(b)
+        for conv, w, b in zip(dec._convs(), dw, db):
+            conv.weight.copy_(w); conv.bias.copy_(b)
+        taps = enc(T(g["vgg_x32"]).cuda())
+    assert len(taps) == 6
+    for i, t in enumerate(taps):
+        ref = T(g[f"vgg_x32_tap{i}"])
+        assert t.shape == ref.shape and t.dtype == torch.float32
+        assert rel_l2(t.cpu(), ref) < 2e-2, f"tap {i}"
+    with torch.no_grad():
+        out = dec(T(g["dec_in"]).cuda()).cpu()
+    assert R.psnr(out, T(g["dec_out"])) >= 40.0
+    # full net through the module API
+    enc9 = M.PretrainedEncoder(['relu_9']).cuda()
+    enc9.load_state_dict(enc.state_dict())
+    net = M.StyleTransferNet(enc9, dec)
+    img = net(R.rand_image(1, 64, 101).cuda(), R.rand_image(1, 64, 102).cuda()).cpu()
+    assert R.psnr(img, T(g["s64_img"])) >= 40.0
