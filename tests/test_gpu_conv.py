@@ -121,7 +121,8 @@ def test_first_and_last_layers():
     pre = F.conv2d((img - mean) / std, w, b, padding=1)
     out = torch.zeros(N, H + 2, W + 2, 64, device="cuda", dtype=torch.bfloat16)
     tap = torch.empty(N, 64, H, W, device="cuda")
-    L.check(lib.ast_conv3x3_first(img.cuda().data_ptr(), w.cuda().data_ptr(), b.cuda().data_ptr(),
+    img_d, w_d, b_d = img.cuda(), w.cuda(), b.cuda()   # keep the device tensors alive
+    L.check(lib.ast_conv3x3_first(img_d.data_ptr(), w_d.data_ptr(), b_d.data_ptr(),
                                   L.float_array(R.IMAGENET_MEAN), L.float_array(R.IMAGENET_STD),
                                   out.data_ptr(), tap.data_ptr(), 1, N, H, W, 64, L.stream_ptr()))
     torch.cuda.synchronize()
@@ -136,10 +137,11 @@ def test_first_and_last_layers():
     exp = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), wl, bl)
     xin = E.nchw_to_native(x.cuda(), reflect=True)
     o = torch.empty(N, 3, H, W, device="cuda")
-    L.check(lib.ast_conv3x3_last(xin.data_ptr(), wl.cuda().data_ptr(), bl.cuda().data_ptr(),
+    wl_d, bl_d = wl.cuda(), bl.cuda()
+    L.check(lib.ast_conv3x3_last(xin.data_ptr(), wl_d.data_ptr(), bl_d.data_ptr(),
                                  o.data_ptr(), N, H, W, 64, 3, 0, L.stream_ptr()))
     torch.testing.assert_close(o.cpu(), exp, rtol=1e-4, atol=1e-4)
-    L.check(lib.ast_conv3x3_last(xin.data_ptr(), wl.cuda().data_ptr(), bl.cuda().data_ptr(),
+    L.check(lib.ast_conv3x3_last(xin.data_ptr(), wl_d.data_ptr(), bl_d.data_ptr(),
                                  o.data_ptr(), N, H, W, 64, 3, 1, L.stream_ptr()))
     torch.testing.assert_close(o.cpu(), exp.clamp(0, 1), rtol=1e-4, atol=1e-4)
 
