@@ -51,9 +51,9 @@ PROTOTYPES = {
     "ast_gram_fwd": (_i, [_vp, _vp, _i, _i, _i64, _vp]),
     "ast_gram_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),
     "ast_conv3x3_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
-    "ast_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "ast_conv3x3_first": (_i, [_vp, _vp, _vp, _fp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "ast_conv3x3_last": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_conv3x3_first": (_i, [_vp, _vp, _vp, _fp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_conv3x3_last": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_nchw_to_native": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_native_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ast_adain_native_ws_bytes": (_sz, [_i, _i, _i]),

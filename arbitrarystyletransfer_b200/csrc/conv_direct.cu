@@ -11,21 +11,27 @@ namespace tc {
 bool tc_supported(const ast_conv_desc* d);
 int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const float* bias, void* out,
                float* tap, cudaStream_t s);
+int conv3x3_first_tc(const float* img, const float* w, const float* bias, const float* mean,
+                     const float* std_, void* out, float* tap, int tap_prerelu, int N, int H, int W,
+                     cudaStream_t s);
+int conv3x3_last_tc(const void* in, const void* wpk16, const float* bias, float* out, int N, int H,
+                    int W, int Cin, int Cout, int clamp01, cudaStream_t s);
 }  // namespace tc
 
 // ---- weight packing: OIHW fp32 -> bf16 [9][Cout][Cin] -------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o,
-                                   int Cout, int Cin, int flip) {
+                                   int Cout, int Cin, int flip, int rows) {
   // flip: out[t][ci][co] = w[co][ci][8 - t]  (a conv from Cout channels to Cin: the data gradient)
-  const int64_t total = (int64_t)9 * Cout * Cin;
+  // rows >= Cout (no flip): zero-padded output-channel rows
+  const int64_t total = (int64_t)9 * rows * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int t = (int)(i / ((int64_t)Cout * Cin));
-    int64_t r = i - (int64_t)t * Cout * Cin;
+    int t = (int)(i / ((int64_t)rows * Cin));
+    int64_t r = i - (int64_t)t * rows * Cin;
     float v;
     if (!flip) {
       int co = (int)(r / Cin), ci = (int)(r % Cin);
-      v = w[((int64_t)co * Cin + ci) * 9 + t];
+      v = co < Cout ? w[((int64_t)co * Cin + ci) * 9 + t] : 0.f;
     } else {
       int ci = (int)(r / Cout), co = (int)(r % Cout);
       v = w[((int64_t)co * Cin + ci) * 9 + (8 - t)];
@@ -249,13 +255,15 @@ conv3x3_last_kernel(const __nv_bfloat16* __restrict__ in, const float* __restric
 using namespace ast;
 
 extern "C" int ast_pack_conv_weight(const float* w_oihw, void* wpk, int Cout, int Cin, int flip,
-                                    void* stream) {
+                                    int cout_pad, void* stream) {
   if (!w_oihw || !wpk || Cout <= 0 || Cin <= 0) return AST_E_BADARG;
-  const int64_t total = (int64_t)9 * Cout * Cin;
+  if (cout_pad != 0 && (flip || cout_pad < Cout)) return AST_E_BADARG;
+  const int rows = cout_pad ? cout_pad : Cout;
+  const int64_t total = (int64_t)9 * rows * Cin;
   int64_t nb = (total + 255) / 256;
   if (nb > 148 * 8) nb = 148 * 8;
   pack_weight_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
-      w_oihw, reinterpret_cast<__nv_bfloat16*>(wpk), Cout, Cin, flip);
+      w_oihw, reinterpret_cast<__nv_bfloat16*>(wpk), Cout, Cin, flip, rows);
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -289,10 +297,15 @@ extern "C" int ast_conv3x3_fwd(const ast_conv_desc* d, const void* in, const voi
 
 extern "C" int ast_conv3x3_first(const float* img, const float* w, const float* bias,
                                  const float* mean, const float* std_, void* out, float* tap,
-                                 int tap_prerelu, int N, int H, int W, int Cout, void* stream) {
+                                 int tap_prerelu, int N, int H, int W, int Cout, int impl,
+                                 void* stream) {
   if (!img || !w || (!out && !tap) || N <= 0 || H <= 0 || W <= 0 || Cout <= 0) return AST_E_BADARG;
   if (Cout % 8 != 0) return AST_E_SHAPE;
   if (out && !aligned16(out)) return AST_E_ALIGN;
+  if (impl == AST_CONV_TC && Cout != 64) return AST_E_SHAPE;
+  if (impl != AST_CONV_DIRECT && Cout == 64 && (!bias || aligned16(bias)))
+    return tc::conv3x3_first_tc(img, w, bias, mean, std_, out, tap, tap_prerelu, N, H, W,
+                                (cudaStream_t)stream);
   float3 m = make_float3(0.f, 0.f, 0.f), rs = make_float3(1.f, 1.f, 1.f);
   const int normalise = (mean && std_) ? 1 : 0;
   if (normalise) {
@@ -311,9 +324,14 @@ extern "C" int ast_conv3x3_first(const float* img, const float* w, const float* 
   return 0;
 }
 
-extern "C" int ast_conv3x3_last(const void* in, const float* w, const float* bias, float* out, int N,
-                                int H, int W, int Cin, int Cout, int clamp01, void* stream) {
-  if (!in || !w || !out || N <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+extern "C" int ast_conv3x3_last(const void* in, const float* w, const void* wpk16, const float* bias,
+                                float* out, int N, int H, int W, int Cin, int Cout, int clamp01,
+                                int impl, void* stream) {
+  if (!in || (!w && !wpk16) || !out || N <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  if (impl == AST_CONV_TC && (!wpk16 || Cin % 64 != 0)) return AST_E_SHAPE;
+  if (impl != AST_CONV_DIRECT && wpk16 && Cin % 64 == 0 && Cout <= 16)
+    return tc::conv3x3_last_tc(in, wpk16, bias, out, N, H, W, Cin, Cout, clamp01, (cudaStream_t)stream);
+  if (!w) return AST_E_BADARG;
   if (Cout < 1 || Cout > kLastMaxCout) return AST_E_SHAPE;
   if (!aligned16(in)) return AST_E_ALIGN;
   const int64_t npix = (int64_t)N * H * W;

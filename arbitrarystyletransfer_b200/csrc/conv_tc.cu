@@ -60,8 +60,8 @@ template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * KBLK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // multiple of 1024
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);  // 192 KB of operands
-  static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);  // <= 192 KB of operands
+  static constexpr int TMEM_COLS = 2 * BN;  // 32 / 128 / 256 / 512: powers of two >= 32
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
 };
@@ -74,7 +74,12 @@ struct ConvParams {
   const float* bias;
   __nv_bfloat16* out;
   float* tap;
+  float* out_nchw;   // EPI_NCHW32 only: fp32 [N][cout_real][H][W]
+  int cout_real;     // EPI_NCHW32 only: channels actually stored (<= BN)
+  int clamp01;       // EPI_NCHW32 only: Hardtanh(0,1) (models.py:304, 315)
 };
+
+constexpr int EPI_NCHW32 = 3;  // internal: last decoder layer, fp32 NCHW image out
 
 // Output coordinates (unpadded grid, -1 and Xo are the halo) that conv coordinate x feeds.
 template <int EPI>
@@ -96,6 +101,122 @@ __device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)
     }
   }
   return n;
+}
+
+
+// Epilogue warps (4 per CTA; warp e may touch TMEM lanes [32e, 32e+32) = tile rows 2e, 2e+1):
+// tcgen05.ld -> +bias -> (tap) -> ReLU -> (tap) -> bf16 -> {plain | 2x2 max-pool | nearest x2} store
+// with the optional reflection halo, or the fp32 NCHW image for the last decoder layer.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int e, int lane,
+                                              uint32_t tfull_bar0, uint32_t tempty_bar0) {
+  constexpr int CH = BN >= 32 ? 32 : 16;  // columns per tcgen05.ld
+  const int hl = 2 * e + (lane >> 4);
+  const int wl = lane & 15;
+  const bool reflect = p.halo == AST_HALO_REFLECT;
+  int as = 0;
+  uint32_t aphase = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int t = tile;
+    const int nb = t % p.n_blocks; t /= p.n_blocks;
+    const int twi = t % p.tiles_w; t /= p.tiles_w;
+    const int thi = t % p.tiles_h;
+    const int n = t / p.tiles_h;
+    const int h = thi * TILE_H + hl, w = twi * TILE_W + wl;
+    const bool in_img = (h < p.H) && (w < p.W);
+
+    int rows[4], cols[4], nr = 0, nc = 0;
+    bool owner;
+    if (EPI == AST_EPI_POOL2) {
+      owner = ((hl & 1) == 0) && ((wl & 1) == 0) && ((h >> 1) < p.Ho) && ((w >> 1) < p.Wo);
+    } else {
+      owner = in_img;
+    }
+    if (owner && EPI != EPI_NCHW32) {
+      nr = out_targets<EPI>(h, p.Ho, reflect, rows);
+      nc = out_targets<EPI>(w, p.Wo, reflect, cols);
+    }
+
+    mbar_wait(tfull_bar0 + 8u * as, aphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / CH; ++chunk) {
+      uint32_t v[CH];
+      const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN + chunk * CH);
+      tmem_ld_cols(taddr, v);
+      tmem_ld_wait();
+      const int ch0 = nb * BN + chunk * CH;
+      if constexpr (EPI == EPI_NCHW32) {
+        if (in_img) {
+          for (int c = 0; c < p.cout_real; ++c) {
+            float val = __uint_as_float(v[c]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+            if (p.relu) val = fmaxf(val, 0.f);
+            if (p.clamp01) val = fminf(fmaxf(val, 0.f), 1.f);
+            p.out_nchw[(((int64_t)n * p.cout_real + c) * p.H + h) * p.W + w] = val;
+          }
+        }
+      } else {
+        float f[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i += 4) {
+          float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[i + 0] = __uint_as_float(v[i + 0]) + b.x;
+          f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
+          f[i + 2] = __uint_as_float(v[i + 2]) + b.z;
+          f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+        }
+        if (p.tap && p.tap_prerelu && in_img) {
+          float* tp = p.tap + (((int64_t)n * p.Cout + ch0) * p.H + h) * p.W + w;
+#pragma unroll
+          for (int i = 0; i < CH; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.tap && !p.tap_prerelu && in_img) {
+          float* tp = p.tap + (((int64_t)n * p.Cout + ch0) * p.H + h) * p.W + w;
+#pragma unroll
+          for (int i = 0; i < CH; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
+        }
+        uint32_t pk[CH / 2];
+#pragma unroll
+        for (int i = 0; i < CH / 2; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+        if (EPI == AST_EPI_POOL2) {
+          // 2x2 max: partner along w is lane^1, along h is lane^16 (tile rows are 16 wide).
+          // max commutes with the (monotonic) bf16 rounding, so pool the packed values.
+#pragma unroll
+          for (int i = 0; i < CH / 2; ++i) {
+            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+            uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+            a = __hmax2_nan(a, *reinterpret_cast<__nv_bfloat162*>(&o1));
+            uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
+            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, 16);
+            a = __hmax2_nan(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
+            pk[i] = *reinterpret_cast<uint32_t*>(&a);
+          }
+        }
+        if (p.out) {
+          for (int ri = 0; ri < nr; ++ri) {
+            for (int ci = 0; ci < nc; ++ci) {
+              __nv_bfloat16* o = p.out +
+                  (((int64_t)n * (p.Ho + 2) + (rows[ri] + 1)) * (p.Wo + 2) + (cols[ci] + 1)) * p.Cout + ch0;
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+              for (int q = 0; q < CH / 8; ++q)
+                o4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar0 + 8u * as);
+    as ^= 1;
+    if (as == 0) aphase ^= 1u;
+  }
 }
 
 template <int BN, int EPI>
@@ -202,103 +323,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int e = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32e, 32e+32)
-    const int hl = 2 * e + (lane >> 4);
-    const int wl = lane & 15;
-    const bool reflect = p.halo == AST_HALO_REFLECT;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int nb = t % p.n_blocks; t /= p.n_blocks;
-      const int twi = t % p.tiles_w; t /= p.tiles_w;
-      const int thi = t % p.tiles_h;
-      const int n = t / p.tiles_h;
-      const int h = thi * TILE_H + hl, w = twi * TILE_W + wl;
-      const bool in_img = (h < p.H) && (w < p.W);
-
-      int rows[4], cols[4], nr = 0, nc = 0;
-      bool owner;
-      if (EPI == AST_EPI_POOL2) {
-        owner = ((hl & 1) == 0) && ((wl & 1) == 0) && ((h >> 1) < p.Ho) && ((w >> 1) < p.Wo);
-      } else {
-        owner = in_img;
-      }
-      if (owner) {
-        nr = out_targets<EPI>(h, p.Ho, reflect, rows);
-        nc = out_targets<EPI>(w, p.Wo, reflect, cols);
-      }
-
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN + chunk * 32);
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_wait();
-        const int ch0 = nb * BN + chunk * 32;
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-          f[i + 0] = __uint_as_float(v[i + 0]) + b.x;
-          f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
-          f[i + 2] = __uint_as_float(v[i + 2]) + b.z;
-          f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
-        }
-        if (p.tap && p.tap_prerelu && in_img) {
-          float* tp = p.tap + (((int64_t)n * p.Cout + ch0) * p.H + h) * p.W + w;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (p.tap && !p.tap_prerelu && in_img) {
-          float* tp = p.tap + (((int64_t)n * p.Cout + ch0) * p.H + h) * p.W + w;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
-        if (EPI == AST_EPI_POOL2) {
-          // 2x2 max: partner along w is lane^1, along h is lane^16 (tile rows are 16 wide).
-          // max commutes with the (monotonic) bf16 rounding, so pool the packed values.
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
-            uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
-            a = __hmax2_nan(a, *reinterpret_cast<__nv_bfloat162*>(&o1));
-            uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
-            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, 16);
-            a = __hmax2_nan(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
-            pk[i] = *reinterpret_cast<uint32_t*>(&a);
-          }
-        }
-        if (p.out) {
-          for (int ri = 0; ri < nr; ++ri) {
-            for (int ci = 0; ci < nc; ++ci) {
-              __nv_bfloat16* o = p.out +
-                  (((int64_t)n * (p.Ho + 2) + (rows[ri] + 1)) * (p.Wo + 2) + (cols[ci] + 1)) * p.Cout + ch0;
-              uint4* o4 = reinterpret_cast<uint4*>(o);
-              o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-              o4[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-              o4[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
-      as ^= 1;
-      if (as == 0) aphase ^= 1u;
-    }
+    epilogue_loop<BN, EPI>(p, tmem_base, warp - 4, lane, tfull_bar(0), tempty_bar(0));
   }
 
   tc_fence_before();
@@ -394,6 +419,232 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
     case 128: return launch_tc_epi<128>(d->epilogue, tmA, tmB, p, sm_count, s);
     default: return launch_tc_epi<64>(d->epilogue, tmA, tmB, p, sm_count, s);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// First VGG layer on the tensor cores: Normalization (models.py:129-131) + conv_1 (3 -> 64, zero pad)
+// + relu_1 straight from the reference's NCHW fp32 image.  K = 27 is padded to 32; the A tile
+// (128 pixels x 32) is built by four producer warps (one pixel per thread: gather 27 taps, normalise,
+// round to bf16) directly in the no-swizzle canonical UMMA layout, so the layer costs two MMAs per
+// tile and is bound by writing its 64-channel output.
+// Warps 0-3 = im2col producers, warps 4-7 = epilogue, warp 8 = TMEM allocator + MMA issuer.
+constexpr int kFirstThreads = 288;
+constexpr int F_K = 32, F_N = 64, F_STAGES = 4;
+constexpr int F_A_BYTES = TILE_M * F_K * 2;   // 8 KB
+constexpr int F_B_BYTES = F_N * F_K * 2;      // 4 KB
+constexpr int F_LBO = 128, F_SBO = (F_K / 8) * 128;
+
+struct FirstParams {
+  const float* img;   // [N][3][H][W]
+  const float* w;     // OIHW fp32 [64][3][3][3]
+  float mean[3], rstd[3];
+  int normalise;
+};
+
+__global__ void __launch_bounds__(kFirstThreads, 1)
+conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
+  __shared__ __align__(128) uint8_t s_a[F_STAGES][F_A_BYTES];
+  __shared__ __align__(128) uint8_t s_b[F_B_BYTES];
+  __shared__ __align__(8) uint64_t s_bar[2 * F_STAGES + 4];
+  __shared__ uint32_t s_tmem;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t bars = smem_u32(s_bar);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (F_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * F_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * F_STAGES + 2 + s); };
+
+  // weights -> bf16 [64][32] (k = ci*9 + kh*3 + kw, zero for k >= 27) in the canonical layout
+  for (int i = threadIdx.x; i < F_N * F_K; i += kFirstThreads) {
+    const int co = i / F_K, k = i % F_K;
+    const float v = k < 27 ? fp.w[co * 27 + k] : 0.f;
+    const uint32_t off = (uint32_t)(co >> 3) * F_SBO + (uint32_t)(k >> 3) * F_LBO + (co & 7) * 16 + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(s_b + off) = __float2bfloat16_rn(v);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < F_STAGES; ++s) {
+      mbar_init(full_bar(s), 4);   // one arrival per producer warp
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc<2 * F_N>(smem_u32(&s_tmem));
+  fence_proxy_async_smem();   // s_b was written with generic stores, the MMA reads it via the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+
+  if (warp < 4) {
+    // ===================== im2col producers =====================
+    const int r = threadIdx.x;           // tile row = pixel
+    const int hl = r >> 4, wl = r & 15;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int twi = t % p.tiles_w; t /= p.tiles_w;
+      const int thi = t % p.tiles_h;
+      const int n = t / p.tiles_h;
+      const int h = thi * TILE_H + hl, w = twi * TILE_W + wl;
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      if (h < p.H && w < p.W) {
+        float v[28];
+        v[27] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float* ip = fp.img + ((int64_t)n * 3 + ci) * p.H * p.W;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const int ih = h + kh - 1;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int iw = w + kw - 1;
+              float x = 0.f;   // zero padding applies to the NORMALISED image
+              if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                x = __ldg(ip + (int64_t)ih * p.W + iw);
+                if (fp.normalise) x = (x - fp.mean[ci]) * fp.rstd[ci];
+              }
+              v[ci * 9 + kh * 3 + kw] = x;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 14; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+      }
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      uint8_t* row = &s_a[stage][0] + (uint32_t)(r >> 3) * F_SBO + (r & 7) * 16;
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc)
+        *reinterpret_cast<uint4*>(row + kc * F_LBO) =
+            make_uint4(pk[4 * kc], pk[4 * kc + 1], pk[4 * kc + 2], pk[4 * kc + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
+      if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, F_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      const uint32_t b_addr = smem_u32(s_b);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(&s_a[stage][0]);
+#pragma unroll
+        for (int k = 0; k < F_K / 16; ++k) {
+          const uint64_t adesc = make_sdesc_k_noswizzle(a_addr + k * 2 * F_LBO, F_LBO, F_SBO);
+          const uint64_t bdesc = make_sdesc_k_noswizzle(b_addr + k * 2 * F_LBO, F_LBO, F_SBO);
+          umma_bf16(tmem_base + (uint32_t)(as * F_N), adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(as));
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 4-7) =====================
+    epilogue_loop<F_N, AST_EPI_PLAIN>(p, tmem_base, warp - 4, lane, tfull_bar(0), tempty_bar(0));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<2 * F_N>(tmem_base);
+  }
+}
+
+static int get_sm_count(int* out) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    AST_CUDA(cudaGetDevice(&dev));
+    AST_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  *out = sm_count;
+  return 0;
+}
+
+int conv3x3_first_tc(const float* img, const float* w, const float* bias, const float* mean,
+                     const float* std_, void* out, float* tap, int tap_prerelu, int N, int H, int W,
+                     cudaStream_t s) {
+  int sm_count = 0;
+  int r = get_sm_count(&sm_count);
+  if (r) return r;
+  FirstParams fp = {};
+  fp.img = img; fp.w = w; fp.normalise = (mean && std_) ? 1 : 0;
+  for (int i = 0; i < 3; ++i) {
+    fp.mean[i] = fp.normalise ? mean[i] : 0.f;
+    fp.rstd[i] = fp.normalise ? 1.f / std_[i] : 1.f;
+  }
+  ConvParams p = {};
+  p.N = N; p.H = H; p.W = W; p.Cin = 3; p.Cout = F_N; p.Ho = H; p.Wo = W;
+  p.relu = 1; p.halo = AST_HALO_KEEP; p.tap_prerelu = tap_prerelu;
+  p.tiles_w = (W + TILE_W - 1) / TILE_W;
+  p.tiles_h = (H + TILE_H - 1) / TILE_H;
+  p.n_blocks = 1;
+  const int64_t nt = (int64_t)N * p.tiles_h * p.tiles_w;
+  if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
+  p.num_tiles = (int)nt;
+  p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.tap = tap;
+  const int grid = p.num_tiles < 2 * sm_count ? p.num_tiles : 2 * sm_count;
+  conv3x3_first_tc_kernel<<<grid, kFirstThreads, 0, s>>>(fp, p);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+// Last decoder layer (Cin % 64 == 0, Cout <= 16): the implicit-GEMM kernel with a 16-wide N block
+// (weights zero-padded to 16 output channels) and the fp32 NCHW epilogue.
+int conv3x3_last_tc(const void* in, const void* wpk16, const float* bias, float* out, int N, int H,
+                    int W, int Cin, int Cout, int clamp01, cudaStream_t s) {
+  if (Cin % 64 != 0 || Cout > 16 || H < 1 || W < 1) return AST_E_SHAPE;
+  if (!aligned16(in) || !aligned16(wpk16)) return AST_E_ALIGN;
+  int sm_count = 0;
+  int r = get_sm_count(&sm_count);
+  if (r) return r;
+  ConvParams p = {};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = 16; p.Ho = H; p.Wo = W;
+  p.relu = 0; p.halo = AST_HALO_KEEP;
+  p.tiles_w = (W + TILE_W - 1) / TILE_W;
+  p.tiles_h = (H + TILE_H - 1) / TILE_H;
+  p.n_blocks = 1;
+  const int64_t nt = (int64_t)N * p.tiles_h * p.tiles_w;
+  if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
+  p.num_tiles = (int)nt;
+  p.bias = bias; p.out_nchw = out; p.cout_real = Cout; p.clamp01 = clamp01;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W + 2, (uint64_t)H + 2, (uint64_t)N};
+    const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)(W + 2) * Cin * 2,
+                             (uint64_t)(H + 2) * (W + 2) * Cin * 2};
+    const uint32_t box[4] = {KBLK, TILE_W, TILE_H, 1};
+    r = encode_bf16_map(&tmA, in, 4, dims, str, box);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)Cin, 16, 9};
+    const uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)16 * Cin * 2};
+    const uint32_t box[3] = {KBLK, 16, 1};
+    r = encode_bf16_map(&tmB, wpk16, 3, dims, str, box);
+    if (r) return r;
+  }
+  return launch_tc<16, EPI_NCHW32>(tmA, tmB, p, sm_count, s);
 }
 
 }  // namespace tc

@@ -52,15 +52,40 @@ def native_empty(N, H, W, Cc, device, zero_halo: bool):
     return torch.empty(shape, device=device, dtype=torch.bfloat16)
 
 
-def pack_conv_weight(w: torch.Tensor, flip: bool = False) -> torch.Tensor:
-    """OIHW fp32 -> bf16 [9][Cout][Cin] (or the data-gradient form when ``flip``)."""
+def pack_conv_weight(w: torch.Tensor, flip: bool = False, cout_pad: int = 0) -> torch.Tensor:
+    """OIHW fp32 -> bf16 [9][Cout][Cin] (or the data-gradient form when ``flip``; or zero-padded
+    to ``cout_pad`` output rows for the 16-wide last-layer kernel)."""
     lib = L.load()
     L.require_cuda(w)
     w = w.detach().float().contiguous()
     co, ci = w.shape[:2]
-    out = torch.empty((9, ci, co) if flip else (9, co, ci), device=w.device, dtype=torch.bfloat16)
-    L.check(lib.ast_pack_conv_weight(w.data_ptr(), out.data_ptr(), co, ci, int(flip),
+    rows = cout_pad or co
+    out = torch.empty((9, ci, co) if flip else (9, rows, ci), device=w.device, dtype=torch.bfloat16)
+    L.check(lib.ast_pack_conv_weight(w.data_ptr(), out.data_ptr(), co, ci, int(flip), int(cout_pad),
                                      L.stream_ptr(w.device)), "ast_pack_conv_weight")
+    return out
+
+
+def conv3x3_first(img, w, bias, out_native, tap=None, tap_prerelu=True, normalise=True,
+                  impl=L.CONV_AUTO):
+    """Normalization + conv_1 + relu_1 (models.py:129-131, 198-224) from NCHW fp32."""
+    lib = L.load()
+    N, _, H, W = img.shape
+    mean = L.float_array(IMAGENET_MEAN) if normalise else None
+    std = L.float_array(IMAGENET_STD) if normalise else None
+    L.check(lib.ast_conv3x3_first(img.data_ptr(), w.data_ptr(), L.ptr(bias), mean, std,
+                                  L.ptr(out_native), L.ptr(tap), int(tap_prerelu), N, H, W,
+                                  w.shape[0], impl, L.stream_ptr(img.device)), "ast_conv3x3_first")
+    return out_native
+
+
+def conv3x3_last(x_native, w, wpk16, bias, out, clamp01=False, impl=L.CONV_AUTO):
+    """Last decoder conv (models.py:626-627): native bf16 with reflection halo -> NCHW fp32."""
+    lib = L.load()
+    N, Cout, H, W = out.shape
+    L.check(lib.ast_conv3x3_last(x_native.data_ptr(), L.ptr(w), L.ptr(wpk16), L.ptr(bias),
+                                 out.data_ptr(), N, H, W, x_native.shape[3], Cout, int(clamp01), impl,
+                                 L.stream_ptr(out.device)), "ast_conv3x3_last")
     return out
 
 
@@ -129,6 +154,7 @@ class StyleTransferEngine:
         if self.device.type != "cuda":
             raise L.AstError("StyleTransferEngine needs a CUDA device (no CPU fallback)")
         self.impl = conv_impl
+        self.impl_edge = L.CONV_AUTO  # first / last layer: tensor cores unless set to CONV_DIRECT
         self.plan = vgg_layer_plan(9)
         dev = self.device
         self.vgg_w0 = vgg_w[0].detach().to(dev, torch.float32).contiguous()
@@ -137,8 +163,7 @@ class StyleTransferEngine:
         self.dec_b = [b.detach().to(dev, torch.float32).contiguous() for b in dec_b]
         self.dec_wpk = [pack_conv_weight(w.to(dev)) for w in dec_w[:8]] + [None]
         self.dec_w_last = dec_w[8].detach().to(dev, torch.float32).contiguous()
-        self._mean = L.float_array(IMAGENET_MEAN)
-        self._std = L.float_array(IMAGENET_STD)
+        self.dec_wpk_last = pack_conv_weight(self.dec_w_last, cout_pad=16)
         self.buf = _Buffers()
         self._ws = None
 
@@ -154,9 +179,7 @@ class StyleTransferEngine:
         dev = img.device
         st = L.stream_ptr(dev)
         x = self.buf.get("enc0", N, H, W, 64, dev, True)
-        L.check(lib.ast_conv3x3_first(img.data_ptr(), self.vgg_w0.data_ptr(),
-                                      self.vgg_b[0].data_ptr(), self._mean, self._std,
-                                      x.data_ptr(), None, 1, N, H, W, 64, st), "ast_conv3x3_first")
+        conv3x3_first(img, self.vgg_w0, self.vgg_b[0], x, impl=self.impl_edge)
         h, w = H, W
         for i in range(1, 9):
             cin, cout, pool = self.plan[i]
@@ -206,9 +229,8 @@ class StyleTransferEngine:
             x, h, w = y, ho, wo
         if out is None:
             out = torch.empty(N, 3, h, w, device=dev, dtype=torch.float32)
-        L.check(lib.ast_conv3x3_last(x.data_ptr(), self.dec_w_last.data_ptr(),
-                                     self.dec_b[8].data_ptr(), out.data_ptr(), N, h, w, 64, 3,
-                                     int(clamp01), L.stream_ptr(dev)), "ast_conv3x3_last")
+        conv3x3_last(x, self.dec_w_last, self.dec_wpk_last, self.dec_b[8], out, clamp01,
+                     impl=self.impl_edge)
         return out
 
     # ---- full path ------------------------------------------------------------------------------

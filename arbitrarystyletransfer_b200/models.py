@@ -91,12 +91,12 @@ class _WeightCache:
     def __init__(self):
         self._c = {}
 
-    def packed(self, p: torch.Tensor, flip=False):
-        key = (id(p), flip)
+    def packed(self, p: torch.Tensor, flip=False, cout_pad=0):
+        key = (id(p), flip, cout_pad)
         ver = (p.data_ptr(), p._version, str(p.device))
         hit = self._c.get(key)
         if hit is None or hit[0] != ver:
-            hit = (ver, E.pack_conv_weight(p, flip))
+            hit = (ver, E.pack_conv_weight(p, flip, cout_pad))
             self._c[key] = hit
         return hit[1]
 
@@ -169,11 +169,7 @@ class PretrainedEncoder(nn.Module):
             ho, wo = (h // 2, w // 2) if fuse_pool else (h, w)
             out = self._buf.get(f"v{ci}", N, ho, wo, cout, dev, True) if more else None
             if ci == 0:
-                mean, std = L.float_array(E.IMAGENET_MEAN), L.float_array(E.IMAGENET_STD)
-                L.check(lib.ast_conv3x3_first(x.data_ptr(), conv.weight.data_ptr(),
-                                              conv.bias.data_ptr(), mean, std, L.ptr(out),
-                                              L.ptr(tap), int(want_c), N, h, w, cout, st),
-                        "ast_conv3x3_first")
+                E.conv3x3_first(x, conv.weight, conv.bias, out, tap=tap, tap_prerelu=want_c)
                 if fuse_pool:
                     raise L.AstError("VGG-19 never pools right after conv_1")
             else:
@@ -241,9 +237,8 @@ class ClassicDecoder(nn.Sequential):
             cur, h, w = y, ho, wo
         out = torch.empty(N, 3, h, w, device=dev, dtype=torch.float32)
         last = convs[8]
-        L.check(lib.ast_conv3x3_last(cur.data_ptr(), last.weight.data_ptr(), last.bias.data_ptr(),
-                                     out.data_ptr(), N, h, w, 64, 3, int(self.exporting),
-                                     L.stream_ptr(dev)), "ast_conv3x3_last")
+        E.conv3x3_last(cur, last.weight, self._cache.packed(last.weight, cout_pad=16), last.bias, out,
+                       self.exporting)
         return out
 
 

@@ -126,6 +126,7 @@ int ast_gram_bwd(const float* x, const float* gg, float* gx, int B, int C, int64
 #define AST_CONV_AUTO   0 /* tcgen05 implicit GEMM when Cin%64==0 && Cout%64==0, else direct */
 #define AST_CONV_TC     1 /* force tcgen05 (AST_E_SHAPE if unsupported) */
 #define AST_CONV_DIRECT 2 /* CUDA-core direct kernel (odd shapes; on-device cross-check) */
+/* impl = 64, 128 or 256 forces the tcgen05 kernel with that N-block width (tuning / tests). */
 
 typedef struct ast_conv_desc {
   int N, H, W;        /* conv input = conv output spatial size (stride 1, 3x3, pad 1)      */
@@ -148,24 +149,30 @@ int ast_conv3x3_fwd(const ast_conv_desc* d, const void* in, const void* wpk, con
 
 /* OIHW fp32 [Cout][Cin][3][3] -> bf16 [9][Cout][Cin] (tap = kh*3+kw).
  * flip=1 additionally rotates the taps by 180 degrees and swaps the O/I roles, producing the
- * data-gradient weights: out is [9][Cin][Cout'] i.e. a conv from Cout channels to Cin. */
-int ast_pack_conv_weight(const float* w_oihw, void* wpk, int Cout, int Cin, int flip,
+ * data-gradient weights: out is [9][Cin][Cout'] i.e. a conv from Cout channels to Cin.
+ * cout_pad > Cout (flip must be 0) writes [9][cout_pad][Cin] with zero rows for co >= Cout: the
+ * 16-row form ast_conv3x3_last's tensor-core path consumes. */
+int ast_pack_conv_weight(const float* w_oihw, void* wpk, int Cout, int Cin, int flip, int cout_pad,
                          void* stream);
 
 /* First VGG layer: Normalization (models.py:129-131) + conv_1 (3->Cout, zero pad) + ReLU from
- * the reference's NCHW fp32 image straight into the native layout.
+ * the reference's NCHW fp32 image straight into the native layout.  Cout == 64 runs on the tensor
+ * cores (im2col A tile built in shared memory, K = 27 padded to 32) unless impl = AST_CONV_DIRECT.
  *   img : fp32 [N][3][H][W]; w : fp32 OIHW [Cout][3][3][3]; bias fp32 [Cout]
  *   mean/std : 3 host floats each (NULL = no normalisation)
  *   out : bf16 [N][H+2][W+2][Cout] (interior only); tap as in ast_conv3x3_fwd. */
 int ast_conv3x3_first(const float* img, const float* w, const float* bias, const float* mean,
                       const float* std_, void* out, float* tap, int tap_prerelu,
-                      int N, int H, int W, int Cout, void* stream);
+                      int N, int H, int W, int Cout, int impl, void* stream);
 
 /* Last decoder layer: reflect-padded native input -> NCHW fp32 image, no ReLU.
  *   in : bf16 [N][H+2][W+2][Cin]; w : fp32 OIHW [Cout][Cin][3][3]; out fp32 [N][Cout][H][W]
+ *   wpk16 : bf16 [9][16][Cin] from ast_pack_conv_weight(..., cout_pad = 16), or NULL.  With wpk16
+ *           and Cin % 64 == 0 the layer runs on the tensor cores (impl AUTO / TC); otherwise the
+ *           CUDA-core kernel reads `w` (Cin in {16, 32, 64}, Cout <= 4).
  *   clamp01 != 0 applies Hardtanh(0,1) (Decoder.last_act when exporting, models.py:304,315) */
-int ast_conv3x3_last(const void* in, const float* w, const float* bias, float* out,
-                     int N, int H, int W, int Cin, int Cout, int clamp01, void* stream);
+int ast_conv3x3_last(const void* in, const float* w, const void* wpk16, const float* bias, float* out,
+                     int N, int H, int W, int Cin, int Cout, int clamp01, int impl, void* stream);
 
 /* layout converters between the reference layout and the native one.
  * nchw fp32 [N][C][H][W] <-> bf16 [N][H+2][W+2][C]; `halo` as AST_HALO_*. */

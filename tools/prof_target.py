@@ -1,0 +1,24 @@
+"""Small, fixed workload for ncu: K1 AdaIN at the config-4 shape, then one stylise pass
+(batch 8, 512x512) = 9 + 9 encoder launches, native AdaIN, 9 decoder launches."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from arbitrarystyletransfer_b200 import functional as Fn
+import bench
+
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+c = torch.relu(torch.randn(32, 512, 64, 64, device=dev) * 3 + 1)
+s = torch.randn(32, 512, 64, 64, device=dev) * 2 + 3
+out = torch.empty_like(c)
+for _ in range(2):
+    Fn.adain_forward(c, [s], out=out)
+eng = bench.build_engine(dev)
+ci = torch.rand(N, 3, 512, 512, device=dev)
+si = torch.rand(N, 3, 512, 512, device=dev)
+for _ in range(2):
+    img = eng.stylize(ci, si)
+torch.cuda.synchronize()
+print("ok", float(img.mean()))
