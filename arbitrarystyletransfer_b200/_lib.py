@@ -19,7 +19,7 @@ MAX_STYLES = 8
 F_CANONICAL, F_BIASED, F_BF16 = 0x1, 0x2, 0x4
 EPI_PLAIN, EPI_POOL2, EPI_UP2 = 0, 1, 2
 HALO_KEEP, HALO_REFLECT = 0, 1
-CONV_AUTO, CONV_TC, CONV_DIRECT = 0, 1, 2
+CONV_AUTO, CONV_TC, CONV_DIRECT, CONV_TC_TAPBOX = 0, 1, 2, 3
 
 
 class AstError(RuntimeError):

@@ -106,7 +106,7 @@ __device__ __forceinline__ float std_from(const Moments& m, float eps, unsigned 
 }
 
 // Turn merged moments into the per-row affine (mu_c, 1/sigma_c, A, B) and optionally dump stats.
-__device__ __forceinline__ void finish_stats(const AdainArgs& a, const Moments (&m)[kMaxQ],
+__device__ __forceinline__ void finish_stats(const AdainArgs& a, const Moments* m,
                                              int64_t row, bool writer, float& mu, float& rsig,
                                              float& A, float& B) {
   mu = m[0].mean;
@@ -117,9 +117,7 @@ __device__ __forceinline__ void finish_stats(const AdainArgs& a, const Moments (
   float* st = a.stats ? a.stats + row * (2 + 2 * a.K) : nullptr;
   if (st && writer) { st[0] = mu; st[1] = sig; }
   if (a.identity_affine) { A = 1.f; B = 0.f; return; }
-#pragma unroll
-  for (int k = 0; k < AST_MAX_STYLES; ++k) {
-    if (k >= a.K) break;
+  for (int k = 0; k < a.K; ++k) {
     float smu = m[1 + k].mean;
     float ssig = std_from(m[1 + k], a.eps, a.flags);
     if (st && writer) { st[2 + 2 * k] = smu; st[3 + 2 * k] = ssig; }
@@ -143,8 +141,34 @@ __device__ __forceinline__ float apply_affine(float x, float mu, float rsig, flo
 
 // ---- register-cached, cluster-split kernel -------------------------------------------------
 // grid = rows * CS CTAs, cluster = CS.  Each CTA owns up to R*kThreads 16-byte vectors of the row.
+// Register budget is what bounds HBM throughput here (bytes in flight per SM = resident CTAs x
+// 2 x R x 4 KB), so the merged moments of the 1 + K quantities live in shared memory, not registers,
+// and R <= 4 is compiled for four resident CTAs per SM.
+
+// CTA-level Chan merge of one quantity: result lands in *dst (shared) for all threads to read
+// after the next __syncthreads().
+__device__ __forceinline__ void cta_merge_to(Moments m, Moments* s_warp, Moments* dst) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  m = moments_warp_reduce(m);
+  __syncthreads();  // s_warp may still be read from the previous quantity
+  if (lane == 0) s_warp[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    Moments r = lane < kWarps ? s_warp[lane] : Moments{0.f, 0.f, 0.f};
+#pragma unroll
+    for (int off = kWarps / 2; off > 0; off >>= 1) {
+      Moments o;
+      o.n = __shfl_xor_sync(0xffffffffu, r.n, off);
+      o.mean = __shfl_xor_sync(0xffffffffu, r.mean, off);
+      o.m2 = __shfl_xor_sync(0xffffffffu, r.m2, off);
+      r = moments_merge(r, o);
+    }
+    if (lane == 0) *dst = r;
+  }
+}
+
 template <bool BF16, int R>
-__global__ void __launch_bounds__(kThreads) adain_cached_kernel(const AdainArgs a) {
+__global__ void __launch_bounds__(kThreads, (R <= 4 ? 4 : 2)) adain_cached_kernel(const AdainArgs a) {
   using VT = Vec16<BF16>;
   constexpr int V = VT::V;
   cg::cluster_group cluster = cg::this_cluster();
@@ -152,8 +176,9 @@ __global__ void __launch_bounds__(kThreads) adain_cached_kernel(const AdainArgs 
   const unsigned rank = cluster.block_rank();
   const int64_t row = blockIdx.x / CS;
 
-  __shared__ Moments s_warp[kWarps][kMaxQ];
-  __shared__ Moments s_part[kMaxQ];
+  __shared__ Moments s_warp[kWarps];
+  __shared__ Moments s_q[kMaxQ];    // this CTA's moments per quantity
+  __shared__ Moments s_fin[kMaxQ];  // cluster-merged
 
   const int Q = a.identity_affine ? 1 : 1 + a.K;
   const int64_t nvec = a.HW / V;
@@ -169,8 +194,6 @@ __global__ void __launch_bounds__(kThreads) adain_cached_kernel(const AdainArgs 
     int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
     if (i < v1) cache[j] = ld_stream_u4(crow + i);
   }
-
-  Moments m[kMaxQ];
   {
     WelfordLanes<V> w;
     w.init();
@@ -183,38 +206,32 @@ __global__ void __launch_bounds__(kThreads) adain_cached_kernel(const AdainArgs 
         w.push(x);
       }
     }
-    m[0] = w.fold();
+    cta_merge_to(w.fold(), s_warp, &s_q[0]);
   }
-#pragma unroll
-  for (int k = 0; k < AST_MAX_STYLES; ++k) {
-    if (k + 1 >= Q) break;
+  for (int k = 0; k + 1 < Q; ++k) {
     const int64_t snvec = a.style_hw[k] / V;
     const int64_t sseg = (snvec + CS - 1) / CS;
     const int64_t s0 = rank * sseg;
     const int64_t s1 = (s0 + sseg < snvec) ? s0 + sseg : snvec;
     const void* srow = reinterpret_cast<const typename VT::elem*>(a.styles[k]) + row * a.style_hw[k];
-    m[1 + k] = (s0 < s1) ? stream_moments_vec<BF16>(srow, s0, s1) : Moments{0.f, 0.f, 0.f};
+    Moments m = (s0 < s1) ? stream_moments_vec<BF16>(srow, s0, s1) : Moments{0.f, 0.f, 0.f};
+    cta_merge_to(m, s_warp, &s_q[1 + k]);
   }
-  block_merge<kMaxQ>(m, Q, s_warp);
-
+  const Moments* fin = s_q;
   if (CS > 1) {
-#pragma unroll
-    for (int q = 0; q < kMaxQ; ++q)
-      if (q < Q && threadIdx.x == q) s_part[q] = m[q];
-    cluster.sync();
-#pragma unroll
-    for (int q = 0; q < kMaxQ; ++q) {
-      if (q < Q) {
-        Moments r = *cluster.map_shared_rank(&s_part[q], 0);
-        for (unsigned c = 1; c < CS; ++c)
-          r = moments_merge(r, *cluster.map_shared_rank(&s_part[q], c));
-        m[q] = r;
-      }
+    cluster.sync();  // every CTA's s_q is complete and visible cluster-wide
+    if ((int)threadIdx.x < Q) {
+      Moments r = *cluster.map_shared_rank(&s_q[threadIdx.x], 0);
+      for (unsigned c = 1; c < CS; ++c)
+        r = moments_merge(r, *cluster.map_shared_rank(&s_q[threadIdx.x], c));
+      s_fin[threadIdx.x] = r;
     }
+    fin = s_fin;
   }
+  __syncthreads();
 
   float mu, rsig, A, B;
-  finish_stats(a, m, row, rank == 0 && threadIdx.x == 0, mu, rsig, A, B);
+  finish_stats(a, fin, row, rank == 0 && threadIdx.x == 0, mu, rsig, A, B);
   const bool blend = a.alpha != 1.f;
 
   uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<typename VT::elem*>(a.out) + row * a.HW);
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(kThreads) adain_cached_kernel(const AdainArgs 
       st_stream_u4(orow + i, VT::pack(x));
     }
   }
-  if (CS > 1) cluster.sync();  // peers may still be reading s_part through DSMEM
+  if (CS > 1) cluster.sync();  // peers may still be reading s_q through DSMEM
 }
 
 // ---- generic two-pass kernel: one CTA per row, any length / alignment ----------------------

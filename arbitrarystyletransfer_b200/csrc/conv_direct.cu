@@ -15,7 +15,7 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
                      const float* std_, void* out, float* tap, int tap_prerelu, int N, int H, int W,
                      cudaStream_t s);
 int conv3x3_last_tc(const void* in, const void* wpk16, const float* bias, float* out, int N, int H,
-                    int W, int Cin, int Cout, int clamp01, cudaStream_t s);
+                    int W, int Cin, int Cout, int clamp01, int kwbox, cudaStream_t s);
 }  // namespace tc
 
 // ---- weight packing: OIHW fp32 -> bf16 [9][Cout][Cin] -------------------------------------------
@@ -279,7 +279,7 @@ extern "C" int ast_conv3x3_fwd(const ast_conv_desc* d, const void* in, const voi
     if (Ho < 2 || Wo < 2) return AST_E_SHAPE;  // ReflectionPad2d(1) needs at least 2 pixels
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const bool want_tc = d->impl == AST_CONV_TC || d->impl >= 64 ||
+  const bool want_tc = d->impl == AST_CONV_TC || d->impl == AST_CONV_TC_TAPBOX || d->impl >= 64 ||
                        (d->impl == AST_CONV_AUTO && tc::tc_supported(d));
   if (want_tc) return tc::conv3x3_tc(d, in, wpk, bias, out, tap, s);
   if (d->impl != AST_CONV_DIRECT && d->impl != AST_CONV_AUTO) return AST_E_BADARG;
@@ -328,9 +328,10 @@ extern "C" int ast_conv3x3_last(const void* in, const float* w, const void* wpk1
                                 float* out, int N, int H, int W, int Cin, int Cout, int clamp01,
                                 int impl, void* stream) {
   if (!in || (!w && !wpk16) || !out || N <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
-  if (impl == AST_CONV_TC && (!wpk16 || Cin % 64 != 0)) return AST_E_SHAPE;
+  if ((impl == AST_CONV_TC || impl == AST_CONV_TC_TAPBOX) && (!wpk16 || Cin % 64 != 0)) return AST_E_SHAPE;
   if (impl != AST_CONV_DIRECT && wpk16 && Cin % 64 == 0 && Cout <= 16)
-    return tc::conv3x3_last_tc(in, wpk16, bias, out, N, H, W, Cin, Cout, clamp01, (cudaStream_t)stream);
+    return tc::conv3x3_last_tc(in, wpk16, bias, out, N, H, W, Cin, Cout, clamp01,
+                               impl == AST_CONV_TC_TAPBOX ? 0 : 1, (cudaStream_t)stream);
   if (!w) return AST_E_BADARG;
   if (Cout < 1 || Cout > kLastMaxCout) return AST_E_SHAPE;
   if (!aligned16(in)) return AST_E_ALIGN;

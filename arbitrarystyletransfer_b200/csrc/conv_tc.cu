@@ -107,12 +107,13 @@ __device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)
 // Epilogue warps (4 per CTA; warp e may touch TMEM lanes [32e, 32e+32) = tile rows 2e, 2e+1):
 // tcgen05.ld -> +bias -> (tap) -> ReLU -> (tap) -> bf16 -> {plain | 2x2 max-pool | nearest x2} store
 // with the optional reflection halo, or the fp32 NCHW image for the last decoder layer.
-template <int BN, int EPI>
+template <int BN, int EPI, int TW = TILE_W>
 __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int e, int lane,
                                               uint32_t tfull_bar0, uint32_t tempty_bar0) {
   constexpr int CH = BN >= 32 ? 32 : 16;  // columns per tcgen05.ld
-  const int hl = 2 * e + (lane >> 4);
-  const int wl = lane & 15;
+  constexpr int TH = TILE_M / TW;         // tile = TH rows x TW cols of pixels, row-major in M
+  const int hl = (32 * e + lane) / TW;
+  const int wl = (32 * e + lane) % TW;
   const bool reflect = p.halo == AST_HALO_REFLECT;
   int as = 0;
   uint32_t aphase = 0;
@@ -122,7 +123,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
     const int twi = t % p.tiles_w; t /= p.tiles_w;
     const int thi = t % p.tiles_h;
     const int n = t / p.tiles_h;
-    const int h = thi * TILE_H + hl, w = twi * TILE_W + wl;
+    const int h = thi * TH + hl, w = twi * TW + wl;
     const bool in_img = (h < p.H) && (w < p.W);
 
     int rows[4], cols[4], nr = 0, nc = 0;
@@ -184,7 +185,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
 #pragma unroll
         for (int i = 0; i < CH / 2; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
         if (EPI == AST_EPI_POOL2) {
-          // 2x2 max: partner along w is lane^1, along h is lane^16 (tile rows are 16 wide).
+          // 2x2 max: partner along w is lane^1, along h is lane^TW (a warp holds 32/TW full tile rows).
           // max commutes with the (monotonic) bf16 rounding, so pool the packed values.
 #pragma unroll
           for (int i = 0; i < CH / 2; ++i) {
@@ -192,7 +193,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
             uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
             a = __hmax2_nan(a, *reinterpret_cast<__nv_bfloat162*>(&o1));
             uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
-            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, 16);
+            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, TW);
             a = __hmax2_nan(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
             pk[i] = *reinterpret_cast<uint32_t*>(&a);
           }
@@ -334,6 +335,197 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// conv3x3_tc2_kernel: same GEMM, 2.7x less A traffic.  Layers with few channels are bound by
+// L2 -> shared-memory bandwidth when every tap re-loads its own shifted 128-pixel box (9 x 16 KB
+// per tile and 64-channel block).  Here the tile is 16 rows x 8 columns, and ONE box of
+// {64 ch, 8 w, 18 h} per kw serves the three kh taps: the tap's operand starts kh * 8 pixels
+// = kh * 1024 B further into the box, which keeps the 1024-byte alignment the 128B swizzle needs,
+// so the UMMA descriptor is the standard one with a different start address.  A traffic drops
+// from 144 KB to 54 KB per (tile, channel block).  A boxes and per-tap weight tiles ride separate
+// mbarrier rings; when the layer has a single 64-channel block and one N block, all nine weight
+// tiles are loaded once per CTA and stay resident.
+constexpr int T2_W = 8, T2_H = 16, T2_BOX_H = T2_H + 2;
+constexpr int A2_BYTES = T2_BOX_H * T2_W * KBLK * 2;  // 18 KB
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int B_BYTES = BN * KBLK * 2;
+  static constexpr int NA = (BN >= 128) ? 4 : (BN == 64 ? 6 : 8);
+  static constexpr int NB = (BN == 256) ? 4 : 9;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int NBAR = 2 * NA + 2 * NB + 4;
+  static constexpr int SMEM_BYTES = NA * A2_BYTES + NB * B_BYTES + NBAR * 8 + 16 + 1024;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const ConvParams p) {
+  using C = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + C::NA * A2_BYTES;
+  const uint32_t bars = b_base + C::NB * C::B_BYTES;
+  auto afull = [&](int s) { return bars + 8u * s; };
+  auto aempty = [&](int s) { return bars + 8u * (C::NA + s); };
+  auto bfull = [&](int s) { return bars + 8u * (2 * C::NA + s); };
+  auto bempty = [&](int s) { return bars + 8u * (2 * C::NA + C::NB + s); };
+  auto tfull = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NB + s); };
+  auto tempty = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NB + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * C::NBAR;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem + C::NA * A2_BYTES + C::NB * C::B_BYTES + 8 * C::NBAR);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int cblocks = p.Cin / KBLK;
+  const bool resident = (C::NB >= 9) && cblocks == 1 && p.n_blocks == 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < C::NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (resident) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_expect_tx(bfull(tap), C::B_BYTES);
+          tma_load_3d(b_base + tap * C::B_BYTES, &tmB, bfull(tap), 0, 0, tap);
+        }
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nb = t % p.n_blocks; t /= p.n_blocks;
+        const int twi = t % p.tiles_w; t /= p.tiles_w;
+        const int thi = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        const int h0 = thi * T2_H, w0 = twi * T2_W;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait(aempty(sa), pa ^ 1u);
+            mbar_expect_tx(afull(sa), A2_BYTES);
+            tma_load_4d(a_base + sa * A2_BYTES, &tmA, afull(sa), cb * KBLK, w0 + kw, h0, n);
+            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            if (!resident) {
+              for (int kh = 0; kh < 3; ++kh) {
+                mbar_wait(bempty(sb), pb ^ 1u);
+                mbar_expect_tx(bfull(sb), C::B_BYTES);
+                tma_load_3d(b_base + sb * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, nb * BN, kh * 3 + kw);
+                if (++sb == C::NB) { sb = 0; pb ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        uint32_t accum = 0;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait(afull(sa), pa);
+            const uint32_t a_addr0 = a_base + sa * A2_BYTES;
+            for (int kh = 0; kh < 3; ++kh) {
+              int slot;
+              if (resident) {
+                slot = kh * 3 + kw;
+                mbar_wait(bfull(slot), 0u);  // completes once per CTA; later waits return at once
+              } else {
+                slot = sb;
+                mbar_wait(bfull(sb), pb);
+              }
+              tc_fence_after();
+              const uint32_t a_addr = a_addr0 + kh * (T2_W * KBLK * 2);  // + kh * 1024 B
+              const uint32_t b_addr = b_base + slot * C::B_BYTES;
+#pragma unroll
+              for (int k = 0; k < KBLK / 16; ++k) {
+                umma_bf16(d_tmem, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32),
+                          idesc, accum);
+                accum = 1u;
+              }
+              if (!resident) {
+                umma_commit(bempty(sb));
+                if (++sb == C::NB) { sb = 0; pb ^= 1u; }
+              }
+            }
+            umma_commit(aempty(sa));
+            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+          }
+        }
+        umma_commit(tfull(as));
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    epilogue_loop<BN, EPI, T2_W>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
+                      int sm_count, cudaStream_t s) {
+  using C = Cfg2<BN>;
+  auto kern = conv3x3_tc2_kernel<BN, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  kern<<<grid, kConvThreads, C::SMEM_BYTES, s>>>(tmA, tmB, p);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BN>
+static int launch_tc2_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                          const ConvParams& p, int sm_count, cudaStream_t s) {
+  switch (epi) {
+    case AST_EPI_PLAIN: return launch_tc2<BN, AST_EPI_PLAIN>(tmA, tmB, p, sm_count, s);
+    case AST_EPI_POOL2: return launch_tc2<BN, AST_EPI_POOL2>(tmA, tmB, p, sm_count, s);
+    case AST_EPI_UP2: return launch_tc2<BN, AST_EPI_UP2>(tmA, tmB, p, sm_count, s);
+  }
+  return AST_E_BADARG;
+}
+
 template <int BN, int EPI>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
                      int sm_count, cudaStream_t s) {
@@ -365,24 +557,48 @@ bool tc_supported(const ast_conv_desc* d) {
   return d->Cin % 64 == 0 && d->Cout % 64 == 0 && d->H >= 2 && d->W >= 2;
 }
 
+static int get_sm_count(int* out);
+
+// Tensor maps for one launch.  kwbox = 1: A box {64, 8, 18, 1} (conv3x3_tc2_kernel);
+// kwbox = 0: A box {64, 16, 8, 1} (conv3x3_tc_kernel).  Weights [9][rows][Cin], box {64, BN, 1}.
+static int make_maps(CUtensorMap* tmA, CUtensorMap* tmB, const void* in, const void* wpk, int N, int H,
+                     int W, int Cin, int wrows, int BN, int kwbox) {
+  const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W + 2, (uint64_t)H + 2, (uint64_t)N};
+  const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)(W + 2) * Cin * 2,
+                           (uint64_t)(H + 2) * (W + 2) * Cin * 2};
+  const uint32_t box_tap[4] = {KBLK, TILE_W, TILE_H, 1};
+  const uint32_t box_kw[4] = {KBLK, T2_W, T2_BOX_H, 1};
+  int r = encode_bf16_map(tmA, in, 4, dims, str, kwbox ? box_kw : box_tap);
+  if (r) return r;
+  const uint64_t wdims[3] = {(uint64_t)Cin, (uint64_t)wrows, 9};
+  const uint64_t wstr[2] = {(uint64_t)Cin * 2, (uint64_t)wrows * Cin * 2};
+  const uint32_t wbox[3] = {KBLK, (uint32_t)BN, 1};
+  return encode_bf16_map(tmB, wpk, 3, wdims, wstr, wbox);
+}
+
+// impl decoding: AST_CONV_AUTO / AST_CONV_TC -> kw-box kernel, automatic N block;
+// AST_CONV_TC_TAPBOX -> per-tap-box kernel; 64/128/256 force the N block of the kw-box kernel,
+// 1064/1128/1256 of the per-tap-box kernel (tuning / A-B tests).
 int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const float* bias, void* out,
                float* tap, cudaStream_t s) {
   if (!tc_supported(d)) return AST_E_SHAPE;
   if (!aligned16(in) || !aligned16(wpk) || (out && !aligned16(out)) || (bias && !aligned16(bias)))
     return AST_E_ALIGN;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    AST_CUDA(cudaGetDevice(&dev));
-    AST_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int sm_count = 0;
+  int r = get_sm_count(&sm_count);
+  if (r) return r;
+  int impl = d->impl;
+  int kwbox = 1;
+  if (impl == AST_CONV_TC_TAPBOX) { kwbox = 0; impl = AST_CONV_TC; }
+  if (impl >= 1000) { kwbox = 0; impl -= 1000; }
   ConvParams p = {};
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   p.Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->H : d->H);
   p.Wo = d->epilogue == AST_EPI_POOL2 ? d->W / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->W : d->W);
   p.relu = d->relu; p.halo = d->halo; p.tap_prerelu = d->tap_prerelu;
-  p.tiles_w = (d->W + TILE_W - 1) / TILE_W;
-  p.tiles_h = (d->H + TILE_H - 1) / TILE_H;
+  const int tw = kwbox ? T2_W : TILE_W, th = kwbox ? T2_H : TILE_H;
+  p.tiles_w = (d->W + tw - 1) / tw;
+  p.tiles_h = (d->H + th - 1) / th;
   p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.tap = tap;
 
   // N-block: the widest that still gives every SM a tile (a wide N amortises the A-operand
@@ -391,7 +607,7 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   int BN = 64;
   if (d->Cout % 256 == 0 && sp_tiles * (d->Cout / 256) >= sm_count) BN = 256;
   else if (d->Cout % 128 == 0 && sp_tiles * (d->Cout / 128) >= sm_count) BN = 128;
-  if (d->impl >= 64 && d->impl <= 256 && d->Cout % d->impl == 0) BN = d->impl;  // tuning override
+  if (impl >= 64 && impl <= 256 && d->Cout % impl == 0) BN = impl;  // tuning override
   if (BN != 64 && BN != 128 && BN != 256) return AST_E_SHAPE;
   p.n_blocks = d->Cout / BN;
   const int64_t nt = sp_tiles * p.n_blocks;
@@ -399,20 +615,14 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   p.num_tiles = (int)nt;
 
   CUtensorMap tmA, tmB;
-  {
-    const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W + 2, (uint64_t)d->H + 2, (uint64_t)d->N};
-    const uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)(d->W + 2) * d->Cin * 2,
-                             (uint64_t)(d->H + 2) * (d->W + 2) * d->Cin * 2};
-    const uint32_t box[4] = {KBLK, TILE_W, TILE_H, 1};
-    int r = encode_bf16_map(&tmA, in, 4, dims, str, box);
-    if (r) return r;
-  }
-  {
-    const uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, 9};
-    const uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout * d->Cin * 2};
-    const uint32_t box[3] = {KBLK, (uint32_t)BN, 1};
-    int r = encode_bf16_map(&tmB, wpk, 3, dims, str, box);
-    if (r) return r;
+  r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, BN, kwbox);
+  if (r) return r;
+  if (kwbox) {
+    switch (BN) {
+      case 256: return launch_tc2_epi<256>(d->epilogue, tmA, tmB, p, sm_count, s);
+      case 128: return launch_tc2_epi<128>(d->epilogue, tmA, tmB, p, sm_count, s);
+      default: return launch_tc2_epi<64>(d->epilogue, tmA, tmB, p, sm_count, s);
+    }
   }
   switch (BN) {
     case 256: return launch_tc_epi<256>(d->epilogue, tmA, tmB, p, sm_count, s);
@@ -442,7 +652,7 @@ struct FirstParams {
   int normalise;
 };
 
-__global__ void __launch_bounds__(kFirstThreads, 1)
+__global__ void __launch_bounds__(kFirstThreads, 2)
 conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
   __shared__ __align__(128) uint8_t s_a[F_STAGES][F_A_BYTES];
   __shared__ __align__(128) uint8_t s_b[F_B_BYTES];
@@ -483,43 +693,52 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
 
   if (warp < 4) {
     // ===================== im2col producers =====================
+    // One pixel per thread.  All 27 loads are unconditional (clamped address, value selected
+    // afterwards) so they issue back to back, and the loads of tile i+1 are in flight while tile i
+    // is packed and stored (software pipeline over the persistent tile loop).
     const int r = threadIdx.x;           // tile row = pixel
     const int hl = r >> 4, wl = r & 15;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    auto gather = [&](int tile, float (&v)[27]) {
       int t = tile;
       const int twi = t % p.tiles_w; t /= p.tiles_w;
       const int thi = t % p.tiles_h;
       const int n = t / p.tiles_h;
       const int h = thi * TILE_H + hl, w = twi * TILE_W + wl;
-      uint32_t pk[16];
+      const bool pix_ok = (h < p.H) && (w < p.W);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      if (h < p.H && w < p.W) {
-        float v[28];
-        v[27] = 0.f;
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* ip = fp.img + ((int64_t)n * 3 + ci) * p.H * p.W;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float* ip = fp.img + ((int64_t)n * 3 + ci) * p.H * p.W;
+        for (int kh = 0; kh < 3; ++kh) {
+          const int ih = h + kh - 1;
+          const int ihc = min(max(ih, 0), p.H - 1);
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const int ih = h + kh - 1;
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const int iw = w + kw - 1;
-              float x = 0.f;   // zero padding applies to the NORMALISED image
-              if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
-                x = __ldg(ip + (int64_t)ih * p.W + iw);
-                if (fp.normalise) x = (x - fp.mean[ci]) * fp.rstd[ci];
-              }
-              v[ci * 9 + kh * 3 + kw] = x;
-            }
+          for (int kw = 0; kw < 3; ++kw) {
+            const int iw = w + kw - 1;
+            const int iwc = min(max(iw, 0), p.W - 1);
+            float x = __ldg(ip + (int64_t)ihc * p.W + iwc);
+            if (fp.normalise) x = (x - fp.mean[ci]) * fp.rstd[ci];
+            // zero padding applies to the NORMALISED image (models.py:131, then Conv2d padding=1)
+            const bool ok = pix_ok && ih == ihc && iw == iwc;
+            v[ci * 9 + kh * 3 + kw] = ok ? x : 0.f;
           }
         }
-#pragma unroll
-        for (int i = 0; i < 14; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
       }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    float cur[27], nxt[27];
+    int tile = blockIdx.x;
+    if (tile < p.num_tiles) gather(tile, cur);
+    for (; tile < p.num_tiles; tile += gridDim.x) {
+      const int ntile = tile + gridDim.x;
+      if (ntile < p.num_tiles) gather(ntile, nxt);
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 13; ++i) pk[i] = pack_bf16(cur[2 * i], cur[2 * i + 1]);
+      pk[13] = pack_bf16(cur[26], 0.f);
+      pk[14] = 0u;
+      pk[15] = 0u;
       mbar_wait(empty_bar(stage), phase ^ 1u);
       uint8_t* row = &s_a[stage][0] + (uint32_t)(r >> 3) * F_SBO + (r & 7) * 16;
 #pragma unroll
@@ -530,6 +749,8 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+#pragma unroll
+      for (int i = 0; i < 27; ++i) cur[i] = nxt[i];
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
@@ -612,7 +833,7 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
 // Last decoder layer (Cin % 64 == 0, Cout <= 16): the implicit-GEMM kernel with a 16-wide N block
 // (weights zero-padded to 16 output channels) and the fp32 NCHW epilogue.
 int conv3x3_last_tc(const void* in, const void* wpk16, const float* bias, float* out, int N, int H,
-                    int W, int Cin, int Cout, int clamp01, cudaStream_t s) {
+                    int W, int Cin, int Cout, int clamp01, int kwbox, cudaStream_t s) {
   if (Cin % 64 != 0 || Cout > 16 || H < 1 || W < 1) return AST_E_SHAPE;
   if (!aligned16(in) || !aligned16(wpk16)) return AST_E_ALIGN;
   int sm_count = 0;
@@ -621,29 +842,18 @@ int conv3x3_last_tc(const void* in, const void* wpk16, const float* bias, float*
   ConvParams p = {};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = 16; p.Ho = H; p.Wo = W;
   p.relu = 0; p.halo = AST_HALO_KEEP;
-  p.tiles_w = (W + TILE_W - 1) / TILE_W;
-  p.tiles_h = (H + TILE_H - 1) / TILE_H;
+  const int tw = kwbox ? T2_W : TILE_W, th = kwbox ? T2_H : TILE_H;
+  p.tiles_w = (W + tw - 1) / tw;
+  p.tiles_h = (H + th - 1) / th;
   p.n_blocks = 1;
   const int64_t nt = (int64_t)N * p.tiles_h * p.tiles_w;
   if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
   p.num_tiles = (int)nt;
   p.bias = bias; p.out_nchw = out; p.cout_real = Cout; p.clamp01 = clamp01;
   CUtensorMap tmA, tmB;
-  {
-    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W + 2, (uint64_t)H + 2, (uint64_t)N};
-    const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)(W + 2) * Cin * 2,
-                             (uint64_t)(H + 2) * (W + 2) * Cin * 2};
-    const uint32_t box[4] = {KBLK, TILE_W, TILE_H, 1};
-    r = encode_bf16_map(&tmA, in, 4, dims, str, box);
-    if (r) return r;
-  }
-  {
-    const uint64_t dims[3] = {(uint64_t)Cin, 16, 9};
-    const uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)16 * Cin * 2};
-    const uint32_t box[3] = {KBLK, 16, 1};
-    r = encode_bf16_map(&tmB, wpk16, 3, dims, str, box);
-    if (r) return r;
-  }
+  r = make_maps(&tmA, &tmB, in, wpk16, N, H, W, Cin, 16, 16, kwbox);
+  if (r) return r;
+  if (kwbox) return launch_tc2<16, EPI_NCHW32>(tmA, tmB, p, sm_count, s);
   return launch_tc<16, EPI_NCHW32>(tmA, tmB, p, sm_count, s);
 }
 

@@ -194,7 +194,7 @@ def build_engine(device):
     return net.engine()
 
 
-def time_layers(eng, N, size, reps=5):
+def time_layers(eng, N, size, reps=5, impl=0):
     """CUDA-event duration of every conv launch of one stylise pass (on the launching stream),
     for the roofline of the dominant kernel family (conv3x3_tc_kernel)."""
     from arbitrarystyletransfer_b200 import _lib as L, engine as E
@@ -223,7 +223,8 @@ def time_layers(eng, N, size, reps=5):
         y = eng.buf.get(f"enc{i}" + ("c" if i == 8 else ""), N, ho, ho, cout, dev, True)
         ms = timed(lambda: E.conv3x3(x, eng.vgg_wpk[i], eng.vgg_b[i], y, N=N, H=h, W=h, cin=cin,
                                      cout=cout, relu=True,
-                                     epilogue=L.EPI_POOL2 if pool else L.EPI_PLAIN, halo=L.HALO_KEEP))
+                                     epilogue=L.EPI_POOL2 if pool else L.EPI_PLAIN, halo=L.HALO_KEEP,
+                                     impl=impl))
         rows.append({"layer": f"enc_conv{i + 1}", "cin": cin, "cout": cout, "hw": h, "epi": "pool" if pool else "plain",
                      "ms": ms, "flops": 2.0 * cout * cin * 9 * h * h * N, "per_step": 2})
         x, h = y, ho
@@ -234,7 +235,8 @@ def time_layers(eng, N, size, reps=5):
         y = eng.buf.get(f"dec{i}", N, ho, ho, cout, dev, False)
         ms = timed(lambda: E.conv3x3(x, eng.dec_wpk[i], eng.dec_b[i], y, N=N, H=h, W=h, cin=cin,
                                      cout=cout, relu=relu,
-                                     epilogue=L.EPI_UP2 if up else L.EPI_PLAIN, halo=L.HALO_REFLECT))
+                                     epilogue=L.EPI_UP2 if up else L.EPI_PLAIN, halo=L.HALO_REFLECT,
+                                     impl=impl))
         rows.append({"layer": f"dec_conv{i + 1}", "cin": cin, "cout": cout, "hw": h, "epi": "up" if up else "plain",
                      "ms": ms, "flops": 2.0 * cout * cin * 9 * h * h * N, "per_step": 1})
         x, h = y, ho
@@ -364,6 +366,9 @@ def run_native(args):
                                   "traffic": None, "peak_source": pk["source"]}
         if args.layers_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
+            alt = time_layers(eng, N, S, impl=3)   # AST_CONV_TC_TAPBOX, for the A/B table only
+            for r, a in zip(rows, alt):
+                r["ms_tapbox"], r["tflops_tapbox"] = a["ms"], a["tflops"]
             json.dump(rows, open(args.layers_out, "w"), indent=1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(S, args.cpu_sample or 8)

@@ -126,7 +126,11 @@ int ast_gram_bwd(const float* x, const float* gg, float* gx, int B, int C, int64
 #define AST_CONV_AUTO   0 /* tcgen05 implicit GEMM when Cin%64==0 && Cout%64==0, else direct */
 #define AST_CONV_TC     1 /* force tcgen05 (AST_E_SHAPE if unsupported) */
 #define AST_CONV_DIRECT 2 /* CUDA-core direct kernel (odd shapes; on-device cross-check) */
-/* impl = 64, 128 or 256 forces the tcgen05 kernel with that N-block width (tuning / tests). */
+#define AST_CONV_TC_TAPBOX 3 /* tcgen05 kernel variant that loads one 8x16-pixel A box per tap (the
+                                default tensor-core kernel loads one 18x8 box per kw and reuses it
+                                for the three kh taps: 2.7x less L2 -> shared-memory traffic) */
+/* impl = 64, 128 or 256 forces the default tcgen05 kernel with that N-block width; 1064, 1128 or
+ * 1256 does the same for the TAPBOX variant (tuning / tests). */
 
 typedef struct ast_conv_desc {
   int N, H, W;        /* conv input = conv output spatial size (stride 1, 3x3, pad 1)      */

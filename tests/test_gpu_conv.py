@@ -57,25 +57,35 @@ SHAPES_TC = [
 ]
 
 
+KERNELS = {"kwbox": 1, "tapbox": 3}   # AST_CONV_TC (default kernel), AST_CONV_TC_TAPBOX
+
+
+@pytest.mark.parametrize("kern", list(KERNELS))
 @pytest.mark.parametrize("shape", SHAPES_TC)
 @pytest.mark.parametrize("epi", [0, 1, 2])
-def test_tc_conv_zero_pad(shape, epi):
-    from arbitrarystyletransfer_b200 import _lib as L
+def test_tc_conv_zero_pad(shape, epi, kern):
     N, H, W, cin, cout = shape
-    _run(N, H, W, cin, cout, True, epi, False, L.CONV_TC, seed=epi)
+    _run(N, H, W, cin, cout, True, epi, False, KERNELS[kern], seed=epi)
 
 
+@pytest.mark.parametrize("kern", list(KERNELS))
 @pytest.mark.parametrize("shape", SHAPES_TC[:5])
 @pytest.mark.parametrize("epi", [0, 2])
-def test_tc_conv_reflect_halo(shape, epi):
-    from arbitrarystyletransfer_b200 import _lib as L
+def test_tc_conv_reflect_halo(shape, epi, kern):
     N, H, W, cin, cout = shape
-    _run(N, H, W, cin, cout, True, epi, True, L.CONV_TC, seed=3 + epi)
+    _run(N, H, W, cin, cout, True, epi, True, KERNELS[kern], seed=3 + epi)
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("bn", [64, 128, 256, 1064, 1128, 1256])
 def test_tc_conv_forced_n_block(bn):
     _run(2, 16, 32, 128, 256, True, 0, True, bn, seed=11)
+
+
+@pytest.mark.parametrize("bn", [64, 128])
+def test_tc_conv_resident_weights(bn):
+    """Cin = 64 with one N block: the nine weight tiles stay resident in shared memory."""
+    _run(3, 40, 24, 64, bn, True, 1, False, bn, seed=14)
+    _run(2, 32, 48, 64, bn, True, 2, True, bn, seed=15)
 
 
 def test_tc_conv_no_relu_and_taps():
@@ -100,14 +110,15 @@ def test_tc_matches_direct_bitwise_mostly():
     assert (a != b).float().mean().item() < 0.02   # only rounding-boundary flips
 
 
-def test_many_tiles_persistent_loop():
+@pytest.mark.parametrize("kern", list(KERNELS))
+def test_many_tiles_persistent_loop(kern):
     """More tiles than SMs and > 2 tiles per CTA: exercises stage / accumulator phase wrap."""
-    from arbitrarystyletransfer_b200 import _lib as L
-    _run(4, 64, 96, 64, 64, True, 1, False, L.CONV_TC, seed=12)
-    _run(2, 64, 64, 128, 128, True, 0, True, L.CONV_TC, seed=13)
+    _run(4, 64, 96, 64, 64, True, 1, False, KERNELS[kern], seed=12)
+    _run(2, 64, 64, 128, 128, True, 0, True, KERNELS[kern], seed=13)
+    _run(1, 128, 160, 256, 256, True, 0, False, KERNELS[kern], seed=16)
 
 
-@pytest.mark.parametrize("impl", ["tc", "direct"])
+@pytest.mark.parametrize("impl", ["tc", "tapbox", "direct"])
 def test_first_and_last_layers(impl):
     """conv_1 (Normalization + 3->64 + ReLU, models.py:129-131, 198-224) and the last decoder conv
     (64->3, reflect pad, models.py:626-627).  The tensor-core variants round their operands to bf16
@@ -115,7 +126,8 @@ def test_first_and_last_layers(impl):
     loosely (1 % of the output scale) against the fp32 reference arithmetic."""
     from arbitrarystyletransfer_b200 import _lib as L, engine as E
     from oracle import restate as R
-    im = L.CONV_TC if impl == "tc" else L.CONV_DIRECT
+    im = {"tc": L.CONV_TC, "tapbox": L.CONV_TC_TAPBOX, "direct": L.CONV_DIRECT}[impl]
+    impl = "tc" if impl == "tapbox" else impl
     g = torch.Generator().manual_seed(1)
     N, H, W = 2, 20, 28
     img = torch.rand(N, 3, H, W, generator=g)

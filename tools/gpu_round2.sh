@@ -13,7 +13,7 @@ if [ "$1" == "ncu" ]; then
       --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit=$?" >> gpurun_out/ncu_launches.log
   timeout 300 python tools/prof_target.py 8 > gpurun_out/plain_prof.log 2>&1 &&
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"adain_cached|conv3x3" -s 1 -c 24 \
+  timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"adain_cached|conv3x3" -c 24 \
       -o gpurun_out/prof -f python tools/prof_target.py 8 > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit=$?" >> gpurun_out/ncu_full.log
 fi
