@@ -107,11 +107,16 @@ __device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)
 // Epilogue warps (4 per CTA; warp e may touch TMEM lanes [32e, 32e+32) = tile rows 2e, 2e+1):
 // tcgen05.ld -> +bias -> (tap) -> ReLU -> (tap) -> bf16 -> {plain | 2x2 max-pool | nearest x2} store
 // with the optional reflection halo, or the fp32 NCHW image for the last decoder layer.
-template <int BN, int EPI, int TW = TILE_W>
-__device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int e, int lane,
+template <int BN, int EPI, int TW = TILE_W, int NG = 1>
+__device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
                                               uint32_t tfull_bar0, uint32_t tempty_bar0) {
   constexpr int CH = BN >= 32 ? 32 : 16;  // columns per tcgen05.ld
   constexpr int TH = TILE_M / TW;         // tile = TH rows x TW cols of pixels, row-major in M
+  constexpr int NCH = BN / CH;
+  // 4*NG epilogue warps: warp ew owns TMEM lane quarter e = ew % 4 (hardware rule: a warp may only
+  // touch lanes [32*(warp%4), +32)) and the column chunks g, g+NG, ... with g = ew / 4, so two
+  // warps per SM sub-partition interleave and hide each other's TMEM-load / store latency.
+  const int e = ew & 3, g = ew >> 2;
   const int hl = (32 * e + lane) / TW;
   const int wl = (32 * e + lane) % TW;
   const bool reflect = p.halo == AST_HALO_REFLECT;
@@ -140,12 +145,16 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
 
     mbar_wait(tfull_bar0 + 8u * as, aphase);
     tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
+    uint32_t vnext[CH];
+    if (g < NCH) tmem_ld_cols(trow + g * CH, vnext);
 #pragma unroll 1
-    for (int chunk = 0; chunk < BN / CH; ++chunk) {
+    for (int chunk = g; chunk < NCH; chunk += NG) {
       uint32_t v[CH];
-      const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN + chunk * CH);
-      tmem_ld_cols(taddr, v);
       tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < CH; ++i) v[i] = vnext[i];
+      if (chunk + NG < NCH) tmem_ld_cols(trow + (chunk + NG) * CH, vnext);  // prefetch next chunk
       const int ch0 = nb * BN + chunk * CH;
       if constexpr (EPI == EPI_NCHW32) {
         if (in_img) {
@@ -359,8 +368,11 @@ struct Cfg2 {
   static constexpr int SMEM_BYTES = NA * A2_BYTES + NB * B_BYTES + NBAR * 8 + 16 + 1024;
 };
 
+constexpr int kConv2Threads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: epilogue
+constexpr int kEpi2Groups = 2;
+
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConv2Threads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const ConvParams p) {
   using C = Cfg2<BN>;
@@ -393,7 +405,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < C::NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4 * kEpi2Groups); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -440,37 +452,55 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
+    // The issue thread is latency-bound, not throughput-bound: an mbarrier probe costs ~90 cycles
+    // even when the phase has completed, so every wait is PROBED one step ahead (the MMAs of the
+    // current step issue while the probe is in flight) and descriptors are advanced by adding
+    // constants to one precomputed 64-bit value (start address field = bits [0,14) in 16-byte
+    // units; shared memory is < 256 KB, so the add never carries out of the field).
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
+      const uint64_t a_desc0 = make_sdesc_k128(a_base);
+      const uint64_t b_desc0 = make_sdesc_k128(b_base);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int as = 0;
       uint32_t aphase = 0;
+      bool b_resident_ready = false;
+      bool t_ok = mbar_try_wait(tempty(as), aphase ^ 1u);
+      bool a_ok = mbar_try_wait(afull(sa), pa);
+      bool b_ok = resident ? false : mbar_try_wait(bfull(sb), pb);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty(as), aphase ^ 1u);
+        if (!t_ok) mbar_wait(tempty(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         uint32_t accum = 0;
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = 0; kw < 3; ++kw) {
-            mbar_wait(afull(sa), pa);
-            const uint32_t a_addr0 = a_base + sa * A2_BYTES;
+            if (!a_ok) mbar_wait(afull(sa), pa);
+            const uint64_t a_desc = a_desc0 + (uint64_t)(sa * (A2_BYTES >> 4));
+            int sa_n = sa + 1;
+            uint32_t pa_n = pa;
+            if (sa_n == C::NA) { sa_n = 0; pa_n ^= 1u; }
+            a_ok = mbar_try_wait(afull(sa_n), pa_n);  // probe the next box while this one is consumed
             for (int kh = 0; kh < 3; ++kh) {
               int slot;
               if (resident) {
                 slot = kh * 3 + kw;
-                mbar_wait(bfull(slot), 0u);  // completes once per CTA; later waits return at once
+                if (!b_resident_ready) mbar_wait(bfull(slot), 0u);  // first tile only
               } else {
                 slot = sb;
-                mbar_wait(bfull(sb), pb);
+                if (!b_ok) mbar_wait(bfull(sb), pb);
+                int sb_n = sb + 1;
+                uint32_t pb_n = pb;
+                if (sb_n == C::NB) { sb_n = 0; pb_n ^= 1u; }
+                b_ok = mbar_try_wait(bfull(sb_n), pb_n);
               }
               tc_fence_after();
-              const uint32_t a_addr = a_addr0 + kh * (T2_W * KBLK * 2);  // + kh * 1024 B
-              const uint32_t b_addr = b_base + slot * C::B_BYTES;
+              const uint64_t ad = a_desc + (uint64_t)(kh * ((T2_W * KBLK * 2) >> 4));  // + kh * 1024 B
+              const uint64_t bd = b_desc0 + (uint64_t)(slot * (C::B_BYTES >> 4));
 #pragma unroll
               for (int k = 0; k < KBLK / 16; ++k) {
-                umma_bf16(d_tmem, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32),
-                          idesc, accum);
+                umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, accum);
                 accum = 1u;
               }
               if (!resident) {
@@ -479,16 +509,19 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
             }
             umma_commit(aempty(sa));
-            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            sa = sa_n;
+            pa = pa_n;
           }
         }
+        b_resident_ready = true;
         umma_commit(tfull(as));
         as ^= 1;
         if (as == 0) aphase ^= 1u;
+        t_ok = mbar_try_wait(tempty(as), aphase ^ 1u);
       }
     }
   } else if (warp >= 4) {
-    epilogue_loop<BN, EPI, T2_W>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0));
+    epilogue_loop<BN, EPI, T2_W, kEpi2Groups>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0));
   }
 
   tc_fence_before();
@@ -510,7 +543,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     attr_done = true;
   }
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-  kern<<<grid, kConvThreads, C::SMEM_BYTES, s>>>(tmA, tmB, p);
+  kern<<<grid, kConv2Threads, C::SMEM_BYTES, s>>>(tmA, tmB, p);
   AST_CHECK_LAUNCH();
   return 0;
 }
