@@ -59,6 +59,15 @@ PROTOTYPES = {
     "ast_adain_native_ws_bytes": (_sz, [_i, _i, _i]),
     "ast_adain_native_fwd": (_i, [_vp, C.POINTER(_vp), _fp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _f,
                                   _u, _i, _vp, _sz, _vp]),
+    "ast_pack_conv_weight_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ast_nchw_to_native_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_native_to_nchw_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ast_maxpool2_native": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_vgg_bwd_prep": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_dec_bwd_fold": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_native_to_planar": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp]),
+    "ast_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp]),
+    "ast_unpack_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp]),
 }
 
 _lib = None

@@ -40,6 +40,26 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+__global__ void pack_weight_ex_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o,
+                                      int Cout, int Cin, int flip, int R, int Cc,
+                                      const float* __restrict__ row_scale) {
+  const int64_t total = (int64_t)9 * R * Cc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cc);
+    const int r = (int)((i / Cc) % R);
+    const int t = (int)(i / ((int64_t)Cc * R));
+    float v = 0.f;
+    if (!flip) {
+      if (r < Cout && c < Cin) v = w[((int64_t)r * Cin + c) * 9 + t];
+    } else {
+      if (r < Cin && c < Cout) v = w[((int64_t)c * Cin + r) * 9 + (8 - t)];
+    }
+    if (row_scale) v *= row_scale[r < (flip ? Cin : Cout) ? r : 0];
+    o[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ---- generic direct kernel: one thread per element of the PADDED output grid --------------------
 __device__ __forceinline__ int reflect_idx(int p, int X) {  // ReflectionPad2d(1) source index
   return p < 0 ? -p : (p >= X ? 2 * X - 2 - p : p);
@@ -264,6 +284,22 @@ extern "C" int ast_pack_conv_weight(const float* w_oihw, void* wpk, int Cout, in
   if (nb > 148 * 8) nb = 148 * 8;
   pack_weight_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
       w_oihw, reinterpret_cast<__nv_bfloat16*>(wpk), Cout, Cin, flip, rows);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_pack_conv_weight_ex(const float* w_oihw, void* wpk, int Cout, int Cin, int flip,
+                                       int rows_pad, int cols_pad, const float* row_scale,
+                                       void* stream) {
+  if (!w_oihw || !wpk || Cout <= 0 || Cin <= 0) return AST_E_BADARG;
+  const int rows = flip ? Cin : Cout, cols = flip ? Cout : Cin;
+  const int R = rows_pad ? rows_pad : rows, Cc = cols_pad ? cols_pad : cols;
+  if (R < rows || Cc < cols) return AST_E_BADARG;
+  const int64_t total = (int64_t)9 * R * Cc;
+  int64_t nb = (total + 255) / 256;
+  if (nb > 148 * 8) nb = 148 * 8;
+  pack_weight_ex_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, reinterpret_cast<__nv_bfloat16*>(wpk), Cout, Cin, flip, R, Cc, row_scale);
   AST_CHECK_LAUNCH();
   return 0;
 }

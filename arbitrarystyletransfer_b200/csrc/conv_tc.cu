@@ -107,7 +107,7 @@ __device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)
 // Epilogue warps (4 per CTA; warp e may touch TMEM lanes [32e, 32e+32) = tile rows 2e, 2e+1):
 // tcgen05.ld -> +bias -> (tap) -> ReLU -> (tap) -> bf16 -> {plain | 2x2 max-pool | nearest x2} store
 // with the optional reflection halo, or the fp32 NCHW image for the last decoder layer.
-template <int BN, int EPI, int TW = TILE_W, int NG = 1>
+template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2>
 __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
                                               uint32_t tfull_bar0, uint32_t tempty_bar0) {
   constexpr int CH = BN >= 32 ? 32 : 16;  // columns per tcgen05.ld
@@ -224,8 +224,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty_bar0 + 8u * as);
-    as ^= 1;
-    if (as == 0) aphase ^= 1u;
+    if (++as == NACC) { as = 0; aphase ^= 1u; }
   }
 }
 
@@ -363,8 +362,9 @@ struct Cfg2 {
   static constexpr int B_BYTES = BN * KBLK * 2;
   static constexpr int NA = (BN >= 128) ? 4 : (BN == 64 ? 6 : 8);
   static constexpr int NB = (BN == 256) ? 4 : 9;
-  static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int NBAR = 2 * NA + 2 * NB + 4;
+  static constexpr int NACC = (BN <= 128) ? 4 : 2;  // TMEM accumulator stages (<= 512 columns)
+  static constexpr int TMEM_COLS = (NACC * BN < 32) ? 32 : NACC * BN;
+  static constexpr int NBAR = 2 * NA + 2 * NB + 2 * NACC;
   static constexpr int SMEM_BYTES = NA * A2_BYTES + NB * B_BYTES + NBAR * 8 + 16 + 1024;
 };
 
@@ -388,7 +388,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto bfull = [&](int s) { return bars + 8u * (2 * C::NA + s); };
   auto bempty = [&](int s) { return bars + 8u * (2 * C::NA + C::NB + s); };
   auto tfull = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NB + s); };
-  auto tempty = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NB + 2 + s); };
+  auto tempty = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NB + C::NACC + s); };
   const uint32_t tmem_slot = bars + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
       smem + C::NA * A2_BYTES + C::NB * C::B_BYTES + 8 * C::NBAR);
@@ -405,7 +405,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < C::NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4 * kEpi2Groups); }
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4 * kEpi2Groups); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -515,13 +515,12 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         b_resident_ready = true;
         umma_commit(tfull(as));
-        as ^= 1;
-        if (as == 0) aphase ^= 1u;
+        if (++as == C::NACC) { as = 0; aphase ^= 1u; }
         t_ok = mbar_try_wait(tempty(as), aphase ^ 1u);
       }
     }
   } else if (warp >= 4) {
-    epilogue_loop<BN, EPI, T2_W, kEpi2Groups>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0));
+    epilogue_loop<BN, EPI, T2_W, kEpi2Groups, C::NACC>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0));
   }
 
   tc_fence_before();

@@ -45,6 +45,49 @@ __global__ void __launch_bounds__(256) nchw_to_native_kernel(const float* __rest
   }
 }
 
+// ---- NCHW fp32 -> channels [0,C) of a wider / deeper-halo native tensor ---------------------------
+__global__ void __launch_bounds__(256) nchw_to_native_ex_kernel(const float* __restrict__ src,
+                                                                __nv_bfloat16* __restrict__ dst, int N,
+                                                                int C, int H, int W, int Cdst, int halo) {
+  __shared__ float tile[32][33];  // [c][w]
+  const int ctiles = (C + 31) / 32;
+  const int n = blockIdx.z / ctiles, c0 = (blockIdx.z % ctiles) * 32;
+  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < 32; c += 8) {
+    const int cc = c0 + c, ww = w0 + tx;
+    tile[c][tx] = (cc < C && ww < W) ? src[(((int64_t)n * C + cc) * H + h) * W + ww] : 0.f;
+  }
+  __syncthreads();
+  for (int wl = ty; wl < 32; wl += 8) {
+    const int ww = w0 + wl, cc = c0 + tx;
+    if (ww >= W || cc >= C) continue;
+    dst[(((int64_t)n * (H + 2 * halo) + h + halo) * (W + 2 * halo) + ww + halo) * Cdst + cc] =
+        __float2bfloat16_rn(tile[tx][wl]);
+  }
+}
+
+__global__ void __launch_bounds__(256) native_to_nchw_ex_kernel(const __nv_bfloat16* __restrict__ src,
+                                                                float* __restrict__ dst, int N, int C,
+                                                                int H, int W, int halo) {
+  __shared__ float tile[32][33];  // [w][c]
+  const int ctiles = (C + 31) / 32;
+  const int n = blockIdx.z / ctiles, c0 = (blockIdx.z % ctiles) * 32;
+  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int wl = ty; wl < 32; wl += 8) {
+    const int ww = w0 + wl, cc = c0 + tx;
+    tile[wl][tx] = (ww < W && cc < C)
+        ? __bfloat162float(src[(((int64_t)n * (H + 2 * halo) + h + halo) * (W + 2 * halo) + ww + halo) * C + cc])
+        : 0.f;
+  }
+  __syncthreads();
+  for (int c = ty; c < 32; c += 8) {
+    const int cc = c0 + c, ww = w0 + tx;
+    if (cc < C && ww < W) dst[(((int64_t)n * C + cc) * H + h) * W + ww] = tile[tx][c];
+  }
+}
+
 // ---- native -> NCHW fp32 ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) native_to_nchw_kernel(const __nv_bfloat16* __restrict__ src,
                                                              float* __restrict__ dst, int N, int C,
@@ -228,6 +271,32 @@ extern "C" int ast_native_to_nchw(const void* native, float* nchw, int N, int C,
   dim3 grid((W + 31) / 32, H, N * ctiles);
   native_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(native), nchw, N, C, H, W);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_nchw_to_native_ex(const float* nchw, void* native, int N, int C, int H, int W,
+                                     int Cdst, int dst_halo, void* stream) {
+  if (!nchw || !native || N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cdst < C) return AST_E_BADARG;
+  if (dst_halo < 1 || dst_halo > 2) return AST_E_BADARG;
+  const int ctiles = (C + 31) / 32;
+  if ((int64_t)N * ctiles > 65535 || H > 65535) return AST_E_SHAPE;
+  dim3 grid((W + 31) / 32, H, N * ctiles);
+  nchw_to_native_ex_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      nchw, reinterpret_cast<__nv_bfloat16*>(native), N, C, H, W, Cdst, dst_halo);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_native_to_nchw_ex(const void* native, float* nchw, int N, int C, int H, int W,
+                                     int src_halo, void* stream) {
+  if (!nchw || !native || N <= 0 || C <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  if (src_halo < 1 || src_halo > 2) return AST_E_BADARG;
+  const int ctiles = (C + 31) / 32;
+  if ((int64_t)N * ctiles > 65535 || H > 65535) return AST_E_SHAPE;
+  dim3 grid((W + 31) / 32, H, N * ctiles);
+  native_to_nchw_ex_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(native), nchw, N, C, H, W, src_halo);
   AST_CHECK_LAUNCH();
   return 0;
 }

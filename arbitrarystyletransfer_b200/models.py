@@ -143,6 +143,8 @@ class PretrainedEncoder(nn.Module):
         last_needed = max((k for k, nm in enumerate(names) if nm in wanted), default=-1)
         if last_needed < 0:
             return []
+        if torch.is_grad_enabled() and x.requires_grad:
+            return self._forward_autograd(x, names, last_needed)
         x = x.float().contiguous()
         N, _, H, W = x.shape
         dev = x.device
@@ -189,6 +191,33 @@ class PretrainedEncoder(nn.Module):
         return outs
 
 
+def _encoder_autograd(self, x, names, last_needed):
+    """Training-mode walk (input requires grad): same taps, recorded by train_ops.EncoderFn, which
+    back-propagates to the image only -- the VGG weights are a frozen loss network in every flow
+    of the reference (train.py:55-56, train_autoencoder.py:24-25 build optimisers over the model
+    only), so no weight gradient is produced for them."""
+    from .train_ops import EncoderFn
+    wanted = self._content_layers
+    plan, wb = [], []
+    k = 1
+    while k <= last_needed:
+        conv = self._vgg_layers[k]
+        cname, rname = names[k], names[k + 1]
+        has_pool = k + 2 < len(names) and names[k + 2].startswith("pool_")
+        if has_pool and names[k + 2] in wanted:
+            raise L.AstError("pool_i taps are not supported when the encoder input requires grad")
+        if cname in wanted and rname in wanted:
+            raise L.AstError("tapping both conv_i and relu_i of the same layer is not supported")
+        tap = "pre" if cname in wanted else ("post" if rname in wanted else None)
+        plan.append((conv.in_channels, conv.out_channels, has_pool, tap))
+        wb += [conv.weight, conv.bias]
+        k += 3 if has_pool else 2
+    return list(EncoderFn.apply(x, plan, *wb))
+
+
+PretrainedEncoder._forward_autograd = _encoder_autograd
+
+
 class ClassicDecoder(nn.Sequential):
     """The classic mirrored decoder the reference keeps as a commented ``nn.Sequential``
     (models.py:598-628; channel list conf.py:9): [ReflectionPad2d(1), Conv2d(3x3), ReLU] x 9 (no
@@ -215,8 +244,16 @@ class ClassicDecoder(nn.Sequential):
         return [m for m in self if isinstance(m, nn.Conv2d)]
 
     def forward(self, x):
-        """x: (N, 512, h, w) fp32 NCHW features -> (N, 3, 8h, 8w) fp32 image."""
+        """x: (N, 512, h, w) fp32 NCHW features -> (N, 3, 8h, 8w) fp32 image.  With grad enabled and
+        trainable parameters the call is recorded for autograd (train_ops.DecoderFn: forward, data
+        and weight gradients all on the tensor-core kernels)."""
         L.require_cuda(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .train_ops import DecoderFn
+            params = []
+            for c in self._convs():
+                params += [c.weight, c.bias]
+            return DecoderFn.apply(x, self.exporting, *params)
         t = E.nchw_to_native(x, reflect=True)
         return self.forward_native(t)
 

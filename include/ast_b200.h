@@ -197,6 +197,55 @@ int ast_adain_native_fwd(const void* content, const void* const* styles, const f
                          float alpha, float eps, unsigned flags, int halo,
                          void* ws, size_t ws_bytes, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------
+ * Training (BASELINE config 2: decoder training step).  Gradients live in the native layout too.
+ * Data gradient of a conv = ast_conv3x3_fwd on dZ with ast_pack_conv_weight(flip = 1) weights.
+ * ------------------------------------------------------------------------------------- */
+
+/* Generalised weight packer: bf16 [9][rows_pad][cols_pad], zero beyond the real rows / columns.
+ * flip = 0: rows = Cout, cols = Cin.  flip = 1: rows = Cin, cols = Cout, taps rotated 180 degrees
+ * (the data-gradient weights).  row_scale: optional device fp32 [rows] multiplied into each row
+ * (1/std of Normalization, models.py:131, for the gradient w.r.t. the image). */
+int ast_pack_conv_weight_ex(const float* w_oihw, void* wpk, int Cout, int Cin, int flip,
+                            int rows_pad, int cols_pad, const float* row_scale, void* stream);
+
+/* NCHW fp32 [N][C][H][W] -> channels [0,C) of a native tensor with Cdst channels and halo width
+ * dst_halo (1 or 2); other channels and the halo are left untouched (caller zero-fills once). */
+int ast_nchw_to_native_ex(const float* nchw, void* native, int N, int C, int H, int W, int Cdst,
+                          int dst_halo, void* stream);
+/* interior of a native tensor with halo width src_halo -> NCHW fp32 */
+int ast_native_to_nchw_ex(const void* native, float* nchw, int N, int C, int H, int W, int src_halo,
+                          void* stream);
+
+/* nn.MaxPool2d(2,2) forward on the native layout (training keeps the un-pooled activation). */
+int ast_maxpool2_native(const void* in, void* out, int N, int C, int H, int W, void* stream);
+
+/* Backward through ReLU (+ MaxPool2d) of one VGG layer (torchvision vgg19 inside
+ * models.py:186-240): dZ = [Y>0] * (route(G) + tap_post) + tap_pre, see csrc/train.cu.
+ * Y, G, tap_* : native 1-halo (G at pooled size when pooled); dZ: native with halo dz_halo. */
+int ast_vgg_bwd_prep(const void* Y, const void* G, const void* tap_post, const void* tap_pre,
+                     void* dZ, int N, int C, int H, int W, int pooled, int dz_halo, void* stream);
+
+/* Backward through ReflectionPad2d(1) (+ Upsample x2 nearest) (+ ReLU) between two decoder convs
+ * (models.py:598-628): dXpad [N][Hi+4][Wi+4][C] -> dZ [N][Hc+4][Wc+4][C] (2-pixel zero halo). */
+int ast_dec_bwd_fold(const void* dXpad, const void* Xi, void* dZ, int N, int C, int Hi, int Wi,
+                     int up, int relu, void* stream);
+
+/* native (halo width src_halo) -> channel-planar bf16 [C][ldq], q over the 1-halo padded grid;
+ * ldq >= N*(H+2)*(W+2), multiple of 8.  copy_halo = 0 writes a zero halo. */
+int ast_native_to_planar(const void* native, void* planar, int N, int C, int H, int W, int src_halo,
+                         int copy_halo, int64_t ldq, void* stream);
+
+/* Weight gradient on the tensor cores: dwpk [9][Cout][Cin] fp32 (overwritten) =
+ * sum_q dzT[co][q] * xT[ci][q + (kh-1)*(W+2) + (kw-1)].  Cin % 16 == 0. */
+int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar, float* dwpk, int N, int H, int W,
+                      int Cin, int Cout, int64_t ldq, void* stream);
+
+/* dwpk -> OIHW fp32 gradient (overwrite or accumulate); b_grad (optional) = row sums of dz_planar. */
+int ast_unpack_wgrad(const float* dwpk, float* w_grad, const void* dz_planar, float* b_grad, int Cout,
+                     int Cin, int64_t ldq, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
