@@ -65,8 +65,8 @@ PROTOTYPES = {
     "ast_maxpool2_native": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ast_vgg_bwd_prep": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_dec_bwd_fold": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "ast_native_to_planar": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp]),
-    "ast_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp]),
+    "ast_native_to_planar": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_unpack_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp]),
 }
 

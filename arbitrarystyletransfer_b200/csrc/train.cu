@@ -169,26 +169,29 @@ dec_bwd_fold_kernel(const __nv_bfloat16* __restrict__ dXpad, const __nv_bfloat16
 }
 
 // ---- native -> channel-planar (the K-major operands of the weight-gradient GEMM) ----------------------
-// planar[c][q], q = n*(H+2)*(W+2) + ph*(W+2) + pw over the 1-halo padded grid.  The source has halo
-// width src_halo; the planar halo is copied from the source when copy_halo, else written as zero.
+// planar[s][c][q], q = (n*(H+2) + ph)*wp + pw over the 1-halo padded grid with the row pitch wp
+// (a multiple of 8 pixels >= W+2, so that row shifts stay 16-byte aligned: TMA tiled loads need an
+// aligned innermost coordinate).  Columns pw >= W+2 are zero.  The source has halo width src_halo;
+// the planar halo is copied from the source when copy_halo, else zero.  nshift = 3 writes the three
+// column-shifted copies planar[s][c][q] = x[c][q + s - 1] the kw = 0,1,2 taps read.
 __global__ void __launch_bounds__(256)
 native_to_planar_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N,
-                        int C, int H, int W, int src_halo, int copy_halo, int64_t ldq) {
+                        int C, int H, int W, int src_halo, int copy_halo, int wp, int nshift) {
   __shared__ __nv_bfloat16 tile[32][34];  // [pixel][channel]
-  const int Wp = W + 2, Hp = H + 2;
-  const int64_t Q = (int64_t)N * Hp * Wp;
+  const int Hp = H + 2;
+  const int64_t ldq = (int64_t)N * Hp * wp;
   const int64_t q0 = (int64_t)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int pl = ty; pl < 32; pl += 8) {
     const int64_t q = q0 + pl;
     __nv_bfloat16 val = __float2bfloat16_rn(0.f);
-    if (q < Q && c0 + tx < C) {
-      const int pw = (int)(q % Wp);
-      const int ph = (int)((q / Wp) % Hp);
-      const int n = (int)(q / ((int64_t)Wp * Hp));
-      const bool halo = ph == 0 || pw == 0 || ph == Hp - 1 || pw == Wp - 1;
-      if (!halo || copy_halo) {
+    if (q < ldq && c0 + tx < C) {
+      const int pw = (int)(q % wp);
+      const int ph = (int)((q / wp) % Hp);
+      const int n = (int)(q / ((int64_t)wp * Hp));
+      const bool halo = ph == 0 || pw == 0 || ph == Hp - 1 || pw == W + 1;
+      if (pw < W + 2 && (!halo || copy_halo)) {
         const int sh = ph - 1 + src_halo, sw = pw - 1 + src_halo;
         val = src[(((int64_t)n * (H + 2 * src_halo) + sh) * (W + 2 * src_halo) + sw) * C + c0 + tx];
       }
@@ -196,9 +199,23 @@ native_to_planar_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __
     tile[pl][tx] = val;
   }
   __syncthreads();
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
   for (int cl = ty; cl < 32; cl += 8) {
     const int64_t q = q0 + tx;
-    if (c0 + cl < C && q < ldq) dst[(int64_t)(c0 + cl) * ldq + q] = (q < Q) ? tile[tx][cl] : __float2bfloat16_rn(0.f);
+    if (c0 + cl >= C || q >= ldq) continue;
+    const __nv_bfloat16 v = tile[tx][cl];
+    if (nshift == 1) {
+      dst[(int64_t)(c0 + cl) * ldq + q] = v;
+    } else {
+      __nv_bfloat16* d0 = dst + ((int64_t)0 * C + c0 + cl) * ldq;  // x[q-1]
+      __nv_bfloat16* d1 = dst + ((int64_t)1 * C + c0 + cl) * ldq;  // x[q]
+      __nv_bfloat16* d2 = dst + ((int64_t)2 * C + c0 + cl) * ldq;  // x[q+1]
+      d1[q] = v;
+      if (q + 1 < ldq) d0[q + 1] = v;
+      if (q >= 1) d2[q - 1] = v;
+      if (q == 0) d0[0] = zero;
+      if (q == ldq - 1) d2[ldq - 1] = zero;
+    }
   }
 }
 
@@ -287,17 +304,17 @@ extern "C" int ast_dec_bwd_fold(const void* dXpad, const void* Xi, void* dZ, int
 }
 
 extern "C" int ast_native_to_planar(const void* native, void* planar, int N, int C, int H, int W,
-                                    int src_halo, int copy_halo, int64_t ldq, void* stream) {
+                                    int src_halo, int copy_halo, int wp, int nshift, void* stream) {
   if (!native || !planar || N <= 0 || C <= 0 || H <= 0 || W <= 0 || src_halo < 1 || src_halo > 2)
     return AST_E_BADARG;
-  const int64_t Q = (int64_t)N * (H + 2) * (W + 2);
-  if (ldq < Q || ldq % 8 != 0) return AST_E_SHAPE;
+  if (wp < W + 2 || wp % 8 != 0 || (nshift != 1 && nshift != 3)) return AST_E_SHAPE;
+  const int64_t ldq = (int64_t)N * (H + 2) * wp;
   const int64_t gx = (ldq + 31) / 32;
   if (gx >= 0x7fffffffLL || (C + 31) / 32 > 65535) return AST_E_SHAPE;
   dim3 grid((unsigned)gx, (C + 31) / 32);
   native_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(native), reinterpret_cast<__nv_bfloat16*>(planar), N, C, H, W,
-      src_halo, copy_halo, ldq);
+      src_halo, copy_halo, wp, nshift);
   AST_CHECK_LAUNCH();
   return 0;
 }

@@ -6,12 +6,16 @@
 //   dW[co][ci][kh][kw] = sum_{n,h,w} dZ[n][co][h][w] * Xpad[n][ci][h+kh][w+kw]
 //
 // Both operands are taken from CHANNEL-PLANAR bf16 copies whose pixel axis is the padded linear
-// index q = n*(H+2)*(W+2) + (h+1)*(W+2) + (w+1):
-//   dzT [Cout][ldq]  (zero halo)            xT [Cin][ldq]  (halo = the padding the conv saw)
-// With that index the tap (kh,kw) is a pure shift along q, delta = (kh-1)*(W+2) + (kw-1), and
-// because dZ's halo is zero no product ever crosses an image or row boundary.  So the whole
-// gradient is nine K-major GEMMs  D_tap[co][ci] = dzT[co][:] . xT[ci][: + delta]  with K = ldq:
-// the same SW128 K-major operand form as the forward kernel (rows of 64 pixels = 128 B).
+// index q = (n*(H+2) + h+1)*wp + (w+1), row pitch wp = a multiple of 8 pixels >= W+2:
+//   dzT [Cout][ldq]  (zero halo)            xT [3][Cin][ldq]  (halo = the padding the conv saw)
+// With that index the tap (kh,kw) is a pure shift along q, delta = (kh-1)*wp + (kw-1), and because
+// dZ's halo is zero no product ever crosses an image or row boundary.  So the whole gradient is
+// nine K-major GEMMs  D_tap[co][ci] = dzT[co][:] . xT[ci][: + delta]  with K = ldq: the same SW128
+// K-major operand form as the forward kernel (rows of 64 pixels = 128 B).
+// TMA tiled loads need a 16-byte aligned innermost coordinate (measured on B200: an odd element
+// offset never completes), so the +-1 column shift is materialised as three copies of xT
+// (xT[s][ci][q] = x[ci][q + s - 1]) and only the row shift (kh-1)*wp -- a multiple of 8 -- goes into
+// the coordinate.
 // Work item = (tap, 128-row block of Cout, N block of Cin, split-K chunk); partial sums are
 // reduced with fp32 red.global.add into dwpk [9][Cout][Cin] (zeroed by the caller's memset).
 #include "tc.cuh"
@@ -32,7 +36,7 @@ struct WgCfg {
 };
 
 struct WgParams {
-  int Cin, Cout, W;          // W = conv width (delta uses W + 2)
+  int Cin, Cout, wp;         // wp = planar row pitch
   int m_blocks, n_blocks, k_chunks;
   int ksteps_total, ksteps_per_chunk;
   float* dwpk;               // [9][Cout][Cin] fp32
@@ -65,7 +69,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int mb = t % p.m_blocks;
   const int tap = t / p.m_blocks;
   const int kh = tap / 3, kw = tap - 3 * kh;
-  const int delta = (kh - 1) * (p.W + 2) + (kw - 1);
+  const int delta = (kh - 1) * p.wp;  // multiple of 8 elements; the kw shift selects the xT copy
   const int ks0 = kc * p.ksteps_per_chunk;
   int ks1 = ks0 + p.ksteps_per_chunk;
   if (ks1 > p.ksteps_total) ks1 = p.ksteps_total;
@@ -98,7 +102,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
         const uint32_t a_dst = base + stage * C::STAGE_BYTES;
         tma_load_2d(a_dst, &tmA, full_bar(stage), ks * WG_KBLK, mb * 128);
-        tma_load_2d(a_dst + WG_A_BYTES, &tmB, full_bar(stage), ks * WG_KBLK + delta, nb * BN);
+        tma_load_3d(a_dst + WG_A_BYTES, &tmB, full_bar(stage), ks * WG_KBLK + delta, nb * BN, kw);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -172,12 +176,15 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
 using namespace ast;
 using namespace ast::tc;
 
-extern "C" int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar, float* dwpk, int N,
-                                 int H, int W, int Cin, int Cout, int64_t ldq, void* stream) {
+extern "C" int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar3, float* dwpk, int N,
+                                 int H, int W, int Cin, int Cout, int wp, void* stream) {
+  const void* x_planar = x_planar3;
   if (!dz_planar || !x_planar || !dwpk || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0)
     return AST_E_BADARG;
-  const int64_t Q = (int64_t)N * (H + 2) * (W + 2);
-  if (ldq < Q || ldq % 8 != 0 || ldq >= 0x7fffffffLL) return AST_E_SHAPE;
+  if (wp < W + 2 || wp % 8 != 0) return AST_E_SHAPE;
+  const int64_t ldq = (int64_t)N * (H + 2) * wp;
+  const int64_t Q = ldq;
+  if (ldq >= 0x7fffffffLL) return AST_E_SHAPE;
   if (Cin % 16 != 0) return AST_E_SHAPE;
   if (!aligned16(dz_planar) || !aligned16(x_planar)) return AST_E_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
@@ -187,7 +194,7 @@ extern "C" int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar, fl
   else if (Cin % 64 == 0) BN = 64;
   else if (Cin % 32 == 0) BN = 32;
   WgParams p = {};
-  p.Cin = Cin; p.Cout = Cout; p.W = W;
+  p.Cin = Cin; p.Cout = Cout; p.wp = wp;
   p.m_blocks = (Cout + 127) / 128;
   p.n_blocks = Cin / BN;
   p.ksteps_total = (int)((Q + WG_KBLK - 1) / WG_KBLK);
@@ -213,10 +220,10 @@ extern "C" int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar, fl
     if (r) return r;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)ldq, (uint64_t)Cin};
-    const uint64_t str[1] = {(uint64_t)ldq * 2};
-    const uint32_t box[2] = {WG_KBLK, (uint32_t)BN};
-    int r = encode_bf16_map(&tmB, x_planar, 2, dims, str, box);
+    const uint64_t dims[3] = {(uint64_t)ldq, (uint64_t)Cin, 3};
+    const uint64_t str[2] = {(uint64_t)ldq * 2, (uint64_t)ldq * 2 * Cin};
+    const uint32_t box[3] = {WG_KBLK, (uint32_t)BN, 1};
+    int r = encode_bf16_map(&tmB, x_planar, 3, dims, str, box);
     if (r) return r;
   }
   switch (BN) {

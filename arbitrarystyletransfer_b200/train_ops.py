@@ -14,9 +14,13 @@ from . import _lib as L
 from . import engine as E
 
 
+def _wp(W):
+    """planar row pitch: multiple of 8 pixels (16 B) >= W + 2, so row shifts stay TMA-aligned"""
+    return (W + 2 + 7) // 8 * 8
+
+
 def _ldq(N, H, W):
-    q = N * (H + 2) * (W + 2)
-    return (q + 7) // 8 * 8
+    return N * (H + 2) * _wp(W)
 
 
 def _zeros_native(N, H, W, C, halo, dev):
@@ -36,23 +40,27 @@ def pack_ex(w, flip, rows_pad=0, cols_pad=0, row_scale=None):
     return out
 
 
-def to_planar(native, N, C, H, W, src_halo, copy_halo, ldq):
+def to_planar(native, N, C, H, W, src_halo, copy_halo, nshift=1):
+    """native -> [C][ldq] (nshift 1) or the three column-shifted copies [3][C][ldq] (nshift 3)."""
     lib = L.load()
-    out = torch.empty((C, ldq), device=native.device, dtype=torch.bfloat16)
+    ldq = _ldq(N, H, W)
+    shape = (C, ldq) if nshift == 1 else (3, C, ldq)
+    out = torch.empty(shape, device=native.device, dtype=torch.bfloat16)
     L.check(lib.ast_native_to_planar(native.data_ptr(), out.data_ptr(), N, C, H, W, src_halo,
-                                     int(copy_halo), ldq, L.stream_ptr(native.device)),
+                                     int(copy_halo), _wp(W), nshift, L.stream_ptr(native.device)),
             "ast_native_to_planar")
     return out
 
 
-def conv_wgrad(dz_planar, x_planar, N, H, W, cin, cout, ldq, w_like, b_like):
+def conv_wgrad(dz_planar, x_planar3, N, H, W, cin, cout, w_like, b_like):
     """(dW OIHW fp32, db fp32) of one 3x3 conv from the planar operands."""
     lib = L.load()
     dev = dz_planar.device
     st = L.stream_ptr(dev)
+    ldq = _ldq(N, H, W)
     dwpk = torch.empty((9, cout, cin), device=dev, dtype=torch.float32)
-    L.check(lib.ast_conv3x3_wgrad(dz_planar.data_ptr(), x_planar.data_ptr(), dwpk.data_ptr(), N, H, W,
-                                  cin, cout, ldq, st), "ast_conv3x3_wgrad")
+    L.check(lib.ast_conv3x3_wgrad(dz_planar.data_ptr(), x_planar3.data_ptr(), dwpk.data_ptr(), N, H, W,
+                                  cin, cout, _wp(W), st), "ast_conv3x3_wgrad")
     gw = torch.empty_like(w_like, dtype=torch.float32, memory_format=torch.contiguous_format)
     gb = torch.empty_like(b_like, dtype=torch.float32) if b_like is not None else None
     L.check(lib.ast_unpack_wgrad(dwpk.data_ptr(), gw.data_ptr(), dz_planar.data_ptr(), L.ptr(gb), cout,
@@ -112,12 +120,11 @@ class DecoderFn(torch.autograd.Function):
             cin, cout, relu, up = E.DECODER_SPEC[i]
             Hi, Wi = sizes[i]
             cz = dZ.shape[3]
-            ldq = _ldq(N, Hi, Wi)
-            dzT = to_planar(dZ, N, cz, Hi, Wi, 2, False, ldq)
-            xT = to_planar(acts[i], N, cin, Hi, Wi, 1, True, ldq)
             need_w, need_b = ctx.needs_input_grad[2 + 2 * i], ctx.needs_input_grad[3 + 2 * i]
             if need_w or need_b:
-                gw, gb = conv_wgrad(dzT, xT, N, Hi, Wi, cin, cout, ldq, params[2 * i], params[2 * i + 1])
+                dzT = to_planar(dZ, N, cz, Hi, Wi, 2, False)
+                xT = to_planar(acts[i], N, cin, Hi, Wi, 1, True, nshift=3)
+                gw, gb = conv_wgrad(dzT, xT, N, Hi, Wi, cin, cout, params[2 * i], params[2 * i + 1])
                 grads[2 * i] = gw if need_w else None
                 grads[2 * i + 1] = gb if need_b else None
             if i == 0:

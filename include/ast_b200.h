@@ -232,15 +232,18 @@ int ast_vgg_bwd_prep(const void* Y, const void* G, const void* tap_post, const v
 int ast_dec_bwd_fold(const void* dXpad, const void* Xi, void* dZ, int N, int C, int Hi, int Wi,
                      int up, int relu, void* stream);
 
-/* native (halo width src_halo) -> channel-planar bf16 [C][ldq], q over the 1-halo padded grid;
- * ldq >= N*(H+2)*(W+2), multiple of 8.  copy_halo = 0 writes a zero halo. */
+/* native (halo width src_halo) -> channel-planar bf16 [nshift][C][ldq], q = (n*(H+2)+ph)*wp + pw
+ * over the 1-halo padded grid with row pitch wp (multiple of 8, >= W+2; ldq = N*(H+2)*wp).
+ * copy_halo = 0 writes a zero halo.  nshift = 1: planar[c][q] = x[c][q]; nshift = 3: the three
+ * column-shifted copies planar[s][c][q] = x[c][q+s-1] that the kw taps of the wgrad GEMM read. */
 int ast_native_to_planar(const void* native, void* planar, int N, int C, int H, int W, int src_halo,
-                         int copy_halo, int64_t ldq, void* stream);
+                         int copy_halo, int wp, int nshift, void* stream);
 
 /* Weight gradient on the tensor cores: dwpk [9][Cout][Cin] fp32 (overwritten) =
- * sum_q dzT[co][q] * xT[ci][q + (kh-1)*(W+2) + (kw-1)].  Cin % 16 == 0. */
-int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar, float* dwpk, int N, int H, int W,
-                      int Cin, int Cout, int64_t ldq, void* stream);
+ * sum_q dzT[co][q] * x[ci][q + (kh-1)*wp + (kw-1)], dz_planar [Cout][ldq] (nshift 1, zero halo),
+ * x_planar3 [3][Cin][ldq] (nshift 3, halo copied).  Cin % 16 == 0. */
+int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar3, float* dwpk, int N, int H, int W,
+                      int Cin, int Cout, int wp, void* stream);
 
 /* dwpk -> OIHW fp32 gradient (overwrite or accumulate); b_grad (optional) = row sums of dz_planar. */
 int ast_unpack_wgrad(const float* dwpk, float* w_grad, const void* dz_planar, float* b_grad, int Cout,

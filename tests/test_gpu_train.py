@@ -41,10 +41,14 @@ def test_wgrad_gemm(shape):
     lib = L.load()
     dzd = dz.cuda().contiguous()
     L.check(lib.ast_nchw_to_native_ex(dzd.data_ptr(), dzn.data_ptr(), N, cout, H, W, dzn.shape[3], 2, L.stream_ptr()))
-    ldq = T._ldq(N, H, W)
-    dzT = T.to_planar(dzn, N, dzn.shape[3], H, W, 2, False, ldq)
-    xT = T.to_planar(xin, N, cin, H, W, 1, True, ldq)
-    gw, gb = T.conv_wgrad(dzT, xT, N, H, W, cin, cout, ldq, w.detach().cuda(), b.detach().cuda())
+    dzT = T.to_planar(dzn, N, dzn.shape[3], H, W, 2, False)
+    xT = T.to_planar(xin, N, cin, H, W, 1, True, nshift=3)
+    # planar layout: q = (n*(H+2)+ph)*wp + pw, zero beyond pw = W+1, copy s holds x[q+s-1]
+    wp = T._wp(W)
+    refx = F.pad(F.pad(x, (1, 1, 1, 1), mode="reflect"), (0, wp - W - 2)).permute(1, 0, 2, 3).reshape(cin, -1)
+    assert torch.equal(xT[1].float().cpu(), refx)
+    assert torch.equal(xT[0].float().cpu()[:, 1:], refx[:, :-1]) and torch.equal(xT[2].float().cpu()[:, :-1], refx[:, 1:])
+    gw, gb = T.conv_wgrad(dzT, xT, N, H, W, cin, cout, w.detach().cuda(), b.detach().cuda())
     assert rel(gw.cpu(), w.grad) < 2e-3 and rel(gb.cpu(), b.grad) < 2e-3
 
 
