@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="pairs timed on the CPU arm (0 = auto: about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-2 training-step timing")
     ap.add_argument("--layers-out", default="", help="write the per-layer timing table (JSON) here")
     return ap.parse_args()
 
@@ -267,6 +268,70 @@ def time_adain_k1(N, reps=10):
     return 3.0 * c.numel() * 4, ms
 
 
+def time_train_step(dev, steps=8, warmup=3, batch=8, size=256):
+    """BASELINE config 2: AdaIN decoder training step, batch 8 at 256x256, content + mean/std(+Gram)
+    style loss through the frozen VGG taps relu1_1..relu4_1, clip_grad_norm 2.0, Adam(2e-4) --
+    the reference's step glue (train.py:287-300) unchanged on this package's modules."""
+    from arbitrarystyletransfer_b200 import models as M, losses as Ls
+    taps = ['relu_1', 'relu_3', 'relu_5', 'relu_9']
+    torch.manual_seed(0)
+    enc = M.PretrainedEncoder(taps).to(dev)
+    M.calibrate_encoder_bias(enc)
+    torch.manual_seed(1)
+    dec = M.ClassicDecoder().to(dev)
+    opt = torch.optim.Adam(dec.parameters(), lr=2e-4, betas=(0.9, 0.999), eps=1e-5)
+    adain = M.AdaIN()
+    g = torch.Generator().manual_seed(201)
+    c = torch.rand(batch, 3, size, size, generator=g).to(dev)
+    s = torch.rand(batch, 3, size, size, generator=g).to(dev)
+
+    def step():
+        with torch.no_grad():
+            fc = enc(c)[-1]
+            st = enc(s)
+            t = adain(fc, st[-1])
+        opt.zero_grad(set_to_none=True)
+        gimg = dec(t)
+        gt = enc(gimg)
+        loss = Ls.compute_content_loss(gt[-1], t)
+        for a, b in zip(gt, st):
+            loss = loss + Ls.compute_style_loss(a, b)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(dec.parameters(), 2.0)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        loss = step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    # algorithmic FLOPs: fwd 3 encoders + decoder, bwd encoder dgrad + decoder dgrad + wgrad (SURVEY 8d)
+    f_img = flops_per_image(size)          # 2 enc + 1 dec
+    enc_f = (f_img - _dec_flops(size)) / 2
+    flops = batch * (3 * enc_f + _dec_flops(size) + enc_f + 2 * _dec_flops(size))
+    return {"metric": "train_steps_per_s_256x256_b8_decoder", "value": 1e3 / ms, "unit": "steps/s",
+            "ms_per_step": ms, "img_per_s": batch * 1e3 / ms, "loss_finite": bool(torch.isfinite(loss).item()),
+            "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+            "config": f"BASELINE config 2: batch {batch} at {size}x{size}, taps relu1_1..relu4_1, content + "
+                      "style (mean/std + Gram) loss, clip 2.0, Adam(2e-4), 1 GPU"}
+
+
+def _dec_flops(size):
+    from arbitrarystyletransfer_b200.engine import DECODER_SPEC
+    h, f = size // 8, 0.0
+    for cin, cout, _, up in DECODER_SPEC:
+        f += 2.0 * cout * cin * 9 * h * h
+        if up:
+            h *= 2
+    return f
+
+
 def run_native(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -370,6 +435,11 @@ def run_native(args):
             for r, a in zip(rows, alt):
                 r["ms_tapbox"], r["tflops_tapbox"] = a["ms"], a["tflops"]
             json.dump(rows, open(args.layers_out, "w"), indent=1)
+        if world == 1 and not args.no_train:
+            try:
+                line["train"] = time_train_step(dev)
+            except Exception as e:  # the headline line must still be printed
+                line["train"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(S, args.cpu_sample or 8)
         print(json.dumps(line), flush=True)
