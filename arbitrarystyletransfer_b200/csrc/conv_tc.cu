@@ -690,6 +690,7 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
   __shared__ __align__(128) uint8_t s_b[F_B_BYTES];
   __shared__ __align__(8) uint64_t s_bar[2 * F_STAGES + 4];
   __shared__ uint32_t s_tmem;
+  __shared__ float s_patch[2][3 * (TILE_H + 2) * (TILE_W + 2)];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t bars = smem_u32(s_bar);
@@ -725,52 +726,70 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
 
   if (warp < 4) {
     // ===================== im2col producers =====================
-    // One pixel per thread.  All 27 loads are unconditional (clamped address, value selected
-    // afterwards) so they issue back to back, and the loads of tile i+1 are in flight while tile i
-    // is packed and stored (software pipeline over the persistent tile loop).
+    // The 128 producer threads first stage the tile's (8+2) x (16+2) x 3 input patch -- normalised,
+    // zero outside the image -- in shared memory with ~4 coalesced loads each (instead of 27 cached
+    // loads per pixel), double buffered so the global loads of tile i+1 are in flight while tile i
+    // is expanded; each thread then reads its pixel's 27 taps from the patch, rounds to bf16 and
+    // stores its 64-byte row of the A tile.
     const int r = threadIdx.x;           // tile row = pixel
     const int hl = r >> 4, wl = r & 15;
-    auto gather = [&](int tile, float (&v)[27]) {
+    constexpr int PW = TILE_W + 2, PH = TILE_H + 2, PN = 3 * PH * PW;  // 540 floats
+    constexpr int PER = (PN + 127) / 128;                                 // 5 loads per thread
+    auto fetch = [&](int tile, float (&v)[PER]) {
       int t = tile;
       const int twi = t % p.tiles_w; t /= p.tiles_w;
       const int thi = t % p.tiles_h;
       const int n = t / p.tiles_h;
-      const int h = thi * TILE_H + hl, w = twi * TILE_W + wl;
-      const bool pix_ok = (h < p.H) && (w < p.W);
+      const int h0 = thi * TILE_H - 1, w0 = twi * TILE_W - 1;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float* ip = fp.img + ((int64_t)n * 3 + ci) * p.H * p.W;
+      for (int j = 0; j < PER; ++j) {
+        const int e = r + j * 128;
+        const int ci = e / (PH * PW), rem = e - ci * (PH * PW);
+        const int ih = h0 + rem / PW, iw = w0 + rem % PW;
+        const bool ok = e < PN && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+        const int ihc = min(max(ih, 0), p.H - 1), iwc = min(max(iw, 0), p.W - 1), cic = min(ci, 2);
+        float x = __ldg(fp.img + (((int64_t)n * 3 + cic) * p.H + ihc) * p.W + iwc);
+        if (fp.normalise) x = (x - fp.mean[cic]) * fp.rstd[cic];
+        // zero padding applies to the NORMALISED image (models.py:131, then Conv2d padding=1)
+        v[j] = ok ? x : 0.f;
+      }
+    };
+    auto stash = [&](int buf, const float (&v)[PER]) {
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const int ih = h + kh - 1;
-          const int ihc = min(max(ih, 0), p.H - 1);
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int iw = w + kw - 1;
-            const int iwc = min(max(iw, 0), p.W - 1);
-            float x = __ldg(ip + (int64_t)ihc * p.W + iwc);
-            if (fp.normalise) x = (x - fp.mean[ci]) * fp.rstd[ci];
-            // zero padding applies to the NORMALISED image (models.py:131, then Conv2d padding=1)
-            const bool ok = pix_ok && ih == ihc && iw == iwc;
-            v[ci * 9 + kh * 3 + kw] = ok ? x : 0.f;
-          }
-        }
+      for (int j = 0; j < PER; ++j) {
+        const int e = r + j * 128;
+        if (e < PN) s_patch[buf][e] = v[j];
       }
     };
     int stage = 0;
     uint32_t phase = 0;
-    float cur[27], nxt[27];
+    int cur = 0;
+    float pre[PER];
     int tile = blockIdx.x;
-    if (tile < p.num_tiles) gather(tile, cur);
+    if (tile < p.num_tiles) {
+      fetch(tile, pre);
+      stash(0, pre);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (; tile < p.num_tiles; tile += gridDim.x) {
       const int ntile = tile + gridDim.x;
-      if (ntile < p.num_tiles) gather(ntile, nxt);
+      if (ntile < p.num_tiles) fetch(ntile, pre);
       uint32_t pk[16];
+      {
+        float v[28];
+        v[27] = 0.f;
 #pragma unroll
-      for (int i = 0; i < 13; ++i) pk[i] = pack_bf16(cur[2 * i], cur[2 * i + 1]);
-      pk[13] = pack_bf16(cur[26], 0.f);
-      pk[14] = 0u;
-      pk[15] = 0u;
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              v[ci * 9 + kh * 3 + kw] = s_patch[cur][(ci * PH + hl + kh) * PW + wl + kw];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+        pk[14] = 0u;
+        pk[15] = 0u;
+      }
       mbar_wait(empty_bar(stage), phase ^ 1u);
       uint8_t* row = &s_a[stage][0] + (uint32_t)(r >> 3) * F_SBO + (r & 7) * 16;
 #pragma unroll
@@ -781,8 +800,9 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
-#pragma unroll
-      for (int i = 0; i < 27; ++i) cur[i] = nxt[i];
+      if (ntile < p.num_tiles) stash(cur ^ 1, pre);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // patch[cur^1] complete, patch[cur] free
+      cur ^= 1;
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================

@@ -200,31 +200,34 @@ __global__ void __launch_bounds__(kNThreads) native_coef_kernel(const NativeCoef
 }
 
 // Stage 3: apply + alpha blend, write interior and (optionally) the reflection halo.
+// grid = (pixel chunks, N); a thread owns 8 consecutive channels (its 8 coefficient quadruples stay
+// in registers) and walks the pixels of its chunk: one 16-byte load and store per pixel.
 __global__ void __launch_bounds__(kNThreads)
 native_apply_kernel(const __nv_bfloat16* __restrict__ content, const float4* __restrict__ coef,
                     __nv_bfloat16* __restrict__ out, int N, int C, int H, int W, float alpha,
-                    int reflect) {
+                    int reflect, int chunks) {
   const int cvecs = C / 8;
-  const int64_t total = (int64_t)N * H * W * cvecs;
+  const int groups = kNThreads / cvecs;
+  const int g = threadIdx.x / cvecs, v = threadIdx.x % cvecs;
+  if (g >= groups) return;
+  const int n = blockIdx.y;
   const bool blend = alpha != 1.f;
-  for (int64_t i = (int64_t)blockIdx.x * kNThreads + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * kNThreads) {
-    const int v = (int)(i % cvecs);
-    int64_t r = i / cvecs;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H);
-    const int n = (int)(r / H);
-    const int64_t img = (int64_t)n * (H + 2) * (W + 2);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(
-        content + ((img + (int64_t)(h + 1) * (W + 2) + (w + 1)) * C + v * 8)));
+  float4 k[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k[j] = __ldg(coef + (int64_t)n * C + v * 8 + j);
+  const int64_t npix = (int64_t)H * W;
+  const int64_t per = (npix + chunks - 1) / chunks;
+  const int64_t p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
+  const int64_t img = (int64_t)n * (H + 2) * (W + 2);
+  for (int64_t p = p0 + g; p < p1; p += groups) {
+    const int h = (int)(p / W), w = (int)(p % W);
+    const uint4 u = ld_stream_u4(content + ((img + (int64_t)(h + 1) * (W + 2) + (w + 1)) * C + v * 8));
     float x[8];
     Vec16<true>::unpack(u, x);
-    const float4* cf = coef + (int64_t)n * C + v * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 k = __ldg(cf + j);
-      const float t = (x[j] - k.x) * k.y;   // models.py:47
-      float y = fmaf(t, k.z, k.w);          // models.py:50
+      const float t = (x[j] - k[j].x) * k[j].y;   // models.py:47
+      float y = fmaf(t, k[j].z, k[j].w);          // models.py:50
       if (blend) y = fmaf(alpha, y, (1.f - alpha) * x[j]);  // models.py:471
       x[j] = y;
     }
@@ -347,12 +350,12 @@ extern "C" int ast_adain_native_fwd(const void* content, const void* const* styl
   native_coef_kernel<<<dim3((C + kNThreads - 1) / kNThreads, N), kNThreads, 0, s>>>(ca);
   AST_CHECK_LAUNCH();
 
-  const int64_t total = (int64_t)N * H * W * (C / 8);
-  int64_t nb = (total + kNThreads - 1) / kNThreads;
-  if (nb > 148 * 16) nb = 148 * 16;
-  native_apply_kernel<<<(unsigned)nb, kNThreads, 0, s>>>(
+  int64_t achunks = (8 * 148 + N - 1) / N;
+  if (achunks > (int64_t)H * W / 16) achunks = (int64_t)H * W / 16;
+  if (achunks < 1) achunks = 1;
+  native_apply_kernel<<<dim3((unsigned)achunks, N), kNThreads, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(content), coef, reinterpret_cast<__nv_bfloat16*>(out), N,
-      C, H, W, alpha, halo == AST_HALO_REFLECT);
+      C, H, W, alpha, halo == AST_HALO_REFLECT, (int)achunks);
   AST_CHECK_LAUNCH();
   return 0;
 }
