@@ -81,6 +81,35 @@ struct ConvParams {
 
 constexpr int EPI_NCHW32 = 3;  // internal: last decoder layer, fp32 NCHW image out
 
+// Persistent-loop tile cursor: tile -> (n-block, tile column, tile row, image), advanced by
+// gridDim.x with mixed-radix carries instead of four integer divisions per tile (the epilogue warps
+// are instruction-latency bound, every instruction per tile counts).
+struct TileCursor {
+  int nb, twi, thi, n;
+  int g0, g1, g2, g3;
+  int NB, TWc, THc;
+  __device__ __forceinline__ void init(const ConvParams& p, int tile, int stride) {
+    NB = p.n_blocks; TWc = p.tiles_w; THc = p.tiles_h;
+    int t = tile;
+    nb = t % NB; t /= NB;
+    twi = t % TWc; t /= TWc;
+    thi = t % THc; n = t / THc;
+    t = stride;
+    g0 = t % NB; t /= NB;
+    g1 = t % TWc; t /= TWc;
+    g2 = t % THc; g3 = t / THc;
+  }
+  __device__ __forceinline__ void next() {
+    nb += g0;
+    int c = nb >= NB; nb -= c ? NB : 0;
+    twi += g1 + c;
+    c = twi >= TWc; twi -= c ? TWc : 0;
+    thi += g2 + c;
+    c = thi >= THc; thi -= c ? THc : 0;
+    n += g3 + c;
+  }
+};
+
 // Output coordinates (unpadded grid, -1 and Xo are the halo) that conv coordinate x feeds.
 template <int EPI>
 __device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)[4]) {
@@ -110,7 +139,7 @@ __device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)
 template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2>
 __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
                                               uint32_t tfull_bar0, uint32_t tempty_bar0) {
-  constexpr int CH = BN >= 32 ? 32 : 16;  // columns per tcgen05.ld
+  constexpr int CH = (BN >= 32 && BN / 32 >= NG) ? 32 : 16;  // columns per tcgen05.ld
   constexpr int TH = TILE_M / TW;         // tile = TH rows x TW cols of pixels, row-major in M
   constexpr int NCH = BN / CH;
   // 4*NG epilogue warps: warp ew owns TMEM lane quarter e = ew % 4 (hardware rule: a warp may only
@@ -122,12 +151,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
   const bool reflect = p.halo == AST_HALO_REFLECT;
   int as = 0;
   uint32_t aphase = 0;
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-    int t = tile;
-    const int nb = t % p.n_blocks; t /= p.n_blocks;
-    const int twi = t % p.tiles_w; t /= p.tiles_w;
-    const int thi = t % p.tiles_h;
-    const int n = t / p.tiles_h;
+  TileCursor cur;
+  cur.init(p, blockIdx.x, gridDim.x);
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, cur.next()) {
+    const int nb = cur.nb, twi = cur.twi, thi = cur.thi, n = cur.n;
     const int h = thi * TH + hl, w = twi * TW + wl;
     const bool in_img = (h < p.H) && (w < p.W);
 
@@ -368,11 +395,17 @@ struct Cfg2 {
   static constexpr int SMEM_BYTES = NA * A2_BYTES + NB * B_BYTES + NBAR * 8 + 16 + 1024;
 };
 
-constexpr int kConv2Threads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: epilogue
-constexpr int kEpi2Groups = 2;
+// warps 0-3: TMA / MMA / TMEM alloc / idle; then 4 * NG epilogue warps.  N <= 128 uses 16 epilogue
+// warps (4 per SM sub-partition): their per-tile work is short and latency bound, more resident
+// warps is what hides it; N = 256 keeps 8 (tensor-bound, fewer registers spent).
+template <int BN>
+struct Epi2 {
+  static constexpr int NG = (BN == 256) ? 2 : 4;
+  static constexpr int THREADS = 128 + 128 * NG;
+};
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kConv2Threads, 1)
+__global__ void __launch_bounds__(Epi2<BN>::THREADS, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const ConvParams p) {
   using C = Cfg2<BN>;
@@ -405,7 +438,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < C::NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4 * kEpi2Groups); }
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4 * Epi2<BN>::NG); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -520,7 +553,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    epilogue_loop<BN, EPI, T2_W, kEpi2Groups, C::NACC>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0));
+    epilogue_loop<BN, EPI, T2_W, Epi2<BN>::NG, C::NACC>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0));
   }
 
   tc_fence_before();
@@ -542,7 +575,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     attr_done = true;
   }
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-  kern<<<grid, kConv2Threads, C::SMEM_BYTES, s>>>(tmA, tmB, p);
+  kern<<<grid, Epi2<BN>::THREADS, C::SMEM_BYTES, s>>>(tmA, tmB, p);
   AST_CHECK_LAUNCH();
   return 0;
 }

@@ -123,3 +123,31 @@ def test_modules_drop_in(weights, golden_networks):
     net = M.StyleTransferNet(enc9, dec)
     img = net(R.rand_image(1, 64, 101).cuda(), R.rand_image(1, 64, 102).cuda()).cpu()
     assert R.psnr(img, T(g["s64_img"])) >= 40.0
+
+
+def test_config5_2048_four_style_interpolation_properties(engine):
+    """BASELINE config 5 at full size (2048x2048, 4-style interpolation weights): properties that need
+    no CPU run of 12 TFLOP -- finiteness, linearity of the interpolation in the style statistics
+    (four copies of one style with any weights == that single style), alpha = 0 independence of the
+    styles, and the K1 kernel agreeing with the in-pipeline AdaIN on the 256x256 relu4_1 maps."""
+    from arbitrarystyletransfer_b200 import engine as E, functional as Fn
+    c = R.rand_image(1, 2048, 501).cuda()
+    styles = [R.rand_image(1, 2048, 502 + k).cuda() for k in range(4)]
+    w = [0.4, 0.3, 0.2, 0.1]
+    out = engine.stylize(c, styles, alpha=1.0, style_weights=w).clone()
+    assert out.shape == (1, 3, 2048, 2048) and torch.isfinite(out).all()
+    same = engine.stylize(c, [styles[0]] * 4, alpha=1.0, style_weights=w).clone()
+    single = engine.stylize(c, [styles[0]], alpha=1.0, style_weights=[1.0])
+    assert R.psnr(same.cpu(), single.cpu()) >= 60.0
+    z1 = engine.stylize(c, styles, alpha=0.0, style_weights=w).clone()
+    z2 = engine.stylize(c, styles[::-1], alpha=0.0, style_weights=w)
+    torch.testing.assert_close(z1, z2, rtol=0, atol=0)
+    # relu4_1 maps (1, 512, 256, 256): rows of 65 536 elements -> cluster-split K1 path in fp32
+    fc = E.native_to_nchw(engine.encode(c, "c"))
+    fs = [E.native_to_nchw(engine.encode(s, f"s{k}")) for k, s in enumerate(styles)]
+    t_k1 = Fn.adain_forward(fc, fs, w, alpha=0.6)
+    t_native = E.native_to_nchw(engine.adain(engine.encode(c, "c"),
+                                             [engine.encode(s, f"s{k}") for k, s in enumerate(styles)], w, alpha=0.6))
+    assert rel_l2(t_native, t_k1) < 1e-2      # bf16 output rounding of the native path
+    ref = R.adain_multi(fc.cpu(), [f.cpu() for f in fs], w, alpha=0.6)
+    torch.testing.assert_close(t_k1.cpu(), ref, rtol=1e-5, atol=1e-5 * ref.abs().max().item())
