@@ -17,6 +17,8 @@
 // (one elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias -> ReLU
 // -> {plain | 2x2 max-pool via shuffles | nearest x2 upsample} -> bf16 -> global, plus the
 // reflection halo of the output when the next layer is a decoder conv).
+#include <cstdio>
+#include <cstdlib>
 #include "tc.cuh"
 
 namespace ast {
@@ -77,9 +79,18 @@ struct ConvParams {
   float* out_nchw;   // EPI_NCHW32 only: fp32 [N][cout_real][H][W]
   int cout_real;     // EPI_NCHW32 only: channels actually stored (<= BN)
   int clamp01;       // EPI_NCHW32 only: Hardtanh(0,1) (models.py:304, 315)
+  long long* dbg;    // optional [gridDim.x][8] wait-cycle counters per role (AST_CONV_DEBUG=1)
 };
 
 constexpr int EPI_NCHW32 = 3;  // internal: last decoder layer, fp32 NCHW image out
+
+// wait + optional accounting of the cycles spent waiting (debug instrumentation)
+__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, bool dbg, long long& acc) {
+  if (!dbg) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
 
 // Persistent-loop tile cursor: tile -> (n-block, tile column, tile row, image), advanced by
 // gridDim.x with mixed-radix carries instead of four integer divisions per tile (the epilogue warps
@@ -149,10 +160,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
   const int hl = (32 * e + lane) / TW;
   const int wl = (32 * e + lane) % TW;
   const bool reflect = p.halo == AST_HALO_REFLECT;
+  const bool wide_st = (reinterpret_cast<uintptr_t>(p.out) & 31u) == 0 && (p.Cout % 16) == 0;
   int as = 0;
   uint32_t aphase = 0;
   TileCursor cur;
   cur.init(p, blockIdx.x, gridDim.x);
+  long long dbg_wait = 0;
+  const long long dbg_t0 = clock64();
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, cur.next()) {
     const int nb = cur.nb, twi = cur.twi, thi = cur.thi, n = cur.n;
     const int h = thi * TH + hl, w = twi * TW + wl;
@@ -170,7 +184,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
       nc = out_targets<EPI>(w, p.Wo, reflect, cols);
     }
 
-    mbar_wait(tfull_bar0 + 8u * as, aphase);
+    mbar_wait_acc(tfull_bar0 + 8u * as, aphase, p.dbg != nullptr, dbg_wait);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
     uint32_t vnext[CH];
@@ -239,10 +253,15 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
             for (int ci = 0; ci < nc; ++ci) {
               __nv_bfloat16* o = p.out +
                   (((int64_t)n * (p.Ho + 2) + (rows[ri] + 1)) * (p.Wo + 2) + (cols[ci] + 1)) * p.Cout + ch0;
-              uint4* o4 = reinterpret_cast<uint4*>(o);
+              if (wide_st) {
 #pragma unroll
-              for (int q = 0; q < CH / 8; ++q)
-                o4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                for (int q = 0; q < CH / 16; ++q) st_global_v8(o + 16 * q, &pk[8 * q]);
+              } else {
+                uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+                for (int q = 0; q < CH / 8; ++q)
+                  o4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              }
             }
           }
         }
@@ -252,6 +271,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty_bar0 + 8u * as);
     if (++as == NACC) { as = 0; aphase ^= 1u; }
+  }
+  if (p.dbg && ew == 0 && lane == 0) {
+    p.dbg[blockIdx.x * 8 + 4] = dbg_wait;               // epilogue warp 0: waiting for an accumulator
+    p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;     // epilogue warp 0: total loop time
   }
 }
 
@@ -387,8 +410,11 @@ constexpr int A2_BYTES = T2_BOX_H * T2_W * KBLK * 2;  // 18 KB
 template <int BN>
 struct Cfg2 {
   static constexpr int B_BYTES = BN * KBLK * 2;
-  static constexpr int NA = (BN >= 128) ? 4 : (BN == 64 ? 6 : 8);
-  static constexpr int NB = (BN == 256) ? 4 : 9;
+  static constexpr int NA = (BN >= 128) ? 4 : 8;
+  static constexpr int NB = (BN == 256) ? 4 : 9;       // weight tap slots
+  // BN <= 128: the nine tap slots form three groups (one per kw, holding kh = 0..2): one barrier
+  // pair per group instead of per tap, or no barrier traffic at all when the weights stay resident.
+  static constexpr bool GROUPED = BN <= 128;
   static constexpr int NACC = (BN <= 128) ? 4 : 2;  // TMEM accumulator stages (<= 512 columns)
   static constexpr int TMEM_COLS = (NACC * BN < 32) ? 32 : NACC * BN;
   static constexpr int NBAR = 2 * NA + 2 * NB + 2 * NACC;
@@ -451,13 +477,16 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       if (resident) {
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_expect_tx(bfull(tap), C::B_BYTES);
-          tma_load_3d(b_base + tap * C::B_BYTES, &tmB, bfull(tap), 0, 0, tap);
+        // tap (kh,kw) lives in slot kw*3 + kh (group kw), loaded once per CTA
+        for (int kw = 0; kw < 3; ++kw) {
+          mbar_expect_tx(bfull(kw), 3 * C::B_BYTES);
+          for (int kh = 0; kh < 3; ++kh)
+            tma_load_3d(b_base + (kw * 3 + kh) * C::B_BYTES, &tmB, bfull(kw), 0, 0, kh * 3 + kw);
         }
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      long long dbg_pa = 0, dbg_pb = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int t = tile;
         const int nb = t % p.n_blocks; t /= p.n_blocks;
@@ -467,89 +496,122 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int h0 = thi * T2_H, w0 = twi * T2_W;
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = 0; kw < 3; ++kw) {
-            mbar_wait(aempty(sa), pa ^ 1u);
+            mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa);
             mbar_expect_tx(afull(sa), A2_BYTES);
             tma_load_4d(a_base + sa * A2_BYTES, &tmA, afull(sa), cb * KBLK, w0 + kw, h0, n);
             if (++sa == C::NA) { sa = 0; pa ^= 1u; }
             if (!resident) {
-              for (int kh = 0; kh < 3; ++kh) {
-                mbar_wait(bempty(sb), pb ^ 1u);
-                mbar_expect_tx(bfull(sb), C::B_BYTES);
-                tma_load_3d(b_base + sb * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, nb * BN, kh * 3 + kw);
-                if (++sb == C::NB) { sb = 0; pb ^= 1u; }
+              if constexpr (C::GROUPED) {
+                mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb);
+                mbar_expect_tx(bfull(sb), 3 * C::B_BYTES);
+                for (int kh = 0; kh < 3; ++kh)
+                  tma_load_3d(b_base + (sb * 3 + kh) * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, nb * BN,
+                              kh * 3 + kw);
+                if (++sb == 3) { sb = 0; pb ^= 1u; }
+              } else {
+                for (int kh = 0; kh < 3; ++kh) {
+                  mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb);
+                  mbar_expect_tx(bfull(sb), C::B_BYTES);
+                  tma_load_3d(b_base + sb * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, nb * BN, kh * 3 + kw);
+                  if (++sb == C::NB) { sb = 0; pb ^= 1u; }
+                }
               }
             }
           }
         }
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_pa; p.dbg[blockIdx.x * 8 + 1] = dbg_pb; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    // The issue thread is latency-bound, not throughput-bound: an mbarrier probe costs ~90 cycles
-    // even when the phase has completed, so every wait is PROBED one step ahead (the MMAs of the
-    // current step issue while the probe is in flight) and descriptors are advanced by adding
-    // constants to one precomputed 64-bit value (start address field = bits [0,14) in 16-byte
-    // units; shared memory is < 256 KB, so the add never carries out of the field).
-    if (lane == 0) {
+    // ===================== MMA issuer =====================
+    // The whole warp stays converged (all lanes wait on the barriers) and ONE elected lane issues:
+    // with warp-uniform operands the tcgen05.mma / commit instructions take their descriptors from
+    // uniform registers directly.  Descriptors advance by adding constants to one precomputed
+    // 64-bit value (start-address field = bits [0,14) in 16-byte units; shared memory is < 256 KB so
+    // the add never carries out of the field).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
       const uint64_t a_desc0 = make_sdesc_k128(a_base);
       const uint64_t b_desc0 = make_sdesc_k128(b_base);
+      constexpr uint64_t A_SLOT16 = A2_BYTES >> 4, B_SLOT16 = C::B_BYTES >> 4, KH16 = (T2_W * KBLK * 2) >> 4;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int as = 0;
       uint32_t aphase = 0;
       bool b_resident_ready = false;
-      bool t_ok = mbar_try_wait(tempty(as), aphase ^ 1u);
-      bool a_ok = mbar_try_wait(afull(sa), pa);
-      bool b_ok = resident ? false : mbar_try_wait(bfull(sb), pb);
+      long long dbg_mt = 0, dbg_ma = 0, dbg_mb = 0;
+      const long long dbg_m0 = clock64();
+      const bool dbg = p.dbg != nullptr;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        if (!t_ok) mbar_wait(tempty(as), aphase ^ 1u);
+        mbar_wait_acc(tempty(as), aphase ^ 1u, dbg, dbg_mt);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         uint32_t accum = 0;
         for (int cb = 0; cb < cblocks; ++cb) {
+#pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            if (!a_ok) mbar_wait(afull(sa), pa);
-            const uint64_t a_desc = a_desc0 + (uint64_t)(sa * (A2_BYTES >> 4));
-            int sa_n = sa + 1;
-            uint32_t pa_n = pa;
-            if (sa_n == C::NA) { sa_n = 0; pa_n ^= 1u; }
-            a_ok = mbar_try_wait(afull(sa_n), pa_n);  // probe the next box while this one is consumed
-            for (int kh = 0; kh < 3; ++kh) {
-              int slot;
+            mbar_wait_acc(afull(sa), pa, dbg, dbg_ma);
+            const uint64_t ad = a_desc0 + (uint64_t)sa * A_SLOT16;
+            if constexpr (C::GROUPED) {
+              // one weight group (kh = 0..2 of this kw) per A box: 12 MMAs between barrier operations
+              int grp;
               if (resident) {
-                slot = kh * 3 + kw;
-                if (!b_resident_ready) mbar_wait(bfull(slot), 0u);  // first tile only
+                grp = kw;
+                if (!b_resident_ready) mbar_wait(bfull(kw), 0u);  // first tile only
               } else {
-                slot = sb;
-                if (!b_ok) mbar_wait(bfull(sb), pb);
-                int sb_n = sb + 1;
-                uint32_t pb_n = pb;
-                if (sb_n == C::NB) { sb_n = 0; pb_n ^= 1u; }
-                b_ok = mbar_try_wait(bfull(sb_n), pb_n);
+                grp = sb;
+                mbar_wait_acc(bfull(sb), pb, dbg, dbg_mb);
               }
               tc_fence_after();
-              const uint64_t ad = a_desc + (uint64_t)(kh * ((T2_W * KBLK * 2) >> 4));  // + kh * 1024 B
-              const uint64_t bd = b_desc0 + (uint64_t)(slot * (C::B_BYTES >> 4));
+              const uint64_t bd = b_desc0 + (uint64_t)(grp * 3) * B_SLOT16;
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < KBLK / 16; ++k) {
-                umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, accum);
-                accum = 1u;
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                  for (int k = 0; k < KBLK / 16; ++k) {
+                    umma_bf16(d_tmem, ad + (uint64_t)(kh * KH16 + k * 2), bd + (uint64_t)(kh * B_SLOT16 + k * 2),
+                              idesc, (kh | k) ? 1u : accum);
+                  }
+                }
+                if (!resident) umma_commit(bempty(sb));
+                umma_commit(aempty(sa));
               }
+              __syncwarp();
+              accum = 1u;
               if (!resident) {
-                umma_commit(bempty(sb));
+                if (++sb == 3) { sb = 0; pb ^= 1u; }
+              }
+            } else {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                mbar_wait_acc(bfull(sb), pb, dbg, dbg_mb);
+                tc_fence_after();
+                const uint64_t bd = b_desc0 + (uint64_t)sb * B_SLOT16;
+                if (elect_one_sync()) {
+#pragma unroll
+                  for (int k = 0; k < KBLK / 16; ++k)
+                    umma_bf16(d_tmem, ad + (uint64_t)(kh * KH16 + k * 2), bd + (uint64_t)(k * 2), idesc,
+                              k ? 1u : accum);
+                  umma_commit(bempty(sb));
+                  if (kh == 2) umma_commit(aempty(sa));
+                }
+                __syncwarp();
+                accum = 1u;
                 if (++sb == C::NB) { sb = 0; pb ^= 1u; }
               }
             }
-            umma_commit(aempty(sa));
-            sa = sa_n;
-            pa = pa_n;
+            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
           }
         }
         b_resident_ready = true;
-        umma_commit(tfull(as));
+        if (elect_one_sync()) umma_commit(tfull(as));
+        __syncwarp();
         if (++as == C::NACC) { as = 0; aphase ^= 1u; }
-        t_ok = mbar_try_wait(tempty(as), aphase ^ 1u);
+      }
+      if (p.dbg && lane == 0) {
+        p.dbg[blockIdx.x * 8 + 2] = dbg_ma + dbg_mb;        // MMA warp: waiting for operands
+        p.dbg[blockIdx.x * 8 + 3] = dbg_mt;                 // MMA warp: waiting for a free accumulator
+        p.dbg[blockIdx.x * 8 + 6] = clock64() - dbg_m0;     // MMA warp: total loop time
       }
     }
   } else if (warp >= 4) {
@@ -682,6 +744,32 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   CUtensorMap tmA, tmB;
   r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, BN, kwbox);
   if (r) return r;
+  static const bool dbg_on = getenv("AST_CONV_DEBUG") != nullptr;
+  long long* dbg = nullptr;
+  if (dbg_on && kwbox) {   // debug instrumentation only: allocates and synchronises
+    AST_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * sm_count));
+    AST_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * sm_count, s));
+    p.dbg = dbg;
+  }
+  struct DbgDump {
+    long long* d; int n; const ConvParams& p; int BN; cudaStream_t s;
+    ~DbgDump() {
+      if (!d) return;
+      cudaStreamSynchronize(s);
+      long long* h = new long long[8 * n];
+      cudaMemcpy(h, d, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
+      double a[8] = {0};
+      const int g = p.num_tiles < n ? p.num_tiles : n;
+      for (int i = 0; i < g; ++i) for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / g;
+      const double tiles = (double)p.num_tiles / g;
+      fprintf(stderr, "[conv dbg] Cin=%d Cout=%d H=%d BN=%d tiles/CTA=%.1f | per tile cycles: loop(mma)=%.0f loop(epi)=%.0f | "
+              "producer wait A-empty=%.0f B-empty=%.0f | mma wait operands=%.0f accumulator=%.0f | epilogue wait tfull=%.0f\n",
+              p.Cin, p.Cout, p.H, BN, tiles, a[6] / tiles, a[5] / tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles,
+              a[3] / tiles, a[4] / tiles);
+      delete[] h;
+      cudaFree(d);
+    }
+  } dump{dbg, sm_count, p, BN, s};
   if (kwbox) {
     switch (BN) {
       case 256: return launch_tc2_epi<256>(d->epilogue, tmA, tmB, p, sm_count, s);
