@@ -250,3 +250,57 @@ class StyleTransferEngine:
     def launches_per_stylize(self, K: int = 1) -> int:
         """Kernels of libast_b200 launched by one stylize() call (for bench.py's gpu_launches)."""
         return (1 + K) * 9 + 3 + 9
+
+
+class HostPipeline:
+    """Streaming host API for batch inference (BASELINE config 4): pinned host batches in, pinned
+    host images out, with the PCIe copies of step i+1 / i-1 overlapped with the kernels of step i.
+
+    Three streams: H2D copies, compute (the caller's current stream), D2H copies; two slots of
+    device input / output buffers.  ``submit`` only enqueues work; ``synchronize`` (or the next
+    ``submit`` that reuses a slot) makes the corresponding ``out_host`` valid.  Every step still
+    moves its own inputs and its own result across PCIe -- only the waiting is overlapped.
+    """
+
+    def __init__(self, engine: StyleTransferEngine, N: int, H: int, W: int, slots: int = 2):
+        self.eng = engine
+        dev = engine.device
+        self.dev = dev
+        self.slots = slots
+        self.c = [torch.empty(N, 3, H, W, device=dev) for _ in range(slots)]
+        self.s = [torch.empty(N, 3, H, W, device=dev) for _ in range(slots)]
+        self.o = [torch.empty(N, 3, H, W, device=dev) for _ in range(slots)]
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(slots)]      # inputs landed
+        self.ev_done = [torch.cuda.Event() for _ in range(slots)]    # kernels finished
+        self.ev_out = [torch.cuda.Event() for _ in range(slots)]     # result copied out
+        self.i = 0
+
+    def submit(self, content_host: torch.Tensor, style_host: torch.Tensor, out_host: torch.Tensor,
+               alpha: float = 1.0):
+        if not (content_host.is_pinned() and style_host.is_pinned() and out_host.is_pinned()):
+            raise L.AstError("HostPipeline needs pinned host tensors (torch.Tensor.pin_memory())")
+        k = self.i % self.slots
+        compute = torch.cuda.current_stream(self.dev)
+        if self.i >= self.slots:
+            # slot reuse: its previous kernels must have consumed the inputs, its result must be out
+            self.h2d.wait_event(self.ev_done[k])
+            compute.wait_event(self.ev_out[k])
+        with torch.cuda.stream(self.h2d):
+            self.c[k].copy_(content_host, non_blocking=True)
+            self.s[k].copy_(style_host, non_blocking=True)
+            self.ev_in[k].record(self.h2d)
+        compute.wait_event(self.ev_in[k])
+        self.eng.stylize(self.c[k], self.s[k], alpha=alpha, out=self.o[k])
+        self.ev_done[k].record(compute)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.ev_done[k])
+            out_host.copy_(self.o[k], non_blocking=True)
+            self.ev_out[k].record(self.d2h)
+        self.i += 1
+
+    def synchronize(self):
+        self.h2d.synchronize()
+        self.d2h.synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()

@@ -23,6 +23,19 @@ def _ldq(N, H, W):
     return N * (H + 2) * _wp(W)
 
 
+_RSTD = {}
+
+
+def _imagenet_rstd(dev):
+    """1/std of Normalization (models.py:190) as a device tensor, created once per device (a host ->
+    device copy inside the backward pass would break CUDA-graph capture)."""
+    t = _RSTD.get(str(dev))
+    if t is None:
+        t = torch.tensor([1.0 / s for s in E.IMAGENET_STD], dtype=torch.float32).to(dev)
+        _RSTD[str(dev)] = t
+    return t
+
+
 def _zeros_native(N, H, W, C, halo, dev):
     return torch.zeros((N, H + 2 * halo, W + 2 * halo, C), device=dev, dtype=torch.bfloat16)
 
@@ -156,6 +169,7 @@ class EncoderFn(torch.autograd.Function):
         img = img.float().contiguous()
         N, _, H, W = img.shape
         dev = img.device
+        _imagenet_rstd(dev)   # make sure the constant exists before any graph capture of backward
         Ys, outs = [], []
         x, h, w = None, H, W
         sizes = []
@@ -223,8 +237,7 @@ class EncoderFn(torch.autograd.Function):
                 E.conv3x3(dZ, wflip, None, G, N=N, H=Hi, W=Wi, cin=cout, cout=cin, relu=False,
                           epilogue=L.EPI_PLAIN, halo=L.HALO_KEEP)
             else:
-                rstd = torch.tensor([1.0 / s for s in E.IMAGENET_STD], device=dev, dtype=torch.float32)
-                wflip = pack_ex(wb[0], flip=True, rows_pad=16, cols_pad=64, row_scale=rstd)
+                wflip = pack_ex(wb[0], flip=True, rows_pad=16, cols_pad=64, row_scale=_imagenet_rstd(dev))
                 dimg = torch.empty(N, 3, Hi, Wi, device=dev, dtype=torch.float32)
                 E.conv3x3_last(dZ, None, wflip, None, dimg, False, impl=L.CONV_TC)
         ctx.Ys = None

@@ -151,3 +151,22 @@ def test_config5_2048_four_style_interpolation_properties(engine):
     assert rel_l2(t_native, t_k1) < 1e-2      # bf16 output rounding of the native path
     ref = R.adain_multi(fc.cpu(), [f.cpu() for f in fs], w, alpha=0.6)
     torch.testing.assert_close(t_k1.cpu(), ref, rtol=1e-5, atol=1e-5 * ref.abs().max().item())
+
+
+def test_host_pipeline_matches_direct_calls(engine):
+    """engine.HostPipeline (pinned host in/out, overlapped copies) returns exactly what direct
+    stylize() calls return, for more steps than slots and distinct batches per step."""
+    from arbitrarystyletransfer_b200.engine import HostPipeline
+    N, S, steps = 2, 96, 5
+    pipe = HostPipeline(engine, N, S, S)
+    cs = [R.rand_image(N, S, 600 + i).pin_memory() for i in range(steps)]
+    ss = [R.rand_image(N, S, 700 + i).pin_memory() for i in range(steps)]
+    outs = [torch.empty(N, 3, S, S).pin_memory() for _ in range(steps)]
+    for i in range(steps):
+        pipe.submit(cs[i], ss[i], outs[i])
+    pipe.synchronize()
+    for i in range(steps):
+        ref = engine.stylize(cs[i].cuda(), ss[i].cuda()).cpu()
+        assert torch.equal(outs[i], ref), f"step {i}"
+    with pytest.raises(Exception):
+        pipe.submit(torch.zeros(N, 3, S, S), ss[0], outs[0])      # not pinned

@@ -273,3 +273,48 @@ def test_full_training_step_vs_oracle():
     with torch.no_grad():
         out2 = dec(td)
     assert not torch.equal(out2, gd.detach())
+
+
+def test_cuda_graph_step_matches_eager():
+    """graphs.GraphedStep: a captured decoder training step (fwd + bwd + clip + Adam) replays to the
+    same parameters as the same step run eagerly."""
+    from arbitrarystyletransfer_b200 import models as M, losses as Ls
+    from arbitrarystyletransfer_b200.graphs import GraphedStep
+    taps = ['relu_1', 'relu_3', 'relu_5', 'relu_9']
+
+    def build():
+        torch.manual_seed(0)
+        enc = M.PretrainedEncoder(taps).cuda()
+        M.calibrate_encoder_bias(enc, size=64)
+        torch.manual_seed(1)
+        dec = M.ClassicDecoder().cuda()
+        opt = torch.optim.Adam(dec.parameters(), lr=2e-4, betas=(0.9, 0.999), eps=1e-5, capturable=True)
+        ada = M.AdaIN()
+
+        def step(c, s):
+            with torch.no_grad():
+                fc = enc(c)[-1]
+                st = enc(s)
+                t = ada(fc, st[-1])
+            opt.zero_grad(set_to_none=True)
+            gt = enc(dec(t))
+            loss = Ls.compute_content_loss(gt[-1], t)
+            for a, b in zip(gt, st):
+                loss = loss + Ls.compute_style_loss(a, b)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(dec.parameters(), 2.0)
+            opt.step()
+            return loss
+        return dec, step
+
+    c, s = R.rand_image(2, 64, 201).cuda(), R.rand_image(2, 64, 202).cuda()
+    dec_e, step_e = build()
+    for _ in range(5):          # GraphedStep runs 3 warm-up steps + the capture step + 1 replay below
+        le = step_e(c, s)
+    dec_g, step_g = build()
+    g = GraphedStep(step_g, [c.clone(), s.clone()], warmup=3)
+    lg = g(c, s)
+    torch.cuda.synchronize()
+    assert torch.isfinite(lg).item()
+    for a, b in zip(dec_e.parameters(), dec_g.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
