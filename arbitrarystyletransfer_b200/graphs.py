@@ -16,7 +16,10 @@ class GraphedStep:
     static tensors, replays the captured graph and returns ``fn``'s (static) outputs.
 
     ``fn`` must be shape-static and must not synchronise or touch the host (no ``.item()``).
-    Optimisers must be built with ``capturable=True``."""
+    Optimisers must be built with ``capturable=True``.  Build the GraphedStep BEFORE running ``fn``'s
+    backward eagerly on the default stream: autograd ties each parameter's gradient accumulation to
+    the stream of its first backward, and the legacy default stream cannot join a capture.  (The
+    warm-up steps here run on a side stream for that reason.)"""
 
     def __init__(self, fn: Callable, static_inputs, warmup: int = 3):
         self.static_inputs = list(static_inputs)

@@ -274,32 +274,37 @@ def time_train_step(dev, steps=8, warmup=3, batch=8, size=256):
     the reference's step glue (train.py:287-300) unchanged on this package's modules."""
     from arbitrarystyletransfer_b200 import models as M, losses as Ls
     taps = ['relu_1', 'relu_3', 'relu_5', 'relu_9']
-    torch.manual_seed(0)
-    enc = M.PretrainedEncoder(taps).to(dev)
-    M.calibrate_encoder_bias(enc)
-    torch.manual_seed(1)
-    dec = M.ClassicDecoder().to(dev)
-    opt = torch.optim.Adam(dec.parameters(), lr=2e-4, betas=(0.9, 0.999), eps=1e-5, capturable=True)
-    adain = M.AdaIN()
     g = torch.Generator().manual_seed(201)
     c = torch.rand(batch, 3, size, size, generator=g).to(dev)
     s = torch.rand(batch, 3, size, size, generator=g).to(dev)
 
-    def step(c, s):
-        with torch.no_grad():
-            fc = enc(c)[-1]
-            st = enc(s)
-            t = adain(fc, st[-1])
-        opt.zero_grad(set_to_none=True)
-        gimg = dec(t)
-        gt = enc(gimg)
-        loss = Ls.compute_content_loss(gt[-1], t)
-        for a, b in zip(gt, st):
-            loss = loss + Ls.compute_style_loss(a, b)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(dec.parameters(), 2.0)
-        opt.step()
-        return loss
+    def build():
+        """A fresh model + optimiser + step closure.  The graph-captured instance must never have run
+        a backward pass on the default stream (its AccumulateGrad nodes would stay tied to it)."""
+        torch.manual_seed(0)
+        enc = M.PretrainedEncoder(taps).to(dev)
+        M.calibrate_encoder_bias(enc)
+        torch.manual_seed(1)
+        dec = M.ClassicDecoder().to(dev)
+        opt = torch.optim.Adam(dec.parameters(), lr=2e-4, betas=(0.9, 0.999), eps=1e-5, capturable=True)
+        adain = M.AdaIN()
+
+        def step(c, s):
+            with torch.no_grad():
+                fc = enc(c)[-1]
+                st = enc(s)
+                t = adain(fc, st[-1])
+            opt.zero_grad(set_to_none=True)
+            gimg = dec(t)
+            gt = enc(gimg)
+            loss = Ls.compute_content_loss(gt[-1], t)
+            for a, b in zip(gt, st):
+                loss = loss + Ls.compute_style_loss(a, b)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(dec.parameters(), 2.0)
+            opt.step()
+            return loss
+        return step
 
     def timeit(fn):
         for _ in range(warmup):
@@ -313,15 +318,17 @@ def time_train_step(dev, steps=8, warmup=3, batch=8, size=256):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / steps, loss
 
-    ms_eager, loss = timeit(step)
     graph_err = None
-    ms = ms_eager
+    ms = None
     try:
         from arbitrarystyletransfer_b200.graphs import GraphedStep
-        gstep = GraphedStep(step, [c.clone(), s.clone()])
+        gstep = GraphedStep(build(), [c.clone(), s.clone()])
         ms, loss = timeit(gstep)
     except Exception as e:   # keep the eager number
         graph_err = repr(e)[:200]
+    ms_eager, loss_e = timeit(build())
+    if ms is None:
+        ms, loss = ms_eager, loss_e
     # algorithmic FLOPs: fwd 3 encoders + decoder, bwd encoder dgrad + decoder dgrad + wgrad
     f_img = flops_per_image(size)          # 2 enc + 1 dec
     enc_f = (f_img - _dec_flops(size)) / 2

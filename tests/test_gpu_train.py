@@ -309,7 +309,7 @@ def test_cuda_graph_step_matches_eager():
 
     c, s = R.rand_image(2, 64, 201).cuda(), R.rand_image(2, 64, 202).cuda()
     dec_e, step_e = build()
-    for _ in range(5):          # GraphedStep runs 3 warm-up steps + the capture step + 1 replay below
+    for _ in range(4):          # GraphedStep executes 3 warm-up steps (capture itself runs nothing) + 1 replay below
         le = step_e(c, s)
     dec_g, step_g = build()
     g = GraphedStep(step_g, [c.clone(), s.clone()], warmup=3)
