@@ -174,47 +174,48 @@ dec_bwd_fold_kernel(const __nv_bfloat16* __restrict__ dXpad, const __nv_bfloat16
 // aligned innermost coordinate).  Columns pw >= W+2 are zero.  The source has halo width src_halo;
 // the planar halo is copied from the source when copy_halo, else zero.  nshift = 3 writes the three
 // column-shifted copies planar[s][c][q] = x[c][q + s - 1] the kw = 0,1,2 taps read.
+// Tile = 64 consecutive q x 64 channels (+ one q on each side for the shifted copies): 16-byte loads
+// along the channels, transpose through shared memory, 16-byte stores along q (q0 is a multiple of
+// 8, so the stores of all three copies are aligned; the +-1 shift is applied while reading the tile).
+constexpr int PT_Q = 64, PT_C = 64;
+
 __global__ void __launch_bounds__(256)
 native_to_planar_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N,
                         int C, int H, int W, int src_halo, int copy_halo, int wp, int nshift) {
-  __shared__ __nv_bfloat16 tile[32][34];  // [pixel][channel]
+  __shared__ __align__(16) __nv_bfloat16 tile[PT_Q + 2][PT_C + 8];  // [q - q0 + 1][channel], padded rows
   const int Hp = H + 2;
   const int64_t ldq = (int64_t)N * Hp * wp;
-  const int64_t q0 = (int64_t)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int pl = ty; pl < 32; pl += 8) {
-    const int64_t q = q0 + pl;
-    __nv_bfloat16 val = __float2bfloat16_rn(0.f);
-    if (q < ldq && c0 + tx < C) {
+  const int64_t q0 = (int64_t)blockIdx.x * PT_Q;
+  const int c0 = blockIdx.y * PT_C;
+  const int Ws = W + 2 * src_halo, Hs = H + 2 * src_halo;
+  // load (PT_Q + 2) q-rows x 8 channel-vectors
+  for (int i = threadIdx.x; i < (PT_Q + 2) * (PT_C / 8); i += 256) {
+    const int r = i / (PT_C / 8), v = i % (PT_C / 8);
+    const int64_t q = q0 + r - 1;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (q >= 0 && q < ldq && c0 + v * 8 < C) {
       const int pw = (int)(q % wp);
       const int ph = (int)((q / wp) % Hp);
       const int n = (int)(q / ((int64_t)wp * Hp));
       const bool halo = ph == 0 || pw == 0 || ph == Hp - 1 || pw == W + 1;
-      if (pw < W + 2 && (!halo || copy_halo)) {
-        const int sh = ph - 1 + src_halo, sw = pw - 1 + src_halo;
-        val = src[(((int64_t)n * (H + 2 * src_halo) + sh) * (W + 2 * src_halo) + sw) * C + c0 + tx];
-      }
+      if (pw < W + 2 && (!halo || copy_halo))
+        val = ldv(src + (((int64_t)n * Hs + ph - 1 + src_halo) * Ws + pw - 1 + src_halo) * C + c0 + v * 8);
     }
-    tile[pl][tx] = val;
+    *reinterpret_cast<uint4*>(&tile[r][v * 8]) = val;
   }
   __syncthreads();
-  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-  for (int cl = ty; cl < 32; cl += 8) {
-    const int64_t q = q0 + tx;
-    if (c0 + cl >= C || q >= ldq) continue;
-    const __nv_bfloat16 v = tile[tx][cl];
-    if (nshift == 1) {
-      dst[(int64_t)(c0 + cl) * ldq + q] = v;
-    } else {
-      __nv_bfloat16* d0 = dst + ((int64_t)0 * C + c0 + cl) * ldq;  // x[q-1]
-      __nv_bfloat16* d1 = dst + ((int64_t)1 * C + c0 + cl) * ldq;  // x[q]
-      __nv_bfloat16* d2 = dst + ((int64_t)2 * C + c0 + cl) * ldq;  // x[q+1]
-      d1[q] = v;
-      if (q + 1 < ldq) d0[q + 1] = v;
-      if (q >= 1) d2[q - 1] = v;
-      if (q == 0) d0[0] = zero;
-      if (q == ldq - 1) d2[ldq - 1] = zero;
+  // store: thread -> (channel, group of 8 consecutive q); copy s holds x[q + s - 1]
+  for (int i = threadIdx.x; i < PT_C * (PT_Q / 8); i += 256) {
+    const int c = i / (PT_Q / 8), g = i % (PT_Q / 8);
+    const int64_t q = q0 + g * 8;
+    if (c0 + c >= C || q >= ldq) continue;
+    for (int sft = 0; sft < nshift; ++sft) {
+      const int off = nshift == 1 ? 1 : sft;  // tile row of x[q + s - 1] is (q - q0) + s
+      __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = tile[g * 8 + j + off][c];
+      __nv_bfloat16* d = dst + ((int64_t)(nshift == 1 ? 0 : sft) * C + c0 + c) * ldq + q;
+      *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(o);
     }
   }
 }
@@ -308,10 +309,11 @@ extern "C" int ast_native_to_planar(const void* native, void* planar, int N, int
   if (!native || !planar || N <= 0 || C <= 0 || H <= 0 || W <= 0 || src_halo < 1 || src_halo > 2)
     return AST_E_BADARG;
   if (wp < W + 2 || wp % 8 != 0 || (nshift != 1 && nshift != 3)) return AST_E_SHAPE;
+  if (C % 8 != 0 || !aligned16(native) || !aligned16(planar)) return AST_E_SHAPE;
   const int64_t ldq = (int64_t)N * (H + 2) * wp;
-  const int64_t gx = (ldq + 31) / 32;
-  if (gx >= 0x7fffffffLL || (C + 31) / 32 > 65535) return AST_E_SHAPE;
-  dim3 grid((unsigned)gx, (C + 31) / 32);
+  const int64_t gx = (ldq + PT_Q - 1) / PT_Q;
+  if (gx >= 0x7fffffffLL || (C + PT_C - 1) / PT_C > 65535) return AST_E_SHAPE;
+  dim3 grid((unsigned)gx, (C + PT_C - 1) / PT_C);
   native_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(native), reinterpret_cast<__nv_bfloat16*>(planar), N, C, H, W,
       src_halo, copy_halo, wp, nshift);

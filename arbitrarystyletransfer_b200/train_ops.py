@@ -36,8 +36,22 @@ def _imagenet_rstd(dev):
     return t
 
 
-def _zeros_native(N, H, W, C, halo, dev):
-    return torch.zeros((N, H + 2 * halo, W + 2 * halo, C), device=dev, dtype=torch.bfloat16)
+_ZERO_HALO = {}
+
+
+def _zeros_native(N, H, W, C, halo, dev, tag=None):
+    """Gradient buffer whose halo must be zero.  With a ``tag`` the buffer is cached per (tag, shape):
+    the kernels that fill it rewrite every interior element and never touch the halo, so the zeros
+    written at allocation stay valid and no per-step memset is needed."""
+    shape = (N, H + 2 * halo, W + 2 * halo, C)
+    if tag is None:
+        return torch.zeros(shape, device=dev, dtype=torch.bfloat16)
+    key = (tag, shape, str(dev))
+    t = _ZERO_HALO.get(key)
+    if t is None:
+        t = torch.zeros(shape, device=dev, dtype=torch.bfloat16)
+        _ZERO_HALO[key] = t
+    return t
 
 
 def pack_ex(w, flip, rows_pad=0, cols_pad=0, row_scale=None):
@@ -149,7 +163,7 @@ class DecoderFn(torch.autograd.Function):
                       epilogue=L.EPI_PLAIN, halo=L.HALO_KEEP)
             _, _, prelu, pup = E.DECODER_SPEC[i - 1]
             Hc, Wc = (Hi // 2, Wi // 2) if pup else (Hi, Wi)
-            dZp = _zeros_native(N, Hc, Wc, cin, 2, dev)
+            dZp = _zeros_native(N, Hc, Wc, cin, 2, dev, tag=("dec", i - 1))
             L.check(lib.ast_dec_bwd_fold(dXpad.data_ptr(), acts[i].data_ptr(), dZp.data_ptr(), N, cin, Hi,
                                          Wi, int(pup), int(prelu), st), "ast_dec_bwd_fold")
             dZ = dZp
@@ -227,7 +241,7 @@ class EncoderFn(torch.autograd.Function):
             if G is None and tpost is None and tpre is None:
                 continue  # nothing flows into this layer (deeper than the last tap with a gradient)
             pooled = pool and i + 1 < len(plan) and G is not None
-            dZ = _zeros_native(N, Hi, Wi, cout, 1, dev)
+            dZ = _zeros_native(N, Hi, Wi, cout, 1, dev, tag=("enc", i))
             L.check(lib.ast_vgg_bwd_prep(Ys[i].data_ptr(), L.ptr(G), L.ptr(tpost), L.ptr(tpre),
                                          dZ.data_ptr(), N, cout, Hi, Wi, int(pooled), 1, st),
                     "ast_vgg_bwd_prep")
