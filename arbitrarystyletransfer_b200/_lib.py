@@ -50,6 +50,7 @@ PROTOTYPES = {
     "ast_huber_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _vp]),
     "ast_gram_fwd": (_i, [_vp, _vp, _i, _i, _i64, _vp]),
     "ast_gram_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),
+    "ast_gram_fwd_tf32": (_i, [_vp, _vp, _i, _i, _i64, _vp]),
     "ast_conv3x3_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "ast_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ast_conv3x3_first": (_i, [_vp, _vp, _vp, _fp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

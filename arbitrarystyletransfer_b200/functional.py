@@ -198,6 +198,12 @@ def huber_loss(inp: torch.Tensor, tgt: torch.Tensor, scale: float = 1.0) -> torc
     return _Huber.apply(inp, tgt, scale)
 
 
+# "tf32": Gram forward on the tensor cores when the shape allows (default); "fp32": CUDA-core kernel
+# with 1e-6 agreement.  The reference computes torch.bmm in fp32 (losses.py:109); on Ampere+ GPUs
+# PyTorch itself may run that bmm in TF32 when torch.backends.cuda.matmul.allow_tf32 is set.
+GRAM_PRECISION = "tf32"
+
+
 class _Gram(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -208,8 +214,12 @@ class _Gram(torch.autograd.Function):
         x = _c(x.float())
         B, Cc, H, W = x.shape
         g = torch.empty(B, Cc, Cc, device=x.device, dtype=torch.float32)
-        L.check(lib.ast_gram_fwd(x.data_ptr(), g.data_ptr(), B, Cc, H * W, L.stream_ptr(x.device)),
-                "ast_gram_fwd")
+        if GRAM_PRECISION == "tf32" and (H * W) % 4 == 0 and Cc % 16 == 0 and H * W >= 64:
+            L.check(lib.ast_gram_fwd_tf32(x.data_ptr(), g.data_ptr(), B, Cc, H * W, L.stream_ptr(x.device)),
+                    "ast_gram_fwd_tf32")
+        else:
+            L.check(lib.ast_gram_fwd(x.data_ptr(), g.data_ptr(), B, Cc, H * W, L.stream_ptr(x.device)),
+                    "ast_gram_fwd")
         ctx.save_for_backward(x)
         return g
 

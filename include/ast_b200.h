@@ -104,6 +104,9 @@ int ast_huber_bwd(const float* inp, const float* tgt, const float* g_loss, float
 
 /* gram_matrix (losses.py:105-109): G[b] = X[b] X[b]^T / (C*HW), X fp32 [B][C][HW] -> [B][C][C] */
 int ast_gram_fwd(const float* x, float* g, int B, int C, int64_t HW, void* stream);
+/* Same Gram matrix on the tensor cores in TF32 (inputs rounded to 10 mantissa bits, fp32
+ * accumulate; ~1e-4 relative agreement).  Needs HW % 4 == 0 and C % 16 == 0. */
+int ast_gram_fwd_tf32(const float* x, float* g, int B, int C, int64_t HW, void* stream);
 /* gx[b] = (gG[b] + gG[b]^T) X[b] / (C*HW) */
 int ast_gram_bwd(const float* x, const float* gg, float* gx, int B, int C, int64_t HW,
                  void* stream);
