@@ -133,50 +133,83 @@ __global__ void __launch_bounds__(256) gram_fwd_kernel(const float* __restrict__
     }
 }
 
-// gx[b] = S X * scale, S = gG + gG^T (C x C), X (C x HW): tile 64 rows x 64 cols of HW per CTA.
+// gx[b] = S X * scale, S = gG + gG^T (C x C), X (C x HW).  Tile = 64 rows (c) x 256 columns (q) per
+// CTA, 8 x 8 outputs per thread, K chunks of 16 through shared memory: four 128-bit shared loads per
+// 64 FMAs (the earlier 4 x 4 micro-tile was shared-memory-load bound).
+constexpr int GB_R = 64, GB_Q = 256, GB_K = 16;
+
 __global__ void __launch_bounds__(256) gram_bwd_kernel(const float* __restrict__ x,
                                                        const float* __restrict__ gg,
                                                        float* __restrict__ gx, int C, int64_t HW,
                                                        float scale) {
-  __shared__ float sS[GK][GT + 4];  // S^T chunk: [k][row]
-  __shared__ float sX[GK][GT + 4];  // X chunk:   [k][col]
+  __shared__ __align__(16) float sS[GB_K][GB_R];   // S^T chunk: [k][row]
+  __shared__ __align__(16) float sX[GB_K][GB_Q];   // X chunk:   [k][col]
   const int b = blockIdx.z;
-  const int r0 = blockIdx.y * GT;
-  const int64_t c0 = (int64_t)blockIdx.x * GT;
+  const int r0 = blockIdx.y * GB_R;
+  const int64_t c0 = (int64_t)blockIdx.x * GB_Q;
   const float* xb = x + (int64_t)b * C * HW;
   const float* gb = gg + (int64_t)b * C * C;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4] = {};
-  for (int kk = 0; kk < C; kk += GK) {
-    for (int e = threadIdx.x; e < GT * GK; e += 256) {
-      int k = e / GT, r = e % GT;  // S[r0+r][kk+k] = gG[r][k] + gG[k][r]
-      int rg = r0 + r, kg = kk + k;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // tx -> 8 columns, ty -> 8 rows
+  const bool vec_ok = (HW % 4 == 0) && aligned16(xb);
+  float acc[8][8] = {};
+  for (int kk = 0; kk < C; kk += GB_K) {
+    for (int e = threadIdx.x; e < GB_K * GB_R; e += 256) {
+      const int k = e / GB_R, r = e % GB_R;
+      const int rg = r0 + r, kg = kk + k;
       sS[k][r] = (rg < C && kg < C) ? gb[(int64_t)rg * C + kg] + gb[(int64_t)kg * C + rg] : 0.f;
-      int64_t cg = c0 + r;  // reuse r as column index: coalesced along HW
-      sX[k][r] = (kg < C && cg < HW) ? xb[(int64_t)kg * HW + cg] : 0.f;
+    }
+    for (int e = threadIdx.x; e < GB_K * GB_Q / 4; e += 256) {
+      const int k = e / (GB_Q / 4), c4 = (e % (GB_Q / 4)) * 4;
+      const int kg = kk + k;
+      const int64_t cg = c0 + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kg < C) {
+        if (vec_ok && cg + 3 < HW) {
+          v = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)kg * HW + cg));
+        } else {
+          if (cg < HW) v.x = xb[(int64_t)kg * HW + cg];
+          if (cg + 1 < HW) v.y = xb[(int64_t)kg * HW + cg + 1];
+          if (cg + 2 < HW) v.z = xb[(int64_t)kg * HW + cg + 2];
+          if (cg + 3 < HW) v.w = xb[(int64_t)kg * HW + cg + 3];
+        }
+      }
+      *reinterpret_cast<float4*>(&sX[k][c4]) = v;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < GK; ++k) {
-      float a[4], bb[4];
+    for (int k = 0; k < GB_K; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sS[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sS[k][ty * 8 + 4]);
+      // columns owned by this thread: tx*4 .. tx*4+3 and 128 + tx*4 .. (conflict-free 128-bit loads)
+      const float4 b0 = *reinterpret_cast<const float4*>(&sX[k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sX[k][128 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = sS[k][ty * 4 + i]; bb[i] = sX[k][tx * 4 + i]; }
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
   float* ob = gx + (int64_t)b * C * HW;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty * 8 + i;
+    if (r >= C) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int r = r0 + ty * 4 + i;
-      int64_t c = c0 + tx * 4 + j;
-      if (r < C && c < HW) ob[(int64_t)r * HW + c] = acc[i][j] * scale;
+    for (int half = 0; half < 2; ++half) {
+      const int64_t c = c0 + half * 128 + tx * 4;
+      float* o = ob + (int64_t)r * HW + c;
+      if (vec_ok && aligned16(ob) && c + 3 < HW) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[i][half * 4] * scale, acc[i][half * 4 + 1] * scale,
+                                                    acc[i][half * 4 + 2] * scale, acc[i][half * 4 + 3] * scale);
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (c + j < HW) o[j] = acc[i][half * 4 + j] * scale;
+      }
     }
+  }
 }
 
 }  // namespace ast
@@ -240,9 +273,9 @@ extern "C" int ast_gram_fwd(const float* x, float* g, int B, int C, int64_t HW, 
 extern "C" int ast_gram_bwd(const float* x, const float* gg, float* gx, int B, int C, int64_t HW,
                             void* stream) {
   if (!x || !gg || !gx || B <= 0 || C <= 0 || HW <= 0) return AST_E_BADARG;
-  if (B > 65535 || (C + GT - 1) / GT > 65535) return AST_E_SHAPE;
+  if (B > 65535 || (C + GB_R - 1) / GB_R > 65535) return AST_E_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid((unsigned)((HW + GT - 1) / GT), (C + GT - 1) / GT, B);
+  dim3 grid((unsigned)((HW + GB_Q - 1) / GB_Q), (C + GB_R - 1) / GB_R, B);
   gram_bwd_kernel<<<grid, 256, 0, s>>>(x, gg, gx, C, HW, 1.f / ((float)C * (float)HW));
   AST_CHECK_LAUNCH();
   return 0;
