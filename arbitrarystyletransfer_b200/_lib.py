@@ -69,6 +69,13 @@ PROTOTYPES = {
     "ast_native_to_planar": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_unpack_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp]),
+    "ast_pw_conv": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp]),
+    "ast_dw_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_se_fc": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ast_scale_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ast_stem_conv": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_head_conv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_nhwc_to_nchw": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
 }
 
 _lib = None

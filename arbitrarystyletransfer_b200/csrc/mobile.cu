@@ -1,0 +1,313 @@
+// K4: the non-GEMM pieces of the MobileNet-style Encoder / Decoder / AutoEncoder blocks
+// (reference: mobilenetv2.py:38-43 conv_3x3_bn, :63-81 SELayer, :95-165 DepthWiseConv;
+// models.py:140-184 Encoder, :242-320 DecoderBlock / Decoder, :322-338 AutoEncoder), eval mode.
+// Layout: plain NHWC bf16 [N][H][W][C] (no halo: these blocks use reflect padding of 1 or 2 and
+// stride 1 or 2, resolved by index arithmetic in the stencil).  All HBM-bound.
+#include "common.cuh"
+
+namespace ast {
+
+constexpr int kM = 256;
+
+__device__ __forceinline__ float hswish(float x) {
+  return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+}
+__device__ __forceinline__ int reflect(int p, int X) {  // padding_mode="reflect" / ReflectionPad2d
+  p = p < 0 ? -p : p;
+  return p >= X ? 2 * X - 2 - p : p;
+}
+
+// ---- depthwise k x k (k = 3 or 5), stride 1 or 2, reflect padding (k-1)/2, + bias (folded BN) +
+// Hardswish, with the SELayer's global average pool fused: per-(n,c) sums of the OUTPUT.
+// up2 != 0: the input is read through a virtual nearest x2 upsample (DecoderBlock._upsample_3,
+// models.py:254, 265-267), reflect padding applied on the upsampled grid.
+// grid = (pixel chunks, N); thread -> 8 channels of one pixel group (as native_stats_kernel).
+__global__ void __launch_bounds__(kM)
+dw_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[k*k][C]*/,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, float* __restrict__ pool,
+               int C, int H, int W, int Ho, int Wo, int k, int stride, int up2, int act, int chunks) {
+  extern __shared__ float s_pool[];  // [groups][C]
+  const int cv = C / 8;
+  const int groups = kM / cv;
+  const int g = threadIdx.x / cv, v = threadIdx.x % cv;
+  const int n = blockIdx.y;
+  const int pad = (k - 1) / 2;
+  const int Hin = up2 ? 2 * H : H, Win = up2 ? 2 * W : W;   // size of the (virtual) conv input
+  const int64_t npix = (int64_t)Ho * Wo;
+  const int64_t per = (npix + chunks - 1) / chunks;
+  const int64_t p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
+  float psum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) psum[j] = 0.f;
+  if (g < groups) {
+    float b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = bias ? __ldg(bias + v * 8 + j) : 0.f;
+    const __nv_bfloat16* xin = x + (int64_t)n * H * W * C + v * 8;
+    for (int64_t p = p0 + g; p < p1; p += groups) {
+      const int ho = (int)(p / Wo), wo = (int)(p % Wo);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = b[j];
+      for (int kh = 0; kh < k; ++kh) {
+        int ih = reflect(ho * stride + kh - pad, Hin);
+        if (up2) ih >>= 1;
+        for (int kw = 0; kw < k; ++kw) {
+          int iw = reflect(wo * stride + kw - pad, Win);
+          if (up2) iw >>= 1;
+          float xv[8];
+          Vec16<true>::unpack(__ldg(reinterpret_cast<const uint4*>(xin + ((int64_t)ih * W + iw) * C)), xv);
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(kh * k + kw) * C + v * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(kh * k + kw) * C + v * 8 + 4));
+          acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
+          acc[2] = fmaf(xv[2], w0.z, acc[2]); acc[3] = fmaf(xv[3], w0.w, acc[3]);
+          acc[4] = fmaf(xv[4], w1.x, acc[4]); acc[5] = fmaf(xv[5], w1.y, acc[5]);
+          acc[6] = fmaf(xv[6], w1.z, acc[6]); acc[7] = fmaf(xv[7], w1.w, acc[7]);
+        }
+      }
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = hswish(acc[j]);
+      }
+      const uint4 o = Vec16<true>::pack(acc);
+      *reinterpret_cast<uint4*>(out + (((int64_t)n * Ho + ho) * Wo + wo) * C + v * 8) = o;
+      // pool what the next layer will actually read (the bf16-rounded value)
+      float r[8];
+      Vec16<true>::unpack(o, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) psum[j] += r[j];
+    }
+  }
+  if (!pool) return;
+  if (g < groups) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_pool[g * C + v * 8 + j] = psum[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kM) {
+    float s = 0.f;
+    for (int gg = 0; gg < groups; ++gg) s += s_pool[gg * C + c];
+    atomicAdd(pool + (int64_t)n * C + c, s);
+  }
+}
+
+// ---- SELayer excitation (mobilenetv2.py:66-80): y = Hardtanh(0,1)(W2 relu(W1 mean + b1) + b2) ------
+// one block per image; pool holds the per-channel SUMS, inv_hw turns them into means.
+__global__ void __launch_bounds__(kM)
+se_fc_kernel(const float* __restrict__ pool, float inv_hw, const float* __restrict__ w1,
+             const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+             float* __restrict__ scale, int C, int S) {
+  extern __shared__ float sm[];  // mean[C] + hid[S]
+  float* mean = sm;
+  float* hid = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += kM) mean[c] = pool[(int64_t)n * C + c] * inv_hw;
+  __syncthreads();
+  for (int j = threadIdx.x; j < S; j += kM) {
+    float a = b1[j];
+    for (int c = 0; c < C; ++c) a = fmaf(w1[(int64_t)j * C + c], mean[c], a);
+    hid[j] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kM) {
+    float a = b2[c];
+    for (int j = 0; j < S; ++j) a = fmaf(w2[(int64_t)c * S + j], hid[j], a);
+    scale[(int64_t)n * C + c] = fminf(fmaxf(a, 0.f), 1.f);
+  }
+}
+
+// ---- per-sample weights of the pw-linear conv: W'[n][co][ci] = W[co][ci] * se[n][ci] (bf16) --------
+// (x * y in SELayer.forward, mobilenetv2.py:81, moved from the activation into the weights: exact in
+// real arithmetic, and it saves one full pass over the widest tensor of the block.)
+__global__ void scale_weights_kernel(const float* __restrict__ w, const float* __restrict__ se,
+                                     __nv_bfloat16* __restrict__ out, int N, int Cout, int Cin) {
+  const int64_t total = (int64_t)N * Cout * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int64_t r = i / Cin;
+    const int co = (int)(r % Cout);
+    const int n = (int)(r / Cout);
+    const float s = se ? se[(int64_t)n * Cin + ci] : 1.f;
+    out[i] = __float2bfloat16_rn(w[(int64_t)co * Cin + ci] * s);
+  }
+}
+
+// ---- stem: NCHW fp32 image -> conv 3x3 (reflect pad 1, stride 1, no bias) -> Hardswish -> NHWC bf16
+// (conv_3x3_bn, mobilenetv2.py:38-43; Cout <= 32).  One thread per pixel.
+constexpr int kStemMaxCout = 32;
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*OIHW [Cout][3][3][3]*/,
+                 __nv_bfloat16* __restrict__ out, int N, int H, int W, int Cout) {
+  __shared__ float s_w[27][kStemMaxCout];
+  for (int i = threadIdx.x; i < 27 * kStemMaxCout; i += 128) {
+    const int kk = i / kStemMaxCout, c = i % kStemMaxCout;
+    s_w[kk][c] = c < Cout ? w[c * 27 + kk] : 0.f;
+  }
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (pix >= (int64_t)N * H * W) return;
+  const int x = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+  float acc[kStemMaxCout];
+#pragma unroll
+  for (int c = 0; c < kStemMaxCout; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float v = __ldg(img + (((int64_t)n * 3 + ci) * H + reflect(h + kh - 1, H)) * W + reflect(x + kw - 1, W));
+#pragma unroll
+        for (int c = 0; c < kStemMaxCout; ++c) acc[c] = fmaf(v, s_w[ci * 9 + kh * 3 + kw][c], acc[c]);
+      }
+  __nv_bfloat16* o = out + pix * Cout;
+  for (int c = 0; c < Cout; c += 8) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = hswish(acc[c + j]);
+    *reinterpret_cast<uint4*>(o + c) = Vec16<true>::pack(t);
+  }
+}
+
+// ---- image head: NHWC bf16 -> ReflectionPad2d(1) -> conv 3x3 (bias) -> NCHW fp32 (+ Hardtanh(0,1))
+// (Decoder._ref_out + _img_out + last_act, models.py:300-316; Cin <= 32, Cout <= 4)
+__global__ void __launch_bounds__(128)
+head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*OIHW*/,
+                 const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W, int Cin,
+                 int Cout, int clamp01) {
+  __shared__ float s_w[9][32][4];
+  for (int i = threadIdx.x; i < 9 * 32 * 4; i += 128) {
+    const int co = i % 4, ci = (i / 4) % 32, t = i / 128;
+    s_w[t][ci][co] = (co < Cout && ci < Cin) ? w[((int64_t)co * Cin + ci) * 9 + t] : 0.f;
+  }
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (pix >= (int64_t)N * H * W) return;
+  const int xw = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+  float acc[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] = (bias && c < Cout) ? bias[c] : 0.f;
+  for (int t = 0; t < 9; ++t) {
+    const int ih = reflect(h + t / 3 - 1, H), iw = reflect(xw + t % 3 - 1, W);
+    const __nv_bfloat16* ip = x + (((int64_t)n * H + ih) * W + iw) * Cin;
+    for (int v = 0; v < Cin / 8; ++v) {
+      float f[8];
+      Vec16<true>::unpack(__ldg(reinterpret_cast<const uint4*>(ip + v * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 ww = *reinterpret_cast<const float4*>(&s_w[t][v * 8 + j][0]);
+        acc[0] = fmaf(f[j], ww.x, acc[0]); acc[1] = fmaf(f[j], ww.y, acc[1]);
+        acc[2] = fmaf(f[j], ww.z, acc[2]); acc[3] = fmaf(f[j], ww.w, acc[3]);
+      }
+    }
+  }
+  for (int c = 0; c < Cout; ++c) {
+    float v = acc[c];
+    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+    out[(((int64_t)n * Cout + c) * H + h) * W + xw] = v;
+  }
+}
+
+// ---- NHWC bf16 (row stride ld) -> NCHW fp32 (feature taps at the reference boundary) ---------------
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld,
+                                                           float* __restrict__ dst, int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int pl = ty; pl < 32; pl += 8) {
+    const int64_t p = p0 + pl;
+    tile[pl][tx] = (p < HW && c0 + tx < C) ? __bfloat162float(src[((int64_t)n * HW + p) * ld + c0 + tx]) : 0.f;
+  }
+  __syncthreads();
+  for (int cl = ty; cl < 32; cl += 8) {
+    const int64_t p = p0 + tx;
+    if (c0 + cl < C && p < HW) dst[((int64_t)n * C + c0 + cl) * HW + p] = tile[tx][cl];
+  }
+}
+
+}  // namespace ast
+
+using namespace ast;
+
+extern "C" int ast_dw_conv(const void* x, const float* w, const float* bias, void* out, float* pool, int N,
+                           int C, int H, int W, int k, int stride, int up2, int act, void* stream) {
+  if (!x || !w || !out || N <= 0 || C <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  if ((k != 3 && k != 5) || (stride != 1 && stride != 2) || C % 8 != 0 || C / 8 > kM) return AST_E_SHAPE;
+  const int Hin = up2 ? 2 * H : H, Win = up2 ? 2 * W : W, pad = (k - 1) / 2;
+  if (Hin <= pad || Win <= pad) return AST_E_SHAPE;   // reflect padding needs pad < size
+  const int Ho = (Hin + 2 * pad - k) / stride + 1, Wo = (Win + 2 * pad - k) / stride + 1;
+  if (N > 65535) return AST_E_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pool) AST_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)N * C, s));
+  int64_t chunks = (4 * 148 + N - 1) / N;
+  const int64_t npix = (int64_t)Ho * Wo;
+  if (chunks > npix / 8) chunks = npix / 8;
+  if (chunks < 1) chunks = 1;
+  const int groups = kM / (C / 8);
+  const size_t smem = pool ? (size_t)groups * C * sizeof(float) : 0;
+  if (smem > 48 * 1024) return AST_E_SHAPE;
+  dw_conv_kernel<<<dim3((unsigned)chunks, N), kM, smem, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), w, bias, reinterpret_cast<__nv_bfloat16*>(out), pool, C, H, W,
+      Ho, Wo, k, stride, up2, act, (int)chunks);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_se_fc(const float* pool, float inv_hw, const float* w1, const float* b1, const float* w2,
+                         const float* b2, float* scale, int N, int C, int S, void* stream) {
+  if (!pool || !w1 || !b1 || !w2 || !b2 || !scale || N <= 0 || C <= 0 || S <= 0) return AST_E_BADARG;
+  const size_t smem = (size_t)(C + S) * sizeof(float);
+  if (smem > 48 * 1024) return AST_E_SHAPE;
+  se_fc_kernel<<<N, kM, smem, (cudaStream_t)stream>>>(pool, inv_hw, w1, b1, w2, b2, scale, C, S);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_scale_weights(const float* w, const float* se, void* out, int N, int Cout, int Cin,
+                                 void* stream) {
+  if (!w || !out || N <= 0 || Cout <= 0 || Cin <= 0) return AST_E_BADARG;
+  const int64_t total = (int64_t)N * Cout * Cin;
+  int64_t nb = (total + 255) / 256;
+  if (nb > 148 * 8) nb = 148 * 8;
+  scale_weights_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
+      w, se, reinterpret_cast<__nv_bfloat16*>(out), N, Cout, Cin);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_stem_conv(const float* img, const float* w, void* out, int N, int H, int W, int Cout,
+                             void* stream) {
+  if (!img || !w || !out || N <= 0 || H < 2 || W < 2) return AST_E_BADARG;
+  if (Cout % 8 != 0 || Cout > kStemMaxCout) return AST_E_SHAPE;
+  const int64_t nb = ((int64_t)N * H * W + 127) / 128;
+  if (nb >= 0x7fffffffLL) return AST_E_SHAPE;
+  stem_conv_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(img, w, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                   N, H, W, Cout);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_head_conv(const void* x, const float* w, const float* bias, float* out, int N, int H, int W,
+                             int Cin, int Cout, int clamp01, void* stream) {
+  if (!x || !w || !out || N <= 0 || H < 2 || W < 2) return AST_E_BADARG;
+  if (Cin % 8 != 0 || Cin > 32 || Cout < 1 || Cout > 4) return AST_E_SHAPE;
+  const int64_t nb = ((int64_t)N * H * W + 127) / 128;
+  if (nb >= 0x7fffffffLL) return AST_E_SHAPE;
+  head_conv_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), w,
+                                                                   bias, out, N, H, W, Cin, Cout, clamp01);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_nhwc_to_nchw(const void* x, int ld, float* out, int N, int C, int64_t HW, void* stream) {
+  if (!x || !out || N <= 0 || C <= 0 || HW <= 0 || ld < C) return AST_E_BADARG;
+  if (N > 65535 || (C + 31) / 32 > 65535 || (HW + 31) / 32 >= 0x7fffffffLL) return AST_E_SHAPE;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out,
+                                                              C, HW);
+  AST_CHECK_LAUNCH();
+  return 0;
+}

@@ -252,6 +252,45 @@ int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar3, float* dwpk,
 int ast_unpack_wgrad(const float* dwpk, float* w_grad, const void* dz_planar, float* b_grad, int Cout,
                      int Cin, int64_t ldq, int accumulate, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K4  MobileNet-style blocks (Encoder / Decoder / AutoEncoder, eval mode), plain NHWC bf16.
+ * Replaces the layers of DepthWiseConv (mobilenetv2.py:95-165), SELayer (:63-81), conv_3x3_bn
+ * (:38-43) and Decoder._ref_out/_img_out (models.py:300-316).
+ * ------------------------------------------------------------------------------------- */
+
+/* Pointwise conv as a tcgen05 GEMM: out[p][co] = act(sum_ci x[p][ci] * w[n?][co][ci] + bias[co]) (+ res).
+ *   x   : bf16 [N*HW][ld_in]  (first Cin channels of each row are read)
+ *   w   : bf16 [Cout][Cin], or [N][Cout][Cin] when per_sample_w (SE scaling folded in)
+ *   act : 0 none, 1 Hardswish;  residual (optional): bf16 [N*HW][ld_res];  out: bf16 [N*HW][ld_out]
+ * Cin, Cout, ld_* multiples of 8. */
+int ast_pw_conv(const void* x, int ld_in, const void* w, int per_sample_w, const float* bias, int act,
+                const void* residual, int ld_res, void* out, int ld_out, int N, int64_t HW, int Cin,
+                int Cout, void* stream);
+
+/* Depthwise k x k (3 or 5), stride 1 or 2, reflect padding (k-1)/2, + bias + optional Hardswish.
+ *   x : bf16 [N][H][W][C]; w : fp32 [k*k][C]; out : bf16 [N][Ho][Wo][C]
+ *   pool (optional) : fp32 [N][C], receives the per-channel SUM of the output (SE squeeze)
+ *   up2 : read x through a virtual nearest x2 upsample (conv input = 2H x 2W). */
+int ast_dw_conv(const void* x, const float* w, const float* bias, void* out, float* pool, int N, int C,
+                int H, int W, int k, int stride, int up2, int act, void* stream);
+
+/* SE excitation: scale[n][c] = clamp(W2 relu(W1 (pool[n]*inv_hw) + b1) + b2, 0, 1). */
+int ast_se_fc(const float* pool, float inv_hw, const float* w1, const float* b1, const float* w2,
+              const float* b2, float* scale, int N, int C, int S, void* stream);
+
+/* out[n][co][ci] (bf16) = w[co][ci] * se[n][ci]  (se NULL: plain cast, N copies). */
+int ast_scale_weights(const float* w, const float* se, void* out, int N, int Cout, int Cin, void* stream);
+
+/* Stem: NCHW fp32 image -> conv3x3 (reflect pad, no bias) -> Hardswish -> NHWC bf16; Cout <= 32. */
+int ast_stem_conv(const float* img, const float* w, void* out, int N, int H, int W, int Cout, void* stream);
+
+/* Image head: NHWC bf16 -> ReflectionPad2d(1) -> conv3x3 + bias -> NCHW fp32 (+ Hardtanh(0,1)). */
+int ast_head_conv(const void* x, const float* w, const float* bias, float* out, int N, int H, int W,
+                  int Cin, int Cout, int clamp01, void* stream);
+
+/* NHWC bf16 (row stride ld) -> NCHW fp32. */
+int ast_nhwc_to_nchw(const void* x, int ld, float* out, int N, int C, int64_t HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

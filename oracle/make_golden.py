@@ -153,6 +153,64 @@ def golden_networks(M, out):
         out["dec_in"], out["dec_out"] = f.numpy(), dec(f).numpy()
 
 
+def golden_autoencoder(M, out):
+    """Genuine ``AutoEncoder`` (models.py:322-338) under ``torch.manual_seed(2)``:
+    weight checksums, eval forward, train-mode forward (batch statistics + running-stat update) and the
+    gradients of one train_autoencoder.py:111-139 loss, at 2 x 3 x 32 x 32."""
+    import torch.nn.functional as F
+    from oracle import restate_ae as A
+    torch.manual_seed(2)
+    ae = M.AutoEncoder()
+    sd = ae.state_dict()
+    keys = sorted(sd.keys())
+    out["ae_state_keys"] = np.array(keys)
+    out["ae_state_sum"] = np.array([sd[k].double().sum().item() for k in keys])
+    out["ae_state_abs"] = np.array([sd[k].double().abs().sum().item() for k in keys])
+    x = R.rand_image(2, 32, 301)
+    out["ae_x"] = x.numpy()
+    ae.eval()
+    with torch.no_grad():
+        out["ae_eval_recon_fresh"] = ae(x).numpy()
+        taps = ae.encoder(x, out_layers=[0, 2, 12, 14])
+        for i, t in zip((0, 2, 12, 14), taps):
+            out[f"ae_eval_enc{i}"] = t.numpy()
+        out["ae_eval_autoenc"] = ae.encoder(x, auto_enc=True).numpy()
+    # one training step's loss and gradients (train_autoencoder.py:111-139), VGG = oracle recipe
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    enc = M.PretrainedEncoder().eval()
+    convs = [l for l in enc._vgg_layers if isinstance(l, torch.nn.Conv2d)]
+    with torch.no_grad():
+        for c, w, b in zip(convs, vw, vb):
+            c.weight.copy_(w)
+            c.bias.copy_(b)
+    ae.train()
+    recon = ae(x)
+    recon_loss = torch.nn.HuberLoss()(recon, x)
+    cm, rm = enc(x), enc(recon)
+    perp = None
+    for a, b in zip(rm, cm):
+        l = F.huber_loss(a, b.detach())
+        perp = l if perp is None else perp + l
+    loss = 100.0 * recon_loss + 0.01 * perp
+    loss.backward()
+    out["ae_train_recon"] = recon.detach().numpy()
+    out["ae_train_losses"] = np.array([loss.item(), recon_loss.item(), perp.item()])
+    named = dict(ae.named_parameters())
+    gkeys = sorted(named.keys())
+    out["ae_grad_keys"] = np.array(gkeys)
+    out["ae_grad_norm"] = np.array([named[k].grad.double().norm().item() for k in gkeys])
+    for k in A.GOLDEN_GRAD_KEYS:
+        out["ae_grad::" + k] = named[k].grad.numpy()
+    sd = ae.state_dict()
+    for k in A.GOLDEN_BUFFER_KEYS:
+        out["ae_buf::" + k] = sd[k].numpy()
+    # eval forward with the updated running statistics
+    ae.eval()
+    with torch.no_grad():
+        out["ae_eval_recon_after_step"] = ae(x).numpy()
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present: golden vectors can only be made in the build container")
@@ -164,7 +222,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     for name, fn, args in (("stats_adain", golden_stats_adain, (M, mu)),
                            ("losses", golden_losses, (Ls,)),
-                           ("networks", golden_networks, (M,))):
+                           ("networks", golden_networks, (M,)),
+                           ("autoencoder", golden_autoencoder, (M,))):
         d = dict(_versions())
         fn(*args, d)
         path = os.path.join(OUT, f"{name}.npz")

@@ -1,0 +1,83 @@
+"""The autoencoder oracle (oracle/restate_ae.py) against golden vectors produced by the GENUINE reference
+``AutoEncoder`` / ``Encoder`` / ``Decoder`` (oracle/make_golden.py::golden_autoencoder, executed in the
+build container), and the product module tree's construction against the same weights.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+from oracle import restate_ae as A
+from tests.conftest import load_golden
+
+
+@pytest.fixture(scope="module")
+def g():
+    return load_golden("autoencoder")
+
+
+@pytest.fixture(scope="module")
+def state():
+    return A.make_ae_state(2)
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_seeded_state_matches_reference_draw_for_draw(g, state):
+    keys = sorted(state.keys())
+    assert keys == list(g["ae_state_keys"])
+    assert len(keys) == 434
+    s = np.array([state[k].double().sum().item() for k in keys])
+    a = np.array([state[k].double().abs().sum().item() for k in keys])
+    np.testing.assert_array_equal(s, g["ae_state_sum"])
+    np.testing.assert_array_equal(a, g["ae_state_abs"])
+    n_params = sum(v.numel() for k, v in state.items() if "running_" not in k and "num_batches" not in k)
+    assert n_params == 2925931
+
+
+def test_eval_forward_bit_exact(g, state):
+    x = T(g["ae_x"])
+    P = A.clone_state(state)
+    with torch.no_grad():
+        assert torch.equal(A.autoencoder_forward(P, x), T(g["ae_eval_recon_fresh"]))
+        taps = A.encoder_forward(P, x, (0, 2, 12, 14))
+        for i, t in zip((0, 2, 12, 14), taps):
+            assert torch.equal(t, T(g[f"ae_eval_enc{i}"])), i
+        assert torch.equal(A.encoder_forward(P, x, auto_enc=True), T(g["ae_eval_autoenc"]))
+
+
+def test_train_step_losses_gradients_and_running_stats(g, state):
+    x = T(g["ae_x"])
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    P = A.clone_state(state, requires_grad=True)
+    loss, recon_loss, perp, recon = A.ae_losses(P, x, vw, vb)
+    assert torch.equal(recon.detach(), T(g["ae_train_recon"]))
+    np.testing.assert_allclose([loss.item(), recon_loss.item(), perp.item()], g["ae_train_losses"], rtol=1e-6)
+    loss.backward()
+    gkeys = list(g["ae_grad_keys"])
+    assert gkeys == sorted(k for k, v in P.items() if v.requires_grad)
+    norms = np.array([P[k].grad.double().norm().item() for k in gkeys])
+    np.testing.assert_allclose(norms, g["ae_grad_norm"], rtol=1e-4, atol=1e-9)
+    for k in A.GOLDEN_GRAD_KEYS:
+        torch.testing.assert_close(P[k].grad, T(g["ae_grad::" + k]), rtol=1e-4, atol=1e-7)
+    for k in A.GOLDEN_BUFFER_KEYS:
+        assert torch.equal(P[k].detach(), T(g["ae_buf::" + k])), k
+    with torch.no_grad():
+        assert torch.equal(A.autoencoder_forward(P, x), T(g["ae_eval_recon_after_step"]))
+
+
+def test_product_module_tree_draws_the_same_weights(g):
+    """arbitrarystyletransfer_b200.mobilenet.AutoEncoder() under manual_seed(2) must have the reference's
+    434 state-dict keys with identical values (checkpoints ae.pth load unchanged)."""
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    torch.manual_seed(2)
+    ae = MB.AutoEncoder()
+    sd = ae.state_dict()
+    keys = sorted(sd.keys())
+    assert keys == list(g["ae_state_keys"])
+    s = np.array([sd[k].double().sum().item() for k in keys])
+    np.testing.assert_array_equal(s, g["ae_state_sum"])
+    ref = A.make_ae_state(2)
+    ae.load_state_dict(ref, strict=True)

@@ -74,3 +74,26 @@ def test_vgg_names_and_early_return(ref):
         out = enc(x)
         assert len(out) == 1
         torch.testing.assert_close(out[0], R.vgg_relu4_1(x, vw, vb), rtol=1e-5, atol=1e-5)
+
+
+def test_autoencoder_restatement_live(ref):
+    """oracle/restate_ae.py vs the genuine AutoEncoder at a ragged size (40 x 24), eval and train mode."""
+    from oracle import restate_ae as A
+    M = ref[0]
+    torch.manual_seed(5)
+    ae = M.AutoEncoder()
+    sd = A.make_ae_state(5)
+    ref_sd = ae.state_dict()
+    assert sorted(sd) == sorted(ref_sd)
+    assert all(torch.equal(sd[k], ref_sd[k]) for k in sd)
+    x = torch.rand(3, 3, 40, 24, generator=torch.Generator().manual_seed(9))
+    ae.train()
+    P = A.clone_state(sd)
+    with torch.no_grad():
+        assert torch.equal(ae(x), A.autoencoder_forward(P, x, training=True))
+        ae.eval()
+        assert torch.equal(ae(x), A.autoencoder_forward(P, x, training=False))
+        dec = M.Decoder(exporting=True)
+        dsd = {"decoder." + k: v for k, v in dec.state_dict().items()}
+        z = torch.randn(1, 128, 3, 5, generator=torch.Generator().manual_seed(3))
+        assert torch.equal(dec(z), A.decoder_forward(dsd, z, exporting=True))
