@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
 
 
 _vp, _i, _i64, _f, _u, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint, C.c_size_t
+_d = C.c_double
 _fp = C.POINTER(C.c_float)
 
 # name -> (restype, argtypes); every symbol include/ast_b200.h declares
@@ -69,13 +70,31 @@ PROTOTYPES = {
     "ast_native_to_planar": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_unpack_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp]),
-    "ast_pw_conv": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp]),
+    "ast_pw_conv": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp, _i, _i, _vp]),
     "ast_dw_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "ast_se_fc": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ast_se_fc": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ast_scale_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
-    "ast_stem_conv": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_stem_conv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ast_head_conv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_nhwc_to_nchw": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
+    "ast_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp]),
+    "ast_bn_stats": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
+    "ast_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _vp]),
+    "ast_affine_act": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _vp]),
+    "ast_dw_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
+    "ast_se_bn_combine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _vp]),
+    "ast_dw_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
+    "ast_bn_bwd_reduce": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i64, _vp]),
+    "ast_bn_bwd_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _i, _vp]),
+    "ast_bn_bwd_apply": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i64, _vp]),
+    "ast_dw_conv_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_dw_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ast_se_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ast_pw_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _i64, _vp, _i64, _i64, _vp]),
+    "ast_stem_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_head_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ast_head_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ast_prep_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -65,17 +65,18 @@ dw_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w 
           acc[6] = fmaf(xv[6], w1.z, acc[6]); acc[7] = fmaf(xv[7], w1.w, acc[7]);
         }
       }
-      if (act) {
+      if (act == 1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = hswish(acc[j]);
       }
       const uint4 o = Vec16<true>::pack(acc);
       *reinterpret_cast<uint4*>(out + (((int64_t)n * Ho + ho) * Wo + wo) * C + v * 8) = o;
-      // pool what the next layer will actually read (the bf16-rounded value)
+      // pool what the next layer will actually read (the bf16-rounded value); act == 2 (training):
+      // the RAW value is stored for the backward pass and the pool sees Hardswish of it
       float r[8];
       Vec16<true>::unpack(o, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) psum[j] += r[j];
+      for (int j = 0; j < 8; ++j) psum[j] += (act == 2) ? hswish(r[j]) : r[j];
     }
   }
   if (!pool) return;
@@ -96,7 +97,8 @@ dw_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w 
 __global__ void __launch_bounds__(kM)
 se_fc_kernel(const float* __restrict__ pool, float inv_hw, const float* __restrict__ w1,
              const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-             float* __restrict__ scale, int C, int S) {
+             float* __restrict__ scale, float* __restrict__ hid_out, float* __restrict__ pre_out, int C,
+             int S) {
   extern __shared__ float sm[];  // mean[C] + hid[S]
   float* mean = sm;
   float* hid = sm + C;
@@ -107,12 +109,14 @@ se_fc_kernel(const float* __restrict__ pool, float inv_hw, const float* __restri
     float a = b1[j];
     for (int c = 0; c < C; ++c) a = fmaf(w1[(int64_t)j * C + c], mean[c], a);
     hid[j] = fmaxf(a, 0.f);
+    if (hid_out) hid_out[(int64_t)n * S + j] = hid[j];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += kM) {
     float a = b2[c];
     for (int j = 0; j < S; ++j) a = fmaf(w2[(int64_t)c * S + j], hid[j], a);
     scale[(int64_t)n * C + c] = fminf(fmaxf(a, 0.f), 1.f);
+    if (pre_out) pre_out[(int64_t)n * C + c] = a;
   }
 }
 
@@ -138,7 +142,8 @@ __global__ void scale_weights_kernel(const float* __restrict__ w, const float* _
 constexpr int kStemMaxCout = 32;
 __global__ void __launch_bounds__(128)
 stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*OIHW [Cout][3][3][3]*/,
-                 __nv_bfloat16* __restrict__ out, int N, int H, int W, int Cout) {
+                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_raw, int N, int H, int W,
+                 int Cout) {
   __shared__ float s_w[27][kStemMaxCout];
   for (int i = threadIdx.x; i < 27 * kStemMaxCout; i += 128) {
     const int kk = i / kStemMaxCout, c = i % kStemMaxCout;
@@ -162,10 +167,19 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*OI
         for (int c = 0; c < kStemMaxCout; ++c) acc[c] = fmaf(v, s_w[ci * 9 + kh * 3 + kw][c], acc[c]);
       }
   __nv_bfloat16* o = out + pix * Cout;
-  for (int c = 0; c < Cout; c += 8) {
+#pragma unroll
+  for (int c = 0; c < kStemMaxCout; c += 8) {
+    if (c >= Cout) break;
     float t[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = hswish(acc[c + j]);
+    for (int j = 0; j < 8; ++j) t[j] = acc[c + j];
+    if (out_raw) {   // training: keep the rounded pre-activation, activate the rounded value
+      const uint4 rv = Vec16<true>::pack(t);
+      *reinterpret_cast<uint4*>(out_raw + pix * Cout + c) = rv;
+      Vec16<true>::unpack(rv, t);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = hswish(t[j]);
     *reinterpret_cast<uint4*>(o + c) = Vec16<true>::pack(t);
   }
 }
@@ -257,11 +271,13 @@ extern "C" int ast_dw_conv(const void* x, const float* w, const float* bias, voi
 }
 
 extern "C" int ast_se_fc(const float* pool, float inv_hw, const float* w1, const float* b1, const float* w2,
-                         const float* b2, float* scale, int N, int C, int S, void* stream) {
+                         const float* b2, float* scale, float* hid_out, float* pre_out, int N, int C, int S,
+                         void* stream) {
   if (!pool || !w1 || !b1 || !w2 || !b2 || !scale || N <= 0 || C <= 0 || S <= 0) return AST_E_BADARG;
   const size_t smem = (size_t)(C + S) * sizeof(float);
   if (smem > 48 * 1024) return AST_E_SHAPE;
-  se_fc_kernel<<<N, kM, smem, (cudaStream_t)stream>>>(pool, inv_hw, w1, b1, w2, b2, scale, C, S);
+  se_fc_kernel<<<N, kM, smem, (cudaStream_t)stream>>>(pool, inv_hw, w1, b1, w2, b2, scale, hid_out,
+                                                               pre_out, C, S);
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -278,14 +294,14 @@ extern "C" int ast_scale_weights(const float* w, const float* se, void* out, int
   return 0;
 }
 
-extern "C" int ast_stem_conv(const float* img, const float* w, void* out, int N, int H, int W, int Cout,
-                             void* stream) {
+extern "C" int ast_stem_conv(const float* img, const float* w, void* out, void* out_raw, int N, int H, int W,
+                             int Cout, void* stream) {
   if (!img || !w || !out || N <= 0 || H < 2 || W < 2) return AST_E_BADARG;
   if (Cout % 8 != 0 || Cout > kStemMaxCout) return AST_E_SHAPE;
   const int64_t nb = ((int64_t)N * H * W + 127) / 128;
   if (nb >= 0x7fffffffLL) return AST_E_SHAPE;
-  stem_conv_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(img, w, reinterpret_cast<__nv_bfloat16*>(out),
-                                                                   N, H, W, Cout);
+  stem_conv_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(
+      img, w, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(out_raw), N, H, W, Cout);
   AST_CHECK_LAUNCH();
   return 0;
 }

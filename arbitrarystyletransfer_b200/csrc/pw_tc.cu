@@ -30,6 +30,9 @@ struct PwParams {
   const float* bias;               // [Cout] or null
   const __nv_bfloat16* residual;   // [N*HW][ld_res] or null
   __nv_bfloat16* out;              // [N*HW][ld_out]
+  __nv_bfloat16* out_act;          // optional [N*HW][ld_act]: Hardswish(out) while out keeps the raw value
+  int ld_act;
+  int res_w;                       // > 0: residual is read through a nearest x2 upsample; res_w = output width
 };
 
 __device__ __forceinline__ float hardswish(float x) {
@@ -102,7 +105,8 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, k ? 1u : accum);
+          if (ks * 64 + k * 16 < p.Cin)   // K tail: skip 16-channel steps that are pure TMA zero fill
+            umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, k ? 1u : accum);
         umma_commit(empty_bar(stage));
       }
       __syncwarp();
@@ -119,6 +123,11 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int64_t pix = (int64_t)ti * 128 + e * 32 + lane;   // pixel inside the image
     const bool ok = pix < p.HW;
     const int64_t row = (int64_t)n * p.HW + pix;
+    int64_t rrow = row;
+    if (p.res_w > 0 && ok) {   // residual = the block input BEFORE the nearest x2 upsample (models.py:265-267)
+      const int h = (int)(pix / p.res_w), w = (int)(pix % p.res_w);
+      rrow = (int64_t)n * (p.HW >> 2) + (int64_t)(h >> 1) * (p.res_w >> 1) + (w >> 1);
+    }
     for (int c0 = 0; c0 < p.BN; c0 += 16) {
       uint32_t v[16];
       tmem_ld_32x16(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)c0, v);
@@ -130,11 +139,11 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int i = 0; i < 16; ++i) {
         f[i] = __uint_as_float(v[i]);
         if (p.bias && co0 + i < p.Cout) f[i] += __ldg(p.bias + co0 + i);
-        if (p.act) f[i] = hardswish(f[i]);
+        if (p.act && !p.out_act) f[i] = hardswish(f[i]);
       }
       const int valid = min(16, p.Cout - co0);   // multiple of 8 (host enforces Cout % 8 == 0)
       if (p.residual) {
-        const __nv_bfloat16* rp = p.residual + row * p.ld_res + co0;
+        const __nv_bfloat16* rp = p.residual + rrow * p.ld_res + co0;
         for (int i = 0; i < valid; i += 8) {
           float r[8];
           Vec16<true>::unpack(__ldg(reinterpret_cast<const uint4*>(rp + i)), r);
@@ -147,7 +156,15 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = f[i + j];
-        *reinterpret_cast<uint4*>(op + i) = Vec16<true>::pack(o);
+        const uint4 ov = Vec16<true>::pack(o);
+        *reinterpret_cast<uint4*>(op + i) = ov;
+        if (p.out_act) {   // training: raw pre-activation in `out`, Hardswish of the ROUNDED value here
+          float r[8];
+          Vec16<true>::unpack(ov, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = hardswish(r[j]);
+          *reinterpret_cast<uint4*>(p.out_act + row * p.ld_act + co0 + i) = Vec16<true>::pack(r);
+        }
       }
     }
   }
@@ -167,8 +184,9 @@ using namespace ast::tc;
 
 extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_sample_w, const float* bias,
                            int act, const void* residual, int ld_res, void* out, int ld_out, int N,
-                           int64_t HW, int Cin, int Cout, void* stream) {
+                           int64_t HW, int Cin, int Cout, void* out_act, int ld_act, int res_up2_w, void* stream) {
   if (!x || !w || !out || N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0) return AST_E_BADARG;
+  if (out_act && (ld_act % 8 != 0 || ld_act < Cout || !aligned16(out_act) || residual)) return AST_E_SHAPE;
   if (Cin % 8 != 0 || Cout % 8 != 0 || ld_in % 8 != 0 || ld_out % 8 != 0 || (residual && ld_res % 8 != 0))
     return AST_E_SHAPE;
   if (ld_in < Cin || ld_out < Cout || HW >= 0x7fffffffLL) return AST_E_SHAPE;
@@ -187,6 +205,12 @@ extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_samp
   p.ld_out = ld_out; p.ld_res = ld_res;
   p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.out_act = reinterpret_cast<__nv_bfloat16*>(out_act);
+  p.ld_act = ld_act;
+  if (res_up2_w < 0 || (res_up2_w > 0 && (!residual || res_up2_w % 2 != 0 || HW % res_up2_w != 0 ||
+                                          (HW / res_up2_w) % 2 != 0)))
+    return AST_E_SHAPE;
+  p.res_w = res_up2_w;
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)HW, (uint64_t)N};

@@ -4,10 +4,14 @@ building blocks ``DepthWiseConv`` / ``SELayer`` / ``conv_3x3_bn`` (mobilenetv2.p
 95-181).  Module trees, attribute names and ModuleList indices mirror the reference so that its
 state dicts (``ae.pth`` keys such as ``encoder.mob_net.1._layers.3.weight``) load unchanged.
 
-Status: FORWARD, EVAL MODE (BatchNorm running statistics, folded into the convolutions).  Training
-mode (batch statistics + backward) is not implemented yet and raises instead of computing silently
-wrong results.  All device work goes through libast_b200 (pointwise convs on tcgen05, depthwise
-stencil with the SE squeeze fused, SE excitation folded into per-sample pointwise weights).
+Two execution paths, both entirely through libast_b200 (no torch arithmetic on activations):
+  * inference (eval mode, no grad): BatchNorm running statistics folded into the convolutions, SE
+    excitation folded into per-sample pointwise weights, SE squeeze fused into the depthwise stencil;
+  * training (train_autoencoder.py:111-148): BatchNorm with batch statistics and running-stat updates,
+    every intermediate kept in NHWC bf16, and hand-written backward kernels (pointwise data / weight
+    gradients on tcgen05, depthwise data / weight gradients, BatchNorm / Hardswish / SE backward), wired
+    into autograd one block at a time so the reference's optimiser / clip code runs unchanged.
+Eval-mode BatchNorm WITH gradients is not implemented and raises.
 """
 from __future__ import annotations
 
@@ -43,51 +47,146 @@ def _make_divisible(v, divisor, min_value=None):
     return new_v
 
 
-# ---- thin kernel wrappers (NHWC bf16 tensors) ------------------------------------------------------
+# ---- thin kernel wrappers (NHWC bf16 tensors, "row-strided": stride(3) == 1, rows ld apart) -------
 def _st(t):
     return L.stream_ptr(t.device)
 
 
-def pw_conv(x, w_bf16, bias, act, out_channels, residual=None, per_sample=False):
-    """x: (N,H,W,Cin) bf16 (last-dim stride 1, row stride x.stride(2)) -> (N,H,W,Cout) bf16."""
+def _rows(t):
+    """(tensor, ld) with t addressable as a [N*H*W][ld] row matrix (a channel slice of a wider contiguous
+    NHWC buffer qualifies); anything else is made contiguous."""
+    N, H, W, Cc = t.shape
+    ld = t.stride(2)
+    ok = (t.stride(3) == 1 and ld % 8 == 0 and ld >= Cc and t.stride(1) == W * ld
+          and t.stride(0) == H * W * ld and t.data_ptr() % 16 == 0)
+    if not ok:
+        t = t.contiguous()
+        ld = Cc
+    return t, ld
+
+
+def _empty(N, H, W, Cc, dev):
+    return torch.empty(N, H, W, Cc, device=dev, dtype=torch.bfloat16)
+
+
+def pw_conv(x, w_bf16, bias, act, out_channels, residual=None, per_sample=False, want_raw=False, res_up2=False):
+    """x: (N,H,W,Cin) bf16 row-strided -> (N,H,W,Cout) bf16.  ``want_raw`` (training): returns
+    (raw pre-activation, Hardswish(raw)).  ``res_up2``: residual is the half-resolution tensor, read
+    through a nearest x2 upsample."""
     lib = L.load()
+    x, ldx = _rows(x)
     N, H, W, Cin = x.shape
-    out = torch.empty(N, H, W, out_channels, device=x.device, dtype=torch.bfloat16)
-    L.check(lib.ast_pw_conv(x.data_ptr(), x.stride(2), w_bf16.data_ptr(), int(per_sample), L.ptr(bias),
-                            int(act), L.ptr(residual), residual.stride(2) if residual is not None else 0,
-                            out.data_ptr(), out_channels, N, H * W, Cin, out_channels, _st(x)), "ast_pw_conv")
-    return out
+    out = _empty(N, H, W, out_channels, x.device)
+    out_act = _empty(N, H, W, out_channels, x.device) if want_raw else None
+    ld_res = 0
+    if residual is not None:
+        residual, ld_res = _rows(residual)
+    L.check(lib.ast_pw_conv(x.data_ptr(), ldx, w_bf16.data_ptr(), int(per_sample), L.ptr(bias), int(act),
+                            L.ptr(residual), ld_res, out.data_ptr(), out_channels, N, H * W, Cin, out_channels,
+                            L.ptr(out_act), out_channels, W if res_up2 else 0, _st(x)), "ast_pw_conv")
+    return (out, out_act) if want_raw else out
 
 
-def dw_conv(x, w_kkc, bias, k, stride, up2=False, act=True, want_pool=True):
+def dw_conv(x, w_kkc, bias, k, stride, up2=False, act=1, want_pool=True):
+    """act: 0 none, 1 store Hardswish, 2 store raw + pool Hardswish (training)."""
     lib = L.load()
     N, H, W, Cc = x.shape
+    assert x.is_contiguous()
     Hin, Win = (2 * H, 2 * W) if up2 else (H, W)
     pad = (k - 1) // 2
     Ho, Wo = (Hin + 2 * pad - k) // stride + 1, (Win + 2 * pad - k) // stride + 1
-    out = torch.empty(N, Ho, Wo, Cc, device=x.device, dtype=torch.bfloat16)
+    out = _empty(N, Ho, Wo, Cc, x.device)
     pool = torch.empty(N, Cc, device=x.device, dtype=torch.float32) if want_pool else None
     L.check(lib.ast_dw_conv(x.data_ptr(), w_kkc.data_ptr(), L.ptr(bias), out.data_ptr(), L.ptr(pool), N, Cc,
                             H, W, k, stride, int(up2), int(act), _st(x)), "ast_dw_conv")
     return out, pool
 
 
+def se_fc(pool, inv_hw, w1, b1, w2, b2, save=False):
+    lib = L.load()
+    N, Cc = pool.shape
+    S = w1.shape[0]
+    scale = torch.empty(N, Cc, device=pool.device, dtype=torch.float32)
+    hid = torch.empty(N, S, device=pool.device, dtype=torch.float32) if save else None
+    pre = torch.empty(N, Cc, device=pool.device, dtype=torch.float32) if save else None
+    L.check(lib.ast_se_fc(pool.data_ptr(), float(inv_hw), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                          b2.data_ptr(), scale.data_ptr(), L.ptr(hid), L.ptr(pre), N, Cc, S, _st(pool)),
+            "ast_se_fc")
+    return scale, hid, pre
+
+
+def affine_act(x, sc, sh, act, se=None, res=None, want_out=True, want_pool=False):
+    lib = L.load()
+    x, ldx = _rows(x)
+    N, H, W, Cc = x.shape
+    out = _empty(N, H, W, Cc, x.device) if want_out else None
+    pool = torch.empty(N, Cc, device=x.device, dtype=torch.float32) if want_pool else None
+    ld_res = 0
+    if res is not None:
+        res, ld_res = _rows(res)
+    L.check(lib.ast_affine_act(x.data_ptr(), ldx, L.ptr(sc), L.ptr(sh), int(act), L.ptr(se), L.ptr(res), ld_res,
+                               L.ptr(out), Cc, L.ptr(pool), N, Cc, H * W, _st(x)), "ast_affine_act")
+    return out, pool
+
+
+def prep_weight(w, rows, cols, mode):
+    """fp32 parameter viewed as [rows][cols] -> 0: bf16 same layout, 1: bf16 transposed, 2: fp32 transposed."""
+    lib = L.load()
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    shape = (rows, cols) if mode == 0 else (cols, rows)
+    out = torch.empty(shape, device=w.device, dtype=torch.float32 if mode == 2 else torch.bfloat16)
+    L.check(lib.ast_prep_weight(w.data_ptr(), out.data_ptr(), rows, cols, mode, _st(w)), "ast_prep_weight")
+    return out
+
+
 def nchw_to_nhwc(x):
     lib = L.load()
     x = x.float().contiguous()
     N, Cc, H, W = x.shape
-    out = torch.empty(N, H, W, Cc, device=x.device, dtype=torch.bfloat16)
-    L.check(lib.ast_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), N, Cc, H * W, _st(x)), "ast_nchw_to_nhwc")
+    out = _empty(N, H, W, Cc, x.device)
+    L.check(lib.ast_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), Cc, N, Cc, H * W, _st(x)), "ast_nchw_to_nhwc")
     return out
 
 
 def nhwc_to_nchw(x):
     lib = L.load()
+    x, ld = _rows(x)
     N, H, W, Cc = x.shape
     out = torch.empty(N, Cc, H, W, device=x.device, dtype=torch.float32)
-    L.check(lib.ast_nhwc_to_nchw(x.data_ptr(), x.stride(2), out.data_ptr(), N, Cc, H * W, _st(x)),
-            "ast_nhwc_to_nchw")
+    L.check(lib.ast_nhwc_to_nchw(x.data_ptr(), ld, out.data_ptr(), N, Cc, H * W, _st(x)), "ast_nhwc_to_nchw")
     return out
+
+
+class _ToNHWC(torch.autograd.Function):
+    """NCHW fp32 -> NHWC bf16; the gradient goes back through the inverse conversion."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return nchw_to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return nhwc_to_nchw(g)
+
+
+class _ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return nhwc_to_nchw(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return nchw_to_nhwc(g)
+
+
+def to_nhwc(x):
+    return _ToNHWC.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else nchw_to_nhwc(x)
+
+
+def to_nchw(x):
+    return _ToNCHW.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else nhwc_to_nchw(x)
 
 
 def _fold_bn(conv_w, bn):
@@ -99,13 +198,261 @@ def _fold_bn(conv_w, bn):
     return w * inv.view(-1, 1, 1, 1), bn.bias.detach().float() - bn.running_mean.detach().float() * inv
 
 
-def _forward_only(module):
-    if module.training and any(isinstance(m, nn.BatchNorm2d) for m in module.modules()):
-        raise L.AstError("train-mode BatchNorm (batch statistics) is not implemented for the MobileNet-style "
-                         "blocks yet: call .eval()")
-    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise L.AstError("the MobileNet-style blocks are forward-only so far (no backward kernels): "
-                         "call them under torch.no_grad()")
+# ---- training: BatchNorm with batch statistics, block forward / backward ----------------------------
+def _bn_train_forward(a, bn):
+    """Batch statistics of the NHWC tensor ``a`` for nn.BatchNorm2d ``bn`` (mobilenetv2.py:108 etc.): returns
+    stat = float[4][C] (mean, invstd, scale, shift) and updates the running statistics in place."""
+    lib = L.load()
+    a, ld = _rows(a)
+    N, H, W, Cc = a.shape
+    if bn.momentum is None:
+        raise L.AstError("BatchNorm2d(momentum=None) is not supported")
+    sums = torch.empty(2, Cc, device=a.device, dtype=torch.float64)
+    stat = torch.empty(4, Cc, device=a.device, dtype=torch.float32)
+    L.check(lib.ast_bn_stats(a.data_ptr(), ld, sums.data_ptr(), N, Cc, H * W, _st(a)), "ast_bn_stats")
+    track = bn.training and bn.track_running_stats
+    L.check(lib.ast_bn_finalize(sums.data_ptr(), float(N * H * W), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                bn.running_mean.data_ptr() if track else None,
+                                bn.running_var.data_ptr() if track else None, float(bn.momentum), float(bn.eps),
+                                stat.data_ptr(), Cc, _st(a)), "ast_bn_finalize")
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return stat
+
+
+def _bn_backward(dy, a, stat):
+    """Generic BatchNorm backward on NHWC tensors: returns (da, dgamma, dbeta)."""
+    lib = L.load()
+    dy, ld_dy = _rows(dy)
+    a, ld_a = _rows(a)
+    N, H, W, Cc = a.shape
+    dev = a.device
+    sums = torch.empty(2, Cc, device=dev, dtype=torch.float64)
+    coef = torch.empty(2, Cc, device=dev, dtype=torch.float32)
+    dgamma = torch.empty(Cc, device=dev, dtype=torch.float32)
+    dbeta = torch.empty(Cc, device=dev, dtype=torch.float32)
+    da = _empty(N, H, W, Cc, dev)
+    st = _st(a)
+    L.check(lib.ast_bn_bwd_reduce(dy.data_ptr(), ld_dy, a.data_ptr(), ld_a, stat.data_ptr(), sums.data_ptr(),
+                                  N, Cc, H * W, st), "ast_bn_bwd_reduce")
+    L.check(lib.ast_bn_bwd_finalize(sums.data_ptr(), float(N * H * W), dgamma.data_ptr(), dbeta.data_ptr(),
+                                    coef.data_ptr(), Cc, st), "ast_bn_bwd_finalize")
+    L.check(lib.ast_bn_bwd_apply(dy.data_ptr(), ld_dy, a.data_ptr(), ld_a, stat.data_ptr(), coef.data_ptr(),
+                                 da.data_ptr(), N, Cc, H * W, st), "ast_bn_bwd_apply")
+    return da, dgamma, dbeta
+
+
+def _pw_wgrad(a, b, out, si, sj):
+    """out[i*si + j*sj] += sum_p a[p][i] * b[p][j]  (a, b NHWC row-strided bf16; out fp32, zero-filled)."""
+    lib = L.load()
+    a, lda = _rows(a)
+    b, ldb = _rows(b)
+    P = a.shape[0] * a.shape[1] * a.shape[2]
+    L.check(lib.ast_pw_wgrad(a.data_ptr(), lda, a.shape[3], b.data_ptr(), ldb, b.shape[3], P, out.data_ptr(),
+                             si, sj, _st(a)), "ast_pw_wgrad")
+
+
+class _BlockFn(torch.autograd.Function):
+    """One DepthWiseConv block (mobilenetv2.py:95-165) in training mode on NHWC bf16 tensors.
+    ``params`` follow DepthWiseConv._param_list()."""
+
+    @staticmethod
+    def forward(ctx, x, mod, up2, *params):
+        lib = L.load()
+        P = mod._unpack(params)
+        norm, expand = mod.use_norm, mod.expand
+        bns = mod._bns()
+        x = _rows(x)[0] if expand else x.contiguous()
+        N, H, W, _ = x.shape
+        dev = x.device
+        hid, k, stride = mod.hidden, mod.k, mod.stride
+        a1 = stat1 = stat2 = stat3 = a3 = None
+        if expand:
+            if up2:
+                raise L.AstError("the upsampled input is only supported for expand_ratio == 1 blocks")
+            w1b = prep_weight(P["w1"], hid, mod.inp, 0)
+            if norm:
+                a1 = pw_conv(x, w1b, None, 0, hid)
+                stat1 = _bn_train_forward(a1, bns[0])
+                dw_in, _ = affine_act(a1, stat1[2], stat1[3], 1)
+            else:
+                a1, dw_in = pw_conv(x, w1b, None, 1, hid, want_raw=True)
+        else:
+            dw_in = x
+        wd = prep_weight(P["wd"], hid, k * k, 2)                       # fp32 [k*k][C]
+        a2, pool = dw_conv(dw_in, wd, None, k, stride, up2=up2, act=0 if norm else 2, want_pool=not norm)
+        Ho, Wo = a2.shape[1], a2.shape[2]
+        if norm:
+            stat2 = _bn_train_forward(a2, bns[1])
+            _, pool = affine_act(a2, stat2[2], stat2[3], 1, want_out=False, want_pool=True)
+        inv_hw = 1.0 / (Ho * Wo)
+        s, sehid, sepre = se_fc(pool, inv_hw, P["se_w1"], P["se_b1"], P["se_w2"], P["se_b2"], save=True)
+        u, _ = affine_act(a2, stat2[2] if norm else None, stat2[3] if norm else None, 1, se=s)
+        w2b = prep_weight(P["w2"], mod.oup, hid, 0)
+        res = x if mod.identity else None
+        if norm:
+            a3 = pw_conv(u, w2b, None, 0, mod.oup)
+            stat3 = _bn_train_forward(a3, bns[2])
+            out, _ = affine_act(a3, stat3[2], stat3[3], 0, res=res)
+        else:
+            out = pw_conv(u, w2b, None, 0, mod.oup, residual=res, res_up2=bool(up2 and mod.identity))
+        ctx.mod, ctx.up2, ctx.geom = mod, up2, (N, H, W, Ho, Wo)
+        ctx.n_params = len(params)
+        ctx.save_for_backward(x, a1, dw_in if expand else None, a2, u, a3, s, sehid, sepre, pool, stat1, stat2,
+                              stat3, wd, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = L.load()
+        mod, up2 = ctx.mod, ctx.up2
+        N, H, W, Ho, Wo = ctx.geom
+        saved = ctx.saved_tensors
+        x, a1, h1, a2, u, a3, s, sehid, sepre, pool, stat1, stat2, stat3, wd = saved[:14]
+        P = mod._unpack(saved[14:])
+        norm, expand = mod.use_norm, mod.expand
+        hid, k, stride, inp, oup = mod.hidden, mod.k, mod.stride, mod.inp, mod.oup
+        dev = x.device
+        st = _st(x)
+        grads = {}
+        d_out, _ = _rows(d_out.to(torch.bfloat16))
+        # ---- pw-linear (+ its norm) ----
+        if norm:
+            d_a3, grads["g3"], grads["b3"] = _bn_backward(d_out, a3, stat3)
+        else:
+            d_a3 = d_out
+        d_u = pw_conv(d_a3, prep_weight(P["w2"], oup, hid, 1), None, 0, hid)
+        dW2 = torch.zeros_like(P["w2"], dtype=torch.float32)
+        _pw_wgrad(u, d_a3, dW2, 1, hid)                                  # dW2[j][i] += sum u[p][i] d_a3[p][j]
+        grads["w2"] = dW2
+        # ---- SE, Hardswish and the depthwise norm ----
+        HWo = Ho * Wo
+        T = torch.empty(N, 5, hid, device=dev, dtype=torch.float32)
+        L.check(lib.ast_dw_bwd_reduce(d_u.data_ptr(), a2.data_ptr(), L.ptr(stat2), T.data_ptr(), N, hid, HWo, st),
+                "ast_dw_bwd_reduce")
+        S = P["se_w1"].shape[0]
+        dpre = torch.empty(N, hid, device=dev, dtype=torch.float32)
+        dhid = torch.empty(N, S, device=dev, dtype=torch.float32)
+        g = torch.empty(N, hid, device=dev, dtype=torch.float32)
+        for nm in ("se_w1", "se_b1", "se_w2", "se_b2"):
+            grads[nm] = torch.empty_like(P[nm], dtype=torch.float32)
+        L.check(lib.ast_se_bwd(T.data_ptr(), 5 * hid, sepre.data_ptr(), sehid.data_ptr(), pool.data_ptr(),
+                               1.0 / HWo, P["se_w1"].data_ptr(), P["se_w2"].data_ptr(), dpre.data_ptr(),
+                               dhid.data_ptr(), g.data_ptr(), grads["se_w1"].data_ptr(), grads["se_b1"].data_ptr(),
+                               grads["se_w2"].data_ptr(), grads["se_b2"].data_ptr(), N, hid, S, st), "ast_se_bwd")
+        coef2 = None
+        if norm:
+            coef2 = torch.empty(2, hid, device=dev, dtype=torch.float32)
+            grads["g2"] = torch.empty(hid, device=dev, dtype=torch.float32)
+            grads["b2"] = torch.empty(hid, device=dev, dtype=torch.float32)
+            L.check(lib.ast_se_bn_combine(T.data_ptr(), s.data_ptr(), g.data_ptr(), grads["g2"].data_ptr(),
+                                          grads["b2"].data_ptr(), coef2.data_ptr(), N, hid, float(N * HWo), st),
+                    "ast_se_bn_combine")
+        d_a2 = _empty(N, Ho, Wo, hid, dev)
+        L.check(lib.ast_dw_bwd_apply(d_u.data_ptr(), a2.data_ptr(), s.data_ptr(), g.data_ptr(), L.ptr(stat2),
+                                     L.ptr(coef2), d_a2.data_ptr(), N, hid, HWo, st), "ast_dw_bwd_apply")
+        # ---- depthwise conv ----
+        dw_in = h1 if expand else x
+        dWd = torch.zeros_like(P["wd"], dtype=torch.float32)
+        L.check(lib.ast_dw_conv_wgrad(d_a2.data_ptr(), dw_in.data_ptr(), dWd.data_ptr(), N, hid, H, W, k, stride,
+                                      int(up2), st), "ast_dw_conv_wgrad")
+        grads["wd"] = dWd
+        d_in = _empty(N, H, W, hid, dev)
+        dres = d_out if (not expand and mod.identity) else None
+        if dres is not None and not dres.is_contiguous():
+            dres = dres.contiguous()
+        L.check(lib.ast_dw_conv_dgrad(d_a2.data_ptr(), wd.data_ptr(), L.ptr(a1) if expand else None,
+                                      L.ptr(stat1) if expand else None, L.ptr(dres), d_in.data_ptr(), N, hid, H, W,
+                                      k, stride, int(up2), st), "ast_dw_conv_dgrad")
+        # ---- pw expand (+ its norm) ----
+        if expand:
+            if norm:
+                d_a1, grads["g1"], grads["b1"] = _bn_backward(d_in, a1, stat1)
+            else:
+                d_a1 = d_in
+            dW1 = torch.zeros_like(P["w1"], dtype=torch.float32)
+            _pw_wgrad(d_a1, x, dW1, inp, 1)                              # dW1[i][j] += sum d_a1[p][i] x[p][j]
+            grads["w1"] = dW1
+            d_x = None
+            if ctx.needs_input_grad[0]:
+                d_x = pw_conv(d_a1, prep_weight(P["w1"], hid, inp, 1), None, 0, inp,
+                              residual=d_out if mod.identity else None)
+        else:
+            d_x = d_in if ctx.needs_input_grad[0] else None
+        return (d_x, None, None) + tuple(grads[nm] for nm in mod._param_names())
+
+
+class _StemFn(torch.autograd.Function):
+    """conv_3x3_bn (mobilenetv2.py:38-43) from the NCHW fp32 image to NHWC bf16, with the weight gradient."""
+
+    @staticmethod
+    def forward(ctx, img, w):
+        lib = L.load()
+        img = img.float().contiguous()
+        N, _, H, W = img.shape
+        cout = w.shape[0]
+        y = _empty(N, H, W, cout, img.device)
+        z = _empty(N, H, W, cout, img.device)
+        wf = w.detach().float().contiguous()
+        L.check(lib.ast_stem_conv(img.data_ptr(), wf.data_ptr(), y.data_ptr(), z.data_ptr(), N, H, W, cout,
+                                  _st(img)), "ast_stem_conv")
+        ctx.save_for_backward(img, z)
+        ctx.wshape = tuple(w.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        if ctx.needs_input_grad[0]:
+            raise L.AstError("gradient with respect to the Encoder's input image is not implemented")
+        img, z = ctx.saved_tensors
+        N, _, H, W = img.shape
+        dy = dy.to(torch.bfloat16).contiguous()
+        dw = torch.zeros(ctx.wshape, device=img.device, dtype=torch.float32)
+        L.check(lib.ast_stem_wgrad(dy.data_ptr(), z.data_ptr(), img.data_ptr(), dw.data_ptr(), N, H, W,
+                                   ctx.wshape[0], _st(img)), "ast_stem_wgrad")
+        return None, dw
+
+
+class _HeadFn(torch.autograd.Function):
+    """Decoder._ref_out + _img_out (models.py:300-314): NHWC bf16 -> NCHW fp32 image, with all gradients."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, clamp):
+        lib = L.load()
+        x = x if x.is_contiguous() else x.contiguous()
+        N, H, W, Cc = x.shape
+        co = w.shape[0]
+        out = torch.empty(N, co, H, W, device=x.device, dtype=torch.float32)
+        wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
+        L.check(lib.ast_head_conv(x.data_ptr(), wf.data_ptr(), bf.data_ptr(), out.data_ptr(), N, H, W, Cc, co,
+                                  int(clamp), _st(x)), "ast_head_conv")
+        ctx.save_for_backward(x, wf)
+        return out
+
+    @staticmethod
+    def backward(ctx, dY):
+        lib = L.load()
+        x, wf = ctx.saved_tensors
+        N, H, W, Cc = x.shape
+        co = wf.shape[0]
+        dY = dY.float().contiguous()
+        st = _st(x)
+        dw = torch.zeros_like(wf)
+        db = torch.zeros(co, device=x.device, dtype=torch.float32)
+        L.check(lib.ast_head_wgrad(dY.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), N, H, W, Cc, co, st),
+                "ast_head_wgrad")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _empty(N, H, W, Cc, x.device)
+            L.check(lib.ast_head_dgrad(dY.data_ptr(), wf.data_ptr(), dx.data_ptr(), N, H, W, Cc, co, st),
+                    "ast_head_dgrad")
+        return dx, dw, db, None
+
+
+def _wants_grad(module, *tensors):
+    return torch.is_grad_enabled() and (any(t.requires_grad for t in tensors)
+                                        or any(p.requires_grad for p in module.parameters()))
 
 
 # ---- modules ---------------------------------------------------------------------------------------
@@ -137,6 +484,7 @@ class DepthWiseConv(nn.Module):
         self.identity = stride == 1 and inp == oup and use_identity
         self.inp, self.oup, self.hidden, self.stride, self.k = inp, oup, hidden_dim, stride, kernel_size
         self.expand = expand_ratio != 1
+        self.use_norm = use_norm
         layers = []
 
         def bn(c):
@@ -212,30 +560,72 @@ class DepthWiseConv(nn.Module):
         self._prep = (ver, d)
         return d
 
+    # -- parameter plumbing for the training Function ------------------------------------------------
+    def _split(self):
+        mods = list(self._layers)
+        convs = [m for m in mods if isinstance(m, nn.Conv2d)]
+        bns = [m for m in mods if isinstance(m, nn.BatchNorm2d)]
+        se = next(m for m in mods if isinstance(m, SELayer))
+        return convs, bns, se
+
+    def _bns(self):
+        return self._split()[1]
+
+    def _param_names(self):
+        n = self.use_norm
+        names = (["w1"] + (["g1", "b1"] if n else [])) if self.expand else []
+        names += ["wd"] + (["g2", "b2"] if n else [])
+        names += ["se_w1", "se_b1", "se_w2", "se_b2", "w2"] + (["g3", "b3"] if n else [])
+        return names
+
+    def _param_list(self):
+        convs, bns, se = self._split()
+        out = []
+        bi = 0
+        if self.expand:
+            out.append(convs[0].weight)
+            if self.use_norm:
+                out += [bns[bi].weight, bns[bi].bias]; bi += 1
+        out.append(convs[-2].weight)
+        if self.use_norm:
+            out += [bns[bi].weight, bns[bi].bias]; bi += 1
+        out += [se.fc[0].weight, se.fc[0].bias, se.fc[2].weight, se.fc[2].bias, convs[-1].weight]
+        if self.use_norm:
+            out += [bns[bi].weight, bns[bi].bias]
+        return out
+
+    def _unpack(self, params):
+        return dict(zip(self._param_names(), params))
+
     def forward_nhwc(self, x, up2=False):
         """x: (N,H,W,inp) bf16 NHWC -> (N,Ho,Wo,oup) bf16 NHWC.  ``up2``: the block consumes the nearest
         x2 upsample of x (DecoderBlock._upsample_3 followed by _upsample_2, models.py:263-267)."""
         lib = L.load()
+        grad = _wants_grad(self, x)
+        if grad or (self.training and self.use_norm):
+            if grad and self.use_norm and not self.training:
+                raise L.AstError("eval-mode BatchNorm with gradients is not implemented: call .train()")
+            return _BlockFn.apply(x, self, up2, *self._param_list())
         d = self._prepared()
         N = x.shape[0]
         h = pw_conv(x, d["w1"], d["b1"], act=True, out_channels=self.hidden) if self.expand else x
-        y, pool = dw_conv(h, d["wd"], d["bd"], self.k, self.stride, up2=up2, act=True, want_pool=True)
+        if not self.expand and not h.is_contiguous():
+            h = h.contiguous()
+        y, pool = dw_conv(h, d["wd"], d["bd"], self.k, self.stride, up2=up2, act=1, want_pool=True)
         Ho, Wo = y.shape[1], y.shape[2]
         w1, b1, w2, b2 = d["se"]
-        scale = torch.empty(N, self.hidden, device=x.device, dtype=torch.float32)
-        L.check(lib.ast_se_fc(pool.data_ptr(), 1.0 / (Ho * Wo), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                              b2.data_ptr(), scale.data_ptr(), N, self.hidden, w1.shape[0], _st(x)), "ast_se_fc")
+        scale, _, _ = se_fc(pool, 1.0 / (Ho * Wo), w1, b1, w2, b2)
         w2s = torch.empty(N, self.oup, self.hidden, device=x.device, dtype=torch.bfloat16)
         L.check(lib.ast_scale_weights(d["w2"].data_ptr(), scale.data_ptr(), w2s.data_ptr(), N, self.oup,
                                       self.hidden, _st(x)), "ast_scale_weights")
         res = x if self.identity else None
-        return pw_conv(y, w2s, d["b2"], act=False, out_channels=self.oup, residual=res, per_sample=True)
+        return pw_conv(y, w2s, d["b2"], act=False, out_channels=self.oup, residual=res, per_sample=True,
+                       res_up2=bool(up2 and self.identity))
 
     def forward(self, x):
         """NCHW fp32 in / out like the reference module."""
         L.require_cuda(x)
-        _forward_only(self)
-        return nhwc_to_nchw(self.forward_nhwc(nchw_to_nhwc(x)))
+        return to_nchw(self.forward_nhwc(to_nhwc(x)))
 
 
 class Encoder(nn.Module):
@@ -257,9 +647,12 @@ class Encoder(nn.Module):
         N, _, H, W = x.shape
         stem = self.mob_net[0][0]
         cout = stem.out_channels
-        y = torch.empty(N, H, W, cout, device=x.device, dtype=torch.bfloat16)
-        L.check(lib.ast_stem_conv(x.data_ptr(), stem.weight.detach().float().contiguous().data_ptr(),
-                                  y.data_ptr(), N, H, W, cout, _st(x)), "ast_stem_conv")
+        if _wants_grad(self.mob_net[0], x):
+            y = _StemFn.apply(x, stem.weight)
+        else:
+            y = _empty(N, H, W, cout, x.device)
+            L.check(lib.ast_stem_conv(x.data_ptr(), stem.weight.detach().float().contiguous().data_ptr(),
+                                      y.data_ptr(), None, N, H, W, cout, _st(x)), "ast_stem_conv")
         outs = [y] if 0 in out_layers else []
         for i, layer in enumerate(self.mob_net):
             if i == 0:
@@ -271,9 +664,8 @@ class Encoder(nn.Module):
 
     def forward(self, x, out_layers=[], auto_enc=False):
         L.require_cuda(x)
-        _forward_only(self)
         r = self.forward_nhwc(x, tuple(out_layers), auto_enc)
-        return nhwc_to_nchw(r) if auto_enc else [nhwc_to_nchw(t) for t in r]
+        return to_nchw(r) if auto_enc else [to_nchw(t) for t in r]
 
 
 class DecoderBlock(nn.Module):
@@ -298,8 +690,7 @@ class DecoderBlock(nn.Module):
 
     def forward(self, x):
         L.require_cuda(x)
-        _forward_only(self)
-        return nhwc_to_nchw(self.forward_nhwc(nchw_to_nhwc(x)))
+        return to_nchw(self.forward_nhwc(to_nhwc(x)))
 
 
 class Decoder(nn.Module):
@@ -322,8 +713,13 @@ class Decoder(nn.Module):
         lib = L.load()
         for block in self._decoder_blocks:
             x = block.forward_nhwc(x)
+        if _wants_grad(self._img_out, x):
+            if self.exporting:
+                raise L.AstError("exporting=True (Hardtanh output) has no backward; train with exporting=False")
+            return _HeadFn.apply(x, self._img_out.weight, self._img_out.bias, False)
         N, H, W, Cc = x.shape
         co = self._img_out.out_channels
+        x = x if x.is_contiguous() else x.contiguous()
         out = torch.empty(N, co, H, W, device=x.device, dtype=torch.float32)
         L.check(lib.ast_head_conv(x.data_ptr(), self._img_out.weight.detach().float().contiguous().data_ptr(),
                                   self._img_out.bias.detach().float().contiguous().data_ptr(), out.data_ptr(),
@@ -332,8 +728,7 @@ class Decoder(nn.Module):
 
     def forward(self, x):
         L.require_cuda(x)
-        _forward_only(self)
-        return self.forward_nhwc(nchw_to_nhwc(x))
+        return self.forward_nhwc(to_nhwc(x))
 
 
 class AutoEncoder(nn.Module):
@@ -348,7 +743,6 @@ class AutoEncoder(nn.Module):
 
     def forward(self, x):
         L.require_cuda(x)
-        _forward_only(self)
         e = self.encoder.forward_nhwc(x, tuple(enc_out_layers))
         z = self.ada_out.forward_nhwc(torch.cat((e[0], e[1]), dim=3))     # models.py:332
         return self.decoder.forward_nhwc(z)

@@ -263,26 +263,35 @@ int ast_unpack_wgrad(const float* dwpk, float* w_grad, const void* dz_planar, fl
  *   w   : bf16 [Cout][Cin], or [N][Cout][Cin] when per_sample_w (SE scaling folded in)
  *   act : 0 none, 1 Hardswish;  residual (optional): bf16 [N*HW][ld_res];  out: bf16 [N*HW][ld_out]
  * Cin, Cout, ld_* multiples of 8. */
+/*   out_act (optional, training): `out` keeps the raw pre-activation and out_act [N*HW][ld_act] receives
+ *   Hardswish of the rounded value (both are needed by the backward pass); excludes residual.
+ *   res_up2_w > 0: the residual is the quarter-size tensor [N*HW/4][ld_res] read through a nearest x2
+ *   upsample (DecoderBlock._upsample_3 + identity of _upsample_2); res_up2_w = width of the output grid. */
 int ast_pw_conv(const void* x, int ld_in, const void* w, int per_sample_w, const float* bias, int act,
                 const void* residual, int ld_res, void* out, int ld_out, int N, int64_t HW, int Cin,
-                int Cout, void* stream);
+                int Cout, void* out_act, int ld_act, int res_up2_w, void* stream);
 
 /* Depthwise k x k (3 or 5), stride 1 or 2, reflect padding (k-1)/2, + bias + optional Hardswish.
  *   x : bf16 [N][H][W][C]; w : fp32 [k*k][C]; out : bf16 [N][Ho][Wo][C]
  *   pool (optional) : fp32 [N][C], receives the per-channel SUM of the output (SE squeeze)
- *   up2 : read x through a virtual nearest x2 upsample (conv input = 2H x 2W). */
+ *   up2 : read x through a virtual nearest x2 upsample (conv input = 2H x 2W).
+ *   act : 0 none, 1 store Hardswish(y), 2 (training) store raw y and pool Hardswish(y). */
 int ast_dw_conv(const void* x, const float* w, const float* bias, void* out, float* pool, int N, int C,
                 int H, int W, int k, int stride, int up2, int act, void* stream);
 
 /* SE excitation: scale[n][c] = clamp(W2 relu(W1 (pool[n]*inv_hw) + b1) + b2, 0, 1). */
+/* hid_out [N][S] / pre_out [N][C] (optional): post-ReLU hidden layer and pre-clamp output, for ast_se_bwd. */
 int ast_se_fc(const float* pool, float inv_hw, const float* w1, const float* b1, const float* w2,
-              const float* b2, float* scale, int N, int C, int S, void* stream);
+              const float* b2, float* scale, float* hid_out, float* pre_out, int N, int C, int S,
+              void* stream);
 
 /* out[n][co][ci] (bf16) = w[co][ci] * se[n][ci]  (se NULL: plain cast, N copies). */
 int ast_scale_weights(const float* w, const float* se, void* out, int N, int Cout, int Cin, void* stream);
 
 /* Stem: NCHW fp32 image -> conv3x3 (reflect pad, no bias) -> Hardswish -> NHWC bf16; Cout <= 32. */
-int ast_stem_conv(const float* img, const float* w, void* out, int N, int H, int W, int Cout, void* stream);
+/* out_raw (optional, training): the rounded pre-activation, NHWC bf16. */
+int ast_stem_conv(const float* img, const float* w, void* out, void* out_raw, int N, int H, int W, int Cout,
+                  void* stream);
 
 /* Image head: NHWC bf16 -> ReflectionPad2d(1) -> conv3x3 + bias -> NCHW fp32 (+ Hardtanh(0,1)). */
 int ast_head_conv(const void* x, const float* w, const float* bias, float* out, int N, int H, int W,
@@ -290,6 +299,73 @@ int ast_head_conv(const void* x, const float* w, const float* bias, float* out, 
 
 /* NHWC bf16 (row stride ld) -> NCHW fp32. */
 int ast_nhwc_to_nchw(const void* x, int ld, float* out, int N, int C, int64_t HW, void* stream);
+
+/* NCHW fp32 -> NHWC bf16 (row stride ld). */
+int ast_nchw_to_nhwc(const float* x, void* out, int ld, int N, int C, int64_t HW, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4t  Training mode of the MobileNet-style blocks (train_autoencoder.py:111-148): nn.BatchNorm2d with
+ * batch statistics (mobilenetv2.py:108,128,137,149), Hardswish / SELayer / residual passes and all
+ * backward kernels.  Tensors are NHWC bf16 [N*HW][ld]; statistics fp32, cross-CTA sums fp64.
+ * `stat` = float[4][C]: mean, invstd, scale = gamma*invstd, shift = beta - mean*scale.
+ * ------------------------------------------------------------------------------------- */
+
+/* sums[0][c] = sum x, sums[1][c] = sum x^2 over all N*HW rows. */
+int ast_bn_stats(const void* x, int ld, double* sums, int N, int C, int64_t HW, void* stream);
+/* sums -> stat; running_mean/var (nullable) updated like nn.BatchNorm2d (momentum, unbiased variance). */
+int ast_bn_finalize(const double* sums, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, float* stat, int C,
+                    void* stream);
+/* out = act(x*sc[c] + sh[c]) [* se[n][c]] [+ res]; pool[n][c] (optional) = sum over pixels of act(..)
+ * (before the se factor).  sc/sh null = identity; act 0 none, 1 Hardswish; out may be null (pool only). */
+int ast_affine_act(const void* x, int ld_x, const float* sc, const float* sh, int act, const float* se,
+                   const void* res, int ld_res, void* out, int ld_out, float* pool, int N, int C, int64_t HW,
+                   void* stream);
+/* Backward through u = Hardswish(z)*s, z = a*scale+shift: out[n][0..4][c] = sums over pixels of
+ * du*h, du*h', h', du*h'*ahat, h'*ahat (h' = dHardswish/dz, ahat = (a-mean)*invstd; stat null: identity). */
+int ast_dw_bwd_reduce(const void* du, const void* a, const float* stat, float* out, int N, int C, int64_t HW,
+                      void* stream);
+/* BatchNorm coefficients of the depthwise norm from those sums: dgamma, dbeta, coef[2][C] = (dbeta, dgamma)/count. */
+int ast_se_bn_combine(const float* T, const float* s, const float* g, float* dgamma, float* dbeta, float* coef,
+                      int N, int C, double count, void* stream);
+/* da = ((du*s[n][c] + g[n][c]) * h'(z) - coef0 - ahat*coef1) * scale   (stat null: da = (du*s+g)*h'(a)). */
+int ast_dw_bwd_apply(const void* du, const void* a, const float* s, const float* g, const float* stat,
+                     const float* coef, void* da, int N, int C, int64_t HW, void* stream);
+/* Generic BatchNorm backward: sums[0][c] = sum dy, sums[1][c] = sum dy*ahat;  finalize -> dgamma, dbeta,
+ * coef;  apply: da = (dy - coef0 - ahat*coef1) * scale. */
+int ast_bn_bwd_reduce(const void* dy, int ld_dy, const void* a, int ld_a, const float* stat, double* sums, int N,
+                      int C, int64_t HW, void* stream);
+int ast_bn_bwd_finalize(const double* sums, double count, float* dgamma, float* dbeta, float* coef, int C,
+                        void* stream);
+int ast_bn_bwd_apply(const void* dy, int ld_dy, const void* a, int ld_a, const float* stat, const float* coef,
+                     void* da, int N, int C, int64_t HW, void* stream);
+/* Depthwise conv data gradient (gather form, reflection and x2-upsample folded back):
+ *   dy [N][Ho][Wo][C] -> dx [N][H][W][C];  w fp32 [k*k][C];  a_pre (optional): dx *= Hardswish'(a_pre*scale+shift). */
+/*   dres (optional): residual-branch gradient [N][Ho][Wo][C] added to dx (summed over 2x2 when up2);
+ *   requires stride 1 (Ho x Wo == conv-input size). */
+int ast_dw_conv_dgrad(const void* dy, const float* w, const void* a_pre, const float* stat, const void* dres,
+                      void* dx, int N, int C, int H, int W, int k, int stride, int up2, void* stream);
+/* Depthwise conv weight gradient, accumulated (atomics) into dw fp32 (C,1,k,k); x = the conv's stored input. */
+int ast_dw_conv_wgrad(const void* dy, const void* x, float* dw, int N, int C, int H, int W, int k, int stride,
+                      int up2, void* stream);
+/* SELayer backward (mobilenetv2.py:73-81): ds [N][ds_stride] = gradient of the scale; outputs dpre, dhid
+ * (scratch, [N][C] / [N][S]), g[n][c] = gradient of the pooled mean / HW, and the four parameter gradients. */
+int ast_se_bwd(const float* ds, int ds_stride, const float* pre, const float* hid, const float* pool,
+               float inv_hw, const float* w1, const float* w2, float* dpre, float* dhid, float* g, float* dw1,
+               float* db1, float* dw2, float* db2, int N, int C, int S, void* stream);
+/* Pointwise conv weight gradient on tcgen05 (MN-major operands): out[i*si + j*sj] += sum_p a[p][i]*b[p][j]. */
+int ast_pw_wgrad(const void* a, int ld_a, int Ca, const void* b, int ld_b, int Cb, int64_t P, float* out,
+                 int64_t si, int64_t sj, void* stream);
+/* Stem (conv_3x3_bn) weight gradient: dw (16,3,3,3) += sum dy*Hardswish'(z) (x) img[reflected tap]. */
+int ast_stem_wgrad(const void* dy, const void* z, const float* img, float* dw, int N, int H, int W, int Cout,
+                   void* stream);
+/* Image head (_ref_out + _img_out): weight / bias gradient (accumulated) and data gradient (NHWC bf16). */
+int ast_head_wgrad(const float* dY, const void* x, float* dw, float* db, int N, int H, int W, int Cin, int Cout,
+                   void* stream);
+int ast_head_dgrad(const float* dY, const float* w, void* dx, int N, int H, int W, int Cin, int Cout,
+                   void* stream);
+/* fp32 [R][Cc] -> mode 0: bf16 [R][Cc]; 1: bf16 [Cc][R]; 2: fp32 [Cc][R]. */
+int ast_prep_weight(const float* w, void* out, int R, int Cc, int mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,461 @@
+"""MobileNet-style Encoder / Decoder / AutoEncoder (BASELINE config 3):
+every K4 kernel in isolation against the same op in torch fp32 on bf16-rounded operands, then whole
+blocks and the whole autoencoder (eval forward, train forward, one train_autoencoder.py step's
+gradients) against the CPU oracle and the golden vectors made from the genuine reference.
+
+Tolerances.  Activations and inter-layer gradients are stored in bf16 (8 mantissa bits): a single kernel
+agrees with fp32 arithmetic on the same rounded inputs to <= 1e-2 relative L2 (one rounding of the
+output, 2^-9 relative per element); chains of ~30 blocks are held to relative L2 <= 5e-2 / cosine
+>= 0.995 on features and gradients and PSNR >= 40 dB on images, the bar BASELINE.json states for bf16."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restate as R
+from oracle import restate_ae as A
+from tests.conftest import load_golden
+from tests.gpu_util import bf16r
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm().clamp_min(1e-30)).item()
+
+
+def cos(a, b):
+    return F.cosine_similarity(a.double().cpu().flatten(), b.double().cpu().flatten(), dim=0).item()
+
+
+def nhwc(x):
+    """(N,C,H,W) fp32 -> (N,H,W,C) bf16 cuda, contiguous."""
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def G(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# pointwise conv (tcgen05 GEMM), forward and the weight-gradient GEMM with MN-major operands
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 16, 16, 16, 96), (1, 12, 20, 96, 16), (2, 9, 7, 24, 144),
+                                   (1, 16, 16, 240, 40), (2, 8, 8, 256, 768), (2, 8, 8, 768, 128),
+                                   (3, 5, 5, 80, 320)])
+def test_pw_conv_forward(shape):
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    N, H, W, cin, cout = shape
+    g = G(sum(shape))
+    x = bf16r(torch.randn(N, cin, H, W, generator=g))
+    w = bf16r(torch.randn(cout, cin, generator=g) / cin ** 0.5)
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w.view(cout, cin, 1, 1), b)
+    out = MB.pw_conv(nhwc(x), w.to(torch.bfloat16).cuda(), b.cuda(), 0, cout)
+    assert rel(nchw(out), ref) < 5e-3
+    out = MB.pw_conv(nhwc(x), w.to(torch.bfloat16).cuda(), b.cuda(), 1, cout)
+    assert rel(nchw(out), F.hardswish(ref)) < 5e-3
+    raw, act = MB.pw_conv(nhwc(x), w.to(torch.bfloat16).cuda(), None, 1, cout, want_raw=True)
+    ref0 = F.conv2d(x, w.view(cout, cin, 1, 1))
+    assert rel(nchw(raw), ref0) < 5e-3
+    assert torch.equal(act.float().cpu(), bf16r(F.hardswish(raw.float().cpu())))
+
+
+def test_pw_conv_residual_strided_input_and_per_sample_weights():
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    N, H, W, cin, cout = 2, 8, 12, 128, 128
+    g = G(5)
+    wide = bf16r(torch.randn(N, 2 * cin, H, W, generator=g))
+    w = bf16r(torch.randn(N, cout, cin, generator=g) / cin ** 0.5)
+    res = bf16r(torch.randn(N, cout, H, W, generator=g))
+    xw = nhwc(wide)
+    x_view = xw[..., cin:]                      # channel slice: row stride 2*cin
+    ref = torch.stack([F.conv2d(wide[n:n + 1, cin:], w[n].view(cout, cin, 1, 1))[0] for n in range(N)]) + res
+    out = MB.pw_conv(x_view, w.to(torch.bfloat16).cuda(), None, 0, cout, residual=nhwc(res), per_sample=True)
+    assert rel(nchw(out), ref) < 5e-3
+    # residual read through a nearest x2 upsample
+    small = bf16r(torch.randn(N, cout, H // 2, W // 2, generator=g))
+    ref = F.conv2d(wide[:, :cin], w[0].view(cout, cin, 1, 1)) + F.interpolate(small, scale_factor=2, mode="nearest")
+    out = MB.pw_conv(xw[..., :cin], w[0].to(torch.bfloat16).cuda().contiguous(), None, 0, cout,
+                     residual=nhwc(small), res_up2=True)
+    assert rel(nchw(out), ref) < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 96, 16), (1, 12, 20, 16, 96), (2, 9, 7, 144, 24),
+                                   (1, 16, 16, 240, 40), (2, 8, 8, 768, 256), (2, 8, 8, 128, 768),
+                                   (4, 32, 32, 384, 128), (1, 3, 3, 320, 80)])
+def test_pw_wgrad_mn_major_gemm(shape):
+    """out[i][j] = sum_p a[p][i] b[p][j] on tcgen05 with both operands MN-major, vs fp32 matmul."""
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    N, H, W, ca, cb = shape
+    g = G(sum(shape) + 1)
+    a = bf16r(torch.randn(N, ca, H, W, generator=g))
+    b = bf16r(torch.randn(N, cb, H, W, generator=g))
+    ref = torch.einsum("nihw,njhw->ij", a.double(), b.double()).float()
+    out = torch.zeros(ca, cb, device="cuda")
+    MB._pw_wgrad(nhwc(a), nhwc(b), out, cb, 1)
+    assert rel(out, ref) < 1e-3
+    out_t = torch.zeros(cb, ca, device="cuda")
+    MB._pw_wgrad(nhwc(a), nhwc(b), out_t, 1, ca)
+    assert rel(out_t, ref.t()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# depthwise conv: forward (reflect, stride, virtual upsample, fused pool), data and weight gradients
+# ------------------------------------------------------------------------------------------------
+def _dw_ref(x, w, k, stride, up2):
+    if up2:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    p = (k - 1) // 2
+    return F.conv2d(F.pad(x, (p, p, p, p), mode="reflect"), w, stride=stride, groups=x.shape[1])
+
+
+@pytest.mark.parametrize("cfg", [(2, 16, 10, 12, 3, 1, False), (1, 96, 16, 16, 3, 2, False), (2, 144, 9, 11, 5, 2, False),
+                                 (1, 240, 8, 8, 5, 1, False), (2, 96, 6, 5, 3, 1, True), (1, 768, 4, 4, 3, 1, False),
+                                 (1, 40, 3, 3, 5, 1, False), (1, 24, 2, 2, 3, 1, False)])
+def test_dw_conv_forward_dgrad_wgrad(cfg):
+    from arbitrarystyletransfer_b200 import mobilenet as MB, _lib as L
+    N, C, H, W, k, stride, up2 = cfg
+    g = G(sum(int(v) for v in cfg))
+    x = bf16r(torch.randn(N, C, H, W, generator=g)).requires_grad_(True)
+    w = torch.randn(C, 1, k, k, generator=g).div_(k).requires_grad_(True)
+    y = _dw_ref(x, w, k, stride, up2)
+    dy = bf16r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    wd = MB.prep_weight(w.detach().cuda(), C, k * k, 2)
+    assert torch.equal(wd.cpu(), w.detach().view(C, k * k).t())
+    out, pool = MB.dw_conv(nhwc(x.detach()), wd, None, k, stride, up2=up2, act=0, want_pool=True)
+    assert rel(nchw(out), y.detach()) < 5e-3
+    torch.testing.assert_close(pool.cpu(), out.float().sum(dim=(1, 2)).cpu(), rtol=1e-4, atol=1e-3)
+    out1, pool1 = MB.dw_conv(nhwc(x.detach()), wd, None, k, stride, up2=up2, act=1, want_pool=True)
+    assert rel(nchw(out1), F.hardswish(y.detach())) < 6e-3
+    out2, pool2 = MB.dw_conv(nhwc(x.detach()), wd, None, k, stride, up2=up2, act=2, want_pool=True)
+    assert torch.equal(out2, out)
+    torch.testing.assert_close(pool2.cpu(), F.hardswish(out.float()).sum(dim=(1, 2)).cpu(), rtol=1e-4, atol=1e-3)
+    lib = L.load()
+    st = L.stream_ptr(out.device)
+    dyd = nhwc(dy)
+    dx = torch.empty(N, H, W, C, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.ast_dw_conv_dgrad(dyd.data_ptr(), wd.data_ptr(), None, None, None, dx.data_ptr(), N, C, H, W, k,
+                                  stride, int(up2), st))
+    assert rel(nchw(dx), x.grad) < 5e-3
+    dw = torch.zeros(C, 1, k, k, device="cuda")
+    L.check(lib.ast_dw_conv_wgrad(dyd.data_ptr(), nhwc(x.detach()).data_ptr(), dw.data_ptr(), N, C, H, W, k, stride,
+                                  int(up2), st))
+    assert rel(dw, w.grad) < 2e-3
+    if stride == 1:   # identity branch folded into the data gradient
+        dx2 = torch.empty_like(dx)
+        L.check(lib.ast_dw_conv_dgrad(dyd.data_ptr(), wd.data_ptr(), None, None, dyd.data_ptr(), dx2.data_ptr(), N, C,
+                                      H, W, k, stride, int(up2), st))
+        extra = F.avg_pool2d(dy, 2) * 4 if up2 else dy
+        assert rel(nchw(dx2), x.grad + extra) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm (batch statistics), Hardswish / SE passes and their backward kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4, 96, 16, 16), (2, 16, 9, 7), (3, 240, 5, 5)])
+def test_batchnorm_train_forward_backward(shape):
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    N, C, H, W = shape
+    g = G(sum(shape))
+    a = bf16r(torch.randn(N, C, H, W, generator=g) * 2 + torch.randn(1, C, 1, 1, generator=g)).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(C, generator=g))
+    bn_g = torch.nn.BatchNorm2d(C).cuda()
+    bn_g.load_state_dict(bn.state_dict())
+    y = bn(a)
+    dy = bf16r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    ad = nhwc(a.detach())
+    stat = MB._bn_train_forward(ad, bn_g)
+    yg, _ = MB.affine_act(ad, stat[2], stat[3], 0)
+    assert rel(nchw(yg), y.detach()) < 5e-3
+    torch.testing.assert_close(bn_g.running_mean.cpu(), bn.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bn_g.running_var.cpu(), bn.running_var, rtol=1e-4, atol=1e-5)
+    assert int(bn_g.num_batches_tracked) == 1
+    da, dgamma, dbeta = MB._bn_backward(nhwc(dy), ad, stat)
+    assert rel(nchw(da), a.grad) < 6e-3
+    assert rel(dgamma, bn.weight.grad) < 1e-3 and rel(dbeta, bn.bias.grad) < 1e-3
+
+
+@pytest.mark.parametrize("norm", [False, True])
+def test_se_hardswish_norm_backward_chain(norm):
+    """u = Hardswish(BN(a)) * SE(mean Hardswish(BN(a))): forward pieces and the fused backward
+    (dw_bwd_reduce -> se_bwd -> se_bn_combine -> dw_bwd_apply) vs torch autograd."""
+    from arbitrarystyletransfer_b200 import mobilenet as MB, _lib as L
+    N, C, H, W, S = 3, 96, 8, 8, 24
+    g = G(7 + norm)
+    a = bf16r(torch.randn(N, C, H, W, generator=g) * 2).requires_grad_(True)
+    w1 = (torch.randn(S, C, generator=g) * 0.3).requires_grad_(True)
+    b1 = (torch.randn(S, generator=g) * 0.1).requires_grad_(True)
+    w2 = (torch.randn(C, S, generator=g) * 0.3).requires_grad_(True)
+    b2 = (torch.rand(C, generator=g)).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(C, generator=g) * 0.5)
+    z = bn(a) if norm else a
+    h = F.hardswish(z)
+    pool = h.mean(dim=(2, 3))
+    s = F.hardtanh(F.linear(F.relu(F.linear(pool, w1, b1)), w2, b2), 0.0, 1.0)
+    u = h * s.view(N, C, 1, 1)
+    du = bf16r(torch.randn(u.shape, generator=g))
+    pool.retain_grad()
+    s.retain_grad()
+    u.backward(du)
+
+    lib = L.load()
+    ad = nhwc(a.detach())
+    st = L.stream_ptr(ad.device)
+    stat = None
+    if norm:
+        bn_g = torch.nn.BatchNorm2d(C).cuda()
+        bn_g.load_state_dict(bn.state_dict())
+        stat = MB._bn_train_forward(ad, bn_g)
+    sc, sh = (stat[2], stat[3]) if norm else (None, None)
+    _, pool_g = MB.affine_act(ad, sc, sh, 1, want_out=False, want_pool=True)
+    torch.testing.assert_close(pool_g.cpu() / (H * W), pool.detach(), rtol=2e-3, atol=2e-3)
+    cw = [t.detach().cuda().contiguous() for t in (w1, b1, w2, b2)]
+    s_g, hid, pre = MB.se_fc(pool_g, 1.0 / (H * W), *cw, save=True)
+    torch.testing.assert_close(s_g.cpu(), s.detach(), rtol=2e-3, atol=2e-3)
+    u_g, _ = MB.affine_act(ad, sc, sh, 1, se=s_g)
+    assert rel(nchw(u_g), u.detach()) < 6e-3
+    dud = nhwc(du)
+    T = torch.empty(N, 5, C, device="cuda")
+    L.check(lib.ast_dw_bwd_reduce(dud.data_ptr(), ad.data_ptr(), L.ptr(stat), T.data_ptr(), N, C, H * W, st))
+    dpre, dhid, gg = torch.empty(N, C, device="cuda"), torch.empty(N, S, device="cuda"), torch.empty(N, C, device="cuda")
+    gw1, gb1, gw2, gb2 = (torch.empty_like(t) for t in cw)
+    L.check(lib.ast_se_bwd(T.data_ptr(), 5 * C, pre.data_ptr(), hid.data_ptr(), pool_g.data_ptr(), 1.0 / (H * W),
+                           cw[0].data_ptr(), cw[2].data_ptr(), dpre.data_ptr(), dhid.data_ptr(), gg.data_ptr(),
+                           gw1.data_ptr(), gb1.data_ptr(), gw2.data_ptr(), gb2.data_ptr(), N, C, S, st))
+    assert rel(T[:, 0], s.grad) < 1e-3, rel(T[:, 0], s.grad)                 # d loss / d gate
+    assert rel(gg * (H * W), pool.grad) < 1e-3, rel(gg * (H * W), pool.grad)   # d loss / d pooled mean
+    for got, want in ((gw1, w1.grad), (gb1, b1.grad), (gw2, w2.grad), (gb2, b2.grad)):
+        assert rel(got, want) < 1e-3, rel(got, want)
+    coef = None
+    if norm:
+        coef = torch.empty(2, C, device="cuda")
+        dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        L.check(lib.ast_se_bn_combine(T.data_ptr(), s_g.data_ptr(), gg.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                      coef.data_ptr(), N, C, float(N * H * W), st))
+        assert rel(dg, bn.weight.grad) < 1e-2 and rel(db, bn.bias.grad) < 1e-2
+    da = torch.empty_like(ad)
+    L.check(lib.ast_dw_bwd_apply(dud.data_ptr(), ad.data_ptr(), s_g.data_ptr(), gg.data_ptr(), L.ptr(stat),
+                                 L.ptr(coef), da.data_ptr(), N, C, H * W, st))
+    assert rel(nchw(da), a.grad) < 1e-2, rel(nchw(da), a.grad)
+
+
+def test_stem_and_head_forward_backward():
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    g = G(11)
+    N, H, W = 2, 12, 10
+    img = torch.rand(N, 3, H, W, generator=g)
+    w = (torch.randn(16, 3, 3, 3, generator=g) * 0.4).requires_grad_(True)
+    y = F.hardswish(F.conv2d(F.pad(img, (1, 1, 1, 1), mode="reflect"), w))
+    dy = bf16r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    wg = w.detach().cuda().requires_grad_(True)
+    yg = MB._StemFn.apply(img.cuda(), wg)
+    assert rel(nchw(yg), y.detach()) < 5e-3
+    yg.backward(nhwc(dy))
+    assert rel(wg.grad, w.grad) < 1e-2
+    # head: ReflectionPad2d(1) + Conv2d(16, 3, 3) with bias
+    x = bf16r(torch.randn(N, 16, H, W, generator=g)).requires_grad_(True)
+    hw = (torch.randn(3, 16, 3, 3, generator=g) * 0.2).requires_grad_(True)
+    hb = torch.randn(3, generator=g).requires_grad_(True)
+    out = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), hw, hb)
+    dY = torch.randn(out.shape, generator=g)
+    out.backward(dY)
+    xg = nhwc(x.detach()).requires_grad_(True)
+    hwg, hbg = hw.detach().cuda().requires_grad_(True), hb.detach().cuda().requires_grad_(True)
+    og = MB._HeadFn.apply(xg, hwg, hbg, False)
+    assert rel(og, out.detach()) < 1e-4
+    og.backward(dY.cuda())
+    assert rel(hwg.grad, hw.grad) < 1e-4 and rel(hbg.grad, hb.grad) < 1e-4
+    assert rel(nchw(xg.grad), x.grad) < 5e-3
+    assert rel(MB.nhwc_to_nchw(MB.nchw_to_nhwc(out.detach().cuda())), bf16r(out.detach())) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# whole blocks against the oracle (CPU fp32 autograd of oracle/restate_ae.py::depthwise_block)
+# ------------------------------------------------------------------------------------------------
+BLOCKS = [  # inp, oup, stride, t, k, norm, identity, up2, H, W
+    (16, 16, 1, 6, 3, True, True, False, 16, 16),
+    (24, 40, 2, 6, 5, True, True, False, 12, 16),
+    (96, 96, 1, 3, 5, False, True, False, 8, 8),
+    (40, 24, 1, 6, 5, False, True, False, 10, 6),
+    (96, 96, 1, 1, 3, False, True, True, 6, 8),
+    (256, 128, 1, 3, 3, False, False, False, 4, 4),
+]
+
+
+def _block_state(blk, prefix="b"):
+    return {f"{prefix}.{k}": v.detach().cpu().clone() for k, v in blk.state_dict().items()}
+
+
+@pytest.mark.parametrize("cfg", BLOCKS)
+def test_block_train_forward_backward_vs_oracle(cfg):
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    inp, oup, stride, t, k, norm, ident, up2, H, W = cfg
+    torch.manual_seed(sum(int(v) for v in cfg))
+    blk = MB.DepthWiseConv(inp, oup, stride, t, kernel_size=k, use_norm=norm, use_identity=ident)
+    # Make the SE gate and the norms non-trivial (the N(0, 0.01) / zero-bias init leaves the gate ~0), but keep
+    # the gate's pre-activations strictly inside the ReLU / Hardtanh linear regions: a bf16-level perturbation
+    # of the pooled mean must not flip a mask, which would change the gradient of a whole sample by ~10 % and
+    # says nothing about kernel correctness (the masks themselves are tested on exact inputs above).
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.Linear):
+                m.weight.normal_(0, 0.05)
+                m.bias.uniform_(0.3, 0.7)
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.3)
+    sd = _block_state(blk)
+    P = A.clone_state(sd, requires_grad=True)
+    N = 3
+    x = bf16r(torch.randn(N, inp, H, W, generator=G(3))).requires_grad_(True)
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if up2 else x
+    ref = A.depthwise_block(P, "b", xin, inp, oup, stride, t, k, norm=norm, use_identity=ident, training=True)
+    dy = bf16r(torch.randn(ref.shape, generator=G(4)))
+    ref.backward(dy)
+
+    blk = blk.cuda().train()
+    xg = nhwc(x.detach()).requires_grad_(True)
+    out = blk.forward_nhwc(xg, up2=up2)
+    assert rel(nchw(out), ref.detach()) < 1.5e-2, rel(nchw(out), ref.detach())
+    out.backward(nhwc(dy))
+    assert rel(nchw(xg.grad), x.grad) < 3e-2, rel(nchw(xg.grad), x.grad)
+    # Hardswish' jumps by 1/2 at +-3; a pre-activation within bf16 rounding of a kink (a few elements per
+    # ten thousand) takes the other branch than the fp32 oracle and moves the BatchNorm gamma / beta gradient
+    # of ITS channel by ~20 % when only ~150 elements feed that channel, as in these small cases.  Those two
+    # get a wider relative-L2 bar; direction (cosine) is held tight for everything.
+    for name, p in blk.named_parameters():
+        want = P["b." + name].grad
+        r, c = rel(p.grad, want), cos(p.grad, want)
+        is_norm = p.dim() == 1 and ".fc." not in name
+        assert r < (1e-1 if is_norm else 4e-2) and c > (0.995 if is_norm else 0.999), (name, r, c)
+    if norm:   # running statistics updated exactly like nn.BatchNorm2d
+        for name, b in blk.named_buffers():
+            torch.testing.assert_close(b.cpu().float(), P["b." + name].float(), rtol=2e-2, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole autoencoder against the goldens made from the genuine reference
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def g():
+    return load_golden("autoencoder")
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture()
+def ae():
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    torch.manual_seed(2)
+    return MB.AutoEncoder().cuda()
+
+
+def test_autoencoder_eval_forward_vs_reference_golden(g, ae):
+    x = T(g["ae_x"]).cuda()
+    ae.eval()
+    with torch.no_grad():
+        recon = ae(x)
+        taps = ae.encoder(x, out_layers=[0, 2, 12, 14])
+        z = ae.encoder(x, auto_enc=True)
+    for i, t in zip((0, 2, 12, 14), taps):
+        assert rel(t, T(g[f"ae_eval_enc{i}"])) < 3e-2, (i, rel(t, T(g[f"ae_eval_enc{i}"])))
+    assert rel(z, T(g["ae_eval_autoenc"])) < 3e-2
+    ref = T(g["ae_eval_recon_fresh"])
+    assert rel(recon, ref) < 3e-2, rel(recon, ref)
+    assert R.psnr(recon.cpu(), ref) >= 40.0
+
+
+def test_autoencoder_train_step_vs_reference_golden(g, ae):
+    """One train_autoencoder.py:111-139 step: train-mode forward (batch statistics), loss, gradients of
+    every parameter (norms) and of the stored subset (full tensors), running statistics, and the eval
+    forward with the updated statistics."""
+    from arbitrarystyletransfer_b200 import models as M
+    from arbitrarystyletransfer_b200.losses import compute_content_loss
+    x = T(g["ae_x"]).cuda()
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    enc = M.PretrainedEncoder().cuda().eval()
+    with torch.no_grad():
+        for c, w, b in zip(enc._convs(), vw, vb):
+            c.weight.copy_(w)
+            c.bias.copy_(b)
+    for p in enc.parameters():
+        p.requires_grad_(False)
+    ae.train()
+    recon = ae(x)
+    assert rel(recon, T(g["ae_train_recon"])) < 4e-2, rel(recon, T(g["ae_train_recon"]))
+    recon_loss = compute_content_loss(recon, x)
+    with torch.no_grad():
+        cm = enc(x)
+    rm = enc(recon)
+    perp = None
+    for a, b in zip(rm, cm):
+        l = compute_content_loss(a, b.detach())
+        perp = l if perp is None else perp + l
+    loss = 100.0 * recon_loss + 0.01 * perp
+    want = g["ae_train_losses"]
+    assert abs(recon_loss.item() - want[1]) / want[1] < 2e-2
+    assert abs(perp.item() - want[2]) / want[2] < 5e-2
+    loss.backward()
+    named = dict(ae.named_parameters())
+    gkeys = list(g["ae_grad_keys"])
+    norms = np.array([named[k].grad.double().norm().item() for k in gkeys])
+    ratio = norms / np.maximum(g["ae_grad_norm"], 1e-12)
+    big = g["ae_grad_norm"] > 1e-4 * g["ae_grad_norm"].max()
+    assert np.all(np.abs(ratio[big] - 1) < 0.15), (np.array(gkeys)[big][np.abs(ratio[big] - 1) >= 0.15], ratio[big])
+    for k in A.GOLDEN_GRAD_KEYS:
+        want = T(g["ae_grad::" + k])
+        if want.norm() < 1e-4 * g["ae_grad_norm"].max():
+            continue
+        assert cos(named[k].grad, want) > 0.99, (k, cos(named[k].grad, want), rel(named[k].grad, want))
+    sd = ae.state_dict()
+    for k in A.GOLDEN_BUFFER_KEYS:
+        torch.testing.assert_close(sd[k].cpu().float(), T(g["ae_buf::" + k]).float(), rtol=3e-2, atol=3e-3)
+    ae.eval()
+    with torch.no_grad():
+        after = ae(x)
+    assert rel(after, T(g["ae_eval_recon_after_step"])) < 4e-2
+
+
+def test_autoencoder_config3_shape_properties(ae):
+    """BASELINE config 3 geometry (256x256) at a reduced batch: finite outputs, determinism, every
+    parameter receives a finite gradient, BatchNorm-normalised activations have the batch statistics they
+    must have, and a few Adam steps on one batch reduce the reconstruction loss."""
+    x = R.rand_image(4, 256, 301).cuda()
+    ae.train()
+    out1 = ae(x)
+    assert out1.shape == (4, 3, 256, 256) and torch.isfinite(out1).all()
+    loss = F.huber_loss(out1, x)
+    loss.backward()
+    for n, p in ae.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    opt = torch.optim.Adam(ae.parameters(), lr=2e-4, betas=(0.9, 0.99), eps=1e-7)
+    first = None
+    for _ in range(6):
+        opt.zero_grad()
+        l = F.huber_loss(ae(x), x)
+        l.backward()
+        torch.nn.utils.clip_grad_norm_(ae.parameters(), 10.0)
+        opt.step()
+        first = first if first is not None else l.item()
+    assert l.item() < first
+    ae.eval()
+    with torch.no_grad():
+        a, b = ae(x), ae(x)
+    assert torch.equal(a, b)
