@@ -1,0 +1,543 @@
+// K4d: shared-memory-tiled depthwise convolution kernels for stride 1 (the layers that carry the
+// traffic: every decoder block and most encoder blocks of models.py:140-320).  Forward, data gradient
+// and weight gradient of nn.Conv2d(C, C, k, 1, groups=C, padding_mode="reflect") on NHWC bf16.
+//
+// Why tiles: the direct kernels (mobile.cu / mobile_train.cu) issue k*k global loads with 64-bit index
+// arithmetic and a reflection per tap and ran 15-20x above the HBM floor.  Here a CTA stages the
+// (TH+k-1) x (TW+k-1) input patch of one channel block ONCE (reflection / zero fill / x2-upsample resolved
+// during staging) and each thread produces a strip of 8 consecutive outputs x 4 channels from shared
+// memory with packed FFMA2 (fma.rn.f32x2), fp32 accumulation.
+//
+// What bounds it (ncu, profiles/): a 5x5 depthwise conv does 25 FMA per 4 bytes of HBM traffic, which is
+// the FP32 roof (128 FMA/clk/SM) rather than the HBM roof, and every FMA operand comes through the
+// 128 B/clk shared-memory port: a strip of R outputs re-uses each LDS'ed input for up to k taps, so R = 8
+// and 4 channels per thread (32 accumulators, ~80 registers, 3 CTAs per SM) balance the LDS port, the FMA
+// pipe and the latency hiding.  The 3x3 layers get close to the HBM floor.
+//
+// Geometry is chosen on the host per channel count (pick_geom): hvn = 8-byte channel groups per CTA (a
+// divisor of C/4), workers = 256 / hvn thread groups, tile = TH x TW with TH * TW/8 a multiple of the
+// worker count so that every round of the strip loop is full.
+#include "common.cuh"
+
+namespace ast {
+namespace dwt {
+
+constexpr int kThreads = 256;
+constexpr int R = 8;   // outputs per strip
+constexpr int CH = 4;  // channels per thread (one 8-byte vector)
+
+__device__ __forceinline__ float hsw(float x) { return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f); }
+__device__ __forceinline__ float hsw_grad(float x) {   // ATen CPU convention, see mobile_train.cu
+  return x <= -3.f ? 0.f : (x < 3.f ? fmaf(x, 1.f / 3.f, 0.5f) : 1.f);
+}
+__device__ __forceinline__ int reflect_idx(int p, int X) {
+  p = p < 0 ? -p : p;
+  return p >= X ? 2 * X - 2 - p : p;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// 4 bf16 -> 2 float2 (channel pairs).  All FMAs are the packed FFMA2: on sm_100 the scalar 3-register FFMA
+// issues at half rate per SM sub-partition, FFMA2 restores the full FP32 rate.
+__device__ __forceinline__ void unpack2x2(uint2 u, float2 (&x)[2]) {
+  x[0] = make_float2(bf16lo(u.x), bf16hi(u.x));
+  x[1] = make_float2(bf16lo(u.y), bf16hi(u.y));
+}
+__device__ __forceinline__ void ld_w2x2(const float* p, float2 (&w)[2]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  w[0] = make_float2(a.x, a.y);
+  w[1] = make_float2(a.z, a.w);
+}
+__device__ __forceinline__ uint2 ldg_u2(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+// Row pitch (in 8-byte units) of a staged tile with `cols` pixels of hvn vectors: padded so that
+// pitch == hvn (mod 16).  Consecutive workers take consecutive ROWS of the same 8-pixel column group, so
+// the (worker, vector) pairs of a half warp fall on 16 consecutive 8-byte bank pairs: conflict free for
+// every hvn.
+__host__ __device__ __forceinline__ int row_pitch(int cols, int hvn) {
+  const int raw = cols * hvn;
+  return raw + (((hvn - raw) % 16) + 16) % 16;
+}
+
+struct Geom {
+  int hvn, workers, TH, TW, tiles_h, tiles_w, cblocks;
+};
+
+struct Params {
+  const __nv_bfloat16* in;     // forward: x [N][H][W][C];  dgrad: dy [N][H][W][C]
+  const float* w;              // fp32 [k*k][C]
+  const float* bias;           // forward only, nullable
+  __nv_bfloat16* out;          // [N][Hc][Wc][C]   (Hc x Wc = conv grid = 2H x 2W when up2)
+  float* pool;                 // forward only, nullable: [N][C] sums
+  const __nv_bfloat16* a_pre;  // dgrad only, nullable: multiply by Hardswish'(a_pre * sc + sh)
+  const float* stat;           // dgrad only, nullable: [4][C]
+  const __nv_bfloat16* dres;   // dgrad only, nullable: identity-branch gradient added
+  int C, H, W, Hc, Wc, up2, act;
+  Geom g;
+};
+
+// MODE 0: forward (reflect staging, bias / Hardswish / pool epilogue)
+// MODE 1: data gradient (zero-fill staging, flipped weights, reflection fold at the borders)
+template <int K, int MODE>
+__global__ void __launch_bounds__(kThreads, 3)
+dw_tiled_kernel(const Params p) {
+  extern __shared__ __align__(16) uint2 smem_u2[];
+  constexpr int PAD = (K - 1) / 2;
+  const Geom g = p.g;
+  const int PH = g.TH + K - 1, PW = g.TW + K - 1;
+  const int RP = row_pitch(PW, g.hvn);
+  uint2* patch = smem_u2;                                            // [PH] rows of RP: [PW][cvn] + pad
+  float* s_w = reinterpret_cast<float*>(patch + ((PH * RP + 1) & ~1));   // 16-byte aligned            // [K*K][hvn*4]
+  float* s_pool = s_w + K * K * g.hvn * CH;                          // [hvn*4]
+  const int CB = g.hvn * CH;
+  const int tile = blockIdx.x;
+  const int th = tile / g.tiles_w, tw = tile - th * g.tiles_w;
+  const int cb = blockIdx.y, n = blockIdx.z;
+  const int c0 = cb * CB;
+  const int oh0 = th * g.TH, ow0 = tw * g.TW;
+
+  // ---- stage weights (flipped for the data gradient) and the input patch ----
+  for (int i = threadIdx.x; i < K * K * CB; i += kThreads) {
+    const int t = i / CB, c = i - t * CB;
+    const int ts = MODE == 1 ? (K * K - 1 - t) : t;
+    s_w[i] = __ldg(p.w + (int64_t)ts * p.C + c0 + c);
+  }
+  if (MODE == 0 && p.pool && threadIdx.x < CB) s_pool[threadIdx.x] = 0.f;
+  {
+    const __nv_bfloat16* src = p.in + (int64_t)n * p.H * p.W * p.C + c0;
+    const int total = PH * PW * g.hvn;
+    for (int i = threadIdx.x; i < total; i += kThreads) {
+      const int v = i % g.hvn;
+      const int pix = i / g.hvn;
+      const int py = pix / PW, px = pix - py * PW;
+      int y = oh0 - PAD + py, x = ow0 - PAD + px;      // position on the conv grid (may be outside)
+      uint2 val = make_uint2(0u, 0u);
+      if (MODE == 0) {
+        // reflection; positions only needed by masked outputs are clamped into range
+        y = reflect_idx(clampi(y, -PAD, p.Hc - 1 + PAD), p.Hc);
+        x = reflect_idx(clampi(x, -PAD, p.Wc - 1 + PAD), p.Wc);
+        if (p.up2) { y >>= 1; x >>= 1; }
+        val = ldg_u2(src + ((int64_t)y * p.W + x) * p.C + v * CH);
+      } else if (y >= 0 && y < p.Hc && x >= 0 && x < p.Wc) {
+        val = ldg_u2(src + ((int64_t)y * p.W + x) * p.C + v * CH);
+      }
+      patch[py * RP + px * g.hvn + v] = val;
+    }
+  }
+  __syncthreads();
+
+  const int worker = threadIdx.x / g.hvn;
+  const int v = threadIdx.x - worker * g.hvn;
+  const int groups_w = g.TW / R;
+  const int items = g.TH * groups_w;
+  float psum[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) psum[j] = 0.f;
+
+  if (worker < g.workers) {
+    for (int item = worker; item < items; item += g.workers) {
+      const int cg = item / g.TH, r = item - cg * g.TH;   // rows fastest: see row_pitch()
+      const int oh = oh0 + r, owb = ow0 + cg * R;
+      if (oh >= p.Hc || owb >= p.Wc) continue;
+      float2 acc2[R][2];
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) { acc2[rr][0] = make_float2(0.f, 0.f); acc2[rr][1] = make_float2(0.f, 0.f); }
+
+      // Plain correlation from the staged patch.  For the data gradient this is exact everywhere except on
+      // the few border rows / columns that also receive reflected contributions; those pixels are
+      // recomputed by the border pass below.
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh) {
+        float2 wrow[K][2];
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) ld_w2x2(s_w + (kh * K + kw) * CB + v * CH, wrow[kw]);
+        const uint2* prow = patch + (r + kh) * RP + cg * R * g.hvn + v;
+#pragma unroll
+        for (int c = 0; c < R + K - 1; ++c) {
+          float2 xv[2];
+          unpack2x2(prow[c * g.hvn], xv);
+#pragma unroll
+          for (int kw = 0; kw < K; ++kw) {
+            const int rr = c - kw;
+            if (rr >= 0 && rr < R) {
+              acc2[rr][0] = __ffma2_rn(xv[0], wrow[kw][0], acc2[rr][0]);
+              acc2[rr][1] = __ffma2_rn(xv[1], wrow[kw][1], acc2[rr][1]);
+            }
+          }
+        }
+      }
+
+      // ---- epilogue ----
+      const int64_t obase = (((int64_t)n * p.Hc + oh) * p.Wc) * p.C + c0 + v * CH;
+      if (MODE == 0) {
+        float b[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) b[j] = p.bias ? __ldg(p.bias + c0 + v * CH + j) : 0.f;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          const int ow = owb + rr;
+          if (ow >= p.Wc) continue;
+          float o[CH] = {acc2[rr][0].x + b[0], acc2[rr][0].y + b[1], acc2[rr][1].x + b[2], acc2[rr][1].y + b[3]};
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) o[j] = hsw(o[j]);
+          }
+          const uint2 ov = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+          *reinterpret_cast<uint2*>(p.out + obase + (int64_t)ow * p.C) = ov;
+          if (p.pool) {
+            const float rv[CH] = {bf16lo(ov.x), bf16hi(ov.x), bf16lo(ov.y), bf16hi(ov.y)};
+#pragma unroll
+            for (int j = 0; j < CH; ++j) psum[j] += (p.act == 2) ? hsw(rv[j]) : rv[j];
+          }
+        }
+      } else {
+        float sc[CH], sh[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+        if (p.stat) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            sc[j] = __ldg(p.stat + 2 * p.C + c0 + v * CH + j);
+            sh[j] = __ldg(p.stat + 3 * p.C + c0 + v * CH + j);
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          const int ow = owb + rr;
+          if (ow >= p.Wc) continue;
+          float o[CH] = {acc2[rr][0].x, acc2[rr][0].y, acc2[rr][1].x, acc2[rr][1].y};
+          if (p.dres) {
+            const uint2 rv = ldg_u2(p.dres + obase + (int64_t)ow * p.C);
+            o[0] += bf16lo(rv.x); o[1] += bf16hi(rv.x); o[2] += bf16lo(rv.y); o[3] += bf16hi(rv.y);
+          }
+          if (p.a_pre) {
+            const uint2 av = ldg_u2(p.a_pre + obase + (int64_t)ow * p.C);
+            const float a4[CH] = {bf16lo(av.x), bf16hi(av.x), bf16lo(av.y), bf16hi(av.y)};
+#pragma unroll
+            for (int j = 0; j < CH; ++j) o[j] *= hsw_grad(fmaf(a4[j], sc[j], sh[j]));
+          }
+          *reinterpret_cast<uint2*>(p.out + obase + (int64_t)ow * p.C) =
+              make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+        }
+      }
+    }
+  }
+  if (MODE == 1) {
+    // ---- border pass of the data gradient (reflection fold) ----
+    // Position i collects the full correlation G[q] at every padded position q that reflects onto it:
+    // q = i, q = -i (1 <= i <= PAD), q = 2(X-1)-i (X-1-PAD <= i <= X-2).  Only tiles that touch such rows /
+    // columns do anything here; taps outside the staged patch are zeros by construction.
+    const bool touches = (oh0 <= PAD) || (oh0 + g.TH - 1 >= p.Hc - 1 - PAD) || (ow0 <= PAD) ||
+                         (ow0 + g.TW - 1 >= p.Wc - 1 - PAD);
+    if (touches) {
+      __syncthreads();   // the main loop's stores to these pixels are ordered before the rewrites
+      const int total = g.TH * g.TW * g.hvn;
+      for (int i = threadIdx.x; i < total; i += kThreads) {
+        const int vv = i % g.hvn;
+        const int pix = i / g.hvn;
+        const int r = pix / g.TW, c = pix - r * g.TW;
+        const int oh = oh0 + r, ow = ow0 + c;
+        if (oh >= p.Hc || ow >= p.Wc) continue;
+        const bool row_b = (oh >= 1 && oh <= PAD) || (oh >= p.Hc - 1 - PAD && oh <= p.Hc - 2);
+        const bool col_b = (ow >= 1 && ow <= PAD) || (ow >= p.Wc - 1 - PAD && ow <= p.Wc - 2);
+        if (!(row_b || col_b)) continue;
+        int qh[3], qw[3];
+        int nh = 0, nw = 0;
+        qh[nh++] = oh;
+        if (oh >= 1 && oh <= PAD) qh[nh++] = -oh;
+        if (oh <= p.Hc - 2 && 2 * (p.Hc - 1) - oh <= p.Hc - 1 + PAD) qh[nh++] = 2 * (p.Hc - 1) - oh;
+        qw[nw++] = ow;
+        if (ow >= 1 && ow <= PAD) qw[nw++] = -ow;
+        if (ow <= p.Wc - 2 && 2 * (p.Wc - 1) - ow <= p.Wc - 1 + PAD) qw[nw++] = 2 * (p.Wc - 1) - ow;
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+        for (int a = 0; a < nh; ++a)
+          for (int b = 0; b < nw; ++b)
+            for (int kh = 0; kh < K; ++kh) {
+              const int pr = qh[a] - oh0 + kh;
+              if (pr < 0 || pr >= PH) continue;
+              for (int kw = 0; kw < K; ++kw) {
+                const int pc = qw[b] - ow0 + kw;
+                if (pc < 0 || pc >= PW) continue;
+                float2 xv[2], wv[2];
+                unpack2x2(patch[pr * RP + pc * g.hvn + vv], xv);
+                ld_w2x2(s_w + (kh * K + kw) * CB + vv * CH, wv);
+                a0 = __ffma2_rn(xv[0], wv[0], a0);
+                a1 = __ffma2_rn(xv[1], wv[1], a1);
+              }
+            }
+        float o[CH] = {a0.x, a0.y, a1.x, a1.y};
+        const int64_t off = (((int64_t)n * p.Hc + oh) * p.Wc + ow) * p.C + c0 + vv * CH;
+        if (p.dres) {
+          const uint2 rv = ldg_u2(p.dres + off);
+          o[0] += bf16lo(rv.x); o[1] += bf16hi(rv.x); o[2] += bf16lo(rv.y); o[3] += bf16hi(rv.y);
+        }
+        if (p.a_pre) {
+          const uint2 av = ldg_u2(p.a_pre + off);
+          const float a4[CH] = {bf16lo(av.x), bf16hi(av.x), bf16lo(av.y), bf16hi(av.y)};
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const float scj = p.stat ? __ldg(p.stat + 2 * p.C + c0 + vv * CH + j) : 1.f;
+            const float shj = p.stat ? __ldg(p.stat + 3 * p.C + c0 + vv * CH + j) : 0.f;
+            o[j] *= hsw_grad(fmaf(a4[j], scj, shj));
+          }
+        }
+        *reinterpret_cast<uint2*>(p.out + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+      }
+    }
+  }
+  if (MODE == 0 && p.pool) {
+    if (worker < g.workers) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) atomicAdd(s_pool + v * CH + j, psum[j]);
+    }
+    __syncthreads();
+    if (threadIdx.x < CB) atomicAdd(p.pool + (int64_t)n * p.C + c0 + threadIdx.x, s_pool[threadIdx.x]);
+  }
+}
+
+// ---- weight gradient: dW[c][kh][kw] += sum_{n,o} dy[n,o,c] * x[n, R(o + k - pad), c] -------------------
+// A thread owns 2 channels (one 4-byte bf16 pair) and ALL k*k taps: k*k float2 accumulators live in registers
+// across a strided set of tiles, the dy tile and the reflected x patch are staged once per tile, and a strip
+// of 8 outputs re-uses every LDS'ed x value for up to k taps.  One shared-memory reduction over the workers
+// and one atomic per (channel, tap) per CTA at the end.  blockIdx.y = channel block.
+struct WParams {
+  const __nv_bfloat16* dy;   // [N][Hc][Wc][C]
+  const __nv_bfloat16* x;    // [N][H][W][C]
+  float* dw;                 // (C,1,K,K) fp32, accumulated
+  int N, C, H, W, Hc, Wc, up2;
+  Geom g;                    // hvn = channel PAIRS per CTA here
+};
+
+// pitch in 4-byte units, == pn (mod 32): rows-fastest workers give one bank per lane
+__host__ __device__ __forceinline__ int row_pitch32(int cols, int pn) {
+  const int raw = cols * pn;
+  return raw + (((pn - raw) % 32) + 32) % 32;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads, 3)
+dw_wgrad_tiled_kernel(const WParams p) {
+  extern __shared__ __align__(16) uint32_t smem_u1[];
+  constexpr int PAD = (K - 1) / 2;
+  const Geom g = p.g;
+  const int pn = g.hvn;
+  const int PH = g.TH + K - 1, PW = g.TW + K - 1;
+  const int RPX = row_pitch32(PW, pn), RPD = row_pitch32(g.TW, pn);
+  uint32_t* s_x = smem_u1;                 // [PH] rows of RPX
+  uint32_t* s_dy = s_x + PH * RPX;         // [TH] rows of RPD
+  const int CB = pn * 2;
+  const int c0 = blockIdx.y * CB;
+  const int worker = threadIdx.x / pn;
+  const int v = threadIdx.x - worker * pn;
+  const int groups_w = g.TW / R;
+  const int items = g.TH * groups_w;
+  const int tiles_per_img = g.tiles_h * g.tiles_w;
+  const int64_t total_tiles = (int64_t)p.N * tiles_per_img;
+  float2 acc[K][K];
+#pragma unroll
+  for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw) acc[kh][kw] = make_float2(0.f, 0.f);
+
+  for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = (int)(t / tiles_per_img);
+    const int tile = (int)(t - (int64_t)n * tiles_per_img);
+    const int th = tile / g.tiles_w, tw = tile - th * g.tiles_w;
+    const int oh0 = th * g.TH, ow0 = tw * g.TW;
+    __syncthreads();   // previous tile fully consumed
+    {
+      const __nv_bfloat16* src = p.x + (int64_t)n * p.H * p.W * p.C + c0;
+      const int total = PH * PW * pn;
+      for (int i = threadIdx.x; i < total; i += kThreads) {
+        const int vv = i % pn;
+        const int pix = i / pn;
+        const int py = pix / PW, px = pix - py * PW;
+        int y = reflect_idx(clampi(oh0 - PAD + py, -PAD, p.Hc - 1 + PAD), p.Hc);
+        int x = reflect_idx(clampi(ow0 - PAD + px, -PAD, p.Wc - 1 + PAD), p.Wc);
+        if (p.up2) { y >>= 1; x >>= 1; }
+        s_x[py * RPX + px * pn + vv] =
+            __ldg(reinterpret_cast<const uint32_t*>(src + ((int64_t)y * p.W + x) * p.C) + vv);
+      }
+      const __nv_bfloat16* dsrc = p.dy + (int64_t)n * p.Hc * p.Wc * p.C + c0;
+      const int dtotal = g.TH * g.TW * pn;
+      for (int i = threadIdx.x; i < dtotal; i += kThreads) {
+        const int vv = i % pn;
+        const int pix = i / pn;
+        const int py = pix / g.TW, px = pix - py * g.TW;
+        const int y = oh0 + py, x = ow0 + px;
+        uint32_t val = 0u;   // outputs outside the image contribute nothing
+        if (y < p.Hc && x < p.Wc)
+          val = __ldg(reinterpret_cast<const uint32_t*>(dsrc + ((int64_t)y * p.Wc + x) * p.C) + vv);
+        s_dy[py * RPD + px * pn + vv] = val;
+      }
+    }
+    __syncthreads();
+    if (worker < g.workers) {
+      for (int item = worker; item < items; item += g.workers) {
+        const int cg = item / g.TH, r = item - cg * g.TH;   // rows fastest
+        float2 d[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          const uint32_t u = s_dy[r * RPD + (cg * R + rr) * pn + v];
+          d[rr] = make_float2(bf16lo(u), bf16hi(u));
+        }
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+          const uint32_t* prow = s_x + (r + kh) * RPX + cg * R * pn + v;
+#pragma unroll
+          for (int c = 0; c < R + K - 1; ++c) {
+            const uint32_t u = prow[c * pn];
+            const float2 xv = make_float2(bf16lo(u), bf16hi(u));
+#pragma unroll
+            for (int kw = 0; kw < K; ++kw) {
+              const int rr = c - kw;
+              if (rr >= 0 && rr < R) acc[kh][kw] = __ffma2_rn(d[rr], xv, acc[kh][kw]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- reduce over the workers of each channel pair, then one atomic per (channel, tap) ----
+  __syncthreads();
+  float* s_red = reinterpret_cast<float*>(smem_u1);   // [workers][K*K][CB]
+  if (worker < g.workers) {
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) {
+        s_red[(worker * K * K + kh * K + kw) * CB + v * 2] = acc[kh][kw].x;
+        s_red[(worker * K * K + kh * K + kw) * CB + v * 2 + 1] = acc[kh][kw].y;
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K * CB; i += kThreads) {
+    float s = 0.f;
+    for (int wk = 0; wk < g.workers; ++wk) s += s_red[wk * K * K * CB + i];
+    const int tap = i / CB, c = i - tap * CB;
+    atomicAdd(p.dw + (int64_t)(c0 + c) * K * K + tap, s);
+  }
+}
+
+// Host: tile geometry for C channels (C % 8 == 0).
+static size_t fwd_smem(const Geom& g, int k) {
+  return (size_t)(g.TH + k - 1) * row_pitch(g.TW + k - 1, g.hvn) * 8 + 8 + (size_t)k * k * g.hvn * CH * 4 + g.hvn * CH * 4;
+}
+static size_t wgrad_smem(const Geom& g, int k) {   // g.hvn = channel pairs
+  const size_t tiles = ((size_t)(g.TH + k - 1) * row_pitch32(g.TW + k - 1, g.hvn) +
+                        (size_t)g.TH * row_pitch32(g.TW, g.hvn)) * 4;
+  const size_t red = (size_t)g.workers * k * k * g.hvn * 2 * 4;
+  return tiles > red ? tiles : red;
+}
+static bool pick_geom(int C, int Hc, int Wc, int k, size_t smem_limit, bool wgrad, Geom* out) {
+  const int hv = wgrad ? C / 2 : C / CH;          // wgrad: channel pairs; else 4-channel vectors
+  const int hvn_max = wgrad ? 64 : 24;
+  double best = -1.0;
+  Geom bg = {};
+  for (int hvn = 1; hvn <= hvn_max && hvn <= hv; ++hvn) {
+    if (hv % hvn) continue;
+    const int workers_max = kThreads / hvn;
+    for (int slack = 0; slack <= 2; ++slack) {
+      const int workers = workers_max - slack;
+      if (workers < 1) break;
+      for (int gw = 1; gw <= 6; ++gw) {            // strips per tile row: TW = 8 * gw
+        for (int TH = 4; TH <= 32; ++TH) {
+          const int items = TH * gw;
+          if (items % workers) continue;
+          if (items / workers > (wgrad ? 16 : 4)) continue;
+          Geom g = {};
+          g.hvn = hvn; g.workers = workers; g.TH = TH; g.TW = gw * R;
+          g.tiles_h = (Hc + TH - 1) / TH; g.tiles_w = (Wc + g.TW - 1) / g.TW; g.cblocks = hv / hvn;
+          if ((wgrad ? wgrad_smem(g, k) : fwd_smem(g, k)) > smem_limit) continue;
+          const double thread_eff = (double)(workers * hvn) / kThreads;
+          const double halo_eff = (double)(TH * g.TW) / ((TH + k - 1) * (g.TW + k - 1));
+          const double edge_eff = (double)Hc * Wc / ((double)g.tiles_h * TH * g.tiles_w * g.TW);
+          const int bytes = hvn * (wgrad ? 4 : 8);   // contiguous HBM bytes per pixel and CTA
+          const double wide = bytes >= 64 ? 1.0 : (bytes >= 32 ? 0.95 : (bytes >= 16 ? 0.85 : 0.7));
+          const double score = thread_eff * halo_eff * edge_eff * wide;
+          if (score > best) { best = score; bg = g; }
+        }
+      }
+    }
+  }
+  if (best < 0) return false;
+  *out = bg;
+  return true;
+}
+
+constexpr size_t kSmemLimit = 56 * 1024;   // 3-4 CTAs per SM
+
+template <int K, int MODE>
+static int launch_tiled(const Params& p, int N, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(dw_tiled_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemLimit);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  const Geom& g = p.g;
+  const size_t smem = fwd_smem(g, K);
+  dim3 grid(g.tiles_h * g.tiles_w, g.cblocks, N);
+  dw_tiled_kernel<K, MODE><<<grid, kThreads, smem, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int K>
+static int launch_wgrad(const WParams& p, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tiled_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemLimit);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  const Geom& g = p.g;
+  const size_t smem = wgrad_smem(g, K);
+  const int64_t total_tiles = (int64_t)p.N * g.tiles_h * g.tiles_w;
+  int64_t gx = (148 * 3 + g.cblocks - 1) / g.cblocks;
+  if (gx < 1) gx = 1;
+  if (gx > total_tiles) gx = total_tiles;
+  dim3 grid((unsigned)gx, g.cblocks, 1);
+  dw_wgrad_tiled_kernel<K><<<grid, kThreads, smem, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace dwt
+}  // namespace ast
+
+using namespace ast;
+
+// Entry points used by ast_dw_conv / ast_dw_conv_dgrad / ast_dw_conv_wgrad for stride 1.  Return
+// AST_E_SHAPE when no tiling fits so that the caller can fall back to the direct kernels.
+int dw_tiled_forward(const void* x, const float* w, const float* bias, void* out, float* pool, int N, int C, int H,
+                     int W, int k, int up2, int act, cudaStream_t s) {
+  dwt::Params p = {};
+  p.in = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.w = w; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.pool = pool;
+  p.C = C; p.H = H; p.W = W; p.Hc = up2 ? 2 * H : H; p.Wc = up2 ? 2 * W : W; p.up2 = up2; p.act = act;
+  if (N > 65535 || !dwt::pick_geom(C, p.Hc, p.Wc, k, dwt::kSmemLimit, false, &p.g)) return AST_E_SHAPE;
+  return k == 3 ? dwt::launch_tiled<3, 0>(p, N, s) : dwt::launch_tiled<5, 0>(p, N, s);
+}
+
+int dw_tiled_dgrad(const void* dy, const float* w, const void* a_pre, const float* stat, const void* dres, void* dx,
+                   int N, int C, int H, int W, int k, cudaStream_t s) {
+  dwt::Params p = {};
+  p.in = reinterpret_cast<const __nv_bfloat16*>(dy);
+  p.w = w; p.out = reinterpret_cast<__nv_bfloat16*>(dx);
+  p.a_pre = reinterpret_cast<const __nv_bfloat16*>(a_pre); p.stat = stat;
+  p.dres = reinterpret_cast<const __nv_bfloat16*>(dres);
+  p.C = C; p.H = H; p.W = W; p.Hc = H; p.Wc = W;
+  if (N > 65535 || H < 2 * k || W < 2 * k) return AST_E_SHAPE;   // tiny maps: the direct kernel handles them
+  if (!dwt::pick_geom(C, H, W, k, dwt::kSmemLimit, false, &p.g)) return AST_E_SHAPE;
+  return k == 3 ? dwt::launch_tiled<3, 1>(p, N, s) : dwt::launch_tiled<5, 1>(p, N, s);
+}
+
+int dw_tiled_wgrad(const void* dy, const void* x, float* dw, int N, int C, int H, int W, int k, int up2,
+                   cudaStream_t s) {
+  dwt::WParams p = {};
+  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.dw = dw; p.N = N; p.C = C; p.H = H; p.W = W; p.Hc = up2 ? 2 * H : H; p.Wc = up2 ? 2 * W : W; p.up2 = up2;
+  if (!dwt::pick_geom(C, p.Hc, p.Wc, k, dwt::kSmemLimit, true, &p.g)) return AST_E_SHAPE;
+  return k == 3 ? dwt::launch_wgrad<3>(p, s) : dwt::launch_wgrad<5>(p, s);
+}

@@ -4,6 +4,7 @@
 // Layout: plain NHWC bf16 [N][H][W][C] (no halo: these blocks use reflect padding of 1 or 2 and
 // stride 1 or 2, resolved by index arithmetic in the stencil).  All HBM-bound.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ast {
 
@@ -246,6 +247,18 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* 
 
 using namespace ast;
 
+// dw_tiled.cu: shared-memory-tiled stride-1 kernels (AST_E_SHAPE = no tiling fits, use the direct kernel)
+int dw_tiled_forward(const void* x, const float* w, const float* bias, void* out, float* pool, int N, int C, int H,
+                     int W, int k, int up2, int act, cudaStream_t s);
+bool dw_force_direct() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AST_DW_DIRECT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 extern "C" int ast_dw_conv(const void* x, const float* w, const float* bias, void* out, float* pool, int N,
                            int C, int H, int W, int k, int stride, int up2, int act, void* stream) {
   if (!x || !w || !out || N <= 0 || C <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
@@ -256,6 +269,10 @@ extern "C" int ast_dw_conv(const void* x, const float* w, const float* bias, voi
   if (N > 65535) return AST_E_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   if (pool) AST_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)N * C, s));
+  if (stride == 1 && !dw_force_direct()) {
+    const int r = dw_tiled_forward(x, w, bias, out, pool, N, C, H, W, k, up2, act, s);
+    if (r != AST_E_SHAPE) return r;
+  }
   int64_t chunks = (4 * 148 + N - 1) / N;
   const int64_t npix = (int64_t)Ho * Wo;
   if (chunks > npix / 8) chunks = npix / 8;

@@ -702,6 +702,12 @@ static bool chan_ok(int C) { return C > 0 && C % 8 == 0 && C / 8 <= kT; }
 
 using namespace ast;
 typedef __nv_bfloat16 bf16;
+// dw_tiled.cu
+int dw_tiled_dgrad(const void* dy, const float* w, const void* a_pre, const float* stat, const void* dres, void* dx,
+                   int N, int C, int H, int W, int k, cudaStream_t s);
+int dw_tiled_wgrad(const void* dy, const void* x, float* dw, int N, int C, int H, int W, int k, int up2,
+                   cudaStream_t s);
+bool dw_force_direct();
 #define BF(p) reinterpret_cast<bf16*>(p)
 #define CBF(p) reinterpret_cast<const bf16*>(p)
 
@@ -815,6 +821,10 @@ extern "C" int ast_dw_conv_dgrad(const void* dy, const float* w, const void* a_p
   if (Hin <= pad || Win <= pad) return AST_E_SHAPE;
   const int Ho = (Hin + 2 * pad - k) / stride + 1, Wo = (Win + 2 * pad - k) / stride + 1;
   if (dres && (stride != 1 || a_pre)) return AST_E_SHAPE;
+  if (stride == 1 && !up2 && !dw_force_direct()) {
+    const int r = dw_tiled_dgrad(dy, w, a_pre, stat, dres, dx, N, C, H, W, k, (cudaStream_t)stream);
+    if (r != AST_E_SHAPE) return r;
+  }
   dw_dgrad_kernel<<<dim3(pick_chunks(N, (int64_t)H * W, C), N), kT, 0, (cudaStream_t)stream>>>(
       CBF(dy), w, CBF(a_pre), stat, CBF(dres), BF(dx), C, H, W, Ho, Wo, k, stride, up2);
   AST_CHECK_LAUNCH();
@@ -828,6 +838,10 @@ extern "C" int ast_dw_conv_wgrad(const void* dy, const void* x, float* dw, int N
   const int Hin = up2 ? 2 * H : H, Win = up2 ? 2 * W : W, pad = (k - 1) / 2;
   if (Hin <= pad || Win <= pad) return AST_E_SHAPE;
   const int Ho = (Hin + 2 * pad - k) / stride + 1, Wo = (Win + 2 * pad - k) / stride + 1;
+  if (stride == 1 && !dw_force_direct()) {
+    const int r = dw_tiled_wgrad(dy, x, dw, N, C, H, W, k, up2, (cudaStream_t)stream);
+    if (r != AST_E_SHAPE) return r;
+  }
   const int groups = kT / (C / 8);
   const size_t smem = (size_t)groups * k * C * 4;   // <= 40 KB
   int chunks = pick_chunks(N, (int64_t)Ho * Wo, C);

@@ -116,7 +116,10 @@ def _dw_ref(x, w, k, stride, up2):
 
 @pytest.mark.parametrize("cfg", [(2, 16, 10, 12, 3, 1, False), (1, 96, 16, 16, 3, 2, False), (2, 144, 9, 11, 5, 2, False),
                                  (1, 240, 8, 8, 5, 1, False), (2, 96, 6, 5, 3, 1, True), (1, 768, 4, 4, 3, 1, False),
-                                 (1, 40, 3, 3, 5, 1, False), (1, 24, 2, 2, 3, 1, False)])
+                                 (1, 40, 3, 3, 5, 1, False), (1, 24, 2, 2, 3, 1, False),
+                                 # large enough for the shared-memory-tiled stride-1 kernels (ragged tiles, borders)
+                                 (2, 96, 20, 24, 5, 1, False), (1, 240, 33, 17, 5, 1, False), (2, 160, 16, 40, 3, 1, False),
+                                 (1, 40, 12, 10, 3, 1, True), (1, 144, 64, 64, 3, 1, False), (1, 80, 10, 50, 5, 1, False)])
 def test_dw_conv_forward_dgrad_wgrad(cfg):
     from arbitrarystyletransfer_b200 import mobilenet as MB, _lib as L
     N, C, H, W, k, stride, up2 = cfg
