@@ -56,6 +56,34 @@ __host__ __device__ __forceinline__ int row_pitch(int cols, int hvn) {
   return raw + (((hvn - raw) % 16) + 16) % 16;
 }
 
+// Cooperative staging of a rows x cols pixel tile, `cpp` 16-byte chunks per pixel, into shared-memory rows of
+// `pitch16` 16-byte units.  src(py, px) returns the pixel's channel-block address or nullptr for zero fill.
+// 16-byte global loads whatever the compute granularity, and the (row, pixel, chunk) cursor advances by
+// carries instead of divisions: staging used to cost more instructions than the convolution itself.
+template <class SrcFn>
+__device__ __forceinline__ void stage_tile(uint4* dst, int rows, int cols, int cpp, int pitch16, SrcFn src) {
+  const int per_row = cols * cpp;
+  int py = threadIdx.x / per_row;
+  int rem = threadIdx.x - py * per_row;
+  int px = rem / cpp;
+  int cc = rem - px * cpp;
+  const int dpy = kThreads / per_row;
+  const int drem = kThreads - dpy * per_row;
+  const int dpx = drem / cpp;
+  const int dcc = drem - dpx * cpp;
+  while (py < rows) {
+    const __nv_bfloat16* sp = src(py, px);
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (sp) val = __ldg(reinterpret_cast<const uint4*>(sp) + cc);
+    dst[py * pitch16 + px * cpp + cc] = val;
+    cc += dcc;
+    if (cc >= cpp) { cc -= cpp; ++px; }
+    px += dpx;
+    if (px >= cols) { px -= cols; ++py; }
+    py += dpy;
+  }
+}
+
 struct Geom {
   int hvn, workers, TH, TW, tiles_h, tiles_w, cblocks;
 };
@@ -102,24 +130,18 @@ dw_tiled_kernel(const Params p) {
   if (MODE == 0 && p.pool && threadIdx.x < CB) s_pool[threadIdx.x] = 0.f;
   {
     const __nv_bfloat16* src = p.in + (int64_t)n * p.H * p.W * p.C + c0;
-    const int total = PH * PW * g.hvn;
-    for (int i = threadIdx.x; i < total; i += kThreads) {
-      const int v = i % g.hvn;
-      const int pix = i / g.hvn;
-      const int py = pix / PW, px = pix - py * PW;
+    stage_tile(reinterpret_cast<uint4*>(patch), PH, PW, g.hvn / 2, RP / 2, [&](int py, int px) -> const __nv_bfloat16* {
       int y = oh0 - PAD + py, x = ow0 - PAD + px;      // position on the conv grid (may be outside)
-      uint2 val = make_uint2(0u, 0u);
       if (MODE == 0) {
         // reflection; positions only needed by masked outputs are clamped into range
         y = reflect_idx(clampi(y, -PAD, p.Hc - 1 + PAD), p.Hc);
         x = reflect_idx(clampi(x, -PAD, p.Wc - 1 + PAD), p.Wc);
         if (p.up2) { y >>= 1; x >>= 1; }
-        val = ldg_u2(src + ((int64_t)y * p.W + x) * p.C + v * CH);
-      } else if (y >= 0 && y < p.Hc && x >= 0 && x < p.Wc) {
-        val = ldg_u2(src + ((int64_t)y * p.W + x) * p.C + v * CH);
+      } else if (y < 0 || y >= p.Hc || x < 0 || x >= p.Wc) {
+        return nullptr;
       }
-      patch[py * RP + px * g.hvn + v] = val;
-    }
+      return src + ((int64_t)y * p.W + x) * p.C;
+    });
   }
   __syncthreads();
 
@@ -344,29 +366,18 @@ dw_wgrad_tiled_kernel(const WParams p) {
     __syncthreads();   // previous tile fully consumed
     {
       const __nv_bfloat16* src = p.x + (int64_t)n * p.H * p.W * p.C + c0;
-      const int total = PH * PW * pn;
-      for (int i = threadIdx.x; i < total; i += kThreads) {
-        const int vv = i % pn;
-        const int pix = i / pn;
-        const int py = pix / PW, px = pix - py * PW;
+      stage_tile(reinterpret_cast<uint4*>(s_x), PH, PW, pn / 4, RPX / 4, [&](int py, int px) -> const __nv_bfloat16* {
         int y = reflect_idx(clampi(oh0 - PAD + py, -PAD, p.Hc - 1 + PAD), p.Hc);
         int x = reflect_idx(clampi(ow0 - PAD + px, -PAD, p.Wc - 1 + PAD), p.Wc);
         if (p.up2) { y >>= 1; x >>= 1; }
-        s_x[py * RPX + px * pn + vv] =
-            __ldg(reinterpret_cast<const uint32_t*>(src + ((int64_t)y * p.W + x) * p.C) + vv);
-      }
+        return src + ((int64_t)y * p.W + x) * p.C;
+      });
       const __nv_bfloat16* dsrc = p.dy + (int64_t)n * p.Hc * p.Wc * p.C + c0;
-      const int dtotal = g.TH * g.TW * pn;
-      for (int i = threadIdx.x; i < dtotal; i += kThreads) {
-        const int vv = i % pn;
-        const int pix = i / pn;
-        const int py = pix / g.TW, px = pix - py * g.TW;
+      stage_tile(reinterpret_cast<uint4*>(s_dy), g.TH, g.TW, pn / 4, RPD / 4, [&](int py, int px) -> const __nv_bfloat16* {
         const int y = oh0 + py, x = ow0 + px;
-        uint32_t val = 0u;   // outputs outside the image contribute nothing
-        if (y < p.Hc && x < p.Wc)
-          val = __ldg(reinterpret_cast<const uint32_t*>(dsrc + ((int64_t)y * p.Wc + x) * p.C) + vv);
-        s_dy[py * RPD + px * pn + vv] = val;
-      }
+        if (y >= p.Hc || x >= p.Wc) return nullptr;   // outputs outside the image contribute nothing
+        return dsrc + ((int64_t)y * p.Wc + x) * p.C;
+      });
     }
     __syncthreads();
     if (worker < g.workers) {
@@ -433,6 +444,7 @@ static bool pick_geom(int C, int Hc, int Wc, int k, size_t smem_limit, bool wgra
   Geom bg = {};
   for (int hvn = 1; hvn <= hvn_max && hvn <= hv; ++hvn) {
     if (hv % hvn) continue;
+    if (hvn % (wgrad ? 4 : 2)) continue;          // whole 16-byte chunks per pixel (staging granularity)
     const int workers_max = kThreads / hvn;
     for (int slack = 0; slack <= 2; ++slack) {
       const int workers = workers_max - slack;

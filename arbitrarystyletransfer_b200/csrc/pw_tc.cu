@@ -11,17 +11,21 @@
 //    works: that is how torch.cat of the two encoder taps, models.py:332, costs nothing);
 // B: 3-D TMA box {64 ci, BN co, 1 (image or 0)}.  Channel counts that are not multiples of 64 / 16
 // rely on TMA zero fill for the K tail and on epilogue masking for the N tail.
-// These layers are HBM-bound (K <= 384), so the kernel is one tile per CTA, two CTAs per SM.
+// These layers are HBM-bound (K <= 768): one 128-pixel tile per CTA, shared memory and TMEM sized to the
+// layer's N block so that 2-6 CTAs share an SM, and eight epilogue warps per CTA (two per TMEM lane quarter,
+// splitting the columns) to keep enough stores in flight.
 #include "tc.cuh"
 
 namespace ast {
 namespace tc {
 
-constexpr int PW_THREADS = 192;            // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int PW_THREADS = 320;            // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
 constexpr int PW_A_BYTES = 128 * 64 * 2;   // 16 KB
-constexpr int PW_B_BYTES = 256 * 64 * 2;   // 32 KB (N up to 256)
 constexpr int PW_STAGES = 2;
-constexpr int PW_SMEM = PW_STAGES * (PW_A_BYTES + PW_B_BYTES) + (2 * PW_STAGES + 1) * 8 + 16 + 1024;
+__host__ __device__ constexpr int pw_stage_bytes(int BN) { return PW_A_BYTES + ((BN * 128 + 1023) / 1024) * 1024; }
+__host__ __device__ constexpr int pw_smem_bytes(int BN) {
+  return PW_STAGES * pw_stage_bytes(BN) + (2 * PW_STAGES + 1) * 8 + 16 + 1024;
+}
 
 struct PwParams {
   int N, Cin, Cout, BN, n_blocks, tiles_per_img, per_sample_w, act;
@@ -39,14 +43,15 @@ __device__ __forceinline__ float hardswish(float x) {
   return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);   // nn.Hardswish
 }
 
-__global__ void __launch_bounds__(PW_THREADS, 2)
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(PW_THREADS)
 pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const PwParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  constexpr int STAGE = PW_A_BYTES + PW_B_BYTES;
+  const int STAGE = pw_stage_bytes(p.BN);
   const uint32_t bars = base + PW_STAGES * STAGE;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (PW_STAGES + s); };
@@ -72,7 +77,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<256>(tmem_slot);
+    tmem_alloc<TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -116,8 +121,9 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (elect_one_sync()) umma_commit(done_bar);
     __syncwarp();
   } else {
-    // epilogue: warps 2..5 -> TMEM lane quarter (warp % 4)
+    // epilogue: warps 2..9 -> TMEM lane quarter (warp % 4); the two warps of a quarter alternate 16-column chunks
     const int e = warp & 3;
+    const int half = (warp - 2) >> 2;
     mbar_wait(done_bar, 0u);
     tc_fence_after();
     const int64_t pix = (int64_t)ti * 128 + e * 32 + lane;   // pixel inside the image
@@ -128,7 +134,9 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int h = (int)(pix / p.res_w), w = (int)(pix % p.res_w);
       rrow = (int64_t)n * (p.HW >> 2) + (int64_t)(h >> 1) * (p.res_w >> 1) + (w >> 1);
     }
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+    const bool wide_ok = ((p.ld_out & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) &&
+                         (!p.out_act || ((p.ld_act & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out_act) & 31) == 0));
+    for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
       uint32_t v[16];
       tmem_ld_32x16(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
@@ -152,6 +160,17 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       __nv_bfloat16* op = p.out + row * p.ld_out + co0;
+      if (wide_ok && valid == 16) {   // one 32-byte sector per lane per store
+        uint32_t pk[8], pa[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+          if (p.out_act) pa[j] = pack_bf16(hardswish(bf16lo(pk[j])), hardswish(bf16hi(pk[j])));
+        }
+        st_global_v8(op, pk);
+        if (p.out_act) st_global_v8(p.out_act + row * p.ld_act + co0, pa);
+        continue;
+      }
       for (int i = 0; i < valid; i += 8) {
         float o[8];
 #pragma unroll
@@ -172,7 +191,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -228,12 +247,20 @@ extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_samp
   }
   static bool attr_done = false;
   if (!attr_done) {
-    AST_CUDA(cudaFuncSetAttribute(pw_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM));
+    const int mx = pw_smem_bytes(256);
+    AST_CUDA(cudaFuncSetAttribute(pw_conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    AST_CUDA(cudaFuncSetAttribute(pw_conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    AST_CUDA(cudaFuncSetAttribute(pw_conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    AST_CUDA(cudaFuncSetAttribute(pw_conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_done = true;
   }
   const int64_t grid = (int64_t)N * p.tiles_per_img * n_blocks;
   if (grid >= 0x7fffffffLL) return AST_E_SHAPE;
-  pw_conv_tc_kernel<<<(unsigned)grid, PW_THREADS, PW_SMEM, s>>>(tmA, tmB, p);
+  const int smem = pw_smem_bytes(BN);
+  if (BN <= 32) pw_conv_tc_kernel<32><<<(unsigned)grid, PW_THREADS, smem, s>>>(tmA, tmB, p);
+  else if (BN <= 64) pw_conv_tc_kernel<64><<<(unsigned)grid, PW_THREADS, smem, s>>>(tmA, tmB, p);
+  else if (BN <= 128) pw_conv_tc_kernel<128><<<(unsigned)grid, PW_THREADS, smem, s>>>(tmA, tmB, p);
+  else pw_conv_tc_kernel<256><<<(unsigned)grid, PW_THREADS, smem, s>>>(tmA, tmB, p);
   AST_CHECK_LAUNCH();
   return 0;
 }
