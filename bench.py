@@ -40,6 +40,7 @@ def parse():
                     help="pairs timed on the CPU arm (0 = auto: about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the config-2 training-step timing")
+    ap.add_argument("--no-train-ae", action="store_true", help="skip the config-3 autoencoder training-step timing")
     ap.add_argument("--layers-out", default="", help="write the per-layer timing table (JSON) here")
     return ap.parse_args()
 
@@ -343,6 +344,162 @@ def time_train_step(dev, steps=8, warmup=3, batch=8, size=256):
                       "style (mean/std + Gram) loss, clip 2.0, Adam(2e-4), 1 GPU"}
 
 
+def ae_forward_bytes(size: int) -> float:
+    """Algorithmic HBM bytes of ONE image through AutoEncoder.forward (models.py:329-338) executed layer by
+    layer in bf16 NHWC: every kernel reads its input tensor once and writes its output once (pw expand:
+    inp -> hidden; depthwise: hidden -> hidden; pw linear: hidden -> oup, + the residual read), stem reads the
+    fp32 image, head writes the fp32 image.  SE vectors and weights are O(C) and ignored."""
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    hw = size * size
+    total = 3 * hw * 4 + 16 * hw * 2                     # stem
+    def block(inp, oup, stride, t, hw_in, up2=False, identity=True):
+        hidden = round(inp * t)
+        hw_conv = hw_in * 4 if up2 else hw_in
+        hw_out = hw_conv // (stride * stride)
+        b = 0
+        if t != 1:
+            b += (inp + hidden) * hw_in * 2              # pw expand
+        b += hidden * (hw_in if t == 1 else hw_conv) * 2 + hidden * hw_out * 2   # depthwise
+        b += (hidden + oup) * hw_out * 2                 # pw linear
+        if stride == 1 and inp == oup and identity:
+            b += oup * (hw_in if up2 else hw_out) * 2    # residual read
+        return b, hw_out
+    cur = hw
+    for (i, o, s_, k, t) in MB.enc_conv_shapes[1:-1]:
+        b, cur = block(i, o, s_, t, cur); total += b
+    b, cur = block(128, 128, 1, MB.EXPAND_RATIO, cur); total += b
+    b, cur = block(256, 128, 1, MB.EXPAND_RATIO, cur, identity=False); total += b
+    for idx, (i, o, s_, k, t) in enumerate(MB.decoder_conv_shapes[:-1]):
+        b, cur = block(i, o, s_, t, cur); total += b
+        if i != o and idx + 6 < len(MB.decoder_conv_shapes):
+            b, cur = block(o, o, 1, 1, cur, up2=True); total += b
+    total += 16 * cur * 2 + 3 * cur * 4                  # head
+    return float(total)
+
+
+def cpu_ae_train_sample(size=256, batch=2):
+    """CPU comparator for config 3 (kind "port"): one train_autoencoder.py:111-139 forward + backward of the
+    oracle restatement (oracle/restate_ae.py) on `batch` images, all host threads, fp32."""
+    from oracle import restate as R, restate_ae as A
+    torch.set_num_threads(os.cpu_count() or 1)
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    P = A.clone_state(A.make_ae_state(2), requires_grad=True)
+    x = torch.rand(batch, 3, size, size, generator=torch.Generator().manual_seed(301))
+    t0 = time.perf_counter()
+    loss, _, _, _ = A.ae_losses(P, x, vw, vb)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return {"value": batch / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one forward+backward of the oracle AutoEncoder step on {batch} images at {size}x{size} "
+                      f"(fp32, torch {torch.__version__} CPU), {dt:.1f} s"}
+
+
+def time_train_ae(dev, rank, world, steps=6, warmup=3, global_batch=32, size=256, cpu=False):
+    """BASELINE config 3: the train_autoencoder.py:111-148 step on the MobileNet-style AutoEncoder, global batch
+    32 at 256x256 sharded over `world` GPUs (DDP semantics: per-shard BatchNorm statistics), ONE NCCL all-reduce
+    of the flat 11.7 MB fp32 gradient bucket per step, clip 10, Adam(2e-4, (0.9, 0.99), 1e-7).  Loss =
+    100 * Huber(recon, x) + 0.01 * sum of Huber over the six default PretrainedEncoder taps."""
+    import torch.distributed as dist
+    from arbitrarystyletransfer_b200 import models as M, mobilenet as MB, losses as Ls, parallel as P
+    per = global_batch // world
+    g = torch.Generator().manual_seed(301)
+    x_all = torch.rand(global_batch, 3, size, size, generator=g)
+    x = x_all[rank * per:(rank + 1) * per].to(dev)
+
+    def build():
+        torch.manual_seed(0)
+        enc = M.PretrainedEncoder().to(dev).eval()
+        M.calibrate_encoder_bias(enc, n_convs=16)
+        for p in enc.parameters():
+            p.requires_grad_(False)
+        torch.manual_seed(2)
+        ae = MB.AutoEncoder().to(dev).train()
+        P.broadcast_parameters(list(ae.parameters()))
+        bucket = P.GradBucket(ae.parameters())
+        opt = torch.optim.Adam(ae.parameters(), lr=2e-4, betas=(0.9, 0.99), eps=1e-7, capturable=True)
+
+        def step(x):
+            bucket.zero()
+            recon = ae(x)
+            recon_loss = Ls.compute_content_loss(recon, x)
+            with torch.no_grad():
+                cm = enc(x)
+            rm = enc(recon)
+            perp = None
+            for a, b in zip(rm, cm):
+                l = Ls.compute_content_loss(a, b)
+                perp = l if perp is None else perp + l
+            loss = 100.0 * recon_loss + 0.01 * perp
+            loss.backward()
+            bucket.all_reduce_mean()
+            torch.nn.utils.clip_grad_norm_(ae.parameters(), 10.0)
+            opt.step()
+            return loss
+        return step, ae, bucket
+
+    def timeit(fn, n):
+        for _ in range(warmup):
+            loss = fn(x)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            loss = fn(x)
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, loss
+
+    mode, ms = None, None
+    if world == 1:
+        try:
+            from arbitrarystyletransfer_b200.graphs import GraphedStep
+            step, ae, bucket = build()
+            gstep = GraphedStep(step, [x.clone()])
+            ms, loss = timeit(gstep, steps)
+            mode = "whole step (fwd + bwd + clip + Adam) replayed from one CUDA graph"
+            del gstep, step
+        except Exception as e:
+            mode = "eager (graph capture failed: " + repr(e)[:160] + ")"
+            ms = None
+    step, ae, bucket = build()
+    ms_eager, loss_e = timeit(step, steps)
+    if ms is None:
+        ms, loss = ms_eager, loss_e
+        mode = mode or "eager, one NCCL all-reduce of the flat gradient bucket per step"
+    # eval-mode inference throughput of the same network (HBM-bound: reported against the HBM roof)
+    ae.eval()
+    with torch.no_grad():
+        ms_fwd, _ = timeit(ae, steps)
+    fwd_bytes = ae_forward_bytes(size) * per
+    pk = peaks()
+    cpu_res = None
+    if cpu and rank == 0:
+        try:
+            cpu_res = cpu_ae_train_sample(size)
+        except Exception as e:
+            cpu_res = {"error": repr(e)[:200]}
+    return {"cpu_baseline": cpu_res, "metric": "train_steps_per_s_256x256_b32_autoencoder", "value": 1e3 / ms, "unit": "steps/s",
+            "ms_per_step": ms, "img_per_s": global_batch * 1e3 / ms, "loss_finite": bool(torch.isfinite(loss).item()),
+            "mode": mode, "eager_steps_per_s": 1e3 / ms_eager, "global_batch": global_batch, "batch_per_gpu": per,
+            "scaling": "strong", "allreduce_bytes_per_step": bucket.numel * 4 if world > 1 else 0,
+            "eval_forward": {"img_per_s": world * per * 1e3 / ms_fwd, "ms": ms_fwd, "bound": "hbm",
+                             "algorithmic_bytes": fwd_bytes, "achieved_gbs": fwd_bytes / (ms_fwd * 1e-3) / 1e9,
+                             "peak_gbs": pk["hbm_gbs"], "frac": fwd_bytes / (ms_fwd * 1e-3) / 1e9 / pk["hbm_gbs"]},
+            "config": f"BASELINE config 3: MobileNet-style AutoEncoder training (train_autoencoder.py step), global "
+                      f"batch {global_batch} at {size}x{size} over {world} GPU(s), 100*Huber + 0.01*perceptual (6 VGG taps), "
+                      "clip 10, Adam(2e-4, b2 .99, eps 1e-7), per-shard BatchNorm statistics"}
+
+
 def _dec_flops(size):
     from arbitrarystyletransfer_b200.engine import DECODER_SPEC
     h, f = size // 8, 0.0
@@ -469,6 +626,17 @@ def run_native(args):
                 line["train"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(S, args.cpu_sample or 8)
+    if not args.no_train_ae:       # every rank takes part (NCCL all-reduce of the gradient bucket)
+        del eng, pipe
+        torch.cuda.empty_cache()
+        try:
+            tae = time_train_ae(dev, rank, world, cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as e:
+            if world > 1:
+                raise
+            tae = {"error": repr(e)[:300]}
+        line["train_ae"] = tae
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
