@@ -60,14 +60,15 @@ __device__ __forceinline__ void block_merge(Moments (&m)[MAXQ], int Q, Moments (
   }
 }
 
-// Streaming Welford over vectors [v0, v1) of a 16B-aligned row, strided by the block.
+// Streaming moments over vectors [v0, v1) of a 16B-aligned row, strided by the block (shifted sums, see
+// ShiftedLanes; the shift is the segment's first element, one broadcast load).
 template <bool BF16>
 __device__ __forceinline__ Moments stream_moments_vec(const void* row, int64_t v0, int64_t v1) {
   using VT = Vec16<BF16>;
   constexpr int V = VT::V;
-  constexpr int U = 4;
-  WelfordLanes<V> w;
-  w.init();
+  constexpr int U = 8;   // 8 x 16 B in flight per thread: the long-row paths are latency-bound otherwise
+  ShiftedLanes<V> w;
+  w.init(VT::load1(row, v0 * V));
   const uint4* p = reinterpret_cast<const uint4*>(row);
   int64_t i = v0 + threadIdx.x;
   for (; i + (U - 1) * kThreads < v1; i += U * kThreads) {
@@ -168,7 +169,7 @@ __device__ __forceinline__ void cta_merge_to(Moments m, Moments* s_warp, Moments
 }
 
 template <bool BF16, int R>
-__global__ void __launch_bounds__(kThreads, (R <= 4 ? 4 : 2)) adain_cached_kernel(const AdainArgs a) {
+__global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) adain_cached_kernel(const AdainArgs a) {
   using VT = Vec16<BF16>;
   constexpr int V = VT::V;
   cg::cluster_group cluster = cg::this_cluster();
@@ -194,9 +195,19 @@ __global__ void __launch_bounds__(kThreads, (R <= 4 ? 4 : 2)) adain_cached_kerne
     int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
     if (i < v1) cache[j] = ld_stream_u4(crow + i);
   }
-  {
-    WelfordLanes<V> w;
-    w.init();
+  uint4 scache[R <= 4 ? R : 1];
+  if (R <= 4 && Q == 2 && a.style_hw[0] == a.HW) {
+    const uint4* srow0 =
+        reinterpret_cast<const uint4*>(reinterpret_cast<const typename VT::elem*>(a.styles[0]) + row * a.HW);
+#pragma unroll
+    for (int j = 0; j < (R <= 4 ? R : 1); ++j) {
+      int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
+      if (i < v1) scache[j] = ld_stream_u4(srow0 + i);
+    }
+  }
+  if (!((R <= 4) && Q == 2 && a.style_hw[0] == a.HW && CS == 1)) {   // not the two-pass fast path below
+    ShiftedLanes<V> w;
+    w.init(VT::load1(a.content, row * a.HW));
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
@@ -208,7 +219,84 @@ __global__ void __launch_bounds__(kThreads, (R <= 4 ? 4 : 2)) adain_cached_kerne
     }
     cta_merge_to(w.fold(), s_warp, &s_q[0]);
   }
-  for (int k = 0; k + 1 < Q; ++k) {
+  // Common case (one style map of the content's size, both rows cached in <= 4 vectors per thread, no cluster
+  // split): the style row's loads were issued together with the content row's, and the statistics are a TRUE
+  // two-pass computation on the register-resident rows -- sum, then centred sum of squares -- with two cheap
+  // two-value block reductions.  The streaming Welford + Chan merges this replaces cost ~1150 instructions per
+  // thread and made the kernel issue-bound (ncu: issue slots 65 % busy at 62 % of the HBM copy peak).
+  const bool style_prefetched = (R <= 4) && Q == 2 && a.style_hw[0] == a.HW;
+  const bool two_pass = style_prefetched && CS == 1;
+  if (two_pass) {
+    __shared__ float s_sum[2][kWarps][2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
+      if (i < v1) {
+        float xs[V], ys[V];
+        VT::unpack(cache[j], xs);
+        VT::unpack(scache[j], ys);
+#pragma unroll
+        for (int e = 0; e < V; ++e) { t0 += xs[e]; t1 += ys[e]; }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      t0 += __shfl_xor_sync(0xffffffffu, t0, off);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+    }
+    if (lane == 0) { s_sum[0][wid][0] = t0; s_sum[0][wid][1] = t1; }
+    __syncthreads();
+    float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < kWarps; ++w2) { m0 += s_sum[0][w2][0]; m1 += s_sum[0][w2][1]; }
+    const float inv_n = 1.f / (float)a.HW;
+    m0 *= inv_n; m1 *= inv_n;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
+      if (i < v1) {
+        float xs[V], ys[V];
+        VT::unpack(cache[j], xs);
+        VT::unpack(scache[j], ys);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float dx = xs[e] - m0, dy = ys[e] - m1;
+          q0 = fmaf(dx, dx, q0);
+          q1 = fmaf(dy, dy, q1);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      q0 += __shfl_xor_sync(0xffffffffu, q0, off);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, off);
+    }
+    if (lane == 0) { s_sum[1][wid][0] = q0; s_sum[1][wid][1] = q1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float r0 = 0.f, r1 = 0.f;
+      for (int w2 = 0; w2 < kWarps; ++w2) { r0 += s_sum[1][w2][0]; r1 += s_sum[1][w2][1]; }
+      s_q[0] = Moments{(float)a.HW, m0, r0};
+      s_q[1] = Moments{(float)a.HW, m1, r1};
+    }
+  } else if (style_prefetched) {
+    ShiftedLanes<V> w;
+    w.init(VT::load1(a.styles[0], row * a.HW));
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
+      if (i < v1) {
+        float x[V];
+        VT::unpack(scache[j], x);
+        w.push(x);
+      }
+    }
+    cta_merge_to(w.fold(), s_warp, &s_q[1]);
+  }
+  for (int k = 0; k + 1 < Q && !style_prefetched; ++k) {
     const int64_t snvec = a.style_hw[k] / V;
     const int64_t sseg = (snvec + CS - 1) / CS;
     const int64_t s0 = rank * sseg;
