@@ -84,6 +84,41 @@ __device__ __forceinline__ void stage_tile(uint4* dst, int rows, int cols, int c
   }
 }
 
+// Same cursor, but the copy is an asynchronous 16-byte cp.async (zero fill when src returns nullptr): the
+// caller commits the group, computes on the other buffer and waits before use.
+__device__ __forceinline__ void cp_async16(uint4* dst, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class SrcFn>
+__device__ __forceinline__ void stage_tile_async(uint4* dst, int rows, int cols, int cpp, int pitch16,
+                                                 const void* safe, SrcFn src) {
+  const int per_row = cols * cpp;
+  int py = threadIdx.x / per_row;
+  int rem = threadIdx.x - py * per_row;
+  int px = rem / cpp;
+  int cc = rem - px * cpp;
+  const int dpy = kThreads / per_row;
+  const int drem = kThreads - dpy * per_row;
+  const int dpx = drem / cpp;
+  const int dcc = drem - dpx * cpp;
+  while (py < rows) {
+    const __nv_bfloat16* sp = src(py, px);
+    cp_async16(dst + py * pitch16 + px * cpp + cc, sp ? (const void*)(reinterpret_cast<const uint4*>(sp) + cc) : safe,
+               sp != nullptr);
+    cc += dcc;
+    if (cc >= cpp) { cc -= cpp; ++px; }
+    px += dpx;
+    if (px >= cols) { px -= cols; ++py; }
+    py += dpy;
+  }
+}
+
 struct Geom {
   int hvn, workers, TH, TW, tiles_h, tiles_w, cblocks;
 };
@@ -97,40 +132,45 @@ struct Params {
   const __nv_bfloat16* a_pre;  // dgrad only, nullable: multiply by Hardswish'(a_pre * sc + sh)
   const float* stat;           // dgrad only, nullable: [4][C]
   const __nv_bfloat16* dres;   // dgrad only, nullable: identity-branch gradient added
-  int C, H, W, Hc, Wc, up2, act;
+  int N, C, H, W, Hc, Wc, up2, act;
   Geom g;
 };
 
 // MODE 0: forward (reflect staging, bias / Hardswish / pool epilogue)
 // MODE 1: data gradient (zero-fill staging, flipped weights, reflection fold at the borders)
 template <int K, int MODE>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, (MODE == 0 ? 2 : 3))
 dw_tiled_kernel(const Params p) {
   extern __shared__ __align__(16) uint2 smem_u2[];
   constexpr int PAD = (K - 1) / 2;
   const Geom g = p.g;
   const int PH = g.TH + K - 1, PW = g.TW + K - 1;
   const int RP = row_pitch(PW, g.hvn);
-  uint2* patch = smem_u2;                                            // [PH] rows of RP: [PW][cvn] + pad
-  float* s_w = reinterpret_cast<float*>(patch + ((PH * RP + 1) & ~1));   // 16-byte aligned            // [K*K][hvn*4]
+  const int patch_elems = (PH * RP + 1) & ~1;                        // 16-byte aligned buffers
+  float* s_w = reinterpret_cast<float*>(smem_u2 + 2 * patch_elems);  // [K*K][hvn*4], after the two patch buffers
   float* s_pool = s_w + K * K * g.hvn * CH;                          // [hvn*4]
   const int CB = g.hvn * CH;
-  const int tile = blockIdx.x;
-  const int th = tile / g.tiles_w, tw = tile - th * g.tiles_w;
-  const int cb = blockIdx.y, n = blockIdx.z;
+  const int cb = blockIdx.y;
   const int c0 = cb * CB;
-  const int oh0 = th * g.TH, ow0 = tw * g.TW;
+  const int tiles_per_img = g.tiles_h * g.tiles_w;
+  const int64_t total_tiles = (int64_t)p.N * tiles_per_img;
 
-  // ---- stage weights (flipped for the data gradient) and the input patch ----
+  // ---- weights of this channel block, staged once (flipped for the data gradient) ----
   for (int i = threadIdx.x; i < K * K * CB; i += kThreads) {
     const int t = i / CB, c = i - t * CB;
     const int ts = MODE == 1 ? (K * K - 1 - t) : t;
     s_w[i] = __ldg(p.w + (int64_t)ts * p.C + c0 + c);
   }
-  if (MODE == 0 && p.pool && threadIdx.x < CB) s_pool[threadIdx.x] = 0.f;
-  {
+
+  // ---- persistent, double-buffered tile loop: the cp.async copies of tile i+1 fly while tile i is consumed ----
+  auto stage = [&](int64_t t, int b) {
+    const int n = (int)(t / tiles_per_img);
+    const int tile = (int)(t - (int64_t)n * tiles_per_img);
+    const int th = tile / g.tiles_w, tw = tile - th * g.tiles_w;
+    const int oh0 = th * g.TH, ow0 = tw * g.TW;
     const __nv_bfloat16* src = p.in + (int64_t)n * p.H * p.W * p.C + c0;
-    stage_tile(reinterpret_cast<uint4*>(patch), PH, PW, g.hvn / 2, RP / 2, [&](int py, int px) -> const __nv_bfloat16* {
+    stage_tile_async(reinterpret_cast<uint4*>(smem_u2 + b * patch_elems), PH, PW, g.hvn / 2, RP / 2, p.in,
+                     [&](int py, int px) -> const __nv_bfloat16* {
       int y = oh0 - PAD + py, x = ow0 - PAD + px;      // position on the conv grid (may be outside)
       if (MODE == 0) {
         // reflection; positions only needed by masked outputs are clamped into range
@@ -142,13 +182,31 @@ dw_tiled_kernel(const Params p) {
       }
       return src + ((int64_t)y * p.W + x) * p.C;
     });
-  }
-  __syncthreads();
+    cp_async_commit();
+  };
 
   const int worker = threadIdx.x / g.hvn;
   const int v = threadIdx.x - worker * g.hvn;
   const int groups_w = g.TW / R;
   const int items = g.TH * groups_w;
+
+  if ((int64_t)blockIdx.x < total_tiles) stage(blockIdx.x, 0);
+  int buf = 0;
+  for (int64_t tcur = blockIdx.x; tcur < total_tiles; tcur += gridDim.x, buf ^= 1) {
+  const int64_t tnext = tcur + gridDim.x;
+  if (tnext < total_tiles) {
+    stage(tnext, buf ^ 1);   // that buffer was released by the barrier that ended the previous iteration
+    cp_async_wait<1>();
+  } else {
+    cp_async_wait<0>();
+  }
+  if (MODE == 0 && p.pool && threadIdx.x < CB) s_pool[threadIdx.x] = 0.f;
+  __syncthreads();
+  const uint2* patch = smem_u2 + buf * patch_elems;
+  const int n = (int)(tcur / tiles_per_img);
+  const int tile = (int)(tcur - (int64_t)n * tiles_per_img);
+  const int th = tile / g.tiles_w, tw = tile - th * g.tiles_w;
+  const int oh0 = th * g.TH, ow0 = tw * g.TW;
   float psum[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) psum[j] = 0.f;
@@ -249,17 +307,35 @@ dw_tiled_kernel(const Params p) {
     const bool touches = (oh0 <= PAD) || (oh0 + g.TH - 1 >= p.Hc - 1 - PAD) || (ow0 <= PAD) ||
                          (ow0 + g.TW - 1 >= p.Wc - 1 - PAD);
     if (touches) {
-      __syncthreads();   // the main loop's stores to these pixels are ordered before the rewrites
-      const int total = g.TH * g.TW * g.hvn;
+      __syncthreads();   // the main loop's stores to these pixels are ordered before the updates below
+      // Border rows / columns of this tile as (start, count) bands in tile-local coordinates; the affected pixels
+      // are enumerated compactly (band rows x all columns, then the other rows x band columns) so that the
+      // work spreads over all 256 threads instead of the few whose strips happen to lie on the border.
+      const int ch = min(g.TH, p.Hc - oh0), cw = min(g.TW, p.Wc - ow0);
+      const int rt0 = max(1, oh0), rt1 = min(PAD, oh0 + ch - 1);
+      const int rb0 = max(p.Hc - 1 - PAD, oh0), rb1 = min(p.Hc - 2, oh0 + ch - 1);
+      const int nrt = max(0, rt1 - rt0 + 1), nrb = max(0, rb1 - rb0 + 1), nr = nrt + nrb;
+      const int ct0 = max(1, ow0), ct1 = min(PAD, ow0 + cw - 1);
+      const int cb0 = max(p.Wc - 1 - PAD, ow0), cb1 = min(p.Wc - 2, ow0 + cw - 1);
+      const int nct = max(0, ct1 - ct0 + 1), ncb = max(0, cb1 - cb0 + 1), nc = nct + ncb;
+      const int nA = nr * cw, nB = (ch - nr) * nc;
+      const int total = (nA + nB) * g.hvn;
       for (int i = threadIdx.x; i < total; i += kThreads) {
         const int vv = i % g.hvn;
-        const int pix = i / g.hvn;
-        const int r = pix / g.TW, c = pix - r * g.TW;
-        const int oh = oh0 + r, ow = ow0 + c;
-        if (oh >= p.Hc || ow >= p.Wc) continue;
-        const bool row_b = (oh >= 1 && oh <= PAD) || (oh >= p.Hc - 1 - PAD && oh <= p.Hc - 2);
-        const bool col_b = (ow >= 1 && ow <= PAD) || (ow >= p.Wc - 1 - PAD && ow <= p.Wc - 2);
-        if (!(row_b || col_b)) continue;
+        int e = i / g.hvn;
+        int oh, ow;
+        if (e < nA) {
+          const int ri = e / cw;
+          ow = ow0 + (e - ri * cw);
+          oh = ri < nrt ? rt0 + ri : rb0 + (ri - nrt);
+        } else {
+          e -= nA;
+          const int j = e / nc, ci = e - j * nc;
+          ow = ci < nct ? ct0 + ci : cb0 + (ci - nct);
+          oh = oh0 + j;                                   // j-th row of the tile that is NOT in a band
+          if (nrt && oh >= rt0) oh += nrt;
+          if (nrb && oh >= rb0) oh += nrb;
+        }
         int qh[3], qw[3];
         int nh = 0, nw = 0;
         qh[nh++] = oh;
@@ -268,9 +344,10 @@ dw_tiled_kernel(const Params p) {
         qw[nw++] = ow;
         if (ow >= 1 && ow <= PAD) qw[nw++] = -ow;
         if (ow <= p.Wc - 2 && 2 * (p.Wc - 1) - ow <= p.Wc - 1 + PAD) qw[nw++] = 2 * (p.Wc - 1) - ow;
+        // the direct term (q = position itself) was produced by the main loop: add only the reflected ones
         float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
         for (int a = 0; a < nh; ++a)
-          for (int b = 0; b < nw; ++b)
+          for (int b = (a == 0 ? 1 : 0); b < nw; ++b)
             for (int kh = 0; kh < K; ++kh) {
               const int pr = qh[a] - oh0 + kh;
               if (pr < 0 || pr >= PH) continue;
@@ -286,10 +363,6 @@ dw_tiled_kernel(const Params p) {
             }
         float o[CH] = {a0.x, a0.y, a1.x, a1.y};
         const int64_t off = (((int64_t)n * p.Hc + oh) * p.Wc + ow) * p.C + c0 + vv * CH;
-        if (p.dres) {
-          const uint2 rv = ldg_u2(p.dres + off);
-          o[0] += bf16lo(rv.x); o[1] += bf16hi(rv.x); o[2] += bf16lo(rv.y); o[3] += bf16hi(rv.y);
-        }
         if (p.a_pre) {
           const uint2 av = ldg_u2(p.a_pre + off);
           const float a4[CH] = {bf16lo(av.x), bf16hi(av.x), bf16lo(av.y), bf16hi(av.y)};
@@ -300,7 +373,10 @@ dw_tiled_kernel(const Params p) {
             o[j] *= hsw_grad(fmaf(a4[j], scj, shj));
           }
         }
-        *reinterpret_cast<uint2*>(p.out + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+        uint2* op = reinterpret_cast<uint2*>(p.out + off);
+        const uint2 prev = *op;
+        *op = make_uint2(pack_bf16(bf16lo(prev.x) + o[0], bf16hi(prev.x) + o[1]),
+                         pack_bf16(bf16lo(prev.y) + o[2], bf16hi(prev.y) + o[3]));
       }
     }
   }
@@ -309,9 +385,11 @@ dw_tiled_kernel(const Params p) {
 #pragma unroll
       for (int j = 0; j < CH; ++j) atomicAdd(s_pool + v * CH + j, psum[j]);
     }
-    __syncthreads();
-    if (threadIdx.x < CB) atomicAdd(p.pool + (int64_t)n * p.C + c0 + threadIdx.x, s_pool[threadIdx.x]);
   }
+  __syncthreads();   // tile consumed (its buffer may be refilled next iteration); s_pool complete
+  if (MODE == 0 && p.pool && threadIdx.x < CB)
+    atomicAdd(p.pool + (int64_t)n * p.C + c0 + threadIdx.x, s_pool[threadIdx.x]);
+  }  // tile loop
 }
 
 // ---- weight gradient: dW[c][kh][kw] += sum_{n,o} dy[n,o,c] * x[n, R(o + k - pad), c] -------------------
@@ -342,8 +420,7 @@ dw_wgrad_tiled_kernel(const WParams p) {
   const int pn = g.hvn;
   const int PH = g.TH + K - 1, PW = g.TW + K - 1;
   const int RPX = row_pitch32(PW, pn), RPD = row_pitch32(g.TW, pn);
-  uint32_t* s_x = smem_u1;                 // [PH] rows of RPX
-  uint32_t* s_dy = s_x + PH * RPX;         // [TH] rows of RPD
+  const int buf_words = PH * RPX + g.TH * RPD;   // one staged tile: x patch [PH] rows of RPX + dy [TH] rows of RPD
   const int CB = pn * 2;
   const int c0 = blockIdx.y * CB;
   const int worker = threadIdx.x / pn;
@@ -358,28 +435,42 @@ dw_wgrad_tiled_kernel(const WParams p) {
 #pragma unroll
     for (int kw = 0; kw < K; ++kw) acc[kh][kw] = make_float2(0.f, 0.f);
 
-  for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+  // Double-buffered tile loop: the cp.async copies of tile i+1 are in flight while tile i is consumed.
+  auto stage = [&](int64_t t, int b) {
     const int n = (int)(t / tiles_per_img);
     const int tile = (int)(t - (int64_t)n * tiles_per_img);
     const int th = tile / g.tiles_w, tw = tile - th * g.tiles_w;
     const int oh0 = th * g.TH, ow0 = tw * g.TW;
-    __syncthreads();   // previous tile fully consumed
-    {
-      const __nv_bfloat16* src = p.x + (int64_t)n * p.H * p.W * p.C + c0;
-      stage_tile(reinterpret_cast<uint4*>(s_x), PH, PW, pn / 4, RPX / 4, [&](int py, int px) -> const __nv_bfloat16* {
-        int y = reflect_idx(clampi(oh0 - PAD + py, -PAD, p.Hc - 1 + PAD), p.Hc);
-        int x = reflect_idx(clampi(ow0 - PAD + px, -PAD, p.Wc - 1 + PAD), p.Wc);
-        if (p.up2) { y >>= 1; x >>= 1; }
-        return src + ((int64_t)y * p.W + x) * p.C;
-      });
-      const __nv_bfloat16* dsrc = p.dy + (int64_t)n * p.Hc * p.Wc * p.C + c0;
-      stage_tile(reinterpret_cast<uint4*>(s_dy), g.TH, g.TW, pn / 4, RPD / 4, [&](int py, int px) -> const __nv_bfloat16* {
-        const int y = oh0 + py, x = ow0 + px;
-        if (y >= p.Hc || x >= p.Wc) return nullptr;   // outputs outside the image contribute nothing
-        return dsrc + ((int64_t)y * p.Wc + x) * p.C;
-      });
+    uint32_t* bx = smem_u1 + b * buf_words;
+    uint32_t* bd = bx + PH * RPX;
+    const __nv_bfloat16* src = p.x + (int64_t)n * p.H * p.W * p.C + c0;
+    stage_tile_async(reinterpret_cast<uint4*>(bx), PH, PW, pn / 4, RPX / 4, p.x, [&](int py, int px) -> const __nv_bfloat16* {
+      int y = reflect_idx(clampi(oh0 - PAD + py, -PAD, p.Hc - 1 + PAD), p.Hc);
+      int x = reflect_idx(clampi(ow0 - PAD + px, -PAD, p.Wc - 1 + PAD), p.Wc);
+      if (p.up2) { y >>= 1; x >>= 1; }
+      return src + ((int64_t)y * p.W + x) * p.C;
+    });
+    const __nv_bfloat16* dsrc = p.dy + (int64_t)n * p.Hc * p.Wc * p.C + c0;
+    stage_tile_async(reinterpret_cast<uint4*>(bd), g.TH, g.TW, pn / 4, RPD / 4, p.x, [&](int py, int px) -> const __nv_bfloat16* {
+      const int y = oh0 + py, x = ow0 + px;
+      if (y >= p.Hc || x >= p.Wc) return nullptr;   // outputs outside the image contribute nothing
+      return dsrc + ((int64_t)y * p.Wc + x) * p.C;
+    });
+    cp_async_commit();
+  };
+  if ((int64_t)blockIdx.x < total_tiles) stage(blockIdx.x, 0);
+  int buf = 0;
+  for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, buf ^= 1) {
+    const int64_t tn = t + gridDim.x;
+    if (tn < total_tiles) {
+      stage(tn, buf ^ 1);      // buffer buf^1 was released by the barrier that ended the previous iteration
+      cp_async_wait<1>();      // everything but the group just committed has landed
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const uint32_t* s_x = smem_u1 + buf * buf_words;
+    const uint32_t* s_dy = s_x + PH * RPX;
     if (worker < g.workers) {
       for (int item = worker; item < items; item += g.workers) {
         const int cg = item / g.TH, r = item - cg * g.TH;   // rows fastest
@@ -405,6 +496,7 @@ dw_wgrad_tiled_kernel(const WParams p) {
         }
       }
     }
+    __syncthreads();   // tile consumed: its buffer may be refilled by the next iteration's prefetch
   }
   // ---- reduce over the workers of each channel pair, then one atomic per (channel, tap) ----
   __syncthreads();
@@ -429,11 +521,11 @@ dw_wgrad_tiled_kernel(const WParams p) {
 
 // Host: tile geometry for C channels (C % 8 == 0).
 static size_t fwd_smem(const Geom& g, int k) {
-  return (size_t)(g.TH + k - 1) * row_pitch(g.TW + k - 1, g.hvn) * 8 + 8 + (size_t)k * k * g.hvn * CH * 4 + g.hvn * CH * 4;
+  return 2 * ((size_t)(g.TH + k - 1) * row_pitch(g.TW + k - 1, g.hvn) * 8 + 8) + (size_t)k * k * g.hvn * CH * 4 + g.hvn * CH * 4;
 }
 static size_t wgrad_smem(const Geom& g, int k) {   // g.hvn = channel pairs
-  const size_t tiles = ((size_t)(g.TH + k - 1) * row_pitch32(g.TW + k - 1, g.hvn) +
-                        (size_t)g.TH * row_pitch32(g.TW, g.hvn)) * 4;
+  const size_t tiles = 2 * ((size_t)(g.TH + k - 1) * row_pitch32(g.TW + k - 1, g.hvn) +
+                            (size_t)g.TH * row_pitch32(g.TW, g.hvn)) * 4;   // double buffered
   const size_t red = (size_t)g.workers * k * k * g.hvn * 2 * 4;
   return tiles > red ? tiles : red;
 }
@@ -474,20 +566,25 @@ static bool pick_geom(int C, int Hc, int Wc, int k, size_t smem_limit, bool wgra
   return true;
 }
 
-constexpr size_t kSmemLimit = 56 * 1024;   // 3-4 CTAs per SM
+constexpr size_t kSmemLimit = 72 * 1024;      // data / weight gradient: 3 CTAs per SM, two patch buffers each
+constexpr size_t kSmemLimitFwd = 100 * 1024;  // forward (heavier epilogue, 128 registers): 2 CTAs per SM, larger tiles
 
 template <int K, int MODE>
 static int launch_tiled(const Params& p, int N, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(dw_tiled_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemLimit);
+                                         (int)kSmemLimitFwd);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
   const Geom& g = p.g;
   const size_t smem = fwd_smem(g, K);
-  dim3 grid(g.tiles_h * g.tiles_w, g.cblocks, N);
+  const int64_t total_tiles = (int64_t)N * g.tiles_h * g.tiles_w;
+  int64_t gx = (148 * (MODE == 0 ? 2 : 3)) / g.cblocks;   // never more CTAs than fit at once: a partial second wave doubles the time
+  if (gx < 1) gx = 1;
+  if (gx > total_tiles) gx = total_tiles;
+  dim3 grid((unsigned)gx, g.cblocks, 1);
   dw_tiled_kernel<K, MODE><<<grid, kThreads, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -505,7 +602,8 @@ static int launch_wgrad(const WParams& p, cudaStream_t s) {
   const Geom& g = p.g;
   const size_t smem = wgrad_smem(g, K);
   const int64_t total_tiles = (int64_t)p.N * g.tiles_h * g.tiles_w;
-  int64_t gx = (148 * 3 + g.cblocks - 1) / g.cblocks;
+  int64_t gx = (148 * 3) / g.cblocks;   // never more CTAs than fit at once: a partial second wave doubles the time
+  if (gx < 1) gx = 1;
   if (gx < 1) gx = 1;
   if (gx > total_tiles) gx = total_tiles;
   dim3 grid((unsigned)gx, g.cblocks, 1);
@@ -526,8 +624,8 @@ int dw_tiled_forward(const void* x, const float* w, const float* bias, void* out
   dwt::Params p = {};
   p.in = reinterpret_cast<const __nv_bfloat16*>(x);
   p.w = w; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.pool = pool;
-  p.C = C; p.H = H; p.W = W; p.Hc = up2 ? 2 * H : H; p.Wc = up2 ? 2 * W : W; p.up2 = up2; p.act = act;
-  if (N > 65535 || !dwt::pick_geom(C, p.Hc, p.Wc, k, dwt::kSmemLimit, false, &p.g)) return AST_E_SHAPE;
+  p.N = N; p.C = C; p.H = H; p.W = W; p.Hc = up2 ? 2 * H : H; p.Wc = up2 ? 2 * W : W; p.up2 = up2; p.act = act;
+  if (N > 65535 || !dwt::pick_geom(C, p.Hc, p.Wc, k, dwt::kSmemLimitFwd, false, &p.g)) return AST_E_SHAPE;
   return k == 3 ? dwt::launch_tiled<3, 0>(p, N, s) : dwt::launch_tiled<5, 0>(p, N, s);
 }
 
@@ -538,7 +636,7 @@ int dw_tiled_dgrad(const void* dy, const float* w, const void* a_pre, const floa
   p.w = w; p.out = reinterpret_cast<__nv_bfloat16*>(dx);
   p.a_pre = reinterpret_cast<const __nv_bfloat16*>(a_pre); p.stat = stat;
   p.dres = reinterpret_cast<const __nv_bfloat16*>(dres);
-  p.C = C; p.H = H; p.W = W; p.Hc = H; p.Wc = W;
+  p.N = N; p.C = C; p.H = H; p.W = W; p.Hc = H; p.Wc = W;
   if (N > 65535 || H < 2 * k || W < 2 * k) return AST_E_SHAPE;   // tiny maps: the direct kernel handles them
   if (!dwt::pick_geom(C, H, W, k, dwt::kSmemLimit, false, &p.g)) return AST_E_SHAPE;
   return k == 3 ? dwt::launch_tiled<3, 1>(p, N, s) : dwt::launch_tiled<5, 1>(p, N, s);

@@ -287,7 +287,7 @@ def time_train_step(dev, steps=8, warmup=3, batch=8, size=256):
         M.calibrate_encoder_bias(enc)
         torch.manual_seed(1)
         dec = M.ClassicDecoder().to(dev)
-        opt = torch.optim.Adam(dec.parameters(), lr=2e-4, betas=(0.9, 0.999), eps=1e-5, capturable=True)
+        opt = torch.optim.Adam(dec.parameters(), lr=2e-4, betas=(0.9, 0.999), eps=1e-5, capturable=True, fused=True)
         adain = M.AdaIN()
 
         def step(c, s):
@@ -417,7 +417,7 @@ def time_train_ae(dev, rank, world, steps=6, warmup=3, global_batch=32, size=256
         ae = MB.AutoEncoder().to(dev).train()
         P.broadcast_parameters(list(ae.parameters()))
         bucket = P.GradBucket(ae.parameters())
-        opt = torch.optim.Adam(ae.parameters(), lr=2e-4, betas=(0.9, 0.99), eps=1e-7, capturable=True)
+        opt = torch.optim.Adam(ae.parameters(), lr=2e-4, betas=(0.9, 0.99), eps=1e-7, capturable=True, fused=True)
 
         def step(x):
             bucket.zero()

@@ -25,7 +25,7 @@ def build():
         p.requires_grad_(False)
     torch.manual_seed(2)
     ae = MB.AutoEncoder().to(dev).train()
-    opt = torch.optim.Adam(ae.parameters(), lr=2e-4, betas=(0.9, 0.99), eps=1e-7, capturable=True)
+    opt = torch.optim.Adam(ae.parameters(), lr=2e-4, betas=(0.9, 0.99), eps=1e-7, capturable=True, fused=True)
 
     def step(x):
         recon = ae(x)
