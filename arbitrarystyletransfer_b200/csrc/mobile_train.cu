@@ -166,44 +166,58 @@ affine_act_kernel(const __nv_bfloat16* __restrict__ x, int ld_x, const float* __
 //   T0 = sum du * h          (-> gradient of the SE scale)            h = Hardswish(z)
 //   T1 = sum du * h'(z)      T2 = sum h'(z)      T3 = sum du * h'(z) * ahat      T4 = sum h'(z) * ahat
 // T1..T4 feed the BatchNorm backward (only when mean != null); out = [N][5][C].
+template <bool NORM>
 __global__ void __launch_bounds__(kT)
 dw_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ a,
-                     const float* __restrict__ stat /*[4][C] or null*/, float* __restrict__ out, int C,
+                     const float* __restrict__ stat /*[4][C] (NORM only)*/, float* __restrict__ out, int C,
                      int64_t HW) {
   extern __shared__ float s_red[];
   const RowMap m = row_map(C);
   const int n = blockIdx.y;
   int64_t p0, p1;
   chunk_range(HW, p0, p1);
-  float q[5][8];
+  constexpr int Q = NORM ? 5 : 1;   // without a norm only T0 is needed: a small, high-occupancy kernel
+  float q[Q][8];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) fill8(q[k], 0.f);
+  for (int k = 0; k < Q; ++k) fill8(q[k], 0.f);
   if (m.on) {
     float mu[8], is[8], sc[8], sh[8];
-    fill8(mu, 0.f); fill8(is, 1.f); fill8(sc, 1.f); fill8(sh, 0.f);
-    if (stat) {
+    if (NORM) {
       ldf8(stat + m.v * 8, mu); ldf8(stat + C + m.v * 8, is);
       ldf8(stat + 2 * C + m.v * 8, sc); ldf8(stat + 3 * C + m.v * 8, sh);
     }
     const int64_t row0 = (int64_t)n * HW;
-    for (int64_t p = p0 + m.g; p < p1; p += m.groups) {
-      float g[8], av[8];
-      ld8(du + (row0 + p) * C + m.v * 8, g);
-      ld8(a + (row0 + p) * C + m.v * 8, av);
+    for (int64_t p = p0 + m.g; p < p1; p += 2 * m.groups) {
+      const bool two = p + m.groups < p1;
+      float g[2][8], av[2][8];
+      ld8(du + (row0 + p) * C + m.v * 8, g[0]);
+      ld8(a + (row0 + p) * C + m.v * 8, av[0]);
+      if (two) {
+        ld8(du + (row0 + p + m.groups) * C + m.v * 8, g[1]);
+        ld8(a + (row0 + p + m.groups) * C + m.v * 8, av[1]);
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(av[j], sc[j], sh[j]);
-        const float hp = hsw_grad(z);
-        const float ah = (av[j] - mu[j]) * is[j];
-        q[0][j] = fmaf(g[j], hsw(z), q[0][j]);
-        q[1][j] = fmaf(g[j], hp, q[1][j]);
-        q[2][j] += hp;
-        q[3][j] = fmaf(g[j] * hp, ah, q[3][j]);
-        q[4][j] = fmaf(hp, ah, q[4][j]);
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (NORM) {
+            const float z = fmaf(av[u][j], sc[j], sh[j]);
+            const float hp = hsw_grad(z);
+            const float ah = (av[u][j] - mu[j]) * is[j];
+            q[0][j] = fmaf(g[u][j], hsw(z), q[0][j]);
+            q[NORM ? 1 : 0][j] = fmaf(g[u][j], hp, q[NORM ? 1 : 0][j]);
+            q[NORM ? 2 : 0][j] += hp;
+            q[NORM ? 3 : 0][j] = fmaf(g[u][j] * hp, ah, q[NORM ? 3 : 0][j]);
+            q[NORM ? 4 : 0][j] = fmaf(hp, ah, q[NORM ? 4 : 0][j]);
+          } else {
+            q[0][j] = fmaf(g[u][j], hsw(av[u][j]), q[0][j]);
+          }
+        }
       }
     }
   }
-  block_channel_reduce<5, float>(m, C, q, s_red, out + (int64_t)n * 5 * C);
+  block_channel_reduce<Q, float>(m, C, q, s_red, out + (int64_t)n * 5 * C);
 }
 
 // BatchNorm backward coefficients of the dw conv's norm from the per-sample sums above:
@@ -229,6 +243,7 @@ __global__ void se_bn_combine_kernel(const float* __restrict__ T, const float* _
 }
 
 // da = ((du * s[n][c] + g[n][c]) * h'(z) - coef0 - ahat * coef1) * sc      (stat == null: da = (..) * h'(a))
+template <bool NORM>
 __global__ void __launch_bounds__(kT)
 dw_bwd_apply_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ a,
                     const float* __restrict__ s, const float* __restrict__ g, const float* __restrict__ stat,
@@ -239,8 +254,7 @@ dw_bwd_apply_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* _
   int64_t p0, p1;
   chunk_range(HW, p0, p1);
   float mu[8], is[8], sc[8], sh[8], c0[8], c1[8], sv[8], gv[8];
-  fill8(mu, 0.f); fill8(is, 1.f); fill8(sc, 1.f); fill8(sh, 0.f); fill8(c0, 0.f); fill8(c1, 0.f);
-  if (stat) {
+  if (NORM) {
     ldf8(stat + m.v * 8, mu); ldf8(stat + C + m.v * 8, is);
     ldf8(stat + 2 * C + m.v * 8, sc); ldf8(stat + 3 * C + m.v * 8, sh);
     ldf8(coef + m.v * 8, c0); ldf8(coef + C + m.v * 8, c1);
@@ -248,17 +262,26 @@ dw_bwd_apply_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* _
   ldf8(s + (int64_t)n * C + m.v * 8, sv);
   ldf8(g + (int64_t)n * C + m.v * 8, gv);
   const int64_t row0 = (int64_t)n * HW;
-  for (int64_t p = p0 + m.g; p < p1; p += m.groups) {
-    float d[8], av[8];
-    ld8(du + (row0 + p) * C + m.v * 8, d);
-    ld8(a + (row0 + p) * C + m.v * 8, av);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(av[j], sc[j], sh[j]);
-      const float dz = fmaf(d[j], sv[j], gv[j]) * hsw_grad(z);
-      d[j] = stat ? (dz - c0[j] - (av[j] - mu[j]) * is[j] * c1[j]) * sc[j] : dz;
+  for (int64_t p = p0 + m.g; p < p1; p += 2 * m.groups) {   // two pixels per iteration: 4 loads in flight
+    const bool two = p + m.groups < p1;
+    float d[2][8], av[2][8];
+    ld8(du + (row0 + p) * C + m.v * 8, d[0]);
+    ld8(a + (row0 + p) * C + m.v * 8, av[0]);
+    if (two) {
+      ld8(du + (row0 + p + m.groups) * C + m.v * 8, d[1]);
+      ld8(a + (row0 + p + m.groups) * C + m.v * 8, av[1]);
     }
-    *reinterpret_cast<uint4*>(da + (row0 + p) * C + m.v * 8) = Vec16<true>::pack(d);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = NORM ? fmaf(av[u][j], sc[j], sh[j]) : av[u][j];
+        const float dz = fmaf(d[u][j], sv[j], gv[j]) * hsw_grad(z);
+        d[u][j] = NORM ? (dz - c0[j] - (av[u][j] - mu[j]) * is[j] * c1[j]) * sc[j] : dz;
+      }
+      *reinterpret_cast<uint4*>(da + (row0 + p + u * m.groups) * C + m.v * 8) = Vec16<true>::pack(d[u]);
+    }
   }
 }
 
@@ -756,7 +779,10 @@ extern "C" int ast_dw_bwd_reduce(const void* du, const void* a, const float* sta
   AST_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N * 5 * C, s));
   const int groups = kT / (C / 8);
   const size_t smem = (size_t)groups * 5 * C * 4;   // <= 40 KB
-  dw_bwd_reduce_kernel<<<dim3(pick_chunks(N, HW, C), N), kT, smem, s>>>(CBF(du), CBF(a), stat, out, C, HW);
+  if (stat)
+    dw_bwd_reduce_kernel<true><<<dim3(pick_chunks(N, HW, C), N), kT, smem, s>>>(CBF(du), CBF(a), stat, out, C, HW);
+  else
+    dw_bwd_reduce_kernel<false><<<dim3(pick_chunks(N, HW, C), N), kT, smem / 5, s>>>(CBF(du), CBF(a), stat, out, C, HW);
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -774,8 +800,12 @@ extern "C" int ast_dw_bwd_apply(const void* du, const void* a, const float* s, c
                                 const float* coef, void* da, int N, int C, int64_t HW, void* stream) {
   if (!du || !a || !s || !g || !da || N <= 0 || HW <= 0 || (stat && !coef)) return AST_E_BADARG;
   if (!chan_ok(C) || N > 65535) return AST_E_SHAPE;
-  dw_bwd_apply_kernel<<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
-      CBF(du), CBF(a), s, g, stat, coef, BF(da), C, HW);
+  if (stat)
+    dw_bwd_apply_kernel<true><<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
+        CBF(du), CBF(a), s, g, stat, coef, BF(da), C, HW);
+  else
+    dw_bwd_apply_kernel<false><<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
+        CBF(du), CBF(a), s, g, stat, coef, BF(da), C, HW);
   AST_CHECK_LAUNCH();
   return 0;
 }
