@@ -45,6 +45,17 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` at the bench shape, from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json, written from the .ncu-rep by
+    tools/ncu_traffic.py); None when no capture is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -612,7 +623,7 @@ def run_native(args):
         line["adain_roofline"] = {"bound": "hbm", "kernel": "adain_cached_kernel (K1, NCHW fp32, (N,512,64,64))",
                                   "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                   "frac": gbs / pk["hbm_gbs"], "bytes_per_launch": ab, "ms_per_launch": ams,
-                                  "traffic": None, "peak_source": pk["source"]}
+                                  "traffic": ncu_traffic("adain_cached_kernel"), "peak_source": pk["source"]}
         if args.layers_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
             alt = time_layers(eng, N, S, impl=3)   # AST_CONV_TC_TAPBOX, for the A/B table only

@@ -210,6 +210,51 @@ def golden_autoencoder(M, out):
     with torch.no_grad():
         out["ae_eval_recon_after_step"] = ae(x).numpy()
 
+    # ---- the same on the NON-DEGENERATE variant of the state (restate_ae.activate_gates explains why) ----
+    torch.manual_seed(2)
+    ae2 = M.AutoEncoder()
+    ae2.load_state_dict(A.activate_gates(ae2.state_dict()), strict=True)
+    ae2.train()
+    recon = ae2(x)
+    recon_loss = torch.nn.HuberLoss()(recon, x)
+    cm, rm = enc(x), enc(recon)
+    perp = None
+    for a, b in zip(rm, cm):
+        l = F.huber_loss(a, b.detach())
+        perp = l if perp is None else perp + l
+    loss = 100.0 * recon_loss + 0.01 * perp
+    loss.backward()
+    out["act_train_recon"] = recon.detach().numpy()
+    out["act_train_losses"] = np.array([loss.item(), recon_loss.item(), perp.item()])
+    named = dict(ae2.named_parameters())
+    out["act_grad_norm"] = np.array([named[k].grad.double().norm().item() for k in gkeys])
+    for k in A.GOLDEN_GRAD_KEYS:
+        out["act_grad::" + k] = named[k].grad.numpy()
+    sd2 = ae2.state_dict()
+    for k in A.GOLDEN_BUFFER_KEYS:
+        out["act_buf::" + k] = sd2[k].numpy()
+    # eval mode with running statistics calibrated on x (bn.momentum = 1.0 for one training-mode forward)
+    torch.manual_seed(2)
+    ae3 = M.AutoEncoder()
+    ae3.load_state_dict(A.activate_gates(ae3.state_dict()), strict=True)
+    bns = [m for m in ae3.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:
+        m.momentum = 1.0
+    ae3.train()
+    with torch.no_grad():
+        ae3(x)
+    for m in bns:
+        m.momentum = 0.1
+    ae3.eval()
+    with torch.no_grad():
+        out["act_eval_recon"] = ae3(x).numpy()
+        taps = ae3.encoder(x, out_layers=[0, 2, 12, 14])
+        for i, t in zip((0, 2, 12, 14), taps):
+            out[f"act_eval_enc{i}"] = t.numpy()
+        z = ae3.ada_out(torch.cat((taps[2], taps[3]), dim=1))
+        out["act_eval_code"] = z.numpy()
+        out["act_eval_dec_of_code"] = ae3.decoder(z).numpy()
+
 
 def main():
     if not ref_loader.available():

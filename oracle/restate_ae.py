@@ -89,11 +89,11 @@ def _layer_index(expand: bool, norm: bool):
     return idx
 
 
-def _bn(P, key, x, training):
+def _bn(P, key, x, training, momentum=BN_MOMENTUM):
     """nn.BatchNorm2d(affine, track_running_stats): batch statistics + in-place running-stat update in
     training mode, running statistics in eval mode."""
     rm, rv = P[key + ".running_mean"], P[key + ".running_var"]
-    y = F.batch_norm(x, rm, rv, P[key + ".weight"], P[key + ".bias"], training, BN_MOMENTUM, BN_EPS)
+    y = F.batch_norm(x, rm, rv, P[key + ".weight"], P[key + ".bias"], training, momentum, BN_EPS)
     if training and (key + ".num_batches_tracked") in P:
         P[key + ".num_batches_tracked"] += 1
     return y
@@ -108,7 +108,8 @@ def se_layer(P, key, x):
     return x * y.view(b, c, 1, 1)
 
 
-def depthwise_block(P, prefix, x, inp, oup, stride, t, k=3, norm=False, use_identity=True, training=False):
+def depthwise_block(P, prefix, x, inp, oup, stride, t, k=3, norm=False, use_identity=True, training=False,
+                    bn_momentum=BN_MOMENTUM):
     """DepthWiseConv.forward (mobilenetv2.py:152-165) for the block whose parameters live under
     ``prefix + '._layers.'``."""
     expand = t != 1
@@ -119,7 +120,7 @@ def depthwise_block(P, prefix, x, inp, oup, stride, t, k=3, norm=False, use_iden
     if expand:
         x = F.conv2d(x, P[f"{L}{ix['pw1']}.weight"])
         if norm:
-            x = _bn(P, f"{L}{ix['bn1']}", x, training)
+            x = _bn(P, f"{L}{ix['bn1']}", x, training, bn_momentum)
         x = F.hardswish(x)
         pad = (k - 1) // 2                                                  # mobilenetv2.py:133
     else:
@@ -127,19 +128,19 @@ def depthwise_block(P, prefix, x, inp, oup, stride, t, k=3, norm=False, use_iden
     x = F.pad(x, (pad, pad, pad, pad), mode="reflect")
     x = F.conv2d(x, P[f"{L}{ix['dw']}.weight"], stride=stride, groups=hidden)
     if norm:
-        x = _bn(P, f"{L}{ix['bn2']}", x, training)
+        x = _bn(P, f"{L}{ix['bn2']}", x, training, bn_momentum)
     x = F.hardswish(x)
     x = se_layer(P, f"{L}{ix['se']}", x)
     x = F.conv2d(x, P[f"{L}{ix['pw2']}.weight"])
     if norm:
-        x = _bn(P, f"{L}{ix['bn3']}", x, training)
+        x = _bn(P, f"{L}{ix['bn3']}", x, training, bn_momentum)
     if stride == 1 and inp == oup and use_identity:                         # mobilenetv2.py:99, 161
         x = x + org
     return x
 
 
 # ---- Encoder / Decoder / AutoEncoder ---------------------------------------------------------------
-def encoder_forward(P, x, out_layers=(), auto_enc=False, training=False, prefix="encoder"):
+def encoder_forward(P, x, out_layers=(), auto_enc=False, training=False, prefix="encoder", bn_momentum=BN_MOMENTUM):
     """Encoder.forward, models.py:158-184.  Block 0 = reflect-padded 3x3 conv, no bias, Hardswish
     (conv_3x3_bn, mobilenetv2.py:38-43: no BatchNorm despite the name)."""
     outs = []
@@ -148,7 +149,8 @@ def encoder_forward(P, x, out_layers=(), auto_enc=False, training=False, prefix=
     if 0 in out_layers:
         outs.append(x)
     for i, (inp, oup, s, t, k) in enumerate(encoder_block_specs(), start=1):
-        x = depthwise_block(P, f"{prefix}.mob_net.{i}", x, inp, oup, s, t, k, norm=True, training=training)
+        x = depthwise_block(P, f"{prefix}.mob_net.{i}", x, inp, oup, s, t, k, norm=True, training=training,
+                            bn_momentum=bn_momentum)
         if i in out_layers:
             outs.append(x)
     return x if auto_enc else outs
@@ -169,9 +171,9 @@ def decoder_forward(P, x, exporting=False, prefix="decoder"):
     return x
 
 
-def autoencoder_forward(P, x, training=False):
+def autoencoder_forward(P, x, training=False, bn_momentum=BN_MOMENTUM):
     """AutoEncoder.forward, models.py:329-338."""
-    e = encoder_forward(P, x, ENC_OUT_LAYERS, training=training)
+    e = encoder_forward(P, x, ENC_OUT_LAYERS, training=training, bn_momentum=bn_momentum)
     z = depthwise_block(P, "ada_out", torch.cat((e[0], e[1]), dim=1), ENC_OUT_CHANNELS * 2, ENC_OUT_CHANNELS,
                         1, EXPAND_RATIO, 3, norm=False, use_identity=False)
     return decoder_forward(P, z)
@@ -278,3 +280,124 @@ GOLDEN_BUFFER_KEYS = (
     "encoder.mob_net.7._layers.4.running_mean", "encoder.mob_net.7._layers.4.running_var",
     "encoder.mob_net.14._layers.8.running_mean", "encoder.mob_net.14._layers.8.running_var",
 )
+
+
+def activate_gates(sd, gate_bias: float = 0.5, hidden_bias: float = 0.25):
+    """A NON-DEGENERATE variant of a seeded state, for parity fixtures.
+
+    The reference's initialisation is degenerate for this network: (1) SELayer Linear weights N(0, 0.01) with
+    zero biases (mobilenetv2.py:178-181) leave every gate at Hardtanh(~1e-4); (2) depthwise weights are drawn
+    with std sqrt(2 / (k*k*C)) (mobilenetv2.py:171-172), a gain of sqrt(2/C) ~ 0.07 per depthwise conv, and the
+    decoder has no BatchNorm to undo it.  A freshly constructed AutoEncoder therefore outputs EXACTLY its head
+    bias in fp32 and most gradients are exactly zero: that state pins names, shapes, the encoder and the first
+    blocks, but exercises nothing downstream.  The fixtures are therefore ALSO made on this variant of the same
+    seeded state: SE biases moved into the gates' linear region (fc.2.bias = 0.5, fc.0.bias = 0.25) and every
+    depthwise weight rescaled to unit gain (x sqrt(C/2); the encoder's too, so that eval mode with fresh running
+    statistics -- BatchNorm ~ identity -- keeps a signal as well).
+    Returns a new state dict."""
+    out = clone_state(sd)
+    for k in out:
+        if k.endswith(".fc.2.bias"):
+            out[k].fill_(gate_bias)
+        elif k.endswith(".fc.0.bias"):
+            out[k].fill_(hidden_bias)
+        elif out[k].dim() == 4 and out[k].shape[1] == 1 and out[k].shape[2] > 1:      # every depthwise weight
+            out[k].mul_(math.sqrt(out[k].shape[0] / 2.0))
+    return out
+
+
+def calibrate_running_stats(P, x):
+    """Set every BatchNorm's running statistics to the batch statistics of ``x`` (one training-mode forward with
+    momentum 1.0, i.e. ``bn.momentum = 1.0`` on the reference modules), so that the eval-mode forward that
+    follows normalises a non-degenerate signal.  In place; returns P."""
+    with torch.no_grad():
+        autoencoder_forward(P, x, training=True, bn_momentum=1.0)
+    return P
+
+
+# ------------------------------------------------------------------------------------------------------
+# The bf16 STORAGE CONTRACT of the CUDA inference path, restated on CPU.
+# Same mathematics as depthwise_block(..., training=False), but every tensor the kernels keep in HBM is rounded
+# to bf16 at exactly the point where they round it: the folded pointwise weights, the Hardswish'ed expand
+# output, the Hardswish'ed depthwise output, the SE-scaled per-sample pointwise weights and the block output
+# (after bias and residual).  Accumulation, biases, BatchNorm folding, SE and the depthwise weights stay fp32.
+# Comparing the fp32 restatement with this one shows what bf16 storage costs on a given state (it is what the
+# CUDA path is allowed to differ by); comparing the CUDA path with this one checks the kernels themselves.
+# ------------------------------------------------------------------------------------------------------
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _fold_bn_eval(P, conv_key, bn_key):
+    w = P[conv_key + ".weight"]
+    if bn_key is None:
+        return w, None
+    inv = (P[bn_key + ".running_var"] + BN_EPS).rsqrt() * P[bn_key + ".weight"]
+    return w * inv.view(-1, 1, 1, 1), P[bn_key + ".bias"] - P[bn_key + ".running_mean"] * inv
+
+
+def depthwise_block_bf16(P, prefix, x, inp, oup, stride, t, k=3, norm=False, use_identity=True, up2=False):
+    """x: bf16-representable (N,inp,H,W) -> bf16-representable block output, eval mode."""
+    expand = t != 1
+    hidden = round(inp * t)
+    ix = _layer_index(expand, norm)
+    L = prefix + "._layers."
+    h = x
+    if expand:
+        w1, b1 = _fold_bn_eval(P, f"{L}{ix['pw1']}", f"{L}{ix['bn1']}" if norm else None)
+        a = F.conv2d(x, _bf(w1))
+        if b1 is not None:
+            a = a + b1.view(1, -1, 1, 1)
+        h = _bf(F.hardswish(a))
+        pad = (k - 1) // 2
+    else:
+        pad = 1
+    if up2:
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+    wd, bd = _fold_bn_eval(P, f"{L}{ix['dw']}", f"{L}{ix['bn2']}" if norm else None)
+    y = F.conv2d(F.pad(h, (pad, pad, pad, pad), mode="reflect"), wd, stride=stride, groups=hidden)
+    if bd is not None:
+        y = y + bd.view(1, -1, 1, 1)
+    y = _bf(F.hardswish(y))
+    se = f"{L}{ix['se']}"
+    g = F.hardtanh(F.linear(F.relu(F.linear(y.mean(dim=(2, 3)), P[se + ".fc.0.weight"], P[se + ".fc.0.bias"])),
+                            P[se + ".fc.2.weight"], P[se + ".fc.2.bias"]), 0.0, 1.0)
+    w2, b2 = _fold_bn_eval(P, f"{L}{ix['pw2']}", f"{L}{ix['bn3']}" if norm else None)
+    outs = []
+    for n in range(x.shape[0]):
+        w2s = _bf(w2.view(oup, hidden) * g[n].view(1, -1)).view(oup, hidden, 1, 1)
+        outs.append(F.conv2d(y[n:n + 1], w2s))
+    o = torch.cat(outs)
+    if b2 is not None:
+        o = o + b2.view(1, -1, 1, 1)
+    if stride == 1 and inp == oup and use_identity:
+        o = o + (F.interpolate(x, scale_factor=2, mode="nearest") if up2 else x)
+    return _bf(o)
+
+
+def autoencoder_forward_bf16(P, x, want=()):
+    """AutoEncoder.forward in eval mode under the bf16 storage contract.  Returns (image, {name: tensor}) with the
+    intermediate tensors named in ``want`` ('enc<i>', 'code')."""
+    keep = {}
+    h = _bf(F.hardswish(F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), P["encoder.mob_net.0.0.weight"])))
+    if "enc0" in want:
+        keep["enc0"] = h
+    taps = {}
+    for i, (inp, oup, s, t, k) in enumerate(encoder_block_specs(), start=1):
+        h = depthwise_block_bf16(P, f"encoder.mob_net.{i}", h, inp, oup, s, t, k, norm=True)
+        if f"enc{i}" in want:
+            keep[f"enc{i}"] = h
+        if i in ENC_OUT_LAYERS:
+            taps[i] = h
+    z = depthwise_block_bf16(P, "ada_out", torch.cat((taps[12], taps[14]), dim=1), 256, 128, 1, EXPAND_RATIO, 3,
+                             norm=False, use_identity=False)
+    if "code" in want:
+        keep["code"] = z
+    h = z
+    for i, (inp, oup, s, t, k, up) in enumerate(decoder_block_specs()):
+        b = f"decoder._decoder_blocks.{i}"
+        h = depthwise_block_bf16(P, b + "._conv", h, inp, oup, s, t, k, norm=False)
+        if up:
+            h = depthwise_block_bf16(P, b + "._upsample_2", h, oup, oup, 1, 1, 3, norm=False, up2=True)
+    img = F.conv2d(F.pad(h, (1, 1, 1, 1), mode="reflect"), P["decoder._img_out.weight"], P["decoder._img_out.bias"])
+    return img, keep

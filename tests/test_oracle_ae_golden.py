@@ -81,3 +81,54 @@ def test_product_module_tree_draws_the_same_weights(g):
     np.testing.assert_array_equal(s, g["ae_state_sum"])
     ref = A.make_ae_state(2)
     ae.load_state_dict(ref, strict=True)
+
+
+def test_non_degenerate_variant_train_step_and_calibrated_eval(g, state):
+    """The reference's fresh initialisation makes the AutoEncoder output exactly its head bias (restate_ae.
+    activate_gates explains why); these fixtures were made by the genuine reference on the non-degenerate variant
+    of the same state, so every block sees a real signal and every parameter a non-zero gradient."""
+    x = T(g["ae_x"])
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    act = A.activate_gates(state)
+    P = A.clone_state(act, requires_grad=True)
+    loss, recon_loss, perp, recon = A.ae_losses(P, x, vw, vb)
+    assert torch.equal(recon.detach(), T(g["act_train_recon"]))
+    assert recon.detach().std(dim=(0, 2, 3)).min() > 1e-3            # a real signal reaches the image
+    np.testing.assert_allclose([loss.item(), recon_loss.item(), perp.item()], g["act_train_losses"], rtol=1e-6)
+    loss.backward()
+    gkeys = list(g["ae_grad_keys"])
+    norms = np.array([P[k].grad.double().norm().item() for k in gkeys])
+    assert (norms > 0).all()                                         # nothing is cut off from the loss
+    np.testing.assert_allclose(norms, g["act_grad_norm"], rtol=2e-4, atol=1e-12)
+    for k in A.GOLDEN_GRAD_KEYS:
+        torch.testing.assert_close(P[k].grad, T(g["act_grad::" + k]), rtol=2e-4, atol=1e-8)
+    for k in A.GOLDEN_BUFFER_KEYS:
+        assert torch.equal(P[k].detach(), T(g["act_buf::" + k])), k
+    Q = A.calibrate_running_stats(A.clone_state(act), x)
+    with torch.no_grad():
+        assert torch.equal(A.autoencoder_forward(Q, x), T(g["act_eval_recon"]))
+        taps = A.encoder_forward(Q, x, (0, 2, 12, 14))
+        for i, t in zip((0, 2, 12, 14), taps):
+            assert torch.equal(t, T(g[f"act_eval_enc{i}"])), i
+        z = A.depthwise_block(Q, "ada_out", torch.cat((taps[2], taps[3]), dim=1), 256, 128, 1, A.EXPAND_RATIO, 3,
+                              norm=False, use_identity=False)
+        assert torch.equal(z, T(g["act_eval_code"]))
+        assert torch.equal(A.decoder_forward(Q, z), T(g["act_eval_dec_of_code"]))
+    assert T(g["act_eval_recon"]).std(dim=(0, 2, 3)).min() > 5e-4
+
+
+def test_bf16_storage_contract_distance_from_fp32(g, state):
+    """What bf16 storage alone costs on the non-degenerate state (CPU only): the contract restatement
+    (autoencoder_forward_bf16, the arithmetic the CUDA inference path implements) against the fp32 reference
+    outputs.  Shallow taps stay within 1 %, the deepest 4x4 features drift to ~10 %, the image keeps PSNR >> 40 dB."""
+    x = T(g["ae_x"])
+    Q = A.calibrate_running_stats(A.clone_state(A.activate_gates(state)), x)
+    with torch.no_grad():
+        img, keep = A.autoencoder_forward_bf16(Q, x, want=("enc0", "enc2", "enc12", "enc14", "code"))
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+    e = {k: rel(keep[k], T(g["act_eval_" + k])) for k in ("enc0", "enc2", "enc12", "enc14", "code")}
+    assert e["enc0"] < 3e-3 and e["enc2"] < 1.5e-2 and e["enc12"] < 0.12 and e["enc14"] < 0.15 and e["code"] < 0.15, e
+    assert R.psnr(img, T(g["act_eval_recon"])) >= 50.0

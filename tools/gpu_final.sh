@@ -1,25 +1,32 @@
 #!/bin/bash
-# Round-end evidence run: tests, smoke, bench (+layers, +train), per-role wait breakdown, ncu launch lists
-# (inference + training step) and one --set full capture of the hot kernels.
+# Round-end evidence run: tests, smoke, bench (+layers, +train, +train_ae), per-role wait breakdown, ncu launch
+# lists (inference step, config-2 step, config-3 step) and --set full captures of the hot kernels.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
-for f in test_gpu_train test_gpu_conv test_gpu_pipeline test_gpu_adain test_gpu_losses; do
-  timeout 900 python -m pytest tests/$f.py -q -m gpu --timeout=600 > gpurun_out/$f.log 2>&1
-  echo "exit=$?" >> gpurun_out/$f.log
-done
+timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/test_gpu_all.log 2>&1; echo "exit=$?" >> gpurun_out/test_gpu_all.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit=$?" >> gpurun_out/smoke.log
-timeout 900 python bench.py --steps 20 --warmup 3 --layers-out gpurun_out/layers.json > gpurun_out/bench.log 2>&1; echo "exit=$?" >> gpurun_out/bench.log
+timeout 1200 python bench.py --steps 20 --warmup 3 --layers-out gpurun_out/layers.json > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "exit=$?" >> gpurun_out/bench.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "exit=$?" >> gpurun_out/bench_ref.log
+timeout 300 python tools/bench_k1.py > gpurun_out/bench_k1.log 2>&1
+timeout 300 python tools/bench_dw.py --n 32 > gpurun_out/bench_dw.log 2>&1
 AST_CONV_DEBUG=1 timeout 300 python tools/dbg_layers.py 32 2>&1 | grep "conv dbg" | awk "NR%2==0" > gpurun_out/conv_role_breakdown.txt
-timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > gpurun_out/plain_bench.log 2>&1 &&
+# launch lists (each command first runs clean without ncu)
+timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train --no-train-ae > gpurun_out/plain_bench.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > gpurun_out/ncu_launches.log 2>&1
+    --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train --no-train-ae > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit=$?" >> gpurun_out/ncu_launches.log
 timeout 200 python tools/prof_train.py > gpurun_out/plain_train.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 1000 --csv \
     --log-file gpurun_out/train_launches.csv python tools/prof_train.py > gpurun_out/ncu_train.log 2>&1
+timeout 300 python tools/prof_ae.py --batch 32 --steps 5 > gpurun_out/ae_b32.log 2>&1 &&
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file gpurun_out/ae_train_launches.csv python tools/prof_ae.py --batch 32 --profile > gpurun_out/ae_ncu.log 2>&1
+# full captures
 timeout 300 python tools/prof_target.py 8 > gpurun_out/plain_prof.log 2>&1 &&
 timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"adain_cached|conv3x3|native_" -c 36 \
     -o gpurun_out/prof -f python tools/prof_target.py 8 > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit=$?" >> gpurun_out/ncu_full.log
-tail -n 3 gpurun_out/*.log | cut -c1-400
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:adain_cached_kernel -c 2 -o gpurun_out/k1 -f python tools/bench_k1.py > gpurun_out/ncu_k1.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dw_tiled|dw_wgrad_tiled" -c 6 -o gpurun_out/dw -f python tools/bench_dw.py --n 32 --only 240x5 --reps 1 > gpurun_out/ncu_dw.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"pw_conv_tc|pw_wgrad_tc" -c 8 -s 60 -o gpurun_out/pw -f python tools/prof_ae.py --batch 32 --profile > gpurun_out/ncu_pw.log 2>&1
+tail -n 3 gpurun_out/*.log | cut -c1-300
