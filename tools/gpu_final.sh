@@ -23,10 +23,18 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
     --log-file gpurun_out/ae_train_launches.csv python tools/prof_ae.py --batch 32 --profile > gpurun_out/ae_ncu.log 2>&1
 # full captures
 timeout 300 python tools/prof_target.py 8 > gpurun_out/plain_prof.log 2>&1 &&
-timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"adain_cached|conv3x3|native_" -c 36 \
+timeout 1500 ncu --set full --clock-control none --profile-from-start off -k regex:"adain_cached|conv3x3|native_" -c 36 \
     -o gpurun_out/prof -f python tools/prof_target.py 8 > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit=$?" >> gpurun_out/ncu_full.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:adain_cached_kernel -c 2 -o gpurun_out/k1 -f python tools/bench_k1.py > gpurun_out/ncu_k1.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dw_tiled|dw_wgrad_tiled" -c 6 -o gpurun_out/dw -f python tools/bench_dw.py --n 32 --only 240x5 --reps 1 > gpurun_out/ncu_dw.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"pw_conv_tc|pw_wgrad_tc" -c 8 -s 60 -o gpurun_out/pw -f python tools/prof_ae.py --batch 32 --profile > gpurun_out/ncu_pw.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:adain_cached_kernel -c 2 -o gpurun_out/k1 -f python tools/bench_k1.py > gpurun_out/ncu_k1.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:"dw_tiled|dw_wgrad_tiled" -c 6 -o gpurun_out/dw -f python tools/bench_dw.py --n 32 --only 240x5 --reps 1 > gpurun_out/ncu_dw.log 2>&1
+timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:"pw_conv_tc|pw_wgrad_tc" -c 8 -s 60 -o gpurun_out/pw -f python tools/prof_ae.py --batch 32 --profile > gpurun_out/ncu_pw.log 2>&1
+# keep the raw-metric CSV of every capture, drop the (large) reports: gpurun_out/ travels back only below 64 MiB
+for r in prof k1 dw pw; do
+  if [ -f gpurun_out/$r.ncu-rep ]; then
+    ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/ncu_${r}_raw.csv 2>/dev/null
+    rm -f gpurun_out/$r.ncu-rep
+  fi
+done
+du -sh gpurun_out
 tail -n 3 gpurun_out/*.log | cut -c1-300

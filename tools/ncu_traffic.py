@@ -3,7 +3,8 @@ usage: python tools/ncu_traffic.py <report.ncu-rep> <kernel substring> <key> [la
 import csv, io, json, os, subprocess, sys
 rep, sub, key = sys.argv[1], sys.argv[2], sys.argv[3]
 idx = int(sys.argv[4]) if len(sys.argv) > 4 else -1
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = (open(rep).read() if rep.endswith(".csv") else
+       subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 sel = [r for r in rows[2:] if sub in r[hdr.index("Kernel Name")]]
