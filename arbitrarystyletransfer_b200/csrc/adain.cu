@@ -540,13 +540,6 @@ static int launch_cached(const AdainArgs& a, int64_t rows, unsigned CS, cudaStre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (CS > 8) {   // 16-CTA clusters are non-portable: opt in once per instantiation
-    static bool allowed = false;
-    if (!allowed) {
-      AST_CUDA(cudaFuncSetAttribute(adain_cached_kernel<BF16, R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      allowed = true;
-    }
-  }
   AST_CUDA(cudaLaunchKernelEx(&cfg, adain_cached_kernel<BF16, R>, a));
   return 0;
 }
@@ -565,20 +558,9 @@ static int adain_dispatch(const AdainArgs& a, int64_t rows, cudaStream_t s) {
     while ((int64_t)CS * kMaxSeg < nvec) CS <<= 1;
     // prefer more, smaller CTAs when there are few rows (fills 148 SMs at cfg 1 / cfg 5)
     while (CS < 8 && rows * CS < 2 * 148 && nvec / (2 * CS) >= kThreads) CS <<= 1;
-    // long rows: 4 cached vectors per thread (3 CTAs per SM) instead of 8 (2 CTAs per SM) when a wider cluster
-    // can provide it -- the cluster path is latency-bound, occupancy is what it lacks.  16-CTA clusters are
-    // tried once and remembered if the device refuses them.
-    static bool cs16_ok = true;
-    if ((nvec + CS - 1) / CS > 4 * kThreads && (CS < 8 || (CS == 8 && cs16_ok))) {
-      const unsigned CS2 = CS * 2;
-      const int64_t seg2 = (nvec + CS2 - 1) / CS2;
-      if ((seg2 + kThreads - 1) / kThreads <= 4 && rows * CS2 < 0x7fffffffLL) {
-        const int rc = launch_cached<BF16, 4>(a, rows, CS2, s);
-        if (rc == 0 || CS2 <= 8) return rc;
-        cs16_ok = false;            // fall through to the portable 8-CTA cluster
-        (void)cudaGetLastError();
-      }
-    }
+    // (Tried: twice as wide clusters -- 16 CTAs, non-portable -- to cache 4 instead of 8 vectors per thread and
+    // fit 3 CTAs per SM on the long-row path: config 5 went from 283 to 461 us, cluster scheduling costs more
+    // than the occupancy buys.)
     const int64_t seg = (nvec + CS - 1) / CS;
     const int64_t r = (seg + kThreads - 1) / kThreads;
     if (r <= 1) return launch_cached<BF16, 1>(a, rows, CS, s);
