@@ -169,7 +169,7 @@ __device__ __forceinline__ void cta_merge_to(Moments m, Moments* s_warp, Moments
 }
 
 template <bool BF16, int R>
-__global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) adain_cached_kernel(const AdainArgs a) {
+__global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 4))) adain_cached_kernel(const AdainArgs a) {
   using VT = Vec16<BF16>;
   constexpr int V = VT::V;
   cg::cluster_group cluster = cg::this_cluster();
@@ -189,12 +189,25 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) ada
 
   const uint4* crow =
       reinterpret_cast<const uint4*>(reinterpret_cast<const typename VT::elem*>(a.content) + row * a.HW);
-  uint4 cache[R];
+  // R <= 4: the content segment lives in registers.  R == 8 (long rows, cluster-split): it is staged in shared
+  // memory with asynchronous 16-byte copies instead -- no registers are held while the style rows stream, which
+  // doubles the CTAs per SM of this latency-bound path (each thread later reads back only what it copied).
+  constexpr bool SM = (R == 8);
+  extern __shared__ uint4 s_cache[];
+  uint4 cache[SM ? 1 : R];
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
-    if (i < v1) cache[j] = ld_stream_u4(crow + i);
+    if (i < v1) {
+      if (SM) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(s_cache + threadIdx.x + j * kThreads);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(crow + i) : "memory");
+      } else {
+        cache[SM ? 0 : j] = ld_stream_u4(crow + i);
+      }
+    }
   }
+  if (SM) asm volatile("cp.async.commit_group;" ::: "memory");
   uint4 scache[R <= 4 ? R : 1];
   if (R <= 4 && Q == 2 && a.style_hw[0] == a.HW) {
     const uint4* srow0 =
@@ -205,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) ada
       if (i < v1) scache[j] = ld_stream_u4(srow0 + i);
     }
   }
-  if (!((R <= 4) && Q == 2 && a.style_hw[0] == a.HW && CS == 1)) {   // not the two-pass fast path below
+  if (!SM && !((R <= 4) && Q == 2 && a.style_hw[0] == a.HW && CS == 1)) {   // not the two-pass fast path below
     ShiftedLanes<V> w;
     w.init(VT::load1(a.content, row * a.HW));
 #pragma unroll
@@ -213,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) ada
       int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
       if (i < v1) {
         float x[V];
-        VT::unpack(cache[j], x);
+        VT::unpack(cache[SM ? 0 : j], x);
         w.push(x);
       }
     }
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) ada
       int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
       if (i < v1) {
         float xs[V], ys[V];
-        VT::unpack(cache[j], xs);
+        VT::unpack(cache[SM ? 0 : j], xs);
         VT::unpack(scache[j], ys);
 #pragma unroll
         for (int e = 0; e < V; ++e) { t0 += xs[e]; t1 += ys[e]; }
@@ -259,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) ada
       int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
       if (i < v1) {
         float xs[V], ys[V];
-        VT::unpack(cache[j], xs);
+        VT::unpack(cache[SM ? 0 : j], xs);
         VT::unpack(scache[j], ys);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -305,6 +318,21 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) ada
     Moments m = (s0 < s1) ? stream_moments_vec<BF16>(srow, s0, s1) : Moments{0.f, 0.f, 0.f};
     cta_merge_to(m, s_warp, &s_q[1 + k]);
   }
+  if (SM) {   // the content copies have had the whole style stream to land
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    ShiftedLanes<V> w;
+    w.init(VT::load1(a.content, row * a.HW));
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
+      if (i < v1) {
+        float x[V];
+        VT::unpack(s_cache[threadIdx.x + j * kThreads], x);
+        w.push(x);
+      }
+    }
+    cta_merge_to(w.fold(), s_warp, &s_q[0]);
+  }
   const Moments* fin = s_q;
   if (CS > 1) {
     cluster.sync();  // every CTA's s_q is complete and visible cluster-wide
@@ -328,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 2))) ada
     int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
     if (i < v1) {
       float x[V];
-      VT::unpack(cache[j], x);
+      VT::unpack(SM ? s_cache[threadIdx.x + j * kThreads] : cache[SM ? 0 : j], x);
 #pragma unroll
       for (int e = 0; e < V; ++e) x[e] = apply_affine(x[e], mu, rsig, A, B, a.alpha, blend);
       st_stream_u4(orow + i, VT::pack(x));
@@ -531,7 +559,7 @@ static int launch_cached(const AdainArgs& a, int64_t rows, unsigned CS, cudaStre
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(rows * CS));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = (R == 8) ? (size_t)R * kThreads * sizeof(uint4) : 0;   // 32 KB content segment
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
