@@ -535,6 +535,56 @@ def test_autoencoder_non_degenerate_state_vs_reference_golden(g, ae):
     assert max(cerr.values()) < 8e-2, cerr
 
 
+@pytest.mark.parametrize("hw", [(40, 24), (72, 56), (24, 88)])
+def test_autoencoder_ragged_sizes_vs_contract(ae, hw):
+    """Sizes that are multiples of 8 but of nothing else (deepest maps 5x3, 9x7, 3x11): partial tiles, TMA zero
+    fill, odd extents under the stride-2 convs, reflection on 2- and 3-pixel maps.  Eval forward and train-mode
+    forward + backward against the oracle (fp32 and the bf16 storage contract)."""
+    H, W = hw
+    x = torch.rand(3, 3, H, W, generator=G(H * W))
+    act = A.activate_gates(A.make_ae_state(2))
+    Q = A.calibrate_running_stats(A.clone_state(act), x)
+    ae.load_state_dict(Q, strict=True)
+    bias = act["decoder._img_out.bias"]
+    ae.eval()
+    with torch.no_grad():
+        rec = ae(x.cuda())
+        cimg, _ = A.autoencoder_forward_bf16(Q, x)
+        ref = A.autoencoder_forward(Q, x)
+    assert rec.shape == ref.shape and torch.isfinite(rec).all()
+    e_contract, e_fp32 = rel(_signal(rec, bias), _signal(cimg, bias)), rel(_signal(rec, bias), _signal(ref, bias))
+    print(f"ragged {H}x{W}: image signal vs contract {e_contract:.4f}, vs fp32 {e_fp32:.4f}")
+    assert e_contract < 0.1 and e_fp32 < 0.2 and R.psnr(rec.cpu(), ref) >= 40.0, (e_contract, e_fp32)
+    # train mode: loss and a few gradients against the oracle's autograd
+    ae.load_state_dict(act, strict=True)
+    ae.train()
+    loss = F.huber_loss(ae(x.cuda()), x.cuda())
+    loss.backward()
+    P = A.clone_state(act, requires_grad=True)
+    ref_loss = F.huber_loss(A.autoencoder_forward(P, x, training=True), x)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    named = dict(ae.named_parameters())
+    for k in ("decoder._img_out.weight", "decoder._decoder_blocks.8._conv._layers.2.weight",
+              "decoder._decoder_blocks.4._upsample_2._layers.1.weight", "ada_out._layers.0.weight",
+              "encoder.mob_net.7._layers.3.weight", "encoder.mob_net.2._layers.0.weight", "encoder.mob_net.0.0.weight"):
+        c = cos(named[k].grad, P[k].grad)
+        assert c > 0.95, (k, c)
+
+
+def test_autoencoder_too_small_input_raises_like_the_reference(ae):
+    """16 x 48 leaves a 2-pixel map under a 5x5 reflect-padded depthwise conv: torch raises in the reference
+    ("Padding size should be less than the corresponding input dimension"); this path must refuse too."""
+    from arbitrarystyletransfer_b200 import _lib as L
+    x = torch.rand(1, 3, 16, 48, generator=G(1))
+    with pytest.raises(RuntimeError):
+        A.autoencoder_forward(A.clone_state(A.make_ae_state(2)), x)
+    ae.eval()
+    with pytest.raises(L.AstError), torch.no_grad():
+        ae(x.cuda())
+        torch.cuda.synchronize()
+
+
 def test_autoencoder_config3_shape_properties(ae):
     """BASELINE config 3 geometry (256x256) at a reduced batch: finite outputs, determinism, every
     parameter receives a finite gradient, BatchNorm-normalised activations have the batch statistics they
