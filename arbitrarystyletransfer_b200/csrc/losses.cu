@@ -75,6 +75,51 @@ __global__ void __launch_bounds__(kLThreads) huber_bwd_kernel(const float* __res
   }
 }
 
+// ---- total variation: sum (x[..,w]-x[..,w+1])^2 + sum (x[..,h,:]-x[..,h+1,:])^2   (losses.py:90-103) ------
+// planes = N*C images of H x W fp32; same deterministic two-stage reduction as the Huber loss.
+__global__ void __launch_bounds__(kLThreads) tv_partial_kernel(const float* __restrict__ img,
+                                                               float* __restrict__ partial, int64_t planes,
+                                                               int H, int W) {
+  __shared__ float s_red[kLThreads / 32];
+  float acc = 0.f;
+  const int64_t n = planes * H * W;
+  const int64_t stride = (int64_t)gridDim.x * kLThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kLThreads + threadIdx.x; i < n; i += stride) {
+    const int w = (int)(i % W), h = (int)((i / W) % H);
+    const float x = img[i];
+    if (w + 1 < W) { const float d = x - img[i + 1]; acc = fmaf(d, d, acc); }
+    if (h + 1 < H) { const float d = x - img[i + W]; acc = fmaf(d, d, acc); }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int w = 0; w < kLThreads / 32; ++w) r += s_red[w];
+    partial[blockIdx.x] = r;
+  }
+}
+
+// d loss / d x[h][w] = 2 g [ (x - right) - (left - x) + (x - below) - (above - x) ] with absent neighbours dropped
+__global__ void __launch_bounds__(kLThreads) tv_bwd_kernel(const float* __restrict__ img,
+                                                           const float* __restrict__ g_loss,
+                                                           float* __restrict__ g_img, int64_t planes, int H, int W) {
+  const float g2 = 2.f * g_loss[0];
+  const int64_t n = planes * H * W;
+  const int64_t stride = (int64_t)gridDim.x * kLThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kLThreads + threadIdx.x; i < n; i += stride) {
+    const int w = (int)(i % W), h = (int)((i / W) % H);
+    const float x = img[i];
+    float d = 0.f;
+    if (w + 1 < W) d += x - img[i + 1];
+    if (w > 0) d -= img[i - 1] - x;
+    if (h + 1 < H) d += x - img[i + W];
+    if (h > 0) d -= img[i - W] - x;
+    g_img[i] = g2 * d;
+  }
+}
+
 // ---- Gram: G[b] = X X^T / (C*HW) ---------------------------------------------------------------
 // 64x64 output tile per CTA, 4x4 per thread, K chunks of 32 through shared memory, split-K over HW
 // with fp32 atomics into a pre-zeroed G.  Only tiles with tj >= ti are computed; the mirror is
@@ -234,6 +279,29 @@ extern "C" int ast_huber_fwd(const float* inp, const float* tgt, float* loss, in
   huber_partial_kernel<<<nb, kLThreads, 0, s>>>(inp, tgt, (float*)ws, n);
   AST_CHECK_LAUNCH();
   huber_final_kernel<<<1, kLThreads, 0, s>>>((const float*)ws, nb, loss, scale / (float)n);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_tv_fwd(const float* img, float* loss, int64_t planes, int H, int W, void* ws, size_t ws_bytes,
+                          void* stream) {
+  if (!img || !loss || !ws || planes <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  if (ws_bytes < kHuberMaxBlocks * sizeof(float)) return AST_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = huber_blocks(planes * H * W);
+  tv_partial_kernel<<<nb, kLThreads, 0, s>>>(img, (float*)ws, planes, H, W);
+  AST_CHECK_LAUNCH();
+  huber_final_kernel<<<1, kLThreads, 0, s>>>((const float*)ws, nb, loss, 1.f);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_tv_bwd(const float* img, const float* g_loss, float* g_img, int64_t planes, int H, int W,
+                          void* stream) {
+  if (!img || !g_loss || !g_img || planes <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  int64_t nb = (planes * H * W + kLThreads - 1) / kLThreads;
+  if (nb > 148 * 16) nb = 148 * 16;
+  tv_bwd_kernel<<<(unsigned)nb, kLThreads, 0, (cudaStream_t)stream>>>(img, g_loss, g_img, planes, H, W);
   AST_CHECK_LAUNCH();
   return 0;
 }

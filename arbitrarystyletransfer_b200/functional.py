@@ -198,6 +198,40 @@ def huber_loss(inp: torch.Tensor, tgt: torch.Tensor, scale: float = 1.0) -> torc
     return _Huber.apply(inp, tgt, scale)
 
 
+class _TV(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img):
+        lib = L.load()
+        L.require_cuda(img)
+        if img.dim() != 4:
+            raise L.AstError("tv_loss expects a 4-D (N, C, H, W) tensor")
+        img = _c(img.float())
+        N, Cc, H, W = img.shape
+        loss = torch.empty((), device=img.device, dtype=torch.float32)
+        wsb = lib.ast_huber_ws_bytes(img.numel())
+        ws = torch.empty(wsb, device=img.device, dtype=torch.uint8)
+        L.check(lib.ast_tv_fwd(img.data_ptr(), loss.data_ptr(), N * Cc, H, W, ws.data_ptr(), wsb,
+                               L.stream_ptr(img.device)), "ast_tv_fwd")
+        ctx.save_for_backward(img)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        (img,) = ctx.saved_tensors
+        N, Cc, H, W = img.shape
+        g = _c(g.float().reshape(1))
+        gi = torch.empty_like(img)
+        L.check(lib.ast_tv_bwd(img.data_ptr(), g.data_ptr(), gi.data_ptr(), N * Cc, H, W, L.stream_ptr(img.device)),
+                "ast_tv_bwd")
+        return gi
+
+
+def tv_loss(img: torch.Tensor) -> torch.Tensor:
+    """sum of squared horizontal and vertical neighbour differences (losses.py:90-103), 0-dim, differentiable."""
+    return _TV.apply(img)
+
+
 # "tf32": Gram forward on the tensor cores when the shape allows (default); "fp32": CUDA-core kernel
 # with 1e-6 agreement.  The reference computes torch.bmm in fp32 (losses.py:109); on Ampere+ GPUs
 # PyTorch itself may run that bmm in TF32 when torch.backends.cuda.matmul.allow_tf32 is set.

@@ -1,4 +1,4 @@
-"""Drop-in for the hot-path part of the reference's losses.py (losses.py:105-139).
+"""Drop-in for the hot-path part of the reference's losses.py (losses.py:90-139).
 
 Same names, argument meaning and return convention (0-dim tensors with autograd history); the
 device work is libast_b200's Huber / Gram / channel-statistics kernels."""
@@ -30,3 +30,9 @@ def compute_style_loss(t_cs_map: torch.Tensor, style_map: torch.Tensor) -> torch
     g_s = gram_matrix(style_map)
     gram_loss = Fn.huber_loss(g_c, g_s, 10.0)
     return mean_loss + std_loss + gram_loss
+
+
+def tv_loss(img: torch.Tensor) -> torch.Tensor:
+    """Total variation: sum of squared differences between horizontal and vertical neighbours, un-normalised --
+    losses.py:90-103 (train.py:266 weights it with args.tv_lam)."""
+    return Fn.tv_loss(img)

@@ -102,6 +102,11 @@ int ast_huber_fwd(const float* inp, const float* tgt, float* loss, int64_t n, fl
 int ast_huber_bwd(const float* inp, const float* tgt, const float* g_loss, float* g_inp,
                   int64_t n, float scale, void* stream);
 
+/* tv_loss (losses.py:90-103): loss[0] = sum of squared horizontal + vertical neighbour differences over
+ * `planes` = N*C images of H x W (fp32 NCHW); ws as for ast_huber_fwd.  Backward: g_img = g_loss[0] * d loss/d img. */
+int ast_tv_fwd(const float* img, float* loss, int64_t planes, int H, int W, void* ws, size_t ws_bytes, void* stream);
+int ast_tv_bwd(const float* img, const float* g_loss, float* g_img, int64_t planes, int H, int W, void* stream);
+
 /* gram_matrix (losses.py:105-109): G[b] = X[b] X[b]^T / (C*HW), X fp32 [B][C][HW] -> [B][C][C] */
 int ast_gram_fwd(const float* x, float* g, int B, int C, int64_t HW, void* stream);
 /* Same Gram matrix on the tensor cores in TF32 (inputs rounded to 10 mantissa bits, fp32

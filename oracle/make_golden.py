@@ -95,6 +95,10 @@ def golden_losses(Ls, out):
     l = Ls.compute_style_loss(a, b)                                       # losses.py:128-139
     l.backward()
     out["style_loss"], out["style_loss_ga"] = l.detach().numpy(), a.grad.numpy()
+    a.grad = None
+    l = Ls.tv_loss(a)                                                     # losses.py:90-103
+    (l * 0.37).backward()
+    out["tv_loss"], out["tv_loss_ga"] = l.detach().numpy(), a.grad.numpy()
 
 
 def golden_networks(M, out):

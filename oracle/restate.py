@@ -229,6 +229,13 @@ def huber_np(inp: np.ndarray, tgt: np.ndarray) -> float:
     return float(np.where(a < 1.0, 0.5 * d * d, a - 0.5).mean())
 
 
+def tv_loss(img):
+    """sum (x[..., :-1] - x[..., 1:])^2 + sum (x[..., :-1, :] - x[..., 1:, :])^2, un-normalised.  losses.py:90-103."""
+    w_variance = torch.sum(torch.pow(img[:, :, :, :-1] - img[:, :, :, 1:], 2))
+    h_variance = torch.sum(torch.pow(img[:, :, :-1, :] - img[:, :, 1:, :], 2))
+    return h_variance + w_variance
+
+
 def gram_matrix(tensor):
     """X X^T / (C*H*W), X = (B, C, HW).  losses.py:105-109."""
     B, C, H, W = tensor.shape

@@ -72,3 +72,25 @@ def test_huber_large_and_both_branches():
     got = Fn.huber_loss(a.cuda(), b.cuda()).item()
     assert got == pytest.approx(ref, rel=1e-5)
     assert Fn.huber_loss(a.cuda(), b.cuda(), 10.0).item() == pytest.approx(10 * ref, rel=1e-5)
+
+
+def test_tv_loss_golden_and_shapes(golden_losses):
+    """tv_loss (losses.py:90-103): the reference's golden value / gradient, then ragged shapes vs the oracle
+    (1-pixel-wide and 1-pixel-high images exercise the missing-neighbour cases)."""
+    from arbitrarystyletransfer_b200 import losses as Ls
+    g = golden_losses
+    a = T(g["loss_a"]).cuda().requires_grad_(True)
+    l = Ls.tv_loss(a)
+    assert l.dim() == 0 and l.item() == pytest.approx(float(g["tv_loss"]), rel=1e-5)
+    (l * 0.37).backward()
+    torch.testing.assert_close(a.grad.cpu(), T(g["tv_loss_ga"]), rtol=1e-5, atol=1e-6)
+    for shape in [(1, 3, 64, 48), (2, 3, 1, 17), (2, 5, 9, 1), (1, 1, 1, 1), (4, 3, 256, 256)]:
+        x = torch.rand(*shape, generator=torch.Generator().manual_seed(sum(shape)))
+        xr = x.clone().requires_grad_(True)
+        lr = R.tv_loss(xr)
+        lr.backward()
+        xg = x.cuda().requires_grad_(True)
+        lg = Ls.tv_loss(xg)
+        lg.backward()
+        assert lg.item() == pytest.approx(lr.item(), rel=2e-5, abs=1e-6), shape
+        torch.testing.assert_close(xg.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-6)

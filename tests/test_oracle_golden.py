@@ -98,6 +98,11 @@ def test_losses(golden_losses):
     assert l.item() == pytest.approx(float(g["style_loss"]), rel=1e-6)
     l.backward()
     torch.testing.assert_close(a.grad, T(g["style_loss_ga"]), rtol=1e-5, atol=1e-8)
+    a.grad = None
+    l = R.tv_loss(a)
+    assert l.item() == pytest.approx(float(g["tv_loss"]), rel=1e-6)
+    (l * 0.37).backward()
+    torch.testing.assert_close(a.grad, T(g["tv_loss_ga"]), rtol=1e-5, atol=1e-6)
 
 
 def test_vgg_taps_and_decoder(golden_networks):
