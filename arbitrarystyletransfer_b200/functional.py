@@ -232,8 +232,9 @@ def tv_loss(img: torch.Tensor) -> torch.Tensor:
     return _TV.apply(img)
 
 
-# "tf32": Gram forward on the tensor cores when the shape allows (default); "fp32": CUDA-core kernel
-# with 1e-6 agreement.  The reference computes torch.bmm in fp32 (losses.py:109); on Ampere+ GPUs
+# "tf32": Gram forward on the tensor cores in TF32 and Gram backward on the tensor cores with bf16 operands when
+# the shape allows (default; the gradient is rounded to bf16 anyway when it enters the VGG backward pass);
+# "fp32": CUDA-core kernels with 1e-6 agreement.  The reference computes torch.bmm in fp32 (losses.py:109); on Ampere+ GPUs
 # PyTorch itself may run that bmm in TF32 when torch.backends.cuda.matmul.allow_tf32 is set.
 GRAM_PRECISION = "tf32"
 
@@ -264,8 +265,16 @@ class _Gram(torch.autograd.Function):
         B, Cc, H, W = x.shape
         gg = _c(gg.float())
         gx = torch.empty_like(x)
-        L.check(lib.ast_gram_bwd(x.data_ptr(), gg.data_ptr(), gx.data_ptr(), B, Cc, H * W,
-                                 L.stream_ptr(x.device)), "ast_gram_bwd")
+        HW = H * W
+        if GRAM_PRECISION == "tf32" and Cc % 8 == 0 and HW % 8 == 0 and Cc >= 64 and HW >= 256:
+            # tensor-core backward: bf16 copies of X and of (gg + gg^T)/(C*HW) as MN-major operands, fp32 accumulate
+            wsb = lib.ast_gram_bwd_tc_ws_bytes(B, Cc, HW)
+            ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
+            L.check(lib.ast_gram_bwd_tc(x.data_ptr(), gg.data_ptr(), gx.data_ptr(), B, Cc, HW, ws.data_ptr(), wsb,
+                                        L.stream_ptr(x.device)), "ast_gram_bwd_tc")
+        else:
+            L.check(lib.ast_gram_bwd(x.data_ptr(), gg.data_ptr(), gx.data_ptr(), B, Cc, HW,
+                                     L.stream_ptr(x.device)), "ast_gram_bwd")
         return gx
 
 

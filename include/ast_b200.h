@@ -102,6 +102,13 @@ int ast_huber_fwd(const float* inp, const float* tgt, float* loss, int64_t n, fl
 int ast_huber_bwd(const float* inp, const float* tgt, const float* g_loss, float* g_inp,
                   int64_t n, float scale, void* stream);
 
+/* Gram backward on the tensor cores: gx[b] = (gg[b] + gg[b]^T) X[b] / (C*HW) with bf16 copies of both operands
+ * (MN-major UMMA operands straight from the NCHW tap), fp32 accumulation.  C % 8 == 0, HW % 8 == 0.
+ * ws: >= ast_gram_bwd_tc_ws_bytes(B, C, HW) bytes. */
+size_t ast_gram_bwd_tc_ws_bytes(int B, int C, int64_t HW);
+int ast_gram_bwd_tc(const float* x, const float* gg, float* gx, int B, int C, int64_t HW, void* ws, size_t ws_bytes,
+                    void* stream);
+
 /* tv_loss (losses.py:90-103): loss[0] = sum of squared horizontal + vertical neighbour differences over
  * `planes` = N*C images of H x W (fp32 NCHW); ws as for ast_huber_fwd.  Backward: g_img = g_loss[0] * d loss/d img. */
 int ast_tv_fwd(const float* img, float* loss, int64_t planes, int H, int W, void* ws, size_t ws_bytes, void* stream);

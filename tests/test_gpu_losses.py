@@ -94,3 +94,25 @@ def test_tv_loss_golden_and_shapes(golden_losses):
         lg.backward()
         assert lg.item() == pytest.approx(lr.item(), rel=2e-5, abs=1e-6), shape
         torch.testing.assert_close(xg.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 32), (1, 128, 16, 24), (3, 256, 16, 16), (1, 512, 8, 32), (2, 64, 64, 64)])
+def test_gram_backward_tensor_core(shape):
+    """Gram backward as a bf16 MN-major tcgen05 GEMM vs fp64: (gg + gg^T) X / (C*HW)."""
+    from arbitrarystyletransfer_b200 import functional as Fn
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, C, H, W, generator=g)
+    gg = torch.randn(B, C, C, generator=g)
+    X = x.double().view(B, C, H * W)
+    want = torch.bmm(gg.double() + gg.double().transpose(1, 2), X).view(B, C, H, W) / (C * H * W)
+    old = Fn.GRAM_PRECISION
+    try:
+        Fn.GRAM_PRECISION = "tf32"
+        xg = x.cuda().requires_grad_(True)
+        (Fn.gram_matrix(xg) * gg.cuda()).sum().backward()
+        got = xg.grad.cpu().double()
+    finally:
+        Fn.GRAM_PRECISION = old
+    err = ((got - want).norm() / want.norm()).item()
+    assert err < 6e-3, err      # bf16 operands: 2^-9 relative rounding of X and S, fp32 accumulation
