@@ -99,6 +99,17 @@ PROTOTYPES = {
     "ast_head_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_head_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_prep_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "ast_bgemm": (_i, [_vp, _i, _i, _i64, _vp, _i, _i, _i64, _vp, _i, _i64, _i64, _i, _i, _i, _i, _vp]),
+    "ast_attn_softmax": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp]),
+    "ast_attn_softmax_bwd": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _vp]),
+    "ast_attn_vv3": (_i, [_vp, _i64, _vp, _i64, _i, _vp]),
+    "ast_attn_vv5": (_i, [_vp, _i64, _vp, _i64, _i, _vp]),
+    "ast_attn_out_fwd": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i, _vp]),
+    "ast_attn_out_bwd": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp]),
+    "ast_split3_rows": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp]),
+    "ast_split3_nchw": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp]),
+    "ast_attn_dv": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _vp]),
+    "ast_axpby": (_i, [_vp, _vp, _f, _f, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -120,7 +120,7 @@ def channel_stats_flat(x: torch.Tensor, eps: float = 0.0, biased: bool = False):
 # ------------------------------------------------------------------------------------------
 class _MVN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, eps):
+    def forward(ctx, x, eps, biased=False):
         lib = L.load()
         L.require_cuda(x)
         x = _c(x)
@@ -128,7 +128,7 @@ class _MVN(torch.autograd.Function):
         HW = x[0, 0].numel()
         y = torch.empty_like(x)
         stats = torch.empty(N * Cc, 2, device=x.device, dtype=torch.float32)
-        fl = _flags(x)
+        fl = _flags(x, biased=biased)
         L.check(lib.ast_mvn_fwd(x.data_ptr(), y.data_ptr(), stats.data_ptr(), N * Cc, HW, float(eps),
                                 fl, L.stream_ptr(x.device)), "ast_mvn_fwd")
         ctx.save_for_backward(x, stats)
@@ -145,11 +145,17 @@ class _MVN(torch.autograd.Function):
         gx = torch.empty_like(x)
         L.check(lib.ast_mvn_bwd(x.data_ptr(), gy.data_ptr(), stats.data_ptr(), gx.data_ptr(), N * Cc,
                                 HW, ctx.fl, L.stream_ptr(x.device)), "ast_mvn_bwd")
-        return gx, None
+        return gx, None, None
 
 
 def mean_variance_norm(feat: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     return _MVN.apply(feat, eps)
+
+
+def instance_norm(feat: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """nn.InstanceNorm2d without affine / running statistics (models.py:78-80): the same fused kernel with the
+    BIASED variance, (x - mean) / sqrt(var_biased + eps) per (n, c); differentiable."""
+    return _MVN.apply(feat, eps, True)
 
 
 # ------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ from . import functional as Fn
 from .model_util import channel_stats  # re-exported like the reference's star import
 
 __all__ = ["AdaIN", "calc_mean_std", "mean_variance_norm", "PretrainedEncoder", "ClassicDecoder",
-           "StyleTransferNet", "channel_stats"]
+           "StyleTransferNet", "channel_stats", "AdaAttN", "AST", "Encoder", "Decoder", "DecoderBlock", "AutoEncoder"]
 
 
 class AdaIN(nn.Module):
@@ -334,3 +334,9 @@ def calibrate_encoder_bias(enc: PretrainedEncoder, n_convs: int = 9, size: int =
             conv.bias.copy_(-m.view(-1))
     finally:
         enc._content_layers = saved
+
+
+# The rest of the reference's ``models`` surface (``from models import *``, train.py:15): the MobileNet-style
+# networks (models.py:140-338) and the attention network (models.py:70-115, 393-582) live in their own modules.
+from .mobilenet import Encoder, Decoder, DecoderBlock, AutoEncoder  # noqa: E402,F401
+from .attention import AdaAttN, AST  # noqa: E402,F401

@@ -379,6 +379,47 @@ int ast_head_dgrad(const float* dY, const float* w, void* dx, int N, int H, int 
 /* fp32 [R][Cc] -> mode 0: bf16 [R][Cc]; 1: bf16 [Cc][R]; 2: fp32 [Cc][R]. */
 int ast_prep_weight(const float* w, void* out, int R, int Cc, int mode, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K6  AdaAttN (models.py:70-115).  The layer's contractions -- Q K^T (:97),
+ * P V and P V^2 (:101-103) and the five products of their backward pass -- run on one batched tcgen05 GEMM that
+ * reads either operand K-major or MN-major, so the NHWC activations are used as they lie in HBM; the passes
+ * between them are row-matrix streaming kernels.  All bf16 tensors are [rows][channels] with the given row stride.
+ * ------------------------------------------------------------------------------------- */
+
+/* d[b][i][j] = sum_k A(b,i,k) * B(b,j,k), bf16 operands, fp32 accumulation, d fp32 (d_bf16 = 0) or bf16.
+ * a_mn = 0: a is [M][K] (row stride ld_a); a_mn = 1: a is [K][M].  b_mn = 0: b is [N][K]; b_mn = 1: b is [K][N].
+ * ld_a, ld_b, a_bs, b_bs (batch strides, elements) multiples of 8; a, b 16-byte aligned; any M, N, K. */
+int ast_bgemm(const void* a, int a_mn, int ld_a, int64_t a_bs, const void* b, int b_mn, int ld_b, int64_t b_bs,
+              void* d, int d_bf16, int64_t ld_d, int64_t d_bs, int M, int N, int K, int batch, void* stream);
+/* p[r][:] = bf16(softmax(s[r][:])) (nn.Softmax(dim=-1), models.py:75, 99); lsum[r] = sum of the rounded weights. */
+int ast_attn_softmax(const float* s, int64_t ld_s, void* p, int64_t ld_p, float* lsum, int64_t rows, int cols,
+                     void* stream);
+/* ds[r][j] = p[r][j] * (da[r][j] - sum_j' da[r][j'] p[r][j'] / lsum[r]). */
+int ast_attn_softmax_bwd(const void* p, int64_t ld_p, const float* lsum, const float* da, int64_t ld_a, void* ds,
+                         int64_t ld_o, int64_t rows, int cols, void* stream);
+/* out[r] = [v | hi | lo] (3C bf16 per row), hi + lo = v^2 exactly. */
+int ast_attn_vv3(const void* v, int64_t ld_v, void* out, int64_t rows, int C, void* stream);
+/* out[r] = [v | v | hi | hi | lo] (5C): backward-pass partner of ast_attn_out_bwd's dmm. */
+int ast_attn_vv5(const void* v, int64_t ld_v, void* out, int64_t rows, int C, void* stream);
+/* mm = P [v | hi | lo] (fp32, 3C per row): mean = mm0/lsum, m2 = (mm1+mm2)/lsum;
+ * out = sqrt(relu(m2 - mean^2)) * cn + mean  (models.py:103, 115), bf16. */
+int ast_attn_out_fwd(const float* mm, const float* lsum, const void* cn, int64_t ld_cn, void* out, int64_t rows,
+                     int C, void* stream);
+/* From d(out): dmm[r] = [dMean_hi | dMean_lo | dM2_hi | dM2_lo | dM2_hi] (bf16, 5C per row: two-term splits of
+ * d mean and d m2, already divided by lsum) and dcn = d(out) * std. */
+int ast_attn_out_bwd(const float* mm, const float* lsum, const void* cn, int64_t ld_cn, const void* dout, void* dmm,
+                     void* dcn, int64_t rows, int C, void* stream);
+/* dv = (dvv0 + dvv1) + 2 v (dvv2 + dvv3)  (dvv = P^T dmm[:, :4C], fp32, 4C per row). */
+int ast_attn_dv(const float* dvv, const void* v, int64_t ld_v, void* dv, int64_t rows, int C, void* stream);
+/* Two-term bf16 split x = hi + lo of an fp32 row matrix / NCHW tensor into rows of 3C: pattern 0 [hi | lo | hi]
+ * (A side), pattern 1 [hi | hi | lo] (B side): one K = 3C GEMM of an A-side by a B-side matrix is the product to
+ * ~2^-17 -- used for the logits Q K^T and the 1x1 convolutions W_q, W_k in front of them (softmax exponentiates
+ * the logits' absolute error; models.py:87-88, 97 have no 1/sqrt(d) scaling). */
+int ast_split3_rows(const float* x, int64_t ld_x, void* out, int64_t rows, int C, int pattern, void* stream);
+int ast_split3_nchw(const float* x, void* out, int N, int C, int64_t HW, int pattern, void* stream);
+/* out = a*x + b*y (y nullable: a*x), fp32: the alpha blend of models.py:471 and its gradient. */
+int ast_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

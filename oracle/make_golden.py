@@ -260,6 +260,80 @@ def golden_autoencoder(M, out):
         out["act_eval_dec_of_code"] = ae3.decoder(z).numpy()
 
 
+def restore_ast(M, ast):
+    """Restore the two attributes AST.__init__ leaves commented out (models.py:407, 410) although encode / forward
+    / train.py use them -- with exactly the commented constructor calls."""
+    ast.ada_att_2 = M.AdaAttN(M.enc_out_channels)
+    ast.ada_out = M.DepthWiseConv(M.enc_out_channels * 2, M.enc_out_channels, 1, M.EXPAND_RATIO, use_norm=False,
+                                  use_identity=False)
+    return ast
+
+
+def golden_adaattn(M, out):
+    """Genuine ``AdaAttN`` (models.py:70-115) forward + gradients, and the genuine ``AST`` (models.py:393-575, with
+    ada_att_2 / ada_out restored) forward + one loss's gradients, on seeded inputs."""
+    from oracle import restate_ae as A, restate_attn as T
+    # ---- the layer alone: default init (flat attention) and sharpened (peaked attention), ragged style size ----
+    for tag, gain, (h, w, hs, ws) in (("flat", 1.0, (8, 8, 8, 8)), ("sharp", 36.0, (8, 12, 6, 10))):
+        torch.manual_seed(11)
+        layer = M.AdaAttN(32)
+        with torch.no_grad():
+            layer.W_q.weight.mul_(gain ** 0.5)
+            layer.W_k.weight.mul_(gain ** 0.5)
+        c = _t(601, 2, 32, h, w, scale=1.5, shift=0.5).requires_grad_(True)
+        s = _t(602, 2, 32, hs, ws, scale=2.0, shift=1.0).requires_grad_(True)
+        y = layer(c, s)
+        gy = _t(603, *y.shape)
+        y.backward(gy)
+        out[f"{tag}_content"], out[f"{tag}_style"], out[f"{tag}_gy"] = c.detach().numpy(), s.detach().numpy(), gy.numpy()
+        for n in ("W_q", "W_k", "W_v"):
+            out[f"{tag}_{n}"] = getattr(layer, n).weight.detach().numpy()
+            out[f"{tag}_g{n}"] = getattr(layer, n).weight.grad.numpy()
+        out[f"{tag}_out"] = y.detach().numpy()
+        out[f"{tag}_gcontent"], out[f"{tag}_gstyle"] = c.grad.numpy(), s.grad.numpy()
+    # ---- the network: non-degenerate seeded state (restate_ae.activate_gates) whose encoder running statistics are
+    # calibrated on the two images (momentum 1.0 for one training-mode pass): with FRESH running statistics the
+    # eval-mode encoder of AST.encode(detach=True) emits taps of ~5e-5, InstanceNorm's eps dominates their variance
+    # and the attention is uniform -- a fixture that pins nothing in the layer ----
+    sd = A.activate_gates(T.make_ast_state(3))
+    torch.manual_seed(5)
+    ast = restore_ast(M, M.AST())
+    ast.load_state_dict(sd, strict=True)
+    out["ast_state_keys"] = np.array(sorted(ast.state_dict().keys()))
+    c, s = R.rand_image(2, 64, 701), R.rand_image(2, 64, 702)
+    out["ast_content"], out["ast_style"] = c.numpy(), s.numpy()
+    bns = [m for m in ast._enc.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:
+        m.momentum = 1.0
+    ast._enc.train()
+    with torch.no_grad():
+        ast._enc(torch.cat((c, s)), out_layers=M.enc_out_layers)
+    for m in bns:
+        m.momentum = 0.1
+    sd = {k: v.detach().clone() for k, v in ast.state_dict().items()}
+    out["ast_buf_cal::_enc.mob_net.14._layers.8.running_var"] = sd["_enc.mob_net.14._layers.8.running_var"].numpy()
+    ast.train()
+    t_cs, t_ret, org = ast(c, s, alpha=0.75)
+    loss = torch.nn.functional.huber_loss(t_cs, s) + 0.5 * torch.nn.functional.huber_loss(org, c) + 0.1 * t_ret.mean()
+    loss.backward()
+    out["ast_t_cs"], out["ast_t_return"], out["ast_org_out"] = t_cs.detach().numpy(), t_ret.detach().numpy(), org.detach().numpy()
+    out["ast_loss"] = np.array(loss.item())
+    named = dict(ast.named_parameters())
+    gk = sorted(k for k, p in named.items() if p.grad is not None)
+    out["ast_grad_keys"] = np.array(gk)
+    out["ast_grad_norm"] = np.array([named[k].grad.double().norm().item() for k in gk])
+    for k in T.GOLDEN_GRAD_KEYS:
+        out["ast_grad::" + k] = named[k].grad.numpy()
+    out["ast_buf::_enc.mob_net.1._layers.1.running_mean"] = ast.state_dict()["_enc.mob_net.1._layers.1.running_mean"].numpy()
+    # exporting network: encode without detach + Hardtanh head (models.py:304, 315-316, 478-479)
+    torch.manual_seed(5)
+    ast_e = restore_ast(M, M.AST(exporting=True))
+    ast_e.load_state_dict(sd, strict=True)
+    ast_e.eval()
+    with torch.no_grad():
+        out["ast_export_t_cs"] = ast_e(c, s).numpy()
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present: golden vectors can only be made in the build container")
@@ -272,7 +346,10 @@ def main():
     for name, fn, args in (("stats_adain", golden_stats_adain, (M, mu)),
                            ("losses", golden_losses, (Ls,)),
                            ("networks", golden_networks, (M,)),
-                           ("autoencoder", golden_autoencoder, (M,))):
+                           ("autoencoder", golden_autoencoder, (M,)),
+                           ("adaattn", golden_adaattn, (M,))):
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         d = dict(_versions())
         fn(*args, d)
         path = os.path.join(OUT, f"{name}.npz")
