@@ -217,7 +217,8 @@ static int gemm_tn_bf16(const void* a, int ld_a, int Ca, int64_t a_bs, const voi
   if (accumulate) {
     split = 148 / ((int64_t)m_blocks * n_blocks * batch);
     if (split < 1) split = 1;
-    if (split > p.chunks) split = p.chunks;
+    if (split > p.chunks / 4) split = p.chunks / 4;     // >= 4 K chunks per CTA: the 128 x BN atomic epilogue must amortise
+    if (split < 1) split = 1;
   }
   p.split = (int)split;
   if (split * batch >= 0x7fffffffLL) return AST_E_SHAPE;

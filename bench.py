@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the config-2 training-step timing")
     ap.add_argument("--no-train-ae", action="store_true", help="skip the config-3 autoencoder training-step timing")
+    ap.add_argument("--no-train-ast", action="store_true", help="skip the AST (AdaAttN network) training-step timing")
     ap.add_argument("--layers-out", default="", help="write the per-layer timing table (JSON) here")
     return ap.parse_args()
 
@@ -511,6 +512,169 @@ def time_train_ae(dev, rank, world, steps=6, warmup=3, global_batch=32, size=256
                       "clip 10, Adam(2e-4, b2 .99, eps 1e-7), per-shard BatchNorm statistics"}
 
 
+def _nondegenerate_(net):
+    """Synthetic-weight recipe for the MobileNet-style blocks (the same one the parity fixtures use, see
+    oracle/restate_ae.py::activate_gates): the reference's fresh initialisation leaves every SE gate closed and every
+    depthwise conv at gain ~0.07, so the network outputs exactly its head bias; constant images make the style
+    loss's std gradient singular.  SE biases 0.5 / 0.25, depthwise weights x sqrt(C/2)."""
+    with torch.no_grad():
+        for k, v in net.state_dict().items():
+            if k.endswith(".fc.2.bias"):
+                v.fill_(0.5)
+            elif k.endswith(".fc.0.bias"):
+                v.fill_(0.25)
+            elif v.dim() == 4 and v.shape[1] == 1 and v.shape[2] > 1:
+                v.mul_((v.shape[0] / 2.0) ** 0.5)
+
+
+def build_ast_step(dev, c, s):
+    """(step, net) for time_train_ast: a fresh AST + frozen VGG + Adam and the train.py:189-300 step closure."""
+    from arbitrarystyletransfer_b200 import models as M, losses as Ls, attention as AT
+    torch.manual_seed(0)
+    enc = M.PretrainedEncoder().to(dev).eval()
+    M.calibrate_encoder_bias(enc, n_convs=16)
+    for p in enc.parameters():
+        p.requires_grad_(False)
+    torch.manual_seed(3)
+    net = AT.AST().to(dev).train()
+    _nondegenerate_(net)
+    bns = [m for m in net._enc.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:                                  # running statistics of the eval-mode passes: calibrated
+        m.momentum = 1.0
+    with torch.no_grad():
+        net._enc(torch.cat((c, s)), out_layers=AT.enc_out_layers)
+    for m in bns:
+        m.momentum = 0.1
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4, betas=(0.9, 0.999), eps=1e-5, capturable=True, fused=True)
+    sw = (1.0, 1.0, 1.0, 1.0, 0.75, 0.5)
+
+    def step(c, s):
+        stylized, t, org_out = net(c, s)                                           # train.py:189
+        with torch.no_grad():
+            content_map, style_map = enc(c), enc(s)                                # :191-192
+        t_cs_map, org_out_map = enc(stylized), enc(org_out)                        # :193-194
+        content_loss = style_loss = org_loss = None
+        for i in range(len(t_cs_map)):                                             # :217-244
+            cl = Ls.compute_content_loss(M.mean_variance_norm(t_cs_map[i]), M.mean_variance_norm(content_map[i]))
+            sl = Ls.compute_style_loss(t_cs_map[i], style_map[i]) * sw[i]
+            ol = Ls.compute_content_loss(org_out_map[i], content_map[i])           # :248-255
+            content_loss = cl if content_loss is None else content_loss + cl
+            style_loss = sl if style_loss is None else style_loss + sl
+            org_loss = ol if org_loss is None else org_loss + ol
+        content_loss = content_loss + Ls.compute_content_loss(M.mean_variance_norm(stylized),
+                                                              M.mean_variance_norm(c)) * 0.1          # :258
+        oor = Ls.compute_content_loss(stylized, torch.clip(stylized.detach(), 0.0, 1.0)) * 1e8     # :259
+        org_loss = (org_loss + ((c - org_out) ** 2).mean() * 100) * 0.5                               # :268-270
+        style_loss = style_loss + Ls.compute_style_loss(stylized, s)                                 # :271
+        loss = 1.25 * content_loss + 0.5 * style_loss + 6e-4 * Ls.tv_loss(stylized) + org_loss + oor  # :283
+        opt.zero_grad(set_to_none=True)                                             # :287
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 2.0)                       # :292
+        opt.step()
+        return loss
+    return step, net
+
+
+def cpu_ast_sample(size=256):
+    """CPU comparator for the AST step (kind "port"): AST.forward (models.py:425-533) + backward of the image-space
+    terms on ONE content/style pair through the oracle restatement, all host threads, fp32."""
+    from oracle import restate_ae as A, restate_attn as T
+    import torch.nn.functional as F
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = A.clone_state(A.activate_gates(T.make_ast_state(3)), requires_grad=True)
+    g = torch.Generator().manual_seed(801)
+    c, s = torch.rand(1, 3, size, size, generator=g), torch.rand(1, 3, size, size, generator=g)
+    t0 = time.perf_counter()
+    t_cs, t_ret, org = T.ast_forward(P, c, s)
+    (F.huber_loss(t_cs, s) + F.huber_loss(org, c)).backward()
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"AST.forward + backward (image-space Huber terms only, no VGG taps) of the oracle restatement "
+                      f"on 1 pair at {size}x{size} (fp32, torch {torch.__version__} CPU), {dt:.1f} s"}
+
+
+def time_train_ast(dev, steps=6, warmup=3, batch=8, size=256, cpu=False):
+    """the train.py:189-300 step on the AdaAttN network ``AST`` -- batch 8 (train.py's
+    default) at 256x256: AST.forward (two eval-mode encoder passes, two AdaAttN layers, ada_out, a train-mode encoder
+    pass, two decoder passes), four PretrainedEncoder passes (6 taps), MVN content loss, mean/std + Gram style loss,
+    perceptual + MSE reconstruction loss, image-level terms, out-of-range and TV loss, clip 2.0, Adam(2e-4, eps 1e-5).
+    Not included: compute_hist_loss (not built) and the local-feature term (train.py:274-277 indexes a
+    tensor where a list is meant and raises in the reference)."""
+    from arbitrarystyletransfer_b200 import models as M, losses as Ls, attention as AT
+    g = torch.Generator().manual_seed(801)
+    c = torch.rand(batch, 3, size, size, generator=g).to(dev)
+    s = torch.rand(batch, 3, size, size, generator=g).to(dev)
+
+    def build():
+        return build_ast_step(dev, c, s)
+
+    def timeit(fn, n=steps):
+        for _ in range(warmup):
+            loss = fn(c, s)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            loss = fn(c, s)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n, loss
+
+    mode, ms = None, None
+    try:
+        from arbitrarystyletransfer_b200.graphs import GraphedStep
+        step, net = build()
+        gstep = GraphedStep(step, [c.clone(), s.clone()])
+        ms, loss = timeit(gstep)
+        mode = "whole step (fwd + bwd + clip + Adam) replayed from one CUDA graph"
+        del gstep, step
+    except Exception as e:
+        mode = "eager (graph capture failed: " + repr(e)[:160] + ")"
+    step, net = build()
+    ms_eager, loss_e = timeit(step)
+    if ms is None:
+        ms, loss = ms_eager, loss_e
+    # inference: AST(exporting) forward on the same batch, and one AdaAttN layer alone at the network's shape
+    net_e = AT.AST(exporting=True).to(dev).eval()
+    net_e.load_state_dict(net.state_dict())
+    with torch.no_grad():
+        ms_fwd, _ = timeit(net_e, 10)
+        h = size // 8
+        layer = net_e.ada_att_1
+        fc = torch.randn(batch, 128, h, h, device=dev)
+        fs = torch.randn(batch, 128, h, h, device=dev) * 2 + 1
+        ms_layer, _ = timeit(lambda a, b: layer(fc, fs), 20)
+    fcg, fsg = fc.clone().requires_grad_(True), fs.clone().requires_grad_(True)
+    lay = net.ada_att_1
+
+    def layer_fb(a, b):
+        y = lay(fcg, fsg)
+        y.backward(fc)
+        return y
+    ms_layer_fb, _ = timeit(layer_fb, 20)
+    hw = h * h
+    layer_flops = batch * (2.0 * hw * hw * 128 * 3 + 3 * 2.0 * hw * 128 * 128)   # QK^T + P[v|v^2] + W_q,k,v
+    cpu_res = None
+    if cpu:
+        try:
+            cpu_res = cpu_ast_sample(size)
+        except Exception as e:
+            cpu_res = {"error": repr(e)[:200]}
+    return {"metric": "train_steps_per_s_256x256_b8_ast", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms,
+            "img_per_s": batch * 1e3 / ms, "loss_finite": bool(torch.isfinite(loss).item()), "mode": mode,
+            "eager_steps_per_s": 1e3 / ms_eager,
+            "inference": {"img_per_s": batch * 1e3 / ms_fwd, "ms": ms_fwd,
+                          "what": "AST(exporting=True).forward, batch 8 at 256x256, eval mode"},
+            "adaattn_layer": {"shape": [batch, 128, h, h], "fwd_ms": ms_layer, "fwd_bwd_ms": ms_layer_fb,
+                              "algorithmic_gflop_fwd": layer_flops / 1e9,
+                              "fwd_tflops": layer_flops / (ms_layer * 1e-3) / 1e12,
+                              "note": "launch/latency-bound at this size (17 small launches forward)"},
+            "cpu_baseline": cpu_res,
+            "config": f"SURVEY 8 f1: train.py:189-300 step on AST (AdaAttN network), batch {batch} at {size}x{size}, "
+                      "6 VGG taps x 4 images, MVN content + mean/std/Gram style + reconstruction + TV + out-of-range "
+                      "losses, clip 2.0, Adam(2e-4); hist / local-feature terms excluded (see docstring)"}
+
+
 def _dec_flops(size):
     from arbitrarystyletransfer_b200.engine import DECODER_SPEC
     h, f = size // 8, 0.0
@@ -647,6 +811,12 @@ def run_native(args):
                 raise
             tae = {"error": repr(e)[:300]}
         line["train_ae"] = tae
+    if world == 1 and not args.no_train_ast:
+        torch.cuda.empty_cache()
+        try:
+            line["train_ast"] = time_train_ast(dev, cpu=not args.no_cpu_baseline)
+        except Exception as e:
+            line["train_ast"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
