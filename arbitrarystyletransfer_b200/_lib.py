@@ -51,6 +51,9 @@ PROTOTYPES = {
     "ast_huber_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _vp]),
     "ast_gram_bwd_tc_ws_bytes": (_sz, [_i, _i, _i64]),
     "ast_gram_bwd_tc": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _sz, _vp]),
+    "ast_hist_ws_bytes": (_sz, [_i]),
+    "ast_hist_loss_fwd": (_i, [_vp, _vp, _i, _i64, _i64, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "ast_hist_loss_bwd": (_i, [_vp, _vp, _vp, _f, _f, _vp, _i, _i64, _vp]),
     "ast_tv_fwd": (_i, [_vp, _vp, _i64, _i, _i, _vp, _sz, _vp]),
     "ast_tv_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
     "ast_gram_fwd": (_i, [_vp, _vp, _i, _i, _i64, _vp]),

@@ -238,6 +238,50 @@ def tv_loss(img: torch.Tensor) -> torch.Tensor:
     return _TV.apply(img)
 
 
+class _HistLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        lib = L.load()
+        L.require_cuda(x, y)
+        if x.dim() != 4 or y.dim() != 4 or x.shape[0] != y.shape[0]:
+            raise L.AstError("compute_hist_loss expects two 4-D (B, C, H, W) tensors with the same batch size")
+        x, y = _c(x.float()), _c(y.float())
+        B = x.shape[0]
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        gd = torch.empty(B, 256, device=x.device, dtype=torch.float32)
+        wsb = lib.ast_hist_ws_bytes(B)
+        ws = torch.empty((wsb + 7) // 8, device=x.device, dtype=torch.int64)
+        ctx.norms = (float(x.shape[1] * x.shape[2]), float(y.shape[1] * y.shape[2]))     # losses.py:54
+        L.check(lib.ast_hist_loss_fwd(x.data_ptr(), y.data_ptr(), B, x[0].numel(), y[0].numel(), ctx.norms[0],
+                                      ctx.norms[1], loss.data_ptr(), gd.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                      L.stream_ptr(x.device)), "ast_hist_loss_fwd")
+        ctx.save_for_backward(x, y, gd)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        x, y, gd = ctx.saved_tensors
+        g = _c(g.float().reshape(1))
+        out = []
+        for i, (t, sign) in enumerate(((x, 1.0), (y, -1.0))):
+            if not ctx.needs_input_grad[i]:
+                out.append(None)
+                continue
+            gt = torch.empty_like(t)
+            L.check(lib.ast_hist_loss_bwd(t.data_ptr(), gd.data_ptr(), g.data_ptr(), sign, ctx.norms[i],
+                                          gt.data_ptr(), t.shape[0], t[0].numel(), L.stream_ptr(t.device)),
+                    "ast_hist_loss_bwd")
+            out.append(gt)
+        return tuple(out)
+
+
+def hist_loss(t_cs: torch.Tensor, style_map: torch.Tensor) -> torch.Tensor:
+    """compute_hist_loss (losses.py:82-87): mean over the batch of the squared EMD between the soft 256-bin histograms
+    of the two tensors; 0-dim, differentiable in both arguments."""
+    return _HistLoss.apply(t_cs, style_map)
+
+
 # "tf32": Gram forward on the tensor cores in TF32 and Gram backward on the tensor cores with bf16 operands when
 # the shape allows (default; the gradient is rounded to bf16 anyway when it enters the VGG backward pass);
 # "fp32": CUDA-core kernels with 1e-6 agreement.  The reference computes torch.bmm in fp32 (losses.py:109); on Ampere+ GPUs

@@ -36,3 +36,11 @@ def tv_loss(img: torch.Tensor) -> torch.Tensor:
     """Total variation: sum of squared differences between horizontal and vertical neighbours, un-normalised --
     losses.py:90-103 (train.py:266 weights it with args.tv_lam)."""
     return Fn.tv_loss(img)
+
+
+def compute_hist_loss(t_cs: torch.Tensor, style_map: torch.Tensor) -> torch.Tensor:
+    """Squared earth mover's distance between the soft 256-bin histograms of the two tensors (all C*H*W values of
+    each sample in one histogram, normalised by C*H as the reference does), averaged over the batch --
+    losses.py:8-87 (train.py:261 weights it with 1e-5).  One fused pass per tensor; the reference's
+    (B, 256, C*H*W) intermediates are never formed."""
+    return Fn.hist_loss(t_cs, style_map)

@@ -566,7 +566,8 @@ def build_ast_step(dev, c, s):
         oor = Ls.compute_content_loss(stylized, torch.clip(stylized.detach(), 0.0, 1.0)) * 1e8     # :259
         org_loss = (org_loss + ((c - org_out) ** 2).mean() * 100) * 0.5                               # :268-270
         style_loss = style_loss + Ls.compute_style_loss(stylized, s)                                 # :271
-        loss = 1.25 * content_loss + 0.5 * style_loss + 6e-4 * Ls.tv_loss(stylized) + org_loss + oor  # :283
+        hist = Ls.compute_hist_loss(stylized, s) * 1e-5                                              # :261
+        loss = 1.25 * content_loss + 0.5 * style_loss + 6e-4 * Ls.tv_loss(stylized) + hist + org_loss + oor  # :283
         opt.zero_grad(set_to_none=True)                                             # :287
         loss.backward()
         torch.nn.utils.clip_grad_norm_(net.parameters(), 2.0)                       # :292
@@ -597,9 +598,9 @@ def time_train_ast(dev, steps=6, warmup=3, batch=8, size=256, cpu=False):
     """the train.py:189-300 step on the AdaAttN network ``AST`` -- batch 8 (train.py's
     default) at 256x256: AST.forward (two eval-mode encoder passes, two AdaAttN layers, ada_out, a train-mode encoder
     pass, two decoder passes), four PretrainedEncoder passes (6 taps), MVN content loss, mean/std + Gram style loss,
-    perceptual + MSE reconstruction loss, image-level terms, out-of-range and TV loss, clip 2.0, Adam(2e-4, eps 1e-5).
-    Not included: compute_hist_loss (not built) and the local-feature term (train.py:274-277 indexes a
-    tensor where a list is meant and raises in the reference)."""
+    perceptual + MSE reconstruction loss, image-level terms, histogram (EMD), out-of-range and TV loss, clip 2.0,
+    Adam(2e-4, eps 1e-5).  Not included: the local-feature term (train.py:274-277 indexes a tensor where a list is
+    meant and raises in the reference)."""
     from arbitrarystyletransfer_b200 import models as M, losses as Ls, attention as AT
     g = torch.Generator().manual_seed(801)
     c = torch.rand(batch, 3, size, size, generator=g).to(dev)
@@ -671,8 +672,8 @@ def time_train_ast(dev, steps=6, warmup=3, batch=8, size=256, cpu=False):
                               "note": "launch/latency-bound at this size (17 small launches forward)"},
             "cpu_baseline": cpu_res,
             "config": f"SURVEY 8 f1: train.py:189-300 step on AST (AdaAttN network), batch {batch} at {size}x{size}, "
-                      "6 VGG taps x 4 images, MVN content + mean/std/Gram style + reconstruction + TV + out-of-range "
-                      "losses, clip 2.0, Adam(2e-4); hist / local-feature terms excluded (see docstring)"}
+                      "6 VGG taps x 4 images, MVN content + mean/std/Gram style + reconstruction + histogram + TV + "
+                      "out-of-range losses, clip 2.0, Adam(2e-4); local-feature term excluded (see docstring)"}
 
 
 def _dec_flops(size):

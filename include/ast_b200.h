@@ -109,6 +109,18 @@ size_t ast_gram_bwd_tc_ws_bytes(int B, int C, int64_t HW);
 int ast_gram_bwd_tc(const float* x, const float* gg, float* gx, int B, int C, int64_t HW, void* ws, size_t ws_bytes,
                     void* stream);
 
+/* compute_hist_loss (losses.py:8-87): squared earth mover's distance between the soft 256-bin
+ * histograms (sigmoid-difference bins, L = 1/256, W = L/2.5) of two fp32 image batches x (B, nx elements each) and
+ * y (B, ny), averaged over the batch; norm_* = the reference's normaliser x.size(1) * x.size(2).  32.32 fixed-point
+ * integer accumulation (bit-deterministic); no (B, 256, C*H*W) intermediate.  gd[B][256] = d loss / d cdf_x is saved
+ * for the backward pass.  ws: >= ast_hist_ws_bytes(B) bytes, 8-byte aligned.
+ * Backward: gx = sign * g_loss[0] * d loss / d x (sign +1: first argument, -1: second, with its own norm). */
+size_t ast_hist_ws_bytes(int B);
+int ast_hist_loss_fwd(const float* x, const float* y, int B, int64_t nx, int64_t ny, float norm_x, float norm_y,
+                      float* loss, float* gd, void* ws, size_t ws_bytes, void* stream);
+int ast_hist_loss_bwd(const float* x, const float* gd, const float* g_loss, float sign, float norm, float* gx, int B,
+                      int64_t n, void* stream);
+
 /* tv_loss (losses.py:90-103): loss[0] = sum of squared horizontal + vertical neighbour differences over
  * `planes` = N*C images of H x W (fp32 NCHW); ws as for ast_huber_fwd.  Backward: g_img = g_loss[0] * d loss/d img. */
 int ast_tv_fwd(const float* img, float* loss, int64_t planes, int H, int W, void* ws, size_t ws_bytes, void* stream);

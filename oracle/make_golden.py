@@ -260,6 +260,20 @@ def golden_autoencoder(M, out):
         out["act_eval_dec_of_code"] = ae3.decoder(z).numpy()
 
 
+def golden_hist(Ls, out):
+    """compute_hist_loss (losses.py:8-87) value and input gradients from the genuine reference: image-like inputs with
+    a few values outside [0, 1] (a stylised image is not clamped, models.py:315)."""
+    for tag, shape, seed in (("a", (2, 3, 24, 20), 61), ("b", (3, 3, 16, 16), 63)):
+        g = torch.Generator().manual_seed(seed)
+        x = (torch.rand(*shape, generator=g) * 1.2 - 0.1).requires_grad_(True)
+        y = (torch.rand(*shape, generator=g) ** 2).requires_grad_(True)
+        l = Ls.compute_hist_loss(x, y)
+        (l * 0.5).backward()
+        out[f"hist_{tag}_x"], out[f"hist_{tag}_y"] = x.detach().numpy(), y.detach().numpy()
+        out[f"hist_{tag}_loss"] = l.detach().numpy()
+        out[f"hist_{tag}_gx"], out[f"hist_{tag}_gy"] = x.grad.numpy(), y.grad.numpy()
+
+
 def restore_ast(M, ast):
     """Restore the two attributes AST.__init__ leaves commented out (models.py:407, 410) although encode / forward
     / train.py use them -- with exactly the commented constructor calls."""
@@ -347,7 +361,8 @@ def main():
                            ("losses", golden_losses, (Ls,)),
                            ("networks", golden_networks, (M,)),
                            ("autoencoder", golden_autoencoder, (M,)),
-                           ("adaattn", golden_adaattn, (M,))):
+                           ("adaattn", golden_adaattn, (M,)),
+                           ("hist", golden_hist, (Ls,))):
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         d = dict(_versions())

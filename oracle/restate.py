@@ -236,6 +236,36 @@ def tv_loss(img):
     return h_variance + w_variance
 
 
+HIST_K = 256                      # losses.py:42-46 (HistLayerBase): K bins of width L = 1/K over [0, 1], W = L / 2.5
+HIST_L = 1.0 / HIST_K
+HIST_W = HIST_L / 2.5
+
+
+def soft_histogram(x, chunk: int = 1 << 14):
+    """SingleDimHistLayer.forward, losses.py:49-56 (+ compute_pj / phi_k, :24-37): per image, over ALL C*H*W
+    elements, hist_k = sum_i [sigmoid((x_i - mu_k + L/2)/W) - sigmoid((x_i - mu_k - L/2)/W)] / N with
+    N = x.size(1) * x.size(2) = C*H (the reference's normaliser, not C*H*W).  Same arithmetic as the reference, but
+    the (B, 256, C*H*W) tensor it materialises is walked in chunks of elements."""
+    B = x.size(0)
+    N = x.size(1) * x.size(2)
+    mu_k = (HIST_L * (torch.arange(HIST_K, dtype=x.dtype) + 0.5)).view(1, -1, 1)
+    flat = x.reshape(B, 1, -1)
+    hist = torch.zeros(B, HIST_K, dtype=x.dtype)
+    for i in range(0, flat.size(2), chunk):
+        d = flat[:, :, i:i + chunk] - mu_k
+        hist = hist + (torch.sigmoid((d + HIST_L / 2) / HIST_W) - torch.sigmoid((d - HIST_L / 2) / HIST_W)).sum(dim=2)
+    return hist / N
+
+
+def compute_hist_loss(t_cs, style_map):
+    """losses.py:82-87: squared earth mover's distance between the two soft histograms -- sum over bins of the
+    squared difference of their cumulative sums (EarthMoversDistanceLoss, :8-22: matmul with the upper-triangular
+    ones matrix) -- averaged over the batch."""
+    hx, hy = soft_histogram(t_cs), soft_histogram(style_map)
+    tt = torch.triu(torch.ones(HIST_K, HIST_K, dtype=hx.dtype))          # tt[s][t] = (t >= s)
+    return torch.sum(torch.square(hx @ tt - hy @ tt), dim=1).mean()
+
+
 def gram_matrix(tensor):
     """X X^T / (C*H*W), X = (B, C, HW).  losses.py:105-109."""
     B, C, H, W = tensor.shape

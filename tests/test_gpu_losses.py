@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from oracle import restate as R
+from tests.gpu_util import rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -116,3 +117,39 @@ def test_gram_backward_tensor_core(shape):
         Fn.GRAM_PRECISION = old
     err = ((got - want).norm() / want.norm()).item()
     assert err < 6e-3, err      # bf16 operands: 2^-9 relative rounding of X and S, fp32 accumulation
+
+
+def test_hist_loss_golden_oracle_and_determinism():
+    """compute_hist_loss (losses.py:8-87): the reference's golden values / gradients (out-of-range values included),
+    then train.py's size (8 x 3 x 256 x 256, where the reference would materialise 2 x 1.6 GB) against the chunked
+    fp64 oracle; integer accumulation makes the result bit-deterministic."""
+    from arbitrarystyletransfer_b200 import losses as Ls
+    from tests.conftest import load_golden
+    g = load_golden("hist")
+    for tag in "ab":
+        x = T(g[f"hist_{tag}_x"]).cuda().requires_grad_(True)
+        y = T(g[f"hist_{tag}_y"]).cuda().requires_grad_(True)
+        l = Ls.compute_hist_loss(x, y)
+        assert l.dim() == 0 and l.item() == pytest.approx(float(g[f"hist_{tag}_loss"]), rel=2e-5)
+        (l * 0.5).backward()
+        for got, ref in ((x.grad, T(g[f"hist_{tag}_gx"])), (y.grad, T(g[f"hist_{tag}_gy"]))):
+            assert rel_err(got.cpu(), ref) < 1e-4
+            torch.testing.assert_close(got.cpu(), ref, rtol=1e-3, atol=1e-4 * float(ref.abs().max()))
+    gen = torch.Generator().manual_seed(77)
+    x = torch.rand(8, 3, 256, 256, generator=gen) * 1.1 - 0.05
+    y = torch.rand(8, 3, 256, 256, generator=gen) ** 1.5
+    xr = x[:2].double().requires_grad_(True)
+    lr = R.compute_hist_loss(xr, y[:2].double())
+    lr.backward()
+    xg = x[:2].cuda().requires_grad_(True)
+    lg = Ls.compute_hist_loss(xg, y[:2].cuda())
+    lg.backward()
+    assert lg.item() == pytest.approx(lr.item(), rel=2e-5)
+    assert rel_err(xg.grad.cpu(), xr.grad.float()) < 1e-4
+    a = Ls.compute_hist_loss(x.cuda(), y.cuda())
+    b = Ls.compute_hist_loss(x.cuda(), y.cuda())
+    assert torch.equal(a, b) and torch.isfinite(a)
+    assert Ls.compute_hist_loss(y.cuda(), y.cuda()).item() == 0.0
+    bad = x.clone()
+    bad[3, 1, 5, 5] = float("nan")
+    assert torch.isnan(Ls.compute_hist_loss(bad.cuda(), y.cuda()))

@@ -131,3 +131,22 @@ def test_stylize_64(golden_networks):
         img = R.stylize(c, s, vw, vb, dw, db)
     assert torch.isfinite(img).all()
     assert R.psnr(img, T(g["s64_img"])) > 80.0
+
+
+def test_hist_loss_restatement_matches_reference_golden():
+    """compute_hist_loss (losses.py:8-87): value and both input gradients, bit for bit in one chunk and to fp32
+    round-off when the element axis is walked in chunks."""
+    from tests.conftest import load_golden
+    g = load_golden("hist")
+    for tag in "ab":
+        x = T(g[f"hist_{tag}_x"]).clone().requires_grad_(True)
+        y = T(g[f"hist_{tag}_y"]).clone().requires_grad_(True)
+        l = R.compute_hist_loss(x, y)
+        assert l.item() == float(g[f"hist_{tag}_loss"])
+        (l * 0.5).backward()
+        torch.testing.assert_close(x.grad, T(g[f"hist_{tag}_gx"]), rtol=0, atol=0)
+        torch.testing.assert_close(y.grad, T(g[f"hist_{tag}_gy"]), rtol=0, atol=0)
+        h = R.soft_histogram(x.detach(), chunk=100)
+        torch.testing.assert_close(h, R.soft_histogram(x.detach()), rtol=1e-5, atol=1e-6)
+        # N = C*H (losses.py:54), not C*H*W: the bins of one image sum to W
+        assert h.sum(1).mean().item() == pytest.approx(x.shape[3] * ((x.detach() > 0.02) & (x.detach() < 0.98)).float().mean().item(), rel=0.1)
