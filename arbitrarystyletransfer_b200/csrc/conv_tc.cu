@@ -1003,8 +1003,13 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
   return 0;
 }
 
-// Last decoder layer (Cin % 64 == 0, Cout <= 16): the implicit-GEMM kernel with a 16-wide N block
-// (weights zero-padded to 16 output channels) and the fp32 NCHW epilogue.
+int conv3x3_last_tn(const void* in, const void* wpk16, const float* bias, float* out, int N, int H, int W, int Cout,
+                    int clamp01, int sm_count, cudaStream_t s);   // conv_last_tn.cu
+
+// Last decoder layer (Cin % 64 == 0, Cout <= 16).  Cin == 64, Cout <= 3 (the decoder's image layer and the image
+// gradient of the VGG backward pass): the taps-in-N kernel of conv_last_tn.cu.  Otherwise -- or with
+// AST_LAST_TAPS_IN_K=1 / the tap-box implementation, kept as A/B references -- the implicit-GEMM kernel with a
+// 16-wide N block (weights zero-padded to 16 output channels) and the fp32 NCHW epilogue.
 int conv3x3_last_tc(const void* in, const void* wpk16, const float* bias, float* out, int N, int H,
                     int W, int Cin, int Cout, int clamp01, int kwbox, cudaStream_t s) {
   if (Cin % 64 != 0 || Cout > 16 || H < 1 || W < 1) return AST_E_SHAPE;
@@ -1012,6 +1017,9 @@ int conv3x3_last_tc(const void* in, const void* wpk16, const float* bias, float*
   int sm_count = 0;
   int r = get_sm_count(&sm_count);
   if (r) return r;
+  static const bool taps_in_k = getenv("AST_LAST_TAPS_IN_K") != nullptr;
+  if (kwbox && Cin == 64 && Cout <= 3 && !taps_in_k)
+    return conv3x3_last_tn(in, wpk16, bias, out, N, H, W, Cout, clamp01, sm_count, s);
   ConvParams p = {};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = 16; p.Ho = H; p.Wo = W;
   p.relu = 0; p.halo = AST_HALO_KEEP;
