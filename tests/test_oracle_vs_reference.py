@@ -97,3 +97,31 @@ def test_autoencoder_restatement_live(ref):
         dsd = {"decoder." + k: v for k, v in dec.state_dict().items()}
         z = torch.randn(1, 128, 3, 5, generator=torch.Generator().manual_seed(3))
         assert torch.equal(dec(z), A.decoder_forward(dsd, z, exporting=True))
+
+
+def test_adaattn_ast_and_hist_restatements_live(ref):
+    """oracle/restate_attn.py vs the genuine AdaAttN / AST (ada_att_2 / ada_out restored, models.py:407, 410) at a
+    ragged size, and oracle/restate.py::compute_hist_loss vs the genuine losses.compute_hist_loss."""
+    from oracle import restate as R, restate_ae as A, restate_attn as T
+    from oracle.make_golden import restore_ast
+    M, _, Ls = ref[0], ref[1], ref[2]
+    torch.manual_seed(13)
+    layer = M.AdaAttN(24)
+    P = {f"a.{n}.weight": getattr(layer, n).weight.detach().clone() for n in ("W_q", "W_k", "W_v")}
+    g = torch.Generator().manual_seed(4)
+    c, s = torch.randn(2, 24, 5, 9, generator=g) * 2, torch.randn(2, 24, 7, 3, generator=g) + 1
+    with torch.no_grad():
+        torch.testing.assert_close(T.adaattn(P, "a", c, s), layer(c, s), rtol=1e-5, atol=1e-5)
+    sd = A.activate_gates(T.make_ast_state(7))
+    torch.manual_seed(1)
+    ast = restore_ast(M, M.AST())
+    ast.load_state_dict(sd, strict=True)
+    ast.train()
+    ci, si = R.rand_image(2, 48, 21), R.rand_image(2, 48, 22)
+    with torch.no_grad():
+        want = ast(ci, si, alpha=0.5)
+        got = T.ast_forward(A.clone_state(sd), ci, si, alpha=0.5)
+    for a, b in zip(got, want):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    x, y = torch.rand(2, 3, 12, 10, generator=g) * 1.2 - 0.1, torch.rand(2, 3, 12, 10, generator=g)
+    assert R.compute_hist_loss(x, y).item() == Ls.compute_hist_loss(x, y).item()
