@@ -805,7 +805,8 @@ struct FirstParams {
   int normalise;
 };
 
-__global__ void __launch_bounds__(kFirstThreads, 2)
+constexpr int F_CTAS_PER_SM = 2;   // 41 KB shared memory, 128 TMEM columns and <= 75 registers per thread each
+__global__ void __launch_bounds__(kFirstThreads, F_CTAS_PER_SM)
 conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
   __shared__ __align__(128) uint8_t s_a[F_STAGES][F_A_BYTES];
   __shared__ __align__(128) uint8_t s_b[F_B_BYTES];
@@ -882,23 +883,19 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
         if (e < PN) s_patch[buf][e] = v[j];
       }
     };
-    // Register prefetch two tiles ahead: the global loads of tile i+2 are issued before tile i is expanded and are
-    // first needed (as the source of a register move) at the end of iteration i+1, so their latency (~1 us under
-    // load, which a one-tile lookahead consumed inside the same iteration left exposed: ~1 300 cycles per tile) is
-    // covered by two full iterations.  The patch is double buffered in shared memory, which makes ONE barrier per
-    // tile enough: a thread can only be one iteration ahead of the slowest one, i.e. in the other buffer.
     int stage = 0;
     uint32_t phase = 0;
     int cur = 0;
-    float p0[PER], p1[PER], p2[PER];
-    const int G = gridDim.x;
+    float pre[PER];
     int tile = blockIdx.x;
-    if (tile < p.num_tiles) fetch(tile, p0);
-    if (tile + G < p.num_tiles) fetch(tile + G, p1);
-    for (; tile < p.num_tiles; tile += G) {
-      if (tile + 2 * G < p.num_tiles) fetch(tile + 2 * G, p2);
-      stash(cur, p0);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // patch[cur] complete
+    if (tile < p.num_tiles) {
+      fetch(tile, pre);
+      stash(0, pre);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (; tile < p.num_tiles; tile += gridDim.x) {
+      const int ntile = tile + gridDim.x;
+      if (ntile < p.num_tiles) fetch(ntile, pre);
       uint32_t pk[16];
       {
         float v[28];
@@ -925,9 +922,9 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+      if (ntile < p.num_tiles) stash(cur ^ 1, pre);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // patch[cur^1] complete, patch[cur] free
       cur ^= 1;
-#pragma unroll
-      for (int j = 0; j < PER; ++j) { p0[j] = p1[j]; p1[j] = p2[j]; }
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
@@ -1001,7 +998,7 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
   if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
   p.num_tiles = (int)nt;
   p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.tap = tap;
-  const int grid = p.num_tiles < 2 * sm_count ? p.num_tiles : 2 * sm_count;
+  const int grid = p.num_tiles < F_CTAS_PER_SM * sm_count ? p.num_tiles : F_CTAS_PER_SM * sm_count;
   conv3x3_first_tc_kernel<<<grid, kFirstThreads, 0, s>>>(fp, p);
   AST_CHECK_LAUNCH();
   return 0;
