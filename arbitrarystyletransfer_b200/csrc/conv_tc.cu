@@ -147,27 +147,31 @@ __device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)
 // Epilogue warps (4 per CTA; warp e may touch TMEM lanes [32e, 32e+32) = tile rows 2e, 2e+1):
 // tcgen05.ld -> +bias -> (tap) -> ReLU -> (tap) -> bf16 -> {plain | 2x2 max-pool | nearest x2} store
 // with the optional reflection halo, or the fp32 NCHW image for the last decoder layer.
-template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2>
+// TG > 1 (tile groups, requires NG == 1 and NACC == TG): instead of splitting every tile's columns over the warp
+// groups, group tg = ew / 4 takes every TG-th tile whole and owns accumulator stage tg -- TG tiles are in the
+// epilogue at once, which is what a layer whose work IS the epilogue (conv1_1) needs.
+template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2, int TG = 1>
 __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
                                               uint32_t tfull_bar0, uint32_t tempty_bar0) {
-  constexpr int CH = (BN >= 32 && BN / 32 >= NG) ? 32 : 16;  // columns per tcgen05.ld
+  constexpr int CH = (TG > 1) ? 16 : ((BN >= 32 && BN / 32 >= NG) ? 32 : 16);  // columns per tcgen05.ld
   constexpr int TH = TILE_M / TW;         // tile = TH rows x TW cols of pixels, row-major in M
   constexpr int NCH = BN / CH;
   // 4*NG epilogue warps: warp ew owns TMEM lane quarter e = ew % 4 (hardware rule: a warp may only
   // touch lanes [32*(warp%4), +32)) and the column chunks g, g+NG, ... with g = ew / 4, so two
   // warps per SM sub-partition interleave and hide each other's TMEM-load / store latency.
-  const int e = ew & 3, g = ew >> 2;
+  static_assert(TG == 1 || (NG == 1 && NACC == TG), "tile groups own one accumulator stage each");
+  const int e = ew & 3, g = (TG > 1) ? 0 : (ew >> 2), tg = (TG > 1) ? (ew >> 2) : 0;
   const int hl = (32 * e + lane) / TW;
   const int wl = (32 * e + lane) % TW;
   const bool reflect = p.halo == AST_HALO_REFLECT;
   const bool wide_st = (reinterpret_cast<uintptr_t>(p.out) & 31u) == 0 && (p.Cout % 16) == 0;
-  int as = 0;
+  int as = tg;
   uint32_t aphase = 0;
   TileCursor cur;
-  cur.init(p, blockIdx.x, gridDim.x);
+  cur.init(p, blockIdx.x + tg * gridDim.x, TG * gridDim.x);
   long long dbg_wait = 0;
   const long long dbg_t0 = clock64();
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, cur.next()) {
+  for (int tile = blockIdx.x + tg * gridDim.x; tile < p.num_tiles; tile += TG * gridDim.x, cur.next()) {
     const int nb = cur.nb, twi = cur.twi, thi = cur.thi, n = cur.n;
     const int h = thi * TH + hl, w = twi * TW + wl;
     const bool in_img = (h < p.H) && (w < p.W);
@@ -270,7 +274,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty_bar0 + 8u * as);
-    if (++as == NACC) { as = 0; aphase ^= 1u; }
+    if (TG > 1) aphase ^= 1u;
+    else if (++as == NACC) { as = 0; aphase ^= 1u; }
   }
   if (p.dbg && ew == 0 && lane == 0) {
     p.dbg[blockIdx.x * 8 + 4] = dbg_wait;               // epilogue warp 0: waiting for an accumulator
@@ -965,6 +970,173 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// First layer, TMA-fed variant (default when W % 4 == 0): the (8+2) x (16+2) x 3 fp32 input patch of a tile is ONE
+// 4-D TMA box {24 w, 10 h, 3 c, 1 n} of the NCHW image starting FOUR columns left of the tile (TMA loads never complete
+// when the innermost coordinate is not 16-byte aligned -- the constraint measured for the wgrad kernel -- so the box
+// starts at w0 - 4 instead of w0 - 1; out-of-image pixels arrive as zeros), prefetched four tiles
+// ahead by a dedicated warp, so the four producer warps only expand -- normalise (zero padding applies to the
+// NORMALISED image: out-of-image taps are forced to 0 in border tiles), round to bf16, store their A rows -- and
+// are coupled to nothing but mbarriers: no block barrier, no global-load latency in their loop.
+constexpr int F2_NG = 4;                   // epilogue groups of 4 warps; group g takes every 4th tile (accumulator stage g)
+constexpr int F2_MMA_WARP = 4 + 4 * F2_NG, F2_TMA_WARP = F2_MMA_WARP + 1;
+constexpr int F2_THREADS = 32 * (F2_TMA_WARP + 1);   // warps 0-3 producers, 4-19 epilogue, 20 MMA + TMEM, 21 TMA
+constexpr int F2_PSTAGES = 4;
+constexpr int F2_PW = 24, F2_PH = TILE_H + 2;                 // patch row = image columns [w0 - 4, w0 + 20)
+constexpr int F2_X0 = 3;                                      // column of the tile's left halo pixel (w0 - 1) in it
+constexpr int F2_PATCH_FLOATS = 3 * F2_PH * F2_PW;            // 720
+constexpr int F2_PATCH_BYTES = F2_PATCH_FLOATS * 4;           // 2880
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const FirstParams fp, const ConvParams p) {
+  __shared__ __align__(128) uint8_t s_a[F_STAGES][F_A_BYTES];
+  __shared__ __align__(128) uint8_t s_b[F_B_BYTES];
+  __shared__ __align__(128) float s_patch[F2_PSTAGES][F2_PATCH_FLOATS + 16];  // +16: keeps every stage 128 B aligned
+  __shared__ __align__(8) uint64_t s_bar[2 * F_STAGES + 2 * F2_NG + 2 * F2_PSTAGES];
+  __shared__ uint32_t s_tmem;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t bars = smem_u32(s_bar);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (F_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * F_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * F_STAGES + F2_NG + s); };
+  auto pfull_bar = [&](int s) { return bars + 8u * (2 * F_STAGES + 2 * F2_NG + s); };
+  auto pempty_bar = [&](int s) { return bars + 8u * (2 * F_STAGES + 2 * F2_NG + F2_PSTAGES + s); };
+
+  for (int i = threadIdx.x; i < F_N * F_K; i += F2_THREADS) {
+    const int co = i / F_K, k = i % F_K;
+    const float v = k < 27 ? fp.w[co * 27 + k] : 0.f;
+    const uint32_t off = (uint32_t)(co >> 3) * F_SBO + (uint32_t)(k >> 3) * F_LBO + (co & 7) * 16 + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(s_b + off) = __float2bfloat16_rn(v);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < F_STAGES; ++s) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < F2_NG; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < F2_PSTAGES; ++s) { mbar_init(pfull_bar(s), 1); mbar_init(pempty_bar(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == F2_TMA_WARP && lane == 0) tma_prefetch_desc(&tmImg);
+  if (warp == F2_MMA_WARP) tmem_alloc<F2_NG * F_N>(smem_u32(&s_tmem));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+
+  if (warp == F2_TMA_WARP) {
+    // ===================== TMA: input patches =====================
+    if (lane == 0) {
+      int ps = 0;
+      uint32_t pphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int twi = t % p.tiles_w; t /= p.tiles_w;
+        const int thi = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        mbar_wait(pempty_bar(ps), pphase ^ 1u);
+        mbar_expect_tx(pfull_bar(ps), F2_PATCH_BYTES);
+        tma_load_4d(smem_u32(&s_patch[ps][0]), &tmImg, pfull_bar(ps), twi * TILE_W - 4, thi * TILE_H - 1, 0, n);
+        if (++ps == F2_PSTAGES) { ps = 0; pphase ^= 1u; }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== producers: expand the patch to the 128 x 32 bf16 A tile =====================
+    const int r = threadIdx.x;           // tile row = pixel
+    const int hl = r >> 4, wl = r & 15;
+    float sc[3], sh[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      sc[c] = fp.normalise ? fp.rstd[c] : 1.f;
+      sh[c] = fp.normalise ? -fp.mean[c] * fp.rstd[c] : 0.f;
+    }
+    int stage = 0, ps = 0;
+    uint32_t phase = 0, pphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int twi = t % p.tiles_w; t /= p.tiles_w;
+      const int thi = t % p.tiles_h;
+      const int h0 = thi * TILE_H - 1, w0 = twi * TILE_W - 1;
+      const bool border = h0 < 0 || w0 < 0 || h0 + F2_PH > p.H || w0 + TILE_W + 2 > p.W;
+      mbar_wait(pfull_bar(ps), pphase);
+      const float* pt = &s_patch[ps][0];
+      float v[28];
+      v[27] = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            v[ci * 9 + kh * 3 + kw] = fmaf(pt[(ci * F2_PH + hl + kh) * F2_PW + F2_X0 + wl + kw], sc[ci], sh[ci]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pempty_bar(ps));       // this warp has read its taps
+      if (++ps == F2_PSTAGES) { ps = 0; pphase ^= 1u; }
+      if (border) {                                       // zero padding of the normalised image (models.py:131 + pad=1)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int ih = h0 + hl + kh, iw = w0 + wl + kw;
+            if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) {
+              v[kh * 3 + kw] = 0.f; v[9 + kh * 3 + kw] = 0.f; v[18 + kh * 3 + kw] = 0.f;
+            }
+          }
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 14; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+      pk[14] = 0u;
+      pk[15] = 0u;
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      uint8_t* row = &s_a[stage][0] + (uint32_t)(r >> 3) * F_SBO + (r & 7) * 16;
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc)
+        *reinterpret_cast<uint4*>(row + kc * F_LBO) =
+            make_uint4(pk[4 * kc], pk[4 * kc + 1], pk[4 * kc + 2], pk[4 * kc + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
+      if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == F2_MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, F_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      const uint32_t b_addr = smem_u32(s_b);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(&s_a[stage][0]);
+#pragma unroll
+        for (int k = 0; k < F_K / 16; ++k) {
+          const uint64_t adesc = make_sdesc_k_noswizzle(a_addr + k * 2 * F_LBO, F_LBO, F_SBO);
+          const uint64_t bdesc = make_sdesc_k_noswizzle(b_addr + k * 2 * F_LBO, F_LBO, F_SBO);
+          umma_bf16(tmem_base + (uint32_t)(as * F_N), adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(as));
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+        if (++as == F2_NG) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 4 .. 4 + 4 F2_NG) =====================
+    epilogue_loop<F_N, AST_EPI_PLAIN, TILE_W, 1, F2_NG, F2_NG>(p, tmem_base, warp - 4, lane, tfull_bar(0), tempty_bar(0));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == F2_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc<F2_NG * F_N>(tmem_base);
+  }
+}
+
 static int get_sm_count(int* out) {
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -999,6 +1171,48 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
   p.num_tiles = (int)nt;
   p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.tap = tap;
   const int grid = p.num_tiles < F_CTAS_PER_SM * sm_count ? p.num_tiles : F_CTAS_PER_SM * sm_count;
+  static const bool dbg_on = getenv("AST_CONV_DEBUG") != nullptr;     // debug only: allocates and synchronises
+  if (getenv("AST_FIRST_NOSTORE")) p.out = nullptr;                   // diagnostic: the layer without its output stores
+  long long* dbg = nullptr;
+  if (dbg_on) {
+    AST_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * grid));
+    AST_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, s));
+    p.dbg = dbg;
+  }
+  struct Dump {
+    long long* d; int grid; int tiles; cudaStream_t s;
+    ~Dump() {
+      if (!d) return;
+      cudaStreamSynchronize(s);
+      long long* h = (long long*)malloc(sizeof(long long) * 8 * grid);
+      cudaMemcpy(h, d, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+      double w = 0, t = 0;
+      for (int i = 0; i < grid; ++i) { w += (double)h[i * 8 + 4]; t += (double)h[i * 8 + 5]; }
+      const double per = (double)tiles / grid;
+      fprintf(stderr, "[conv dbg] first layer: tiles/CTA=%.1f | epilogue warp 0 per tile: loop=%.0f cycles, of which waiting "
+                      "for an accumulator=%.0f\n", per, t / grid / per, w / grid / per);
+      free(h);
+      cudaFree(d);
+    }
+  } dump{dbg, grid, p.num_tiles, s};   // dump.grid is corrected below when the one-CTA-per-SM kernel is launched
+  static const bool no_tma = getenv("AST_FIRST_NO_TMA") != nullptr;   // A/B reference: the register-staged producer
+  if (!no_tma && W % 4 == 0 && aligned16(img)) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return AST_E_NODRIVER;
+    CUtensorMap tmImg;
+    const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)N};
+    const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * 12};
+    const cuuint32_t bx[4] = {F2_PW, F2_PH, 3, 1}, es[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&tmImg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(img), gdim, gstr, bx, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return AST_E_SHAPE;
+    const int grid1 = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+    dump.grid = grid1;
+    conv3x3_first_tma_kernel<<<grid1, F2_THREADS, 0, s>>>(tmImg, fp, p);
+    AST_CHECK_LAUNCH();
+    return 0;
+  }
   conv3x3_first_tc_kernel<<<grid, kFirstThreads, 0, s>>>(fp, p);
   AST_CHECK_LAUNCH();
   return 0;
