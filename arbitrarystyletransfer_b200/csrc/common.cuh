@@ -147,6 +147,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// ReLU + round + pack in ONE instruction (cvt.rn.relu: negative -> +0, NaN stays NaN like torch.relu)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // Element-type traits for 16-byte vectors: fp32 -> 4 lanes, bf16 -> 8 lanes.
 template <bool BF16>

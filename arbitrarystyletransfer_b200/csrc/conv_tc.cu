@@ -226,18 +226,24 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
 #pragma unroll
           for (int i = 0; i < CH; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
         }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (p.tap && !p.tap_prerelu && in_img) {
-          float* tp = p.tap + (((int64_t)n * p.Cout + ch0) * p.H + h) * p.W + w;
-#pragma unroll
-          for (int i = 0; i < CH; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
-        }
+        const bool post_tap = p.tap && !p.tap_prerelu;
         uint32_t pk[CH / 2];
+        if (p.relu && !post_tap) {      // the common case: ReLU folded into the bf16 conversion
 #pragma unroll
-        for (int i = 0; i < CH / 2; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+          for (int i = 0; i < CH / 2; ++i) pk[i] = pack_bf16_relu(f[2 * i], f[2 * i + 1]);
+        } else {
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (post_tap && in_img) {
+            float* tp = p.tap + (((int64_t)n * p.Cout + ch0) * p.H + h) * p.W + w;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) tp[(int64_t)i * p.H * p.W] = f[i];
+          }
+#pragma unroll
+          for (int i = 0; i < CH / 2; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+        }
         if (EPI == AST_EPI_POOL2) {
           // 2x2 max: partner along w is lane^1, along h is lane^TW (a warp holds 32/TW full tile rows).
           // max commutes with the (monotonic) bf16 rounding, so pool the packed values.
@@ -806,6 +812,7 @@ constexpr int F_LBO = 128, F_SBO = (F_K / 8) * 128;
 struct FirstParams {
   const float* img;   // [N][3][H][W]
   const float* w;     // OIHW fp32 [64][3][3][3]
+  const float* bias;  // TMA variant only: folded into the GEMM through the K padding (see the kernel)
   float mean[3], rstd[3];
   int normalise;
 };
@@ -1006,7 +1013,15 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const FirstP
 
   for (int i = threadIdx.x; i < F_N * F_K; i += F2_THREADS) {
     const int co = i / F_K, k = i % F_K;
-    const float v = k < 27 ? fp.w[co * 27 + k] : 0.f;
+    // k < 27: the taps.  k = 27, 28: the bias as a two-term bf16 split against two columns of ones in A -- K is
+    // padded to 32 anyway, and it takes 16 broadcast loads + 64 adds per pixel out of an epilogue that ncu shows
+    // bound by the L1/LSU pipe (86 %) and instruction issue (63 %).  hi + lo carries the bias to ~2^-17.
+    float v = k < 27 ? fp.w[co * 27 + k] : 0.f;
+    if (fp.bias && (k == 27 || k == 28)) {
+      const float bv = fp.bias[co];
+      const float hi = __bfloat162float(__float2bfloat16_rn(bv));
+      v = k == 27 ? hi : bv - hi;
+    }
     const uint32_t off = (uint32_t)(co >> 3) * F_SBO + (uint32_t)(k >> 3) * F_LBO + (co & 7) * 16 + (k & 7) * 2;
     *reinterpret_cast<__nv_bfloat16*>(s_b + off) = __float2bfloat16_rn(v);
   }
@@ -1085,8 +1100,10 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const FirstP
       }
       uint32_t pk[16];
 #pragma unroll
+      v[27] = 1.f;                                        // the ones that multiply the bias rows of B (k = 27, 28)
+#pragma unroll
       for (int i = 0; i < 14; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-      pk[14] = 0u;
+      pk[14] = pack_bf16(1.f, 0.f);
       pk[15] = 0u;
       mbar_wait(empty_bar(stage), phase ^ 1u);
       uint8_t* row = &s_a[stage][0] + (uint32_t)(r >> 3) * F_SBO + (r & 7) * 16;
@@ -1209,6 +1226,8 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
     if (cr != CUDA_SUCCESS) return AST_E_SHAPE;
     const int grid1 = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     dump.grid = grid1;
+    fp.bias = bias;
+    p.bias = nullptr;               // folded into the GEMM
     conv3x3_first_tma_kernel<<<grid1, F2_THREADS, 0, s>>>(tmImg, fp, p);
     AST_CHECK_LAUNCH();
     return 0;

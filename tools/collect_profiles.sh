@@ -18,6 +18,8 @@ python tools/ncu_condense.py $G/ncu_dw_raw.csv "ncu --set full: tools/bench_dw.p
 python tools/ncu_condense.py $G/ncu_pw_raw.csv "ncu --set full: pointwise / weight-gradient GEMM launches inside the config-3 step" > $P/r1_ncu_pointwise_summary.csv
 python tools/ncu_condense.py $G/ncu_attn_raw.csv "ncu --set full: tools/prof_ast.py --layer, one AdaAttN layer forward + backward at (8,128,32,32)" > $P/r1_ncu_adaattn_summary.csv
 python tools/ncu_condense.py $G/ncu_last_raw.csv "ncu --set full: tools/bench_last.py, conv3x3_last_tn_kernel at (32,64,512,512)" > $P/r1_ncu_last_layer_summary.csv
+python tools/ncu_condense.py $G/ncu_first_raw.csv "ncu --set full: tools/bench_first.py, conv3x3_first_tma_kernel at (32,3,512,512)" > $P/r1_ncu_first_layer_summary.csv
+python tools/ncu_traffic.py $G/ncu_first_raw.csv conv3x3_first_tma conv3x3_first_tma_kernel
 python tools/ncu_traffic.py $G/ncu_k1_raw.csv adain_cached_kernel adain_cached_kernel
 python tools/ncu_traffic.py $G/ncu_last_raw.csv conv3x3_last_tn conv3x3_last_tn_kernel
 python tools/ncu_traffic.py $G/ncu_attn_raw.csv attn_softmax_kernel attn_softmax_kernel
@@ -25,6 +27,8 @@ cp $G/layers.json $P/r1_layers_table.json
 cp $G/bench_k1.log $P/r1_bench_k1.txt
 cp $G/bench_dw.log $P/r1_bench_depthwise_kernels.txt
 cp $G/bench_last.log $P/r1_bench_last_layer.txt
+cp $G/bench_first.log $P/r1_bench_first_layer.txt
+cp $G/bw_probe.log $P/r1_bw_probe.txt
 cp $G/conv_role_breakdown.txt $P/r1_conv_role_breakdown.txt
 cp $G/smoke.log $P/r1_smoke.log
 tail -n 3 $G/test_gpu_all.log > $P/r1_pytest_gpu.log
