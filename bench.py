@@ -259,6 +259,42 @@ def time_layers(eng, N, size, reps=5, impl=0):
     return rows
 
 
+def time_edge_layers(eng, N, S, reps=10):
+    """The two HBM-bound layers of the step alone at the bench shape, against the measured HBM copy peak: conv1_1
+    (Normalization + 3 -> 64 + ReLU: fp32 NCHW image in, 64-channel bf16 native map out) and the last decoder conv
+    (64 -> 3: native map in, fp32 NCHW image out).  Algorithmic bytes as in DESIGN.md (K2f / K2l)."""
+    from arbitrarystyletransfer_b200 import engine as E
+    dev = eng.device
+    pk = peaks()
+    img = torch.rand(N, 3, S, S, device=dev)
+    x64 = eng.buf.get("enc0", N, S, S, 64, dev, True)
+    out = torch.empty(N, 3, S, S, device=dev)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ms_f = timed(lambda: E.conv3x3_first(img, eng.vgg_w0, eng.vgg_b[0], x64, impl=eng.impl_edge))
+    xd = eng.buf.get("dec7", N, S, S, 64, dev, False)
+    ms_l = timed(lambda: E.conv3x3_last(xd, eng.dec_w_last, eng.dec_wpk_last, eng.dec_b[8], out, False, impl=eng.impl_edge))
+    bf = N * 3 * S * S * 4 + N * S * S * 64 * 2
+    bl = N * (S + 2) * (S + 2) * 64 * 2 + N * 3 * S * S * 4
+    return {"first": {"kernel": "conv3x3_first_tma_kernel (conv1_1, 2 launches/step)", "bound": "hbm", "ms_per_launch": ms_f,
+                      "bytes_per_launch": bf, "achieved": bf / ms_f / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                      "frac": bf / ms_f / 1e6 / pk["hbm_gbs"], "traffic": ncu_traffic("conv3x3_first_tma_kernel")},
+            "last": {"kernel": "conv3x3_last_tn_kernel (decoder image layer, 1 launch/step)", "bound": "hbm",
+                     "ms_per_launch": ms_l, "bytes_per_launch": bl, "achieved": bl / ms_l / 1e6, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": bl / ms_l / 1e6 / pk["hbm_gbs"], "traffic": ncu_traffic("conv3x3_last_tn_kernel")}}
+
+
 def time_adain_k1(N, reps=10):
     """Standalone K1 (fused AdaIN, NCHW fp32) at the config-4 per-GPU shape (N,512,64,64)."""
     from arbitrarystyletransfer_b200 import functional as Fn
@@ -789,6 +825,10 @@ def run_native(args):
                                   "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                   "frac": gbs / pk["hbm_gbs"], "bytes_per_launch": ab, "ms_per_launch": ams,
                                   "traffic": ncu_traffic("adain_cached_kernel"), "peak_source": pk["source"]}
+        try:
+            line["edge_layers"] = time_edge_layers(eng, N, S)
+        except Exception as e:
+            line["edge_layers"] = {"error": repr(e)[:200]}
         if args.layers_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
             alt = time_layers(eng, N, S, impl=3)   # AST_CONV_TC_TAPBOX, for the A/B table only

@@ -51,6 +51,12 @@ def test_argument_errors_without_gpu(lib_path):
     assert lib.ast_adain_fwd(None, None, None, None, 1, None, None, 1, 1, 1, 1.0, 0.0, 0, None) == -1
     assert lib.ast_gram_fwd(None, None, 1, 1, 1, None) == -1
     assert lib.ast_huber_ws_bytes(10) >= 4
+    # K6 / hist-loss entry points
+    assert lib.ast_bgemm(None, 0, 8, 0, None, 0, 8, 0, None, 0, 8, 0, 1, 1, 1, 1, None) == -1
+    assert lib.ast_attn_softmax(None, 8, None, 8, None, 1, 8, None) == -1
+    assert lib.ast_hist_ws_bytes(4) >= 2 * 4 * 257 * 8
+    assert lib.ast_hist_loss_fwd(None, None, 1, 1, 1, 1.0, 1.0, None, None, None, 0, None) == -1
+    assert lib.ast_split3_rows(None, 8, None, 1, 8, 0, None) == -1
 
 
 def test_no_cpu_fallback():
