@@ -137,7 +137,25 @@ __global__ void __launch_bounds__(kNThreads) native_stats_kernel(const NativeSta
   wl.init();
   if (g < groups) {
     const __nv_bfloat16* base = a.maps[q] + (int64_t)n * (H + 2) * (W + 2) * a.C + v * 8;
-    for (int64_t p = p0 + g; p < p1; p += groups) {
+    // four pixels' loads in flight per thread: one load per Welford update left the loop a chain of exposed
+    // HBM latencies (1.8 TB/s)
+    int64_t p = p0 + g;
+    for (; p + 3 * groups < p1; p += 4 * groups) {
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t pj = p + (int64_t)j * groups;
+        const int h = (int)(pj / W), w = (int)(pj % W);
+        u[j] = ld_stream_u4(base + ((int64_t)(h + 1) * (W + 2) + (w + 1)) * a.C);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x[8];
+        Vec16<true>::unpack(u[j], x);
+        wl.push(x);
+      }
+    }
+    for (; p < p1; p += groups) {
       const int h = (int)(p / W), w = (int)(p % W);
       const uint4 u = ld_stream_u4(base + ((int64_t)(h + 1) * (W + 2) + (w + 1)) * a.C);
       float x[8];
@@ -219,9 +237,23 @@ native_apply_kernel(const __nv_bfloat16* __restrict__ content, const float4* __r
   const int64_t per = (npix + chunks - 1) / chunks;
   const int64_t p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
   const int64_t img = (int64_t)n * (H + 2) * (W + 2);
-  for (int64_t p = p0 + g; p < p1; p += groups) {
+  for (int64_t pb = p0 + g; pb < p1; pb += 4 * groups) {
+   // four pixels per iteration: their loads are issued before the first one is used
+   uint4 ub[4];
+#pragma unroll
+   for (int jj = 0; jj < 4; ++jj) {
+     const int64_t pj = pb + (int64_t)jj * groups;
+     if (pj < p1) {
+       const int h = (int)(pj / W), w = (int)(pj % W);
+       ub[jj] = ld_stream_u4(content + ((img + (int64_t)(h + 1) * (W + 2) + (w + 1)) * C + v * 8));
+     }
+   }
+#pragma unroll
+   for (int jj = 0; jj < 4; ++jj) {
+    const int64_t p = pb + (int64_t)jj * groups;
+    if (p >= p1) break;
     const int h = (int)(p / W), w = (int)(p % W);
-    const uint4 u = ld_stream_u4(content + ((img + (int64_t)(h + 1) * (W + 2) + (w + 1)) * C + v * 8));
+    const uint4 u = ub[jj];
     float x[8];
     Vec16<true>::unpack(u, x);
 #pragma unroll
@@ -238,6 +270,7 @@ native_apply_kernel(const __nv_bfloat16* __restrict__ content, const float4* __r
     for (int ri = 0; ri < nr; ++ri)
       for (int ci = 0; ci < nc; ++ci)
         *reinterpret_cast<uint4*>(out + ((img + (int64_t)(rows[ri] + 1) * (W + 2) + (cols[ci] + 1)) * C + v * 8)) = o;
+   }
   }
 }
 
