@@ -275,7 +275,8 @@ native_apply_kernel(const __nv_bfloat16* __restrict__ content, const float4* __r
 }
 
 static int native_chunks(int N, int64_t hw) {
-  int64_t c = (2 * 148 + N - 1) / N;
+  // ~8 CTAs per SM: these are streaming kernels (2 per SM left them latency-bound at a third of the HBM rate)
+  int64_t c = (8 * 148 + N - 1) / N;
   if (c > kMaxChunks) c = kMaxChunks;
   if (c > hw / 32) c = hw / 32;
   if (c < 1) c = 1;
