@@ -147,3 +147,40 @@ GOLDEN_GRAD_KEYS = (
     "_dec._img_out.weight", "_dec._decoder_blocks.8._conv._layers.2.weight",
     "_enc.mob_net.14._layers.7.weight", "_enc.mob_net.1._layers.1.weight", "_enc.mob_net.0.0.weight",
 )
+
+
+# ------------------------------------------------------------------------------------------------------
+# The STORAGE / PRECISION CONTRACT of the CUDA AdaAttN forward path (csrc/bgemm_tc.cu, attn.cu), restated on CPU:
+# fp32 instance norms; W_q, W_k and Q K^T as two-term bf16 splits (three of the four cross terms, fp32 accumulation);
+# softmax in fp32, weights rounded to bf16 and the moments divided by the sum of the ROUNDED weights; v = W_v(style)
+# from bf16-rounded operands, rounded to bf16; v^2 exact (hi + lo); output rounded to bf16.  Comparing the fp32
+# restatement with this one shows what the contract costs; comparing the CUDA path with this one checks the kernels.
+# ------------------------------------------------------------------------------------------------------
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _split_matmul(a, b):
+    """a @ b^T with both operands as hi + lo bf16 splits, dropping lo*lo (what one K = 3C GEMM of [hi|lo|hi] by
+    [hi|hi|lo] computes)."""
+    ah, bh = _bf(a), _bf(b)
+    al, bl = _bf(a - ah), _bf(b - bh)
+    return ah @ bh.transpose(-1, -2) + al @ bh.transpose(-1, -2) + ah @ bl.transpose(-1, -2)
+
+
+def adaattn_contract(P, prefix, content_map, style_map):
+    b, c, h, w = content_map.shape
+    cn = instance_norm(content_map).flatten(2).transpose(1, 2)                  # (b, HW, c) fp32
+    sn = instance_norm(style_map).flatten(2).transpose(1, 2)
+    xs = _bf(style_map).flatten(2).transpose(1, 2)
+    wq, wk, wv = (P[f"{prefix}.{n}.weight"].view(c, c) for n in ("W_q", "W_k", "W_v"))
+    q = _split_matmul(cn, wq.unsqueeze(0))                                      # fp32, ~2^-17
+    k = _split_matmul(sn, wk.unsqueeze(0))
+    v = _bf(xs @ _bf(wv).t())
+    att = _bf(torch.softmax(_split_matmul(q, k), dim=-1))
+    lsum = att.sum(-1, keepdim=True)
+    mean = (att @ v) / lsum
+    m2 = (att @ (v * v)) / lsum                                                 # v^2 = hi + lo is exact for bf16 v
+    std = torch.sqrt(torch.relu(m2 - mean * mean))
+    out = _bf(std * _bf(cn) + mean)
+    return out.transpose(1, 2).reshape(b, c, h, w)

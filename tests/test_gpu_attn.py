@@ -311,3 +311,24 @@ def test_ast_alpha_zero_is_independent_of_style(g, ast_state):
     with torch.no_grad():
         a, _, org_a = net(c, s, alpha=0.0)
     assert rel(a, org_a) < 1e-3
+
+
+@pytest.mark.parametrize("gain", [1.0, 6.0])
+def test_adaattn_forward_vs_its_precision_contract(gain):
+    """The CUDA forward path against the CPU restatement of its own storage / precision contract
+    (oracle/restate_attn.py::adaattn_contract): what remains is accumulation order, the fast exponential and bf16
+    rounding flips of the output -- several times smaller than the contract's own distance to fp32 (3e-3)."""
+    from arbitrarystyletransfer_b200 import attention as AT
+    torch.manual_seed(0)
+    C = 64
+    layer = AT.AdaAttN(C)
+    with torch.no_grad():
+        layer.W_q.weight.mul_(gain)
+        layer.W_k.weight.mul_(gain)
+    P = {f"a.{n}.weight": getattr(layer, n).weight.detach().clone() for n in ("W_q", "W_k", "W_v")}
+    layer = layer.cuda()
+    c, s = torch.randn(2, C, 12, 12) * 1.5 + 0.5, torch.randn(2, C, 10, 14) * 2 + 1
+    with torch.no_grad():
+        y = layer(c.cuda(), s.cuda())
+        con = T.adaattn_contract(P, "a", c, s)
+    assert rel(y, con) < 2e-3, rel(y, con)
