@@ -14,11 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libast_b200.so")
 
 # mirrors of the header constants
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_STYLES = 8
 F_CANONICAL, F_BIASED, F_BF16 = 0x1, 0x2, 0x4
-EPI_PLAIN, EPI_POOL2, EPI_UP2 = 0, 1, 2
-HALO_KEEP, HALO_REFLECT = 0, 1
+EPI_PLAIN, EPI_POOL2, EPI_UP2, EPI_UPFOLD = 0, 1, 2, 4
+HALO_KEEP, HALO_REFLECT, HALO_CLAMP = 0, 1, 2
 CONV_AUTO, CONV_TC, CONV_DIRECT, CONV_TC_TAPBOX = 0, 1, 2, 3
 
 
@@ -61,12 +61,15 @@ PROTOTYPES = {
     "ast_gram_fwd_tf32": (_i, [_vp, _vp, _i, _i, _i64, _vp]),
     "ast_conv3x3_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "ast_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_pack_conv_weight_fold": (_i, [_vp, _vp, _i, _i, _vp]),
     "ast_conv3x3_first": (_i, [_vp, _vp, _vp, _fp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_conv3x3_last": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_nchw_to_native": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_native_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_u8hwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "ast_nchw_to_u8hwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ast_adain_native_ws_bytes": (_sz, [_i, _i, _i]),
-    "ast_adain_native_fwd": (_i, [_vp, C.POINTER(_vp), _fp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _f,
+    "ast_adain_native_fwd": (_i, [_vp, C.POINTER(_vp), _fp, _i, _vp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _f, _f,
                                   _u, _i, _vp, _sz, _vp]),
     "ast_pack_conv_weight_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ast_nchw_to_native_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -288,6 +288,36 @@ extern "C" int ast_pack_conv_weight(const float* w_oihw, void* wpk, int Cout, in
   return 0;
 }
 
+// ---- fold packing: OIHW fp32 -> bf16 [16][Cout][Cin] (see ast_b200.h) ---------------------------------
+__global__ void pack_weight_fold_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Cin) {
+  const int64_t total = (int64_t)16 * Cout * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int t = (int)(i / ((int64_t)Cin * Cout));
+    const int b = t & 1, a = (t >> 1) & 1, px = (t >> 2) & 1, py = t >> 3;
+    // taps of the 3x3 kernel that read low-res row offset a (column offset b) for output parity py (px)
+    const int kh0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), kh1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    const int kw0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kw1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    const float* wp = w + ((int64_t)co * Cin + ci) * 9;
+    float acc = 0.f;
+    for (int kh = kh0; kh <= kh1; ++kh)
+      for (int kw = kw0; kw <= kw1; ++kw) acc += wp[kh * 3 + kw];
+    o[i] = __float2bfloat16_rn(acc);
+  }
+}
+
+extern "C" int ast_pack_conv_weight_fold(const float* w_oihw, void* wpk, int Cout, int Cin, void* stream) {
+  if (!w_oihw || !wpk || Cout <= 0 || Cin <= 0) return AST_E_BADARG;
+  const int64_t total = (int64_t)16 * Cout * Cin;
+  int64_t nb = (total + 255) / 256;
+  if (nb > 148 * 8) nb = 148 * 8;
+  pack_weight_fold_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, reinterpret_cast<__nv_bfloat16*>(wpk), Cout, Cin);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int ast_pack_conv_weight_ex(const float* w_oihw, void* wpk, int Cout, int Cin, int flip,
                                        int rows_pad, int cols_pad, const float* row_scale,
                                        void* stream) {
@@ -308,16 +338,20 @@ extern "C" int ast_conv3x3_fwd(const ast_conv_desc* d, const void* in, const voi
                                const float* bias, void* out, float* tap, void* stream) {
   if (!d || !in || !wpk || (!out && !tap)) return AST_E_BADARG;
   if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0) return AST_E_BADARG;
-  if (d->epilogue < AST_EPI_PLAIN || d->epilogue > AST_EPI_UP2) return AST_E_BADARG;
+  const bool fold = d->epilogue == AST_EPI_UPFOLD;
+  if ((d->epilogue < AST_EPI_PLAIN || d->epilogue > AST_EPI_UP2) && !fold) return AST_E_BADARG;
+  if (d->halo < AST_HALO_KEEP || d->halo > AST_HALO_CLAMP) return AST_E_BADARG;
   if (d->halo == AST_HALO_REFLECT) {
-    const int Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->H : d->H);
-    const int Wo = d->epilogue == AST_EPI_POOL2 ? d->W / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->W : d->W);
+    const bool up = d->epilogue == AST_EPI_UP2 || fold;
+    const int Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (up ? 2 * d->H : d->H);
+    const int Wo = d->epilogue == AST_EPI_POOL2 ? d->W / 2 : (up ? 2 * d->W : d->W);
     if (Ho < 2 || Wo < 2) return AST_E_SHAPE;  // ReflectionPad2d(1) needs at least 2 pixels
   }
   cudaStream_t s = (cudaStream_t)stream;
   const bool want_tc = d->impl == AST_CONV_TC || d->impl == AST_CONV_TC_TAPBOX || d->impl >= 64 ||
                        (d->impl == AST_CONV_AUTO && tc::tc_supported(d));
   if (want_tc) return tc::conv3x3_tc(d, in, wpk, bias, out, tap, s);
+  if (fold || d->halo == AST_HALO_CLAMP) return AST_E_SHAPE;   // folded upsample conv: tcgen05 path only
   if (d->impl != AST_CONV_DIRECT && d->impl != AST_CONV_AUTO) return AST_E_BADARG;
   const int Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->H : d->H);
   const int Wo = d->epilogue == AST_EPI_POOL2 ? d->W / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->W : d->W);

@@ -122,8 +122,11 @@ struct TileCursor {
 };
 
 // Output coordinates (unpadded grid, -1 and Xo are the halo) that conv coordinate x feeds.
+// halo: AST_HALO_REFLECT = ReflectionPad2d(1) of the output grid (-1 <- 1, Xo <- Xo-2);
+//       AST_HALO_CLAMP   = replicate (-1 <- 0, Xo <- Xo-1): what the reflection of the x2-upsampled grid is
+//                          in low-resolution coordinates (consumer: conv3x3_fold_kernel).
 template <int EPI>
-__device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)[4]) {
+__device__ __forceinline__ int out_targets(int x, int Xo, int halo, int (&t)[4]) {
   int n = 0;
   if (EPI == AST_EPI_PLAIN) {
     t[n++] = x;
@@ -133,11 +136,12 @@ __device__ __forceinline__ int out_targets(int x, int Xo, bool reflect, int (&t)
   } else {
     t[n++] = x >> 1;
   }
-  if (reflect) {  // ReflectionPad2d(1) of the OUTPUT grid: index -1 <- 1, index Xo <- Xo-2
+  if (halo != AST_HALO_KEEP) {
+    const int lo = halo == AST_HALO_REFLECT ? 1 : 0, hi = halo == AST_HALO_REFLECT ? Xo - 2 : Xo - 1;
     const int m = n;
     for (int i = 0; i < m; ++i) {
-      if (t[i] == 1) t[n++] = -1;
-      if (t[i] == Xo - 2) t[n++] = Xo;
+      if (t[i] == lo) t[n++] = -1;
+      if (t[i] == hi) t[n++] = Xo;
     }
   }
   return n;
@@ -163,7 +167,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
   const int e = ew & 3, g = (TG > 1) ? 0 : (ew >> 2), tg = (TG > 1) ? (ew >> 2) : 0;
   const int hl = (32 * e + lane) / TW;
   const int wl = (32 * e + lane) % TW;
-  const bool reflect = p.halo == AST_HALO_REFLECT;
+  const int halo = p.halo;
   const bool wide_st = (reinterpret_cast<uintptr_t>(p.out) & 31u) == 0 && (p.Cout % 16) == 0;
   int as = tg;
   uint32_t aphase = 0;
@@ -184,8 +188,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
       owner = in_img;
     }
     if (owner && EPI != EPI_NCHW32) {
-      nr = out_targets<EPI>(h, p.Ho, reflect, rows);
-      nc = out_targets<EPI>(w, p.Wo, reflect, cols);
+      nr = out_targets<EPI>(h, p.Ho, halo, rows);
+      nc = out_targets<EPI>(w, p.Wo, halo, cols);
     }
 
     mbar_wait_acc(tfull_bar0 + 8u * as, aphase, p.dbg != nullptr, dbg_wait);
@@ -691,6 +695,8 @@ static int launch_tc_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB
   return AST_E_BADARG;
 }
 
+#include "conv_fold.cuh"
+
 bool tc_supported(const ast_conv_desc* d) {
   return d->Cin % 64 == 0 && d->Cout % 64 == 0 && d->H >= 2 && d->W >= 2;
 }
@@ -700,7 +706,7 @@ static int get_sm_count(int* out);
 // Tensor maps for one launch.  kwbox = 1: A box {64, 8, 18, 1} (conv3x3_tc2_kernel);
 // kwbox = 0: A box {64, 16, 8, 1} (conv3x3_tc_kernel).  Weights [9][rows][Cin], box {64, BN, 1}.
 static int make_maps(CUtensorMap* tmA, CUtensorMap* tmB, const void* in, const void* wpk, int N, int H,
-                     int W, int Cin, int wrows, int BN, int kwbox) {
+                     int W, int Cin, int wrows, int BN, int kwbox, int ntaps = 9) {
   const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W + 2, (uint64_t)H + 2, (uint64_t)N};
   const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)(W + 2) * Cin * 2,
                            (uint64_t)(H + 2) * (W + 2) * Cin * 2};
@@ -708,7 +714,7 @@ static int make_maps(CUtensorMap* tmA, CUtensorMap* tmB, const void* in, const v
   const uint32_t box_kw[4] = {KBLK, T2_W, T2_BOX_H, 1};
   int r = encode_bf16_map(tmA, in, 4, dims, str, kwbox ? box_kw : box_tap);
   if (r) return r;
-  const uint64_t wdims[3] = {(uint64_t)Cin, (uint64_t)wrows, 9};
+  const uint64_t wdims[3] = {(uint64_t)Cin, (uint64_t)wrows, (uint64_t)ntaps};
   const uint64_t wstr[2] = {(uint64_t)Cin * 2, (uint64_t)wrows * Cin * 2};
   const uint32_t wbox[3] = {KBLK, (uint32_t)BN, 1};
   return encode_bf16_map(tmB, wpk, 3, wdims, wstr, wbox);
@@ -731,9 +737,36 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   if (impl >= 1000) { kwbox = 0; impl -= 1000; }
   ConvParams p = {};
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
-  p.Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->H : d->H);
-  p.Wo = d->epilogue == AST_EPI_POOL2 ? d->W / 2 : (d->epilogue == AST_EPI_UP2 ? 2 * d->W : d->W);
+  const bool up = d->epilogue == AST_EPI_UP2 || d->epilogue == AST_EPI_UPFOLD;
+  p.Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (up ? 2 * d->H : d->H);
+  p.Wo = d->epilogue == AST_EPI_POOL2 ? d->W / 2 : (up ? 2 * d->W : d->W);
   p.relu = d->relu; p.halo = d->halo; p.tap_prerelu = d->tap_prerelu;
+  if (d->epilogue == AST_EPI_UPFOLD) {
+    // Upsample(x2) -> ReflectionPad2d(1) -> conv as four 2x2 convs on the low-res map (conv_fold.cuh):
+    // d->H, d->W are the LOW-res input dims, wpk = ast_pack_conv_weight_fold's [16][Cout][Cin].
+    if (!kwbox || tap || !out) return AST_E_BADARG;
+    p.tiles_w = (d->W + T2_W - 1) / T2_W;
+    p.tiles_h = (d->H + T2_H - 1) / T2_H;
+    p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    const int64_t sp = (int64_t)d->N * p.tiles_h * p.tiles_w;
+    int BN = 64;   // tiles per spatial tile: 4 * Cout / 256 for every BN, so the widest N block that divides Cout
+    if (d->Cout % 256 == 0) BN = 256;
+    else if (d->Cout % 128 == 0) BN = 128;
+    if (impl >= 64 && impl <= 256 && d->Cout % impl == 0) BN = impl;
+    if (BN != 64 && BN != 128 && BN != 256) return AST_E_SHAPE;
+    p.n_blocks = (4 / (256 / BN)) * (d->Cout / BN);
+    const int64_t nt = sp * p.n_blocks;
+    if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
+    p.num_tiles = (int)nt;
+    CUtensorMap tmA, tmB;
+    r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, BN, 1, 16);
+    if (r) return r;
+    switch (BN) {
+      case 256: return launch_fold<256>(tmA, tmB, p, sm_count, s);
+      case 128: return launch_fold<128>(tmA, tmB, p, sm_count, s);
+      default: return launch_fold<64>(tmA, tmB, p, sm_count, s);
+    }
+  }
   const int tw = kwbox ? T2_W : TILE_W, th = kwbox ? T2_H : TILE_H;
   p.tiles_w = (d->W + tw - 1) / tw;
   p.tiles_h = (d->H + th - 1) / th;

@@ -110,6 +110,66 @@ __global__ void __launch_bounds__(256) native_to_nchw_kernel(const __nv_bfloat16
   }
 }
 
+// ---- f3 input path: uint8 HWC images <-> the reference's NCHW fp32 tensors ---------------------------
+// The loader's transforms.ToTensor() (data_loader.py:114, 132) turns a PIL uint8 HWC image into float CHW / 255;
+// transforms.ToPILImage() (train.py:18) turns a float CHW image back into uint8 with pic.mul(255).byte() (truncation).
+// Doing both on the device lets images cross PCIe as bytes: 4x less host traffic per stylised image.
+// One thread handles 4 consecutive pixels of one image row: 12 bytes in (3 x u32 when aligned), 3 x float4 out.
+__global__ void __launch_bounds__(256) u8hwc_to_nchw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                            int64_t npix_total, int64_t hw) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // group of 4 pixels
+  const int64_t p0 = q * 4;
+  if (p0 >= npix_total) return;
+  const int64_t n = p0 / hw, r = p0 - n * hw;
+  if (r + 4 <= hw && (hw & 3) == 0) {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + p0 * 3);   // p0 % 4 == 0 -> 12-byte groups, 4-aligned
+    const uint32_t a = __ldg(s32), b = __ldg(s32 + 1), c = __ldg(s32 + 2);
+    const uint8_t by[12] = {(uint8_t)a, (uint8_t)(a >> 8), (uint8_t)(a >> 16), (uint8_t)(a >> 24),
+                            (uint8_t)b, (uint8_t)(b >> 8), (uint8_t)(b >> 16), (uint8_t)(b >> 24),
+                            (uint8_t)c, (uint8_t)(c >> 8), (uint8_t)(c >> 16), (uint8_t)(c >> 24)};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float4 v = make_float4(__fdiv_rn((float)by[ch], 255.f), __fdiv_rn((float)by[3 + ch], 255.f),
+                             __fdiv_rn((float)by[6 + ch], 255.f), __fdiv_rn((float)by[9 + ch], 255.f));
+      *reinterpret_cast<float4*>(dst + (n * 3 + ch) * hw + r) = v;
+    }
+  } else {
+    for (int64_t p = p0; p < p0 + 4 && p < npix_total; ++p) {
+      const int64_t nn = p / hw, rr = p - nn * hw;
+      for (int ch = 0; ch < 3; ++ch) dst[(nn * 3 + ch) * hw + rr] = __fdiv_rn((float)src[p * 3 + ch], 255.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_u8hwc_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst,
+                                                            int64_t npix_total, int64_t hw) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p0 = q * 4;
+  if (p0 >= npix_total) return;
+  const int64_t n = p0 / hw, r = p0 - n * hw;
+  auto q8 = [](float x) -> uint32_t {     // Hardtanh(0,1) (models.py:315-316), then ToPILImage: mul(255).byte()
+    x = fminf(fmaxf(x, 0.f), 1.f);        // NaN -> 0 (fmaxf returns the non-NaN operand)
+    return (uint32_t)(x * 255.f);
+  };
+  if (r + 4 <= hw && (hw & 3) == 0) {
+    uint32_t by[12];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (n * 3 + ch) * hw + r);
+      by[ch] = q8(v.x); by[3 + ch] = q8(v.y); by[6 + ch] = q8(v.z); by[9 + ch] = q8(v.w);
+    }
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + p0 * 3);
+    d32[0] = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24);
+    d32[1] = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24);
+    d32[2] = by[8] | (by[9] << 8) | (by[10] << 16) | (by[11] << 24);
+  } else {
+    for (int64_t p = p0; p < p0 + 4 && p < npix_total; ++p) {
+      const int64_t nn = p / hw, rr = p - nn * hw;
+      for (int ch = 0; ch < 3; ++ch) dst[p * 3 + ch] = (uint8_t)q8(src[(nn * 3 + ch) * hw + rr]);
+    }
+  }
+}
+
 // ---- K1n: AdaIN on the native layout -------------------------------------------------------------
 constexpr int kNThreads = 256;
 constexpr int kMaxChunks = 32;
@@ -338,6 +398,26 @@ extern "C" int ast_native_to_nchw_ex(const void* native, float* nchw, int N, int
   return 0;
 }
 
+extern "C" int ast_u8hwc_to_nchw(const void* u8_nhwc, float* nchw, int N, int H, int W, void* stream) {
+  if (!u8_nhwc || !nchw || N <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(u8_nhwc) & 3u) || !aligned16(nchw)) return AST_E_ALIGN;
+  const int64_t hw = (int64_t)H * W, total = hw * N, groups = (total + 3) / 4;
+  u8hwc_to_nchw_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint8_t*>(u8_nhwc), nchw, total, hw);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_nchw_to_u8hwc(const float* nchw, void* u8_nhwc, int N, int H, int W, void* stream) {
+  if (!u8_nhwc || !nchw || N <= 0 || H <= 0 || W <= 0) return AST_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(u8_nhwc) & 3u) || !aligned16(nchw)) return AST_E_ALIGN;
+  const int64_t hw = (int64_t)H * W, total = hw * N, groups = (total + 3) / 4;
+  nchw_to_u8hwc_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      nchw, reinterpret_cast<uint8_t*>(u8_nhwc), total, hw);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" size_t ast_adain_native_ws_bytes(int N, int C, int K) {
   if (N <= 0 || C <= 0 || K < 0) return 0;
   return (size_t)(1 + K) * N * kMaxChunks * C * 3 * sizeof(float) + (size_t)N * C * sizeof(float4);
@@ -345,10 +425,10 @@ extern "C" size_t ast_adain_native_ws_bytes(int N, int C, int K) {
 
 extern "C" int ast_adain_native_fwd(const void* content, const void* const* styles,
                                     const float* style_w, int K, void* out, int N, int C, int H,
-                                    int W, int Hs, int Ws, float alpha, float eps, unsigned flags,
+                                    int W, const int* Hs, const int* Ws, float alpha, float eps, unsigned flags,
                                     int halo, void* ws, size_t ws_bytes, void* stream) {
   if (!content || !out || !ws || N <= 0 || C <= 0 || H <= 0 || W <= 0 || K < 1) return AST_E_BADARG;
-  if (!styles || !style_w || Hs <= 0 || Ws <= 0) return AST_E_BADARG;
+  if (!styles || !style_w || !Hs || !Ws) return AST_E_BADARG;
   if (K > AST_MAX_STYLES) return AST_E_TOOMANY;
   if (C % 8 != 0 || C / 8 > kNThreads) return AST_E_SHAPE;
   if (halo == AST_HALO_REFLECT && (H < 2 || W < 2)) return AST_E_SHAPE;
@@ -356,7 +436,11 @@ extern "C" int ast_adain_native_fwd(const void* content, const void* const* styl
   if (!aligned16(content) || !aligned16(out) || !aligned16(ws)) return AST_E_ALIGN;
   if (N > 65535) return AST_E_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t hw_min = ((int64_t)H * W < (int64_t)Hs * Ws) ? (int64_t)H * W : (int64_t)Hs * Ws;
+  int64_t hw_min = (int64_t)H * W;
+  for (int k = 0; k < K; ++k) {
+    if (Hs[k] <= 0 || Ws[k] <= 0) return AST_E_BADARG;
+    if ((int64_t)Hs[k] * Ws[k] < hw_min) hw_min = (int64_t)Hs[k] * Ws[k];
+  }
   const int chunks = native_chunks(N, hw_min);
 
   float* partial = reinterpret_cast<float*>(ws);
@@ -368,7 +452,7 @@ extern "C" int ast_adain_native_fwd(const void* content, const void* const* styl
   for (int k = 0; k < K; ++k) {
     if (!styles[k] || !aligned16(styles[k])) return AST_E_BADARG;
     sa.maps[1 + k] = reinterpret_cast<const __nv_bfloat16*>(styles[k]);
-    sa.H[1 + k] = Hs; sa.W[1 + k] = Ws;
+    sa.H[1 + k] = Hs[k]; sa.W[1 + k] = Ws[k];
   }
   sa.partial = partial; sa.N = N; sa.C = C; sa.chunks = chunks;
   const int groups = kNThreads / (C / 8);

@@ -100,6 +100,15 @@ class _WeightCache:
             self._c[key] = hit
         return hit[1]
 
+    def folded(self, p: torch.Tensor):
+        key = (id(p), "fold")
+        ver = (p.data_ptr(), p._version, str(p.device))
+        hit = self._c.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, E.pack_conv_weight_fold(p))
+            self._c[key] = hit
+        return hit[1]
+
 
 class PretrainedEncoder(nn.Module):
     """models.py:186-240.  VGG-19 ``features`` behind ImageNet normalisation; layers are named
@@ -110,7 +119,8 @@ class PretrainedEncoder(nn.Module):
     weights are torchvision's default VGG init and ``load_state_dict`` accepts the reference's
     keys (``_vgg_layers.{1,3,6,...}.{weight,bias}``)."""
 
-    def __init__(self, content_layers=['conv_1', 'conv_3', 'conv_5', 'conv_9', 'conv_13', 'relu_15']):
+    def __init__(self, content_layers=['conv_1', 'conv_3', 'conv_5', 'conv_9', 'conv_13', 'relu_15'],
+                 weights_path=None):
         super().__init__()
         self._content_layers = set(content_layers)
         layers = [_Named("norm")]
@@ -131,6 +141,41 @@ class PretrainedEncoder(nn.Module):
         self._cache = _WeightCache()
         self._buf = E._Buffers()
         self.conv_impl = L.CONV_AUTO
+        if weights_path is not None:
+            self.load_vgg19_weights(weights_path)
+
+    def load_vgg19_weights(self, path_or_state):
+        """Offline replacement for ``models.vgg19(pretrained=True)`` (models.py:192): load the 16 conv weights / biases
+        from a file saved on a machine that has them -- either a torchvision ``vgg19().state_dict()`` (keys
+        ``features.{0,2,5,...}.{weight,bias}``; ``classifier.*`` is ignored), the ``features`` sub-module's own state
+        dict (``{0,2,5,...}.weight``), or this module's / the reference's keys (``_vgg_layers.{1,3,6,...}.weight``).
+        torchvision's ``features[i]`` is ``_vgg_layers[i + 1]`` here (the reference puts Normalization at index 0)."""
+        sd = path_or_state
+        if not isinstance(sd, dict):
+            sd = torch.load(path_or_state, map_location="cpu")
+        if isinstance(sd, dict) and "state_dict" in sd and isinstance(sd["state_dict"], dict):
+            sd = sd["state_dict"]
+        own = self.state_dict()
+        new, used = {}, 0
+        for k, v in sd.items():
+            parts = k.split(".")
+            if parts[0] == "_vgg_layers":
+                tgt = k
+            elif parts[0] == "features" and len(parts) == 3 and parts[1].isdigit():
+                tgt = f"_vgg_layers.{int(parts[1]) + 1}.{parts[2]}"
+            elif len(parts) == 2 and parts[0].isdigit():
+                tgt = f"_vgg_layers.{int(parts[0]) + 1}.{parts[1]}"
+            else:
+                continue
+            if tgt in own:
+                if tuple(own[tgt].shape) != tuple(v.shape):
+                    raise L.AstError(f"VGG-19 weight {k}: shape {tuple(v.shape)} != {tuple(own[tgt].shape)}")
+                new[tgt] = v
+                used += 1
+        if used != len(own):
+            raise L.AstError(f"VGG-19 weights file supplies {used} of the {len(own)} conv tensors")
+        self.load_state_dict(new, strict=True)
+        return self
 
     def _convs(self):
         return [m for m in self._vgg_layers if isinstance(m, nn.Conv2d)]
@@ -239,6 +284,7 @@ class ClassicDecoder(nn.Sequential):
         self._cache = _WeightCache()
         self._buf = E._Buffers()
         self.conv_impl = L.CONV_AUTO
+        self.fold = True     # post-upsample convs on the low-res map (engine.run_decoder)
 
     def _convs(self):
         return [m for m in self if isinstance(m, nn.Conv2d)]
@@ -258,25 +304,13 @@ class ClassicDecoder(nn.Sequential):
         return self.forward_native(t)
 
     def forward_native(self, t):
-        lib = L.load()
-        N, hp, wp, _ = t.shape
-        h, w = hp - 2, wp - 2
-        dev = t.device
         convs = self._convs()
-        cur = t
-        for i in range(8):
-            cin, cout, relu, up = E.DECODER_SPEC[i]
-            ho, wo = (2 * h, 2 * w) if up else (h, w)
-            y = self._buf.get(f"d{i}", N, ho, wo, cout, dev, False)
-            E.conv3x3(cur, self._cache.packed(convs[i].weight), convs[i].bias, y, N=N, H=h, W=w,
-                      cin=cin, cout=cout, relu=relu, epilogue=L.EPI_UP2 if up else L.EPI_PLAIN,
-                      halo=L.HALO_REFLECT, impl=self.conv_impl)
-            cur, h, w = y, ho, wo
-        out = torch.empty(N, 3, h, w, device=dev, dtype=torch.float32)
+        wpk = [self._cache.packed(convs[i].weight) for i in range(8)] + [None]
+        wfold = {i: self._cache.folded(convs[i].weight) for i in E.FOLD_LAYERS} if self.fold else {}
         last = convs[8]
-        E.conv3x3_last(cur, last.weight, self._cache.packed(last.weight, cout_pad=16), last.bias, out,
-                       self.exporting)
-        return out
+        return E.run_decoder(self._buf, t, wpk, wfold, [c.bias for c in convs], last.weight,
+                             self._cache.packed(last.weight, cout_pad=16), self.exporting, None, self.conv_impl,
+                             L.CONV_AUTO, self.fold, key="d")
 
 
 class StyleTransferNet(nn.Module):

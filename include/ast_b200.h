@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 1
+#define AST_ABI_VERSION 2
 
 /* error codes (negative) */
 #define AST_E_BADARG   (-1)  /* null pointer / non-positive size */
@@ -146,9 +146,15 @@ int ast_gram_bwd(const float* x, const float* gg, float* gx, int B, int C, int64
 #define AST_EPI_PLAIN 0 /* out[h][w]                          (Ho,Wo) = (H,W)      */
 #define AST_EPI_POOL2 1 /* 2x2/2 max pool of relu(conv)       (Ho,Wo) = (H/2,W/2)  */
 #define AST_EPI_UP2   2 /* nearest x2 upsample of relu(conv)  (Ho,Wo) = (2H,2W)    */
+#define AST_EPI_UPFOLD 4 /* the conv AFTER an Upsample(x2, nearest) + ReflectionPad2d(1) (models.py:602-604, 616-618,
+                            622-624), evaluated as four parity-specific 2x2 convs on the LOW-res map: `in` is the
+                            low-res (H,W) tensor with an AST_HALO_CLAMP halo, `wpk` comes from
+                            ast_pack_conv_weight_fold, (Ho,Wo) = (2H,2W).  tcgen05 path only. */
 /* halo written by the epilogue into the padded output */
 #define AST_HALO_KEEP    0 /* interior only (halo keeps the caller's zeros: next conv zero-pads) */
 #define AST_HALO_REFLECT 1 /* also write the ReflectionPad2d(1) halo of the output grid */
+#define AST_HALO_CLAMP   2 /* also write a replicate halo (-1 <- 0, X <- X-1): the reflection of the x2-upsampled
+                              grid expressed on the low-res grid; feeds AST_EPI_UPFOLD.  tcgen05 path only. */
 /* implementation selector */
 #define AST_CONV_AUTO   0 /* tcgen05 implicit GEMM when Cin%64==0 && Cout%64==0, else direct */
 #define AST_CONV_TC     1 /* force tcgen05 (AST_E_SHAPE if unsupported) */
@@ -186,6 +192,12 @@ int ast_conv3x3_fwd(const ast_conv_desc* d, const void* in, const void* wpk, con
 int ast_pack_conv_weight(const float* w_oihw, void* wpk, int Cout, int Cin, int flip, int cout_pad,
                          void* stream);
 
+/* OIHW fp32 [Cout][Cin][3][3] -> bf16 [16][Cout][Cin], the weights of AST_EPI_UPFOLD: for output parity (py, px) and
+ * low-res tap (a, b) in {0,1}^2, tile ((py*2+px)*2+a)*2+b holds the fp32 sum of the 3x3 taps (kh, kw) that land on
+ * that low-res pixel -- rows: py=0: a=0 <- {kh 0}, a=1 <- {kh 1,2}; py=1: a=0 <- {kh 0,1}, a=1 <- {kh 2}; columns
+ * alike -- rounded to bf16 once.  Replaces nn.Upsample + nn.ReflectionPad2d + nn.Conv2d, models.py:602-604 etc. */
+int ast_pack_conv_weight_fold(const float* w_oihw, void* wpk, int Cout, int Cin, void* stream);
+
 /* First VGG layer: Normalization (models.py:129-131) + conv_1 (3->Cout, zero pad) + ReLU from
  * the reference's NCHW fp32 image straight into the native layout.  Cout == 64 runs on the tensor
  * cores (im2col A tile built in shared memory, K = 27 padded to 32) unless impl = AST_CONV_DIRECT.
@@ -212,15 +224,25 @@ int ast_nchw_to_native(const float* nchw, void* native, int N, int C, int H, int
 int ast_native_to_nchw(const void* native, float* nchw, int N, int C, int H, int W,
                        void* stream);
 
+/* Input path: images cross PCIe as bytes.
+ *   ast_u8hwc_to_nchw : uint8 [N][H][W][3] -> fp32 [N][3][H][W] = u8 / 255 (IEEE division), what the loader's
+ *                       transforms.ToTensor() computes on the host (data_loader.py:114, 132).
+ *   ast_nchw_to_u8hwc : fp32 [N][3][H][W] -> uint8 [N][H][W][3] = trunc(clamp(x, 0, 1) * 255): Hardtanh(0,1) of the
+ *                       exporting decoder (models.py:315-316) followed by transforms.ToPILImage()'s
+ *                       pic.mul(255).byte() (train.py:18).  NaN maps to 0.
+ * The u8 pointer must be 4-byte aligned, the fp32 pointer 16-byte aligned. */
+int ast_u8hwc_to_nchw(const void* u8_nhwc, float* nchw, int N, int H, int W, void* stream);
+int ast_nchw_to_u8hwc(const float* nchw, void* u8_nhwc, int N, int H, int W, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K1n  AdaIN on the native layout (in-pipeline form of K1; same arithmetic).
- *   content : bf16 [N][H+2][W+2][C]; styles[k] : bf16 [N][Hs+2][Ws+2][C]
+ *   content : bf16 [N][H+2][W+2][C]; styles[k] : bf16 [N][Hs[k]+2][Ws[k]+2][C] (each style map has its own size)
  *   out     : bf16 [N][H+2][W+2][C], halo per `halo`
  *   ws      : >= ast_adain_native_ws_bytes(N, C, K) bytes
  * ------------------------------------------------------------------------------------- */
 size_t ast_adain_native_ws_bytes(int N, int C, int K);
 int ast_adain_native_fwd(const void* content, const void* const* styles, const float* style_w,
-                         int K, void* out, int N, int C, int H, int W, int Hs, int Ws,
+                         int K, void* out, int N, int C, int H, int W, const int* Hs, const int* Ws,
                          float alpha, float eps, unsigned flags, int halo,
                          void* ws, size_t ws_bytes, void* stream);
 

@@ -260,6 +260,127 @@ def golden_autoencoder(M, out):
         out["act_eval_dec_of_code"] = ae3.decoder(z).numpy()
 
 
+def _load_vgg_into(enc, vw, vb):
+    convs = [l for l in enc._vgg_layers if isinstance(l, torch.nn.Conv2d)]
+    assert len(convs) == 16
+    with torch.no_grad():
+        for c, w, b in zip(convs, vw, vb):
+            c.weight.copy_(w)
+            c.bias.copy_(b)
+
+
+def golden_bigsizes(M, out):
+    """The classic path AT THE BENCHMARKED SIZES, from the genuine reference pieces (models.py:186-240 encoder,
+    :43-51 AdaIN, :471 alpha blend, :598-628 decoder): BASELINE config 4 (one 512x512 pair, seeds 401 / 402) and
+    config 5 (2048x2048 content seed 501, four 2048x2048 styles seed 502, weights (.4,.3,.2,.1), alpha 1.0 and 0.6).
+    The K-style mix is not in the reference; by AdaIN's linearity in the style statistics it is
+    sum_k w_k * AdaIN(f_c, f_s_k) with the GENUINE AdaIN module (weights sum to 1).  Stored: a 64x64 crop, a stride-8
+    subsample, image statistics, and a subsample of the relu4_1 content map."""
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+    enc = M.PretrainedEncoder(['relu_9']).eval()
+    _load_vgg_into(enc, vw, vb)
+    dec = ref_loader.build_reference_classic_decoder()
+    with torch.no_grad():
+        for c, w, b in zip([l for l in dec if isinstance(l, torch.nn.Conv2d)], dw, db):
+            c.weight.copy_(w)
+            c.bias.copy_(b)
+    adain = M.AdaIN()
+
+    def store(tag, img, fc):
+        H = img.shape[2]
+        a = H // 2 - 32
+        out[f"{tag}_img_crop"] = img[:, :, a:a + 64, a:a + 64].numpy()
+        out[f"{tag}_img_corner"] = img[:, :, :48, H - 48:].numpy()        # includes two image borders (reflection pad)
+        out[f"{tag}_img_sub8"] = img[:, :, ::8, ::8].numpy()
+        out[f"{tag}_img_stats"] = np.array([img.mean().item(), img.std().item(), img.min().item(), img.max().item()])
+        out[f"{tag}_fc_sub"] = fc[:, ::16, ::4, ::4].numpy()
+
+    with torch.no_grad():
+        c, s = R.rand_image(1, 512, 401), R.rand_image(1, 512, 402)
+        fc, fs = enc(c)[0], enc(s)[0]
+        img = dec(adain(fc, fs))
+        store("cfg4", img, fc)
+        del fs, img
+        c = R.rand_image(1, 2048, 501)
+        styles = R.rand_image(4, 2048, 502)
+        w = (0.4, 0.3, 0.2, 0.1)
+        fc = enc(c)[0]
+        t = None
+        for k in range(4):
+            tk = adain(fc, enc(styles[k:k + 1])[0]) * w[k]
+            t = tk if t is None else t + tk
+        out["cfg5_t_sub"] = t[:, ::16, ::4, ::4].numpy()
+        for alpha, tag in ((1.0, "cfg5_a10"), (0.6, "cfg5_a06")):
+            tb = t if alpha == 1.0 else alpha * t + (1 - alpha) * fc        # models.py:471
+            store(tag, dec(tb), fc)
+
+
+def golden_autoencoder256(M, out):
+    """The genuine ``AutoEncoder`` at BASELINE config 3's resolution (256x256, batch 2) on the non-degenerate seeded
+    state (restate_ae.activate_gates): eval-mode forward with running statistics calibrated on the batch, and one
+    train_autoencoder.py:111-139 training step (loss terms, gradient norms of every parameter, full gradients of the
+    GOLDEN_GRAD_KEYS, running statistics).  Tensors are stored subsampled."""
+    import torch.nn.functional as F
+    from oracle import restate_ae as A
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    enc = M.PretrainedEncoder().eval()
+    _load_vgg_into(enc, vw, vb)
+    x = R.rand_image(2, 256, 301)
+    torch.manual_seed(2)
+    ae = M.AutoEncoder()
+    ae.load_state_dict(A.activate_gates(ae.state_dict()), strict=True)
+    # ---- one training step from the seeded state ----
+    ae.train()
+    recon = ae(x)
+    recon_loss = torch.nn.HuberLoss()(recon, x)
+    cm, rm = enc(x), enc(recon)
+    perp = None
+    for a, b in zip(rm, cm):
+        l = F.huber_loss(a, b.detach())
+        perp = l if perp is None else perp + l
+    loss = 100.0 * recon_loss + 0.01 * perp
+    loss.backward()
+    out["t256_recon_sub4"] = recon.detach()[:, :, ::4, ::4].numpy()
+    out["t256_recon_stats"] = np.array([recon.mean().item(), recon.std().item(), recon.min().item(), recon.max().item()])
+    out["t256_losses"] = np.array([loss.item(), recon_loss.item(), perp.item()])
+    named = dict(ae.named_parameters())
+    gkeys = sorted(named.keys())
+    out["t256_grad_keys"] = np.array(gkeys)
+    out["t256_grad_norm"] = np.array([named[k].grad.double().norm().item() for k in gkeys])
+    for k in A.GOLDEN_GRAD_KEYS:
+        out["t256_grad::" + k] = named[k].grad.numpy()
+    sd = ae.state_dict()
+    for k in A.GOLDEN_BUFFER_KEYS:
+        out["t256_buf::" + k] = sd[k].numpy()
+    # ---- eval mode, running statistics calibrated on x (momentum 1.0 for one training-mode forward) ----
+    torch.manual_seed(2)
+    ae3 = M.AutoEncoder()
+    ae3.load_state_dict(A.activate_gates(ae3.state_dict()), strict=True)
+    bns = [m for m in ae3.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:
+        m.momentum = 1.0
+    ae3.train()
+    with torch.no_grad():
+        ae3(x)
+    for m in bns:
+        m.momentum = 0.1
+    ae3.eval()
+    with torch.no_grad():
+        rec = ae3(x)
+        out["e256_recon_sub4"] = rec[:, :, ::4, ::4].numpy()
+        out["e256_recon_crop"] = rec[:, :, 96:160, 96:160].numpy()
+        taps = ae3.encoder(x, out_layers=[0, 2, 4, 7, 12, 14])
+        for i, t in zip((0, 2, 4, 7, 12, 14), taps):
+            st = max(1, t.shape[2] // 32)
+            out[f"e256_enc{i}_sub"] = t[:, :, ::st, ::st].numpy()
+        z = ae3.ada_out(torch.cat((taps[4], taps[5]), dim=1))
+        out["e256_code"] = z.numpy()
+        out["e256_dec_of_code_sub4"] = ae3.decoder(z)[:, :, ::4, ::4].numpy()
+
+
 def golden_hist(Ls, out):
     """compute_hist_loss (losses.py:8-87) value and input gradients from the genuine reference: image-like inputs with
     a few values outside [0, 1] (a stylised image is not clamped, models.py:315)."""
@@ -362,7 +483,9 @@ def main():
                            ("networks", golden_networks, (M,)),
                            ("autoencoder", golden_autoencoder, (M,)),
                            ("adaattn", golden_adaattn, (M,)),
-                           ("hist", golden_hist, (Ls,))):
+                           ("hist", golden_hist, (Ls,)),
+                           ("bigsizes", golden_bigsizes, (M,)),
+                           ("autoencoder256", golden_autoencoder256, (M,))):
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         d = dict(_versions())

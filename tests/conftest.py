@@ -47,3 +47,15 @@ def golden_losses():
 @pytest.fixture(scope="session")
 def golden_networks():
     return load_golden("networks")
+
+
+@pytest.fixture(scope="session")
+def golden_big():
+    """The classic path at the benchmarked sizes (512x512 config 4, 2048x2048 config 5), made by the genuine reference."""
+    return load_golden("bigsizes")
+
+
+@pytest.fixture(scope="session")
+def golden_ae256():
+    """The genuine AutoEncoder at config 3's resolution (256x256, batch 2)."""
+    return load_golden("autoencoder256")

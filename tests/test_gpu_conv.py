@@ -76,6 +76,123 @@ def test_tc_conv_reflect_halo(shape, epi, kern):
     _run(N, H, W, cin, cout, True, epi, True, KERNELS[kern], seed=3 + epi)
 
 
+def _fold_reference(x, w, b, relu, wq=None):
+    """Upsample(x2, nearest) -> ReflectionPad2d(1) -> Conv2d(3x3) (models.py:602-604) in fp32 on the CPU; with ``wq``
+    (a rounding function) the same thing as the four parity-specific 2x2 convs with pre-summed, rounded weights --
+    the arithmetic contract of AST_EPI_UPFOLD."""
+    if wq is None:
+        y = F.conv2d(F.pad(F.interpolate(x, scale_factor=2, mode="nearest"), (1, 1, 1, 1), mode="reflect"), w, b)
+    else:
+        N, _, H, W = x.shape
+        xp = F.pad(x, (1, 1, 1, 1), mode="replicate")
+        y = torch.empty(N, w.shape[0], 2 * H, 2 * W)
+        rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+        for py in (0, 1):
+            for px in (0, 1):
+                wf = torch.zeros(w.shape[0], w.shape[1], 2, 2)
+                for a in (0, 1):
+                    for bb in (0, 1):
+                        for kh in rows[py][a]:
+                            for kw in rows[px][bb]:
+                                wf[:, :, a, bb] += w[:, :, kh, kw]
+                yp = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], wq(wf), b)
+                y[:, :, py::2, px::2] = yp
+    return F.relu(y) if relu else y
+
+
+def _run_fold(N, H, W, cin, cout, relu, out_halo, impl, seed=0):
+    from arbitrarystyletransfer_b200 import _lib as L, engine as E
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(N, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    exact = bf16r(_fold_reference(x, w, b, relu, wq=bf16r))
+    ref32 = _fold_reference(x, w, b, relu)
+    assert rel_err(exact, ref32) < 4e-3          # the fold itself (pre-summed bf16 weights) vs the fp32 sequence
+    xin = F.pad(x, (1, 1, 1, 1), mode="replicate").permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    wf = E.pack_conv_weight_fold(w.cuda())
+    out = torch.full((N, 2 * H + 2, 2 * W + 2, cout), 7.0, device="cuda", dtype=torch.bfloat16)
+    E.conv3x3(xin, wf, b.cuda(), out, N=N, H=H, W=W, cin=cin, cout=cout, relu=relu, epilogue=L.EPI_UPFOLD,
+              halo=out_halo, impl=impl)
+    torch.cuda.synchronize()
+    got = native_to_padded_nchw(out).cpu()
+    inner = got[:, :, 1:-1, 1:-1]
+    assert rel_err(inner, exact) < 2e-3, rel_err(inner, exact)
+    torch.testing.assert_close(inner, exact, rtol=8e-3, atol=2e-3)
+    assert rel_err(inner, ref32) < 5e-3
+    mode = {L.HALO_REFLECT: "reflect", L.HALO_CLAMP: "replicate"}.get(out_halo)
+    if mode:
+        torch.testing.assert_close(got, F.pad(exact, (1, 1, 1, 1), mode=mode), rtol=8e-3, atol=2e-3)
+    else:
+        assert (got[:, :, 0, :] == 7.0).all() and (got[:, :, :, -1] == 7.0).all()
+
+
+FOLD_SHAPES = [
+    # N, H, W, cin, cout   (low-res input)
+    (1, 16, 8, 64, 64),       # one tile, resident weights
+    (2, 20, 12, 64, 64),      # partial tiles
+    (1, 16, 16, 128, 128),    # BN = 128: one row parity per tile
+    (1, 8, 8, 256, 256),      # BN = 256: one parity per tile
+    (3, 12, 20, 128, 64),     # two channel blocks, not resident
+    (1, 24, 40, 64, 128),
+    (2, 9, 7, 256, 128),      # ragged
+]
+
+
+@pytest.mark.parametrize("shape", FOLD_SHAPES)
+def test_upsample_fold_conv(shape):
+    """Upsample -> ReflectionPad -> Conv3x3 on the low-res map (conv3x3_fold_kernel)."""
+    from arbitrarystyletransfer_b200 import _lib as L
+    N, H, W, cin, cout = shape
+    _run_fold(N, H, W, cin, cout, True, L.HALO_REFLECT, L.CONV_TC, seed=H + cin)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_upsample_fold_forced_n_block_many_tiles(bn):
+    from arbitrarystyletransfer_b200 import _lib as L
+    _run_fold(2, 64, 48, 128, 256, True, L.HALO_REFLECT, bn, seed=bn)       # > 148 tiles: stage / phase wrap
+    _run_fold(1, 16, 8, 64, 256, False, L.HALO_KEEP, bn, seed=bn + 1)
+
+
+def test_upsample_fold_many_tiles_resident():
+    from arbitrarystyletransfer_b200 import _lib as L
+    _run_fold(4, 96, 64, 64, 64, True, L.HALO_REFLECT, L.CONV_TC, seed=77)   # 192 tiles, weights resident
+    _run_fold(1, 16, 16, 64, 64, True, L.HALO_CLAMP, L.CONV_TC, seed=78)
+
+
+@pytest.mark.parametrize("epi", [0, 1])
+def test_tc_conv_clamp_halo(epi):
+    """AST_HALO_CLAMP: the producer of a folded conv writes the replicate halo of its (low-res) output."""
+    from arbitrarystyletransfer_b200 import _lib as L, engine as E
+    g = torch.Generator().manual_seed(5)
+    N, H, W, cin, cout = 2, 24, 20, 128, 64
+    x = bf16r(torch.randn(N, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    exp, _, _ = oracle_conv_native(x, w, b, True, epi, "reflect")
+    xin = E.nchw_to_native(x.cuda(), reflect=True)
+    Ho, Wo = (H // 2, W // 2) if epi == 1 else (H, W)
+    out = torch.full((N, Ho + 2, Wo + 2, cout), 7.0, device="cuda", dtype=torch.bfloat16)
+    E.conv3x3(xin, E.pack_conv_weight(w.cuda()), b.cuda(), out, N=N, H=H, W=W, cin=cin, cout=cout, relu=True,
+              epilogue=epi, halo=L.HALO_CLAMP, impl=L.CONV_TC)
+    got = native_to_padded_nchw(out).cpu()
+    torch.testing.assert_close(got, F.pad(exp, (1, 1, 1, 1), mode="replicate"), rtol=8e-3, atol=2e-3)
+
+
+def test_decoder_fold_matches_unfolded(tmp_path):
+    """The whole classic decoder with and without the folded upsample convs (same weights, same input)."""
+    from arbitrarystyletransfer_b200 import models as M
+    torch.manual_seed(1)
+    dec = M.ClassicDecoder().cuda()
+    f = torch.relu(torch.randn(2, 512, 12, 20, generator=torch.Generator().manual_seed(3))).cuda()
+    with torch.no_grad():
+        dec.fold = True
+        a = dec(f).clone()
+        dec.fold = False
+        b = dec(f)
+    assert rel_err(a.cpu(), b.cpu()) < 5e-3
+
+
 @pytest.mark.parametrize("bn", [64, 128, 256, 1064, 1128, 1256])
 def test_tc_conv_forced_n_block(bn):
     _run(2, 16, 32, 128, 256, True, 0, True, bn, seed=11)

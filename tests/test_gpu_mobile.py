@@ -611,3 +611,98 @@ def test_autoencoder_config3_shape_properties(ae):
     with torch.no_grad():
         a, b = ae(x), ae(x)
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 3 AT ITS OWN RESOLUTION (256 x 256, batch 2): fixtures made by the genuine reference AutoEncoder
+# (oracle/make_golden.py::golden_autoencoder256) on the non-degenerate seeded state.
+# ------------------------------------------------------------------------------------------------
+def _sub(t):
+    st = max(1, t.shape[2] // 32)
+    return t[:, :, ::st, ::st]
+
+
+# bars for the whole-network comparisons at 256 x 256 (relative L2 unless noted); see DESIGN.md section 5
+AE256_TAP_BAR = 6e-2          # every encoder tap, the code and the decoder signal, eval mode
+AE256_GRAD_COS = 0.97         # cosine of every GOLDEN_GRAD_KEYS gradient
+AE256_NORM_BAND = 0.25        # |gradient-norm ratio - 1| over all non-negligible parameters
+
+
+def test_autoencoder_256_eval_vs_reference_golden(golden_ae256, ae):
+    g = golden_ae256
+    x = R.rand_image(2, 256, 301)
+    act = A.activate_gates(A.make_ae_state(2))
+    Q = A.calibrate_running_stats(A.clone_state(act), x)
+    ae.load_state_dict(Q, strict=True)
+    ae.eval()
+    bias = act["decoder._img_out.bias"]
+    with torch.no_grad():
+        rec = ae(x.cuda())
+        taps = ae.encoder(x.cuda(), out_layers=[0, 2, 4, 7, 12, 14])
+        z = ae.ada_out(torch.cat((taps[4], taps[5]), dim=1))
+        dimg = ae.decoder(T(g["e256_code"]).cuda())
+    errs = {f"enc{i}": rel(_sub(t), T(g[f"e256_enc{i}_sub"])) for i, t in zip((0, 2, 4, 7, 12, 14), taps)}
+    errs["code"] = rel(z, T(g["e256_code"]))
+    errs["decoder(code)"] = rel(_signal(dimg[:, :, ::4, ::4], bias), _signal(T(g["e256_dec_of_code_sub4"]), bias))
+    errs["recon signal"] = rel(_signal(rec[:, :, ::4, ::4], bias), _signal(T(g["e256_recon_sub4"]), bias))
+    errs["recon"] = rel(rec[:, :, ::4, ::4], T(g["e256_recon_sub4"]))
+    print("AutoEncoder 256x256 eval, relative L2 vs the genuine reference:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < AE256_TAP_BAR, errs
+    assert errs["enc0"] < 5e-3 and errs["recon"] < 1e-2, errs
+    assert R.psnr(rec[:, :, 96:160, 96:160].cpu(), T(g["e256_recon_crop"])) >= 40.0
+
+
+def test_autoencoder_256_train_step_vs_reference_golden(golden_ae256, ae):
+    """One train_autoencoder.py:111-139 step at 256 x 256, batch 2: loss terms, every parameter's gradient norm, full
+    gradients of the GOLDEN_GRAD_KEYS, BatchNorm running statistics."""
+    from arbitrarystyletransfer_b200 import models as M
+    from arbitrarystyletransfer_b200.losses import compute_content_loss
+    g = golden_ae256
+    x = R.rand_image(2, 256, 301).cuda()
+    act = A.activate_gates(A.make_ae_state(2))
+    ae.load_state_dict(act, strict=True)
+    bias = act["decoder._img_out.bias"]
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    enc = M.PretrainedEncoder().cuda().eval()
+    with torch.no_grad():
+        for c, w, b in zip(enc._convs(), vw, vb):
+            c.weight.copy_(w)
+            c.bias.copy_(b)
+    for p in enc.parameters():
+        p.requires_grad_(False)
+    ae.train()
+    for p in ae.parameters():
+        p.grad = None
+    recon = ae(x)
+    sig = rel(_signal(recon.detach()[:, :, ::4, ::4], bias), _signal(T(g["t256_recon_sub4"]), bias))
+    recon_loss = compute_content_loss(recon, x)
+    with torch.no_grad():
+        cm = enc(x)
+    perp = None
+    for a, b in zip(enc(recon), cm):
+        l = compute_content_loss(a, b.detach())
+        perp = l if perp is None else perp + l
+    loss = 100.0 * recon_loss + 0.01 * perp
+    wl = g["t256_losses"]
+    loss.backward()
+    named = dict(ae.named_parameters())
+    gkeys = list(g["t256_grad_keys"])
+    norms = np.array([named[k].grad.double().norm().item() for k in gkeys])
+    big = g["t256_grad_norm"] > 1e-4 * g["t256_grad_norm"].max()
+    ratio = (norms / np.maximum(g["t256_grad_norm"], 1e-30))[big]
+    report = {k.replace("encoder.mob_net.", "e").replace("decoder._decoder_blocks.", "d").replace("._layers.", ".L"):
+              (round(cos(named[k].grad, T(g["t256_grad::" + k])), 4), round(rel(named[k].grad, T(g["t256_grad::" + k])), 4))
+              for k in A.GOLDEN_GRAD_KEYS if T(g["t256_grad::" + k]).norm() > 1e-4 * g["t256_grad_norm"].max()}
+    print(f"AutoEncoder 256x256 train step: recon signal rel {sig:.2e}; losses cuda ({recon_loss.item():.6f}, "
+          f"{perp.item():.5f}) reference ({wl[1]:.6f}, {wl[2]:.5f}); gradient-norm ratio min/median/max "
+          f"{ratio.min():.3f}/{np.median(ratio):.3f}/{ratio.max():.3f} over {int(big.sum())} tensors; "
+          f"(cosine, rel L2) per golden gradient: {report}")
+    assert sig < AE256_TAP_BAR
+    assert abs(recon_loss.item() - wl[1]) / wl[1] < 2e-3 and abs(perp.item() - wl[2]) / wl[2] < 2e-2
+    assert np.all(np.abs(ratio - 1) < AE256_NORM_BAND), (np.array(gkeys)[big][np.abs(ratio - 1) >= AE256_NORM_BAND])
+    assert abs(np.median(ratio) - 1) < 0.03
+    assert min(c for c, _ in report.values()) > AE256_GRAD_COS, report
+    sd = ae.state_dict()
+    for k in A.GOLDEN_BUFFER_KEYS:
+        torch.testing.assert_close(sd[k].cpu().float(), T(g["t256_buf::" + k]).float(), rtol=2e-2, atol=2e-3)

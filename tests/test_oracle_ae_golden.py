@@ -132,3 +132,55 @@ def test_bf16_storage_contract_distance_from_fp32(g, state):
     e = {k: rel(keep[k], T(g["act_eval_" + k])) for k in ("enc0", "enc2", "enc12", "enc14", "code")}
     assert e["enc0"] < 3e-3 and e["enc2"] < 1.5e-2 and e["enc12"] < 0.12 and e["enc14"] < 0.15 and e["code"] < 0.15, e
     assert R.psnr(img, T(g["act_eval_recon"])) >= 50.0
+
+
+# ---- config 3's own resolution: 256 x 256, batch 2 (make_golden.golden_autoencoder256) ----------------------------
+def _sub(t):
+    st = max(1, t.shape[2] // 32)
+    return t[:, :, ::st, ::st]
+
+
+def test_ae256_train_step_and_eval_vs_reference(golden_ae256, state):
+    g = golden_ae256
+    x = R.rand_image(2, 256, 301)
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    act = A.activate_gates(state)
+    P = A.clone_state(act, requires_grad=True)
+    loss, recon_loss, perp, recon = A.ae_losses(P, x, vw, vb)
+    np.testing.assert_allclose(recon.detach()[:, :, ::4, ::4].numpy(), g["t256_recon_sub4"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose([loss.item(), recon_loss.item(), perp.item()], g["t256_losses"], rtol=1e-5)
+    loss.backward()
+    gkeys = list(g["t256_grad_keys"])
+    norms = np.array([P[k].grad.double().norm().item() for k in gkeys])
+    np.testing.assert_allclose(norms, g["t256_grad_norm"], rtol=5e-3, atol=1e-12)
+    for k in A.GOLDEN_GRAD_KEYS:
+        a, b = P[k].grad.double(), T(g["t256_grad::" + k]).double()
+        assert ((a - b).norm() / b.norm()).item() < 5e-3, k
+    for k in A.GOLDEN_BUFFER_KEYS:
+        torch.testing.assert_close(P[k].detach(), T(g["t256_buf::" + k]), rtol=1e-4, atol=1e-6)
+    Q = A.calibrate_running_stats(A.clone_state(act), x)
+    with torch.no_grad():
+        taps = A.encoder_forward(Q, x, (0, 2, 4, 7, 12, 14))
+        for i, t in zip((0, 2, 4, 7, 12, 14), taps):
+            np.testing.assert_allclose(_sub(t).numpy(), g[f"e256_enc{i}_sub"], rtol=1e-3, atol=1e-4, err_msg=str(i))
+        rec = A.autoencoder_forward(Q, x)
+        np.testing.assert_allclose(rec[:, :, ::4, ::4].numpy(), g["e256_recon_sub4"], rtol=1e-3, atol=1e-4)
+
+
+def test_ae256_bf16_storage_contract_distance(golden_ae256, state):
+    """What bf16 storage costs at config 3's resolution: BatchNorm statistics are taken over 2 x 256 x 256 ... 2 x 32 x 32
+    elements instead of 2 x 4 x 4, so the amplification seen on the 32 x 32 fixtures is gone."""
+    g = golden_ae256
+    x = R.rand_image(2, 256, 301)
+    Q = A.calibrate_running_stats(A.clone_state(A.activate_gates(state)), x)
+    with torch.no_grad():
+        img, keep = A.autoencoder_forward_bf16(Q, x, want=("enc0", "enc2", "enc12", "enc14", "code"))
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+    e = {k: rel(_sub(keep[k]), T(g[f"e256_{k}_sub"])) for k in ("enc0", "enc2", "enc12", "enc14")}
+    e["code"] = rel(keep["code"], T(g["e256_code"]))
+    e["recon"] = rel(img[:, :, ::4, ::4], T(g["e256_recon_sub4"]))
+    print("bf16 storage contract vs fp32 reference at 256x256:", {k: f"{v:.2e}" for k, v in e.items()})
+    assert max(e.values()) < 5e-2, e

@@ -150,3 +150,44 @@ def test_hist_loss_restatement_matches_reference_golden():
         torch.testing.assert_close(h, R.soft_histogram(x.detach()), rtol=1e-5, atol=1e-6)
         # N = C*H (losses.py:54), not C*H*W: the bins of one image sum to W
         assert h.sum(1).mean().item() == pytest.approx(x.shape[3] * ((x.detach() > 0.02) & (x.detach() < 0.98)).float().mean().item(), rel=0.1)
+
+
+# ---- the oracle at the benchmarked sizes (fixtures made by the genuine reference: make_golden.golden_bigsizes) ----
+@pytest.fixture(scope="module")
+def classic_weights():
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+    return vw, vb, dw, db
+
+
+def _views(img):
+    S = img.shape[2]
+    a = S // 2 - 32
+    return {"crop": img[:, :, a:a + 64, a:a + 64], "corner": img[:, :, :48, S - 48:], "sub8": img[:, :, ::8, ::8]}
+
+
+def test_oracle_config4_512_vs_reference(golden_big, classic_weights):
+    vw, vb, dw, db = classic_weights
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    with torch.no_grad():
+        img = R.stylize(R.rand_image(1, 512, 401), R.rand_image(1, 512, 402), vw, vb, dw, db)
+    for k, v in _views(img).items():
+        np.testing.assert_allclose(v.numpy(), golden_big[f"cfg4_img_{k}"], rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_config5_2048_vs_reference(golden_big, classic_weights):
+    """The K-style mix of the oracle (adain_multi: one affine with mixed statistics) against the fixture built from
+    the reference's own AdaIN applied per style and summed with the weights; 2048x2048, about 40 s of CPU."""
+    vw, vb, dw, db = classic_weights
+    c = R.rand_image(1, 2048, 501)
+    styles = R.rand_image(4, 2048, 502)
+    w = [0.4, 0.3, 0.2, 0.1]
+    with torch.no_grad():
+        fc = R.vgg_relu4_1(c, vw, vb)
+        fs = [R.vgg_relu4_1(styles[k:k + 1], vw, vb) for k in range(4)]
+        np.testing.assert_allclose(fc[:, ::16, ::4, ::4].numpy(), golden_big["cfg5_a10_fc_sub"], rtol=1e-4, atol=1e-5)
+        t = R.adain_multi(fc, fs, w, 0.6)
+        img = R.decoder_forward(t, dw, db)
+    for k, v in _views(img).items():
+        np.testing.assert_allclose(v.numpy(), golden_big[f"cfg5_a06_img_{k}"], rtol=2e-4, atol=2e-5)
