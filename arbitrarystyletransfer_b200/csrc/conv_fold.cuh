@@ -62,13 +62,14 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
     const bool in_img = (h < p.H) && (w < p.W);
     int py0, npy, px0, npx;
     fold_parities<C::NPAR>(pg, py0, npy, px0, npx);
-    mbar_wait(tfull_bar0 + 8u * as, aphase);
+    if (p.epi_sleep_ns) mbar_wait_sleep(tfull_bar0 + 8u * as, aphase, p.epi_sleep_ns); else mbar_wait(tfull_bar0 + 8u * as, aphase);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
     uint32_t vnext[CH];
-    if (g < NCH) tmem_ld_cols(trow + g * CH, vnext);
+    const bool skip_ld = (p.dbg_flags & 4) != 0;
+    if (g < NCH && !skip_ld) tmem_ld_cols(trow + g * CH, vnext);
 #pragma unroll 1
-    for (int chunk = g; chunk < NCH; chunk += NG) {
+    for (int chunk = g; chunk < NCH && !skip_ld; chunk += NG) {
       uint32_t v[CH];
       tmem_ld_wait();
 #pragma unroll
@@ -94,7 +95,7 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
 #pragma unroll
         for (int i = 0; i < CH / 2; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
       }
-      if (in_img) {
+      if (in_img && !(p.dbg_flags & 2)) {
         int rows[4], cols[4];
         const int nr = out_targets<AST_EPI_PLAIN>(2 * h + py, p.Ho, p.halo, rows);
         const int nc = out_targets<AST_EPI_PLAIN>(2 * w + px, p.Wo, p.halo, cols);
@@ -175,6 +176,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      bool a_filled = false, b_filled = false;   // dbg_flags & 1 (bottleneck elimination): ring slots loaded once
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int t = tile;
         const int nb = t % p.n_blocks; t /= p.n_blocks;
@@ -187,9 +189,14 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int h0 = thi * T2_H, w0 = twi * T2_W;
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = px0; kw <= px0 + npx; ++kw) {
-            mbar_wait(aempty(sa), pa ^ 1u);
-            mbar_expect_tx(afull(sa), A2_BYTES);
-            tma_load_4d(a_base + sa * A2_BYTES, &tmA, afull(sa), cb * KBLK, w0 + kw, h0, n);
+            if (p.prod_sleep_ns) mbar_wait_sleep(aempty(sa), pa ^ 1u, p.prod_sleep_ns); else mbar_wait(aempty(sa), pa ^ 1u);
+            if ((p.dbg_flags & 1) && a_filled) {
+              mbar_arrive(afull(sa));
+            } else {
+              mbar_expect_tx(afull(sa), A2_BYTES);
+              tma_load_4d(a_base + sa * A2_BYTES, &tmA, afull(sa), cb * KBLK, w0 + kw, h0, n);
+            }
+            if (sa + 1 == C::NA) a_filled = true;
             if (++sa == C::NA) { sa = 0; pa ^= 1u; }
             if (!resident) {
               // the weight tiles this box feeds, in the order the MMA warp consumes them
@@ -197,19 +204,24 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int py = py0; py < py0 + npy; ++py)
                 for (int px = px0; px < px0 + npx; ++px)
                   if (kw - px >= 0 && kw - px <= 1) cnt += 2;
-              mbar_wait(bempty(sb), pb ^ 1u);
-              mbar_expect_tx(bfull(sb), cnt * C::B_BYTES);
-              int slot = 0;
-              for (int py = py0; py < py0 + npy; ++py)
-                for (int px = px0; px < px0 + npx; ++px) {
-                  const int b = kw - px;
-                  if (b < 0 || b > 1) continue;
-                  for (int a = 0; a < 2; ++a) {
-                    tma_load_3d(b_base + (sb * C::GSLOTS + slot) * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, cob * BN,
-                                ((py * 2 + px) * 2 + a) * 2 + b);
-                    ++slot;
+              if (p.prod_sleep_ns) mbar_wait_sleep(bempty(sb), pb ^ 1u, p.prod_sleep_ns); else mbar_wait(bempty(sb), pb ^ 1u);
+              if ((p.dbg_flags & 1) && b_filled) {
+                mbar_arrive(bfull(sb));
+              } else {
+                mbar_expect_tx(bfull(sb), cnt * C::B_BYTES);
+                int slot = 0;
+                for (int py = py0; py < py0 + npy; ++py)
+                  for (int px = px0; px < px0 + npx; ++px) {
+                    const int b = kw - px;
+                    if (b < 0 || b > 1) continue;
+                    for (int a = 0; a < 2; ++a) {
+                      tma_load_3d(b_base + (sb * C::GSLOTS + slot) * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, cob * BN,
+                                  ((py * 2 + px) * 2 + a) * 2 + b);
+                      ++slot;
+                    }
                   }
-                }
+              }
+              if (sb + 1 == C::NBG) b_filled = true;
               if (++sb == C::NBG) { sb = 0; pb ^= 1u; }
             }
           }

@@ -80,13 +80,20 @@ struct ConvParams {
   int cout_real;     // EPI_NCHW32 only: channels actually stored (<= BN)
   int clamp01;       // EPI_NCHW32 only: Hardtanh(0,1) (models.py:304, 315)
   long long* dbg;    // optional [gridDim.x][8] wait-cycle counters per role (AST_CONV_DEBUG=1)
+  uint32_t epi_sleep_ns, prod_sleep_ns;   // back-off of the waiting roles (mbar_wait_sleep); 0 = tight polling
+  int dbg_flags;     // AST_CONV_DBGFLAGS (bottleneck elimination, results are WRONG): 1 = operands loaded once per ring
+                     // slot, never refreshed; 2 = epilogue without global stores; 4 = epilogue without TMEM loads
 };
 
 constexpr int EPI_NCHW32 = 3;  // internal: last decoder layer, fp32 NCHW image out
 
 // wait + optional accounting of the cycles spent waiting (debug instrumentation)
-__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, bool dbg, long long& acc) {
-  if (!dbg) { mbar_wait(bar, parity); return; }
+__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, bool dbg, long long& acc,
+                                              uint32_t sleep_ns = 0) {
+  if (!dbg) {
+    if (sleep_ns) mbar_wait_sleep(bar, parity, sleep_ns); else mbar_wait(bar, parity);
+    return;
+  }
   const long long t0 = clock64();
   mbar_wait(bar, parity);
   acc += clock64() - t0;
@@ -192,13 +199,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
       nc = out_targets<EPI>(w, p.Wo, halo, cols);
     }
 
-    mbar_wait_acc(tfull_bar0 + 8u * as, aphase, p.dbg != nullptr, dbg_wait);
+    mbar_wait_acc(tfull_bar0 + 8u * as, aphase, p.dbg != nullptr, dbg_wait, p.epi_sleep_ns);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
     uint32_t vnext[CH];
-    if (g < NCH) tmem_ld_cols(trow + g * CH, vnext);
+    const bool skip_ld = (p.dbg_flags & 4) != 0;
+    if (g < NCH && !skip_ld) tmem_ld_cols(trow + g * CH, vnext);
 #pragma unroll 1
-    for (int chunk = g; chunk < NCH; chunk += NG) {
+    for (int chunk = g; chunk < NCH && !skip_ld; chunk += NG) {
       uint32_t v[CH];
       tmem_ld_wait();
 #pragma unroll
@@ -262,7 +270,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
             pk[i] = *reinterpret_cast<uint32_t*>(&a);
           }
         }
-        if (p.out) {
+        if (p.out && !(p.dbg_flags & 2)) {
           for (int ri = 0; ri < nr; ++ri) {
             for (int ci = 0; ci < nc; ++ci) {
               __nv_bfloat16* o = p.out +
@@ -501,6 +509,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      bool a_filled = false, b_filled = false;   // dbg_flags & 1: every ring slot has been loaded once
       long long dbg_pa = 0, dbg_pb = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int t = tile;
@@ -511,17 +520,27 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int h0 = thi * T2_H, w0 = twi * T2_W;
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = 0; kw < 3; ++kw) {
-            mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa);
-            mbar_expect_tx(afull(sa), A2_BYTES);
-            tma_load_4d(a_base + sa * A2_BYTES, &tmA, afull(sa), cb * KBLK, w0 + kw, h0, n);
+            mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa, p.prod_sleep_ns);
+            if ((p.dbg_flags & 1) && a_filled) {
+              mbar_arrive(afull(sa));
+            } else {
+              mbar_expect_tx(afull(sa), A2_BYTES);
+              tma_load_4d(a_base + sa * A2_BYTES, &tmA, afull(sa), cb * KBLK, w0 + kw, h0, n);
+            }
+            if (sa + 1 == C::NA) a_filled = true;
             if (++sa == C::NA) { sa = 0; pa ^= 1u; }
             if (!resident) {
               if constexpr (C::GROUPED) {
-                mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb);
-                mbar_expect_tx(bfull(sb), 3 * C::B_BYTES);
-                for (int kh = 0; kh < 3; ++kh)
-                  tma_load_3d(b_base + (sb * 3 + kh) * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, nb * BN,
-                              kh * 3 + kw);
+                mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb, p.prod_sleep_ns);
+                if ((p.dbg_flags & 1) && b_filled) {
+                  mbar_arrive(bfull(sb));
+                } else {
+                  mbar_expect_tx(bfull(sb), 3 * C::B_BYTES);
+                  for (int kh = 0; kh < 3; ++kh)
+                    tma_load_3d(b_base + (sb * 3 + kh) * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, nb * BN,
+                                kh * 3 + kw);
+                }
+                if (sb == 2) b_filled = true;
                 if (++sb == 3) { sb = 0; pb ^= 1u; }
               } else {
                 for (int kh = 0; kh < 3; ++kh) {
@@ -736,6 +755,11 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   if (impl == AST_CONV_TC_TAPBOX) { kwbox = 0; impl = AST_CONV_TC; }
   if (impl >= 1000) { kwbox = 0; impl -= 1000; }
   ConvParams p = {};
+  static const int dbg_flags = getenv("AST_CONV_DBGFLAGS") ? atoi(getenv("AST_CONV_DBGFLAGS")) : 0;
+  p.dbg_flags = dbg_flags;
+  static const int epi_sleep = getenv("AST_CONV_EPI_SLEEP") ? atoi(getenv("AST_CONV_EPI_SLEEP")) : 0;
+  static const int prod_sleep = getenv("AST_CONV_PROD_SLEEP") ? atoi(getenv("AST_CONV_PROD_SLEEP")) : 0;
+  p.epi_sleep_ns = (uint32_t)epi_sleep; p.prod_sleep_ns = (uint32_t)prod_sleep;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   const bool up = d->epilogue == AST_EPI_UP2 || d->epilogue == AST_EPI_UPFOLD;
   p.Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (up ? 2 * d->H : d->H);

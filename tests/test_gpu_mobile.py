@@ -624,6 +624,7 @@ def _sub(t):
 
 # bars for the whole-network comparisons at 256 x 256 (relative L2 unless noted); see DESIGN.md section 5
 AE256_TAP_BAR = 6e-2          # every encoder tap, the code and the decoder signal, eval mode
+AE256_TRAIN_BAR = 9e-2        # decoder signal of the train-mode forward (batch statistics)
 AE256_GRAD_COS = 0.97         # cosine of every GOLDEN_GRAD_KEYS gradient
 AE256_NORM_BAND = 0.25        # |gradient-norm ratio - 1| over all non-negligible parameters
 
@@ -698,7 +699,7 @@ def test_autoencoder_256_train_step_vs_reference_golden(golden_ae256, ae):
           f"{perp.item():.5f}) reference ({wl[1]:.6f}, {wl[2]:.5f}); gradient-norm ratio min/median/max "
           f"{ratio.min():.3f}/{np.median(ratio):.3f}/{ratio.max():.3f} over {int(big.sum())} tensors; "
           f"(cosine, rel L2) per golden gradient: {report}")
-    assert sig < AE256_TAP_BAR
+    assert sig < AE256_TRAIN_BAR
     assert abs(recon_loss.item() - wl[1]) / wl[1] < 2e-3 and abs(perp.item() - wl[2]) / wl[2] < 2e-2
     assert np.all(np.abs(ratio - 1) < AE256_NORM_BAND), (np.array(gkeys)[big][np.abs(ratio - 1) >= AE256_NORM_BAND])
     assert abs(np.median(ratio) - 1) < 0.03
