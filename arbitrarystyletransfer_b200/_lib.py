@@ -20,6 +20,7 @@ F_CANONICAL, F_BIASED, F_BF16 = 0x1, 0x2, 0x4
 EPI_PLAIN, EPI_POOL2, EPI_UP2, EPI_UPFOLD = 0, 1, 2, 4
 HALO_KEEP, HALO_REFLECT, HALO_CLAMP = 0, 1, 2
 CONV_AUTO, CONV_TC, CONV_DIRECT, CONV_TC_TAPBOX = 0, 1, 2, 3
+DT_BF16, DT_F16 = 0, 1     # 16-bit storage formats of the MobileNet-style path: gradients / activations
 
 
 class AstError(RuntimeError):
@@ -80,14 +81,17 @@ PROTOTYPES = {
     "ast_native_to_planar": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_unpack_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp]),
-    "ast_pw_conv": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp, _i, _i, _vp]),
+    "ast_set_act_format": (_i, [_i]),
+    "ast_get_act_format": (_i, []),
+    "ast_pw_conv": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp, _i, _i, _i, _vp]),
     "ast_dw_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_se_fc": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ast_scale_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ast_stem_conv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ast_head_conv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "ast_nhwc_to_nchw": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
-    "ast_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp]),
+    "ast_nhwc_to_nchw": (_i, [_vp, _i, _vp, _i, _i, _i64, _i, _vp]),
+    "ast_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _vp]),
+    "ast_cvt_f16_to_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "ast_bn_stats": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
     "ast_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _vp]),
     "ast_affine_act": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _vp]),

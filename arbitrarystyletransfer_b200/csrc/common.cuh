@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "../../include/ast_b200.h"
 
@@ -195,6 +196,81 @@ struct Vec16<true> {
     reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
   }
 };
+
+// ---- 16-bit storage formats of the MobileNet-style path (K4) -------------------------------------------------
+// Forward activations (and the weights they meet in the tensor cores) are IEEE fp16: an 11-bit significand.  With
+// bf16's 8 bits the ~150 roundings between the image and the deepest encoder tap added up to 5 % (eval) / 7 %
+// (train) relative error and to 25 % error on the stem's gradients -- all of it caused by the FORWARD roundings, none
+// by the gradients' (oracle simulation); fp16 brings that to < 1 % / 7 %.  Gradients stay bf16:
+// they need range, not precision.  Conversions to fp16 saturate (+-65504) instead of overflowing to infinity.
+// tcgen05.mma kind::f16 takes fp16 x fp16 or bf16 x bf16 operands, never a mix (measured: an fp16 x bf16 instruction
+// descriptor is an illegal instruction), so weight-gradient GEMMs convert their activation operand to bf16 first.
+typedef __half act_t;            // the DEFAULT activation type; kernels are templates on AT in {__half, __nv_bfloat16}
+typedef __nv_bfloat16 grad_t;
+int act_format();                // AST_DT_F16 (default) or AST_DT_BF16: misc.cu, set by ast_set_act_format
+// Launch for the process-wide activation format (fp16 by default, bf16 when range matters more than precision:
+// ast_set_act_format): inside the macro `AT` is the activation element type.
+#define AST_ACT_DISPATCH(...)                                                    \
+  do {                                                                           \
+    if (ast::act_format() == AST_DT_F16) { using AT = __half; __VA_ARGS__; }     \
+    else { using AT = __nv_bfloat16; __VA_ARGS__; }                              \
+  } while (0)
+
+
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
+template <typename T>
+struct H16;
+template <>
+struct H16<__nv_bfloat16> : Vec16<true> {
+  __device__ static __forceinline__ float2 un2(uint32_t u) { return make_float2(bf16lo(u), bf16hi(u)); }
+  __device__ static __forceinline__ uint32_t pk2(float lo, float hi) { return pack_bf16(lo, hi); }
+};
+template <>
+struct H16<__half> {
+  static constexpr int V = 8;
+  using elem = __half;
+  __device__ static __forceinline__ float2 un2(uint32_t u) { return unpack_f16(u); }
+  __device__ static __forceinline__ uint32_t pk2(float lo, float hi) { return pack_f16(lo, hi); }
+  __device__ static __forceinline__ void unpack(uint4 u, float (&x)[8]) {
+    const float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&x)[8]) {
+    return make_uint4(pack_f16(x[0], x[1]), pack_f16(x[2], x[3]), pack_f16(x[4], x[5]), pack_f16(x[6], x[7]));
+  }
+  __device__ static __forceinline__ float load1(const void* p, int64_t i) {
+    return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  }
+  __device__ static __forceinline__ void store1(void* p, int64_t i, float v) {
+    reinterpret_cast<uint16_t*>(p)[i] = (uint16_t)(pack_f16(v, 0.f) & 0xffffu);
+  }
+};
+// typed 16-byte loads / stores: the pointer type (act_t / grad_t) selects the conversion
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&x)[8]) {
+  H16<T>::unpack(__ldg(reinterpret_cast<const uint4*>(p)), x);
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&x)[8]) {
+  *reinterpret_cast<uint4*>(p) = H16<T>::pack(x);
+}
+// runtime-selected format (kernels that serve both roles: pointwise GEMM epilogue, layout converters)
+__device__ __forceinline__ float2 un2_dt(uint32_t u, int f16) { return f16 ? unpack_f16(u) : make_float2(bf16lo(u), bf16hi(u)); }
+__device__ __forceinline__ uint32_t pk2_dt(float lo, float hi, int f16) { return f16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+__device__ __forceinline__ void unpack8_dt(uint4 u, float (&x)[8], int f16) {
+  if (f16) H16<__half>::unpack(u, x); else Vec16<true>::unpack(u, x);
+}
+__device__ __forceinline__ uint4 pack8_dt(const float (&x)[8], int f16) {
+  return f16 ? H16<__half>::pack(x) : Vec16<true>::pack(x);
+}
 
 __host__ __device__ __forceinline__ bool aligned16(const void* p) {
   return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;

@@ -17,6 +17,7 @@
 // Geometry is chosen on the host per channel count (pick_geom): hvn = 8-byte channel groups per CTA (a
 // divisor of C/4), workers = 256 / hvn thread groups, tile = TH x TW with TH * TW/8 a multiple of the
 // worker count so that every round of the strip loop is full.
+#include <type_traits>
 #include "common.cuh"
 
 namespace ast {
@@ -37,16 +38,27 @@ __device__ __forceinline__ int reflect_idx(int p, int X) {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 // 4 bf16 -> 2 float2 (channel pairs).  All FMAs are the packed FFMA2: on sm_100 the scalar 3-register FFMA
 // issues at half rate per SM sub-partition, FFMA2 restores the full FP32 rate.
+// T = act_t (fp16 activations) or grad_t (bf16 gradients): common.cuh
+template <typename T>
 __device__ __forceinline__ void unpack2x2(uint2 u, float2 (&x)[2]) {
-  x[0] = make_float2(bf16lo(u.x), bf16hi(u.x));
-  x[1] = make_float2(bf16lo(u.y), bf16hi(u.y));
+  x[0] = H16<T>::un2(u.x);
+  x[1] = H16<T>::un2(u.y);
+}
+template <typename T>
+__device__ __forceinline__ void unpack4(uint2 u, float (&x)[4]) {
+  const float2 a = H16<T>::un2(u.x), b = H16<T>::un2(u.y);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+}
+template <typename T>
+__device__ __forceinline__ uint2 pack4(const float (&o)[4]) {
+  return make_uint2(H16<T>::pk2(o[0], o[1]), H16<T>::pk2(o[2], o[3]));
 }
 __device__ __forceinline__ void ld_w2x2(const float* p, float2 (&w)[2]) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   w[0] = make_float2(a.x, a.y);
   w[1] = make_float2(a.z, a.w);
 }
-__device__ __forceinline__ uint2 ldg_u2(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ uint2 ldg_u2(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 // Row pitch (in 8-byte units) of a staged tile with `cols` pixels of hvn vectors: padded so that
 // pitch == hvn (mod 16).  Consecutive workers take consecutive ROWS of the same 8-pixel column group, so
 // the (worker, vector) pairs of a half warp fall on 16 consecutive 8-byte bank pairs: conflict free for
@@ -72,7 +84,7 @@ __device__ __forceinline__ void stage_tile(uint4* dst, int rows, int cols, int c
   const int dpx = drem / cpp;
   const int dcc = drem - dpx * cpp;
   while (py < rows) {
-    const __nv_bfloat16* sp = src(py, px);
+    const uint16_t* sp = src(py, px);
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
     if (sp) val = __ldg(reinterpret_cast<const uint4*>(sp) + cc);
     dst[py * pitch16 + px * cpp + cc] = val;
@@ -108,7 +120,7 @@ __device__ __forceinline__ void stage_tile_async(uint4* dst, int rows, int cols,
   const int dpx = drem / cpp;
   const int dcc = drem - dpx * cpp;
   while (py < rows) {
-    const __nv_bfloat16* sp = src(py, px);
+    const uint16_t* sp = src(py, px);
     cp_async16(dst + py * pitch16 + px * cpp + cc, sp ? (const void*)(reinterpret_cast<const uint4*>(sp) + cc) : safe,
                sp != nullptr);
     cc += dcc;
@@ -124,25 +136,28 @@ struct Geom {
 };
 
 struct Params {
-  const __nv_bfloat16* in;     // forward: x [N][H][W][C];  dgrad: dy [N][H][W][C]
+  // 16-bit tensors as raw uint16_t: forward (MODE 0) in / out are fp16 activations; data gradient (MODE 1) in / out /
+  // dres are bf16 gradients and a_pre is an fp16 activation
+  const uint16_t* in;          // forward: x [N][H][W][C];  dgrad: dy [N][H][W][C]
   const float* w;              // fp32 [k*k][C]
   const float* bias;           // forward only, nullable
-  __nv_bfloat16* out;          // [N][Hc][Wc][C]   (Hc x Wc = conv grid = 2H x 2W when up2)
+  uint16_t* out;               // [N][Hc][Wc][C]   (Hc x Wc = conv grid = 2H x 2W when up2)
   float* pool;                 // forward only, nullable: [N][C] sums
-  const __nv_bfloat16* a_pre;  // dgrad only, nullable: multiply by Hardswish'(a_pre * sc + sh)
+  const uint16_t* a_pre;       // dgrad only, nullable: multiply by Hardswish'(a_pre * sc + sh)
   const float* stat;           // dgrad only, nullable: [4][C]
-  const __nv_bfloat16* dres;   // dgrad only, nullable: identity-branch gradient added
+  const uint16_t* dres;        // dgrad only, nullable: identity-branch gradient added
   int N, C, H, W, Hc, Wc, up2, act;
   Geom g;
 };
 
 // MODE 0: forward (reflect staging, bias / Hardswish / pool epilogue)
 // MODE 1: data gradient (zero-fill staging, flipped weights, reflection fold at the borders)
-template <int K, int MODE>
+template <typename AT, int K, int MODE>
 __global__ void __launch_bounds__(kThreads, (MODE == 0 ? 2 : 3))
 dw_tiled_kernel(const Params p) {
   extern __shared__ __align__(16) uint2 smem_u2[];
   constexpr int PAD = (K - 1) / 2;
+  using IO = typename std::conditional<MODE == 0, AT, grad_t>::type;   // element type of in / out (AT = activation format)
   const Geom g = p.g;
   const int PH = g.TH + K - 1, PW = g.TW + K - 1;
   const int RP = row_pitch(PW, g.hvn);
@@ -168,9 +183,9 @@ dw_tiled_kernel(const Params p) {
     const int tile = (int)(t - (int64_t)n * tiles_per_img);
     const int th = tile / g.tiles_w, tw = tile - th * g.tiles_w;
     const int oh0 = th * g.TH, ow0 = tw * g.TW;
-    const __nv_bfloat16* src = p.in + (int64_t)n * p.H * p.W * p.C + c0;
+    const uint16_t* src = p.in + (int64_t)n * p.H * p.W * p.C + c0;
     stage_tile_async(reinterpret_cast<uint4*>(smem_u2 + b * patch_elems), PH, PW, g.hvn / 2, RP / 2, p.in,
-                     [&](int py, int px) -> const __nv_bfloat16* {
+                     [&](int py, int px) -> const uint16_t* {
       int y = oh0 - PAD + py, x = ow0 - PAD + px;      // position on the conv grid (may be outside)
       if (MODE == 0) {
         // reflection; positions only needed by masked outputs are clamped into range
@@ -232,7 +247,7 @@ dw_tiled_kernel(const Params p) {
 #pragma unroll
         for (int c = 0; c < R + K - 1; ++c) {
           float2 xv[2];
-          unpack2x2(prow[c * g.hvn], xv);
+          unpack2x2<IO>(prow[c * g.hvn], xv);
 #pragma unroll
           for (int kw = 0; kw < K; ++kw) {
             const int rr = c - kw;
@@ -259,10 +274,11 @@ dw_tiled_kernel(const Params p) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) o[j] = hsw(o[j]);
           }
-          const uint2 ov = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+          const uint2 ov = pack4<AT>(o);
           *reinterpret_cast<uint2*>(p.out + obase + (int64_t)ow * p.C) = ov;
           if (p.pool) {
-            const float rv[CH] = {bf16lo(ov.x), bf16hi(ov.x), bf16lo(ov.y), bf16hi(ov.y)};
+            float rv[CH];
+            unpack4<AT>(ov, rv);
 #pragma unroll
             for (int j = 0; j < CH; ++j) psum[j] += (p.act == 2) ? hsw(rv[j]) : rv[j];
           }
@@ -284,17 +300,17 @@ dw_tiled_kernel(const Params p) {
           if (ow >= p.Wc) continue;
           float o[CH] = {acc2[rr][0].x, acc2[rr][0].y, acc2[rr][1].x, acc2[rr][1].y};
           if (p.dres) {
-            const uint2 rv = ldg_u2(p.dres + obase + (int64_t)ow * p.C);
-            o[0] += bf16lo(rv.x); o[1] += bf16hi(rv.x); o[2] += bf16lo(rv.y); o[3] += bf16hi(rv.y);
+            float r4[CH];
+            unpack4<grad_t>(ldg_u2(p.dres + obase + (int64_t)ow * p.C), r4);
+            o[0] += r4[0]; o[1] += r4[1]; o[2] += r4[2]; o[3] += r4[3];
           }
           if (p.a_pre) {
-            const uint2 av = ldg_u2(p.a_pre + obase + (int64_t)ow * p.C);
-            const float a4[CH] = {bf16lo(av.x), bf16hi(av.x), bf16lo(av.y), bf16hi(av.y)};
+            float a4[CH];
+            unpack4<AT>(ldg_u2(p.a_pre + obase + (int64_t)ow * p.C), a4);
 #pragma unroll
             for (int j = 0; j < CH; ++j) o[j] *= hsw_grad(fmaf(a4[j], sc[j], sh[j]));
           }
-          *reinterpret_cast<uint2*>(p.out + obase + (int64_t)ow * p.C) =
-              make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+          *reinterpret_cast<uint2*>(p.out + obase + (int64_t)ow * p.C) = pack4<grad_t>(o);
         }
       }
     }
@@ -355,7 +371,7 @@ dw_tiled_kernel(const Params p) {
                 const int pc = qw[b] - ow0 + kw;
                 if (pc < 0 || pc >= PW) continue;
                 float2 xv[2], wv[2];
-                unpack2x2(patch[pr * RP + pc * g.hvn + vv], xv);
+                unpack2x2<IO>(patch[pr * RP + pc * g.hvn + vv], xv);
                 ld_w2x2(s_w + (kh * K + kw) * CB + vv * CH, wv);
                 a0 = __ffma2_rn(xv[0], wv[0], a0);
                 a1 = __ffma2_rn(xv[1], wv[1], a1);
@@ -364,8 +380,8 @@ dw_tiled_kernel(const Params p) {
         float o[CH] = {a0.x, a0.y, a1.x, a1.y};
         const int64_t off = (((int64_t)n * p.Hc + oh) * p.Wc + ow) * p.C + c0 + vv * CH;
         if (p.a_pre) {
-          const uint2 av = ldg_u2(p.a_pre + off);
-          const float a4[CH] = {bf16lo(av.x), bf16hi(av.x), bf16lo(av.y), bf16hi(av.y)};
+          float a4[CH];
+          unpack4<AT>(ldg_u2(p.a_pre + off), a4);
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             const float scj = p.stat ? __ldg(p.stat + 2 * p.C + c0 + vv * CH + j) : 1.f;
@@ -374,9 +390,11 @@ dw_tiled_kernel(const Params p) {
           }
         }
         uint2* op = reinterpret_cast<uint2*>(p.out + off);
-        const uint2 prev = *op;
-        *op = make_uint2(pack_bf16(bf16lo(prev.x) + o[0], bf16hi(prev.x) + o[1]),
-                         pack_bf16(bf16lo(prev.y) + o[2], bf16hi(prev.y) + o[3]));
+        float pv[CH];
+        unpack4<grad_t>(*op, pv);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) pv[j] += o[j];
+        *op = pack4<grad_t>(pv);
       }
     }
   }
@@ -398,8 +416,8 @@ dw_tiled_kernel(const Params p) {
 // of 8 outputs re-uses every LDS'ed x value for up to k taps.  One shared-memory reduction over the workers
 // and one atomic per (channel, tap) per CTA at the end.  blockIdx.y = channel block.
 struct WParams {
-  const __nv_bfloat16* dy;   // [N][Hc][Wc][C]
-  const __nv_bfloat16* x;    // [N][H][W][C]
+  const uint16_t* dy;   // [N][Hc][Wc][C]  bf16 gradient
+  const uint16_t* x;    // [N][H][W][C]    fp16 activation
   float* dw;                 // (C,1,K,K) fp32, accumulated
   int N, C, H, W, Hc, Wc, up2;
   Geom g;                    // hvn = channel PAIRS per CTA here
@@ -411,7 +429,7 @@ __host__ __device__ __forceinline__ int row_pitch32(int cols, int pn) {
   return raw + (((pn - raw) % 32) + 32) % 32;
 }
 
-template <int K>
+template <typename AT, int K>
 __global__ void __launch_bounds__(kThreads, 3)
 dw_wgrad_tiled_kernel(const WParams p) {
   extern __shared__ __align__(16) uint32_t smem_u1[];
@@ -443,15 +461,15 @@ dw_wgrad_tiled_kernel(const WParams p) {
     const int oh0 = th * g.TH, ow0 = tw * g.TW;
     uint32_t* bx = smem_u1 + b * buf_words;
     uint32_t* bd = bx + PH * RPX;
-    const __nv_bfloat16* src = p.x + (int64_t)n * p.H * p.W * p.C + c0;
-    stage_tile_async(reinterpret_cast<uint4*>(bx), PH, PW, pn / 4, RPX / 4, p.x, [&](int py, int px) -> const __nv_bfloat16* {
+    const uint16_t* src = p.x + (int64_t)n * p.H * p.W * p.C + c0;
+    stage_tile_async(reinterpret_cast<uint4*>(bx), PH, PW, pn / 4, RPX / 4, p.x, [&](int py, int px) -> const uint16_t* {
       int y = reflect_idx(clampi(oh0 - PAD + py, -PAD, p.Hc - 1 + PAD), p.Hc);
       int x = reflect_idx(clampi(ow0 - PAD + px, -PAD, p.Wc - 1 + PAD), p.Wc);
       if (p.up2) { y >>= 1; x >>= 1; }
       return src + ((int64_t)y * p.W + x) * p.C;
     });
-    const __nv_bfloat16* dsrc = p.dy + (int64_t)n * p.Hc * p.Wc * p.C + c0;
-    stage_tile_async(reinterpret_cast<uint4*>(bd), g.TH, g.TW, pn / 4, RPD / 4, p.x, [&](int py, int px) -> const __nv_bfloat16* {
+    const uint16_t* dsrc = p.dy + (int64_t)n * p.Hc * p.Wc * p.C + c0;
+    stage_tile_async(reinterpret_cast<uint4*>(bd), g.TH, g.TW, pn / 4, RPD / 4, p.x, [&](int py, int px) -> const uint16_t* {
       const int y = oh0 + py, x = ow0 + px;
       if (y >= p.Hc || x >= p.Wc) return nullptr;   // outputs outside the image contribute nothing
       return dsrc + ((int64_t)y * p.Wc + x) * p.C;
@@ -478,7 +496,7 @@ dw_wgrad_tiled_kernel(const WParams p) {
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
           const uint32_t u = s_dy[r * RPD + (cg * R + rr) * pn + v];
-          d[rr] = make_float2(bf16lo(u), bf16hi(u));
+          d[rr] = H16<grad_t>::un2(u);
         }
 #pragma unroll
         for (int kh = 0; kh < K; ++kh) {
@@ -486,7 +504,7 @@ dw_wgrad_tiled_kernel(const WParams p) {
 #pragma unroll
           for (int c = 0; c < R + K - 1; ++c) {
             const uint32_t u = prow[c * pn];
-            const float2 xv = make_float2(bf16lo(u), bf16hi(u));
+            const float2 xv = H16<AT>::un2(u);
 #pragma unroll
             for (int kw = 0; kw < K; ++kw) {
               const int rr = c - kw;
@@ -569,11 +587,11 @@ static bool pick_geom(int C, int Hc, int Wc, int k, size_t smem_limit, bool wgra
 constexpr size_t kSmemLimit = 72 * 1024;      // data / weight gradient: 3 CTAs per SM, two patch buffers each
 constexpr size_t kSmemLimitFwd = 100 * 1024;  // forward (heavier epilogue, 128 registers): 2 CTAs per SM, larger tiles
 
-template <int K, int MODE>
-static int launch_tiled(const Params& p, int N, cudaStream_t s) {
+template <typename AT, int K, int MODE>
+static int launch_tiled_t(const Params& p, int N, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tiled_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(dw_tiled_kernel<AT, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemLimitFwd);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
@@ -585,16 +603,20 @@ static int launch_tiled(const Params& p, int N, cudaStream_t s) {
   if (gx < 1) gx = 1;
   if (gx > total_tiles) gx = total_tiles;
   dim3 grid((unsigned)gx, g.cblocks, 1);
-  dw_tiled_kernel<K, MODE><<<grid, kThreads, smem, s>>>(p);
+  dw_tiled_kernel<AT, K, MODE><<<grid, kThreads, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
+template <int K, int MODE>
+static int launch_tiled(const Params& p, int N, cudaStream_t s) {
+  return act_format() == AST_DT_F16 ? launch_tiled_t<__half, K, MODE>(p, N, s) : launch_tiled_t<__nv_bfloat16, K, MODE>(p, N, s);
+}
 
-template <int K>
-static int launch_wgrad(const WParams& p, cudaStream_t s) {
+template <typename AT, int K>
+static int launch_wgrad_t(const WParams& p, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tiled_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tiled_kernel<AT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemLimit);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
@@ -607,9 +629,13 @@ static int launch_wgrad(const WParams& p, cudaStream_t s) {
   if (gx < 1) gx = 1;
   if (gx > total_tiles) gx = total_tiles;
   dim3 grid((unsigned)gx, g.cblocks, 1);
-  dw_wgrad_tiled_kernel<K><<<grid, kThreads, smem, s>>>(p);
+  dw_wgrad_tiled_kernel<AT, K><<<grid, kThreads, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
+}
+template <int K>
+static int launch_wgrad(const WParams& p, cudaStream_t s) {
+  return act_format() == AST_DT_F16 ? launch_wgrad_t<__half, K>(p, s) : launch_wgrad_t<__nv_bfloat16, K>(p, s);
 }
 
 }  // namespace dwt
@@ -622,8 +648,8 @@ using namespace ast;
 int dw_tiled_forward(const void* x, const float* w, const float* bias, void* out, float* pool, int N, int C, int H,
                      int W, int k, int up2, int act, cudaStream_t s) {
   dwt::Params p = {};
-  p.in = reinterpret_cast<const __nv_bfloat16*>(x);
-  p.w = w; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.pool = pool;
+  p.in = reinterpret_cast<const uint16_t*>(x);
+  p.w = w; p.bias = bias; p.out = reinterpret_cast<uint16_t*>(out); p.pool = pool;
   p.N = N; p.C = C; p.H = H; p.W = W; p.Hc = up2 ? 2 * H : H; p.Wc = up2 ? 2 * W : W; p.up2 = up2; p.act = act;
   if (N > 65535 || !dwt::pick_geom(C, p.Hc, p.Wc, k, dwt::kSmemLimitFwd, false, &p.g)) return AST_E_SHAPE;
   return k == 3 ? dwt::launch_tiled<3, 0>(p, N, s) : dwt::launch_tiled<5, 0>(p, N, s);
@@ -632,10 +658,10 @@ int dw_tiled_forward(const void* x, const float* w, const float* bias, void* out
 int dw_tiled_dgrad(const void* dy, const float* w, const void* a_pre, const float* stat, const void* dres, void* dx,
                    int N, int C, int H, int W, int k, cudaStream_t s) {
   dwt::Params p = {};
-  p.in = reinterpret_cast<const __nv_bfloat16*>(dy);
-  p.w = w; p.out = reinterpret_cast<__nv_bfloat16*>(dx);
-  p.a_pre = reinterpret_cast<const __nv_bfloat16*>(a_pre); p.stat = stat;
-  p.dres = reinterpret_cast<const __nv_bfloat16*>(dres);
+  p.in = reinterpret_cast<const uint16_t*>(dy);
+  p.w = w; p.out = reinterpret_cast<uint16_t*>(dx);
+  p.a_pre = reinterpret_cast<const uint16_t*>(a_pre); p.stat = stat;
+  p.dres = reinterpret_cast<const uint16_t*>(dres);
   p.N = N; p.C = C; p.H = H; p.W = W; p.Hc = H; p.Wc = W;
   if (N > 65535 || H < 2 * k || W < 2 * k) return AST_E_SHAPE;   // tiny maps: the direct kernel handles them
   if (!dwt::pick_geom(C, H, W, k, dwt::kSmemLimit, false, &p.g)) return AST_E_SHAPE;
@@ -645,8 +671,8 @@ int dw_tiled_dgrad(const void* dy, const float* w, const void* a_pre, const floa
 int dw_tiled_wgrad(const void* dy, const void* x, float* dw, int N, int C, int H, int W, int k, int up2,
                    cudaStream_t s) {
   dwt::WParams p = {};
-  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
-  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.dy = reinterpret_cast<const uint16_t*>(dy);
+  p.x = reinterpret_cast<const uint16_t*>(x);
   p.dw = dw; p.N = N; p.C = C; p.H = H; p.W = W; p.Hc = up2 ? 2 * H : H; p.Wc = up2 ? 2 * W : W; p.up2 = up2;
   if (!dwt::pick_geom(C, p.Hc, p.Wc, k, dwt::kSmemLimit, true, &p.g)) return AST_E_SHAPE;
   return k == 3 ? dwt::launch_wgrad<3>(p, s) : dwt::launch_wgrad<5>(p, s);

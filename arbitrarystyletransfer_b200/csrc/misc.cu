@@ -3,6 +3,18 @@
 
 extern "C" int ast_abi_version(void) { return AST_ABI_VERSION; }
 
+// Process-wide storage format of the K4 forward activations (include/ast_b200.h): fp16 unless changed.
+namespace ast {
+static int g_act_format = AST_DT_F16;
+int act_format() { return g_act_format; }
+}  // namespace ast
+extern "C" int ast_set_act_format(int dtype) {
+  if (dtype != AST_DT_F16 && dtype != AST_DT_BF16) return AST_E_BADARG;
+  ast::g_act_format = dtype;
+  return 0;
+}
+extern "C" int ast_get_act_format(void) { return ast::g_act_format; }
+
 extern "C" const char* ast_error_string(int code) {
   if (code == 0) return "success";
   if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -1,7 +1,7 @@
 // K4: the non-GEMM pieces of the MobileNet-style Encoder / Decoder / AutoEncoder blocks
 // (reference: mobilenetv2.py:38-43 conv_3x3_bn, :63-81 SELayer, :95-165 DepthWiseConv;
 // models.py:140-184 Encoder, :242-320 DecoderBlock / Decoder, :322-338 AutoEncoder), eval mode.
-// Layout: plain NHWC bf16 [N][H][W][C] (no halo: these blocks use reflect padding of 1 or 2 and
+// Layout: plain NHWC fp16 [N][H][W][C] (act_t, common.cuh) (no halo: these blocks use reflect padding of 1 or 2 and
 // stride 1 or 2, resolved by index arithmetic in the stencil).  All HBM-bound.
 #include "common.cuh"
 #include <stdlib.h>
@@ -23,9 +23,10 @@ __device__ __forceinline__ int reflect(int p, int X) {  // padding_mode="reflect
 // up2 != 0: the input is read through a virtual nearest x2 upsample (DecoderBlock._upsample_3,
 // models.py:254, 265-267), reflect padding applied on the upsampled grid.
 // grid = (pixel chunks, N); thread -> 8 channels of one pixel group (as native_stats_kernel).
+template <typename AT>
 __global__ void __launch_bounds__(kM)
-dw_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[k*k][C]*/,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, float* __restrict__ pool,
+dw_conv_kernel(const AT* __restrict__ x, const float* __restrict__ w /*[k*k][C]*/,
+               const float* __restrict__ bias, AT* __restrict__ out, float* __restrict__ pool,
                int C, int H, int W, int Ho, int Wo, int k, int stride, int up2, int act, int chunks) {
   extern __shared__ float s_pool[];  // [groups][C]
   const int cv = C / 8;
@@ -44,7 +45,7 @@ dw_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w 
     float b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) b[j] = bias ? __ldg(bias + v * 8 + j) : 0.f;
-    const __nv_bfloat16* xin = x + (int64_t)n * H * W * C + v * 8;
+    const AT* xin = x + (int64_t)n * H * W * C + v * 8;
     for (int64_t p = p0 + g; p < p1; p += groups) {
       const int ho = (int)(p / Wo), wo = (int)(p % Wo);
       float acc[8];
@@ -57,7 +58,7 @@ dw_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w 
           int iw = reflect(wo * stride + kw - pad, Win);
           if (up2) iw >>= 1;
           float xv[8];
-          Vec16<true>::unpack(__ldg(reinterpret_cast<const uint4*>(xin + ((int64_t)ih * W + iw) * C)), xv);
+          ld8(xin + ((int64_t)ih * W + iw) * C, xv);
           const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(kh * k + kw) * C + v * 8));
           const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(kh * k + kw) * C + v * 8 + 4));
           acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
@@ -70,12 +71,12 @@ dw_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w 
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = hswish(acc[j]);
       }
-      const uint4 o = Vec16<true>::pack(acc);
+      const uint4 o = H16<AT>::pack(acc);
       *reinterpret_cast<uint4*>(out + (((int64_t)n * Ho + ho) * Wo + wo) * C + v * 8) = o;
-      // pool what the next layer will actually read (the bf16-rounded value); act == 2 (training):
+      // pool what the next layer will actually read (the rounded value); act == 2 (training):
       // the RAW value is stored for the backward pass and the pool sees Hardswish of it
       float r[8];
-      Vec16<true>::unpack(o, r);
+      H16<AT>::unpack(o, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) psum[j] += (act == 2) ? hswish(r[j]) : r[j];
     }
@@ -141,8 +142,9 @@ se_fc_kernel(const float* __restrict__ pool, float inv_hw, const float* __restri
 // ---- per-sample weights of the pw-linear conv: W'[n][co][ci] = W[co][ci] * se[n][ci] (bf16) --------
 // (x * y in SELayer.forward, mobilenetv2.py:81, moved from the activation into the weights: exact in
 // real arithmetic, and it saves one full pass over the widest tensor of the block.)
+template <typename AT>
 __global__ void scale_weights_kernel(const float* __restrict__ w, const float* __restrict__ se,
-                                     __nv_bfloat16* __restrict__ out, int N, int Cout, int Cin) {
+                                     AT* __restrict__ out, int N, int Cout, int Cin) {
   const int64_t total = (int64_t)N * Cout * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -151,16 +153,17 @@ __global__ void scale_weights_kernel(const float* __restrict__ w, const float* _
     const int co = (int)(r % Cout);
     const int n = (int)(r / Cout);
     const float s = se ? se[(int64_t)n * Cin + ci] : 1.f;
-    out[i] = __float2bfloat16_rn(w[(int64_t)co * Cin + ci] * s);
+    H16<AT>::store1(out, i, w[(int64_t)co * Cin + ci] * s);
   }
 }
 
 // ---- stem: NCHW fp32 image -> conv 3x3 (reflect pad 1, stride 1, no bias) -> Hardswish -> NHWC bf16
 // (conv_3x3_bn, mobilenetv2.py:38-43; Cout <= 32).  One thread per pixel.
 constexpr int kStemMaxCout = 32;
+template <typename AT>
 __global__ void __launch_bounds__(128)
 stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*OIHW [Cout][3][3][3]*/,
-                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_raw, int N, int H, int W,
+                 AT* __restrict__ out, AT* __restrict__ out_raw, int N, int H, int W,
                  int Cout) {
   __shared__ float s_w[27][kStemMaxCout];
   for (int i = threadIdx.x; i < 27 * kStemMaxCout; i += 128) {
@@ -184,7 +187,7 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*OI
 #pragma unroll
         for (int c = 0; c < kStemMaxCout; ++c) acc[c] = fmaf(v, s_w[ci * 9 + kh * 3 + kw][c], acc[c]);
       }
-  __nv_bfloat16* o = out + pix * Cout;
+  AT* o = out + pix * Cout;
 #pragma unroll
   for (int c = 0; c < kStemMaxCout; c += 8) {
     if (c >= Cout) break;
@@ -192,20 +195,21 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*OI
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = acc[c + j];
     if (out_raw) {   // training: keep the rounded pre-activation, activate the rounded value
-      const uint4 rv = Vec16<true>::pack(t);
+      const uint4 rv = H16<AT>::pack(t);
       *reinterpret_cast<uint4*>(out_raw + pix * Cout + c) = rv;
-      Vec16<true>::unpack(rv, t);
+      H16<AT>::unpack(rv, t);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = hswish(t[j]);
-    *reinterpret_cast<uint4*>(o + c) = Vec16<true>::pack(t);
+    st8(o + c, t);
   }
 }
 
 // ---- image head: NHWC bf16 -> ReflectionPad2d(1) -> conv 3x3 (bias) -> NCHW fp32 (+ Hardtanh(0,1))
 // (Decoder._ref_out + _img_out + last_act, models.py:300-316; Cin <= 32, Cout <= 4)
+template <typename AT>
 __global__ void __launch_bounds__(128)
-head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*OIHW*/,
+head_conv_kernel(const AT* __restrict__ x, const float* __restrict__ w /*OIHW*/,
                  const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W, int Cin,
                  int Cout, int clamp01) {
   __shared__ float s_w[9][32][4];
@@ -222,10 +226,10 @@ head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
   for (int c = 0; c < 4; ++c) acc[c] = (bias && c < Cout) ? bias[c] : 0.f;
   for (int t = 0; t < 9; ++t) {
     const int ih = reflect(h + t / 3 - 1, H), iw = reflect(xw + t % 3 - 1, W);
-    const __nv_bfloat16* ip = x + (((int64_t)n * H + ih) * W + iw) * Cin;
+    const AT* ip = x + (((int64_t)n * H + ih) * W + iw) * Cin;
     for (int v = 0; v < Cin / 8; ++v) {
       float f[8];
-      Vec16<true>::unpack(__ldg(reinterpret_cast<const uint4*>(ip + v * 8)), f);
+      ld8(ip + v * 8, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 ww = *reinterpret_cast<const float4*>(&s_w[t][v * 8 + j][0]);
@@ -242,8 +246,8 @@ head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 }
 
 // ---- NHWC bf16 (row stride ld) -> NCHW fp32 (feature taps at the reference boundary) ---------------
-__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld,
-                                                           float* __restrict__ dst, int C, int64_t HW) {
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const uint16_t* __restrict__ src, int ld,
+                                                           float* __restrict__ dst, int C, int64_t HW, int f16) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -251,7 +255,8 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* 
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int pl = ty; pl < 32; pl += 8) {
     const int64_t p = p0 + pl;
-    tile[pl][tx] = (p < HW && c0 + tx < C) ? __bfloat162float(src[((int64_t)n * HW + p) * ld + c0 + tx]) : 0.f;
+    const uint32_t raw = (p < HW && c0 + tx < C) ? src[((int64_t)n * HW + p) * ld + c0 + tx] : 0u;
+    tile[pl][tx] = un2_dt(raw, f16).x;
   }
   __syncthreads();
   for (int cl = ty; cl < 32; cl += 8) {
@@ -297,9 +302,9 @@ extern "C" int ast_dw_conv(const void* x, const float* w, const float* bias, voi
   const int groups = kM / (C / 8);
   const size_t smem = pool ? (size_t)groups * C * sizeof(float) : 0;
   if (smem > 48 * 1024) return AST_E_SHAPE;
-  dw_conv_kernel<<<dim3((unsigned)chunks, N), kM, smem, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), w, bias, reinterpret_cast<__nv_bfloat16*>(out), pool, C, H, W,
-      Ho, Wo, k, stride, up2, act, (int)chunks);
+  AST_ACT_DISPATCH(dw_conv_kernel<AT><<<dim3((unsigned)chunks, N), kM, smem, s>>>(
+      reinterpret_cast<const AT*>(x), w, bias, reinterpret_cast<AT*>(out), pool, C, H, W,
+      Ho, Wo, k, stride, up2, act, (int)chunks));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -322,8 +327,8 @@ extern "C" int ast_scale_weights(const float* w, const float* se, void* out, int
   const int64_t total = (int64_t)N * Cout * Cin;
   int64_t nb = (total + 255) / 256;
   if (nb > 148 * 8) nb = 148 * 8;
-  scale_weights_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
-      w, se, reinterpret_cast<__nv_bfloat16*>(out), N, Cout, Cin);
+  AST_ACT_DISPATCH(scale_weights_kernel<AT><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
+      w, se, reinterpret_cast<AT*>(out), N, Cout, Cin));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -334,8 +339,8 @@ extern "C" int ast_stem_conv(const float* img, const float* w, void* out, void* 
   if (Cout % 8 != 0 || Cout > kStemMaxCout) return AST_E_SHAPE;
   const int64_t nb = ((int64_t)N * H * W + 127) / 128;
   if (nb >= 0x7fffffffLL) return AST_E_SHAPE;
-  stem_conv_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(
-      img, w, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(out_raw), N, H, W, Cout);
+  AST_ACT_DISPATCH(stem_conv_kernel<AT><<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(
+      img, w, reinterpret_cast<AT*>(out), reinterpret_cast<AT*>(out_raw), N, H, W, Cout));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -346,18 +351,18 @@ extern "C" int ast_head_conv(const void* x, const float* w, const float* bias, f
   if (Cin % 8 != 0 || Cin > 32 || Cout < 1 || Cout > 4) return AST_E_SHAPE;
   const int64_t nb = ((int64_t)N * H * W + 127) / 128;
   if (nb >= 0x7fffffffLL) return AST_E_SHAPE;
-  head_conv_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), w,
-                                                                   bias, out, N, H, W, Cin, Cout, clamp01);
+  AST_ACT_DISPATCH(head_conv_kernel<AT><<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const AT*>(x), w, bias, out, N, H, W, Cin, Cout, clamp01));
   AST_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int ast_nhwc_to_nchw(const void* x, int ld, float* out, int N, int C, int64_t HW, void* stream) {
-  if (!x || !out || N <= 0 || C <= 0 || HW <= 0 || ld < C) return AST_E_BADARG;
+extern "C" int ast_nhwc_to_nchw(const void* x, int ld, float* out, int N, int C, int64_t HW, int dtype, void* stream) {
+  if (!x || !out || N <= 0 || C <= 0 || HW <= 0 || ld < C || (dtype != AST_DT_BF16 && dtype != AST_DT_F16)) return AST_E_BADARG;
   if (N > 65535 || (C + 31) / 32 > 65535 || (HW + 31) / 32 >= 0x7fffffffLL) return AST_E_SHAPE;
   dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
-  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out,
-                                                              C, HW);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(x), ld, out,
+                                                              C, HW, dtype == AST_DT_F16);
   AST_CHECK_LAUNCH();
   return 0;
 }

@@ -1,8 +1,9 @@
 // K4t: training-mode pieces of the MobileNet-style blocks (train_autoencoder.py:111-148 over
 // models.py:140-338 / mobilenetv2.py:63-181): BatchNorm with batch statistics (forward + backward),
 // Hardswish / SE / residual element-wise passes, depthwise data and weight gradients, SE backward,
-// stem / head gradients.  Everything is HBM-bound streaming over plain NHWC bf16 [pixel][channel]
-// matrices (row stride `ld`), fp32 arithmetic, fp64 for the cross-CTA BatchNorm accumulators.
+// stem / head gradients.  Everything is HBM-bound streaming over plain NHWC 16-bit [pixel][channel]
+// matrices (row stride `ld`): ACTIVATIONS are fp16 (act_t), GRADIENTS bf16 (grad_t) -- the pointer type picks the
+// conversion (common.cuh) --, fp32 arithmetic, fp64 for the cross-CTA BatchNorm accumulators.
 //
 // Thread mapping shared by the streaming kernels: a CTA of 256 threads covers `groups` pixels at a time,
 // thread -> (pixel group g, 8-channel vector v); one 16-byte load per tensor per pixel, consecutive
@@ -44,9 +45,6 @@ __device__ __forceinline__ void chunk_range(int64_t HW, int64_t& p0, int64_t& p1
   p0 = (int64_t)blockIdx.x * per;
   p1 = p0 + per < HW ? p0 + per : HW;
 }
-__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&x)[8]) {
-  Vec16<true>::unpack(__ldg(reinterpret_cast<const uint4*>(p)), x);
-}
 __device__ __forceinline__ void ldf8(const float* p, float (&x)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
@@ -77,8 +75,9 @@ __device__ __forceinline__ void block_channel_reduce(const RowMap& m, int C, flo
 }
 
 // ---- BatchNorm2d batch statistics: sums[0][c] = sum x, sums[1][c] = sum x^2 (fp64 accumulators) ----
+template <typename AT>
 __global__ void __launch_bounds__(kT)
-bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ld, double* __restrict__ sums, int C, int64_t HW) {
+bn_stats_kernel(const AT* __restrict__ x, int ld, double* __restrict__ sums, int C, int64_t HW) {
   extern __shared__ float s_red[];
   const RowMap m = row_map(C);
   int64_t p0, p1;
@@ -86,7 +85,7 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ld, double* __restrict_
   float q[2][8];
   fill8(q[0], 0.f); fill8(q[1], 0.f);
   if (m.on) {
-    const __nv_bfloat16* xp = x + (int64_t)blockIdx.y * HW * ld + m.v * 8;
+    const AT* xp = x + (int64_t)blockIdx.y * HW * ld + m.v * 8;
     for (int64_t p = p0 + m.g; p < p1; p += m.groups) {
       float a[8];
       ld8(xp + p * ld, a);
@@ -122,10 +121,11 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 }
 
 // ---- y = act(x * sc[c] + sh[c]) [* se[n][c]] [+ res]; optional per-(n,c) pool of act(..) ------------
+template <typename AT>
 __global__ void __launch_bounds__(kT)
-affine_act_kernel(const __nv_bfloat16* __restrict__ x, int ld_x, const float* __restrict__ sc,
+affine_act_kernel(const AT* __restrict__ x, int ld_x, const float* __restrict__ sc,
                   const float* __restrict__ sh, int act, const float* __restrict__ se,
-                  const __nv_bfloat16* __restrict__ res, int ld_res, __nv_bfloat16* __restrict__ out, int ld_out,
+                  const AT* __restrict__ res, int ld_res, AT* __restrict__ out, int ld_out,
                   float* __restrict__ pool, int C, int64_t HW) {
   extern __shared__ float s_red[];
   const RowMap m = row_map(C);
@@ -156,7 +156,7 @@ affine_act_kernel(const __nv_bfloat16* __restrict__ x, int ld_x, const float* __
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += r[j];
       }
-      if (out) *reinterpret_cast<uint4*>(out + (row0 + p) * ld_out + m.v * 8) = Vec16<true>::pack(v);
+      if (out) st8(out + (row0 + p) * ld_out + m.v * 8, v);
     }
   }
   if (pool) block_channel_reduce<1, float>(m, C, q, s_red, pool + (int64_t)n * C);
@@ -166,9 +166,9 @@ affine_act_kernel(const __nv_bfloat16* __restrict__ x, int ld_x, const float* __
 //   T0 = sum du * h          (-> gradient of the SE scale)            h = Hardswish(z)
 //   T1 = sum du * h'(z)      T2 = sum h'(z)      T3 = sum du * h'(z) * ahat      T4 = sum h'(z) * ahat
 // T1..T4 feed the BatchNorm backward (only when mean != null); out = [N][5][C].
-template <bool NORM>
+template <typename AT, bool NORM>
 __global__ void __launch_bounds__(kT)
-dw_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ a,
+dw_bwd_reduce_kernel(const grad_t* __restrict__ du, const AT* __restrict__ a,
                      const float* __restrict__ stat /*[4][C] (NORM only)*/, float* __restrict__ out, int C,
                      int64_t HW) {
   extern __shared__ float s_red[];
@@ -243,11 +243,11 @@ __global__ void se_bn_combine_kernel(const float* __restrict__ T, const float* _
 }
 
 // da = ((du * s[n][c] + g[n][c]) * h'(z) - coef0 - ahat * coef1) * sc      (stat == null: da = (..) * h'(a))
-template <bool NORM>
+template <typename AT, bool NORM>
 __global__ void __launch_bounds__(kT)
-dw_bwd_apply_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ a,
+dw_bwd_apply_kernel(const grad_t* __restrict__ du, const AT* __restrict__ a,
                     const float* __restrict__ s, const float* __restrict__ g, const float* __restrict__ stat,
-                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ da, int C, int64_t HW) {
+                    const float* __restrict__ coef, grad_t* __restrict__ da, int C, int64_t HW) {
   const RowMap m = row_map(C);
   if (!m.on) return;
   const int n = blockIdx.y;
@@ -280,14 +280,15 @@ dw_bwd_apply_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* _
         const float dz = fmaf(d[u][j], sv[j], gv[j]) * hsw_grad(z);
         d[u][j] = NORM ? (dz - c0[j] - (av[u][j] - mu[j]) * is[j] * c1[j]) * sc[j] : dz;
       }
-      *reinterpret_cast<uint4*>(da + (row0 + p + u * m.groups) * C + m.v * 8) = Vec16<true>::pack(d[u]);
+      st8(da + (row0 + p + u * m.groups) * C + m.v * 8, d[u]);
     }
   }
 }
 
 // ---- generic BatchNorm backward: sums[0][c] = sum dy, sums[1][c] = sum dy * ahat (fp64) -------------
+template <typename AT>
 __global__ void __launch_bounds__(kT)
-bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int ld_dy, const __nv_bfloat16* __restrict__ a,
+bn_bwd_reduce_kernel(const grad_t* __restrict__ dy, int ld_dy, const AT* __restrict__ a,
                      int ld_a, const float* __restrict__ stat, double* __restrict__ sums, int C, int64_t HW) {
   extern __shared__ float s_red[];
   const RowMap m = row_map(C);
@@ -324,9 +325,10 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double i
 }
 
 // da = (dy - coef0 - ahat * coef1) * sc
+template <typename AT>
 __global__ void __launch_bounds__(kT)
-bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int ld_dy, const __nv_bfloat16* __restrict__ a, int ld_a,
-                    const float* __restrict__ stat, const float* __restrict__ coef, __nv_bfloat16* __restrict__ da,
+bn_bwd_apply_kernel(const grad_t* __restrict__ dy, int ld_dy, const AT* __restrict__ a, int ld_a,
+                    const float* __restrict__ stat, const float* __restrict__ coef, grad_t* __restrict__ da,
                     int C, int64_t HW) {
   const RowMap m = row_map(C);
   if (!m.on) return;
@@ -342,7 +344,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int ld_dy, const __nv_
     ld8(a + (row0 + p) * ld_a + m.v * 8, av);
 #pragma unroll
     for (int j = 0; j < 8; ++j) d[j] = (d[j] - c0[j] - (av[j] - mu[j]) * is[j] * c1[j]) * sc[j];
-    *reinterpret_cast<uint4*>(da + (row0 + p) * C + m.v * 8) = Vec16<true>::pack(d);
+    st8(da + (row0 + p) * C + m.v * 8, d);
   }
 }
 
@@ -361,10 +363,11 @@ __device__ __forceinline__ int reflect_cands(int i, int X, int pad, int (&q)[3])
   return n;
 }
 
+template <typename AT>
 __global__ void __launch_bounds__(kT)
-dw_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w /*[k*k][C]*/,
-                const __nv_bfloat16* __restrict__ a_pre, const float* __restrict__ stat,
-                const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, int C, int H, int W, int Ho, int Wo, int k, int stride, int up2) {
+dw_dgrad_kernel(const grad_t* __restrict__ dy, const float* __restrict__ w /*[k*k][C]*/,
+                const AT* __restrict__ a_pre, const float* __restrict__ stat,
+                const grad_t* __restrict__ dres, grad_t* __restrict__ dx, int C, int H, int W, int Ho, int Wo, int k, int stride, int up2) {
   const RowMap m = row_map(C);
   if (!m.on) return;
   const int n = blockIdx.y;
@@ -375,7 +378,7 @@ dw_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ 
   float sc[8], sh[8];
   fill8(sc, 1.f); fill8(sh, 0.f);
   if (stat) { ldf8(stat + 2 * C + m.v * 8, sc); ldf8(stat + 3 * C + m.v * 8, sh); }
-  const __nv_bfloat16* dyn = dy + (int64_t)n * Ho * Wo * C + m.v * 8;
+  const grad_t* dyn = dy + (int64_t)n * Ho * Wo * C + m.v * 8;
   const float* wv = w + m.v * 8;
   const int reps = up2 ? 2 : 1;
   for (int64_t p = p0 + m.g; p < p1; p += m.groups) {
@@ -422,16 +425,16 @@ dw_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] *= hsw_grad(fmaf(av[j], sc[j], sh[j]));
     }
-    *reinterpret_cast<uint4*>(dx + row * C + m.v * 8) = Vec16<true>::pack(acc);
+    st8(dx + row * C + m.v * 8, acc);
   }
 }
 
 // ---- depthwise conv: weight gradient  dW[c][kh][kw] += sum_{n,o} dy[n,o,c] * xin[n, R(o*s+k-pad), c] ----
 // blockIdx.z = kh; a thread keeps K accumulators x 8 channels.  Output in the parameter's own layout
 // (C,1,K,K) fp32, accumulated with atomics (caller zero-fills).
-template <int K>
+template <typename AT, int K>
 __global__ void __launch_bounds__(kT)
-dw_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, float* __restrict__ dw,
+dw_wgrad_kernel(const grad_t* __restrict__ dy, const AT* __restrict__ x, float* __restrict__ dw,
                 int C, int H, int W, int Ho, int Wo, int stride, int up2) {
   extern __shared__ float s_red[];
   const RowMap m = row_map(C);
@@ -444,8 +447,8 @@ dw_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
 #pragma unroll
   for (int t = 0; t < K; ++t) fill8(q[t], 0.f);
   if (m.on) {
-    const __nv_bfloat16* xn = x + (int64_t)n * H * W * C + m.v * 8;
-    const __nv_bfloat16* dyn = dy + (int64_t)n * Ho * Wo * C + m.v * 8;
+    const AT* xn = x + (int64_t)n * H * W * C + m.v * 8;
+    const grad_t* dyn = dy + (int64_t)n * Ho * Wo * C + m.v * 8;
     for (int64_t p = p0 + m.g; p < p1; p += m.groups) {
       const int oh = (int)(p / Wo), ow = (int)(p % Wo);
       float g[8];
@@ -588,8 +591,9 @@ __device__ __forceinline__ void reduce48_and_add(float (&acc)[48], float* s_part
 }
 
 // stem: dW[co][ci][tap] = sum_p (dy[p][co] * Hardswish'(z[p][co])) * img[ci][R(p + tap)]   (Cout == 16)
+template <typename AT>
 __global__ void __launch_bounds__(kT)
-stem_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+stem_wgrad_kernel(const grad_t* __restrict__ dy, const AT* __restrict__ z,
                   const float* __restrict__ img, float* __restrict__ dw, int N, int H, int W) {
   __shared__ float s_part[(kT / 32) * 48];
   const int tap = blockIdx.y, kh = tap / 3, kw = tap % 3;
@@ -619,8 +623,9 @@ stem_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 }
 
 // head: dW[co][ci][tap] = sum_p dY[co][p] * x[R(p + tap)][ci];  db[co] = sum_p dY[co][p]   (Cin == 16, Cout == 3)
+template <typename AT>
 __global__ void __launch_bounds__(kT)
-head_wgrad_kernel(const float* __restrict__ dY, const __nv_bfloat16* __restrict__ x, float* __restrict__ dw,
+head_wgrad_kernel(const float* __restrict__ dY, const AT* __restrict__ x, float* __restrict__ dw,
                   float* __restrict__ db, int N, int H, int W) {
   __shared__ float s_part[(kT / 32) * 48];
   const int tap = blockIdx.y, kh = tap / 3, kw = tap % 3;
@@ -635,7 +640,7 @@ head_wgrad_kernel(const float* __restrict__ dY, const __nv_bfloat16* __restrict_
 #pragma unroll
     for (int co = 0; co < 3; ++co) g[co] = __ldg(dY + (((int64_t)n * 3 + co) * H + h) * W + xw);
     const int ih = reflect_idx(h + kh - 1, H), iw = reflect_idx(xw + kw - 1, W);
-    const __nv_bfloat16* xp = x + (((int64_t)n * H + ih) * W + iw) * 16;
+    const AT* xp = x + (((int64_t)n * H + ih) * W + iw) * 16;
     float xv[16];
     ld8(xp, *reinterpret_cast<float(*)[8]>(xv));
     ld8(xp + 8, *reinterpret_cast<float(*)[8]>(xv + 8));
@@ -661,7 +666,7 @@ head_wgrad_kernel(const float* __restrict__ dY, const __nv_bfloat16* __restrict_
 // (q runs over the padded-grid positions that reflect onto p).  NCHW fp32 in, NHWC bf16 out, Cin = 16.
 __global__ void __launch_bounds__(128)
 head_dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ w /*OIHW [3][16][3][3]*/,
-                  __nv_bfloat16* __restrict__ dx, int N, int H, int W) {
+                  grad_t* __restrict__ dx, int N, int H, int W) {
   __shared__ float s_w[9][3][16];
   for (int i = threadIdx.x; i < 9 * 3 * 16; i += 128) {
     const int ci = i % 16, co = (i / 16) % 3, t = i / 48;
@@ -695,11 +700,12 @@ head_dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ w /*OI
   float lo[8], hi[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { lo[i] = acc[i]; hi[i] = acc[8 + i]; }
-  *reinterpret_cast<uint4*>(dx + pix * 16) = Vec16<true>::pack(lo);
-  *reinterpret_cast<uint4*>(dx + pix * 16 + 8) = Vec16<true>::pack(hi);
+  st8(dx + pix * 16, lo);
+  st8(dx + pix * 16 + 8, hi);
 }
 
-// ---- weight preparation: fp32 [R][Cc] -> bf16 (optionally transposed) or fp32 transposed ----------------
+// ---- weight preparation: fp32 [R][Cc] -> 0: bf16, 1: bf16 transposed, 2: fp32 transposed, 3: fp16 (forward GEMMs) ----
+template <typename AT>
 __global__ void prep_weight_kernel(const float* __restrict__ w, void* __restrict__ out, int R, int Cc, int mode) {
   const int64_t total = (int64_t)R * Cc;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -708,14 +714,15 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, void* __restrict
     const float v = w[i];
     if (mode == 0) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
     else if (mode == 1) reinterpret_cast<__nv_bfloat16*>(out)[(int64_t)c * R + r] = __float2bfloat16_rn(v);
-    else reinterpret_cast<float*>(out)[(int64_t)c * R + r] = v;
+    else if (mode == 2) reinterpret_cast<float*>(out)[(int64_t)c * R + r] = v;
+    else H16<AT>::store1(out, i, v);
   }
 }
 
 // ---- NCHW fp32 -> NHWC bf16 (row stride ld) --------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src,
-                                                           __nv_bfloat16* __restrict__ dst, int ld, int C,
-                                                           int64_t HW) {
+                                                           uint16_t* __restrict__ dst, int ld, int C,
+                                                           int64_t HW, int f16) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -728,7 +735,23 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   __syncthreads();
   for (int pl = ty; pl < 32; pl += 8) {
     const int64_t p = p0 + pl;
-    if (p < HW && c0 + tx < C) dst[((int64_t)n * HW + p) * ld + c0 + tx] = __float2bfloat16_rn(tile[tx][pl]);
+    if (p < HW && c0 + tx < C) dst[((int64_t)n * HW + p) * ld + c0 + tx] = (uint16_t)(pk2_dt(tile[tx][pl], 0.f, f16) & 0xffffu);
+  }
+}
+
+// ---- fp16 activation -> bf16 copy: the operand of a weight-gradient GEMM (its other operand is a bf16 gradient and
+// the tensor cores take one format per instruction).  rows x C elements, row strides ld_x / ld_out.
+template <typename AT>
+__global__ void __launch_bounds__(256) cvt_act_to_grad_kernel(const AT* __restrict__ x, int64_t ld_x,
+                                                              grad_t* __restrict__ out, int64_t ld_out, int64_t rows,
+                                                              int cv) {
+  const int64_t total = rows * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int v = (int)(i - r * cv);
+    float f[8];
+    H16<AT>::unpack(ld_stream_u4(x + r * ld_x + v * 8), f);
+    st8(out + r * ld_out + v * 8, f);
   }
 }
 
@@ -752,8 +775,10 @@ int dw_tiled_dgrad(const void* dy, const float* w, const void* a_pre, const floa
 int dw_tiled_wgrad(const void* dy, const void* x, float* dw, int N, int C, int H, int W, int k, int up2,
                    cudaStream_t s);
 bool dw_force_direct();
-#define BF(p) reinterpret_cast<bf16*>(p)
-#define CBF(p) reinterpret_cast<const bf16*>(p)
+#define GR(p) reinterpret_cast<grad_t*>(p)
+#define CGR(p) reinterpret_cast<const grad_t*>(p)
+#define AC(p) reinterpret_cast<AT*>(p)          /* inside AST_ACT_DISPATCH */
+#define CAC(p) reinterpret_cast<const AT*>(p)
 
 extern "C" int ast_bn_stats(const void* x, int ld, double* sums, int N, int C, int64_t HW, void* stream) {
   if (!x || !sums || N <= 0 || HW <= 0) return AST_E_BADARG;
@@ -761,7 +786,7 @@ extern "C" int ast_bn_stats(const void* x, int ld, double* sums, int N, int C, i
   cudaStream_t s = (cudaStream_t)stream;
   AST_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s));
   const int groups = kT / (C / 8);
-  bn_stats_kernel<<<dim3(pick_chunks(N, HW, C), N), kT, (size_t)groups * 2 * C * 4, s>>>(CBF(x), ld, sums, C, HW);
+  AST_ACT_DISPATCH(bn_stats_kernel<AT><<<dim3(pick_chunks(N, HW, C), N), kT, (size_t)groups * 2 * C * 4, s>>>(CAC(x), ld, sums, C, HW));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -786,8 +811,8 @@ extern "C" int ast_affine_act(const void* x, int ld_x, const float* sc, const fl
   cudaStream_t s = (cudaStream_t)stream;
   if (pool) AST_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)N * C, s));
   const int groups = kT / (C / 8);
-  affine_act_kernel<<<dim3(pick_chunks(N, HW, C), N), kT, pool ? (size_t)groups * C * 4 : 0, s>>>(
-      CBF(x), ld_x, sc, sh, act, se, CBF(res), ld_res, BF(out), ld_out, pool, C, HW);
+  AST_ACT_DISPATCH(affine_act_kernel<AT><<<dim3(pick_chunks(N, HW, C), N), kT, pool ? (size_t)groups * C * 4 : 0, s>>>(
+      CAC(x), ld_x, sc, sh, act, se, CAC(res), ld_res, AC(out), ld_out, pool, C, HW));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -801,9 +826,9 @@ extern "C" int ast_dw_bwd_reduce(const void* du, const void* a, const float* sta
   const int groups = kT / (C / 8);
   const size_t smem = (size_t)groups * 5 * C * 4;   // <= 40 KB
   if (stat)
-    dw_bwd_reduce_kernel<true><<<dim3(pick_chunks(N, HW, C), N), kT, smem, s>>>(CBF(du), CBF(a), stat, out, C, HW);
+    AST_ACT_DISPATCH(dw_bwd_reduce_kernel<AT, true><<<dim3(pick_chunks(N, HW, C), N), kT, smem, s>>>(CGR(du), CAC(a), stat, out, C, HW));
   else
-    dw_bwd_reduce_kernel<false><<<dim3(pick_chunks(N, HW, C), N), kT, smem / 5, s>>>(CBF(du), CBF(a), stat, out, C, HW);
+    AST_ACT_DISPATCH(dw_bwd_reduce_kernel<AT, false><<<dim3(pick_chunks(N, HW, C), N), kT, smem / 5, s>>>(CGR(du), CAC(a), stat, out, C, HW));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -822,11 +847,11 @@ extern "C" int ast_dw_bwd_apply(const void* du, const void* a, const float* s, c
   if (!du || !a || !s || !g || !da || N <= 0 || HW <= 0 || (stat && !coef)) return AST_E_BADARG;
   if (!chan_ok(C) || N > 65535) return AST_E_SHAPE;
   if (stat)
-    dw_bwd_apply_kernel<true><<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
-        CBF(du), CBF(a), s, g, stat, coef, BF(da), C, HW);
+    AST_ACT_DISPATCH(dw_bwd_apply_kernel<AT, true><<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
+        CGR(du), CAC(a), s, g, stat, coef, GR(da), C, HW));
   else
-    dw_bwd_apply_kernel<false><<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
-        CBF(du), CBF(a), s, g, stat, coef, BF(da), C, HW);
+    AST_ACT_DISPATCH(dw_bwd_apply_kernel<AT, false><<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
+        CGR(du), CAC(a), s, g, stat, coef, GR(da), C, HW));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -838,8 +863,8 @@ extern "C" int ast_bn_bwd_reduce(const void* dy, int ld_dy, const void* a, int l
   cudaStream_t s = (cudaStream_t)stream;
   AST_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s));
   const int groups = kT / (C / 8);
-  bn_bwd_reduce_kernel<<<dim3(pick_chunks(N, HW, C), N), kT, (size_t)groups * 2 * C * 4, s>>>(
-      CBF(dy), ld_dy, CBF(a), ld_a, stat, sums, C, HW);
+  AST_ACT_DISPATCH(bn_bwd_reduce_kernel<AT><<<dim3(pick_chunks(N, HW, C), N), kT, (size_t)groups * 2 * C * 4, s>>>(
+      CGR(dy), ld_dy, CAC(a), ld_a, stat, sums, C, HW));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -857,8 +882,8 @@ extern "C" int ast_bn_bwd_apply(const void* dy, int ld_dy, const void* a, int ld
                                 const float* coef, void* da, int N, int C, int64_t HW, void* stream) {
   if (!dy || !a || !stat || !coef || !da || N <= 0 || HW <= 0) return AST_E_BADARG;
   if (!chan_ok(C) || ld_dy % 8 != 0 || ld_dy < C || ld_a % 8 != 0 || ld_a < C || N > 65535) return AST_E_SHAPE;
-  bn_bwd_apply_kernel<<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
-      CBF(dy), ld_dy, CBF(a), ld_a, stat, coef, BF(da), C, HW);
+  AST_ACT_DISPATCH(bn_bwd_apply_kernel<AT><<<dim3(pick_chunks(N, HW, C), N), kT, 0, (cudaStream_t)stream>>>(
+      CGR(dy), ld_dy, CAC(a), ld_a, stat, coef, GR(da), C, HW));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -876,8 +901,8 @@ extern "C" int ast_dw_conv_dgrad(const void* dy, const float* w, const void* a_p
     const int r = dw_tiled_dgrad(dy, w, a_pre, stat, dres, dx, N, C, H, W, k, (cudaStream_t)stream);
     if (r != AST_E_SHAPE) return r;
   }
-  dw_dgrad_kernel<<<dim3(pick_chunks(N, (int64_t)H * W, C), N), kT, 0, (cudaStream_t)stream>>>(
-      CBF(dy), w, CBF(a_pre), stat, CBF(dres), BF(dx), C, H, W, Ho, Wo, k, stride, up2);
+  AST_ACT_DISPATCH(dw_dgrad_kernel<AT><<<dim3(pick_chunks(N, (int64_t)H * W, C), N), kT, 0, (cudaStream_t)stream>>>(
+      CGR(dy), w, CAC(a_pre), stat, CGR(dres), GR(dx), C, H, W, Ho, Wo, k, stride, up2));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -900,9 +925,9 @@ extern "C" int ast_dw_conv_wgrad(const void* dy, const void* x, float* dw, int N
   if (chunks < 1) chunks = 1;
   cudaStream_t s = (cudaStream_t)stream;
   if (k == 3)
-    dw_wgrad_kernel<3><<<dim3(chunks, N, 3), kT, smem, s>>>(CBF(dy), CBF(x), dw, C, H, W, Ho, Wo, stride, up2);
+    AST_ACT_DISPATCH(dw_wgrad_kernel<AT, 3><<<dim3(chunks, N, 3), kT, smem, s>>>(CGR(dy), CAC(x), dw, C, H, W, Ho, Wo, stride, up2));
   else
-    dw_wgrad_kernel<5><<<dim3(chunks, N, 5), kT, smem, s>>>(CBF(dy), CBF(x), dw, C, H, W, Ho, Wo, stride, up2);
+    AST_ACT_DISPATCH(dw_wgrad_kernel<AT, 5><<<dim3(chunks, N, 5), kT, smem, s>>>(CGR(dy), CAC(x), dw, C, H, W, Ho, Wo, stride, up2));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -932,7 +957,7 @@ extern "C" int ast_stem_wgrad(const void* dy, const void* z, const float* img, f
   if (Cout != 16) return AST_E_SHAPE;
   int64_t nb = ((int64_t)N * H * W + kT - 1) / kT;
   if (nb > 148 * 2) nb = 148 * 2;
-  stem_wgrad_kernel<<<dim3((unsigned)nb, 9), kT, 0, (cudaStream_t)stream>>>(CBF(dy), CBF(z), img, dw, N, H, W);
+  AST_ACT_DISPATCH(stem_wgrad_kernel<AT><<<dim3((unsigned)nb, 9), kT, 0, (cudaStream_t)stream>>>(CGR(dy), CAC(z), img, dw, N, H, W));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -943,7 +968,7 @@ extern "C" int ast_head_wgrad(const float* dY, const void* x, float* dw, float* 
   if (Cin != 16 || Cout != 3) return AST_E_SHAPE;
   int64_t nb = ((int64_t)N * H * W + kT - 1) / kT;
   if (nb > 148 * 2) nb = 148 * 2;
-  head_wgrad_kernel<<<dim3((unsigned)nb, 9), kT, 0, (cudaStream_t)stream>>>(dY, CBF(x), dw, db, N, H, W);
+  AST_ACT_DISPATCH(head_wgrad_kernel<AT><<<dim3((unsigned)nb, 9), kT, 0, (cudaStream_t)stream>>>(dY, CAC(x), dw, db, N, H, W));
   AST_CHECK_LAUNCH();
   return 0;
 }
@@ -954,25 +979,40 @@ extern "C" int ast_head_dgrad(const float* dY, const float* w, void* dx, int N, 
   if (Cin != 16 || Cout != 3) return AST_E_SHAPE;
   const int64_t nb = ((int64_t)N * H * W + 127) / 128;
   if (nb >= 0x7fffffffLL) return AST_E_SHAPE;
-  head_dgrad_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(dY, w, BF(dx), N, H, W);
+  head_dgrad_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(dY, w, GR(dx), N, H, W);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_cvt_f16_to_bf16(const void* x, int64_t ld_x, void* out, int64_t ld_out, int64_t rows, int C,
+                                   void* stream) {
+  if (!x || !out || rows <= 0 || C <= 0) return AST_E_BADARG;
+  if (C % 8 != 0 || ld_x % 8 != 0 || ld_out % 8 != 0 || ld_x < C || ld_out < C) return AST_E_SHAPE;
+  if (!aligned16(x) || !aligned16(out)) return AST_E_ALIGN;
+  const int64_t total = rows * (C / 8);
+  int64_t nb = (total + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (ast::act_format() != AST_DT_F16) return AST_E_BADARG;   // bf16 activations need no conversion
+  { using AT = __half; cvt_act_to_grad_kernel<AT><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(CAC(x), ld_x, GR(out), ld_out, rows, C / 8); }
   AST_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int ast_prep_weight(const float* w, void* out, int R, int Cc, int mode, void* stream) {
-  if (!w || !out || R <= 0 || Cc <= 0 || mode < 0 || mode > 2) return AST_E_BADARG;
+  if (!w || !out || R <= 0 || Cc <= 0 || mode < 0 || mode > 3) return AST_E_BADARG;
   int64_t nb = ((int64_t)R * Cc + 255) / 256;
   if (nb > 148 * 4) nb = 148 * 4;
-  prep_weight_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(w, out, R, Cc, mode);
+  AST_ACT_DISPATCH(prep_weight_kernel<AT><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(w, out, R, Cc, mode));
   AST_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int ast_nchw_to_nhwc(const float* x, void* out, int ld, int N, int C, int64_t HW, void* stream) {
-  if (!x || !out || N <= 0 || C <= 0 || HW <= 0 || ld < C) return AST_E_BADARG;
+extern "C" int ast_nchw_to_nhwc(const float* x, void* out, int ld, int N, int C, int64_t HW, int dtype, void* stream) {
+  if (!x || !out || N <= 0 || C <= 0 || HW <= 0 || ld < C || (dtype != AST_DT_BF16 && dtype != AST_DT_F16)) return AST_E_BADARG;
   if (N > 65535 || (C + 31) / 32 > 65535 || (HW + 31) / 32 >= 0x7fffffffLL) return AST_E_SHAPE;
   dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
-  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, BF(out), ld, C, HW);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint16_t*>(out), ld, C, HW,
+                                                              dtype == AST_DT_F16);
   AST_CHECK_LAUNCH();
   return 0;
 }

@@ -32,9 +32,11 @@ struct PwParams {
   int64_t HW;
   int ld_out, ld_res;              // row strides (elements) of out / residual
   const float* bias;               // [Cout] or null
-  const __nv_bfloat16* residual;   // [N*HW][ld_res] or null
-  __nv_bfloat16* out;              // [N*HW][ld_out]
-  __nv_bfloat16* out_act;          // optional [N*HW][ld_act]: Hardswish(out) while out keeps the raw value
+  int f16;                         // all 16-bit tensors of the call are fp16 (forward activations / weights) instead of
+                                   // bf16 (gradients, attention rows): instruction descriptor + epilogue conversions
+  const uint16_t* residual;        // [N*HW][ld_res] or null
+  uint16_t* out;                   // [N*HW][ld_out]
+  uint16_t* out_act;               // optional [N*HW][ld_act]: Hardswish(out) while out keeps the raw value
   int ld_act;
   int res_w;                       // > 0: residual is read through a nearest x2 upsample; res_w = output width
 };
@@ -98,7 +100,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, p.BN);
+    const uint32_t idesc = p.f16 ? make_idesc_f16(128, p.BN) : make_idesc_bf16(128, p.BN);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t accum = 0;
@@ -151,21 +153,24 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       const int valid = min(16, p.Cout - co0);   // multiple of 8 (host enforces Cout % 8 == 0)
       if (p.residual) {
-        const __nv_bfloat16* rp = p.residual + rrow * p.ld_res + co0;
+        const uint16_t* rp = p.residual + rrow * p.ld_res + co0;
         for (int i = 0; i < valid; i += 8) {
           float r[8];
-          Vec16<true>::unpack(__ldg(reinterpret_cast<const uint4*>(rp + i)), r);
+          unpack8_dt(__ldg(reinterpret_cast<const uint4*>(rp + i)), r, p.f16);
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[i + j] += r[j];
         }
       }
-      __nv_bfloat16* op = p.out + row * p.ld_out + co0;
+      uint16_t* op = p.out + row * p.ld_out + co0;
       if (wide_ok && valid == 16) {   // one 32-byte sector per lane per store
         uint32_t pk[8], pa[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-          if (p.out_act) pa[j] = pack_bf16(hardswish(bf16lo(pk[j])), hardswish(bf16hi(pk[j])));
+          pk[j] = pk2_dt(f[2 * j], f[2 * j + 1], p.f16);
+          if (p.out_act) {
+            const float2 rr = un2_dt(pk[j], p.f16);
+            pa[j] = pk2_dt(hardswish(rr.x), hardswish(rr.y), p.f16);
+          }
         }
         st_global_v8(op, pk);
         if (p.out_act) st_global_v8(p.out_act + row * p.ld_act + co0, pa);
@@ -175,14 +180,14 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = f[i + j];
-        const uint4 ov = Vec16<true>::pack(o);
+        const uint4 ov = pack8_dt(o, p.f16);
         *reinterpret_cast<uint4*>(op + i) = ov;
         if (p.out_act) {   // training: raw pre-activation in `out`, Hardswish of the ROUNDED value here
           float r[8];
-          Vec16<true>::unpack(ov, r);
+          unpack8_dt(ov, r, p.f16);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] = hardswish(r[j]);
-          *reinterpret_cast<uint4*>(p.out_act + row * p.ld_act + co0 + i) = Vec16<true>::pack(r);
+          *reinterpret_cast<uint4*>(p.out_act + row * p.ld_act + co0 + i) = pack8_dt(r, p.f16);
         }
       }
     }
@@ -203,8 +208,10 @@ using namespace ast::tc;
 
 extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_sample_w, const float* bias,
                            int act, const void* residual, int ld_res, void* out, int ld_out, int N,
-                           int64_t HW, int Cin, int Cout, void* out_act, int ld_act, int res_up2_w, void* stream) {
+                           int64_t HW, int Cin, int Cout, void* out_act, int ld_act, int res_up2_w, int dtype,
+                           void* stream) {
   if (!x || !w || !out || N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0) return AST_E_BADARG;
+  if (dtype != AST_DT_BF16 && dtype != AST_DT_F16) return AST_E_BADARG;
   if (out_act && (ld_act % 8 != 0 || ld_act < Cout || !aligned16(out_act) || residual)) return AST_E_SHAPE;
   if (Cin % 8 != 0 || Cout % 8 != 0 || ld_in % 8 != 0 || ld_out % 8 != 0 || (residual && ld_res % 8 != 0))
     return AST_E_SHAPE;
@@ -222,9 +229,10 @@ extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_samp
   p.tiles_per_img = (int)((HW + 127) / 128);
   p.per_sample_w = per_sample_w; p.act = act;
   p.ld_out = ld_out; p.ld_res = ld_res;
-  p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.out_act = reinterpret_cast<__nv_bfloat16*>(out_act);
+  p.f16 = dtype == AST_DT_F16;
+  p.bias = bias; p.residual = reinterpret_cast<const uint16_t*>(residual);
+  p.out = reinterpret_cast<uint16_t*>(out);
+  p.out_act = reinterpret_cast<uint16_t*>(out_act);
   p.ld_act = ld_act;
   if (res_up2_w < 0 || (res_up2_w > 0 && (!residual || res_up2_w % 2 != 0 || HW % res_up2_w != 0 ||
                                           (HW / res_up2_w) % 2 != 0)))

@@ -225,6 +225,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Same with fp16 operands (a_format = b_format = 0).  The two operands must share one format: an fp16 x bf16
+// descriptor is rejected by the hardware as an illegal instruction (tools/ubench/mixed_fmt.cu).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- host: tensor-map encoder through the runtime's driver entry point (no -lcuda link) ------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

@@ -4,6 +4,13 @@ building blocks ``DepthWiseConv`` / ``SELayer`` / ``conv_3x3_bn`` (mobilenetv2.p
 95-181).  Module trees, attribute names and ModuleList indices mirror the reference so that its
 state dicts (``ae.pth`` keys such as ``encoder.mob_net.1._layers.3.weight``) load unchanged.
 
+Storage formats.  Forward activations (and the GEMM weights they meet) are IEEE **fp16**; gradients are **bf16**
+(include/ast_b200.h, K4).  autograd casts a gradient to the dtype of the tensor it belongs to, so a tensor pair
+(fp16 activation, bf16 gradient) cannot be declared to torch as such: every internal NHWC tensor is therefore a
+``torch.bfloat16`` tensor used as an opaque 16-bit container -- forward tensors hold fp16 BIT PATTERNS (``act_bits`` /
+``act_float`` convert), gradient tensors are genuine bf16 (so autograd's own accumulation of gradients is correct).
+No torch arithmetic ever touches a forward tensor; the public boundary is NCHW fp32.
+
 Two execution paths, both entirely through libast_b200 (no torch arithmetic on activations):
   * inference (eval mode, no grad): BatchNorm running statistics folded into the convolutions, SE
     excitation folded into per-sample pointwise weights, SE squeeze fused into the depthwise stencil;
@@ -65,12 +72,51 @@ def _rows(t):
     return t, ld
 
 
+BITS16 = torch.bfloat16      # torch-level dtype of every internal NHWC tensor (opaque container, see module docstring)
+
+
 def _empty(N, H, W, Cc, dev):
-    return torch.empty(N, H, W, Cc, device=dev, dtype=torch.bfloat16)
+    return torch.empty(N, H, W, Cc, device=dev, dtype=BITS16)
 
 
-def pw_conv(x, w_bf16, bias, act, out_channels, residual=None, per_sample=False, want_raw=False, res_up2=False):
-    """x: (N,H,W,Cin) bf16 row-strided -> (N,H,W,Cout) bf16.  ``want_raw`` (training): returns
+_ACT_F16 = [True]
+
+
+def set_activation_format(fmt: str) -> None:
+    """Process-wide storage format of the forward activations: ``"fp16"`` (default: 11-bit significand, values below
+    6e-8 flush to zero, saturation at 65504) or ``"bf16"`` (8-bit significand, fp32's exponent range).  fp16 is what
+    brings the whole network within ~1 % of the fp32 reference; bf16 is for states whose activations leave fp16's
+    range -- e.g. training from the reference's fresh initialisation, whose closed SE gates put decoder activations
+    around 1e-20 (oracle/restate_ae.py::activate_gates).  Switch only while no internal tensor is alive (derived weight
+    caches are keyed on the format)."""
+    if fmt not in ("fp16", "bf16"):
+        raise L.AstError("activation format must be 'fp16' or 'bf16'")
+    L.check(L.load().ast_set_act_format(L.DT_F16 if fmt == "fp16" else L.DT_BF16), "ast_set_act_format")
+    _ACT_F16[0] = fmt == "fp16"
+
+
+def activation_format() -> str:
+    return "fp16" if _ACT_F16[0] else "bf16"
+
+
+def act_is_f16() -> bool:
+    return _ACT_F16[0]
+
+
+def act_bits(x: torch.Tensor) -> torch.Tensor:
+    """fp32 values -> the 16-bit container holding them in the activation format (what forward kernels read)."""
+    return x.to(torch.float16).view(BITS16) if _ACT_F16[0] else x.to(torch.bfloat16)
+
+
+def act_float(t: torch.Tensor) -> torch.Tensor:
+    """A forward (activation) tensor of this module -> fp32 values."""
+    return t.view(torch.float16).float() if _ACT_F16[0] else t.float()
+
+
+def pw_conv(x, w_bf16, bias, act, out_channels, residual=None, per_sample=False, want_raw=False, res_up2=False,
+            f16=False):
+    """x: (N,H,W,Cin) row-strided -> (N,H,W,Cout).  ``f16``: x / weights / residual / outputs are fp16 (forward
+    activations), else bf16 (gradients, attention rows).  ``want_raw`` (training): returns
     (raw pre-activation, Hardswish(raw)).  ``res_up2``: residual is the half-resolution tensor, read
     through a nearest x2 upsample."""
     lib = L.load()
@@ -83,7 +129,8 @@ def pw_conv(x, w_bf16, bias, act, out_channels, residual=None, per_sample=False,
         residual, ld_res = _rows(residual)
     L.check(lib.ast_pw_conv(x.data_ptr(), ldx, w_bf16.data_ptr(), int(per_sample), L.ptr(bias), int(act),
                             L.ptr(residual), ld_res, out.data_ptr(), out_channels, N, H * W, Cin, out_channels,
-                            L.ptr(out_act), out_channels, W if res_up2 else 0, _st(x)), "ast_pw_conv")
+                            L.ptr(out_act), out_channels, W if res_up2 else 0, L.DT_F16 if f16 else L.DT_BF16,
+                            _st(x)), "ast_pw_conv")
     return (out, out_act) if want_raw else out
 
 
@@ -130,63 +177,81 @@ def affine_act(x, sc, sh, act, se=None, res=None, want_out=True, want_pool=False
 
 
 def prep_weight(w, rows, cols, mode):
-    """fp32 parameter viewed as [rows][cols] -> 0: bf16 same layout, 1: bf16 transposed, 2: fp32 transposed."""
+    """fp32 parameter viewed as [rows][cols] -> 0: bf16 same layout, 1: bf16 transposed, 2: fp32 transposed,
+    3: fp16 same layout (forward GEMM weights; returned in the 16-bit container dtype)."""
     lib = L.load()
     w = w.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    shape = (rows, cols) if mode == 0 else (cols, rows)
-    out = torch.empty(shape, device=w.device, dtype=torch.float32 if mode == 2 else torch.bfloat16)
+    shape = (rows, cols) if mode in (0, 3) else (cols, rows)
+    out = torch.empty(shape, device=w.device, dtype=torch.float32 if mode == 2 else BITS16)
     L.check(lib.ast_prep_weight(w.data_ptr(), out.data_ptr(), rows, cols, mode, _st(w)), "ast_prep_weight")
     return out
 
 
-def nchw_to_nhwc(x):
+def nchw_to_nhwc(x, f16=False):
+    """NCHW fp32 -> NHWC 16-bit: fp16 bit patterns (``f16``, forward activations) or bf16 (gradients, attention)."""
     lib = L.load()
     x = x.float().contiguous()
     N, Cc, H, W = x.shape
     out = _empty(N, H, W, Cc, x.device)
-    L.check(lib.ast_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), Cc, N, Cc, H * W, _st(x)), "ast_nchw_to_nhwc")
+    L.check(lib.ast_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), Cc, N, Cc, H * W, L.DT_F16 if f16 else L.DT_BF16,
+                                 _st(x)), "ast_nchw_to_nhwc")
     return out
 
 
-def nhwc_to_nchw(x):
+def nhwc_to_nchw(x, f16=False):
     lib = L.load()
     x, ld = _rows(x)
     N, H, W, Cc = x.shape
     out = torch.empty(N, Cc, H, W, device=x.device, dtype=torch.float32)
-    L.check(lib.ast_nhwc_to_nchw(x.data_ptr(), ld, out.data_ptr(), N, Cc, H * W, _st(x)), "ast_nhwc_to_nchw")
+    L.check(lib.ast_nhwc_to_nchw(x.data_ptr(), ld, out.data_ptr(), N, Cc, H * W, L.DT_F16 if f16 else L.DT_BF16,
+                                 _st(x)), "ast_nhwc_to_nchw")
+    return out
+
+
+def act_to_grad_format(x):
+    """fp16 activation rows -> a bf16 copy: the weight-gradient GEMM multiplies it with a bf16 gradient and the
+    tensor cores take one 16-bit format per instruction (ast_cvt_f16_to_bf16)."""
+    lib = L.load()
+    x, ld = _rows(x)
+    N, H, W, Cc = x.shape
+    out = _empty(N, H, W, Cc, x.device)
+    L.check(lib.ast_cvt_f16_to_bf16(x.data_ptr(), ld, out.data_ptr(), Cc, N * H * W, Cc, _st(x)),
+            "ast_cvt_f16_to_bf16")
     return out
 
 
 class _ToNHWC(torch.autograd.Function):
-    """NCHW fp32 -> NHWC bf16; the gradient goes back through the inverse conversion."""
+    """NCHW fp32 -> NHWC fp16 activation; the (bf16) gradient goes back through the inverse conversion."""
 
     @staticmethod
     def forward(ctx, x):
-        return nchw_to_nhwc(x)
+        return nchw_to_nhwc(x, f16=act_is_f16())
 
     @staticmethod
     def backward(ctx, g):
-        return nhwc_to_nchw(g)
+        return nhwc_to_nchw(g, f16=False)
 
 
 class _ToNCHW(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        return nhwc_to_nchw(x)
+        return nhwc_to_nchw(x, f16=act_is_f16())
 
     @staticmethod
     def backward(ctx, g):
-        return nchw_to_nhwc(g)
+        return nchw_to_nhwc(g, f16=False)
 
 
 def to_nhwc(x):
-    return _ToNHWC.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else nchw_to_nhwc(x)
+    """NCHW fp32 -> the module's forward (activation) layout."""
+    return _ToNHWC.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else nchw_to_nhwc(x, f16=act_is_f16())
 
 
 def to_nchw(x):
-    return _ToNCHW.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else nhwc_to_nchw(x)
+    """A forward (activation) tensor -> NCHW fp32."""
+    return _ToNCHW.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else nhwc_to_nchw(x, f16=act_is_f16())
 
 
 def _fold_bn(conv_w, bn):
@@ -242,9 +307,14 @@ def _bn_backward(dy, a, stat):
     return da, dgamma, dbeta
 
 
-def _pw_wgrad(a, b, out, si, sj):
-    """out[i*si + j*sj] += sum_p a[p][i] * b[p][j]  (a, b NHWC row-strided bf16; out fp32, zero-filled)."""
+def _pw_wgrad(a, b, out, si, sj, a_is_act=False, b_is_act=False):
+    """out[i*si + j*sj] += sum_p a[p][i] * b[p][j]  (a, b NHWC row-strided; out fp32, zero-filled).  The GEMM runs
+    bf16 x bf16: an operand that is a forward activation (fp16) is converted first."""
     lib = L.load()
+    if a_is_act and act_is_f16():
+        a = act_to_grad_format(a)
+    if b_is_act and act_is_f16():
+        b = act_to_grad_format(b)
     a, lda = _rows(a)
     b, ldb = _rows(b)
     P = a.shape[0] * a.shape[1] * a.shape[2]
@@ -270,13 +340,13 @@ class _BlockFn(torch.autograd.Function):
         if expand:
             if up2:
                 raise L.AstError("the upsampled input is only supported for expand_ratio == 1 blocks")
-            w1b = prep_weight(P["w1"], hid, mod.inp, 0)
+            w1b = prep_weight(P["w1"], hid, mod.inp, 3)
             if norm:
-                a1 = pw_conv(x, w1b, None, 0, hid)
+                a1 = pw_conv(x, w1b, None, 0, hid, f16=act_is_f16())
                 stat1 = _bn_train_forward(a1, bns[0])
                 dw_in, _ = affine_act(a1, stat1[2], stat1[3], 1)
             else:
-                a1, dw_in = pw_conv(x, w1b, None, 1, hid, want_raw=True)
+                a1, dw_in = pw_conv(x, w1b, None, 1, hid, want_raw=True, f16=act_is_f16())
         else:
             dw_in = x
         wd = prep_weight(P["wd"], hid, k * k, 2)                       # fp32 [k*k][C]
@@ -288,14 +358,14 @@ class _BlockFn(torch.autograd.Function):
         inv_hw = 1.0 / (Ho * Wo)
         s, sehid, sepre = se_fc(pool, inv_hw, P["se_w1"], P["se_b1"], P["se_w2"], P["se_b2"], save=True)
         u, _ = affine_act(a2, stat2[2] if norm else None, stat2[3] if norm else None, 1, se=s)
-        w2b = prep_weight(P["w2"], mod.oup, hid, 0)
+        w2b = prep_weight(P["w2"], mod.oup, hid, 3)
         res = x if mod.identity else None
         if norm:
-            a3 = pw_conv(u, w2b, None, 0, mod.oup)
+            a3 = pw_conv(u, w2b, None, 0, mod.oup, f16=act_is_f16())
             stat3 = _bn_train_forward(a3, bns[2])
             out, _ = affine_act(a3, stat3[2], stat3[3], 0, res=res)
         else:
-            out = pw_conv(u, w2b, None, 0, mod.oup, residual=res, res_up2=bool(up2 and mod.identity))
+            out = pw_conv(u, w2b, None, 0, mod.oup, residual=res, res_up2=bool(up2 and mod.identity), f16=act_is_f16())
         ctx.mod, ctx.up2, ctx.geom = mod, up2, (N, H, W, Ho, Wo)
         ctx.n_params = len(params)
         ctx.save_for_backward(x, a1, dw_in if expand else None, a2, u, a3, s, sehid, sepre, pool, stat1, stat2,
@@ -323,7 +393,7 @@ class _BlockFn(torch.autograd.Function):
             d_a3 = d_out
         d_u = pw_conv(d_a3, prep_weight(P["w2"], oup, hid, 1), None, 0, hid)
         dW2 = torch.zeros_like(P["w2"], dtype=torch.float32)
-        _pw_wgrad(u, d_a3, dW2, 1, hid)                                  # dW2[j][i] += sum u[p][i] d_a3[p][j]
+        _pw_wgrad(u, d_a3, dW2, 1, hid, a_is_act=True)                   # dW2[j][i] += sum u[p][i] d_a3[p][j]
         grads["w2"] = dW2
         # ---- SE, Hardswish and the depthwise norm ----
         HWo = Ho * Wo
@@ -371,7 +441,7 @@ class _BlockFn(torch.autograd.Function):
             else:
                 d_a1 = d_in
             dW1 = torch.zeros_like(P["w1"], dtype=torch.float32)
-            _pw_wgrad(d_a1, x, dW1, inp, 1)                              # dW1[i][j] += sum d_a1[p][i] x[p][j]
+            _pw_wgrad(d_a1, x, dW1, inp, 1, b_is_act=True)               # dW1[i][j] += sum d_a1[p][i] x[p][j]
             grads["w1"] = dW1
             d_x = None
             if ctx.needs_input_grad[0]:
@@ -530,7 +600,7 @@ class DepthWiseConv(nn.Module):
 
     # -- derived kernel parameters, rebuilt when any parameter / buffer changes ---------------------
     def _prepared(self):
-        ver = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        ver = (act_is_f16(),) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
         if self._prep is not None and self._prep[0] == ver:
             return self._prep[1]
         mods = list(self._layers)
@@ -545,7 +615,7 @@ class DepthWiseConv(nn.Module):
         if self.expand:
             pw1, dw, pw2 = convs
             w, b = _fold_bn(pw1.weight, bn_after(pw1))
-            d["w1"] = w.view(self.hidden, self.inp).to(torch.bfloat16).contiguous()
+            d["w1"] = act_bits(w.view(self.hidden, self.inp)).contiguous()               # fp16 bit patterns
             d["b1"] = b.contiguous() if b is not None else None
         else:
             dw, pw2 = convs
@@ -608,19 +678,19 @@ class DepthWiseConv(nn.Module):
             return _BlockFn.apply(x, self, up2, *self._param_list())
         d = self._prepared()
         N = x.shape[0]
-        h = pw_conv(x, d["w1"], d["b1"], act=True, out_channels=self.hidden) if self.expand else x
+        h = pw_conv(x, d["w1"], d["b1"], act=True, out_channels=self.hidden, f16=act_is_f16()) if self.expand else x
         if not self.expand and not h.is_contiguous():
             h = h.contiguous()
         y, pool = dw_conv(h, d["wd"], d["bd"], self.k, self.stride, up2=up2, act=1, want_pool=True)
         Ho, Wo = y.shape[1], y.shape[2]
         w1, b1, w2, b2 = d["se"]
         scale, _, _ = se_fc(pool, 1.0 / (Ho * Wo), w1, b1, w2, b2)
-        w2s = torch.empty(N, self.oup, self.hidden, device=x.device, dtype=torch.bfloat16)
+        w2s = torch.empty(N, self.oup, self.hidden, device=x.device, dtype=BITS16)
         L.check(lib.ast_scale_weights(d["w2"].data_ptr(), scale.data_ptr(), w2s.data_ptr(), N, self.oup,
                                       self.hidden, _st(x)), "ast_scale_weights")
         res = x if self.identity else None
         return pw_conv(y, w2s, d["b2"], act=False, out_channels=self.oup, residual=res, per_sample=True,
-                       res_up2=bool(up2 and self.identity))
+                       res_up2=bool(up2 and self.identity), f16=act_is_f16())
 
     def forward(self, x):
         """NCHW fp32 in / out like the reference module."""

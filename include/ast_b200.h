@@ -299,15 +299,32 @@ int ast_unpack_wgrad(const float* dwpk, float* w_grad, const void* dz_planar, fl
                      int Cin, int64_t ldq, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * K4  MobileNet-style blocks (Encoder / Decoder / AutoEncoder, eval mode), plain NHWC bf16.
+ * K4  MobileNet-style blocks (Encoder / Decoder / AutoEncoder, eval mode), plain NHWC 16-bit.
  * Replaces the layers of DepthWiseConv (mobilenetv2.py:95-165), SELayer (:63-81), conv_3x3_bn
  * (:38-43) and Decoder._ref_out/_img_out (models.py:300-316).
+ *
+ * Storage formats.  Forward ACTIVATIONS -- and the weights they meet in the tensor cores -- are IEEE fp16 (11-bit
+ * significand, conversions saturate at +-65504): with bf16's 8 bits the roundings of ~30 blocks in series put 5 % on
+ * the deepest encoder tap and 25 % on the stem's weight gradient, all of it from the forward roundings (DESIGN.md
+ * section 5).  GRADIENTS are bf16 (range, not precision).  "act" / "grad" below name the role; entry points that
+ * serve both roles take a `dtype` argument.  tcgen05.mma takes ONE 16-bit format per instruction, so the
+ * weight-gradient GEMM (ast_pw_wgrad: bf16 x bf16) gets its activation operand through ast_cvt_f16_to_bf16.
  * ------------------------------------------------------------------------------------- */
+#define AST_DT_BF16 0
+#define AST_DT_F16  1
+/* Process-wide format of the K4 forward activations: AST_DT_F16 (default: precision) or AST_DT_BF16 (fp32's exponent
+ * range: e.g. training from the reference's fresh initialisation, whose closed SE gates leave decoder activations
+ * around 1e-20, below fp16's 6e-8).  Set it before any K4 tensor exists; tensors written under one format must not be
+ * read under the other.  Gradients are bf16 under both. */
+int ast_set_act_format(int dtype);
+int ast_get_act_format(void);
 
 /* Pointwise conv as a tcgen05 GEMM: out[p][co] = act(sum_ci x[p][ci] * w[n?][co][ci] + bias[co]) (+ res).
- *   x   : bf16 [N*HW][ld_in]  (first Cin channels of each row are read)
- *   w   : bf16 [Cout][Cin], or [N][Cout][Cin] when per_sample_w (SE scaling folded in)
- *   act : 0 none, 1 Hardswish;  residual (optional): bf16 [N*HW][ld_res];  out: bf16 [N*HW][ld_out]
+ *   dtype : AST_DT_F16 (forward: activations and weights fp16) or AST_DT_BF16 (data gradients, attention rows);
+ *           x, w, residual, out and out_act all have that format
+ *   x   : [N*HW][ld_in]  (first Cin channels of each row are read)
+ *   w   : [Cout][Cin], or [N][Cout][Cin] when per_sample_w (SE scaling folded in)
+ *   act : 0 none, 1 Hardswish;  residual (optional): [N*HW][ld_res];  out: [N*HW][ld_out]
  * Cin, Cout, ld_* multiples of 8. */
 /*   out_act (optional, training): `out` keeps the raw pre-activation and out_act [N*HW][ld_act] receives
  *   Hardswish of the rounded value (both are needed by the backward pass); excludes residual.
@@ -315,10 +332,10 @@ int ast_unpack_wgrad(const float* dwpk, float* w_grad, const void* dz_planar, fl
  *   upsample (DecoderBlock._upsample_3 + identity of _upsample_2); res_up2_w = width of the output grid. */
 int ast_pw_conv(const void* x, int ld_in, const void* w, int per_sample_w, const float* bias, int act,
                 const void* residual, int ld_res, void* out, int ld_out, int N, int64_t HW, int Cin,
-                int Cout, void* out_act, int ld_act, int res_up2_w, void* stream);
+                int Cout, void* out_act, int ld_act, int res_up2_w, int dtype, void* stream);
 
 /* Depthwise k x k (3 or 5), stride 1 or 2, reflect padding (k-1)/2, + bias + optional Hardswish.
- *   x : bf16 [N][H][W][C]; w : fp32 [k*k][C]; out : bf16 [N][Ho][Wo][C]
+ *   x : act (fp16) [N][H][W][C]; w : fp32 [k*k][C]; out : act [N][Ho][Wo][C]
  *   pool (optional) : fp32 [N][C], receives the per-channel SUM of the output (SE squeeze)
  *   up2 : read x through a virtual nearest x2 upsample (conv input = 2H x 2W).
  *   act : 0 none, 1 store Hardswish(y), 2 (training) store raw y and pool Hardswish(y). */
@@ -331,28 +348,32 @@ int ast_se_fc(const float* pool, float inv_hw, const float* w1, const float* b1,
               const float* b2, float* scale, float* hid_out, float* pre_out, int N, int C, int S,
               void* stream);
 
-/* out[n][co][ci] (bf16) = w[co][ci] * se[n][ci]  (se NULL: plain cast, N copies). */
+/* out[n][co][ci] (fp16) = w[co][ci] * se[n][ci]  (se NULL: plain cast, N copies). */
 int ast_scale_weights(const float* w, const float* se, void* out, int N, int Cout, int Cin, void* stream);
 
-/* Stem: NCHW fp32 image -> conv3x3 (reflect pad, no bias) -> Hardswish -> NHWC bf16; Cout <= 32. */
-/* out_raw (optional, training): the rounded pre-activation, NHWC bf16. */
+/* Stem: NCHW fp32 image -> conv3x3 (reflect pad, no bias) -> Hardswish -> NHWC act (fp16); Cout <= 32. */
+/* out_raw (optional, training): the rounded pre-activation, NHWC act. */
 int ast_stem_conv(const float* img, const float* w, void* out, void* out_raw, int N, int H, int W, int Cout,
                   void* stream);
 
-/* Image head: NHWC bf16 -> ReflectionPad2d(1) -> conv3x3 + bias -> NCHW fp32 (+ Hardtanh(0,1)). */
+/* Image head: NHWC act (fp16) -> ReflectionPad2d(1) -> conv3x3 + bias -> NCHW fp32 (+ Hardtanh(0,1)). */
 int ast_head_conv(const void* x, const float* w, const float* bias, float* out, int N, int H, int W,
                   int Cin, int Cout, int clamp01, void* stream);
 
-/* NHWC bf16 (row stride ld) -> NCHW fp32. */
-int ast_nhwc_to_nchw(const void* x, int ld, float* out, int N, int C, int64_t HW, void* stream);
+/* NHWC 16-bit (row stride ld, format `dtype`) -> NCHW fp32. */
+int ast_nhwc_to_nchw(const void* x, int ld, float* out, int N, int C, int64_t HW, int dtype, void* stream);
 
-/* NCHW fp32 -> NHWC bf16 (row stride ld). */
-int ast_nchw_to_nhwc(const float* x, void* out, int ld, int N, int C, int64_t HW, void* stream);
+/* NCHW fp32 -> NHWC 16-bit (row stride ld, format `dtype`). */
+int ast_nchw_to_nhwc(const float* x, void* out, int ld, int N, int C, int64_t HW, int dtype, void* stream);
+
+/* fp16 activation rows -> bf16 copy [rows][ld_out] (first C channels), the operand of ast_pw_wgrad. */
+int ast_cvt_f16_to_bf16(const void* x, int64_t ld_x, void* out, int64_t ld_out, int64_t rows, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4t  Training mode of the MobileNet-style blocks (train_autoencoder.py:111-148): nn.BatchNorm2d with
  * batch statistics (mobilenetv2.py:108,128,137,149), Hardswish / SELayer / residual passes and all
- * backward kernels.  Tensors are NHWC bf16 [N*HW][ld]; statistics fp32, cross-CTA sums fp64.
+ * backward kernels.  Tensors are NHWC [N*HW][ld]: activations (x, a, a_pre, z, res, out of forward passes) fp16,
+ * gradients (du, dy, da, dx, dres) bf16; statistics fp32, cross-CTA sums fp64.
  * `stat` = float[4][C]: mean, invstd, scale = gamma*invstd, shift = beta - mean*scale.
  * ------------------------------------------------------------------------------------- */
 
@@ -410,7 +431,7 @@ int ast_head_wgrad(const float* dY, const void* x, float* dw, float* db, int N, 
                    void* stream);
 int ast_head_dgrad(const float* dY, const float* w, void* dx, int N, int H, int W, int Cin, int Cout,
                    void* stream);
-/* fp32 [R][Cc] -> mode 0: bf16 [R][Cc]; 1: bf16 [Cc][R]; 2: fp32 [Cc][R]. */
+/* fp32 [R][Cc] -> mode 0: bf16 [R][Cc]; 1: bf16 [Cc][R]; 2: fp32 [Cc][R]; 3: fp16 [R][Cc] (forward GEMM weights). */
 int ast_prep_weight(const float* w, void* out, int R, int Cc, int mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -316,16 +316,23 @@ def calibrate_running_stats(P, x):
 
 
 # ------------------------------------------------------------------------------------------------------
-# The bf16 STORAGE CONTRACT of the CUDA inference path, restated on CPU.
+# The 16-bit STORAGE CONTRACT of the CUDA inference path, restated on CPU.
 # Same mathematics as depthwise_block(..., training=False), but every tensor the kernels keep in HBM is rounded
-# to bf16 at exactly the point where they round it: the folded pointwise weights, the Hardswish'ed expand
+# to the storage format -- IEEE fp16 since round 2 (fmt="fp16"; "bf16" restates the round-1 kernels and shows what the
+# 8-bit significand cost: 5 % at the deepest encoder tap at 256 x 256, 0.6 % with fp16) -- at exactly the point where
+# they round it: the folded pointwise weights, the Hardswish'ed expand
 # output, the Hardswish'ed depthwise output, the SE-scaled per-sample pointwise weights and the block output
 # (after bias and residual).  Accumulation, biases, BatchNorm folding, SE and the depthwise weights stay fp32.
 # Comparing the fp32 restatement with this one shows what bf16 storage costs on a given state (it is what the
 # CUDA path is allowed to differ by); comparing the CUDA path with this one checks the kernels themselves.
 # ------------------------------------------------------------------------------------------------------
+_FMT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+_fmt = ["fp16"]
+
+
 def _bf(t):
-    return t.to(torch.bfloat16).float()
+    """round-trip through the storage format of the contract being restated (fp16 unless set otherwise)"""
+    return t.to(_FMT[_fmt[0]]).float()
 
 
 def _fold_bn_eval(P, conv_key, bn_key):
@@ -375,9 +382,18 @@ def depthwise_block_bf16(P, prefix, x, inp, oup, stride, t, k=3, norm=False, use
     return _bf(o)
 
 
-def autoencoder_forward_bf16(P, x, want=()):
-    """AutoEncoder.forward in eval mode under the bf16 storage contract.  Returns (image, {name: tensor}) with the
-    intermediate tensors named in ``want`` ('enc<i>', 'code')."""
+def autoencoder_forward_contract(P, x, want=(), fmt="fp16"):
+    """AutoEncoder.forward in eval mode under the 16-bit storage contract of the CUDA path (``fmt``: "fp16" = the
+    kernels as they are, "bf16" = the round-1 kernels).  Returns (image, {name: tensor}) with the intermediate
+    tensors named in ``want`` ('enc<i>', 'code')."""
+    _fmt[0] = fmt
+    try:
+        return _autoencoder_forward_contract(P, x, want)
+    finally:
+        _fmt[0] = "fp16"
+
+
+def _autoencoder_forward_contract(P, x, want=()):
     keep = {}
     h = _bf(F.hardswish(F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), P["encoder.mob_net.0.0.weight"])))
     if "enc0" in want:

@@ -3,10 +3,14 @@ every K4 kernel in isolation against the same op in torch fp32 on bf16-rounded o
 blocks and the whole autoencoder (eval forward, train forward, one train_autoencoder.py step's
 gradients) against the CPU oracle and the golden vectors made from the genuine reference.
 
-Tolerances.  Activations and inter-layer gradients are stored in bf16 (8 mantissa bits): a single kernel
-agrees with fp32 arithmetic on the same rounded inputs to <= 1e-2 relative L2 (one rounding of the
-output, 2^-9 relative per element); chains of ~30 blocks are held to relative L2 <= 5e-2 / cosine
->= 0.995 on features and gradients and PSNR >= 40 dB on images, the bar BASELINE.json states for bf16."""
+Storage formats (include/ast_b200.h, K4): forward ACTIVATIONS are fp16 (11-bit significand), GRADIENTS bf16.  Tensors
+handed to the kernels are built with ``nhwc`` (activation: fp16 bit patterns in the package's 16-bit container) or
+``gnhwc`` (gradient: bf16) and read back with ``nchw`` / ``gnchw``; the torch references run in fp32 on operands
+rounded the same way (``f16r`` / ``bf16r``).
+
+Tolerances.  A single kernel agrees with fp32 arithmetic on the same rounded inputs to one rounding of its output:
+<= 1e-3 relative L2 for fp16 outputs, <= 5e-3 for bf16 outputs; whole blocks and the whole autoencoder are held to the
+bars stated with each test."""
 import numpy as np
 import pytest
 import torch
@@ -28,13 +32,33 @@ def cos(a, b):
     return F.cosine_similarity(a.double().cpu().flatten(), b.double().cpu().flatten(), dim=0).item()
 
 
+def f16r(x):
+    """round-trip through fp16 (what the K4 path stores for forward activations and GEMM weights)."""
+    return x.to(torch.float16).float()
+
+
 def nhwc(x):
-    """(N,C,H,W) fp32 -> (N,H,W,C) bf16 cuda, contiguous."""
-    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    """(N,C,H,W) fp32 -> (N,H,W,C) ACTIVATION tensor on the GPU: fp16 bit patterns in the 16-bit container dtype."""
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.float16).view(torch.bfloat16).cuda()
 
 
 def nchw(t):
+    """ACTIVATION tensor (fp16 bits) -> (N,C,H,W) fp32 on the CPU."""
+    return t.contiguous().view(torch.float16).float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def gnhwc(x):
+    """(N,C,H,W) fp32 -> (N,H,W,C) GRADIENT tensor (bf16) on the GPU."""
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def gnchw(t):
     return t.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def wbits(w, f16):
+    """2-D GEMM weights for pw_conv: fp16 bit patterns (forward) or bf16 (backward)."""
+    return (w.to(torch.float16).view(torch.bfloat16) if f16 else w.to(torch.bfloat16)).cuda().contiguous()
 
 
 def G(seed):
@@ -47,42 +71,50 @@ def G(seed):
 @pytest.mark.parametrize("shape", [(2, 16, 16, 16, 96), (1, 12, 20, 96, 16), (2, 9, 7, 24, 144),
                                    (1, 16, 16, 240, 40), (2, 8, 8, 256, 768), (2, 8, 8, 768, 128),
                                    (3, 5, 5, 80, 320)])
-def test_pw_conv_forward(shape):
+@pytest.mark.parametrize("f16", [True, False])
+def test_pw_conv_forward(shape, f16):
+    """The pointwise GEMM in both of its roles: fp16 (forward activations) and bf16 (data gradients, attention)."""
     from arbitrarystyletransfer_b200 import mobilenet as MB
     N, H, W, cin, cout = shape
     g = G(sum(shape))
-    x = bf16r(torch.randn(N, cin, H, W, generator=g))
-    w = bf16r(torch.randn(cout, cin, generator=g) / cin ** 0.5)
+    rr, to_dev, back = (f16r, nhwc, nchw) if f16 else (bf16r, gnhwc, gnchw)
+    tol = 1e-3 if f16 else 5e-3
+    x = rr(torch.randn(N, cin, H, W, generator=g))
+    w = rr(torch.randn(cout, cin, generator=g) / cin ** 0.5)
     b = torch.randn(cout, generator=g)
     ref = F.conv2d(x, w.view(cout, cin, 1, 1), b)
-    out = MB.pw_conv(nhwc(x), w.to(torch.bfloat16).cuda(), b.cuda(), 0, cout)
-    assert rel(nchw(out), ref) < 5e-3
-    out = MB.pw_conv(nhwc(x), w.to(torch.bfloat16).cuda(), b.cuda(), 1, cout)
-    assert rel(nchw(out), F.hardswish(ref)) < 5e-3
-    raw, act = MB.pw_conv(nhwc(x), w.to(torch.bfloat16).cuda(), None, 1, cout, want_raw=True)
+    out = MB.pw_conv(to_dev(x), wbits(w, f16), b.cuda(), 0, cout, f16=f16)
+    assert rel(back(out), ref) < tol
+    out = MB.pw_conv(to_dev(x), wbits(w, f16), b.cuda(), 1, cout, f16=f16)
+    assert rel(back(out), F.hardswish(ref)) < tol
+    raw, act = MB.pw_conv(to_dev(x), wbits(w, f16), None, 1, cout, want_raw=True, f16=f16)
     ref0 = F.conv2d(x, w.view(cout, cin, 1, 1))
-    assert rel(nchw(raw), ref0) < 5e-3
-    assert torch.equal(act.float().cpu(), bf16r(F.hardswish(raw.float().cpu())))
+    assert rel(back(raw), ref0) < tol
+    assert torch.equal(back(act), rr(F.hardswish(back(raw))))
 
 
 def test_pw_conv_residual_strided_input_and_per_sample_weights():
     from arbitrarystyletransfer_b200 import mobilenet as MB
     N, H, W, cin, cout = 2, 8, 12, 128, 128
     g = G(5)
-    wide = bf16r(torch.randn(N, 2 * cin, H, W, generator=g))
-    w = bf16r(torch.randn(N, cout, cin, generator=g) / cin ** 0.5)
-    res = bf16r(torch.randn(N, cout, H, W, generator=g))
+    wide = f16r(torch.randn(N, 2 * cin, H, W, generator=g))
+    w = f16r(torch.randn(N, cout, cin, generator=g) / cin ** 0.5)
+    res = f16r(torch.randn(N, cout, H, W, generator=g))
     xw = nhwc(wide)
     x_view = xw[..., cin:]                      # channel slice: row stride 2*cin
     ref = torch.stack([F.conv2d(wide[n:n + 1, cin:], w[n].view(cout, cin, 1, 1))[0] for n in range(N)]) + res
-    out = MB.pw_conv(x_view, w.to(torch.bfloat16).cuda(), None, 0, cout, residual=nhwc(res), per_sample=True)
-    assert rel(nchw(out), ref) < 5e-3
+    out = MB.pw_conv(x_view, wbits(w, True), None, 0, cout, residual=nhwc(res), per_sample=True, f16=True)
+    assert rel(nchw(out), ref) < 1e-3
     # residual read through a nearest x2 upsample
-    small = bf16r(torch.randn(N, cout, H // 2, W // 2, generator=g))
+    small = f16r(torch.randn(N, cout, H // 2, W // 2, generator=g))
     ref = F.conv2d(wide[:, :cin], w[0].view(cout, cin, 1, 1)) + F.interpolate(small, scale_factor=2, mode="nearest")
-    out = MB.pw_conv(xw[..., :cin], w[0].to(torch.bfloat16).cuda().contiguous(), None, 0, cout,
-                     residual=nhwc(small), res_up2=True)
-    assert rel(nchw(out), ref) < 5e-3
+    out = MB.pw_conv(xw[..., :cin], wbits(w[0], True), None, 0, cout, residual=nhwc(small), res_up2=True, f16=True)
+    assert rel(nchw(out), ref) < 1e-3
+    # the same call on bf16 tensors (the role the backward pass uses: data gradient + residual gradient)
+    wide_b, w_b, res_b = bf16r(wide), bf16r(w), bf16r(res)
+    ref = torch.stack([F.conv2d(wide_b[n:n + 1, cin:], w_b[n].view(cout, cin, 1, 1))[0] for n in range(N)]) + res_b
+    out = MB.pw_conv(gnhwc(wide_b)[..., cin:], wbits(w_b, False), None, 0, cout, residual=gnhwc(res_b), per_sample=True)
+    assert rel(gnchw(out), ref) < 5e-3
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 16, 96, 16), (1, 12, 20, 16, 96), (2, 9, 7, 144, 24),
@@ -97,11 +129,19 @@ def test_pw_wgrad_mn_major_gemm(shape):
     b = bf16r(torch.randn(N, cb, H, W, generator=g))
     ref = torch.einsum("nihw,njhw->ij", a.double(), b.double()).float()
     out = torch.zeros(ca, cb, device="cuda")
-    MB._pw_wgrad(nhwc(a), nhwc(b), out, cb, 1)
+    MB._pw_wgrad(gnhwc(a), gnhwc(b), out, cb, 1)
     assert rel(out, ref) < 1e-3
     out_t = torch.zeros(cb, ca, device="cuda")
-    MB._pw_wgrad(nhwc(a), nhwc(b), out_t, 1, ca)
+    MB._pw_wgrad(gnhwc(a), gnhwc(b), out_t, 1, ca)
     assert rel(out_t, ref.t()) < 1e-3
+    # an fp16 ACTIVATION operand is converted to bf16 first (one format per tcgen05 instruction)
+    out_a = torch.zeros(ca, cb, device="cuda")
+    MB._pw_wgrad(nhwc(a), gnhwc(b), out_a, cb, 1, a_is_act=True)      # bf16-representable values survive both ways
+    assert rel(out_a, ref) < 1e-3
+    a16 = f16r(torch.randn(N, ca, H, W, generator=g))
+    out_b = torch.zeros(cb, ca, device="cuda")
+    MB._pw_wgrad(gnhwc(b), nhwc(a16), out_b, ca, 1, b_is_act=True)
+    assert rel(out_b, torch.einsum("nihw,njhw->ji", a16.double(), b.double()).float()) < 4e-3   # one bf16 rounding of a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -124,7 +164,7 @@ def test_dw_conv_forward_dgrad_wgrad(cfg):
     from arbitrarystyletransfer_b200 import mobilenet as MB, _lib as L
     N, C, H, W, k, stride, up2 = cfg
     g = G(sum(int(v) for v in cfg))
-    x = bf16r(torch.randn(N, C, H, W, generator=g)).requires_grad_(True)
+    x = f16r(torch.randn(N, C, H, W, generator=g)).requires_grad_(True)
     w = torch.randn(C, 1, k, k, generator=g).div_(k).requires_grad_(True)
     y = _dw_ref(x, w, k, stride, up2)
     dy = bf16r(torch.randn(y.shape, generator=g))
@@ -132,20 +172,20 @@ def test_dw_conv_forward_dgrad_wgrad(cfg):
     wd = MB.prep_weight(w.detach().cuda(), C, k * k, 2)
     assert torch.equal(wd.cpu(), w.detach().view(C, k * k).t())
     out, pool = MB.dw_conv(nhwc(x.detach()), wd, None, k, stride, up2=up2, act=0, want_pool=True)
-    assert rel(nchw(out), y.detach()) < 5e-3
-    torch.testing.assert_close(pool.cpu(), out.float().sum(dim=(1, 2)).cpu(), rtol=1e-4, atol=1e-3)
+    assert rel(nchw(out), y.detach()) < 1e-3
+    torch.testing.assert_close(pool.cpu(), MB.act_float(out).sum(dim=(1, 2)).cpu(), rtol=1e-4, atol=1e-3)
     out1, pool1 = MB.dw_conv(nhwc(x.detach()), wd, None, k, stride, up2=up2, act=1, want_pool=True)
-    assert rel(nchw(out1), F.hardswish(y.detach())) < 6e-3
+    assert rel(nchw(out1), F.hardswish(y.detach())) < 1.5e-3
     out2, pool2 = MB.dw_conv(nhwc(x.detach()), wd, None, k, stride, up2=up2, act=2, want_pool=True)
     assert torch.equal(out2, out)
-    torch.testing.assert_close(pool2.cpu(), F.hardswish(out.float()).sum(dim=(1, 2)).cpu(), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(pool2.cpu(), F.hardswish(MB.act_float(out)).sum(dim=(1, 2)).cpu(), rtol=1e-4, atol=1e-3)
     lib = L.load()
     st = L.stream_ptr(out.device)
-    dyd = nhwc(dy)
+    dyd = gnhwc(dy)
     dx = torch.empty(N, H, W, C, device="cuda", dtype=torch.bfloat16)
     L.check(lib.ast_dw_conv_dgrad(dyd.data_ptr(), wd.data_ptr(), None, None, None, dx.data_ptr(), N, C, H, W, k,
                                   stride, int(up2), st))
-    assert rel(nchw(dx), x.grad) < 5e-3
+    assert rel(gnchw(dx), x.grad) < 5e-3
     dw = torch.zeros(C, 1, k, k, device="cuda")
     L.check(lib.ast_dw_conv_wgrad(dyd.data_ptr(), nhwc(x.detach()).data_ptr(), dw.data_ptr(), N, C, H, W, k, stride,
                                   int(up2), st))
@@ -155,7 +195,7 @@ def test_dw_conv_forward_dgrad_wgrad(cfg):
         L.check(lib.ast_dw_conv_dgrad(dyd.data_ptr(), wd.data_ptr(), None, None, dyd.data_ptr(), dx2.data_ptr(), N, C,
                                       H, W, k, stride, int(up2), st))
         extra = F.avg_pool2d(dy, 2) * 4 if up2 else dy
-        assert rel(nchw(dx2), x.grad + extra) < 5e-3
+        assert rel(gnchw(dx2), x.grad + extra) < 5e-3
 
 
 # ------------------------------------------------------------------------------------------------
@@ -166,7 +206,7 @@ def test_batchnorm_train_forward_backward(shape):
     from arbitrarystyletransfer_b200 import mobilenet as MB
     N, C, H, W = shape
     g = G(sum(shape))
-    a = bf16r(torch.randn(N, C, H, W, generator=g) * 2 + torch.randn(1, C, 1, 1, generator=g)).requires_grad_(True)
+    a = f16r(torch.randn(N, C, H, W, generator=g) * 2 + torch.randn(1, C, 1, 1, generator=g)).requires_grad_(True)
     bn = torch.nn.BatchNorm2d(C)
     with torch.no_grad():
         bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
@@ -179,12 +219,12 @@ def test_batchnorm_train_forward_backward(shape):
     ad = nhwc(a.detach())
     stat = MB._bn_train_forward(ad, bn_g)
     yg, _ = MB.affine_act(ad, stat[2], stat[3], 0)
-    assert rel(nchw(yg), y.detach()) < 5e-3
+    assert rel(nchw(yg), y.detach()) < 1e-3
     torch.testing.assert_close(bn_g.running_mean.cpu(), bn.running_mean, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(bn_g.running_var.cpu(), bn.running_var, rtol=1e-4, atol=1e-5)
     assert int(bn_g.num_batches_tracked) == 1
-    da, dgamma, dbeta = MB._bn_backward(nhwc(dy), ad, stat)
-    assert rel(nchw(da), a.grad) < 6e-3
+    da, dgamma, dbeta = MB._bn_backward(gnhwc(dy), ad, stat)
+    assert rel(gnchw(da), a.grad) < 6e-3
     assert rel(dgamma, bn.weight.grad) < 1e-3 and rel(dbeta, bn.bias.grad) < 1e-3
 
 
@@ -195,7 +235,7 @@ def test_se_hardswish_norm_backward_chain(norm):
     from arbitrarystyletransfer_b200 import mobilenet as MB, _lib as L
     N, C, H, W, S = 3, 96, 8, 8, 24
     g = G(7 + norm)
-    a = bf16r(torch.randn(N, C, H, W, generator=g) * 2).requires_grad_(True)
+    a = f16r(torch.randn(N, C, H, W, generator=g) * 2).requires_grad_(True)
     w1 = (torch.randn(S, C, generator=g) * 0.3).requires_grad_(True)
     b1 = (torch.randn(S, generator=g) * 0.1).requires_grad_(True)
     w2 = (torch.randn(C, S, generator=g) * 0.3).requires_grad_(True)
@@ -229,8 +269,8 @@ def test_se_hardswish_norm_backward_chain(norm):
     s_g, hid, pre = MB.se_fc(pool_g, 1.0 / (H * W), *cw, save=True)
     torch.testing.assert_close(s_g.cpu(), s.detach(), rtol=2e-3, atol=2e-3)
     u_g, _ = MB.affine_act(ad, sc, sh, 1, se=s_g)
-    assert rel(nchw(u_g), u.detach()) < 6e-3
-    dud = nhwc(du)
+    assert rel(nchw(u_g), u.detach()) < 2e-3
+    dud = gnhwc(du)
     T = torch.empty(N, 5, C, device="cuda")
     L.check(lib.ast_dw_bwd_reduce(dud.data_ptr(), ad.data_ptr(), L.ptr(stat), T.data_ptr(), N, C, H * W, st))
     dpre, dhid, gg = torch.empty(N, C, device="cuda"), torch.empty(N, S, device="cuda"), torch.empty(N, C, device="cuda")
@@ -252,7 +292,7 @@ def test_se_hardswish_norm_backward_chain(norm):
     da = torch.empty_like(ad)
     L.check(lib.ast_dw_bwd_apply(dud.data_ptr(), ad.data_ptr(), s_g.data_ptr(), gg.data_ptr(), L.ptr(stat),
                                  L.ptr(coef), da.data_ptr(), N, C, H * W, st))
-    assert rel(nchw(da), a.grad) < 1e-2, rel(nchw(da), a.grad)
+    assert rel(gnchw(da), a.grad) < 1e-2, rel(gnchw(da), a.grad)
 
 
 def test_stem_and_head_forward_backward():
@@ -266,11 +306,11 @@ def test_stem_and_head_forward_backward():
     y.backward(dy)
     wg = w.detach().cuda().requires_grad_(True)
     yg = MB._StemFn.apply(img.cuda(), wg)
-    assert rel(nchw(yg), y.detach()) < 5e-3
-    yg.backward(nhwc(dy))
+    assert rel(nchw(yg), y.detach()) < 1e-3
+    yg.backward(gnhwc(dy))
     assert rel(wg.grad, w.grad) < 1e-2
     # head: ReflectionPad2d(1) + Conv2d(16, 3, 3) with bias
-    x = bf16r(torch.randn(N, 16, H, W, generator=g)).requires_grad_(True)
+    x = f16r(torch.randn(N, 16, H, W, generator=g)).requires_grad_(True)
     hw = (torch.randn(3, 16, 3, 3, generator=g) * 0.2).requires_grad_(True)
     hb = torch.randn(3, generator=g).requires_grad_(True)
     out = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), hw, hb)
@@ -282,8 +322,11 @@ def test_stem_and_head_forward_backward():
     assert rel(og, out.detach()) < 1e-4
     og.backward(dY.cuda())
     assert rel(hwg.grad, hw.grad) < 1e-4 and rel(hbg.grad, hb.grad) < 1e-4
-    assert rel(nchw(xg.grad), x.grad) < 5e-3
+    assert rel(gnchw(xg.grad), x.grad) < 5e-3
     assert rel(MB.nhwc_to_nchw(MB.nchw_to_nhwc(out.detach().cuda())), bf16r(out.detach())) == 0.0
+    assert rel(MB.to_nchw(MB.to_nhwc(out.detach().cuda())), f16r(out.detach())) == 0.0
+    big = torch.tensor([1e6, -1e6, 65504.0, 70000.0]).view(1, 4, 1, 1).expand(1, 4, 2, 2).contiguous()
+    assert torch.equal(MB.to_nchw(MB.to_nhwc(big.cuda())).cpu(), big.clamp(-65504, 65504))   # saturates, never inf
 
 
 # ------------------------------------------------------------------------------------------------
@@ -324,7 +367,7 @@ def test_block_train_forward_backward_vs_oracle(cfg):
     sd = _block_state(blk)
     P = A.clone_state(sd, requires_grad=True)
     N = 3
-    x = bf16r(torch.randn(N, inp, H, W, generator=G(3))).requires_grad_(True)
+    x = f16r(torch.randn(N, inp, H, W, generator=G(3))).requires_grad_(True)
     xin = F.interpolate(x, scale_factor=2, mode="nearest") if up2 else x
     ref = A.depthwise_block(P, "b", xin, inp, oup, stride, t, k, norm=norm, use_identity=ident, training=True)
     dy = bf16r(torch.randn(ref.shape, generator=G(4)))
@@ -333,9 +376,9 @@ def test_block_train_forward_backward_vs_oracle(cfg):
     blk = blk.cuda().train()
     xg = nhwc(x.detach()).requires_grad_(True)
     out = blk.forward_nhwc(xg, up2=up2)
-    assert rel(nchw(out), ref.detach()) < 1.5e-2, rel(nchw(out), ref.detach())
-    out.backward(nhwc(dy))
-    assert rel(nchw(xg.grad), x.grad) < 3e-2, rel(nchw(xg.grad), x.grad)
+    assert rel(nchw(out), ref.detach()) < 3e-3, rel(nchw(out), ref.detach())
+    out.backward(gnhwc(dy))
+    assert rel(gnchw(xg.grad), x.grad) < 2e-2, rel(gnchw(xg.grad), x.grad)
     # Hardswish' jumps by 1/2 at +-3; a pre-activation within bf16 rounding of a kink (a few elements per
     # ten thousand) takes the other branch than the fp32 oracle and moves the BatchNorm gamma / beta gradient
     # of ITS channel by ~20 % when only ~150 elements feed that channel, as in these small cases.  Those two
@@ -369,19 +412,64 @@ def ae():
     return MB.AutoEncoder().cuda()
 
 
-def test_autoencoder_eval_forward_vs_reference_golden(g, ae):
+@pytest.fixture()
+def act_format():
+    """set the process-wide activation format for one test and restore the default (fp16) afterwards"""
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+
+    def use(fmt):
+        MB.set_activation_format(fmt)
+    yield use
+    MB.set_activation_format("fp16")
+
+
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+def test_autoencoder_eval_forward_vs_reference_golden(g, ae, act_format, fmt):
+    """The reference's FRESH initialisation in eval mode: closed SE gates and fresh running statistics shrink the
+    activations by ~1e-4 per block (1e-8 after two blocks), the image is exactly the head bias.  bf16 activations
+    (fp32's exponent range) follow the fp32 reference all the way down; fp16 activations bottom out at their subnormal
+    quantum 2^-24 = 6e-8, i.e. they are exact to that ABSOLUTE error -- the documented price of the 11-bit
+    significand (mobilenet.set_activation_format)."""
+    act_format(fmt)
     x = T(g["ae_x"]).cuda()
     ae.eval()
     with torch.no_grad():
         recon = ae(x)
         taps = ae.encoder(x, out_layers=[0, 2, 12, 14])
         z = ae.encoder(x, auto_enc=True)
-    for i, t in zip((0, 2, 12, 14), taps):
-        assert rel(t, T(g[f"ae_eval_enc{i}"])) < 3e-2, (i, rel(t, T(g[f"ae_eval_enc{i}"])))
-    assert rel(z, T(g["ae_eval_autoenc"])) < 3e-2
+    for i, t in list(zip((0, 2, 12, 14), taps)) + [("z", z)]:
+        ref = T(g[f"ae_eval_enc{i}"]) if i != "z" else T(g["ae_eval_autoenc"])
+        if fmt == "bf16":
+            assert rel(t, ref) < 3e-2, (i, rel(t, ref))
+        else:
+            err = (t.cpu() - ref).abs().max().item()
+            assert err <= max(2e-3 * ref.abs().max().item(), 2.0 ** -24), (i, err, ref.abs().max().item())
     ref = T(g["ae_eval_recon_fresh"])
-    assert rel(recon, ref) < 3e-2, rel(recon, ref)
+    assert rel(recon, ref) < (3e-2 if fmt == "bf16" else 1e-5), rel(recon, ref)
     assert R.psnr(recon.cpu(), ref) >= 40.0
+
+
+def test_bf16_activation_format_train_step(act_format):
+    """The bf16 activation format (range over precision) still runs the whole training path: one Huber step on the
+    non-degenerate state against the oracle, at the looser bars that format earns (round-1 numbers)."""
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    act_format("bf16")
+    assert MB.activation_format() == "bf16"
+    sd = A.activate_gates(A.make_ae_state(2))
+    torch.manual_seed(2)
+    net = MB.AutoEncoder().cuda().train()
+    net.load_state_dict(sd, strict=True)
+    x = R.rand_image(2, 64, 301)
+    loss = F.huber_loss(net(x.cuda()), x.cuda())
+    loss.backward()
+    P = A.clone_state(sd, requires_grad=True)
+    ref_loss = F.huber_loss(A.autoencoder_forward(P, x, training=True), x)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    named = dict(net.named_parameters())
+    for k in ("decoder._img_out.weight", "ada_out._layers.0.weight", "encoder.mob_net.4._layers.3.weight",
+              "encoder.mob_net.0.0.weight"):
+        assert cos(named[k].grad, P[k].grad) > 0.95, (k, cos(named[k].grad, P[k].grad))
 
 
 def test_autoencoder_train_step_vs_reference_golden(g, ae):
@@ -466,11 +554,11 @@ def test_autoencoder_non_degenerate_state_vs_reference_golden(g, ae):
     recon = ae(x)
     want = T(g["act_train_recon"])
     # Train mode at this fixture size (2 x 32 x 32: 32 samples per channel at the deepest BatchNorms) amplifies
-    # rounding: the relative error of the block outputs grows steadily from 0.7 % after block 1 to 9.4 % after
-    # encoder block 14 and stays flat through the decoder; the fp32 oracle with ONLY its block outputs rounded to
-    # bf16 shows the same curve at 1/2.7 (it rounds once per block, the kernels five times), with no jump at any
-    # block (tools/dbg_ae_stages.py, profiles/r1_ae_error_growth.txt).  Hence 0.2 here, tight bars in eval mode.
-    assert rel(_signal(recon.detach(), bias), _signal(want, bias)) < 0.2, rel(_signal(recon.detach(), bias), _signal(want, bias))
+    # rounding.  With the round-1 bf16 activations the decoder signal sat 11 % from the reference (error growing
+    # steadily through the 14 encoder blocks, profiles/r1_ae_error_growth.txt); with fp16 activations it is 1.3 %.
+    sig = rel(_signal(recon.detach(), bias), _signal(want, bias))
+    print(f"train-mode decoder signal rel L2 vs the reference: {sig:.3e}")
+    assert sig < 2.5e-2, sig
     recon_loss = compute_content_loss(recon, x)
     with torch.no_grad():
         cm = enc(x)
@@ -493,9 +581,9 @@ def test_autoencoder_non_degenerate_state_vs_reference_golden(g, ae):
     gkeys = list(np.array(gkeys)[big])
     report = [(k, round(cos(named[k].grad, T(g["act_grad::" + k])), 4)) for k in A.GOLDEN_GRAD_KEYS]
     print("gradient-norm ratio min/median/max:", ratio.min(), np.median(ratio), ratio.max(), "cosines:", report)
-    assert np.all(np.abs(ratio - 1) < 0.35), (np.array(gkeys)[np.abs(ratio - 1) >= 0.35], ratio[np.abs(ratio - 1) >= 0.35])
-    assert abs(np.median(ratio) - 1) < 0.05
-    assert min(c for _, c in report) > 0.95, report
+    assert np.all(np.abs(ratio - 1) < 0.05), (np.array(gkeys)[np.abs(ratio - 1) >= 0.05], ratio[np.abs(ratio - 1) >= 0.05])
+    assert abs(np.median(ratio) - 1) < 0.01
+    assert min(c for _, c in report) > 0.995, report
     sd = ae.state_dict()
     for k in A.GOLDEN_BUFFER_KEYS:
         torch.testing.assert_close(sd[k].cpu().float(), T(g["act_buf::" + k]).float(), rtol=3e-2, atol=3e-3)
@@ -513,26 +601,26 @@ def test_autoencoder_non_degenerate_state_vs_reference_golden(g, ae):
     errs["decoder(code)"] = rel(_signal(img, bias), _signal(T(g["act_eval_dec_of_code"]), bias))
     errs["recon"] = rel(_signal(rec, bias), _signal(T(g["act_eval_recon"]), bias))
     print("eval-mode relative L2 errors:", {k: round(v, 4) for k, v in errs.items()})
-    # same accumulation as in train mode (3-4 bf16 roundings per block, 14 blocks in series): shallow taps are
-    # tight, the deepest features reach ~8 %; the decoder alone (fed the exact code) is held separately
-    assert errs["enc0"] < 5e-3 and errs["enc2"] < 2e-2, errs
-    assert max(errs["enc12"], errs["enc14"], errs["code"]) < 0.15, errs
-    assert errs["decoder(code)"] < 0.1 and errs["recon"] < 0.2, errs
+    # ~150 fp16 roundings in series: shallow taps at 1e-3, the deepest 4x4 features at 1 %; the decoder alone (fed the
+    # exact code) is held separately
+    assert errs["enc0"] < 1e-3 and errs["enc2"] < 3e-3, errs
+    assert max(errs["enc12"], errs["enc14"], errs["code"]) < 2e-2, errs
+    assert errs["decoder(code)"] < 5e-3 and errs["recon"] < 2e-2, errs
     assert R.psnr(rec.cpu(), T(g["act_eval_recon"])) >= 40.0
     # The kernels against THEIR OWN arithmetic contract (oracle/restate_ae.py::autoencoder_forward_bf16: fp32 math,
     # bf16 rounding at exactly the kernels' storage points).  The contract itself sits 0.16 % / 0.87 % / 8.1 % /
     # 10.1 % from the fp32 reference at enc0 / enc2 / enc12 / enc14 on this state -- the same curve as measured
     # above -- so that distance is the price of bf16 storage, not of the kernels.
     with torch.no_grad():
-        cimg, keep = A.autoencoder_forward_bf16(Q, x.cpu(), want=("enc0", "enc2", "enc12", "enc14", "code"))
+        cimg, keep = A.autoencoder_forward_contract(Q, x.cpu(), want=("enc0", "enc2", "enc12", "enc14", "code"))
     cerr = {k: rel(t, keep[k]) for k, t in zip(("enc0", "enc2", "enc12", "enc14"), taps)}
     cerr["code"] = rel(z, keep["code"])
     cerr["recon"] = rel(_signal(rec, bias), _signal(cimg, bias))
     print("relative L2 vs the bf16 storage contract:", {k: round(v, 4) for k, v in cerr.items()})
-    assert cerr["enc0"] < 1e-3 and cerr["enc2"] < 5e-3, cerr
+    assert cerr["enc0"] < 2e-4 and cerr["enc2"] < 1e-3, cerr
     # deep features: two bf16 pipelines that differ in fp32 summation order (atomics, MMA tree) drift apart at
     # the same rate as either drifts from fp32 (measured 3-4.5 % at the 4x4 maps)
-    assert max(cerr.values()) < 8e-2, cerr
+    assert max(cerr.values()) < 1.2e-2, cerr
 
 
 @pytest.mark.parametrize("hw", [(40, 24), (72, 56), (24, 88)])
@@ -549,12 +637,12 @@ def test_autoencoder_ragged_sizes_vs_contract(ae, hw):
     ae.eval()
     with torch.no_grad():
         rec = ae(x.cuda())
-        cimg, _ = A.autoencoder_forward_bf16(Q, x)
+        cimg, _ = A.autoencoder_forward_contract(Q, x)
         ref = A.autoencoder_forward(Q, x)
     assert rec.shape == ref.shape and torch.isfinite(rec).all()
     e_contract, e_fp32 = rel(_signal(rec, bias), _signal(cimg, bias)), rel(_signal(rec, bias), _signal(ref, bias))
     print(f"ragged {H}x{W}: image signal vs contract {e_contract:.4f}, vs fp32 {e_fp32:.4f}")
-    assert e_contract < 0.1 and e_fp32 < 0.2 and R.psnr(rec.cpu(), ref) >= 40.0, (e_contract, e_fp32)
+    assert e_contract < 1.5e-2 and e_fp32 < 2.5e-2 and R.psnr(rec.cpu(), ref) >= 40.0, (e_contract, e_fp32)
     # train mode: loss and a few gradients against the oracle's autograd
     ae.load_state_dict(act, strict=True)
     ae.train()
@@ -569,7 +657,7 @@ def test_autoencoder_ragged_sizes_vs_contract(ae, hw):
               "decoder._decoder_blocks.4._upsample_2._layers.1.weight", "ada_out._layers.0.weight",
               "encoder.mob_net.7._layers.3.weight", "encoder.mob_net.2._layers.0.weight", "encoder.mob_net.0.0.weight"):
         c = cos(named[k].grad, P[k].grad)
-        assert c > 0.95, (k, c)
+        assert c > 0.99, (k, c)
 
 
 def test_autoencoder_too_small_input_raises_like_the_reference(ae):
@@ -623,10 +711,10 @@ def _sub(t):
 
 
 # bars for the whole-network comparisons at 256 x 256 (relative L2 unless noted); see DESIGN.md section 5
-AE256_TAP_BAR = 6e-2          # every encoder tap, the code and the decoder signal, eval mode
-AE256_TRAIN_BAR = 9e-2        # decoder signal of the train-mode forward (batch statistics)
-AE256_GRAD_COS = 0.97         # cosine of every GOLDEN_GRAD_KEYS gradient
-AE256_NORM_BAND = 0.25        # |gradient-norm ratio - 1| over all non-negligible parameters
+AE256_TAP_BAR = 2e-2          # every encoder tap, the code and the decoder signal, eval mode
+AE256_TRAIN_BAR = 2e-2        # decoder signal of the train-mode forward (batch statistics)
+AE256_GRAD_COS = 0.993        # cosine of every GOLDEN_GRAD_KEYS gradient
+AE256_NORM_BAND = 0.07        # |gradient-norm ratio - 1| over all non-negligible parameters
 
 
 def test_autoencoder_256_eval_vs_reference_golden(golden_ae256, ae):
