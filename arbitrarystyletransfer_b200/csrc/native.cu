@@ -174,8 +174,11 @@ __global__ void __launch_bounds__(256) nchw_to_u8hwc_kernel(const float* __restr
 constexpr int kNThreads = 256;
 constexpr int kMaxChunks = 32;
 
-// Stage 1: per (map q, image n, pixel chunk) Welford moments of every channel.
-// grid = (chunks, N, 1 + K); thread -> 8 consecutive channels of one pixel group.
+// Stage 1: per (map q, image n, pixel chunk) moments of every channel.
+// grid = (chunks, N, 1 + K); thread -> 8 consecutive channels of one pixel group.  Per-channel SHIFTED sums
+// (d = x - x_first, sum d and sum d^2 with packed FADD2 / FFMA2: 1.5 instructions per element; the streaming Welford
+// update this replaces made the kernel issue-bound at 69 % issue-slot utilisation and 40 % of the DRAM rate), pixel
+// coordinates advanced by carries (no 64-bit divisions in the loop), four pixels' loads in flight per thread.
 struct NativeStatArgs {
   const __nv_bfloat16* maps[1 + AST_MAX_STYLES];
   int H[1 + AST_MAX_STYLES], W[1 + AST_MAX_STYLES];
@@ -190,42 +193,63 @@ __global__ void __launch_bounds__(kNThreads) native_stats_kernel(const NativeSta
   const int groups = kNThreads / cvecs;
   const int g = threadIdx.x / cvecs, v = threadIdx.x % cvecs;
   const int H = a.H[q], W = a.W[q];
-  const int64_t npix = (int64_t)H * W;
-  const int64_t per = (npix + a.chunks - 1) / a.chunks;
-  const int64_t p0 = chunk * per, p1 = (p0 + per < npix) ? p0 + per : npix;
-  WelfordLanes<8> wl;
-  wl.init();
-  if (g < groups) {
-    const __nv_bfloat16* base = a.maps[q] + (int64_t)n * (H + 2) * (W + 2) * a.C + v * 8;
-    // four pixels' loads in flight per thread: one load per Welford update left the loop a chain of exposed
-    // HBM latencies (1.8 TB/s)
-    int64_t p = p0 + g;
-    for (; p + 3 * groups < p1; p += 4 * groups) {
-      uint4 u[4];
+  const int npix = H * W;
+  const int per = (npix + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = (p0 + per < npix) ? p0 + per : npix;
+  float cnt = 0.f;
+  float2 sh[4], sm[4], sq[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t pj = p + (int64_t)j * groups;
-        const int h = (int)(pj / W), w = (int)(pj % W);
-        u[j] = ld_stream_u4(base + ((int64_t)(h + 1) * (W + 2) + (w + 1)) * a.C);
-      }
+  for (int j = 0; j < 4; ++j) { sh[j] = sm[j] = sq[j] = make_float2(0.f, 0.f); }
+  if (g < groups && p0 + g < p1) {
+    const __nv_bfloat16* base = a.maps[q] + ((int64_t)n * (H + 2) + 1) * (W + 2) * a.C + a.C + v * 8;   // pixel (0,0)
+    const int row = (W + 2) * a.C;                    // elements per padded row
+    int p = p0 + g;
+    int h = p / W, w = p - h * W;
+    const int dh = groups / W, dw = groups - dh * W;  // one pixel-group step in (h, w)
+    {
+      float x0[8];
+      Vec16<true>::unpack(ld_stream_u4(base + (int64_t)h * row + w * a.C), x0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float x[8];
-        Vec16<true>::unpack(u[j], x);
-        wl.push(x);
-      }
+      for (int j = 0; j < 4; ++j) sh[j] = make_float2(-x0[2 * j], -x0[2 * j + 1]);
     }
-    for (; p < p1; p += groups) {
-      const int h = (int)(p / W), w = (int)(p % W);
-      const uint4 u = ld_stream_u4(base + ((int64_t)(h + 1) * (W + 2) + (w + 1)) * a.C);
+    auto acc = [&](const uint4& u) {
       float x[8];
       Vec16<true>::unpack(u, x);
-      wl.push(x);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 d = __fadd2_rn(make_float2(x[2 * j], x[2 * j + 1]), sh[j]);
+        sm[j] = __fadd2_rn(sm[j], d);
+        sq[j] = __ffma2_rn(d, d, sq[j]);
+      }
+      cnt += 1.f;
+    };
+    auto step = [&]() {
+      p += groups; w += dw; h += dh;
+      if (w >= W) { w -= W; ++h; }
+    };
+    while (p + 3 * groups < p1) {
+      uint4 u[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        u[jj] = ld_stream_u4(base + (int64_t)h * row + w * a.C);
+        step();
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc(u[jj]);
     }
+    while (p < p1) {
+      acc(ld_stream_u4(base + (int64_t)h * row + w * a.C));
+      step();
+    }
+  }
+  if (g < groups) {
+    const float rn = cnt > 0.f ? 1.f / cnt : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      const float sj = (j & 1) ? sm[j >> 1].y : sm[j >> 1].x, qj = (j & 1) ? sq[j >> 1].y : sq[j >> 1].x;
+      const float shj = (j & 1) ? sh[j >> 1].y : sh[j >> 1].x;
       float* sp = s_part + ((int64_t)g * a.C + v * 8 + j) * 3;
-      sp[0] = wl.n; sp[1] = wl.mean[j]; sp[2] = wl.m2[j];
+      sp[0] = cnt; sp[1] = sj * rn - shj; sp[2] = fmaxf(fmaf(-sj, sj * rn, qj), 0.f);
     }
   }
   __syncthreads();
@@ -241,6 +265,10 @@ __global__ void __launch_bounds__(kNThreads) native_stats_kernel(const NativeSta
 }
 
 // Stage 2: merge chunks, build the per-(n,c) affine (mu_c, 1/sigma_c, A, B).
+// grid = (C / kCoefCh, N); a CTA of kCoefCh x 32 threads: thread (ch lane, channel) loads the partial of one chunk
+// and the 32 chunk lanes are merged by a fixed-order tree in shared memory (deterministic).  The serial loop over
+// (1 + K) x 32 partials per thread this replaces took 40 us on 64 CTAs -- as long as the statistics pass itself.
+constexpr int kCoefCh = 32;
 struct NativeCoefArgs {
   const float* partial;
   float4* coef;  // [N][C]
@@ -250,36 +278,50 @@ struct NativeCoefArgs {
   unsigned flags;
 };
 
-__global__ void __launch_bounds__(kNThreads) native_coef_kernel(const NativeCoefArgs a) {
+__global__ void __launch_bounds__(kCoefCh * kMaxChunks) native_coef_kernel(const NativeCoefArgs a) {
+  __shared__ float s_m[kMaxChunks][kCoefCh][3];
   const int n = blockIdx.y;
-  const int c = blockIdx.x * kNThreads + threadIdx.x;
-  if (c >= a.C) return;
+  const int cl = threadIdx.x % kCoefCh, ch = threadIdx.x / kCoefCh;
+  const int c = blockIdx.x * kCoefCh + cl;
   float mu = 0.f, rsig = 0.f, A = 0.f, B = 0.f;
   for (int q = 0; q <= a.K; ++q) {
     Moments m{0.f, 0.f, 0.f};
-    for (int ch = 0; ch < a.chunks; ++ch) {
+    if (ch < a.chunks && c < a.C) {
       const float* pp = a.partial + ((((int64_t)q * a.N + n) * a.chunks + ch) * a.C + c) * 3;
-      m = moments_merge(m, Moments{pp[0], pp[1], pp[2]});
+      m = Moments{pp[0], pp[1], pp[2]};
     }
-    const float denom = (a.flags & AST_F_BIASED) ? m.n : m.n - 1.f;
-    const float sig = sqrtf(m.m2 / denom + a.eps);
-    if (q == 0) {
-      mu = m.mean;
-      rsig = 1.f / sig;
-    } else if (a.flags & AST_F_CANONICAL) {
-      A = fmaf(a.style_w[q - 1], sig, A);
-      B = fmaf(a.style_w[q - 1], m.mean, B);
-    } else {  // models.py:44: style_std := mean(style), style_mean := std(style)
-      A = fmaf(a.style_w[q - 1], m.mean, A);
-      B = fmaf(a.style_w[q - 1], sig, B);
+    __syncthreads();
+    s_m[ch][cl][0] = m.n; s_m[ch][cl][1] = m.mean; s_m[ch][cl][2] = m.m2;
+    __syncthreads();
+    for (int off = kMaxChunks / 2; off > 0; off >>= 1) {
+      if (ch < off) {
+        const Moments o{s_m[ch + off][cl][0], s_m[ch + off][cl][1], s_m[ch + off][cl][2]};
+        m = moments_merge(m, o);
+        s_m[ch][cl][0] = m.n; s_m[ch][cl][1] = m.mean; s_m[ch][cl][2] = m.m2;
+      }
+      __syncthreads();
+    }
+    if (ch == 0) {
+      const float denom = (a.flags & AST_F_BIASED) ? m.n : m.n - 1.f;
+      const float sig = sqrtf(m.m2 / denom + a.eps);
+      if (q == 0) {
+        mu = m.mean;
+        rsig = 1.f / sig;
+      } else if (a.flags & AST_F_CANONICAL) {
+        A = fmaf(a.style_w[q - 1], sig, A);
+        B = fmaf(a.style_w[q - 1], m.mean, B);
+      } else {  // models.py:44: style_std := mean(style), style_mean := std(style)
+        A = fmaf(a.style_w[q - 1], m.mean, A);
+        B = fmaf(a.style_w[q - 1], sig, B);
+      }
     }
   }
-  a.coef[(int64_t)n * a.C + c] = make_float4(mu, rsig, A, B);
+  if (ch == 0 && c < a.C) a.coef[(int64_t)n * a.C + c] = make_float4(mu, rsig, A, B);
 }
 
 // Stage 3: apply + alpha blend, write interior and (optionally) the reflection halo.
 // grid = (pixel chunks, N); a thread owns 8 consecutive channels (its 8 coefficient quadruples stay
-// in registers) and walks the pixels of its chunk: one 16-byte load and store per pixel.
+// in registers) and walks the pixels of its chunk: one 16-byte load and store per pixel, coordinates by carries.
 __global__ void __launch_bounds__(kNThreads)
 native_apply_kernel(const __nv_bfloat16* __restrict__ content, const float4* __restrict__ coef,
                     __nv_bfloat16* __restrict__ out, int N, int C, int H, int W, float alpha,
@@ -290,47 +332,54 @@ native_apply_kernel(const __nv_bfloat16* __restrict__ content, const float4* __r
   if (g >= groups) return;
   const int n = blockIdx.y;
   const bool blend = alpha != 1.f;
-  float4 k[8];
+  // y = (x - mu) * rsig * A + B, blended: y' = alpha * y + (1 - alpha) * x  ==  x * ka + kb
+  float ka[8], kb[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) k[j] = __ldg(coef + (int64_t)n * C + v * 8 + j);
-  const int64_t npix = (int64_t)H * W;
-  const int64_t per = (npix + chunks - 1) / chunks;
-  const int64_t p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
-  const int64_t img = (int64_t)n * (H + 2) * (W + 2);
-  for (int64_t pb = p0 + g; pb < p1; pb += 4 * groups) {
-   // four pixels per iteration: their loads are issued before the first one is used
-   uint4 ub[4];
+  for (int j = 0; j < 8; ++j) {
+    const float4 k = __ldg(coef + (int64_t)n * C + v * 8 + j);
+    const float sc = k.y * k.z;                       // rsig * A            (models.py:47, 50)
+    const float of = fmaf(-k.x, sc, k.w);             // B - mu * rsig * A
+    ka[j] = blend ? fmaf(alpha, sc, 1.f - alpha) : sc;    // models.py:471
+    kb[j] = blend ? alpha * of : of;
+  }
+  const int npix = H * W;
+  const int per = (npix + chunks - 1) / chunks;
+  const int p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
+  if (p0 + g >= p1) return;
+  const int row = (W + 2) * C;
+  const int64_t img0 = ((int64_t)n * (H + 2) + 1) * row + C + v * 8;      // pixel (0,0), this thread's channels
+  int p = p0 + g;
+  int h = p / W, w = p - h * W;
+  const int dh = groups / W, dw = groups - dh * W;
+  while (p < p1) {
+    // up to four pixels per iteration: their loads are issued before the first one is used
+    uint4 ub[4];
+    int hh[4], ww[4], cnt = 0;
 #pragma unroll
-   for (int jj = 0; jj < 4; ++jj) {
-     const int64_t pj = pb + (int64_t)jj * groups;
-     if (pj < p1) {
-       const int h = (int)(pj / W), w = (int)(pj % W);
-       ub[jj] = ld_stream_u4(content + ((img + (int64_t)(h + 1) * (W + 2) + (w + 1)) * C + v * 8));
-     }
-   }
-#pragma unroll
-   for (int jj = 0; jj < 4; ++jj) {
-    const int64_t p = pb + (int64_t)jj * groups;
-    if (p >= p1) break;
-    const int h = (int)(p / W), w = (int)(p % W);
-    const uint4 u = ub[jj];
-    float x[8];
-    Vec16<true>::unpack(u, x);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = (x[j] - k[j].x) * k[j].y;   // models.py:47
-      float y = fmaf(t, k[j].z, k[j].w);          // models.py:50
-      if (blend) y = fmaf(alpha, y, (1.f - alpha) * x[j]);  // models.py:471
-      x[j] = y;
+    for (int jj = 0; jj < 4; ++jj) {
+      if (p < p1) {
+        hh[jj] = h; ww[jj] = w;
+        ub[jj] = ld_stream_u4(content + img0 + (int64_t)h * row + w * C);
+        ++cnt;
+        p += groups; w += dw; h += dh;
+        if (w >= W) { w -= W; ++h; }
+      }
     }
-    const uint4 o = Vec16<true>::pack(x);
-    int rows[3], cols[3];
-    const int nr = halo_targets(h, H, reflect != 0, rows);
-    const int nc = halo_targets(w, W, reflect != 0, cols);
-    for (int ri = 0; ri < nr; ++ri)
-      for (int ci = 0; ci < nc; ++ci)
-        *reinterpret_cast<uint4*>(out + ((img + (int64_t)(rows[ri] + 1) * (W + 2) + (cols[ci] + 1)) * C + v * 8)) = o;
-   }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      if (jj >= cnt) break;
+      float x[8];
+      Vec16<true>::unpack(ub[jj], x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], ka[j], kb[j]);
+      const uint4 o = Vec16<true>::pack(x);
+      int rows[3], cols[3];
+      const int nr = halo_targets(hh[jj], H, reflect != 0, rows);
+      const int nc = halo_targets(ww[jj], W, reflect != 0, cols);
+      for (int ri = 0; ri < nr; ++ri)
+        for (int ci = 0; ci < nc; ++ci)
+          *reinterpret_cast<uint4*>(out + img0 + (int64_t)rows[ri] * row + cols[ci] * C) = o;
+    }
   }
 }
 
@@ -434,7 +483,7 @@ extern "C" int ast_adain_native_fwd(const void* content, const void* const* styl
   if (halo == AST_HALO_REFLECT && (H < 2 || W < 2)) return AST_E_SHAPE;
   if (ws_bytes < ast_adain_native_ws_bytes(N, C, K)) return AST_E_WORKSPACE;
   if (!aligned16(content) || !aligned16(out) || !aligned16(ws)) return AST_E_ALIGN;
-  if (N > 65535) return AST_E_SHAPE;
+  if (N > 65535 || (int64_t)H * W >= 0x7fffffffLL) return AST_E_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   int64_t hw_min = (int64_t)H * W;
   for (int k = 0; k < K; ++k) {
@@ -465,7 +514,7 @@ extern "C" int ast_adain_native_fwd(const void* content, const void* const* styl
   ca.partial = partial; ca.coef = coef; ca.N = N; ca.C = C; ca.chunks = chunks; ca.K = K;
   ca.eps = eps; ca.flags = flags;
   for (int k = 0; k < K; ++k) ca.style_w[k] = style_w[k];
-  native_coef_kernel<<<dim3((C + kNThreads - 1) / kNThreads, N), kNThreads, 0, s>>>(ca);
+  native_coef_kernel<<<dim3((C + kCoefCh - 1) / kCoefCh, N), kCoefCh * kMaxChunks, 0, s>>>(ca);
   AST_CHECK_LAUNCH();
 
   int64_t achunks = (8 * 148 + N - 1) / N;
