@@ -795,3 +795,41 @@ def test_autoencoder_256_train_step_vs_reference_golden(golden_ae256, ae):
     sd = ae.state_dict()
     for k in A.GOLDEN_BUFFER_KEYS:
         torch.testing.assert_close(sd[k].cpu().float(), T(g["t256_buf::" + k]).float(), rtol=2e-2, atol=2e-3)
+
+
+def test_autoencoder_per_batch_resolutions_of_the_reference_loader(ae):
+    """the reference's loader draws a new (h, w) from conf.img_sizes = [96, 128, 160] for every
+    batch (data_loader.py:89-97, conf.py:4).  Consecutive training steps at changing, non-square resolutions -- no
+    rebuild, no stale shape-keyed state -- against the CPU oracle running the same steps; then eval mode at each size."""
+    sizes = [(96, 96), (128, 160), (160, 96), (96, 128), (96, 96)]
+    sd = A.activate_gates(A.make_ae_state(2))
+    ae.load_state_dict(sd, strict=True)
+    ae.train()
+    opt = torch.optim.Adam(ae.parameters(), lr=2e-4, betas=(0.9, 0.99), eps=1e-7)
+    P = A.clone_state(sd, requires_grad=True)
+    train = [P[k] for k in sorted(P) if P[k].requires_grad]
+    opt_r = torch.optim.Adam(train, lr=2e-4, betas=(0.9, 0.99), eps=1e-7)
+    for i, (h, w) in enumerate(sizes):
+        x = torch.rand(2, 3, h, w, generator=G(400 + i))
+        opt.zero_grad()
+        loss = F.huber_loss(ae(x.cuda()), x.cuda())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ae.parameters(), 10.0)
+        opt.step()
+        opt_r.zero_grad()
+        ref = F.huber_loss(A.autoencoder_forward(P, x, training=True), x)
+        ref.backward()
+        torch.nn.utils.clip_grad_norm_(train, 10.0)
+        opt_r.step()
+        assert loss.item() == pytest.approx(ref.item(), rel=2e-3), (i, h, w, loss.item(), ref.item())
+    ae.eval()
+    Q = {k: v.detach().clone() for k, v in P.items()}
+    bias = Q["decoder._img_out.bias"]
+    for (h, w) in sizes[:3]:
+        x = torch.rand(1, 3, h, w, generator=G(h + w))
+        with torch.no_grad():
+            ae.load_state_dict(Q, strict=True)
+            got = ae(x.cuda())
+            want = A.autoencoder_forward(Q, x)
+        assert got.shape == want.shape
+        assert rel(_signal(got, bias), _signal(want, bias)) < 3e-2 and R.psnr(got.cpu(), want) >= 40.0

@@ -318,3 +318,65 @@ def test_cuda_graph_step_matches_eager():
     assert torch.isfinite(lg).item()
     for a, b in zip(dec_e.parameters(), dec_g.parameters()):
         torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
+
+
+def test_decoder_training_loss_curve_vs_oracle():
+    """an N-step loss curve of the config-2 step (train.py:287-300 glue: zero_grad,
+    backward, clip_grad_norm_(2.0), Adam(2e-4, eps 1e-5)) against the CPU oracle running the same steps in fp32 on
+    fresh batches each step.  Five steps at 2 x 64 x 64; Adam's normalised updates make the curve sensitive to gradient
+    DIRECTION, which is what the bf16 conv path has to get right."""
+    from arbitrarystyletransfer_b200 import models as M, losses as Ls
+    taps = ['relu_1', 'relu_3', 'relu_5', 'relu_9']
+    vw, _ = R.make_vgg_weights(0)
+    vb = R.calibrate_vgg_bias(vw)
+    dw, db = R.make_decoder_weights(1)
+    batches = [(R.rand_image(2, 64, 211 + i), R.rand_image(2, 64, 231 + i)) for i in range(5)]
+    # ---- oracle
+    wr = [w.clone().requires_grad_(True) for w in dw]
+    br = [b.clone().requires_grad_(True) for b in db]
+    opt_r = torch.optim.Adam(wr + br, lr=2e-4, betas=(0.9, 0.999), eps=1e-5)
+    want = []
+    for c, s in batches:
+        with torch.no_grad():
+            fc = R.vgg_relu4_1(c, vw, vb)
+            st = R.vgg_forward(s, vw, vb, taps)
+            t = R.adain(fc, st[-1])
+        opt_r.zero_grad()
+        gt = R.vgg_forward(R.decoder_forward(t, wr, br), vw, vb, taps)
+        loss = R.compute_content_loss(gt[-1], t) + sum(R.compute_style_loss(a, b) for a, b in zip(gt, st))
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(wr + br, 2.0)
+        opt_r.step()
+        want.append(loss.item())
+    # ---- this package
+    enc = M.PretrainedEncoder(taps).cuda()
+    dec = M.ClassicDecoder().cuda()
+    with torch.no_grad():
+        for cv, w, b in zip(enc._convs(), vw, vb):
+            cv.weight.copy_(w); cv.bias.copy_(b)
+        for cv, w, b in zip(dec._convs(), dw, db):
+            cv.weight.copy_(w); cv.bias.copy_(b)
+    opt = torch.optim.Adam(dec.parameters(), lr=2e-4, betas=(0.9, 0.999), eps=1e-5)
+    ada = M.AdaIN()
+    got = []
+    for c, s in batches:
+        c, s = c.cuda(), s.cuda()
+        with torch.no_grad():
+            fc = enc(c)[-1]
+            st = enc(s)
+            t = ada(fc, st[-1])
+        opt.zero_grad()                                   # set_to_none=True, as the reference's call
+        gt = enc(dec(t))
+        loss = Ls.compute_content_loss(gt[-1], t) + sum(Ls.compute_style_loss(a, b) for a, b in zip(gt, st))
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(dec.parameters(), 2.0, error_if_nonfinite=True)
+        opt.step()
+        got.append(loss.item())
+    print("config-2 loss curve: cuda", [round(v, 5) for v in got], "oracle", [round(v, 5) for v in want])
+    for g, w in zip(got, want):
+        assert g == pytest.approx(w, rel=2e-2)
+    # the parameters moved the same way: direction of the accumulated update, layer by layer
+    for i, cv in enumerate(dec._convs()):
+        d_got = (cv.weight.detach().cpu() - dw[i]).flatten().double()
+        d_ref = (wr[i].detach() - dw[i]).flatten().double()
+        assert torch.nn.functional.cosine_similarity(d_got, d_ref, dim=0).item() > 0.8, i
