@@ -106,6 +106,8 @@ PROTOTYPES = {
     "ast_se_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ast_pw_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _i64, _vp, _i64, _i64, _vp]),
     "ast_stem_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_stem_dgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ast_hardtanh01_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "ast_head_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_head_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_prep_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),

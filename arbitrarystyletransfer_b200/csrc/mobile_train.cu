@@ -704,6 +704,61 @@ head_dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ w /*OI
   st8(dx + pix * 16 + 8, hi);
 }
 
+// stem data gradient: dimg[n][ci][p] = sum_{q in Q(p)} sum_{tap, co} W[co][ci][tap] * (dy * Hardswish'(z))[q - tap + 1][co]
+// (q runs over the padded-grid positions that reflect onto p; conv_3x3_bn, mobilenetv2.py:38-43, Cout == 16).
+// NHWC gradient / activation in, NCHW fp32 out.  Only flows that differentiate through the Encoder's INPUT need it.
+template <typename AT>
+__global__ void __launch_bounds__(128)
+stem_dgrad_kernel(const grad_t* __restrict__ dy, const AT* __restrict__ z, const float* __restrict__ w /*OIHW [16][3][3][3]*/,
+                  float* __restrict__ dimg, int N, int H, int W) {
+  __shared__ float s_w[9][3][16];
+  for (int i = threadIdx.x; i < 9 * 3 * 16; i += 128) {
+    const int co = i % 16, ci = (i / 16) % 3, t = i / 48;
+    s_w[t][ci][co] = w[((int64_t)co * 3 + ci) * 9 + t];
+  }
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (pix >= (int64_t)N * H * W) return;
+  const int xw = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+  float acc[3] = {0.f, 0.f, 0.f};
+  int qh[3], qw[3];
+  const int nh = reflect_cands(h, H, 1, qh), nw = reflect_cands(xw, W, 1, qw);
+  for (int a = 0; a < nh; ++a)
+    for (int kh = 0; kh < 3; ++kh) {
+      const int oh = qh[a] + 1 - kh;
+      if (oh < 0 || oh >= H) continue;
+      for (int b = 0; b < nw; ++b)
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ow = qw[b] + 1 - kw;
+          if (ow < 0 || ow >= W) continue;
+          const int64_t o = (((int64_t)n * H + oh) * W + ow) * 16;
+          float d[16], zz[16];
+          ld8(dy + o, *reinterpret_cast<float(*)[8]>(d));
+          ld8(dy + o + 8, *reinterpret_cast<float(*)[8]>(d + 8));
+          ld8(z + o, *reinterpret_cast<float(*)[8]>(zz));
+          ld8(z + o + 8, *reinterpret_cast<float(*)[8]>(zz + 8));
+#pragma unroll
+          for (int co = 0; co < 16; ++co) {
+            const float dz = d[co] * hsw_grad(zz[co]);
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) acc[ci] = fmaf(dz, s_w[kh * 3 + kw][ci][co], acc[ci]);
+          }
+        }
+    }
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) dimg[(((int64_t)n * 3 + ci) * H + h) * W + xw] = acc[ci];
+}
+
+// Hardtanh(0,1) backward of the exporting decoder head (models.py:304, 315-316): dx = dy where 0 < y < 1 (y = the
+// clamped output), else 0.
+__global__ void hardtanh01_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                                      int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    dx[i] = (v > 0.f && v < 1.f) ? dy[i] : 0.f;
+  }
+}
+
 // ---- weight preparation: fp32 [R][Cc] -> 0: bf16, 1: bf16 transposed, 2: fp32 transposed, 3: fp16 (forward GEMMs) ----
 template <typename AT>
 __global__ void prep_weight_kernel(const float* __restrict__ w, void* __restrict__ out, int R, int Cc, int mode) {
@@ -958,6 +1013,26 @@ extern "C" int ast_stem_wgrad(const void* dy, const void* z, const float* img, f
   int64_t nb = ((int64_t)N * H * W + kT - 1) / kT;
   if (nb > 148 * 2) nb = 148 * 2;
   AST_ACT_DISPATCH(stem_wgrad_kernel<AT><<<dim3((unsigned)nb, 9), kT, 0, (cudaStream_t)stream>>>(CGR(dy), CAC(z), img, dw, N, H, W));
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_stem_dgrad(const void* dy, const void* z, const float* w, float* dimg, int N, int H, int W,
+                              int Cout, void* stream) {
+  if (!dy || !z || !w || !dimg || N <= 0 || H < 2 || W < 2) return AST_E_BADARG;
+  if (Cout != 16) return AST_E_SHAPE;
+  const int64_t nb = ((int64_t)N * H * W + 127) / 128;
+  if (nb >= 0x7fffffffLL) return AST_E_SHAPE;
+  AST_ACT_DISPATCH(stem_dgrad_kernel<AT><<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(CGR(dy), CAC(z), w, dimg, N, H, W));
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_hardtanh01_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+  if (!dy || !y || !dx || n <= 0) return AST_E_BADARG;
+  int64_t nb = (n + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  hardtanh01_bwd_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n);
   AST_CHECK_LAUNCH();
   return 0;
 }

@@ -17,8 +17,9 @@ Two execution paths, both entirely through libast_b200 (no torch arithmetic on a
   * training (train_autoencoder.py:111-148): BatchNorm with batch statistics and running-stat updates,
     every intermediate kept in NHWC bf16, and hand-written backward kernels (pointwise data / weight
     gradients on tcgen05, depthwise data / weight gradients, BatchNorm / Hardswish / SE backward), wired
-    into autograd one block at a time so the reference's optimiser / clip code runs unchanged.
-Eval-mode BatchNorm WITH gradients is not implemented and raises.
+    into autograd one block at a time so the reference's optimiser / clip code runs unchanged.  Eval-mode
+    BatchNorm with gradients (running statistics held constant), the gradient with respect to the input image and
+    the backward of the exporting (Hardtanh) head are covered as well.
 """
 from __future__ import annotations
 
@@ -285,8 +286,27 @@ def _bn_train_forward(a, bn):
     return stat
 
 
-def _bn_backward(dy, a, stat):
-    """Generic BatchNorm backward on NHWC tensors: returns (da, dgamma, dbeta)."""
+def _bn_eval_stat(bn, dev):
+    """stat = float[4][C] (mean, invstd, scale, shift) of nn.BatchNorm2d in EVAL mode: the running statistics take the
+    place of the batch statistics and nothing is updated (ast_bn_finalize on sums that encode them with count 1)."""
+    lib = L.load()
+    rm, rv = bn.running_mean.detach().double(), bn.running_var.detach().double()
+    sums = torch.stack((rm, rv + rm * rm)).contiguous()
+    Cc = rm.numel()
+    stat = torch.empty(4, Cc, device=dev, dtype=torch.float32)
+    L.check(lib.ast_bn_finalize(sums.data_ptr(), 1.0, bn.weight.data_ptr(), bn.bias.data_ptr(), None, None, 0.0,
+                                float(bn.eps), stat.data_ptr(), Cc, L.stream_ptr(dev)), "ast_bn_finalize")
+    return stat
+
+
+def _bn_forward(a, bn, frozen):
+    return _bn_eval_stat(bn, a.device) if frozen else _bn_train_forward(a, bn)
+
+
+def _bn_backward(dy, a, stat, frozen=False):
+    """Generic BatchNorm backward on NHWC tensors: returns (da, dgamma, dbeta).  ``frozen`` (eval mode): the statistics
+    are constants, so da = dy * scale -- the two batch-coupling coefficients are zeroed -- while dgamma / dbeta are the
+    same sums."""
     lib = L.load()
     dy, ld_dy = _rows(dy)
     a, ld_a = _rows(a)
@@ -302,6 +322,8 @@ def _bn_backward(dy, a, stat):
                                   N, Cc, H * W, st), "ast_bn_bwd_reduce")
     L.check(lib.ast_bn_bwd_finalize(sums.data_ptr(), float(N * H * W), dgamma.data_ptr(), dbeta.data_ptr(),
                                     coef.data_ptr(), Cc, st), "ast_bn_bwd_finalize")
+    if frozen:
+        coef.zero_()
     L.check(lib.ast_bn_bwd_apply(dy.data_ptr(), ld_dy, a.data_ptr(), ld_a, stat.data_ptr(), coef.data_ptr(),
                                  da.data_ptr(), N, Cc, H * W, st), "ast_bn_bwd_apply")
     return da, dgamma, dbeta
@@ -336,6 +358,8 @@ class _BlockFn(torch.autograd.Function):
         N, H, W, _ = x.shape
         dev = x.device
         hid, k, stride = mod.hidden, mod.k, mod.stride
+        frozen = norm and not mod.training       # eval-mode BatchNorm with gradients: running statistics, no update
+        ctx.frozen = frozen
         a1 = stat1 = stat2 = stat3 = a3 = None
         if expand:
             if up2:
@@ -343,7 +367,7 @@ class _BlockFn(torch.autograd.Function):
             w1b = prep_weight(P["w1"], hid, mod.inp, 3)
             if norm:
                 a1 = pw_conv(x, w1b, None, 0, hid, f16=act_is_f16())
-                stat1 = _bn_train_forward(a1, bns[0])
+                stat1 = _bn_forward(a1, bns[0], frozen)
                 dw_in, _ = affine_act(a1, stat1[2], stat1[3], 1)
             else:
                 a1, dw_in = pw_conv(x, w1b, None, 1, hid, want_raw=True, f16=act_is_f16())
@@ -353,7 +377,7 @@ class _BlockFn(torch.autograd.Function):
         a2, pool = dw_conv(dw_in, wd, None, k, stride, up2=up2, act=0 if norm else 2, want_pool=not norm)
         Ho, Wo = a2.shape[1], a2.shape[2]
         if norm:
-            stat2 = _bn_train_forward(a2, bns[1])
+            stat2 = _bn_forward(a2, bns[1], frozen)
             _, pool = affine_act(a2, stat2[2], stat2[3], 1, want_out=False, want_pool=True)
         inv_hw = 1.0 / (Ho * Wo)
         s, sehid, sepre = se_fc(pool, inv_hw, P["se_w1"], P["se_b1"], P["se_w2"], P["se_b2"], save=True)
@@ -362,7 +386,7 @@ class _BlockFn(torch.autograd.Function):
         res = x if mod.identity else None
         if norm:
             a3 = pw_conv(u, w2b, None, 0, mod.oup, f16=act_is_f16())
-            stat3 = _bn_train_forward(a3, bns[2])
+            stat3 = _bn_forward(a3, bns[2], frozen)
             out, _ = affine_act(a3, stat3[2], stat3[3], 0, res=res)
         else:
             out = pw_conv(u, w2b, None, 0, mod.oup, residual=res, res_up2=bool(up2 and mod.identity), f16=act_is_f16())
@@ -388,7 +412,7 @@ class _BlockFn(torch.autograd.Function):
         d_out, _ = _rows(d_out.to(torch.bfloat16))
         # ---- pw-linear (+ its norm) ----
         if norm:
-            d_a3, grads["g3"], grads["b3"] = _bn_backward(d_out, a3, stat3)
+            d_a3, grads["g3"], grads["b3"] = _bn_backward(d_out, a3, stat3, ctx.frozen)
         else:
             d_a3 = d_out
         d_u = pw_conv(d_a3, prep_weight(P["w2"], oup, hid, 1), None, 0, hid)
@@ -418,6 +442,8 @@ class _BlockFn(torch.autograd.Function):
             L.check(lib.ast_se_bn_combine(T.data_ptr(), s.data_ptr(), g.data_ptr(), grads["g2"].data_ptr(),
                                           grads["b2"].data_ptr(), coef2.data_ptr(), N, hid, float(N * HWo), st),
                     "ast_se_bn_combine")
+            if ctx.frozen:
+                coef2.zero_()
         d_a2 = _empty(N, Ho, Wo, hid, dev)
         L.check(lib.ast_dw_bwd_apply(d_u.data_ptr(), a2.data_ptr(), s.data_ptr(), g.data_ptr(), L.ptr(stat2),
                                      L.ptr(coef2), d_a2.data_ptr(), N, hid, HWo, st), "ast_dw_bwd_apply")
@@ -437,7 +463,7 @@ class _BlockFn(torch.autograd.Function):
         # ---- pw expand (+ its norm) ----
         if expand:
             if norm:
-                d_a1, grads["g1"], grads["b1"] = _bn_backward(d_in, a1, stat1)
+                d_a1, grads["g1"], grads["b1"] = _bn_backward(d_in, a1, stat1, ctx.frozen)
             else:
                 d_a1 = d_in
             dW1 = torch.zeros_like(P["w1"], dtype=torch.float32)
@@ -466,22 +492,27 @@ class _StemFn(torch.autograd.Function):
         wf = w.detach().float().contiguous()
         L.check(lib.ast_stem_conv(img.data_ptr(), wf.data_ptr(), y.data_ptr(), z.data_ptr(), N, H, W, cout,
                                   _st(img)), "ast_stem_conv")
-        ctx.save_for_backward(img, z)
+        ctx.save_for_backward(img, z, wf)
         ctx.wshape = tuple(w.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = L.load()
-        if ctx.needs_input_grad[0]:
-            raise L.AstError("gradient with respect to the Encoder's input image is not implemented")
-        img, z = ctx.saved_tensors
+        img, z, wf = ctx.saved_tensors
         N, _, H, W = img.shape
         dy = dy.to(torch.bfloat16).contiguous()
-        dw = torch.zeros(ctx.wshape, device=img.device, dtype=torch.float32)
-        L.check(lib.ast_stem_wgrad(dy.data_ptr(), z.data_ptr(), img.data_ptr(), dw.data_ptr(), N, H, W,
-                                   ctx.wshape[0], _st(img)), "ast_stem_wgrad")
-        return None, dw
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(ctx.wshape, device=img.device, dtype=torch.float32)
+            L.check(lib.ast_stem_wgrad(dy.data_ptr(), z.data_ptr(), img.data_ptr(), dw.data_ptr(), N, H, W,
+                                       ctx.wshape[0], _st(img)), "ast_stem_wgrad")
+        dimg = None
+        if ctx.needs_input_grad[0]:
+            dimg = torch.empty_like(img)
+            L.check(lib.ast_stem_dgrad(dy.data_ptr(), z.data_ptr(), wf.data_ptr(), dimg.data_ptr(), N, H, W,
+                                       ctx.wshape[0], _st(img)), "ast_stem_dgrad")
+        return dimg, dw
 
 
 class _HeadFn(torch.autograd.Function):
@@ -497,17 +528,22 @@ class _HeadFn(torch.autograd.Function):
         wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
         L.check(lib.ast_head_conv(x.data_ptr(), wf.data_ptr(), bf.data_ptr(), out.data_ptr(), N, H, W, Cc, co,
                                   int(clamp), _st(x)), "ast_head_conv")
-        ctx.save_for_backward(x, wf)
+        ctx.save_for_backward(x, wf, out if clamp else None)
         return out
 
     @staticmethod
     def backward(ctx, dY):
         lib = L.load()
-        x, wf = ctx.saved_tensors
+        x, wf, y_clamped = ctx.saved_tensors
         N, H, W, Cc = x.shape
         co = wf.shape[0]
         dY = dY.float().contiguous()
         st = _st(x)
+        if y_clamped is not None:     # Hardtanh(0,1) of the exporting head (models.py:304, 315-316)
+            masked = torch.empty_like(dY)
+            L.check(lib.ast_hardtanh01_bwd(dY.data_ptr(), y_clamped.data_ptr(), masked.data_ptr(), dY.numel(), st),
+                    "ast_hardtanh01_bwd")
+            dY = masked
         dw = torch.zeros_like(wf)
         db = torch.zeros(co, device=x.device, dtype=torch.float32)
         L.check(lib.ast_head_wgrad(dY.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), N, H, W, Cc, co, st),
@@ -673,8 +709,6 @@ class DepthWiseConv(nn.Module):
         lib = L.load()
         grad = _wants_grad(self, x)
         if grad or (self.training and self.use_norm):
-            if grad and self.use_norm and not self.training:
-                raise L.AstError("eval-mode BatchNorm with gradients is not implemented: call .train()")
             return _BlockFn.apply(x, self, up2, *self._param_list())
         d = self._prepared()
         N = x.shape[0]
@@ -784,9 +818,7 @@ class Decoder(nn.Module):
         for block in self._decoder_blocks:
             x = block.forward_nhwc(x)
         if _wants_grad(self._img_out, x):
-            if self.exporting:
-                raise L.AstError("exporting=True (Hardtanh output) has no backward; train with exporting=False")
-            return _HeadFn.apply(x, self._img_out.weight, self._img_out.bias, False)
+            return _HeadFn.apply(x, self._img_out.weight, self._img_out.bias, bool(self.exporting))
         N, H, W, Cc = x.shape
         co = self._img_out.out_channels
         x = x if x.is_contiguous() else x.contiguous()

@@ -426,6 +426,12 @@ int ast_pw_wgrad(const void* a, int ld_a, int Ca, const void* b, int ld_b, int C
 /* Stem (conv_3x3_bn) weight gradient: dw (16,3,3,3) += sum dy*Hardswish'(z) (x) img[reflected tap]. */
 int ast_stem_wgrad(const void* dy, const void* z, const float* img, float* dw, int N, int H, int W, int Cout,
                    void* stream);
+/* Stem data gradient: NCHW fp32 gradient of the image (3 channels) from the stem output's gradient dy (bf16) and the
+ * stored pre-activation z; reflection padding folded back.  Needed only when the Encoder's INPUT requires grad. */
+int ast_stem_dgrad(const void* dy, const void* z, const float* w, float* dimg, int N, int H, int W, int Cout,
+                   void* stream);
+/* Hardtanh(0,1) backward of the exporting head (models.py:304, 315-316): dx = dy where 0 < y < 1 else 0 (fp32). */
+int ast_hardtanh01_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
 /* Image head (_ref_out + _img_out): weight / bias gradient (accumulated) and data gradient (NHWC bf16). */
 int ast_head_wgrad(const float* dY, const void* x, float* dw, float* db, int N, int H, int W, int Cin, int Cout,
                    void* stream);

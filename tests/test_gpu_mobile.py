@@ -833,3 +833,93 @@ def test_autoencoder_per_batch_resolutions_of_the_reference_loader(ae):
             want = A.autoencoder_forward(Q, x)
         assert got.shape == want.shape
         assert rel(_signal(got, bias), _signal(want, bias)) < 3e-2 and R.psnr(got.cpu(), want) >= 40.0
+
+
+# ------------------------------------------------------------------------------------------------
+# the three gaps round 1 left on rows a7 / a8: eval-mode BatchNorm WITH gradients, the gradient with respect to the
+# Encoder's input image, and the backward of the exporting (Hardtanh) head
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [BLOCKS[0], BLOCKS[1]])
+def test_block_eval_mode_batchnorm_with_gradients_vs_oracle(cfg):
+    """nn.BatchNorm2d in eval mode inside a differentiated block: running statistics instead of batch statistics, no
+    running-stat update, da = dy * scale (mobilenetv2.py:108, 128, 137, 149 under ``.eval()``)."""
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    inp, oup, stride, t, k, norm, ident, up2, H, W = cfg
+    torch.manual_seed(sum(int(v) for v in cfg) + 1)
+    blk = MB.DepthWiseConv(inp, oup, stride, t, kernel_size=k, use_norm=True, use_identity=ident)
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.Linear):
+                m.weight.normal_(0, 0.05)
+                m.bias.uniform_(0.3, 0.7)
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.3)
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 2.0)
+    sd = _block_state(blk)
+    P = A.clone_state(sd, requires_grad=True)
+    x = f16r(torch.randn(3, inp, H, W, generator=G(3))).requires_grad_(True)
+    ref = A.depthwise_block(P, "b", x, inp, oup, stride, t, k, norm=True, use_identity=ident, training=False)
+    dy = bf16r(torch.randn(ref.shape, generator=G(4)))
+    ref.backward(dy)
+    blk = blk.cuda().eval()
+    xg = nhwc(x.detach()).requires_grad_(True)
+    out = blk.forward_nhwc(xg)
+    assert rel(nchw(out), ref.detach()) < 3e-3, rel(nchw(out), ref.detach())
+    out.backward(gnhwc(dy))
+    assert rel(gnchw(xg.grad), x.grad) < 2e-2, rel(gnchw(xg.grad), x.grad)
+    for name, p in blk.named_parameters():
+        want = P["b." + name].grad
+        assert cos(p.grad, want) > 0.999 and rel(p.grad, want) < 4e-2, (name, rel(p.grad, want), cos(p.grad, want))
+    for name, b in blk.named_buffers():           # eval mode: running statistics untouched
+        assert torch.equal(b.cpu(), sd["b." + name]), name
+
+
+def test_encoder_input_image_gradient_and_exporting_head_backward():
+    from arbitrarystyletransfer_b200 import mobilenet as MB
+    g = G(21)
+    N, H, W = 2, 10, 14
+    # stem: gradient with respect to the image (reflection padding folded back)
+    img = torch.rand(N, 3, H, W, generator=g).requires_grad_(True)
+    w = (torch.randn(16, 3, 3, 3, generator=g) * 0.4).requires_grad_(True)
+    y = F.hardswish(F.conv2d(F.pad(img, (1, 1, 1, 1), mode="reflect"), w))
+    dy = bf16r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    ig, wg = img.detach().cuda().requires_grad_(True), w.detach().cuda().requires_grad_(True)
+    yg = MB._StemFn.apply(ig, wg)
+    yg.backward(gnhwc(dy))
+    assert rel(ig.grad, img.grad) < 5e-3, rel(ig.grad, img.grad)
+    assert rel(wg.grad, w.grad) < 1e-2
+    # through the public module: Encoder(x) with x.requires_grad (eval mode, frozen statistics)
+    xin = torch.rand(2, 3, 32, 32, generator=g)
+    Q = A.calibrate_running_stats(A.clone_state(A.activate_gates(A.make_ae_state(2))), xin)   # non-degenerate state
+    torch.manual_seed(2)
+    enc = MB.Encoder().cuda().eval()
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in Q.items() if k.startswith("encoder.")}, strict=True)
+    gout = torch.randn(2, 128, 4, 4, generator=g)
+    xg_ = xin.clone().cuda().requires_grad_(True)
+    (enc(xg_, auto_enc=True) * gout.cuda()).sum().backward()
+    xr = xin.clone().requires_grad_(True)
+    (A.encoder_forward(Q, xr, auto_enc=True, training=False) * gout).sum().backward()
+    assert xr.grad.abs().sum() > 0
+    assert cos(xg_.grad, xr.grad) > 0.995 and rel(xg_.grad, xr.grad) < 0.1, (cos(xg_.grad, xr.grad), rel(xg_.grad, xr.grad))
+    # exporting head: Hardtanh(0,1) after the conv (models.py:304, 315-316), with its backward
+    x = f16r(torch.randn(N, 16, H, W, generator=g)).requires_grad_(True)
+    hw = (torch.randn(3, 16, 3, 3, generator=g) * 0.2).requires_grad_(True)
+    hb = (torch.rand(3, generator=g) * 0.6 + 0.2).requires_grad_(True)
+    out = F.hardtanh(F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), hw, hb), 0.0, 1.0)
+    dY = torch.randn(out.shape, generator=g)
+    out.backward(dY)
+    assert 0.05 < (out.detach() == 0).float().mean() + (out.detach() == 1).float().mean() < 0.95   # both regimes present
+    xg = nhwc(x.detach()).requires_grad_(True)
+    hwg, hbg = hw.detach().cuda().requires_grad_(True), hb.detach().cuda().requires_grad_(True)
+    og = MB._HeadFn.apply(xg, hwg, hbg, True)
+    assert rel(og, out.detach()) < 1e-4
+    og.backward(dY.cuda())
+    assert rel(hwg.grad, hw.grad) < 1e-4 and rel(hbg.grad, hb.grad) < 1e-4
+    assert rel(gnchw(xg.grad), x.grad) < 5e-3
+    dec = MB.Decoder(exporting=True).cuda()
+    z = torch.rand(1, 128, 4, 4, generator=g).cuda()
+    dec(z).sum().backward()                                  # no longer raises
+    assert dec._img_out.weight.grad is not None
