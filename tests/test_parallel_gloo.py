@@ -58,7 +58,7 @@ def _worker(rank, world, port, out_q):
         bucket.all_reduce_mean()
         outs = P.gather_shards(model(xs).detach(), 8)
         if rank == 0:
-            out_q.put((bucket.flat.clone(), outs))
+            out_q.put((bucket.flat.numpy().copy(), outs.numpy().copy()))   # by value: the producer may exit first
     finally:
         dist.destroy_process_group()
 
@@ -70,7 +70,7 @@ def test_two_rank_gradient_bucket_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    flat, outs = q.get()
+    flat, outs = (torch.from_numpy(a) for a in q.get())
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
@@ -116,7 +116,7 @@ def _worker_ref_step(rank, world, port, out_q):
         bucket.all_reduce_mean(local_count=xs.shape[0])   # adopts the fresh .grad tensors, weights by shard size
         assert bucket.aliased()
         if rank == 0:
-            out_q.put((bucket.flat.clone(), model[1].running_mean.clone()))
+            out_q.put((bucket.flat.numpy().copy(), model[1].running_mean.numpy().copy()))
     finally:
         dist.destroy_process_group()
 
@@ -128,7 +128,7 @@ def test_reference_zero_grad_and_unequal_shards():
     procs = [ctx.Process(target=_worker_ref_step, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    flat, rm = q.get()
+    flat, rm = (torch.from_numpy(a) for a in q.get())
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
