@@ -1,0 +1,247 @@
+// K2p: the kw-box implicit-GEMM conv of conv3x3_tc2_kernel on CTA PAIRS (tcgen05.mma.cta_group::2, M = 256).
+// Included by conv_tc.cu; same tile geometry (16 rows x 8 columns of pixels per CTA, one {64 ch, 8 w, 18 h} A box per
+// kw serving kh = 0..2), same epilogue (epilogue_loop<..., P2 = true>), same reference work replaced
+// (/root/reference/models.py:186-240 VGG convs, models.py:598-628 decoder convs).
+//
+// Why: with both operands in shared memory an M128 x N x K16 instruction reads (128 + N) x 32 B; at N = 64 / 128
+// that is 6 / 8 KB per 32 / 64 tensor cycles, i.e. the 128 B/clk shared-memory port is the limit (48 cycles measured at
+// N = 64, tools/ubench/mma_rate.cu) and the TMA writes of the next operands compete for the same port.  A CTA pair
+// runs ONE M = 256 instruction over the two SMs of a TPC: each CTA holds its own 128 pixel rows of A and only HALF of
+// the weight tile (N/2 rows), so per SM and instruction 5 / 6 / 8 KB are read for N = 64 / 128 / 256, the weight
+// TMA traffic per SM halves, and issue + commit costs are paid once per 256 rows.
+//
+// Protocol (leader = cluster rank 0):
+//   A/B full barriers   live in the LEADER; both CTAs' TMA loads (cp.async.bulk.tensor.cta_group::2) complete their
+//                       bytes there, the leader's producer arms them with the sum of both CTAs' bytes;
+//   A/B empty barriers  live in BOTH CTAs; the leader's MMA warp releases a slot with a multicast tcgen05.commit;
+//   tfull               in both CTAs (multicast commit); each CTA's epilogue warps read their own TMEM;
+//   tempty              in the leader, count = both CTAs' epilogue warps (rank 1 arrives remotely).
+// An odd number of spatial tiles leaves rank 1 of the last pair a phantom tile (image index N): its TMA boxes are out
+// of bounds (zero fill) and its epilogue stores nothing.
+#pragma once
+
+template <int BN>
+struct CfgP {
+  static constexpr int HB = BN / 2;                       // weight rows per CTA
+  static constexpr int B_BYTES = HB * KBLK * 2;           // per tap and CTA
+  static constexpr int NA = (BN == 64) ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int NB = 9;                            // three groups (one per kw) of three taps (kh)
+  static constexpr int NACC = (BN <= 128) ? 4 : 2;
+  static constexpr int TMEM_COLS = NACC * BN;
+  static constexpr int NBAR = 2 * NA + 2 * 3 + 2 * NACC;
+  static constexpr int SMEM_BYTES = NA * A2_BYTES + NB * B_BYTES + NBAR * 8 + 16 + 1024;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(Epi2<BN>::THREADS, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const ConvParams p) {
+  using C = CfgP<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + C::NA * A2_BYTES;
+  const uint32_t bars = b_base + C::NB * C::B_BYTES;
+  auto afull = [&](int s) { return bars + 8u * s; };
+  auto aempty = [&](int s) { return bars + 8u * (C::NA + s); };
+  auto bfull = [&](int s) { return bars + 8u * (2 * C::NA + s); };
+  auto bempty = [&](int s) { return bars + 8u * (2 * C::NA + 3 + s); };
+  auto tfull = [&](int s) { return bars + 8u * (2 * C::NA + 6 + s); };
+  auto tempty = [&](int s) { return bars + 8u * (2 * C::NA + 6 + C::NACC + s); };
+  const uint32_t tmem_slot = bars + 8u * C::NBAR;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem + C::NA * A2_BYTES + C::NB * C::B_BYTES + 8 * C::NBAR);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair0 = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  const int cblocks = p.Cin / KBLK;
+  const bool resident = cblocks == 1 && p.n_blocks == 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < 3; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 2 * 4 * Epi2<BN>::NG); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();          // both CTAs' barriers initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own pixels, own half of the weight rows) =====================
+    if (lane == 0) {
+      const uint32_t afull_l = mapa_shared(afull(0), 0), bfull_l = mapa_shared(bfull(0), 0);
+      if (resident) {
+        for (int kw = 0; kw < 3; ++kw) {
+          if (rank == 0) mbar_expect_tx(bfull(kw), 2 * 3 * C::B_BYTES);
+          for (int kh = 0; kh < 3; ++kh)
+            tma_load_3d_2sm(b_base + (kw * 3 + kh) * C::B_BYTES, &tmB, bfull_l + 8u * kw, 0, rank * C::HB, kh * 3 + kw);
+        }
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      long long dbg_pa = 0, dbg_pb = 0;
+      for (int q = pair0; q < p.num_tiles; q += npairs) {
+        int t = q;
+        const int nb = t % p.n_blocks; t = 2 * (t / p.n_blocks) + rank;
+        const int twi = t % p.tiles_w; t /= p.tiles_w;
+        const int thi = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        const int h0 = thi * T2_H, w0 = twi * T2_W;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa, p.prod_sleep_ns);
+            if (rank == 0) mbar_expect_tx(afull(sa), 2 * A2_BYTES);
+            tma_load_4d_2sm(a_base + sa * A2_BYTES, &tmA, afull_l + 8u * sa, cb * KBLK, w0 + kw, h0, n);
+            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            if (!resident) {
+              mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb, p.prod_sleep_ns);
+              if (rank == 0) mbar_expect_tx(bfull(sb), 2 * 3 * C::B_BYTES);
+              for (int kh = 0; kh < 3; ++kh)
+                tma_load_3d_2sm(b_base + (sb * 3 + kh) * C::B_BYTES, &tmB, bfull_l + 8u * sb, cb * KBLK,
+                                nb * BN + rank * C::HB, kh * 3 + kw);
+              if (++sb == 3) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+      }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_pa; p.dbg[blockIdx.x * 8 + 1] = dbg_pb; }
+      // drain: every multicast release aimed at this CTA has landed before it may exit
+      for (int i = 0; i < C::NA; ++i) {
+        mbar_wait(aempty(sa), pa ^ 1u);
+        if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+      }
+      if (!resident) {
+        for (int i = 0; i < 3; ++i) {
+          mbar_wait(bempty(sb), pb ^ 1u);
+          if (++sb == 3) { sb = 0; pb ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the leader's converged warp, one elected lane =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, BN);
+      const uint64_t a_desc0 = make_sdesc_k128(a_base);
+      const uint64_t b_desc0 = make_sdesc_k128(b_base);
+      constexpr uint64_t A_SLOT16 = A2_BYTES >> 4, B_SLOT16 = C::B_BYTES >> 4, KH16 = (T2_W * KBLK * 2) >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      bool b_resident_ready = false;
+      long long dbg_mt = 0, dbg_ma = 0, dbg_mb = 0;
+      const long long dbg_m0 = clock64();
+      const bool dbg = p.dbg != nullptr;
+      for (int q = pair0; q < p.num_tiles; q += npairs) {
+        mbar_wait_acc(tempty(as), aphase ^ 1u, dbg, dbg_mt);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        uint32_t accum = 0;
+        for (int cb = 0; cb < cblocks; ++cb) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait_acc(afull(sa), pa, dbg, dbg_ma);
+            const uint64_t ad = a_desc0 + (uint64_t)sa * A_SLOT16;
+            int grp;
+            if (resident) {
+              grp = kw;
+              if (!b_resident_ready) mbar_wait(bfull(kw), 0u);  // first tile only
+            } else {
+              grp = sb;
+              mbar_wait_acc(bfull(sb), pb, dbg, dbg_mb);
+            }
+            tc_fence_after();
+            const uint64_t bd = b_desc0 + (uint64_t)(grp * 3) * B_SLOT16;
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int k = 0; k < KBLK / 16; ++k) {
+                  umma_bf16_2sm(d_tmem, ad + (uint64_t)(kh * KH16 + k * 2), bd + (uint64_t)(kh * B_SLOT16 + k * 2),
+                                idesc, (kh | k) ? 1u : accum);
+                }
+              }
+              if (!resident) umma_commit_2sm(bempty(sb));
+              umma_commit_2sm(aempty(sa));
+            }
+            __syncwarp();
+            accum = 1u;
+            if (!resident) {
+              if (++sb == 3) { sb = 0; pb ^= 1u; }
+            }
+            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+          }
+        }
+        b_resident_ready = true;
+        if (elect_one_sync()) umma_commit_2sm(tfull(as));
+        __syncwarp();
+        if (++as == C::NACC) { as = 0; aphase ^= 1u; }
+      }
+      if (p.dbg && lane == 0) {
+        p.dbg[blockIdx.x * 8 + 2] = dbg_ma + dbg_mb;
+        p.dbg[blockIdx.x * 8 + 3] = dbg_mt;
+        p.dbg[blockIdx.x * 8 + 6] = clock64() - dbg_m0;
+      }
+    }
+  } else if (warp >= 4) {
+    epilogue_loop<BN, EPI, T2_W, Epi2<BN>::NG, C::NACC, 1, true>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0), rank);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // no CTA exits (or frees TMEM) while its partner may still touch it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count,
+                       cudaStream_t s) {
+  using C = CfgP<BN>;
+  auto kern = conv3x3_pair_kernel<BN, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int max_pairs = sm_count / 2;
+  const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(Epi2<BN>::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AST_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BN>
+static int launch_pair_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
+                           int sm_count, cudaStream_t s) {
+  switch (epi) {
+    case AST_EPI_PLAIN: return launch_pair<BN, AST_EPI_PLAIN>(tmA, tmB, p, sm_count, s);
+    case AST_EPI_POOL2: return launch_pair<BN, AST_EPI_POOL2>(tmA, tmB, p, sm_count, s);
+    case AST_EPI_UP2: return launch_pair<BN, AST_EPI_UP2>(tmA, tmB, p, sm_count, s);
+  }
+  return AST_E_BADARG;
+}

@@ -105,25 +105,30 @@ __device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, boo
 struct TileCursor {
   int nb, twi, thi, n;
   int g0, g1, g2, g3;
-  int NB, TWc, THc;
-  __device__ __forceinline__ void init(const ConvParams& p, int tile, int stride) {
-    NB = p.n_blocks; TWc = p.tiles_w; THc = p.tiles_h;
+  int NB, TWc, THc, mult;
+  // CTA pairs (mult = 2): the work index counts (spatial tile PAIR, n-block); this CTA's spatial tile is
+  // 2 * pair + rank, so a carry out of the n-block digit advances the spatial digits by 2.
+  __device__ __forceinline__ void init(const ConvParams& p, int tile, int stride, int mult_ = 1, int rank = 0) {
+    NB = p.n_blocks; TWc = p.tiles_w; THc = p.tiles_h; mult = mult_;
     int t = tile;
-    nb = t % NB; t /= NB;
+    nb = t % NB; t = mult * (t / NB) + rank;
     twi = t % TWc; t /= TWc;
     thi = t % THc; n = t / THc;
     t = stride;
-    g0 = t % NB; t /= NB;
+    g0 = t % NB; t = mult * (t / NB);
     g1 = t % TWc; t /= TWc;
     g2 = t % THc; g3 = t / THc;
   }
   __device__ __forceinline__ void next() {
     nb += g0;
-    int c = nb >= NB; nb -= c ? NB : 0;
+    int c = 0;
+    if (nb >= NB) { nb -= NB; c = mult; }
     twi += g1 + c;
-    c = twi >= TWc; twi -= c ? TWc : 0;
+    c = 0;
+    while (twi >= TWc) { twi -= TWc; ++c; }
     thi += g2 + c;
-    c = thi >= THc; thi -= c ? THc : 0;
+    c = 0;
+    while (thi >= THc) { thi -= THc; ++c; }
     n += g3 + c;
   }
 };
@@ -161,9 +166,11 @@ __device__ __forceinline__ int out_targets(int x, int Xo, int halo, int (&t)[4])
 // TG > 1 (tile groups, requires NG == 1 and NACC == TG): instead of splitting every tile's columns over the warp
 // groups, group tg = ew / 4 takes every TG-th tile whole and owns accumulator stage tg -- TG tiles are in the
 // epilogue at once, which is what a layer whose work IS the epilogue (conv1_1) needs.
-template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2, int TG = 1>
+// P2 (CTA pair, conv_pair.cuh): the work index counts tile pairs, this CTA takes spatial tile 2 * pair + rank, and the
+// accumulator is handed back on the LEADER's tempty barrier (a remote arrive for rank 1).
+template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2, int TG = 1, bool P2 = false>
 __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
-                                              uint32_t tfull_bar0, uint32_t tempty_bar0) {
+                                              uint32_t tfull_bar0, uint32_t tempty_bar0, int rank = 0) {
   constexpr int CH = (TG > 1) ? 16 : ((BN >= 32 && BN / 32 >= NG) ? 32 : 16);  // columns per tcgen05.ld
   constexpr int TH = TILE_M / TW;         // tile = TH rows x TW cols of pixels, row-major in M
   constexpr int NCH = BN / CH;
@@ -171,7 +178,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
   // touch lanes [32*(warp%4), +32)) and the column chunks g, g+NG, ... with g = ew / 4, so two
   // warps per SM sub-partition interleave and hide each other's TMEM-load / store latency.
   static_assert(TG == 1 || (NG == 1 && NACC == TG), "tile groups own one accumulator stage each");
+  static_assert(!P2 || TG == 1, "CTA pairs split columns, not tiles");
   const int e = ew & 3, g = (TG > 1) ? 0 : (ew >> 2), tg = (TG > 1) ? (ew >> 2) : 0;
+  const uint32_t tempty_leader0 = P2 ? mapa_shared(tempty_bar0, 0) : 0u;
+  const int t0 = P2 ? (int)(blockIdx.x >> 1) : (int)(blockIdx.x + tg * gridDim.x);
+  const int tstride = P2 ? (int)(gridDim.x >> 1) : (int)(TG * gridDim.x);
   const int hl = (32 * e + lane) / TW;
   const int wl = (32 * e + lane) % TW;
   const int halo = p.halo;
@@ -179,18 +190,18 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
   int as = tg;
   uint32_t aphase = 0;
   TileCursor cur;
-  cur.init(p, blockIdx.x + tg * gridDim.x, TG * gridDim.x);
+  cur.init(p, t0, tstride, P2 ? 2 : 1, rank);
   long long dbg_wait = 0;
   const long long dbg_t0 = clock64();
-  for (int tile = blockIdx.x + tg * gridDim.x; tile < p.num_tiles; tile += TG * gridDim.x, cur.next()) {
+  for (int tile = t0; tile < p.num_tiles; tile += tstride, cur.next()) {
     const int nb = cur.nb, twi = cur.twi, thi = cur.thi, n = cur.n;
     const int h = thi * TH + hl, w = twi * TW + wl;
-    const bool in_img = (h < p.H) && (w < p.W);
+    const bool in_img = (h < p.H) && (w < p.W) && (!P2 || n < p.N);   // an odd tile count leaves rank 1 a phantom tile
 
     int rows[4], cols[4], nr = 0, nc = 0;
     bool owner;
     if (EPI == AST_EPI_POOL2) {
-      owner = ((hl & 1) == 0) && ((wl & 1) == 0) && ((h >> 1) < p.Ho) && ((w >> 1) < p.Wo);
+      owner = ((hl & 1) == 0) && ((wl & 1) == 0) && ((h >> 1) < p.Ho) && ((w >> 1) < p.Wo) && (!P2 || n < p.N);
     } else {
       owner = in_img;
     }
@@ -291,7 +302,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar0 + 8u * as);
+    if (lane == 0) {
+      if (P2) mbar_arrive_cluster(tempty_leader0 + 8u * as);
+      else mbar_arrive(tempty_bar0 + 8u * as);
+    }
     if (TG > 1) aphase ^= 1u;
     else if (++as == NACC) { as = 0; aphase ^= 1u; }
   }
@@ -715,6 +729,7 @@ static int launch_tc_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB
 }
 
 #include "conv_fold.cuh"
+#include "conv_pair.cuh"
 
 bool tc_supported(const ast_conv_desc* d) {
   return d->Cin % 64 == 0 && d->Cout % 64 == 0 && d->H >= 2 && d->W >= 2;
@@ -753,7 +768,9 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   int impl = d->impl;
   int kwbox = 1;
   if (impl == AST_CONV_TC_TAPBOX) { kwbox = 0; impl = AST_CONV_TC; }
-  if (impl >= 1000) { kwbox = 0; impl -= 1000; }
+  bool pair_forced = false;
+  if (impl >= 2000) { pair_forced = true; impl -= 2000; }
+  else if (impl >= 1000) { kwbox = 0; impl -= 1000; }
   ConvParams p = {};
   static const int dbg_flags = getenv("AST_CONV_DBGFLAGS") ? atoi(getenv("AST_CONV_DBGFLAGS")) : 0;
   p.dbg_flags = dbg_flags;
@@ -799,18 +816,26 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   // N-block: the widest that still gives every SM a tile (a wide N amortises the A-operand
   // shared-memory reads of each MMA); narrow blocks only when the problem is small.
   const int64_t sp_tiles = (int64_t)d->N * p.tiles_h * p.tiles_w;
+
+  // CTA pairs (conv_pair.cuh): the default for the kw-box kernel once there are at least two spatial tiles.
+  // AST_CONV_PAIR=0 keeps the one-CTA kernel (A/B reference); impl 2064 / 2128 / 2256 force the pair kernel's N block.
+  static const int pair_env = getenv("AST_CONV_PAIR") ? atoi(getenv("AST_CONV_PAIR")) : 1;
+  const bool pair = kwbox && sp_tiles >= 2 &&
+                    (pair_forced || (pair_env && (impl == AST_CONV_AUTO || impl == AST_CONV_TC)));
+  const int64_t sp_units = pair ? (sp_tiles + 1) / 2 : sp_tiles;      // work units per n-block: tile pairs or tiles
+  const int units_wanted = pair ? sm_count / 2 : sm_count;
   int BN = 64;
-  if (d->Cout % 256 == 0 && sp_tiles * (d->Cout / 256) >= sm_count) BN = 256;
-  else if (d->Cout % 128 == 0 && sp_tiles * (d->Cout / 128) >= sm_count) BN = 128;
+  if (d->Cout % 256 == 0 && sp_units * (d->Cout / 256) >= units_wanted) BN = 256;
+  else if (d->Cout % 128 == 0 && sp_units * (d->Cout / 128) >= units_wanted) BN = 128;
   if (impl >= 64 && impl <= 256 && d->Cout % impl == 0) BN = impl;  // tuning override
   if (BN != 64 && BN != 128 && BN != 256) return AST_E_SHAPE;
   p.n_blocks = d->Cout / BN;
-  const int64_t nt = sp_tiles * p.n_blocks;
+  const int64_t nt = sp_units * p.n_blocks;
   if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
-  p.num_tiles = (int)nt;
+  p.num_tiles = (int)nt;     // pair kernel: counts tile PAIRS x n-blocks
 
   CUtensorMap tmA, tmB;
-  r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, BN, kwbox);
+  r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, pair ? BN / 2 : BN, kwbox);
   if (r) return r;
   static const bool dbg_on = getenv("AST_CONV_DEBUG") != nullptr;
   long long* dbg = nullptr;
@@ -820,24 +845,39 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
     p.dbg = dbg;
   }
   struct DbgDump {
-    long long* d; int n; const ConvParams& p; int BN; cudaStream_t s;
+    long long* d; int n; const ConvParams& p; int BN; cudaStream_t s; bool pair;
     ~DbgDump() {
       if (!d) return;
       cudaStreamSynchronize(s);
       long long* h = new long long[8 * n];
       cudaMemcpy(h, d, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
       double a[8] = {0};
-      const int g = p.num_tiles < n ? p.num_tiles : n;
-      for (int i = 0; i < g; ++i) for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / g;
+      // pair kernel: one work unit per CTA pair; the MMA counters exist in the leader (even CTAs) only
+      const int units = pair ? n / 2 : n;
+      const int g = p.num_tiles < units ? p.num_tiles : units;
+      const int ctas = pair ? 2 * g : g;
+      for (int i = 0; i < ctas; ++i)
+        for (int j = 0; j < 8; ++j) {
+          const bool leader_only = pair && (j == 2 || j == 3 || j == 6);
+          if (leader_only && (i & 1)) continue;
+          a[j] += (double)h[i * 8 + j] / (leader_only ? g : ctas);
+        }
       const double tiles = (double)p.num_tiles / g;
-      fprintf(stderr, "[conv dbg] Cin=%d Cout=%d H=%d BN=%d tiles/CTA=%.1f | per tile cycles: loop(mma)=%.0f loop(epi)=%.0f | "
+      fprintf(stderr, "[conv dbg] %sCin=%d Cout=%d H=%d BN=%d tiles/CTA=%.1f | per tile cycles: loop(mma)=%.0f loop(epi)=%.0f | "
               "producer wait A-empty=%.0f B-empty=%.0f | mma wait operands=%.0f accumulator=%.0f | epilogue wait tfull=%.0f\n",
-              p.Cin, p.Cout, p.H, BN, tiles, a[6] / tiles, a[5] / tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles,
+              pair ? "PAIR " : "", p.Cin, p.Cout, p.H, BN, tiles, a[6] / tiles, a[5] / tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles,
               a[3] / tiles, a[4] / tiles);
       delete[] h;
       cudaFree(d);
     }
-  } dump{dbg, sm_count, p, BN, s};
+  } dump{dbg, sm_count, p, BN, s, pair};
+  if (pair) {
+    switch (BN) {
+      case 256: return launch_pair_epi<256>(d->epilogue, tmA, tmB, p, sm_count, s);
+      case 128: return launch_pair_epi<128>(d->epilogue, tmA, tmB, p, sm_count, s);
+      default: return launch_pair_epi<64>(d->epilogue, tmA, tmB, p, sm_count, s);
+    }
+  }
   if (kwbox) {
     switch (BN) {
       case 256: return launch_tc2_epi<256>(d->epilogue, tmA, tmB, p, sm_count, s);

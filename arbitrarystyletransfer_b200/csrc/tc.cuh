@@ -192,6 +192,80 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of one TPC run ONE M = 256 tcgen05.mma --------
+// Each CTA holds its own 128 rows of A, HALF of the B tile (N/2 rows) and its own 128 x N accumulator in TMEM; only
+// the leader (cluster rank 0) issues MMAs and commits.  Per SM and instruction the shared-memory operand read drops
+// from (128 + N) to (128 + N/2) rows of 32 B, and every per-instruction cost (issue, commit) is paid once per 256 rows.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier of any CTA of the cluster (`bar` = shared::cluster address from mapa_shared).  Default
+// semantics (.release.cta) on purpose: a .release.cluster arrive makes the warp wait until its outstanding GLOBAL stores
+// are visible cluster-wide (measured: the conv epilogue's busy time per tile doubled); what the consumer of these
+// barriers needs ordered are tcgen05.ld reads, and tcgen05.fence::before_thread_sync does that.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// TMA loads into THIS CTA's shared memory whose completion bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t leader_bar,
+                                                int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t leader_bar,
+                                                int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// one warp of EACH CTA of the pair executes these
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem_addr) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem_addr), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (256 rows: 128 per CTA) * B (N rows: N/2 per CTA); leader only
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at offset `bar` in BOTH CTAs once all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
 // ---- descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor for a K-major operand tile stored as rows of 64 bf16 (128 B)
 // with the 128-byte swizzle TMA applies (CU_TENSOR_MAP_SWIZZLE_128B): 8-row x 128 B swizzle atoms
