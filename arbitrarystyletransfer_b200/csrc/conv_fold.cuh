@@ -44,9 +44,9 @@ __device__ __forceinline__ void fold_parities(int pg, int& py0, int& npy, int& p
   else { py0 = pg >> 1; npy = 1; px0 = pg & 1; npx = 1; }
 }
 
-template <int BN, int NG>
+template <int BN, int NG, bool P2 = false>
 __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
-                                              uint32_t tfull_bar0, uint32_t tempty_bar0) {
+                                              uint32_t tfull_bar0, uint32_t tempty_bar0, int rank = 0) {
   using C = CfgF<BN>;
   constexpr int CH = 32, NCH = C::ACC_COLS / CH;
   const int e = ew & 3, g = ew >> 2;
@@ -54,12 +54,15 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
   const bool wide_st = (reinterpret_cast<uintptr_t>(p.out) & 31u) == 0 && (p.Cout % 16) == 0;
   int as = 0;
   uint32_t aphase = 0;
+  const uint32_t tempty_leader0 = P2 ? mapa_shared(tempty_bar0, 0) : 0u;
+  const int t0 = P2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstride = P2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   TileCursor cur;
-  cur.init(p, blockIdx.x, gridDim.x);
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, cur.next()) {
+  cur.init(p, t0, tstride, P2 ? 2 : 1, rank);
+  for (int tile = t0; tile < p.num_tiles; tile += tstride, cur.next()) {
     const int cob = cur.nb / C::NPG, pg = cur.nb % C::NPG, n = cur.n;
     const int h = cur.thi * T2_H + hl, w = cur.twi * T2_W + wl;
-    const bool in_img = (h < p.H) && (w < p.W);
+    const bool in_img = (h < p.H) && (w < p.W) && (!P2 || n < p.N);
     int py0, npy, px0, npx;
     fold_parities<C::NPAR>(pg, py0, npy, px0, npx);
     if (p.epi_sleep_ns) mbar_wait_sleep(tfull_bar0 + 8u * as, aphase, p.epi_sleep_ns); else mbar_wait(tfull_bar0 + 8u * as, aphase);
@@ -117,7 +120,10 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar0 + 8u * as);
+    if (lane == 0) {
+      if (P2) mbar_arrive_cluster(tempty_leader0 + 8u * as);
+      else mbar_arrive(tempty_bar0 + 8u * as);
+    }
     if (++as == C::NACC) { as = 0; aphase ^= 1u; }
   }
 }
@@ -324,6 +330,245 @@ static int launch_fold(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   }
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
   kern<<<grid, Epi2<BN>::THREADS, C::SMEM_BYTES, s>>>(tmA, tmB, p);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same folded convolution on CTA PAIRS (tcgen05.mma.cta_group::2; protocol: conv_pair.cuh).  Each CTA of a pair
+// takes one low-res spatial tile (16 x 8 pixels), both run the same cout block and parity group, and each holds
+// half of every weight tile (BN/2 rows), so the weight ring holds twice as many groups in the same shared memory.
+template <int BN>
+struct CfgFP {
+  static constexpr int NPAR = CfgF<BN>::NPAR, NPG = CfgF<BN>::NPG;
+  static constexpr int HB = BN / 2;
+  static constexpr int B_BYTES = HB * KBLK * 2;
+  static constexpr int NA = 4;
+  static constexpr int GSLOTS = 2 * NPAR;
+  static constexpr int NBG = 4;
+  static constexpr int NACC = 2;
+  static constexpr int ACC_COLS = 256;
+  static constexpr int NBAR = 2 * NA + 2 * NBG + 2 * NACC;
+  static constexpr int SMEM_BYTES = NA * A2_BYTES + NBG * GSLOTS * B_BYTES + NBAR * 8 + 16 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(Epi2<BN>::THREADS, 1)
+conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const ConvParams p) {
+  using C = CfgFP<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + C::NA * A2_BYTES;
+  constexpr int B_REGION = C::NBG * C::GSLOTS * C::B_BYTES;
+  const uint32_t bars = b_base + B_REGION;
+  auto afull = [&](int s) { return bars + 8u * s; };
+  auto aempty = [&](int s) { return bars + 8u * (C::NA + s); };
+  auto bfull = [&](int s) { return bars + 8u * (2 * C::NA + s); };
+  auto bempty = [&](int s) { return bars + 8u * (2 * C::NA + C::NBG + s); };
+  auto tfull = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NBG + s); };
+  auto tempty = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NBG + C::NACC + s); };
+  const uint32_t tmem_slot = bars + 8u * C::NBAR;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + C::NA * A2_BYTES + B_REGION + 8 * C::NBAR);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair0 = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  const int cblocks = p.Cin / KBLK;
+  // BN = 64, Cin = Cout = 64: all sixteen half weight tiles (64 KB) fit the ring's space and stay resident
+  const bool resident = (BN == 64) && cblocks == 1 && p.Cout == BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < C::NBG; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 2 * 4 * Epi2<BN>::NG); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t afull_l = mapa_shared(afull(0), 0), bfull_l = mapa_shared(bfull(0), 0);
+      if (resident) {
+        if (rank == 0) mbar_expect_tx(bfull(0), 2 * 16 * C::B_BYTES);
+        for (int t = 0; t < 16; ++t) tma_load_3d_2sm(b_base + t * C::B_BYTES, &tmB, bfull_l, 0, rank * C::HB, t);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int q = pair0; q < p.num_tiles; q += npairs) {
+        int t = q;
+        const int nb = t % p.n_blocks; t = 2 * (t / p.n_blocks) + rank;
+        const int twi = t % p.tiles_w; t /= p.tiles_w;
+        const int thi = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        const int cob = nb / C::NPG, pg = nb % C::NPG;
+        int py0, npy, px0, npx;
+        fold_parities<C::NPAR>(pg, py0, npy, px0, npx);
+        const int h0 = thi * T2_H, w0 = twi * T2_W;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          for (int kw = px0; kw <= px0 + npx; ++kw) {
+            if (p.prod_sleep_ns) mbar_wait_sleep(aempty(sa), pa ^ 1u, p.prod_sleep_ns); else mbar_wait(aempty(sa), pa ^ 1u);
+            if (rank == 0) mbar_expect_tx(afull(sa), 2 * A2_BYTES);
+            tma_load_4d_2sm(a_base + sa * A2_BYTES, &tmA, afull_l + 8u * sa, cb * KBLK, w0 + kw, h0, n);
+            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            if (!resident) {
+              int cnt = 0;
+              for (int py = py0; py < py0 + npy; ++py)
+                for (int px = px0; px < px0 + npx; ++px)
+                  if (kw - px >= 0 && kw - px <= 1) cnt += 2;
+              if (p.prod_sleep_ns) mbar_wait_sleep(bempty(sb), pb ^ 1u, p.prod_sleep_ns); else mbar_wait(bempty(sb), pb ^ 1u);
+              if (rank == 0) mbar_expect_tx(bfull(sb), 2 * cnt * C::B_BYTES);
+              int slot = 0;
+              for (int py = py0; py < py0 + npy; ++py)
+                for (int px = px0; px < px0 + npx; ++px) {
+                  const int b = kw - px;
+                  if (b < 0 || b > 1) continue;
+                  for (int a = 0; a < 2; ++a) {
+                    tma_load_3d_2sm(b_base + (sb * C::GSLOTS + slot) * C::B_BYTES, &tmB, bfull_l + 8u * sb, cb * KBLK,
+                                    cob * BN + rank * C::HB, ((py * 2 + px) * 2 + a) * 2 + b);
+                    ++slot;
+                  }
+                }
+              if (++sb == C::NBG) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+      }
+      for (int i = 0; i < C::NA; ++i) {       // drain the multicast releases aimed at this CTA
+        mbar_wait(aempty(sa), pa ^ 1u);
+        if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+      }
+      if (!resident) {
+        for (int i = 0; i < C::NBG; ++i) {
+          mbar_wait(bempty(sb), pb ^ 1u);
+          if (++sb == C::NBG) { sb = 0; pb ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, BN);
+      const uint64_t a_desc0 = make_sdesc_k128(a_base);
+      const uint64_t b_desc0 = make_sdesc_k128(b_base);
+      constexpr uint64_t A_SLOT16 = A2_BYTES >> 4, B_SLOT16 = C::B_BYTES >> 4, KH16 = (T2_W * KBLK * 2) >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      bool b_ready = false;
+      for (int q = pair0; q < p.num_tiles; q += npairs) {
+        const int nb = q % p.n_blocks;
+        const int pg = nb % C::NPG;
+        int py0, npy, px0, npx;
+        fold_parities<C::NPAR>(pg, py0, npy, px0, npx);
+        mbar_wait(tempty(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tile = tmem_base + (uint32_t)(as * C::ACC_COLS);
+        uint32_t started = 0;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          for (int kw = px0; kw <= px0 + npx; ++kw) {
+            mbar_wait(afull(sa), pa);
+            if (resident) {
+              if (!b_ready) { mbar_wait(bfull(0), 0u); b_ready = true; }
+            } else {
+              mbar_wait(bfull(sb), pb);
+            }
+            tc_fence_after();
+            const uint64_t ad = a_desc0 + (uint64_t)sa * A_SLOT16;
+            if (elect_one_sync()) {
+              int slot = 0;
+              for (int iy = 0; iy < npy; ++iy) {
+                for (int ix = 0; ix < npx; ++ix) {
+                  const int py = py0 + iy, px = px0 + ix;
+                  const int b = kw - px;
+                  if (b < 0 || b > 1) continue;
+                  const int j = iy * npx + ix;
+                  const uint32_t d_tmem = d_tile + (uint32_t)(j * BN);
+#pragma unroll
+                  for (int a = 0; a < 2; ++a) {
+                    const int kh = py + a;
+                    const int bs = resident ? (((py * 2 + px) * 2 + a) * 2 + b) : (sb * C::GSLOTS + slot);
+                    const uint64_t bd = b_desc0 + (uint64_t)bs * B_SLOT16;
+#pragma unroll
+                    for (int k = 0; k < KBLK / 16; ++k) {
+                      umma_bf16_2sm(d_tmem, ad + (uint64_t)(kh * KH16 + k * 2), bd + (uint64_t)(k * 2), idesc,
+                                    (a | k) ? 1u : ((started >> j) & 1u));
+                    }
+                    ++slot;
+                  }
+                  started |= 1u << j;
+                }
+              }
+              if (!resident) umma_commit_2sm(bempty(sb));
+              umma_commit_2sm(aempty(sa));
+            }
+            __syncwarp();
+            for (int iy = 0; iy < npy; ++iy)
+              for (int ix = 0; ix < npx; ++ix)
+                if (kw - (px0 + ix) >= 0 && kw - (px0 + ix) <= 1) started |= 1u << (iy * npx + ix);
+            if (!resident) {
+              if (++sb == C::NBG) { sb = 0; pb ^= 1u; }
+            }
+            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+          }
+        }
+        if (elect_one_sync()) umma_commit_2sm(tfull(as));
+        __syncwarp();
+        if (++as == C::NACC) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    epilogue_fold<BN, Epi2<BN>::NG, true>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0), rank);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_fold_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count,
+                            cudaStream_t s) {
+  using C = CfgFP<BN>;
+  auto kern = conv3x3_fold_pair_kernel<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int max_pairs = sm_count / 2;
+  const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(Epi2<BN>::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AST_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   AST_CHECK_LAUNCH();
   return 0;
 }

@@ -24,15 +24,37 @@ template <int BN>
 struct CfgP {
   static constexpr int HB = BN / 2;                       // weight rows per CTA
   static constexpr int B_BYTES = HB * KBLK * 2;           // per tap and CTA
-  static constexpr int NA = (BN == 64) ? 8 : (BN == 128 ? 6 : 4);
-  static constexpr int NB = 9;                            // three groups (one per kw) of three taps (kh)
+  static constexpr int NA_MAX = 8;                        // A ring slots (p.na of them are used)
   static constexpr int NACC = (BN <= 128) ? 4 : 2;
   static constexpr int TMEM_COLS = NACC * BN;
-  static constexpr int NBAR = 2 * NA + 2 * 3 + 2 * NACC;
-  static constexpr int SMEM_BYTES = NA * A2_BYTES + NB * B_BYTES + NBAR * 8 + 16 + 1024;
+  static constexpr int NBAR = 2 * NA_MAX + 2 * 3 + 2 * NACC;
+  static constexpr int SMEM_BUDGET = 226 * 1024;          // of the 227 KB a CTA may have
+  static constexpr int smem_bytes(int na, int nbs) { return na * A2_BYTES + nbs * B_BYTES + NBAR * 8 + 16 + 1024; }
 };
 
-template <int BN, int EPI>
+// Shared-memory plan of one launch: weight slots (9 = a ring of three kw groups; 9 * Cin/64 = the layer's whole half
+// weight tile stays RESIDENT, loaded once per CTA) and A ring depth.  Re-streaming the weights for every tile costs
+// 9 * Cin * BN bytes of L2 -> SM traffic per tile and CTA; with Cin = 128 that made the 128-channel layers
+// operand-supply bound (the chip-wide L2 cap is ~6300 B/clk = 42 B/clk per SM: guide B300_MICROARCH.md "LTS cap";
+// measured here: the MMA warp waited for operands 53 % of the time at 42 B/clk per SM).
+template <int BN>
+static void pair_plan(int cblocks, int n_blocks, int* na, int* nbs) {
+  using C = CfgP<BN>;
+  const int res_slots = 9 * cblocks;
+  int a = (C::SMEM_BUDGET - C::smem_bytes(0, res_slots)) / A2_BYTES;
+  if (n_blocks == 1 && a >= 4) {
+    *nbs = res_slots;
+    *na = a < C::NA_MAX ? a : C::NA_MAX;
+    return;
+  }
+  *nbs = 9;
+  a = (C::SMEM_BUDGET - C::smem_bytes(0, 9)) / A2_BYTES;
+  *na = a < C::NA_MAX ? a : C::NA_MAX;
+}
+
+// TG: tile sets of the epilogue (epilogue_loop): the 4 * Epi2<BN>::NG epilogue warps work as TG sets on different
+// tiles, Epi2<BN>::NG / TG column groups each.
+template <int BN, int EPI, int TG>
 __global__ void __launch_bounds__(Epi2<BN>::THREADS, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const ConvParams p) {
@@ -41,34 +63,35 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
+  const int NA = p.na;
   const uint32_t a_base = base;
-  const uint32_t b_base = base + C::NA * A2_BYTES;
-  const uint32_t bars = b_base + C::NB * C::B_BYTES;
+  const uint32_t b_base = base + NA * A2_BYTES;
+  const uint32_t bars = b_base + p.nbs * C::B_BYTES;
   auto afull = [&](int s) { return bars + 8u * s; };
-  auto aempty = [&](int s) { return bars + 8u * (C::NA + s); };
-  auto bfull = [&](int s) { return bars + 8u * (2 * C::NA + s); };
-  auto bempty = [&](int s) { return bars + 8u * (2 * C::NA + 3 + s); };
-  auto tfull = [&](int s) { return bars + 8u * (2 * C::NA + 6 + s); };
-  auto tempty = [&](int s) { return bars + 8u * (2 * C::NA + 6 + C::NACC + s); };
+  auto aempty = [&](int s) { return bars + 8u * (C::NA_MAX + s); };
+  auto bfull = [&](int s) { return bars + 8u * (2 * C::NA_MAX + s); };
+  auto bempty = [&](int s) { return bars + 8u * (2 * C::NA_MAX + 3 + s); };
+  auto tfull = [&](int s) { return bars + 8u * (2 * C::NA_MAX + 6 + s); };
+  auto tempty = [&](int s) { return bars + 8u * (2 * C::NA_MAX + 6 + C::NACC + s); };
   const uint32_t tmem_slot = bars + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      smem + C::NA * A2_BYTES + C::NB * C::B_BYTES + 8 * C::NBAR);
+      smem + NA * A2_BYTES + p.nbs * C::B_BYTES + 8 * C::NBAR);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const int pair0 = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
   const int cblocks = p.Cin / KBLK;
-  const bool resident = cblocks == 1 && p.n_blocks == 1;
+  const bool resident = p.nbs == 9 * cblocks && p.n_blocks == 1;   // pair_plan
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < 3; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 2 * 4 * Epi2<BN>::NG); }
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 2 * 4 * (Epi2<BN>::NG / TG)); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
@@ -82,11 +105,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       const uint32_t afull_l = mapa_shared(afull(0), 0), bfull_l = mapa_shared(bfull(0), 0);
       if (resident) {
-        for (int kw = 0; kw < 3; ++kw) {
-          if (rank == 0) mbar_expect_tx(bfull(kw), 2 * 3 * C::B_BYTES);
-          for (int kh = 0; kh < 3; ++kh)
-            tma_load_3d_2sm(b_base + (kw * 3 + kh) * C::B_BYTES, &tmB, bfull_l + 8u * kw, 0, rank * C::HB, kh * 3 + kw);
-        }
+        // slot of (cb, kw, kh) = (cb * 3 + kw) * 3 + kh; one barrier for the lot
+        if (rank == 0) mbar_expect_tx(bfull(0), 2 * p.nbs * C::B_BYTES);
+        for (int cb = 0; cb < cblocks; ++cb)
+          for (int kw = 0; kw < 3; ++kw)
+            for (int kh = 0; kh < 3; ++kh)
+              tma_load_3d_2sm(b_base + ((cb * 3 + kw) * 3 + kh) * C::B_BYTES, &tmB, bfull_l, cb * KBLK, rank * C::HB,
+                              kh * 3 + kw);
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -103,7 +128,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa, p.prod_sleep_ns);
             if (rank == 0) mbar_expect_tx(afull(sa), 2 * A2_BYTES);
             tma_load_4d_2sm(a_base + sa * A2_BYTES, &tmA, afull_l + 8u * sa, cb * KBLK, w0 + kw, h0, n);
-            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            if (++sa == NA) { sa = 0; pa ^= 1u; }
             if (!resident) {
               mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb, p.prod_sleep_ns);
               if (rank == 0) mbar_expect_tx(bfull(sb), 2 * 3 * C::B_BYTES);
@@ -117,9 +142,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_pa; p.dbg[blockIdx.x * 8 + 1] = dbg_pb; }
       // drain: every multicast release aimed at this CTA has landed before it may exit
-      for (int i = 0; i < C::NA; ++i) {
+      for (int i = 0; i < NA; ++i) {
         mbar_wait(aempty(sa), pa ^ 1u);
-        if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+        if (++sa == NA) { sa = 0; pa ^= 1u; }
       }
       if (!resident) {
         for (int i = 0; i < 3; ++i) {
@@ -155,8 +180,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t ad = a_desc0 + (uint64_t)sa * A_SLOT16;
             int grp;
             if (resident) {
-              grp = kw;
-              if (!b_resident_ready) mbar_wait(bfull(kw), 0u);  // first tile only
+              grp = cb * 3 + kw;
+              if (!b_resident_ready) { mbar_wait(bfull(0), 0u); b_resident_ready = true; }  // first tile only
             } else {
               grp = sb;
               mbar_wait_acc(bfull(sb), pb, dbg, dbg_mb);
@@ -180,10 +205,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (!resident) {
               if (++sb == 3) { sb = 0; pb ^= 1u; }
             }
-            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            if (++sa == NA) { sa = 0; pa ^= 1u; }
           }
         }
-        b_resident_ready = true;
         if (elect_one_sync()) umma_commit_2sm(tfull(as));
         __syncwarp();
         if (++as == C::NACC) { as = 0; aphase ^= 1u; }
@@ -195,7 +219,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    epilogue_loop<BN, EPI, T2_W, Epi2<BN>::NG, C::NACC, 1, true>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0), rank);
+    epilogue_loop<BN, EPI, T2_W, Epi2<BN>::NG / TG, C::NACC, TG, true>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0), rank);
   }
 
   tc_fence_before();
@@ -206,22 +230,23 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int EPI>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count,
-                       cudaStream_t s) {
+template <int BN, int EPI, int TG>
+static int launch_pair_tg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count,
+                          cudaStream_t s) {
   using C = CfgP<BN>;
-  auto kern = conv3x3_pair_kernel<BN, EPI>;
+  auto kern = conv3x3_pair_kernel<BN, EPI, TG>;
   static bool attr_done = false;
   if (!attr_done) {
-    AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BUDGET));
     attr_done = true;
   }
+  const int smem_bytes = C::smem_bytes(p.na, p.nbs);
   const int max_pairs = sm_count / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs, 1, 1);
   cfg.blockDim = dim3(Epi2<BN>::THREADS, 1, 1);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -235,9 +260,24 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   return 0;
 }
 
+template <int BN, int EPI>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count,
+                       cudaStream_t s) {
+  static const int tg_env = getenv("AST_CONV_TG") ? atoi(getenv("AST_CONV_TG")) : 0;   // tuning override
+  int tg = tg_env ? tg_env : 1;
+  if constexpr (BN <= 128) {
+    if (tg == 4) return launch_pair_tg<BN, EPI, 4>(tmA, tmB, p, sm_count, s);
+    if (tg == 2) return launch_pair_tg<BN, EPI, 2>(tmA, tmB, p, sm_count, s);
+  } else {
+    if (tg >= 2) return launch_pair_tg<BN, EPI, 2>(tmA, tmB, p, sm_count, s);
+  }
+  return launch_pair_tg<BN, EPI, 1>(tmA, tmB, p, sm_count, s);
+}
+
 template <int BN>
-static int launch_pair_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
+static int launch_pair_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, ConvParams p,
                            int sm_count, cudaStream_t s) {
+  pair_plan<BN>(p.Cin / KBLK, p.n_blocks, &p.na, &p.nbs);
   switch (epi) {
     case AST_EPI_PLAIN: return launch_pair<BN, AST_EPI_PLAIN>(tmA, tmB, p, sm_count, s);
     case AST_EPI_POOL2: return launch_pair<BN, AST_EPI_POOL2>(tmA, tmB, p, sm_count, s);

@@ -81,6 +81,7 @@ struct ConvParams {
   int clamp01;       // EPI_NCHW32 only: Hardtanh(0,1) (models.py:304, 315)
   long long* dbg;    // optional [gridDim.x][8] wait-cycle counters per role (AST_CONV_DEBUG=1)
   uint32_t epi_sleep_ns, prod_sleep_ns;   // back-off of the waiting roles (mbar_wait_sleep); 0 = tight polling
+  int na, nbs;       // CTA-pair kernels: A ring slots and weight slots of this launch (pair_plan)
   int dbg_flags;     // AST_CONV_DBGFLAGS (bottleneck elimination, results are WRONG): 1 = operands loaded once per ring
                      // slot, never refreshed; 2 = epilogue without global stores; 4 = epilogue without TMEM loads
 };
@@ -163,31 +164,33 @@ __device__ __forceinline__ int out_targets(int x, int Xo, int halo, int (&t)[4])
 // Epilogue warps (4 per CTA; warp e may touch TMEM lanes [32e, 32e+32) = tile rows 2e, 2e+1):
 // tcgen05.ld -> +bias -> (tap) -> ReLU -> (tap) -> bf16 -> {plain | 2x2 max-pool | nearest x2} store
 // with the optional reflection halo, or the fp32 NCHW image for the last decoder layer.
-// TG > 1 (tile groups, requires NG == 1 and NACC == TG): instead of splitting every tile's columns over the warp
-// groups, group tg = ew / 4 takes every TG-th tile whole and owns accumulator stage tg -- TG tiles are in the
-// epilogue at once, which is what a layer whose work IS the epilogue (conv1_1) needs.
+// The 4 * NG * TG epilogue warps form NG * TG groups of four (one warp per TMEM lane quarter).  NG groups split a
+// tile's COLUMNS; TG sets of them work on DIFFERENT tiles at once (set tg takes the CTA's tiles tg, tg + TG, ... and
+// so the accumulator stages (tg + k TG) mod NACC): a tile's epilogue is one warp's latency chain (barrier ->
+// tcgen05.ld -> bias -> pack -> stores -> release), and with TG = 1 only one tile is in that chain at a time however
+// many warps share it -- the limit for conv1_1 (whose work IS the epilogue) and, once CTA pairs had made the MMAs
+// cheap, for the 64- and 128-channel layers.
 // P2 (CTA pair, conv_pair.cuh): the work index counts tile pairs, this CTA takes spatial tile 2 * pair + rank, and the
 // accumulator is handed back on the LEADER's tempty barrier (a remote arrive for rank 1).
 template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2, int TG = 1, bool P2 = false>
 __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
                                               uint32_t tfull_bar0, uint32_t tempty_bar0, int rank = 0) {
-  constexpr int CH = (TG > 1) ? 16 : ((BN >= 32 && BN / 32 >= NG) ? 32 : 16);  // columns per tcgen05.ld
+  constexpr int CH = (TG > 1 && BN <= 64) ? 16 : ((BN >= 32 && BN / 32 >= NG) ? 32 : 16);  // columns per tcgen05.ld
   constexpr int TH = TILE_M / TW;         // tile = TH rows x TW cols of pixels, row-major in M
   constexpr int NCH = BN / CH;
-  // 4*NG epilogue warps: warp ew owns TMEM lane quarter e = ew % 4 (hardware rule: a warp may only
-  // touch lanes [32*(warp%4), +32)) and the column chunks g, g+NG, ... with g = ew / 4, so two
-  // warps per SM sub-partition interleave and hide each other's TMEM-load / store latency.
-  static_assert(TG == 1 || (NG == 1 && NACC == TG), "tile groups own one accumulator stage each");
-  static_assert(!P2 || TG == 1, "CTA pairs split columns, not tiles");
-  const int e = ew & 3, g = (TG > 1) ? 0 : (ew >> 2), tg = (TG > 1) ? (ew >> 2) : 0;
+  // warp ew owns TMEM lane quarter e = ew % 4 (hardware rule: a warp may only touch lanes [32*(warp%4), +32)) and,
+  // inside its tile set, the column chunks g, g+NG, ...
+  static_assert(NACC % TG == 0 && (NACC & (NACC - 1)) == 0, "stages are handed round-robin to the tile sets");
+  const int e = ew & 3, g = (ew >> 2) % NG, tg = (ew >> 2) / NG;
   const uint32_t tempty_leader0 = P2 ? mapa_shared(tempty_bar0, 0) : 0u;
-  const int t0 = P2 ? (int)(blockIdx.x >> 1) : (int)(blockIdx.x + tg * gridDim.x);
-  const int tstride = P2 ? (int)(gridDim.x >> 1) : (int)(TG * gridDim.x);
+  const int units = P2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;          // CTAs or CTA pairs
+  const int t0 = (P2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) + tg * units;
+  const int tstride = TG * units;
   const int hl = (32 * e + lane) / TW;
   const int wl = (32 * e + lane) % TW;
   const int halo = p.halo;
   const bool wide_st = (reinterpret_cast<uintptr_t>(p.out) & 31u) == 0 && (p.Cout % 16) == 0;
-  int as = tg;
+  int as = tg % NACC;
   uint32_t aphase = 0;
   TileCursor cur;
   cur.init(p, t0, tstride, P2 ? 2 : 1, rank);
@@ -306,8 +309,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
       if (P2) mbar_arrive_cluster(tempty_leader0 + 8u * as);
       else mbar_arrive(tempty_bar0 + 8u * as);
     }
-    if (TG > 1) aphase ^= 1u;
-    else if (++as == NACC) { as = 0; aphase ^= 1u; }
+    as += TG;
+    if (as >= NACC) { as -= NACC; aphase ^= 1u; }
   }
   if (p.dbg && ew == 0 && lane == 0) {
     p.dbg[blockIdx.x * 8 + 4] = dbg_wait;               // epilogue warp 0: waiting for an accumulator
@@ -796,12 +799,21 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
     if (impl >= 64 && impl <= 256 && d->Cout % impl == 0) BN = impl;
     if (BN != 64 && BN != 128 && BN != 256) return AST_E_SHAPE;
     p.n_blocks = (4 / (256 / BN)) * (d->Cout / BN);
-    const int64_t nt = sp * p.n_blocks;
+    static const int pair_env_f = getenv("AST_CONV_PAIR") ? atoi(getenv("AST_CONV_PAIR")) : 1;
+    const bool pair_f = (pair_forced || pair_env_f) && sp >= 2;
+    const int64_t nt = (pair_f ? (sp + 1) / 2 : sp) * p.n_blocks;
     if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
     p.num_tiles = (int)nt;
     CUtensorMap tmA, tmB;
-    r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, BN, 1, 16);
+    r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, pair_f ? BN / 2 : BN, 1, 16);
     if (r) return r;
+    if (pair_f) {
+      switch (BN) {
+        case 256: return launch_fold_pair<256>(tmA, tmB, p, sm_count, s);
+        case 128: return launch_fold_pair<128>(tmA, tmB, p, sm_count, s);
+        default: return launch_fold_pair<64>(tmA, tmB, p, sm_count, s);
+      }
+    }
     switch (BN) {
       case 256: return launch_fold<256>(tmA, tmB, p, sm_count, s);
       case 128: return launch_fold<128>(tmA, tmB, p, sm_count, s);
