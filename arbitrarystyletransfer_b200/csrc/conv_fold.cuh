@@ -343,13 +343,13 @@ struct CfgFP {
   static constexpr int NPAR = CfgF<BN>::NPAR, NPG = CfgF<BN>::NPG;
   static constexpr int HB = BN / 2;
   static constexpr int B_BYTES = HB * KBLK * 2;
-  static constexpr int NA = 4;
+  static constexpr int NA = 3;                     // single {64, 10, 18} boxes (conv_pair.cuh), one per (tile, block)
   static constexpr int GSLOTS = 2 * NPAR;
   static constexpr int NBG = 4;
   static constexpr int NACC = 2;
   static constexpr int ACC_COLS = 256;
   static constexpr int NBAR = 2 * NA + 2 * NBG + 2 * NACC;
-  static constexpr int SMEM_BYTES = NA * A2_BYTES + NBG * GSLOTS * B_BYTES + NBAR * 8 + 16 + 1024;
+  static constexpr int SMEM_BYTES = NA * AW_SLOT + NBG * GSLOTS * B_BYTES + NBAR * 8 + 16 + 1024;
 };
 
 template <int BN>
@@ -362,7 +362,7 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t a_base = base;
-  const uint32_t b_base = base + C::NA * A2_BYTES;
+  const uint32_t b_base = base + C::NA * AW_SLOT;
   constexpr int B_REGION = C::NBG * C::GSLOTS * C::B_BYTES;
   const uint32_t bars = b_base + B_REGION;
   auto afull = [&](int s) { return bars + 8u * s; };
@@ -373,7 +373,7 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   auto tempty = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NBG + C::NACC + s); };
   const uint32_t tmem_slot = bars + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + C::NA * A2_BYTES + B_REGION + 8 * C::NBAR);
+      reinterpret_cast<volatile uint32_t*>(smem + C::NA * AW_SLOT + B_REGION + 8 * C::NBAR);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -421,10 +421,12 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int h0 = thi * T2_H, w0 = twi * T2_W;
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = px0; kw <= px0 + npx; ++kw) {
-            if (p.prod_sleep_ns) mbar_wait_sleep(aempty(sa), pa ^ 1u, p.prod_sleep_ns); else mbar_wait(aempty(sa), pa ^ 1u);
-            if (rank == 0) mbar_expect_tx(afull(sa), 2 * A2_BYTES);
-            tma_load_4d_2sm(a_base + sa * A2_BYTES, &tmA, afull_l + 8u * sa, cb * KBLK, w0 + kw, h0, n);
-            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            if (kw == px0) {
+              if (p.prod_sleep_ns) mbar_wait_sleep(aempty(sa), pa ^ 1u, p.prod_sleep_ns); else mbar_wait(aempty(sa), pa ^ 1u);
+              if (rank == 0) mbar_expect_tx(afull(sa), 2 * AW_BYTES);
+              tma_load_4d_2sm(a_base + sa * AW_SLOT, &tmA, afull_l + 8u * sa, cb * KBLK, w0, h0, n);
+              if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            }
             if (!resident) {
               int cnt = 0;
               for (int py = py0; py < py0 + npy; ++py)
@@ -463,9 +465,9 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ===================== MMA issuer (leader only) =====================
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, BN);
-      const uint64_t a_desc0 = make_sdesc_k128(a_base);
+      const uint64_t a_desc0 = make_sdesc_k128_sbo(a_base, WA_W * KBLK * 2, 0);
       const uint64_t b_desc0 = make_sdesc_k128(b_base);
-      constexpr uint64_t A_SLOT16 = A2_BYTES >> 4, B_SLOT16 = C::B_BYTES >> 4, KH16 = (T2_W * KBLK * 2) >> 4;
+      constexpr uint64_t A_SLOT16 = AW_SLOT >> 4, B_SLOT16 = C::B_BYTES >> 4, KH16 = (WA_W * KBLK * 2) >> 4;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int as = 0;
@@ -482,14 +484,14 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t started = 0;
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = px0; kw <= px0 + npx; ++kw) {
-            mbar_wait(afull(sa), pa);
+            if (kw == px0) mbar_wait(afull(sa), pa);
             if (resident) {
               if (!b_ready) { mbar_wait(bfull(0), 0u); b_ready = true; }
             } else {
               mbar_wait(bfull(sb), pb);
             }
             tc_fence_after();
-            const uint64_t ad = a_desc0 + (uint64_t)sa * A_SLOT16;
+            const uint64_t ad = a_desc0 + (uint64_t)sa * A_SLOT16 + (uint64_t)(kw * 8);   // one pixel = 128 B per kw
             if (elect_one_sync()) {
               int slot = 0;
               for (int iy = 0; iy < npy; ++iy) {
@@ -515,7 +517,7 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
               }
               if (!resident) umma_commit_2sm(bempty(sb));
-              umma_commit_2sm(aempty(sa));
+              if (kw == px0 + npx) umma_commit_2sm(aempty(sa));
             }
             __syncwarp();
             for (int iy = 0; iy < npy; ++iy)
@@ -524,7 +526,9 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (!resident) {
               if (++sb == C::NBG) { sb = 0; pb ^= 1u; }
             }
-            if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            if (kw == px0 + npx) {
+              if (++sa == C::NA) { sa = 0; pa ^= 1u; }
+            }
           }
         }
         if (elect_one_sync()) umma_commit_2sm(tfull(as));

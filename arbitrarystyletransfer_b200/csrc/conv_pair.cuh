@@ -29,8 +29,25 @@ struct CfgP {
   static constexpr int TMEM_COLS = NACC * BN;
   static constexpr int NBAR = 2 * NA_MAX + 2 * 3 + 2 * NACC;
   static constexpr int SMEM_BUDGET = 226 * 1024;          // of the 227 KB a CTA may have
-  static constexpr int smem_bytes(int na, int nbs) { return na * A2_BYTES + nbs * B_BYTES + NBAR * 8 + 16 + 1024; }
+  static constexpr int smem_bytes(int na, int nbs, int a_bytes = A2_BYTES) {
+    return na * a_bytes + nbs * B_BYTES + NBAR * 8 + 16 + 1024;
+  }
 };
+
+// Single A box (p.wide_a, the default): ONE box {64 ch, 10 w, 18 h} per (tile, 64-channel block) serves all nine taps.
+// Its pixel rows have a pitch of 10 pixels = 1280 B, so tap (kh, kw) starts (kh * 10 + kw) * 128 B into it, the 8
+// pixels of a tile row are 8 consecutive 128-byte rows, and the stride between 8-row groups (SBO) is 1280 B.  Neither
+// the start nor the groups are aligned to the 1024-byte swizzle atom -- and they need not be: measured here
+// (tests/test_gpu_conv.py bit-compares against the direct kernel), the tensor core applies the 128-byte swizzle to
+// the ABSOLUTE shared-memory address of every 16-byte chunk (bits [4,7) ^= bits [7,10)), exactly as TMA does when it
+// writes the box, so any 16-byte-aligned start and any SBO address the right data; the descriptor's base-offset
+// field must stay 0 (with the phase (start >> 7) & 7 in it the results are wrong).
+// 22.5 KB per (tile, block) instead of 3 x 18 KB of L2 -> shared-memory traffic (the 64- and 128-channel layers
+// were bound by the chip-wide L2 bandwidth: an L2 PREFETCH of the next tile's boxes made them 17 % slower), one TMA
+// operation and one barrier round instead of three.
+constexpr int WA_W = T2_W + 2;
+constexpr int AW_BYTES = T2_BOX_H * WA_W * KBLK * 2;             // 23 040 B landed per box
+constexpr int AW_SLOT = (AW_BYTES + 1023) / 1024 * 1024;         // ring slots stay 1024-byte aligned (TMA swizzle)
 
 // Shared-memory plan of one launch: weight slots (9 = a ring of three kw groups; 9 * Cin/64 = the layer's whole half
 // weight tile stays RESIDENT, loaded once per CTA) and A ring depth.  Re-streaming the weights for every tile costs
@@ -38,17 +55,18 @@ struct CfgP {
 // operand-supply bound (the chip-wide L2 cap is ~6300 B/clk = 42 B/clk per SM: guide B300_MICROARCH.md "LTS cap";
 // measured here: the MMA warp waited for operands 53 % of the time at 42 B/clk per SM).
 template <int BN>
-static void pair_plan(int cblocks, int n_blocks, int* na, int* nbs) {
+static void pair_plan(int cblocks, int n_blocks, int wide, int* na, int* nbs) {
   using C = CfgP<BN>;
+  const int a_bytes = wide ? AW_SLOT : A2_BYTES, a_min = wide ? 2 : 4;
   const int res_slots = 9 * cblocks;
-  int a = (C::SMEM_BUDGET - C::smem_bytes(0, res_slots)) / A2_BYTES;
-  if (n_blocks == 1 && a >= 4) {
+  int a = (C::SMEM_BUDGET - C::smem_bytes(0, res_slots)) / a_bytes;
+  if (n_blocks == 1 && a >= a_min) {
     *nbs = res_slots;
     *na = a < C::NA_MAX ? a : C::NA_MAX;
     return;
   }
   *nbs = 9;
-  a = (C::SMEM_BUDGET - C::smem_bytes(0, 9)) / A2_BYTES;
+  a = (C::SMEM_BUDGET - C::smem_bytes(0, 9)) / a_bytes;
   *na = a < C::NA_MAX ? a : C::NA_MAX;
 }
 
@@ -64,8 +82,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int NA = p.na;
+  const bool wide = p.wide_a != 0;
+  const uint32_t a_slot_bytes = wide ? AW_SLOT : A2_BYTES, a_tx_bytes = wide ? AW_BYTES : A2_BYTES;
   const uint32_t a_base = base;
-  const uint32_t b_base = base + NA * A2_BYTES;
+  const uint32_t b_base = base + NA * a_slot_bytes;
   const uint32_t bars = b_base + p.nbs * C::B_BYTES;
   auto afull = [&](int s) { return bars + 8u * s; };
   auto aempty = [&](int s) { return bars + 8u * (C::NA_MAX + s); };
@@ -75,7 +95,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tempty = [&](int s) { return bars + 8u * (2 * C::NA_MAX + 6 + C::NACC + s); };
   const uint32_t tmem_slot = bars + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      smem + NA * A2_BYTES + p.nbs * C::B_BYTES + 8 * C::NBAR);
+      smem + NA * a_slot_bytes + p.nbs * C::B_BYTES + 8 * C::NBAR);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -123,12 +143,26 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int thi = t % p.tiles_h;
         const int n = t / p.tiles_h;
         const int h0 = thi * T2_H, w0 = twi * T2_W;
+        if (p.pf_dist > 0 && q + p.pf_dist * npairs < p.num_tiles) {
+          // L2 prefetch of the A boxes of the tile this CTA takes pf_dist iterations from now (kw = 0 and 2 cover
+          // the ten columns): a tile's first touch of its input comes from HBM
+          int u = q + p.pf_dist * npairs;
+          u = 2 * (u / p.n_blocks) + rank;
+          const int ptw = u % p.tiles_w; u /= p.tiles_w;
+          const int pth = u % p.tiles_h, pn = u / p.tiles_h;
+          for (int cb = 0; cb < cblocks; ++cb) {
+            tma_prefetch_l2_4d(&tmA, cb * KBLK, ptw * T2_W, pth * T2_H, pn);
+            tma_prefetch_l2_4d(&tmA, cb * KBLK, ptw * T2_W + 2, pth * T2_H, pn);
+          }
+        }
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = 0; kw < 3; ++kw) {
-            mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa, p.prod_sleep_ns);
-            if (rank == 0) mbar_expect_tx(afull(sa), 2 * A2_BYTES);
-            tma_load_4d_2sm(a_base + sa * A2_BYTES, &tmA, afull_l + 8u * sa, cb * KBLK, w0 + kw, h0, n);
-            if (++sa == NA) { sa = 0; pa ^= 1u; }
+            if (!wide || kw == 0) {
+              mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa, p.prod_sleep_ns);
+              if (rank == 0) mbar_expect_tx(afull(sa), 2 * a_tx_bytes);
+              tma_load_4d_2sm(a_base + sa * a_slot_bytes, &tmA, afull_l + 8u * sa, cb * KBLK, w0 + kw, h0, n);
+              if (++sa == NA) { sa = 0; pa ^= 1u; }
+            }
             if (!resident) {
               mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb, p.prod_sleep_ns);
               if (rank == 0) mbar_expect_tx(bfull(sb), 2 * 3 * C::B_BYTES);
@@ -157,9 +191,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== MMA issuer: the leader's converged warp, one elected lane =====================
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, BN);
-      const uint64_t a_desc0 = make_sdesc_k128(a_base);
+      const uint64_t a_desc0 = wide ? make_sdesc_k128_sbo(a_base, WA_W * KBLK * 2, 0) : make_sdesc_k128(a_base);
       const uint64_t b_desc0 = make_sdesc_k128(b_base);
-      constexpr uint64_t A_SLOT16 = A2_BYTES >> 4, B_SLOT16 = C::B_BYTES >> 4, KH16 = (T2_W * KBLK * 2) >> 4;
+      constexpr uint64_t B_SLOT16 = C::B_BYTES >> 4;
+      const uint64_t A_SLOT16 = a_slot_bytes >> 4, KH16 = ((wide ? WA_W : T2_W) * KBLK * 2) >> 4;
+      const uint64_t KW_STEP = wide ? (uint64_t)8 : 0;      // single box: the kw shift is one pixel = 128 B
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int as = 0;
@@ -176,8 +212,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int cb = 0; cb < cblocks; ++cb) {
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            mbar_wait_acc(afull(sa), pa, dbg, dbg_ma);
-            const uint64_t ad = a_desc0 + (uint64_t)sa * A_SLOT16;
+            if (!wide || kw == 0) mbar_wait_acc(afull(sa), pa, dbg, dbg_ma);
+            const uint64_t ad = a_desc0 + (uint64_t)sa * A_SLOT16 + (uint64_t)kw * KW_STEP;
             int grp;
             if (resident) {
               grp = cb * 3 + kw;
@@ -198,14 +234,16 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
               }
               if (!resident) umma_commit_2sm(bempty(sb));
-              umma_commit_2sm(aempty(sa));
+              if (!wide || kw == 2) umma_commit_2sm(aempty(sa));
             }
             __syncwarp();
             accum = 1u;
             if (!resident) {
               if (++sb == 3) { sb = 0; pb ^= 1u; }
             }
-            if (++sa == NA) { sa = 0; pa ^= 1u; }
+            if (!wide || kw == 2) {
+              if (++sa == NA) { sa = 0; pa ^= 1u; }
+            }
           }
         }
         if (elect_one_sync()) umma_commit_2sm(tfull(as));
@@ -240,7 +278,7 @@ static int launch_pair_tg(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BUDGET));
     attr_done = true;
   }
-  const int smem_bytes = C::smem_bytes(p.na, p.nbs);
+  const int smem_bytes = C::smem_bytes(p.na, p.nbs, p.wide_a ? AW_SLOT : A2_BYTES);
   const int max_pairs = sm_count / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
   cudaLaunchConfig_t cfg = {};
@@ -277,7 +315,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 template <int BN>
 static int launch_pair_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, ConvParams p,
                            int sm_count, cudaStream_t s) {
-  pair_plan<BN>(p.Cin / KBLK, p.n_blocks, &p.na, &p.nbs);
+  pair_plan<BN>(p.Cin / KBLK, p.n_blocks, p.wide_a, &p.na, &p.nbs);
   switch (epi) {
     case AST_EPI_PLAIN: return launch_pair<BN, AST_EPI_PLAIN>(tmA, tmB, p, sm_count, s);
     case AST_EPI_POOL2: return launch_pair<BN, AST_EPI_POOL2>(tmA, tmB, p, sm_count, s);

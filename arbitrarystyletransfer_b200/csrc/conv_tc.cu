@@ -81,6 +81,8 @@ struct ConvParams {
   int clamp01;       // EPI_NCHW32 only: Hardtanh(0,1) (models.py:304, 315)
   long long* dbg;    // optional [gridDim.x][8] wait-cycle counters per role (AST_CONV_DEBUG=1)
   uint32_t epi_sleep_ns, prod_sleep_ns;   // back-off of the waiting roles (mbar_wait_sleep); 0 = tight polling
+  int wide_a;        // CTA-pair kernels: one {64, 10, 18} A box per (tile, block) instead of one {64, 8, 18} box per kw
+  int pf_dist;       // CTA-pair kernel: L2 prefetch distance in tiles per CTA (0 = off)
   int na, nbs;       // CTA-pair kernels: A ring slots and weight slots of this launch (pair_plan)
   int dbg_flags;     // AST_CONV_DBGFLAGS (bottleneck elimination, results are WRONG): 1 = operands loaded once per ring
                      // slot, never refreshed; 2 = epilogue without global stores; 4 = epilogue without TMEM loads
@@ -731,8 +733,8 @@ static int launch_tc_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB
   return AST_E_BADARG;
 }
 
-#include "conv_fold.cuh"
 #include "conv_pair.cuh"
+#include "conv_fold.cuh"
 
 bool tc_supported(const ast_conv_desc* d) {
   return d->Cin % 64 == 0 && d->Cout % 64 == 0 && d->H >= 2 && d->W >= 2;
@@ -743,12 +745,12 @@ static int get_sm_count(int* out);
 // Tensor maps for one launch.  kwbox = 1: A box {64, 8, 18, 1} (conv3x3_tc2_kernel);
 // kwbox = 0: A box {64, 16, 8, 1} (conv3x3_tc_kernel).  Weights [9][rows][Cin], box {64, BN, 1}.
 static int make_maps(CUtensorMap* tmA, CUtensorMap* tmB, const void* in, const void* wpk, int N, int H,
-                     int W, int Cin, int wrows, int BN, int kwbox, int ntaps = 9) {
+                     int W, int Cin, int wrows, int BN, int kwbox, int ntaps = 9, int wide_a = 0) {
   const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W + 2, (uint64_t)H + 2, (uint64_t)N};
   const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)(W + 2) * Cin * 2,
                            (uint64_t)(H + 2) * (W + 2) * Cin * 2};
   const uint32_t box_tap[4] = {KBLK, TILE_W, TILE_H, 1};
-  const uint32_t box_kw[4] = {KBLK, T2_W, T2_BOX_H, 1};
+  const uint32_t box_kw[4] = {KBLK, (uint32_t)(wide_a ? T2_W + 2 : T2_W), T2_BOX_H, 1};
   int r = encode_bf16_map(tmA, in, 4, dims, str, kwbox ? box_kw : box_tap);
   if (r) return r;
   const uint64_t wdims[3] = {(uint64_t)Cin, (uint64_t)wrows, (uint64_t)ntaps};
@@ -780,6 +782,8 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   static const int epi_sleep = getenv("AST_CONV_EPI_SLEEP") ? atoi(getenv("AST_CONV_EPI_SLEEP")) : 0;
   static const int prod_sleep = getenv("AST_CONV_PROD_SLEEP") ? atoi(getenv("AST_CONV_PROD_SLEEP")) : 0;
   p.epi_sleep_ns = (uint32_t)epi_sleep; p.prod_sleep_ns = (uint32_t)prod_sleep;
+  static const int pf_env = getenv("AST_CONV_PF") ? atoi(getenv("AST_CONV_PF")) : 0;
+  p.pf_dist = pf_env;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   const bool up = d->epilogue == AST_EPI_UP2 || d->epilogue == AST_EPI_UPFOLD;
   p.Ho = d->epilogue == AST_EPI_POOL2 ? d->H / 2 : (up ? 2 * d->H : d->H);
@@ -805,7 +809,7 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
     if (nt >= 0x7fffffffLL) return AST_E_SHAPE;
     p.num_tiles = (int)nt;
     CUtensorMap tmA, tmB;
-    r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, pair_f ? BN / 2 : BN, 1, 16);
+    r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, pair_f ? BN / 2 : BN, 1, 16, pair_f ? 1 : 0);
     if (r) return r;
     if (pair_f) {
       switch (BN) {
@@ -847,7 +851,9 @@ int conv3x3_tc(const ast_conv_desc* d, const void* in, const void* wpk, const fl
   p.num_tiles = (int)nt;     // pair kernel: counts tile PAIRS x n-blocks
 
   CUtensorMap tmA, tmB;
-  r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, pair ? BN / 2 : BN, kwbox);
+  static const int wide_env = getenv("AST_CONV_WIDEA") ? atoi(getenv("AST_CONV_WIDEA")) : 1;
+  p.wide_a = pair ? wide_env : 0;
+  r = make_maps(&tmA, &tmB, in, wpk, d->N, d->H, d->W, d->Cin, d->Cout, pair ? BN / 2 : BN, kwbox, 9, p.wide_a);
   if (r) return r;
   static const bool dbg_on = getenv("AST_CONV_DEBUG") != nullptr;
   long long* dbg = nullptr;

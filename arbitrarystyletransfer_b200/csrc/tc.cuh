@@ -123,6 +123,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// Pull a tensor box into L2 ahead of the load that will need it (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // ---- tcgen05 --------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -279,6 +286,18 @@ __device__ __forceinline__ uint64_t make_sdesc_k128(uint32_t saddr) {
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024u >> 4) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Same with an explicit stride between 8-row groups and a "matrix base offset" (bits [49,52)): the phase of the
+// 128-byte swizzle pattern at the start address, (start >> 7) & 7, for operands that begin inside a 1024-byte atom.
+__device__ __forceinline__ uint64_t make_sdesc_k128_sbo(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7u) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }
