@@ -1109,8 +1109,81 @@ constexpr int F2_X0 = 3;                                      // column of the t
 constexpr int F2_PATCH_FLOATS = 3 * F2_PH * F2_PW;            // 720
 constexpr int F2_PATCH_BYTES = F2_PATCH_FLOATS * 4;           // 2880
 
+// Epilogue of conv1_1 with a TMA store.  The layer's work IS its 64-channel output, and written from registers it is
+// one 32-byte sector per lane and store (a lane holds ONE pixel's channels): 512 sector transactions per tile through
+// the LSU, which ncu showed 85 % busy.  Here the four warps of a tile set pack their 128 pixel rows (128 B each) into a
+// 16 KB staging buffer in the 128-byte-swizzle layout (chunk c of row r at c ^ (r & 7): conflict-free 16-byte stores),
+// and one lane issues ONE cp.async.bulk.tensor store of the {64 ch, 16 w, 8 h} box; TMA clips ragged tiles against the
+// image.  Tile set tg owns accumulator stage tg and staging buffer tg, so four tiles are in flight per CTA.
+__device__ __forceinline__ void epilogue_first_store(const ConvParams& p, const CUtensorMap* tmOut, uint32_t tmem_base,
+                                                     int ew, int lane, uint32_t tfull_bar0, uint32_t tempty_bar0,
+                                                     uint32_t staging) {
+  const int e = ew & 3, tg = ew >> 2;
+  const int m = 32 * e + lane;                 // pixel row of the tile = TMEM lane
+  const int hl = m / TILE_W, wl = m % TILE_W;
+  const uint32_t buf = staging + (uint32_t)tg * (TILE_M * 128);
+  const uint32_t row = buf + (uint32_t)m * 128u;
+  const uint32_t sw = (uint32_t)(m & 7);
+  const bool issuer = (e == 0);
+  uint32_t aphase = 0;
+  TileCursor cur;
+  cur.init(p, blockIdx.x + tg * gridDim.x, F2_NG * gridDim.x);
+  long long dbg_wait = 0;
+  const long long dbg_t0 = clock64();
+  for (int tile = blockIdx.x + tg * gridDim.x; tile < p.num_tiles; tile += F2_NG * gridDim.x, cur.next()) {
+    const int twi = cur.twi, thi = cur.thi, n = cur.n;
+    mbar_wait_acc(tfull_bar0 + 8u * tg, aphase, p.dbg != nullptr, dbg_wait, p.epi_sleep_ns);
+    tc_fence_after();
+    // the previous store of this tile set has finished reading the staging buffer
+    if (issuer && lane == 0) bulk_wait_group_read0();
+    named_bar_sync(1 + tg, 128);
+    const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(tg * F_N);
+    const int h = thi * TILE_H + hl, w = twi * TILE_W + wl;
+    const bool in_img = (h < p.H) && (w < p.W);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld_32x32(trow + half * 32, v);
+      tmem_ld_wait();
+      if (p.tap && in_img) {      // fp32 NCHW tap (relu1_1 / conv1_1 for the losses): bias is already in the GEMM
+        float* tp = p.tap + (((int64_t)n * p.Cout + half * 32) * p.H + h) * p.W + w;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float f = __uint_as_float(v[i]);
+          tp[(int64_t)i * p.H * p.W] = p.tap_prerelu ? f : fmaxf(f, 0.f);
+        }
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t chunk = (uint32_t)(half * 4 + c) ^ sw;
+        st_shared_v4(row + chunk * 16u, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar0 + 8u * tg);      // accumulator stage free: the MMA warp may refill it
+    fence_proxy_async_smem();                               // staging writes -> visible to the TMA (async proxy)
+    named_bar_sync(1 + tg, 128);
+    if (issuer && lane == 0) {
+      tma_store_4d(tmOut, buf, 0, twi * TILE_W, thi * TILE_H, n);
+      bulk_commit_group();
+    }
+    aphase ^= 1u;
+  }
+  if (issuer && lane == 0) bulk_wait_group0();
+  if (p.dbg && ew == 0 && lane == 0) {
+    p.dbg[blockIdx.x * 8 + 4] = dbg_wait;
+    p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;
+  }
+}
+
 __global__ void __launch_bounds__(F2_THREADS, 1)
-conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const FirstParams fp, const ConvParams p) {
+conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_constant__ CUtensorMap tmOut,
+                         const FirstParams fp, const ConvParams p, const int tma_store) {
+  extern __shared__ uint8_t f2_dyn[];          // tma_store: F2_NG staging buffers of 16 KB, 1024-byte aligned
   __shared__ __align__(128) uint8_t s_a[F_STAGES][F_A_BYTES];
   __shared__ __align__(128) uint8_t s_b[F_B_BYTES];
   __shared__ __align__(128) float s_patch[F2_PSTAGES][F2_PATCH_FLOATS + 16];  // +16: keeps every stage 128 B aligned
@@ -1146,7 +1219,7 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const FirstP
     for (int s = 0; s < F2_PSTAGES; ++s) { mbar_init(pfull_bar(s), 1); mbar_init(pempty_bar(s), 4); }
     fence_barrier_init();
   }
-  if (warp == F2_TMA_WARP && lane == 0) tma_prefetch_desc(&tmImg);
+  if (warp == F2_TMA_WARP && lane == 0) { tma_prefetch_desc(&tmImg); if (tma_store) tma_prefetch_desc(&tmOut); }
   if (warp == F2_MMA_WARP) tmem_alloc<F2_NG * F_N>(smem_u32(&s_tmem));
   fence_proxy_async_smem();
   tc_fence_before();
@@ -1259,7 +1332,12 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const FirstP
     }
   } else {
     // ===================== epilogue (warps 4 .. 4 + 4 F2_NG) =====================
-    epilogue_loop<F_N, AST_EPI_PLAIN, TILE_W, 1, F2_NG, F2_NG>(p, tmem_base, warp - 4, lane, tfull_bar(0), tempty_bar(0));
+    if (tma_store) {
+      const uint32_t staging = (smem_u32(f2_dyn) + 1023u) & ~1023u;
+      epilogue_first_store(p, &tmOut, tmem_base, warp - 4, lane, tfull_bar(0), tempty_bar(0), staging);
+    } else {
+      epilogue_loop<F_N, AST_EPI_PLAIN, TILE_W, 1, F2_NG, F2_NG>(p, tmem_base, warp - 4, lane, tfull_bar(0), tempty_bar(0));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1342,8 +1420,27 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
     const int grid1 = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     dump.grid = grid1;
     fp.bias = bias;
+    // TMA-store epilogue: needs the bias in the GEMM (always here), an output and a 16-byte aligned interior
+    static const bool no_tma_store = getenv("AST_FIRST_NO_TMA_STORE") != nullptr;   // A/B reference: per-lane stores
+    const bool tma_store = !no_tma_store && p.out != nullptr && bias != nullptr && aligned16(out);
     p.bias = nullptr;               // folded into the GEMM
-    conv3x3_first_tma_kernel<<<grid1, F2_THREADS, 0, s>>>(tmImg, fp, p);
+    CUtensorMap tmOut = tmImg;
+    if (tma_store) {
+      // the INTERIOR of the padded NHWC buffer [N][H+2][W+2][64]: boxes are clipped at W and H, never touch the halo
+      const uint64_t odims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+      const uint64_t ostr[3] = {128, (uint64_t)(W + 2) * 128, (uint64_t)(H + 2) * (W + 2) * 128};
+      const uint32_t obox[4] = {64, TILE_W, TILE_H, 1};
+      const __nv_bfloat16* interior = reinterpret_cast<const __nv_bfloat16*>(out) + ((int64_t)(W + 2) + 1) * 64;
+      r = encode_bf16_map(&tmOut, interior, 4, odims, ostr, obox);
+      if (r) return r;
+    }
+    constexpr int F2_DYN = F2_NG * TILE_M * 128 + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+      AST_CUDA(cudaFuncSetAttribute(conv3x3_first_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_DYN));
+      attr_done = true;
+    }
+    conv3x3_first_tma_kernel<<<grid1, F2_THREADS, tma_store ? F2_DYN : 0, s>>>(tmImg, tmOut, fp, p, tma_store ? 1 : 0);
     AST_CHECK_LAUNCH();
     return 0;
   }
