@@ -55,27 +55,28 @@ constexpr int AW_SLOT = (AW_BYTES + 1023) / 1024 * 1024;         // ring slots s
 // operand-supply bound (the chip-wide L2 cap is ~6300 B/clk = 42 B/clk per SM: guide B300_MICROARCH.md "LTS cap";
 // measured here: the MMA warp waited for operands 53 % of the time at 42 B/clk per SM).
 template <int BN>
-static void pair_plan(int cblocks, int n_blocks, int wide, int* na, int* nbs) {
+static void pair_plan(int cblocks, int n_blocks, int wide, int staging, int* na, int* nbs) {
   using C = CfgP<BN>;
   const int a_bytes = wide ? AW_SLOT : A2_BYTES, a_min = wide ? 2 : 4;
   const int res_slots = 9 * cblocks;
-  int a = (C::SMEM_BUDGET - C::smem_bytes(0, res_slots)) / a_bytes;
+  const int budget = C::SMEM_BUDGET - staging;
+  int a = (budget - C::smem_bytes(0, res_slots)) / a_bytes;
   if (n_blocks == 1 && a >= a_min) {
     *nbs = res_slots;
     *na = a < C::NA_MAX ? a : C::NA_MAX;
     return;
   }
   *nbs = 9;
-  a = (C::SMEM_BUDGET - C::smem_bytes(0, 9)) / a_bytes;
+  a = (budget - C::smem_bytes(0, 9)) / a_bytes;
   *na = a < C::NA_MAX ? a : C::NA_MAX;
 }
 
 // TG: tile sets of the epilogue (epilogue_loop): the 4 * Epi2<BN>::NG epilogue warps work as TG sets on different
 // tiles, Epi2<BN>::NG / TG column groups each.
-template <int BN, int EPI, int TG>
+template <int BN, int EPI, int TG, bool TS>
 __global__ void __launch_bounds__(Epi2<BN>::THREADS, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const ConvParams p) {
+                    const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
   using C = CfgP<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -84,8 +85,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int NA = p.na;
   const bool wide = p.wide_a != 0;
   const uint32_t a_slot_bytes = wide ? AW_SLOT : A2_BYTES, a_tx_bytes = wide ? AW_BYTES : A2_BYTES;
-  const uint32_t a_base = base;
-  const uint32_t b_base = base + NA * a_slot_bytes;
+  // [TMA-store staging (1024-byte aligned, p.tma_store bytes)] [A ring] [weight slots] [barriers]
+  const uint32_t a_base = base + (TS ? (uint32_t)p.tma_store : 0u);
+  const uint32_t b_base = a_base + NA * a_slot_bytes;
   const uint32_t bars = b_base + p.nbs * C::B_BYTES;
   auto afull = [&](int s) { return bars + 8u * s; };
   auto aempty = [&](int s) { return bars + 8u * (C::NA_MAX + s); };
@@ -95,7 +97,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tempty = [&](int s) { return bars + 8u * (2 * C::NA_MAX + 6 + C::NACC + s); };
   const uint32_t tmem_slot = bars + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      smem + NA * a_slot_bytes + p.nbs * C::B_BYTES + 8 * C::NBAR);
+      smem + (TS ? p.tma_store : 0) + NA * a_slot_bytes + p.nbs * C::B_BYTES + 8 * C::NBAR);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -107,6 +109,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TS) tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
@@ -257,7 +260,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    epilogue_loop<BN, EPI, T2_W, Epi2<BN>::NG / TG, C::NACC, TG, true>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0), rank);
+    epilogue_loop<BN, EPI, T2_W, Epi2<BN>::NG / TG, C::NACC, TG, true, TS>(p, tmem_base, warp - 4, lane, tfull(0),
+                                                                           tempty(0), rank, &tmOut, base);
   }
 
   tc_fence_before();
@@ -268,17 +272,17 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int EPI, int TG>
-static int launch_pair_tg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count,
-                          cudaStream_t s) {
+template <int BN, int EPI, int TG, bool TS>
+static int launch_pair_tg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const ConvParams& p,
+                          int sm_count, cudaStream_t s) {
   using C = CfgP<BN>;
-  auto kern = conv3x3_pair_kernel<BN, EPI, TG>;
+  auto kern = conv3x3_pair_kernel<BN, EPI, TG, TS>;
   static bool attr_done = false;
   if (!attr_done) {
     AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BUDGET));
     attr_done = true;
   }
-  const int smem_bytes = C::smem_bytes(p.na, p.nbs, p.wide_a ? AW_SLOT : A2_BYTES);
+  const int smem_bytes = C::smem_bytes(p.na, p.nbs, p.wide_a ? AW_SLOT : A2_BYTES) + (TS ? p.tma_store : 0);
   const int max_pairs = sm_count / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
   cudaLaunchConfig_t cfg = {};
@@ -293,33 +297,46 @@ static int launch_pair_tg(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AST_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  AST_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p));
   AST_CHECK_LAUNCH();
   return 0;
 }
 
+// AST_CONV_TG (tile sets of the epilogue, see epilogue_loop) was measured at 1 / 2 / 4: no gain for any layer
+// (profiles/r2_conv_pair_tile_sets.txt), so only TG = 1 is instantiated.
 template <int BN, int EPI>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count,
-                       cudaStream_t s) {
-  static const int tg_env = getenv("AST_CONV_TG") ? atoi(getenv("AST_CONV_TG")) : 0;   // tuning override
-  int tg = tg_env ? tg_env : 1;
-  if constexpr (BN <= 128) {
-    if (tg == 4) return launch_pair_tg<BN, EPI, 4>(tmA, tmB, p, sm_count, s);
-    if (tg == 2) return launch_pair_tg<BN, EPI, 2>(tmA, tmB, p, sm_count, s);
-  } else {
-    if (tg >= 2) return launch_pair_tg<BN, EPI, 2>(tmA, tmB, p, sm_count, s);
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const ConvParams& p,
+                       int sm_count, cudaStream_t s) {
+  if constexpr (EPI == AST_EPI_PLAIN && BN <= 128) {
+    if (p.tma_store) return launch_pair_tg<BN, EPI, 1, true>(tmA, tmB, tmOut, p, sm_count, s);
   }
-  return launch_pair_tg<BN, EPI, 1>(tmA, tmB, p, sm_count, s);
+  return launch_pair_tg<BN, EPI, 1, false>(tmA, tmB, tmOut, p, sm_count, s);
 }
 
 template <int BN>
 static int launch_pair_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, ConvParams p,
                            int sm_count, cudaStream_t s) {
-  pair_plan<BN>(p.Cin / KBLK, p.n_blocks, p.wide_a, &p.na, &p.nbs);
+  // TMA-store epilogue (AST_CONV_TMA_STORE=1; plain tiles, BN <= 128).  OFF by default: what made conv1_1 1.8x faster
+  // (its epilogue was LSU-bound and nothing else used the shared-memory port) is a loss here -- the staging buffer's
+  // writes and the store's reads go through the port the tensor core's operand reads already saturate: measured
+  // enc_conv3 232 -> 257 us, dec_conv5 213 -> 220 us, dec_conv7 244 -> 242 us (profiles/r2_conv_pair_tma_store.txt).
+  static const int ts_env = getenv("AST_CONV_TMA_STORE") ? atoi(getenv("AST_CONV_TMA_STORE")) : 0;
+  CUtensorMap tmOut = tmA;
+  p.tma_store = 0;
+  if (ts_env && epi == AST_EPI_PLAIN && BN <= 128 && p.out && !p.tap && aligned16(p.out) && p.Cout % 64 == 0) {
+    // the INTERIOR of the padded NHWC output [N][H+2][W+2][Cout]: boxes are clipped at W and H, the halo is not touched
+    const uint64_t odims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
+    const uint64_t ostr[3] = {(uint64_t)p.Cout * 2, (uint64_t)(p.Wo + 2) * p.Cout * 2,
+                              (uint64_t)(p.Ho + 2) * (p.Wo + 2) * p.Cout * 2};
+    const uint32_t obox[4] = {64, T2_W, T2_H, 1};
+    const __nv_bfloat16* interior = p.out + ((int64_t)(p.Wo + 2) + 1) * p.Cout;
+    if (encode_bf16_map(&tmOut, interior, 4, odims, ostr, obox) == 0) p.tma_store = (BN / 64) * TILE_M * 128;
+  }
+  pair_plan<BN>(p.Cin / KBLK, p.n_blocks, p.wide_a, p.tma_store, &p.na, &p.nbs);
   switch (epi) {
-    case AST_EPI_PLAIN: return launch_pair<BN, AST_EPI_PLAIN>(tmA, tmB, p, sm_count, s);
-    case AST_EPI_POOL2: return launch_pair<BN, AST_EPI_POOL2>(tmA, tmB, p, sm_count, s);
-    case AST_EPI_UP2: return launch_pair<BN, AST_EPI_UP2>(tmA, tmB, p, sm_count, s);
+    case AST_EPI_PLAIN: return launch_pair<BN, AST_EPI_PLAIN>(tmA, tmB, tmOut, p, sm_count, s);
+    case AST_EPI_POOL2: return launch_pair<BN, AST_EPI_POOL2>(tmA, tmB, tmOut, p, sm_count, s);
+    case AST_EPI_UP2: return launch_pair<BN, AST_EPI_UP2>(tmA, tmB, tmOut, p, sm_count, s);
   }
   return AST_E_BADARG;
 }

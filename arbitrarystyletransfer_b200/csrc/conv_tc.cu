@@ -83,6 +83,7 @@ struct ConvParams {
   uint32_t epi_sleep_ns, prod_sleep_ns;   // back-off of the waiting roles (mbar_wait_sleep); 0 = tight polling
   int wide_a;        // CTA-pair kernels: one {64, 10, 18} A box per (tile, block) instead of one {64, 8, 18} box per kw
   int pf_dist;       // CTA-pair kernel: L2 prefetch distance in tiles per CTA (0 = off)
+  int tma_store;     // CTA-pair kernel, plain epilogue, BN <= 128: staging bytes reserved for the TMA-store epilogue (0 = off)
   int na, nbs;       // CTA-pair kernels: A ring slots and weight slots of this launch (pair_plan)
   int dbg_flags;     // AST_CONV_DBGFLAGS (bottleneck elimination, results are WRONG): 1 = operands loaded once per ring
                      // slot, never refreshed; 2 = epilogue without global stores; 4 = epilogue without TMEM loads
@@ -174,9 +175,14 @@ __device__ __forceinline__ int out_targets(int x, int Xo, int halo, int (&t)[4])
 // cheap, for the 64- and 128-channel layers.
 // P2 (CTA pair, conv_pair.cuh): the work index counts tile pairs, this CTA takes spatial tile 2 * pair + rank, and the
 // accumulator is handed back on the LEADER's tempty barrier (a remote arrive for rank 1).
-template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2, int TG = 1, bool P2 = false>
+// TS (TMA store, plain epilogue, BN <= 128, TG = 1): the 4 * NG warps pack the tile into a staging buffer of BN / 64
+// boxes {64 ch, TW w, TH h} in the 128-byte-swizzle layout and one lane issues the cp.async.bulk.tensor stores (see
+// epilogue_first_store); lanes that own border pixels still write the reflection / clamp halo copies themselves.
+template <int BN, int EPI, int TW = TILE_W, int NG = 1, int NACC = 2, int TG = 1, bool P2 = false, bool TS = false>
 __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
-                                              uint32_t tfull_bar0, uint32_t tempty_bar0, int rank = 0) {
+                                              uint32_t tfull_bar0, uint32_t tempty_bar0, int rank = 0,
+                                              const CUtensorMap* tmOut = nullptr, uint32_t staging = 0) {
+  static_assert(!TS || (EPI == AST_EPI_PLAIN && TG == 1 && BN % 64 == 0), "TMA store: plain tiles, one tile set");
   constexpr int CH = (TG > 1 && BN <= 64) ? 16 : ((BN >= 32 && BN / 32 >= NG) ? 32 : 16);  // columns per tcgen05.ld
   constexpr int TH = TILE_M / TW;         // tile = TH rows x TW cols of pixels, row-major in M
   constexpr int NCH = BN / CH;
@@ -217,6 +223,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
 
     mbar_wait_acc(tfull_bar0 + 8u * as, aphase, p.dbg != nullptr, dbg_wait, p.epi_sleep_ns);
     tc_fence_after();
+    if (TS) {   // the previous tile's stores have finished reading the staging buffer
+      if (ew == 0 && lane == 0) bulk_wait_group_read0();
+      named_bar_sync(1, 128 * NG);
+    }
     const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
     uint32_t vnext[CH];
     const bool skip_ld = (p.dbg_flags & 4) != 0;
@@ -286,9 +296,19 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
             pk[i] = *reinterpret_cast<uint32_t*>(&a);
           }
         }
+        if (TS) {
+          const int m = 32 * e + lane, cl = chunk * CH;        // tile row, first channel of the chunk in the tile
+          const uint32_t rowa = staging + (uint32_t)(cl >> 6) * (TILE_M * 128) + (uint32_t)m * 128u;
+#pragma unroll
+          for (int q = 0; q < CH / 8; ++q) {
+            const uint32_t c16 = (uint32_t)(((cl & 63) >> 3) + q) ^ (uint32_t)(m & 7);
+            st_shared_v4(rowa + c16 * 16u, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+        }
         if (p.out && !(p.dbg_flags & 2)) {
           for (int ri = 0; ri < nr; ++ri) {
             for (int ci = 0; ci < nc; ++ci) {
+              if (TS && ri == 0 && ci == 0) continue;      // the pixel itself goes out with the TMA store
               __nv_bfloat16* o = p.out +
                   (((int64_t)n * (p.Ho + 2) + (rows[ri] + 1)) * (p.Wo + 2) + (cols[ci] + 1)) * p.Cout + ch0;
               if (wide_st) {
@@ -311,9 +331,20 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
       if (P2) mbar_arrive_cluster(tempty_leader0 + 8u * as);
       else mbar_arrive(tempty_bar0 + 8u * as);
     }
+    if (TS) {
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128 * NG);
+      if (ew == 0 && lane == 0 && !(p.dbg_flags & 2)) {
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_store_4d(tmOut, staging + (uint32_t)b * (TILE_M * 128), nb * BN + b * 64, twi * TW, thi * TH, n);
+        bulk_commit_group();
+      }
+    }
     as += TG;
     if (as >= NACC) { as -= NACC; aphase ^= 1u; }
   }
+  if (TS && ew == 0 && lane == 0) bulk_wait_group0();
   if (p.dbg && ew == 0 && lane == 0) {
     p.dbg[blockIdx.x * 8 + 4] = dbg_wait;               // epilogue warp 0: waiting for an accumulator
     p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;     // epilogue warp 0: total loop time
