@@ -159,11 +159,15 @@ int ast_gram_bwd(const float* x, const float* gg, float* gx, int B, int C, int64
 #define AST_CONV_AUTO   0 /* tcgen05 implicit GEMM when Cin%64==0 && Cout%64==0, else direct */
 #define AST_CONV_TC     1 /* force tcgen05 (AST_E_SHAPE if unsupported) */
 #define AST_CONV_DIRECT 2 /* CUDA-core direct kernel (odd shapes; on-device cross-check) */
-#define AST_CONV_TC_TAPBOX 3 /* tcgen05 kernel variant that loads one 8x16-pixel A box per tap (the
-                                default tensor-core kernel loads one 18x8 box per kw and reuses it
-                                for the three kh taps: 2.7x less L2 -> shared-memory traffic) */
-/* impl = 64, 128 or 256 forces the default tcgen05 kernel with that N-block width; 1064, 1128 or
- * 1256 does the same for the TAPBOX variant (tuning / tests). */
+#define AST_CONV_TC_TAPBOX 3 /* one-CTA tcgen05 kernel variant that loads one 8x16-pixel A box per tap (round-1
+                                A/B reference) */
+/* AUTO / TC run the CTA-pair kernel (tcgen05.mma.cta_group::2, one {64 ch, 10 w, 18 h} A box per tile and channel
+ * block for all nine taps, csrc/conv_pair.cuh) whenever the layer has at least two spatial tiles, else the one-CTA
+ * kernel (one {64, 8, 18} box per kw).  impl = 64, 128 or 256 forces the N-block width; 1064, 1128 or 1256 does the
+ * same for the TAPBOX variant and 2064, 2128 or 2256 for the pair kernel (tuning / tests).  Environment switches read
+ * once per process (A/B measurements): AST_CONV_PAIR=0 (one-CTA kernels), AST_CONV_WIDEA=0 (pair
+ * kernel with one A box per kw), AST_CONV_TMA_STORE=1 (TMA-store epilogue for plain tiles), AST_FIRST_NO_TMA_STORE=1
+ * (conv1_1 with per-lane stores), AST_CONV_DEBUG=1 (per-role wait cycles on stderr; synchronises). */
 
 typedef struct ast_conv_desc {
   int N, H, W;        /* conv input = conv output spatial size (stride 1, 3x3, pad 1)      */

@@ -77,4 +77,6 @@ def test_sass_is_blackwell_native(lib_path):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass
+    # round 2: CTA-pair MMAs with multicast commits, TMA loads signalling the leader's barrier, and a TMA store
+    assert "UTCHMMA.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass and ".2CTA" in sass and "UTMASTG" in sass
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", lib_path], capture_output=True, text=True).stdout
