@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 4))) ada
     }
     cta_merge_to(w.fold(), s_warp, &s_q[1]);
   }
-  for (int k = 0; k + 1 < Q && !style_prefetched; ++k) {
+  for (int k = 0; k + 1 < Q && !style_prefetched && !SM; ++k) {
     const int64_t snvec = a.style_hw[k] / V;
     const int64_t sseg = (snvec + CS - 1) / CS;
     const int64_t s0 = rank * sseg;
@@ -318,23 +318,131 @@ __global__ void __launch_bounds__(kThreads, (R <= 2 ? 4 : (R <= 4 ? 3 : 4))) ada
     Moments m = (s0 < s1) ? stream_moments_vec<BF16>(srow, s0, s1) : Moments{0.f, 0.f, 0.f};
     cta_merge_to(m, s_warp, &s_q[1 + k]);
   }
-  if (SM) {   // the content copies have had the whole style stream to land
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    ShiftedLanes<V> w;
-    w.init(VT::load1(a.content, row * a.HW));
+  if (SM) {
+    // Long rows (cluster-split, R == 8): plain sums about a COMMON per-row shift x0 (the row's first element, the same
+    // in every thread and CTA of the cluster), so partial sums simply ADD -- across lanes, warps and CTAs -- and one
+    // reduction with one pair of block barriers serves all 1 + K quantities.  The Chan merges this replaces ran in
+    // every shuffle step of five separate block reductions: 61 thread-instructions per 16-byte vector, issue-bound
+    // at 60 % of the HBM copy peak (profiles/r1_ncu_k1_long_rows_summary.csv).  mean = x0 + S/n,
+    // m2 = Q - S^2/n: the cancellation costs (mean - x0)^2 / sigma^2 ulps, a handful for a shift taken from the row.
+    __shared__ float s_red[kWarps][2 * kMaxQ];
+    __shared__ float s_part[2 * kMaxQ];      // this CTA's (S, Q) per quantity; read by the cluster through DSMEM
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float accS[kMaxQ], accQ[kMaxQ];
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
-      if (i < v1) {
-        float x[V];
-        VT::unpack(s_cache[threadIdx.x + j * kThreads], x);
-        w.push(x);
+    for (int q = 0; q < kMaxQ; ++q) { accS[q] = 0.f; accQ[q] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < AST_MAX_STYLES; ++k) {
+      if (k + 1 < Q) {
+        const int64_t snvec = a.style_hw[k] / V;
+        const int64_t sseg = (snvec + CS - 1) / CS;
+        const int64_t s0 = rank * sseg;
+        const int64_t s1 = (s0 + sseg < snvec) ? s0 + sseg : snvec;
+        const typename VT::elem* sbase = reinterpret_cast<const typename VT::elem*>(a.styles[k]) + row * a.style_hw[k];
+        const float x0 = VT::load1(sbase, 0);
+        const float2 nk = make_float2(-x0, -x0);
+        float2 ss[V / 2], qq[V / 2];
+#pragma unroll
+        for (int j = 0; j < V / 2; ++j) { ss[j] = make_float2(0.f, 0.f); qq[j] = make_float2(0.f, 0.f); }
+        const uint4* sp = reinterpret_cast<const uint4*>(sbase);
+        constexpr int U = 8;
+        int64_t i = s0 + threadIdx.x;
+        for (; i + (U - 1) * kThreads < s1; i += U * kThreads) {
+          uint4 u[U];
+#pragma unroll
+          for (int j = 0; j < U; ++j) u[j] = ld_stream_u4(sp + i + j * kThreads);
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            float x[V];
+            VT::unpack(u[j], x);
+#pragma unroll
+            for (int e = 0; e < V / 2; ++e) {
+              const float2 d = __fadd2_rn(make_float2(x[2 * e], x[2 * e + 1]), nk);
+              ss[e] = __fadd2_rn(ss[e], d);
+              qq[e] = __ffma2_rn(d, d, qq[e]);
+            }
+          }
+        }
+        for (; i < s1; i += kThreads) {
+          float x[V];
+          VT::unpack(ld_stream_u4(sp + i), x);
+#pragma unroll
+          for (int e = 0; e < V / 2; ++e) {
+            const float2 d = __fadd2_rn(make_float2(x[2 * e], x[2 * e + 1]), nk);
+            ss[e] = __fadd2_rn(ss[e], d);
+            qq[e] = __ffma2_rn(d, d, qq[e]);
+          }
+        }
+        float S = 0.f, Qs = 0.f;
+#pragma unroll
+        for (int e = 0; e < V / 2; ++e) { S += ss[e].x + ss[e].y; Qs += qq[e].x + qq[e].y; }
+        accS[1 + k] = S; accQ[1 + k] = Qs;
       }
     }
-    cta_merge_to(w.fold(), s_warp, &s_q[0]);
+    // the content copies have had the whole style stream to land
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const float c0 = VT::load1(a.content, row * a.HW);
+    {
+      const float2 nk = make_float2(-c0, -c0);
+      float2 ss[V / 2], qq[V / 2];
+#pragma unroll
+      for (int j = 0; j < V / 2; ++j) { ss[j] = make_float2(0.f, 0.f); qq[j] = make_float2(0.f, 0.f); }
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        int64_t i = v0 + threadIdx.x + (int64_t)j * kThreads;
+        if (i < v1) {
+          float x[V];
+          VT::unpack(s_cache[threadIdx.x + j * kThreads], x);
+#pragma unroll
+          for (int e = 0; e < V / 2; ++e) {
+            const float2 d = __fadd2_rn(make_float2(x[2 * e], x[2 * e + 1]), nk);
+            ss[e] = __fadd2_rn(ss[e], d);
+            qq[e] = __ffma2_rn(d, d, qq[e]);
+          }
+        }
+      }
+      float S = 0.f, Qs = 0.f;
+#pragma unroll
+      for (int e = 0; e < V / 2; ++e) { S += ss[e].x + ss[e].y; Qs += qq[e].x + qq[e].y; }
+      accS[0] = S; accQ[0] = Qs;
+    }
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q) {
+      if (q < Q) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          accS[q] += __shfl_xor_sync(0xffffffffu, accS[q], off);
+          accQ[q] += __shfl_xor_sync(0xffffffffu, accQ[q], off);
+        }
+        if (lane == 0) { s_red[wid][2 * q] = accS[q]; s_red[wid][2 * q + 1] = accQ[q]; }
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * Q) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < kWarps; ++w2) t += s_red[w2][threadIdx.x];
+      s_part[threadIdx.x] = t;
+    }
+    cluster.sync();   // every CTA's partial sums are complete and visible cluster-wide (CS == 1: a block barrier)
+    if ((int)threadIdx.x < Q) {
+      const int q = threadIdx.x;
+      float S = 0.f, Qs = 0.f;
+      for (unsigned c = 0; c < CS; ++c) {
+        const float* pp = cluster.map_shared_rank(s_part, c);
+        S += pp[2 * q];
+        Qs += pp[2 * q + 1];
+      }
+      const float n = q == 0 ? (float)a.HW : (float)a.style_hw[q - 1];
+      const float x0 = q == 0 ? c0 : VT::load1(reinterpret_cast<const typename VT::elem*>(a.styles[q - 1]) +
+                                               row * a.style_hw[q - 1], 0);
+      s_fin[q] = Moments{n, x0 + S / n, fmaxf(fmaf(-S, S / n, Qs), 0.f)};
+    }
   }
   const Moments* fin = s_q;
-  if (CS > 1) {
+  if (SM) {
+    fin = s_fin;
+  } else if (CS > 1) {
     cluster.sync();  // every CTA's s_q is complete and visible cluster-wide
     if ((int)threadIdx.x < Q) {
       Moments r = *cluster.map_shared_rank(&s_q[threadIdx.x], 0);
