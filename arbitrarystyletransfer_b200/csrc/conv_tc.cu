@@ -1132,8 +1132,10 @@ conv3x3_first_tc_kernel(const FirstParams fp, const ConvParams p) {
 // NORMALISED image: out-of-image taps are forced to 0 in border tiles), round to bf16, store their A rows -- and
 // are coupled to nothing but mbarriers: no block barrier, no global-load latency in their loop.
 constexpr int F2_NG = 4;                   // epilogue groups of 4 warps; group g takes every 4th tile (accumulator stage g)
-constexpr int F2_MMA_WARP = 4 + 4 * F2_NG, F2_TMA_WARP = F2_MMA_WARP + 1;
-constexpr int F2_THREADS = 32 * (F2_TMA_WARP + 1);   // warps 0-3 producers, 4-19 epilogue, 20 MMA + TMEM, 21 TMA
+constexpr int F2_PSETS = 2;                // producer sets of 4 warps: set s expands the CTA's tiles s, s + 2, s + 4, ...
+constexpr int F2_EPI_WARP0 = 4 * F2_PSETS;
+constexpr int F2_MMA_WARP = F2_EPI_WARP0 + 4 * F2_NG, F2_TMA_WARP = F2_MMA_WARP + 1;
+constexpr int F2_THREADS = 32 * (F2_TMA_WARP + 1);   // warps 0-7 producers, 8-23 epilogue, 24 MMA + TMEM, 25 TMA
 constexpr int F2_PSTAGES = 4;
 constexpr int F2_PW = 24, F2_PH = TILE_H + 2;                 // patch row = image columns [w0 - 4, w0 + 20)
 constexpr int F2_X0 = 3;                                      // column of the tile's left halo pixel (w0 - 1) in it
@@ -1274,9 +1276,13 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
         if (++ps == F2_PSTAGES) { ps = 0; pphase ^= 1u; }
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < F2_EPI_WARP0) {
     // ===================== producers: expand the patch to the 128 x 32 bf16 A tile =====================
-    const int r = threadIdx.x;           // tile row = pixel
+    // Two producer sets: set `pset` takes the CTA's tiles pset, pset + 2, ... (sequence index i), i.e. A stage i % 4 and
+    // patch stage i % 4 -- with one set the expansion of a tile (a ~1 100-cycle dependent chain per thread) set the
+    // pace of the whole kernel once the epilogue had become cheap.
+    const int pset = warp >> 2;
+    const int r = threadIdx.x & 127;     // tile row = pixel
     const int hl = r >> 4, wl = r & 15;
     float sc[3], sh[3];
 #pragma unroll
@@ -1284,9 +1290,10 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       sc[c] = fp.normalise ? fp.rstd[c] : 1.f;
       sh[c] = fp.normalise ? -fp.mean[c] * fp.rstd[c] : 0.f;
     }
-    int stage = 0, ps = 0;
+    static_assert(F_STAGES == 4 && F2_PSTAGES == 4 && F2_PSETS == 2, "a set alternates between two stages of each ring");
+    int stage = pset, ps = pset;
     uint32_t phase = 0, pphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + pset * gridDim.x; tile < p.num_tiles; tile += F2_PSETS * gridDim.x) {
       int t = tile;
       const int twi = t % p.tiles_w; t /= p.tiles_w;
       const int thi = t % p.tiles_h;
@@ -1305,7 +1312,8 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
             v[ci * 9 + kh * 3 + kw] = fmaf(pt[(ci * F2_PH + hl + kh) * F2_PW + F2_X0 + wl + kw], sc[ci], sh[ci]);
       __syncwarp();
       if (lane == 0) mbar_arrive(pempty_bar(ps));       // this warp has read its taps
-      if (++ps == F2_PSTAGES) { ps = 0; pphase ^= 1u; }
+      ps += F2_PSETS;
+      if (ps >= F2_PSTAGES) { ps -= F2_PSTAGES; pphase ^= 1u; }
       if (border) {                                       // zero padding of the normalised image (models.py:131 + pad=1)
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
@@ -1333,7 +1341,8 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
-      if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+      stage += F2_PSETS;
+      if (stage >= F_STAGES) { stage -= F_STAGES; phase ^= 1u; }
     }
   } else if (warp == F2_MMA_WARP) {
     // ===================== MMA issuer =====================
@@ -1362,12 +1371,12 @@ conv3x3_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       }
     }
   } else {
-    // ===================== epilogue (warps 4 .. 4 + 4 F2_NG) =====================
+    // ===================== epilogue (warps F2_EPI_WARP0 .. + 4 F2_NG) =====================
     if (tma_store) {
       const uint32_t staging = (smem_u32(f2_dyn) + 1023u) & ~1023u;
-      epilogue_first_store(p, &tmOut, tmem_base, warp - 4, lane, tfull_bar(0), tempty_bar(0), staging);
+      epilogue_first_store(p, &tmOut, tmem_base, warp - F2_EPI_WARP0, lane, tfull_bar(0), tempty_bar(0), staging);
     } else {
-      epilogue_loop<F_N, AST_EPI_PLAIN, TILE_W, 1, F2_NG, F2_NG>(p, tmem_base, warp - 4, lane, tfull_bar(0), tempty_bar(0));
+      epilogue_loop<F_N, AST_EPI_PLAIN, TILE_W, 1, F2_NG, F2_NG>(p, tmem_base, warp - F2_EPI_WARP0, lane, tfull_bar(0), tempty_bar(0));
     }
   }
   tc_fence_before();
