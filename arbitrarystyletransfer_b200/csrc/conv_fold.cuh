@@ -44,10 +44,22 @@ __device__ __forceinline__ void fold_parities(int pg, int& py0, int& npy, int& p
   else { py0 = pg >> 1; npy = 1; px0 = pg & 1; npx = 1; }
 }
 
-template <int BN, int NG, bool P2 = false>
+// The four parity views of the folded layer's output (pixel (2h+py, 2w+px) of the padded NHWC buffer as a tensor over
+// the LOW-res grid), for the TMA-store epilogue.
+struct FoldOutMaps { CUtensorMap m[4]; };
+
+// TS (TMA store, CTA-pair kernel, BN <= 128): warp (e, g) takes the 64 columns [64 g, 64 g + 64) of the 256-column tile
+// -- one parity's 64 channels (BN = 64) or one 64-channel half of a parity (BN = 128) -- for its 32 pixels (tile rows
+// 4e .. 4e+3), packs them into its OWN 4 KB staging buffer ([32 px][128 B], 128-byte swizzle) and lane 0 issues ONE
+// cp.async.bulk.tensor store of the {64 ch, 8 w, 4 h} box against the parity's strided view: no barrier wider than a
+// warp (a first version staged half tiles behind 512-thread named barriers: the staging alone took the layer from
+// 195 to 310 us, profiles/r2_conv_fold_tma_store.txt).  Border lanes still write the halo copies themselves.
+template <int BN, int NG, bool P2 = false, bool TS = false>
 __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem_base, int ew, int lane,
-                                              uint32_t tfull_bar0, uint32_t tempty_bar0, int rank = 0) {
+                                              uint32_t tfull_bar0, uint32_t tempty_bar0, int rank = 0,
+                                              const FoldOutMaps* om = nullptr, uint32_t staging = 0) {
   using C = CfgF<BN>;
+  static_assert(!TS || (BN <= 128 && NG == 4), "TMA store: every warp owns one 32-column chunk per half tile");
   constexpr int CH = 32, NCH = C::ACC_COLS / CH;
   const int e = ew & 3, g = ew >> 2;
   const int hl = (32 * e + lane) / T2_W, wl = (32 * e + lane) % T2_W;
@@ -68,6 +80,66 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
     if (p.epi_sleep_ns) mbar_wait_sleep(tfull_bar0 + 8u * as, aphase, p.epi_sleep_ns); else mbar_wait(tfull_bar0 + 8u * as, aphase);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
+    if constexpr (TS) {
+      const uint32_t wbuf = staging + (uint32_t)ew * 4096u;
+      const int jj = (64 * g) / BN, choff = (64 * g) % BN;            // parity slot and channel offset of this warp
+      const int py = py0 + (npx == 2 ? (jj >> 1) : jj), px = px0 + (npx == 2 ? (jj & 1) : 0);
+      uint32_t va[CH], vb[CH];
+      tmem_ld_cols(trow + (2 * g) * CH, va);
+      tmem_ld_cols(trow + (2 * g + 1) * CH, vb);
+      if (lane == 0) bulk_wait_group_read0();      // this warp's previous store has finished reading its buffer
+      __syncwarp();
+      tmem_ld_wait();
+      int rows[4], cols[4], nr = 0, nc = 0;
+      if (in_img) {
+        nr = out_targets<AST_EPI_PLAIN>(2 * h + py, p.Ho, p.halo, rows);
+        nc = out_targets<AST_EPI_PLAIN>(2 * w + px, p.Wo, p.halo, cols);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const uint32_t* v = cc ? vb : va;
+        const int ch0 = cob * BN + choff + cc * CH;
+        uint32_t pk[CH / 2];
+#pragma unroll
+        for (int i = 0; i < CH; i += 4) {
+          const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float f0 = __uint_as_float(v[i]) + b.x, f1 = __uint_as_float(v[i + 1]) + b.y;
+          const float f2 = __uint_as_float(v[i + 2]) + b.z, f3 = __uint_as_float(v[i + 3]) + b.w;
+          pk[i / 2] = p.relu ? pack_bf16_relu(f0, f1) : pack_bf16(f0, f1);
+          pk[i / 2 + 1] = p.relu ? pack_bf16_relu(f2, f3) : pack_bf16(f2, f3);
+        }
+#pragma unroll
+        for (int q = 0; q < CH / 8; ++q) {
+          const uint32_t c16 = (uint32_t)(cc * (CH / 8) + q) ^ (uint32_t)(lane & 7);
+          st_shared_v4(wbuf + (uint32_t)lane * 128u + c16 * 16u, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+        if (!(p.dbg_flags & 2)) {
+          for (int ri = 0; ri < nr; ++ri)
+            for (int ci = 0; ci < nc; ++ci) {
+              if (ri == 0 && ci == 0) continue;        // the pixel itself goes out with the TMA store
+              __nv_bfloat16* o = p.out +
+                  (((int64_t)n * (p.Ho + 2) + (rows[ri] + 1)) * (p.Wo + 2) + (cols[ci] + 1)) * p.Cout + ch0;
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+              for (int q = 0; q < CH / 8; ++q) o4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (P2) mbar_arrive_cluster(tempty_leader0 + 8u * as);
+        else mbar_arrive(tempty_bar0 + 8u * as);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && !(p.dbg_flags & 2)) {
+        tma_store_4d(&om->m[py * 2 + px], wbuf, cob * BN + choff, cur.twi * T2_W, cur.thi * T2_H + 4 * e, n);
+        bulk_commit_group();
+      }
+      if (++as == C::NACC) { as = 0; aphase ^= 1u; }
+      continue;
+    }
     uint32_t vnext[CH];
     const bool skip_ld = (p.dbg_flags & 4) != 0;
     if (g < NCH && !skip_ld) tmem_ld_cols(trow + g * CH, vnext);
@@ -126,6 +198,7 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
     }
     if (++as == C::NACC) { as = 0; aphase ^= 1u; }
   }
+  if (TS && lane == 0) bulk_wait_group0();
 }
 
 template <int BN>
@@ -352,18 +425,19 @@ struct CfgFP {
   static constexpr int SMEM_BYTES = NA * AW_SLOT + NBG * GSLOTS * B_BYTES + NBAR * 8 + 16 + 1024;
 };
 
-template <int BN>
+template <int BN, bool TS>
 __global__ void __launch_bounds__(Epi2<BN>::THREADS, 1)
 conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const ConvParams p) {
+                         const __grid_constant__ FoldOutMaps om, const ConvParams p) {
   using C = CfgFP<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t a_base = base;
-  const uint32_t b_base = base + C::NA * AW_SLOT;
-  constexpr int B_REGION = C::NBG * C::GSLOTS * C::B_BYTES;
+  // [TMA-store staging: 2 x 32 KB] [A ring] [weights: ring of NBG groups, or p.nbs = 16 resident tiles] [barriers]
+  const uint32_t a_base = base + (TS ? (uint32_t)p.tma_store : 0u);
+  const uint32_t b_base = a_base + C::NA * AW_SLOT;
+  const int B_REGION = p.nbs * C::B_BYTES;
   const uint32_t bars = b_base + B_REGION;
   auto afull = [&](int s) { return bars + 8u * s; };
   auto aempty = [&](int s) { return bars + 8u * (C::NA + s); };
@@ -373,7 +447,7 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   auto tempty = [&](int s) { return bars + 8u * (2 * C::NA + 2 * C::NBG + C::NACC + s); };
   const uint32_t tmem_slot = bars + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + C::NA * AW_SLOT + B_REGION + 8 * C::NBAR);
+      reinterpret_cast<volatile uint32_t*>(smem + (TS ? p.tma_store : 0) + C::NA * AW_SLOT + B_REGION + 8 * C::NBAR);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -382,10 +456,12 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int cblocks = p.Cin / KBLK;
   // BN = 64, Cin = Cout = 64: all sixteen half weight tiles (64 KB) fit the ring's space and stay resident
   const bool resident = (BN == 64) && cblocks == 1 && p.Cout == BN;
+  const int NBG = resident ? 1 : p.nbs / C::GSLOTS;      // weight groups in the ring (launch_fold_pair: 4, or 2 beside a staging buffer)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TS) { for (int i = 0; i < 4; ++i) tma_prefetch_desc(&om.m[i]); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
@@ -445,7 +521,7 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     ++slot;
                   }
                 }
-              if (++sb == C::NBG) { sb = 0; pb ^= 1u; }
+              if (++sb == NBG) { sb = 0; pb ^= 1u; }
             }
           }
         }
@@ -455,9 +531,9 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (++sa == C::NA) { sa = 0; pa ^= 1u; }
       }
       if (!resident) {
-        for (int i = 0; i < C::NBG; ++i) {
+        for (int i = 0; i < NBG; ++i) {
           mbar_wait(bempty(sb), pb ^ 1u);
-          if (++sb == C::NBG) { sb = 0; pb ^= 1u; }
+          if (++sb == NBG) { sb = 0; pb ^= 1u; }
         }
       }
     }
@@ -524,7 +600,7 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               for (int ix = 0; ix < npx; ++ix)
                 if (kw - (px0 + ix) >= 0 && kw - (px0 + ix) <= 1) started |= 1u << (iy * npx + ix);
             if (!resident) {
-              if (++sb == C::NBG) { sb = 0; pb ^= 1u; }
+              if (++sb == NBG) { sb = 0; pb ^= 1u; }
             }
             if (kw == px0 + npx) {
               if (++sa == C::NA) { sa = 0; pa ^= 1u; }
@@ -537,7 +613,7 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp >= 4) {
-    epilogue_fold<BN, Epi2<BN>::NG, true>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0), rank);
+    epilogue_fold<BN, Epi2<BN>::NG, true, TS>(p, tmem_base, warp - 4, lane, tfull(0), tempty(0), rank, &om, base);
   }
 
   tc_fence_before();
@@ -548,22 +624,23 @@ conv3x3_fold_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-template <int BN>
-static int launch_fold_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count,
-                            cudaStream_t s) {
+template <int BN, bool TS>
+static int launch_fold_pair_ts(const CUtensorMap& tmA, const CUtensorMap& tmB, const FoldOutMaps& om, const ConvParams& p,
+                               int sm_count, cudaStream_t s) {
   using C = CfgFP<BN>;
-  auto kern = conv3x3_fold_pair_kernel<BN>;
+  auto kern = conv3x3_fold_pair_kernel<BN, TS>;
   static bool attr_done = false;
   if (!attr_done) {
-    AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    AST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_done = true;
   }
+  const int smem_bytes = (TS ? p.tma_store : 0) + C::NA * AW_SLOT + p.nbs * C::B_BYTES + C::NBAR * 8 + 16 + 1024;
   const int max_pairs = sm_count / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs, 1, 1);
   cfg.blockDim = dim3(Epi2<BN>::THREADS, 1, 1);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -572,7 +649,44 @@ static int launch_fold_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AST_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  AST_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, om, p));
   AST_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN>
+static int launch_fold_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvParams p, int sm_count,
+                            cudaStream_t s) {
+  using C = CfgFP<BN>;
+  const bool resident = (BN == 64) && p.Cin == KBLK && p.Cout == BN;
+  p.nbs = resident ? 16 : C::NBG * C::GSLOTS;
+  FoldOutMaps om = {};
+  p.tma_store = 0;
+  if constexpr (BN <= 128) {
+    // TMA-store epilogue where the staging (64 KB) fits beside the operands: the resident 64 -> 64 layer by default
+    // (store-bound); AST_CONV_TMA_STORE=0 / 1 forces it off / on where it fits
+    static const int ts_env = getenv("AST_CONV_TMA_STORE") ? atoi(getenv("AST_CONV_TMA_STORE")) : -1;
+    const int staging = 4 * TILE_M * 128;
+    const bool want = ts_env < 0 ? resident : ts_env != 0;
+    auto fits_with = [&](int nbs) { return staging + C::NA * AW_SLOT + nbs * C::B_BYTES + C::NBAR * 8 + 16 + 1024 <= 226 * 1024; };
+    bool fits = fits_with(p.nbs);
+    if (want && !fits && !resident && fits_with(2 * C::GSLOTS)) { p.nbs = 2 * C::GSLOTS; fits = true; }   // a shallower weight ring
+    if (want && fits && p.out && aligned16(p.out) && p.Cout % 64 == 0) {
+      bool ok = true;
+      for (int py = 0; py < 2 && ok; ++py)
+        for (int px = 0; px < 2 && ok; ++px) {
+          // output pixel (2h+py, 2w+px) of the padded NHWC buffer [N][Ho+2][Wo+2][Cout] as a tensor over (c, w, h, n)
+          const uint64_t odims[4] = {(uint64_t)p.Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+          const uint64_t ostr[3] = {(uint64_t)2 * p.Cout * 2, (uint64_t)2 * (p.Wo + 2) * p.Cout * 2,
+                                    (uint64_t)(p.Ho + 2) * (p.Wo + 2) * p.Cout * 2};
+          const uint32_t obox[4] = {64, T2_W, 4, 1};      // one warp's 32 pixels: 4 tile rows of 8
+          const __nv_bfloat16* view = p.out + ((int64_t)(py + 1) * (p.Wo + 2) + (px + 1)) * p.Cout;
+          ok = encode_bf16_map(&om.m[py * 2 + px], view, 4, odims, ostr, obox) == 0;
+        }
+      if (ok) p.tma_store = staging;
+    }
+    if (!p.tma_store && !resident) p.nbs = C::NBG * C::GSLOTS;
+    if (p.tma_store) return launch_fold_pair_ts<BN, true>(tmA, tmB, om, p, sm_count, s);
+  }
+  return launch_fold_pair_ts<BN, false>(tmA, tmB, om, p, sm_count, s);
 }

@@ -316,21 +316,23 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 template <int BN>
 static int launch_pair_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, ConvParams p,
                            int sm_count, cudaStream_t s) {
-  // TMA-store epilogue (AST_CONV_TMA_STORE=1; plain tiles, BN <= 128).  OFF by default: what made conv1_1 1.8x faster
-  // (its epilogue was LSU-bound and nothing else used the shared-memory port) is a loss here -- the staging buffer's
-  // writes and the store's reads go through the port the tensor core's operand reads already saturate: measured
-  // enc_conv3 232 -> 257 us, dec_conv5 213 -> 220 us, dec_conv7 244 -> 242 us (profiles/r2_conv_pair_tma_store.txt).
-  static const int ts_env = getenv("AST_CONV_TMA_STORE") ? atoi(getenv("AST_CONV_TMA_STORE")) : 0;
+  // TMA-store epilogue (plain tiles, BN <= 128, two staging buffers).  It pays where the epilogue's per-lane sector
+  // stores are the limiter and costs where the operand rings need the shared memory more: measured enc_conv3 (Cin 64)
+  // 230 -> 209 us, dec_conv7 (Cin 128) 242 -> 242 us, dec_conv5 (Cin 256) 211 -> 220 us
+  // (profiles/r2_conv_pair_tma_store.txt; a single staging buffer was slower everywhere).  Default: Cin <= 64;
+  // AST_CONV_TMA_STORE=0 / 1 forces it off / on (A/B).
+  static const int ts_env = getenv("AST_CONV_TMA_STORE") ? atoi(getenv("AST_CONV_TMA_STORE")) : -1;
+  const bool ts_want = ts_env < 0 ? p.Cin <= 64 : ts_env != 0;
   CUtensorMap tmOut = tmA;
   p.tma_store = 0;
-  if (ts_env && epi == AST_EPI_PLAIN && BN <= 128 && p.out && !p.tap && aligned16(p.out) && p.Cout % 64 == 0) {
+  if (ts_want && epi == AST_EPI_PLAIN && BN <= 128 && p.out && !p.tap && aligned16(p.out) && p.Cout % 64 == 0) {
     // the INTERIOR of the padded NHWC output [N][H+2][W+2][Cout]: boxes are clipped at W and H, the halo is not touched
     const uint64_t odims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
     const uint64_t ostr[3] = {(uint64_t)p.Cout * 2, (uint64_t)(p.Wo + 2) * p.Cout * 2,
                               (uint64_t)(p.Ho + 2) * (p.Wo + 2) * p.Cout * 2};
     const uint32_t obox[4] = {64, T2_W, T2_H, 1};
     const __nv_bfloat16* interior = p.out + ((int64_t)(p.Wo + 2) + 1) * p.Cout;
-    if (encode_bf16_map(&tmOut, interior, 4, odims, ostr, obox) == 0) p.tma_store = (BN / 64) * TILE_M * 128;
+    if (encode_bf16_map(&tmOut, interior, 4, odims, ostr, obox) == 0) p.tma_store = 2 * (BN / 64) * TILE_M * 128;   // two buffers
   }
   pair_plan<BN>(p.Cin / KBLK, p.n_blocks, p.wide_a, p.tma_store, &p.na, &p.nbs);
   switch (epi) {

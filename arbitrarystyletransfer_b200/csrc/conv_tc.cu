@@ -202,6 +202,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
   uint32_t aphase = 0;
   TileCursor cur;
   cur.init(p, t0, tstride, P2 ? 2 : 1, rank);
+  int ts_buf = 0;
   long long dbg_wait = 0;
   const long long dbg_t0 = clock64();
   for (int tile = t0; tile < p.num_tiles; tile += tstride, cur.next()) {
@@ -223,10 +224,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
 
     mbar_wait_acc(tfull_bar0 + 8u * as, aphase, p.dbg != nullptr, dbg_wait, p.epi_sleep_ns);
     tc_fence_after();
-    if (TS) {   // the previous tile's stores have finished reading the staging buffer
-      if (ew == 0 && lane == 0) bulk_wait_group_read0();
+    if (TS) {   // two staging buffers alternate: the stores issued two tiles ago have finished reading this one
+      if (ew == 0 && lane == 0) bulk_wait_group_read1();
       named_bar_sync(1, 128 * NG);
     }
+    const uint32_t stg = TS ? staging + (ts_buf ? (uint32_t)(BN / 64) * (TILE_M * 128) : 0u) : 0u;
     const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
     uint32_t vnext[CH];
     const bool skip_ld = (p.dbg_flags & 4) != 0;
@@ -298,7 +300,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
         }
         if (TS) {
           const int m = 32 * e + lane, cl = chunk * CH;        // tile row, first channel of the chunk in the tile
-          const uint32_t rowa = staging + (uint32_t)(cl >> 6) * (TILE_M * 128) + (uint32_t)m * 128u;
+          const uint32_t rowa = stg + (uint32_t)(cl >> 6) * (TILE_M * 128) + (uint32_t)m * 128u;
 #pragma unroll
           for (int q = 0; q < CH / 8; ++q) {
             const uint32_t c16 = (uint32_t)(((cl & 63) >> 3) + q) ^ (uint32_t)(m & 7);
@@ -337,9 +339,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
       if (ew == 0 && lane == 0 && !(p.dbg_flags & 2)) {
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b)
-          tma_store_4d(tmOut, staging + (uint32_t)b * (TILE_M * 128), nb * BN + b * 64, twi * TW, thi * TH, n);
+          tma_store_4d(tmOut, stg + (uint32_t)b * (TILE_M * 128), nb * BN + b * 64, twi * TW, thi * TH, n);
         bulk_commit_group();
       }
+      ts_buf ^= 1;
     }
     as += TG;
     if (as >= NACC) { as -= NACC; aphase ^= 1u; }
