@@ -47,6 +47,7 @@ PROTOTYPES = {
     "ast_channel_stats_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _u, _vp]),
     "ast_mvn_fwd": (_i, [_vp, _vp, _vp, _i64, _i64, _f, _u, _vp]),
     "ast_mvn_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _u, _vp]),
+    "ast_adain_bwd": (_i, [_vp, _vp, _vp, _fp, _i, _f, _vp, _vp, _i64, _i64, _u, _vp]),
     "ast_huber_ws_bytes": (_sz, [_i64]),
     "ast_huber_fwd": (_i, [_vp, _vp, _vp, _i64, _f, _vp, _sz, _vp]),
     "ast_huber_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _vp]),

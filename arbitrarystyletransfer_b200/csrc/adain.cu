@@ -661,6 +661,61 @@ __global__ void __launch_bounds__(kThreads) mvn_bwd_kernel(const void* x, const 
   }
 }
 
+struct AdainBwdW { float w[AST_MAX_STYLES]; };
+
+// AdaIN backward with respect to the content map, plus everything the style gradients need, in one kernel.
+// Forward (models.py:43-51, :471): y = alpha * (z A + B) + (1 - alpha) c with z = (c - mu) / sigma (unbiased sigma, no
+// eps) and, per row, (A, B) = sum_k w_k (mean_k, std_k) of the style maps [reference binding, models.py:44] or
+// sum_k w_k (std_k, mean_k) [canonical].  With g = dL/dy:
+//   gc = alpha A / sigma * (g - mean(g) - z sum(g z) / (HW - 1)) + (1 - alpha) g
+//   dA = alpha sum(g z), dB = alpha sum(g)  ->  per style k: g_mean_k, g_std_k = w_k (dA, dB) [or (dB, dA)]
+// aux[k] = (mean_k, std_k, g_mean_k, g_std_k), each [rows], contiguous: the arguments of ast_channel_stats_bwd.
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads) adain_bwd_kernel(const void* c, const void* gy, const float* stats, int K,
+                                                            const AdainBwdW ww, float alpha, void* gc, float* aux,
+                                                            int64_t rows, int64_t HW, unsigned flags) {
+  const float* w = ww.w;
+  using VT = Vec16<BF16>;
+  using E = typename VT::elem;
+  __shared__ float s_red[kWarps];
+  const int64_t row = blockIdx.x;
+  const E* xr = reinterpret_cast<const E*>(c) + row * HW;
+  const E* gr = reinterpret_cast<const E*>(gy) + row * HW;
+  E* o = reinterpret_cast<E*>(gc) + row * HW;
+  const float* st = stats + row * (2 + 2 * K);
+  const float n = (float)HW;
+  const float mu = st[0], rs = 1.f / st[1];
+  float A = 0.f;
+  for (int k = 0; k < K; ++k) A = fmaf(w[k], st[2 + 2 * k + ((flags & AST_F_CANONICAL) ? 1 : 0)], A);
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t i = threadIdx.x; i < HW; i += kThreads) {
+    const float g = VT::load1(gr, i);
+    const float z = (VT::load1(xr, i) - mu) * rs;
+    s1 += g;
+    s2 = fmaf(g, z, s2);
+  }
+  s1 = block_sum(s1, s_red);
+  s2 = block_sum(s2, s_red);
+  const float gmean = s1 / n, cz = s2 / (n - 1.f);
+  const float sc = alpha * A * rs, direct = 1.f - alpha;
+  for (int64_t i = threadIdx.x; i < HW; i += kThreads) {
+    const float g = VT::load1(gr, i);
+    const float z = (VT::load1(xr, i) - mu) * rs;
+    VT::store1(o, i, fmaf(sc, (g - gmean) - z * cz, direct * g));
+  }
+  if (threadIdx.x == 0 && aux) {
+    const float dA = alpha * s2, dB = alpha * s1;
+    for (int k = 0; k < K; ++k) {
+      float* a = aux + (int64_t)k * 4 * rows;
+      a[row] = st[2 + 2 * k];
+      a[rows + row] = st[3 + 2 * k];
+      const bool canon = (flags & AST_F_CANONICAL) != 0;
+      a[2 * rows + row] = w[k] * (canon ? dB : dA);     // dL/d mean_k
+      a[3 * rows + row] = w[k] * (canon ? dA : dB);     // dL/d std_k
+    }
+  }
+}
+
 // ---- host dispatch -------------------------------------------------------------------------
 template <bool BF16, int R>
 static int launch_cached(const AdainArgs& a, int64_t rows, unsigned CS, cudaStream_t s) {
@@ -785,6 +840,23 @@ extern "C" int ast_mvn_bwd(const void* x, const void* gy, const float* stats, vo
     mvn_bwd_kernel<true><<<(unsigned)rows, kThreads, 0, s>>>(x, gy, stats, gx, HW, flags);
   else
     mvn_bwd_kernel<false><<<(unsigned)rows, kThreads, 0, s>>>(x, gy, stats, gx, HW, flags);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_adain_bwd(const void* content, const void* gy, const float* stats, const float* style_w, int K,
+                             float alpha, void* g_content, float* aux, int64_t rows, int64_t HW, unsigned flags,
+                             void* stream) {
+  if (!content || !gy || !stats || !style_w || !g_content || K < 1 || K > AST_MAX_STYLES || rows <= 0 || HW <= 1)
+    return AST_E_BADARG;
+  if (rows >= 0x7fffffffLL) return AST_E_SHAPE;
+  AdainBwdW ww = {};
+  for (int k = 0; k < K; ++k) ww.w[k] = style_w[k];
+  cudaStream_t s = (cudaStream_t)stream;
+  if (flags & AST_F_BF16)
+    adain_bwd_kernel<true><<<(unsigned)rows, kThreads, 0, s>>>(content, gy, stats, K, ww, alpha, g_content, aux, rows, HW, flags);
+  else
+    adain_bwd_kernel<false><<<(unsigned)rows, kThreads, 0, s>>>(content, gy, stats, K, ww, alpha, g_content, aux, rows, HW, flags);
   AST_CHECK_LAUNCH();
   return 0;
 }

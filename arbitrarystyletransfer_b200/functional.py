@@ -72,6 +72,55 @@ def adain_forward(content: torch.Tensor, styles: Sequence[torch.Tensor],
     return (out, stats) if return_stats else out
 
 
+class _AdaIN(torch.autograd.Function):
+    """AdaIN.forward (models.py:43-51) + alpha blend (:471) for feature maps that require grad: the fused forward
+    kernel, and a backward made of kernels only -- ``ast_adain_bwd`` (content gradient + the per-row statistics
+    gradients of every style) and ``ast_channel_stats_bwd`` per style map."""
+
+    @staticmethod
+    def forward(ctx, alpha, canonical, weights, content, *styles):
+        out, stats = adain_forward(content, list(styles), list(weights), alpha, canonical, return_stats=True)
+        ctx.save_for_backward(_c(content), stats, *[_c(s) for s in styles])
+        ctx.alpha, ctx.canonical, ctx.weights = float(alpha), bool(canonical), [float(w) for w in weights]
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.load()
+        content, stats, *styles = ctx.saved_tensors
+        K = len(styles)
+        N, Cc = content.shape[:2]
+        rows, HW = N * Cc, content[0, 0].numel()
+        gy = _c(gy.to(content.dtype))
+        gc = torch.empty_like(content)
+        need_styles = any(ctx.needs_input_grad[4 + k] for k in range(K))
+        aux = torch.empty(K, 4, rows, device=content.device, dtype=torch.float32) if need_styles else None
+        fl = _flags(content, ctx.canonical)
+        L.check(lib.ast_adain_bwd(content.data_ptr(), gy.data_ptr(), stats.data_ptr(), L.float_array(ctx.weights), K,
+                                  ctx.alpha, gc.data_ptr(), L.ptr(aux), rows, HW, fl, L.stream_ptr(content.device)),
+                "ast_adain_bwd")
+        gs = []
+        for k, s in enumerate(styles):
+            if not ctx.needs_input_grad[4 + k]:
+                gs.append(None)
+                continue
+            g = torch.empty_like(s)
+            a = aux[k]
+            L.check(lib.ast_channel_stats_bwd(s.data_ptr(), a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(),
+                                              a[3].data_ptr(), g.data_ptr(), rows, s[0, 0].numel(),
+                                              _flags(s), L.stream_ptr(s.device)), "ast_channel_stats_bwd")
+            gs.append(g)
+        return (None, None, None, gc if ctx.needs_input_grad[3] else None, *gs)
+
+
+def adain_autograd(content, styles, weights=None, alpha: float = 1.0, canonical: bool = False):
+    """Differentiable fused AdaIN (see :class:`_AdaIN`)."""
+    styles = [styles] if isinstance(styles, torch.Tensor) else list(styles)
+    K = len(styles)
+    weights = list(weights) if weights is not None else [1.0 / K] * K
+    return _AdaIN.apply(alpha, canonical, tuple(weights), content, *styles)
+
+
 # ------------------------------------------------------------------------------------------
 # channel_stats                          reference: model_util.py:3-8, models.py:54-62
 # ------------------------------------------------------------------------------------------

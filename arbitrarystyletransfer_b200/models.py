@@ -46,21 +46,9 @@ class AdaIN(nn.Module):
 
 
 def _adain_autograd(content, styles, weights, alpha, canonical):
-    """Differentiable composition out of the differentiable kernels (MVN with eps = 0 and
-    channel statistics); used only when a feature map requires grad."""
-    K = len(styles)
-    weights = weights or [1.0 / K] * K
-    z = Fn.mean_variance_norm(content, eps=0.0)
-    A = B = None
-    for w, s in zip(weights, styles):
-        m, sd = channel_stats(s)
-        a, b = (sd, m) if canonical else (m, sd)
-        A = w * a if A is None else A + w * a
-        B = w * b if B is None else B + w * b
-    t = z * A + B
-    if alpha != 1.0:
-        t = alpha * t + (1 - alpha) * content
-    return t
+    """Differentiable AdaIN: the fused forward kernel with a backward made of kernels only
+    (functional._AdaIN: ast_adain_bwd + ast_channel_stats_bwd); used when a feature map requires grad."""
+    return Fn.adain_autograd(content, styles, weights, alpha, canonical)
 
 
 def calc_mean_std(feat, eps=1e-5):

@@ -89,6 +89,16 @@ int ast_mvn_fwd(const void* x, void* y, float* stats, int64_t rows, int64_t HW,
 int ast_mvn_bwd(const void* x, const void* gy, const float* stats, void* gx,
                 int64_t rows, int64_t HW, unsigned flags, void* stream);
 
+/* Backward of ast_adain_fwd (AdaIN.forward models.py:43-51 + the alpha blend :471, eps = 0) for a feature map that
+ * requires grad.  gy = dL/d out.  stats = the [rows][2+2K] array ast_adain_fwd wrote; style_w = K host floats.
+ *   g_content = alpha A / sigma_c * (gy - mean(gy) - z sum(gy z) / (HW-1)) + (1 - alpha) gy,  z = (c - mu_c) / sigma_c
+ *   aux (optional, device [K][4][rows] fp32) = per style k: mean_k, std_k, dL/d mean_k, dL/d std_k -- the arguments
+ *   of ast_channel_stats_bwd on style map k, which completes the style gradients.
+ * flags: AST_F_BF16, AST_F_CANONICAL as in the forward call. */
+int ast_adain_bwd(const void* content, const void* gy, const float* stats, const float* style_w, int K,
+                  float alpha, void* g_content, float* aux, int64_t rows, int64_t HW, unsigned flags,
+                  void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K3  losses.
  * ------------------------------------------------------------------------------------- */

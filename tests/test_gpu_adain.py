@@ -162,6 +162,49 @@ def test_adain_autograd_matches_oracle():
     close(cg.grad, cr.grad, rtol=1e-4); close(sg.grad, sr.grad, rtol=1e-4)
 
 
+@pytest.mark.parametrize("canonical", [False, True])
+def test_adain_autograd_two_styles_weights_and_partial_grads(canonical):
+    """The kernel-only backward (ast_adain_bwd + ast_channel_stats_bwd) against torch autograd through the oracle's
+    formula: K = 2 styles of different sizes, mix weights, alpha blend, both bindings of (A, B); then with only the
+    styles / only the content requiring grad."""
+    from arbitrarystyletransfer_b200 import models as M
+    g = torch.Generator().manual_seed(18)
+    c = torch.randn(2, 6, 8, 12, generator=g) * 1.5 + 0.5
+    s1 = torch.randn(2, 6, 5, 7, generator=g) * 0.7 + 2
+    s2 = torch.randn(2, 6, 9, 4, generator=g) * 1.2 - 1
+    go = torch.randn(2, 6, 8, 12, generator=g)
+    w, alpha = [0.3, 0.7], 0.6
+
+    def ref(c_, a_, b_):
+        mu = c_.mean(dim=(2, 3), keepdim=True)
+        sd = c_.std(dim=(2, 3), keepdim=True)
+        A = B = 0
+        for wk, sk in zip(w, (a_, b_)):
+            m, d = sk.mean(dim=(2, 3), keepdim=True), sk.std(dim=(2, 3), keepdim=True)
+            A = A + wk * (d if canonical else m)      # models.py:44 binds them swapped; canonical = the paper's form
+            B = B + wk * (m if canonical else d)
+        t = (c_ - mu) / sd * A + B
+        return alpha * t + (1 - alpha) * c_
+
+    cr, ar, br = (t.clone().double().requires_grad_(True) for t in (c, s1, s2))
+    ref(cr, ar, br).backward(go.double())
+    cg, ag, bg = (t.cuda().requires_grad_(True) for t in (c, s1, s2))
+    layer = M.AdaIN()
+    layer.canonical = canonical
+    out = layer(cg, [ag, bg], alpha=alpha, style_weights=w)
+    out.backward(go.cuda())
+    close(out.detach(), ref(c.double(), s1.double(), s2.double()).float(), rtol=1e-4)
+    for got, want in ((cg.grad, cr.grad), (ag.grad, ar.grad), (bg.grad, br.grad)):
+        close(got, want.float(), rtol=2e-4)
+    # only the styles require grad / only the content requires grad
+    a2, b2 = (t.cuda().requires_grad_(True) for t in (s1, s2))
+    layer(c.cuda(), [a2, b2], alpha=alpha, style_weights=w).backward(go.cuda())
+    close(a2.grad, ar.grad.float(), rtol=2e-4); close(b2.grad, br.grad.float(), rtol=2e-4)
+    c2 = c.cuda().requires_grad_(True)
+    layer(c2, [s1.cuda(), s2.cuda()], alpha=alpha, style_weights=w).backward(go.cuda())
+    close(c2.grad, cr.grad.float(), rtol=2e-4)
+
+
 def test_errors():
     from arbitrarystyletransfer_b200 import _lib as L, functional as Fn
     c = torch.zeros(1, 4, 8, 8, device="cuda")
