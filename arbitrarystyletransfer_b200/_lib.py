@@ -64,6 +64,7 @@ PROTOTYPES = {
     "ast_conv3x3_fwd": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "ast_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ast_pack_conv_weight_fold": (_i, [_vp, _vp, _i, _i, _vp]),
+    "ast_conv12_fused": (_i, [_vp, _vp, _vp, _fp, _fp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ast_conv3x3_first": (_i, [_vp, _vp, _vp, _fp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_conv3x3_last": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_nchw_to_native": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -16,6 +16,8 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
                      cudaStream_t s);
 int conv3x3_last_tc(const void* in, const void* wpk16, const float* bias, float* out, int N, int H,
                     int W, int Cin, int Cout, int clamp01, int kwbox, cudaStream_t s);
+int conv12_fused(const float* img, const float* w1, const float* b1, const float* mean, const float* std_,
+                 const void* wpk2, const float* b2, void* out, int N, int H, int W, cudaStream_t s);
 }  // namespace tc
 
 // ---- weight packing: OIHW fp32 -> bf16 [9][Cout][Cin] -------------------------------------------
@@ -363,6 +365,12 @@ extern "C" int ast_conv3x3_fwd(const ast_conv_desc* d, const void* in, const voi
       reinterpret_cast<__nv_bfloat16*>(out), tap, *d, Ho, Wo);
   AST_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int ast_conv12_fused(const float* img, const float* w1, const float* b1, const float* mean,
+                                const float* std_, const void* wpk2, const float* b2, void* out, int N, int H, int W,
+                                void* stream) {
+  return tc::conv12_fused(img, w1, b1, mean, std_, wpk2, b2, out, N, H, W, (cudaStream_t)stream);
 }
 
 extern "C" int ast_conv3x3_first(const float* img, const float* w, const float* bias,

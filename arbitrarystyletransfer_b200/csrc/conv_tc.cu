@@ -1492,6 +1492,8 @@ int conv3x3_first_tc(const float* img, const float* w, const float* bias, const 
   return 0;
 }
 
+#include "conv12_fused.cuh"
+
 int conv3x3_last_tn(const void* in, const void* wpk16, const float* bias, float* out, int N, int H, int W, int Cout,
                     int clamp01, int sm_count, cudaStream_t s);   // conv_last_tn.cu
 

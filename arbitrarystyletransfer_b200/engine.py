@@ -10,6 +10,7 @@ boundary: images in, image out, and optional feature taps.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Sequence
 
 import torch
@@ -164,6 +165,19 @@ def conv3x3_first(img, w, bias, out_native, tap=None, tap_prerelu=True, normalis
     return out_native
 
 
+def conv12_fused(img, w1, b1, wpk2, b2, out_native, normalise=True):
+    """Normalization + conv_1 + relu_1 + conv_2 + relu_2 + pool_2 (models.py:129-131, 198-224) in one kernel:
+    (N,3,H,W) fp32 -> native bf16 [N][H/2+2][W/2+2][64]; the full-resolution 64-channel map never reaches HBM."""
+    lib = L.load()
+    N, _, H, W = img.shape
+    mean = L.float_array(IMAGENET_MEAN) if normalise else None
+    std = L.float_array(IMAGENET_STD) if normalise else None
+    L.check(lib.ast_conv12_fused(img.data_ptr(), w1.data_ptr(), b1.data_ptr(), mean, std, wpk2.data_ptr(),
+                                 b2.data_ptr(), out_native.data_ptr(), N, H, W, L.stream_ptr(img.device)),
+            "ast_conv12_fused")
+    return out_native
+
+
 def conv3x3_last(x_native, w, wpk16, bias, out, clamp01=False, impl=L.CONV_AUTO):
     """Last decoder conv (models.py:626-627): native bf16 with reflection halo -> NCHW fp32."""
     lib = L.load()
@@ -281,6 +295,9 @@ class StyleTransferEngine:
         self.dec_wpk = [pack_conv_weight(w.to(dev)) for w in dec_w[:8]] + [None]
         self.dec_wfold = {i: pack_conv_weight_fold(dec_w[i].to(dev)) for i in FOLD_LAYERS}
         self.fold = True      # evaluate the three post-upsample convs on the low-res map (AST_EPI_UPFOLD)
+        # conv1_1 + conv1_2 (+ pool) in one kernel (ast_conv12_fused) where its shape rules hold; AST_CONV12_FUSED=0
+        # keeps the two separate launches (A/B reference)
+        self.fuse12 = os.environ.get("AST_CONV12_FUSED", "1") != "0"
         self.dec_w_last = dec_w[8].detach().to(dev, torch.float32).contiguous()
         self.dec_wpk_last = pack_conv_weight(self.dec_w_last, cout_pad=16)
         self.buf = _Buffers()
@@ -298,11 +315,18 @@ class StyleTransferEngine:
             raise L.AstError("images must have 3 channels")
         dev = img.device
         st = L.stream_ptr(dev)
-        x = self.buf.get("enc0", N, H, W, 64, dev, True)
-        with _Span("enc_conv1"):
-            conv3x3_first(img, self.vgg_w0, self.vgg_b[0], x, impl=self.impl_edge)
         h, w = H, W
-        for i in range(1, 9):
+        first = 1
+        if self.fused12_ok(H, W):
+            x = self.buf.get("enc1", N, H // 2, W // 2, 64, dev, True)
+            with _Span("enc_conv12"):
+                conv12_fused(img, self.vgg_w0, self.vgg_b[0], self.vgg_wpk[1], self.vgg_b[1], x)
+            h, w, first = H // 2, W // 2, 2
+        else:
+            x = self.buf.get("enc0", N, H, W, 64, dev, True)
+            with _Span("enc_conv1"):
+                conv3x3_first(img, self.vgg_w0, self.vgg_b[0], x, impl=self.impl_edge)
+        for i in range(first, 9):
             cin, cout, pool = self.plan[i]
             ho, wo = (h // 2, w // 2) if pool else (h, w)
             last = i == 8
@@ -383,9 +407,14 @@ class StyleTransferEngine:
             self._f32buf[k] = t
         return t
 
-    def launches_per_stylize(self, K: int = 1) -> int:
+    def fused12_ok(self, H: int, W: int) -> bool:
+        """Whether encode() runs the first two VGG layers as one kernel at this image size."""
+        return (self.fuse12 and self.impl == L.CONV_AUTO and self.impl_edge == L.CONV_AUTO and W % 4 == 0
+                and H % 2 == 0 and H >= 2 and W >= 4 and self.plan[1] == (64, 64, True))
+
+    def launches_per_stylize(self, K: int = 1, H: int = 512, W: int = 512) -> int:
         """Kernels of libast_b200 launched by one stylize() call (for bench.py's gpu_launches)."""
-        return (1 + K) * 9 + 3 + 9
+        return (1 + K) * (8 if self.fused12_ok(H, W) else 9) + 3 + 9
 
 
 class HostPipeline:

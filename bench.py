@@ -216,8 +216,17 @@ def layer_table(eng, N, size):
     from arbitrarystyletransfer_b200 import engine as E
     rows = {}
     h = size
+    fused12 = eng.fused12_ok(size, size)
     for i, (cin, cout, pool) in enumerate(eng.plan):
         f = 2.0 * cout * cin * 9 * h * h * N
+        if fused12 and i == 0:      # conv1_1 + conv1_2 (+ pool) are ONE launch (ast_conv12_fused): one row, both layers' FLOPs
+            f12 = f + 2.0 * 64 * 64 * 9 * h * h * N
+            rows["enc_conv12"] = {"layer": "enc_conv12", "cin": 3, "cout": 64, "hw": h, "epi": "conv1_1 + conv1_2 + pool, fused",
+                                  "per_step": 2, "flops": f12, "flops_executed": f12}
+            continue
+        if fused12 and i == 1:
+            h //= 2
+            continue
         rows[f"enc_conv{i + 1}"] = {"layer": f"enc_conv{i + 1}", "cin": cin, "cout": cout, "hw": h,
                                     "epi": "pool" if pool else "plain", "per_step": 2, "flops": f, "flops_executed": f}
         if pool:
@@ -328,7 +337,7 @@ def time_edge_layers(eng, N, S, reps=10):
     ms_l = timed(lambda: E.conv3x3_last(xd, eng.dec_w_last, eng.dec_wpk_last, eng.dec_b[8], out, False, impl=eng.impl_edge))
     bf = N * 3 * S * S * 4 + N * S * S * 64 * 2
     bl = N * (S + 2) * (S + 2) * 64 * 2 + N * 3 * S * S * 4
-    return {"first": {"kernel": "conv3x3_first_tma_kernel (conv1_1, 2 launches/step)", "bound": "hbm", "ms_per_launch": ms_f,
+    return {"first": {"kernel": "conv3x3_first_tma_kernel (conv1_1 alone: the kernel of passes that tap relu1_1 / relu1_2, e.g. training; the inference step fuses conv1_1 into conv1_2)", "bound": "hbm", "ms_per_launch": ms_f,
                       "bytes_per_launch": bf, "achieved": bf / ms_f / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
                       "frac": bf / ms_f / 1e6 / pk["hbm_gbs"], "traffic": ncu_traffic("conv3x3_first_tma_kernel")},
             "last": {"kernel": "conv3x3_last_tn_kernel (decoder image layer, 1 launch/step)", "bound": "hbm",
@@ -896,7 +905,7 @@ def run_native(args):
                                           "h2d_bytes_per_step": 2 * c_host.numel() * 4,
                                           "d2h_bytes_per_step": out_host.numel() * 4,
                                           "api": "engine.HostPipeline(dtype='f32').submit: fp32 (N,3,H,W) host tensors"}},
-            "gpu_launches": eng.launches_per_stylize(1) * args.steps,
+            "gpu_launches": eng.launches_per_stylize(1, S, S) * args.steps,
             "clocks": clk.summary()}
 
     if rank == 0:
@@ -920,8 +929,9 @@ def run_native(args):
         mhz = line["sustained"].get("sm_mhz_median") or 0.0
         clock_peak = sms * 8192.0 * mhz * 1e6 / 1e12 if mhz else None
         line["roofline"] = {"bound": "tensor",
-                            "kernel": f"conv3x3_pair_kernel + conv3x3_fold_pair_kernel (tcgen05.mma.cta_group::2 implicit GEMM, "
-                                      f"{n_tc} launches/step)",
+                            "kernel": f"conv3x3_pair_kernel + conv3x3_fold_pair_kernel"
+                                      + (" + conv12_fused_pair_kernel" if eng.fused12_ok(S, S) else "")
+                                      + f" (tcgen05.mma.cta_group::2 implicit GEMM, {n_tc} launches/step)",
                             "achieved": ach_x, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                             "frac": ach_x / pk["bf16_tflops_sustained"],
                             "achieved_algorithmic": ach, "frac_algorithmic": ach / pk["bf16_tflops_sustained"],
@@ -942,7 +952,7 @@ def run_native(args):
                             "share_of_step": tc_ms / step_ms,
                             "step_ms_instrumented": step_ms,
                             "step_accounting_ms": {"tcgen05_3x3_convs": tc_ms, "conv1_1_x2": conv_ms - tc_ms - next(
-                                                       r["ms"] for r in rows if r["layer"] == "dec_conv9"),
+                                                       r["ms"] for r in rows if r["layer"] == "dec_conv9"),   # 0 when fused into conv1_2
                                                    "image_layer": next(r["ms"] for r in rows if r["layer"] == "dec_conv9"),
                                                    "adain_native": other_ms,
                                                    "gaps_between_launches": step_ms - conv_ms - other_ms},

@@ -212,6 +212,17 @@ int ast_pack_conv_weight(const float* w_oihw, void* wpk, int Cout, int Cin, int 
  * alike -- rounded to bf16 once.  Replaces nn.Upsample + nn.ReflectionPad2d + nn.Conv2d, models.py:602-604 etc. */
 int ast_pack_conv_weight_fold(const float* w_oihw, void* wpk, int Cout, int Cin, void* stream);
 
+/* The first TWO VGG layers in one kernel (csrc/conv12_fused.cuh): Normalization (models.py:129-131) + conv_1 (3->64,
+ * zero pad) + relu_1 + conv_2 (64->64, zero pad) + relu_2 + pool_2 (models.py:198-224, vgg19.features[0..4]) from the
+ * reference's NCHW fp32 image; the 64-channel full-resolution map between the two convs never reaches HBM.  For passes
+ * that tap neither relu_1 nor relu_2 (inference to relu4_1).
+ *   img : fp32 [N][3][H][W], W % 4 == 0, H % 2 == 0; w1 : fp32 OIHW [64][3][3][3]; b1 fp32 [64]
+ *   mean/std : 3 host floats each (NULL = no normalisation)
+ *   wpk2 : ast_pack_conv_weight of conv_2, bf16 [9][64][64]; b2 fp32 [64]
+ *   out : bf16 [N][H/2+2][W/2+2][64] (interior only). */
+int ast_conv12_fused(const float* img, const float* w1, const float* b1, const float* mean, const float* std_,
+                     const void* wpk2, const float* b2, void* out, int N, int H, int W, void* stream);
+
 /* First VGG layer: Normalization (models.py:129-131) + conv_1 (3->Cout, zero pad) + ReLU from
  * the reference's NCHW fp32 image straight into the native layout.  Cout == 64 runs on the tensor
  * cores (im2col A tile built in shared memory, K = 27 padded to 32) unless impl = AST_CONV_DIRECT.
