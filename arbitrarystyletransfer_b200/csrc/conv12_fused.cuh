@@ -27,8 +27,8 @@
 constexpr int G_WARP_PROD0 = 4, G_PSETS = 2;
 constexpr int G_WARP_MID0 = G_WARP_PROD0 + 4 * G_PSETS;      // 12
 constexpr int G_WARP_EPI0 = G_WARP_MID0 + 8;                 // 20
-constexpr int G_EPI_NG = 2;
-constexpr int G_THREADS = 32 * (G_WARP_EPI0 + 4 * G_EPI_NG); // 896
+constexpr int G_EPI_NG = 2, G_EPI_TG = 1;                    // eight epilogue warps on one tile, 32 columns per tcgen05.ld
+constexpr int G_THREADS = 32 * (G_WARP_EPI0 + 4 * G_EPI_NG * G_EPI_TG); // 896
 constexpr int G_ROWS = T2_BOX_H * WA_W;                      // 180 conv1_1 pixels per tile
 constexpr int G_PW = 16, G_PH = T2_H + 4, G_X0 = 2;          // patch: columns [w0 - 4, w0 + 12), rows [h0 - 2, h0 + 18)
 constexpr int G_PATCH_FLOATS = 3 * G_PH * G_PW;              // 960
@@ -50,6 +50,9 @@ constexpr int G_OFF_BAR = G_OFF_PATCH + G_PSTAGES * G_PATCH_BYTES;
 constexpr int G_NBAR = 2 * G_PSTAGES + 4 * G_PSETS + 2 * G_NA2 + 1 + 2 * G_NACC;
 constexpr int G_SMEM_BYTES = G_OFF_BAR + G_NBAR * 8 + 16 + 1024;
 
+// V: bit 0 = per-role register budgets (setmaxnreg), bit 1 = mid warps work on 32 columns at a time; DBG: elimination
+// flags and wait counters compiled in (AST_CONV_DEBUG / AST_CONV_DBGFLAGS)
+template <int V, bool DBG>
 __global__ void __launch_bounds__(G_THREADS, 1)
 conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_constant__ CUtensorMap tmB2,
                          const FirstParams fp, const ConvParams p) {
@@ -118,15 +121,13 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tmem_t1 = tmem_base, tmem_t2 = tmem_base + 256u;    // conv1_1: 2 stages x 2 blocks x 64 columns; conv1_2: 4 x 64
 
-  // this CTA's i-th tile: spatial tile 2 * (pair0 + i * npairs) + rank
-  auto tile_coords = [&](int i, int& h0, int& w0, int& n) {
-    int t = 2 * (pair0 + i * npairs) + rank;
-    const int twi = t % p.tiles_w; t /= p.tiles_w;
-    const int thi = t % p.tiles_h;
-    n = t / p.tiles_h;
-    h0 = thi * T2_H; w0 = twi * T2_W;
-  };
+  // this CTA's i-th tile is spatial tile 2 * (pair0 + i * npairs) + rank (TileCursor with mult = 2)
 
+  // Register budget per warpgroup (896 threads x 72 at launch): the control warps and the mid warps hand registers to the
+  // epilogue warps, whose spills would otherwise share the shared-memory / L1 port with the MMA's operand reads
+  const int dflags = DBG ? p.dbg_flags : 0;
+  if (warp < G_WARP_PROD0) {
+    if (V & 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================== TMA: resident conv1_2 weights, then the image patches =====================
     if (lane == 0) {
@@ -137,9 +138,10 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
           tma_load_3d_2sm(b2_base + (kw * 3 + kh) * G_B2_TILE, &tmB2, b2full_l, 0, rank * 32, kh * 3 + kw);
       int ps = 0;
       uint32_t pph = 0;
-      for (int i = 0; i < ntiles; ++i) {
-        int h0, w0, n;
-        tile_coords(i, h0, w0, n);
+      TileCursor cur;
+      cur.init(p, pair0, npairs, 2, rank);
+      for (int i = 0; i < ntiles; ++i, cur.next()) {
+        const int h0 = cur.thi * T2_H, w0 = cur.twi * T2_W, n = cur.n;
         mbar_wait(pempty(ps), pph ^ 1u);
         mbar_expect_tx(pfull(ps), G_PATCH_BYTES);
         tma_load_4d(base + G_OFF_PATCH + ps * G_PATCH_BYTES, &tmImg, pfull(ps), w0 - 4, h0 - 2, 0, n);
@@ -164,11 +166,13 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       const uint64_t b2_desc0 = make_sdesc_k128(b2_base);
       constexpr uint32_t A2_SLOT16 = AW_SLOT >> 4, KH16 = (WA_W * KBLK * 2) >> 4;
       constexpr uint64_t B2_SLOT16 = G_B2_TILE >> 4;
+      const bool dbg = DBG && p.dbg != nullptr;
+      long long w_a1 = 0, w_t1e = 0, w_a2 = 0, w_te = 0;
       auto issue_conv11 = [&](int i) {       // tile i of this pair: A1 stage / TMEM stage s = i & 1
         const int s = i & 1;
         const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait(a1full(s), ph);
-        mbar_wait(t1empty(s), ph ^ 1u);
+        mbar_wait_acc(a1full(s), ph, dbg, w_a1);
+        mbar_wait_acc(t1empty(s), ph ^ 1u, dbg, w_t1e);
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
@@ -185,14 +189,16 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
         }
         __syncwarp();
       };
+      const bool no_c12 = (dflags & 256) != 0;
+      const long long t_begin = clock64();
       issue_conv11(0);
       int sa = 0, as = 0;
       uint32_t pa = 0, aphase = 0;
       mbar_wait(b2full, 0u);
       for (int i = 0; i < ntiles; ++i) {
         if (i + 1 < ntiles) issue_conv11(i + 1);      // its accumulators are packed while this tile's conv1_2 runs
-        mbar_wait(a2full(sa), pa);
-        mbar_wait(tempty(as), aphase ^ 1u);
+        mbar_wait_acc(a2full(sa), pa, dbg, w_a2);
+        mbar_wait_acc(tempty(as), aphase ^ 1u, dbg, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_t2 + (uint32_t)(as * 64);
         const uint32_t ad0 = a2_lo0 + (uint32_t)sa * A2_SLOT16;
@@ -201,6 +207,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
           for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
+              if (no_c12 && (kw | kh)) continue;
 #pragma unroll
               for (int k = 0; k < KBLK / 16; ++k) {
                 umma_bf16_2sm(d_tmem, a2_desc(ad0 + (uint32_t)(kw * 8 + kh * KH16 + k * 2)),
@@ -215,7 +222,12 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
         if (++sa == G_NA2) { sa = 0; pa ^= 1u; }
         if (++as == G_NACC) { as = 0; aphase ^= 1u; }
       }
+      if (dbg && lane == 0) {
+        long long* d = p.dbg + 8 * gridDim.x + 16 * blockIdx.x;
+        d[0] = w_a1; d[1] = w_t1e; d[2] = w_a2; d[3] = w_te; d[4] = clock64() - t_begin;
+      }
     }
+  }
   } else if (warp >= G_WARP_PROD0 && warp < G_WARP_MID0) {
     // ===================== im2col producers: patch -> A1 (two sets alternate tiles) =====================
     const int pset = (warp - G_WARP_PROD0) >> 2;
@@ -228,20 +240,24 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       sh[c] = fp.normalise ? -fp.mean[c] * fp.rstd[c] : 0.f;
     }
     uint32_t uses = 0;
-    for (int i = pset; i < ntiles; i += G_PSETS) {
-      int h0, w0, n;
-      tile_coords(i, h0, w0, n);
+    const bool dbg = DBG && p.dbg != nullptr;
+    long long w_pf = 0, w_a1e = 0;
+    const long long t_begin = clock64();
+    TileCursor cur;
+    cur.init(p, pair0 + pset * npairs, G_PSETS * npairs, 2, rank);
+    for (int i = pset; i < ntiles; i += G_PSETS, cur.next()) {
+      const int h0 = cur.thi * T2_H, w0 = cur.twi * T2_W;
       const int ps = i & (G_PSTAGES - 1);
       const uint32_t pph = (uint32_t)(i / G_PSTAGES) & 1u;
       // taps outside the image must be 0 AFTER normalisation (models.py:131, then Conv2d padding = 1)
       const bool border = h0 - 2 < 0 || w0 - 2 < 0 || h0 + T2_H + 2 > p.H || w0 + T2_W + 2 > p.W;
-      mbar_wait(pfull(ps), pph);
+      mbar_wait_acc(pfull(ps), pph, dbg, w_pf);
       const float* pt = reinterpret_cast<const float*>(smem + G_OFF_PATCH + ps * G_PATCH_BYTES);
       uint32_t pk[2][16];
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         const int r = r0 + 128 * pass;
-        if (r < G_ROWS) {
+        if (r < G_ROWS && !(dflags & 64)) {
           const int rr = r / WA_W, cc = r % WA_W;
           float v[28];
 #pragma unroll
@@ -271,7 +287,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(pempty(ps));            // this warp has read its taps
-      mbar_wait(a1empty(pset), (uses & 1u) ^ 1u);
+      mbar_wait_acc(a1empty(pset), (uses & 1u) ^ 1u, dbg, w_a1e);
       ++uses;
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
@@ -289,9 +305,14 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a1full_l);
     }
+    if (dbg && r0 == 0 && pset == 0) {
+      long long* d = p.dbg + 8 * gridDim.x + 16 * blockIdx.x;
+      d[5] = w_pf; d[6] = w_a1e; d[7] = clock64() - t_begin;
+    }
     if (uses) mbar_wait(a1empty(pset), (uses - 1u) & 1u);      // the last multicast release has landed
   } else if (warp >= G_WARP_MID0 && warp < G_WARP_EPI0) {
     // ===================== mid warps: conv1_1 accumulators -> ReLU -> bf16 -> conv1_2's A slot =====================
+    if (V & 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     const int mw = warp - G_WARP_MID0;
     const int e = mw & 3, j = mw >> 2;                   // TMEM lane quarter (= warp % 4), 128-row block
     const int r = j * 128 + 32 * e + lane;               // row of the 18 x 10 region
@@ -300,51 +321,88 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
     const uint32_t t1empty_l = mapa_shared(t1empty(0), 0), a2full_l = mapa_shared(a2full(0), 0);
     int sa = 0;
     uint32_t pa = 0;
-    uint32_t used[G_NA2] = {0u, 0u, 0u};
-    for (int i = 0; i < ntiles; ++i) {
-      int h0, w0, n;
-      tile_coords(i, h0, w0, n);
+    const bool dbg = DBG && p.dbg != nullptr;
+    long long w_t1f = 0, w_a2e = 0;
+    const long long t_begin = clock64();
+    TileCursor cur;
+    cur.init(p, pair0, npairs, 2, rank);
+    for (int i = 0; i < ntiles; ++i, cur.next()) {
+      const int h0 = cur.thi * T2_H, w0 = cur.twi * T2_W, n = cur.n;
       const int s = i & 1;
       const uint32_t ph = (uint32_t)(i >> 1) & 1u;
       const int ih = h0 - 1 + rr, iw = w0 - 1 + cc;
       const bool inimg = valid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && n < p.N;
-      mbar_wait(t1full(s), ph);
+      mbar_wait_acc(t1full(s), ph, dbg, w_t1f);
       tc_fence_after();
       const uint32_t trow = tmem_t1 + ((uint32_t)(e * 32) << 16) + (uint32_t)(s * 128 + j * 64);
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(trow, v0);
-      tmem_ld_32x32(trow + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(t1empty_l + 8u * s);    // TMEM stage free for conv1_1 of tile i + 2
-      uint32_t pk[32];
+      const bool skip_mid = (dflags & 128) != 0;
+      const uint32_t row = a2_base + sa * AW_SLOT + (uint32_t)r * 128u;
+      const uint32_t sw = (uint32_t)(r & 7);
+      if constexpr (V & 2) {
+        // 32 columns at a time: fewer live registers (896 threads share the register file)
+        mbar_wait_acc(a2empty(sa), pa ^ 1u, dbg, w_a2e);   // three slots: free long before the accumulators are ready
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        pk[q] = inimg ? pack_bf16_relu(__uint_as_float(v0[2 * q]), __uint_as_float(v0[2 * q + 1])) : 0u;
-        pk[16 + q] = inimg ? pack_bf16_relu(__uint_as_float(v1[2 * q]), __uint_as_float(v1[2 * q + 1])) : 0u;
-      }
-      mbar_wait(a2empty(sa), pa ^ 1u);
-      ++used[sa];
-      if (valid) {
-        const uint32_t row = a2_base + sa * AW_SLOT + (uint32_t)r * 128u;
-        const uint32_t sw = (uint32_t)(r & 7);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32], pk[16];
+          if (!skip_mid) {
+            tmem_ld_32x32(trow + 32 * half, v);
+            tmem_ld_wait();
+          }
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          st_shared_v4(row + (((uint32_t)c ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          for (int q = 0; q < 16; ++q)
+            pk[q] = inimg ? pack_bf16_relu(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])) : 0u;
+          if (valid && !skip_mid) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              st_shared_v4(row + (((uint32_t)(4 * half + c) ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(t1empty_l + 8u * s);    // TMEM stage free for conv1_1 of tile i + 2
+      } else {
+        // all 64 columns at once, the TMEM stage handed back before the pack
+        uint32_t v0[32], v1[32];
+        if (!skip_mid) {
+          tmem_ld_32x32(trow, v0);
+          tmem_ld_32x32(trow + 32, v1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(t1empty_l + 8u * s);
+        uint32_t pk[32];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          pk[q] = inimg ? pack_bf16_relu(__uint_as_float(v0[2 * q]), __uint_as_float(v0[2 * q + 1])) : 0u;
+          pk[16 + q] = inimg ? pack_bf16_relu(__uint_as_float(v1[2 * q]), __uint_as_float(v1[2 * q + 1])) : 0u;
+        }
+        mbar_wait_acc(a2empty(sa), pa ^ 1u, dbg, w_a2e);
+        if (valid && !skip_mid) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            st_shared_v4(row + (((uint32_t)c ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a2full_l + 8u * sa);
       if (++sa == G_NA2) { sa = 0; pa ^= 1u; }
     }
+    if (dbg && mw == 0 && lane == 0) {
+      long long* d = p.dbg + 8 * gridDim.x + 16 * blockIdx.x;
+      d[8] = w_t1f; d[9] = w_a2e; d[10] = clock64() - t_begin;
+    }
     if (mw == 0) {
 #pragma unroll
-      for (int s = 0; s < G_NA2; ++s)
-        if (used[s]) mbar_wait(a2empty(s), (used[s] - 1u) & 1u);   // the last multicast releases have landed
+      for (int s = 0; s < G_NA2; ++s) {
+        const int used = (ntiles - s + G_NA2 - 1) / G_NA2;         // tiles s, s + 3, ... of this CTA went through slot s
+        if (ntiles > s) mbar_wait(a2empty(s), (uint32_t)(used - 1) & 1u);   // the last multicast releases have landed
+      }
     }
   } else if (warp >= G_WARP_EPI0) {
-    epilogue_loop<64, AST_EPI_POOL2, T2_W, G_EPI_NG, G_NACC, 1, true>(p, tmem_t2, warp - G_WARP_EPI0, lane, tfull(0),
+    if (V & 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    epilogue_loop<64, AST_EPI_POOL2, T2_W, G_EPI_NG, G_NACC, G_EPI_TG, true>(p, tmem_t2, warp - G_WARP_EPI0, lane, tfull(0),
                                                                       tempty(0), rank);
   }
 
@@ -382,6 +440,10 @@ int conv12_fused(const float* img, const float* w1, const float* b1, const float
   if (pairs_total >= 0x7fffffffLL) return AST_E_SHAPE;
   p.num_tiles = (int)pairs_total;
   p.bias = b2; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  // bottleneck elimination (tools/bench_conv12.py): 2 / 4 = epilogue without stores / TMEM loads (epilogue_loop),
+  // 64 = producers skip the im2col arithmetic, 128 = mid warps skip TMEM load + pack + A2 stores, 256 = no conv1_2 MMAs
+  static const int dbg_flags = getenv("AST_CONV_DBGFLAGS") ? atoi(getenv("AST_CONV_DBGFLAGS")) : 0;
+  p.dbg_flags = dbg_flags;
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return AST_E_NODRIVER;
   CUtensorMap tmImg, tmB2;
@@ -401,13 +463,15 @@ int conv12_fused(const float* img, const float* w1, const float* b1, const float
     r = encode_bf16_map(&tmB2, wpk2, 3, wdims, wstr, wbox);
     if (r) return r;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    AST_CUDA(cudaFuncSetAttribute(conv12_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
-    attr_done = true;
-  }
   const int max_pairs = sm_count / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+  static const bool dbg_on = getenv("AST_CONV_DEBUG") != nullptr;     // debug only: allocates and synchronises
+  long long* dbg = nullptr;
+  if (dbg_on) {
+    AST_CUDA(cudaMalloc(&dbg, sizeof(long long) * 24 * 2 * pairs));
+    AST_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 24 * 2 * pairs, s));
+    p.dbg = dbg;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs, 1, 1);
   cfg.blockDim = dim3(G_THREADS, 1, 1);
@@ -420,7 +484,36 @@ int conv12_fused(const float* img, const float* w1, const float* b1, const float
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AST_CUDA(cudaLaunchKernelEx(&cfg, conv12_fused_pair_kernel, tmImg, tmB2, fp, p));
+  static const int variant = getenv("AST_CONV12_V") ? atoi(getenv("AST_CONV12_V")) & 3 : 3;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const FirstParams, const ConvParams);
+  static const KernelFn kerns[5] = {conv12_fused_pair_kernel<0, false>, conv12_fused_pair_kernel<1, false>,
+                                    conv12_fused_pair_kernel<2, false>, conv12_fused_pair_kernel<3, false>,
+                                    conv12_fused_pair_kernel<3, true>};
+  const int ki = (dbg_on || dbg_flags) ? 4 : variant;
+  static bool attr_done[5] = {false, false, false, false, false};
+  if (!attr_done[ki]) {
+    AST_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
+    attr_done[ki] = true;
+  }
+  AST_CUDA(cudaLaunchKernelEx(&cfg, kerns[ki], tmImg, tmB2, fp, p));
   AST_CHECK_LAUNCH();
+  if (dbg) {
+    cudaStreamSynchronize(s);
+    const int g = 2 * pairs;
+    long long* h = new long long[24 * g];
+    cudaMemcpy(h, dbg, sizeof(long long) * 24 * g, cudaMemcpyDeviceToHost);
+    double a[16] = {0}, e[2] = {0};
+    for (int b = 0; b < g; ++b) {
+      for (int j = 0; j < 16; ++j) a[j] += (double)h[8 * g + 16 * b + j] / ((j < 5) ? pairs : g);
+      e[0] += (double)h[8 * b + 4] / g; e[1] += (double)h[8 * b + 5] / g;
+    }
+    const double tiles = (double)p.num_tiles / pairs;
+    fprintf(stderr, "[conv12 dbg] tiles/CTA=%.1f | per tile cycles: mma loop=%.0f wait a1full=%.0f t1empty=%.0f a2full=%.0f tempty=%.0f | "
+            "producer set 0 (per its tile) loop=%.0f wait patch=%.0f a1empty=%.0f | mid loop=%.0f wait t1full=%.0f a2empty=%.0f | "
+            "epilogue loop=%.0f wait tfull=%.0f\n", tiles, a[4] / tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles,
+            a[7] / tiles * 2, a[5] / tiles * 2, a[6] / tiles * 2, a[10] / tiles, a[8] / tiles, a[9] / tiles, e[1] / tiles, e[0] / tiles);
+    delete[] h;
+    cudaFree(dbg);
+  }
   return 0;
 }
