@@ -80,3 +80,12 @@ def test_sass_is_blackwell_native(lib_path):
     # round 2: CTA-pair MMAs with multicast commits, TMA loads signalling the leader's barrier, and a TMA store
     assert "UTCHMMA.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass and ".2CTA" in sass and "UTMASTG" in sass
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", lib_path], capture_output=True, text=True).stdout
+    # the fused conv1_1 + conv1_2 kernel: ptxas 12.9 once dropped the high word of its A-operand descriptor (stride,
+    # version, 128-byte-swizzle layout type = 0x40004050) when it was built as one 64-bit sum; every instantiation
+    # must carry the constant (csrc/conv12_fused.cuh)
+    parts = sass.split("Function : ")
+    fused = [p for p in parts if p.startswith("_ZN3ast2tc24conv12_fused_pair_kernel")]
+    assert len(fused) >= 2
+    for body in fused:
+        assert "0x40004050" in body and "UTCHMMA.2CTA" in body
+    assert any("USETMAXREG" in body for body in fused)        # the default variant rebalances registers per role

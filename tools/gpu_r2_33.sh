@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+  --log-file gpurun_out/train_launches.csv python tools/prof_train.py --profile > gpurun_out/train_ncu.log 2>&1
+echo "ncu exit=$?"; tail -2 gpurun_out/train_ncu.log
+python tools/launch_summary.py gpurun_out/train_launches.csv | head -45 | tee gpurun_out/train_step_kernel_totals.txt
