@@ -17,6 +17,7 @@
 // run.  (Round 1 launched one CTA per tile: TMEM allocation, barrier set-up, the first TMA round trip and the
 // epilogue's latency chain were serial inside every CTA and only 2-3 CTAs fitted an SM: 19-25 % of the DRAM
 // bandwidth, profiles/r1_ncu_pointwise_summary.csv.)
+#include <cstdlib>
 #include "tc.cuh"
 
 namespace ast {
@@ -28,14 +29,23 @@ constexpr int PW_A_BYTES = 128 * 64 * 2;   // 16 KB
 constexpr int PW_MAX_STAGES = 8;
 __host__ __device__ constexpr int pw_stage_bytes(int BN) { return PW_A_BYTES + ((BN * 128 + 1023) / 1024) * 1024; }
 constexpr int PW_STG_BYTES = 128 * 128;   // one staged output block: 128 pixel rows x 64 channels, 128-byte swizzle
-__host__ __device__ constexpr int pw_smem_bytes(int BN, int stages, int staging = 0) {
-  return stages * pw_stage_bytes(BN) + staging + (2 * PW_MAX_STAGES + 4) * 8 + 16 + 1024;
+__host__ __device__ constexpr int pw_b_slot_bytes(int BN) { return ((BN * 128 + 1023) / 1024) * 1024; }
+// resident > 0: the whole weight matrix (resident = K steps of one slot each) sits behind an A-only ring
+__host__ __device__ constexpr int pw_smem_bytes(int BN, int stages, int staging = 0, int resident = 0) {
+  return stages * (resident ? PW_A_BYTES : pw_stage_bytes(BN)) + resident * pw_b_slot_bytes(BN) + staging +
+         (2 * PW_MAX_STAGES + 5) * 8 + 16 + 1024;
 }
 
 struct PwParams {
   int N, Cin, Cout, BN, n_blocks, tiles_per_img, per_sample_w, act;
   int stages, total_tiles;         // operand ring depth; N * tiles_per_img * n_blocks
   int staging;                     // bytes of TMA-store staging after the ring: 2 buffers (x 2 with out_act)
+  int resident;                    // > 0: weights loaded ONCE per CTA into `resident` (= K steps) slots; else streamed
+                                   // with every A stage.  (Measured: the TMA unit handles one box ROW per ~18 cycles;
+                                   // re-streaming BN weight rows per 128 pixel rows made the expand layers
+                                   // TMA-row-bound: 368 rows per tile for 40 -> 240.)
+  int dbg_flags;                   // AST_PW_DBGFLAGS (bottleneck elimination, results are WRONG): 1 = no TMA stores,
+                                   // 2 = no staging writes, 4 = no TMEM loads
   int64_t HW;
   int ld_out, ld_res;              // row strides (elements) of out / residual
   const float* bias;               // [Cout] or null
@@ -62,17 +72,20 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int STAGE = pw_stage_bytes(p.BN);
+  const int STAGE = p.resident ? PW_A_BYTES : pw_stage_bytes(p.BN);
   const int NS = p.stages;
-  const uint32_t stg_base = base + NS * STAGE;     // 1024-byte aligned: stage sizes are multiples of 1024
+  const int B_SLOT = pw_b_slot_bytes(p.BN);
+  const uint32_t bres_base = base + NS * STAGE;    // resident weights (p.resident slots); 1024-byte aligned
+  const uint32_t stg_base = bres_base + p.resident * B_SLOT;
   const uint32_t bars = stg_base + p.staging;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (PW_MAX_STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * PW_MAX_STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * PW_MAX_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bars + 8u * (2 * PW_MAX_STAGES + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + NS * STAGE + p.staging + 8 * (2 * PW_MAX_STAGES + 4));
+  const uint32_t bres_bar = bars + 8u * (2 * PW_MAX_STAGES + 4);
+  const uint32_t tmem_slot = bars + 8u * (2 * PW_MAX_STAGES + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem + NS * STAGE + p.resident * B_SLOT + p.staging + 8 * (2 * PW_MAX_STAGES + 5));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   constexpr uint32_t ACC_COLS = TMEM_COLS / 2;     // two accumulators
@@ -95,6 +108,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), PW_EPI_WARPS); }
+      mbar_init(bres_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -109,15 +123,20 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.resident) {      // one n-block, shared weights: the whole matrix, once
+        mbar_expect_tx(bres_bar, (uint32_t)ksteps * b_bytes);
+        for (int ks = 0; ks < ksteps; ++ks) tma_load_3d(bres_base + ks * B_SLOT, &tmB, bres_bar, ks * 64, 0, 0);
+      }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int nb, ti, n;
         decode(t, nb, ti, n);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), PW_A_BYTES + b_bytes);
+          mbar_expect_tx(full_bar(stage), PW_A_BYTES + (p.resident ? 0u : b_bytes));
           const uint32_t a_dst = base + stage * STAGE;
           tma_load_3d(a_dst, &tmA, full_bar(stage), ks * 64, ti * 128, n);
-          tma_load_3d(a_dst + PW_A_BYTES, &tmB, full_bar(stage), ks * 64, nb * p.BN, p.per_sample_w ? n : 0);
+          if (!p.resident)
+            tma_load_3d(a_dst + PW_A_BYTES, &tmB, full_bar(stage), ks * 64, nb * p.BN, p.per_sample_w ? n : 0);
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
       }
@@ -126,6 +145,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t idesc = F16 ? make_idesc_f16(128, p.BN) : make_idesc_bf16(128, p.BN);
     int stage = 0, acc = 0;
     uint32_t phase = 0, aphase = 0;
+    if (p.resident && (int)blockIdx.x < p.total_tiles) mbar_wait(bres_bar, 0u);
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       mbar_wait(tempty_bar(acc), aphase ^ 1u);       // the epilogue has drained this accumulator (two tiles ago)
       tc_fence_after();
@@ -135,7 +155,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint64_t ad = make_sdesc_k128(base + stage * STAGE);
-        const uint64_t bd = make_sdesc_k128(base + stage * STAGE + PW_A_BYTES);
+        const uint64_t bd = make_sdesc_k128(p.resident ? bres_base + ks * B_SLOT : base + stage * STAGE + PW_A_BYTES);
         if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -192,8 +212,10 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int c0 = b0 + sub * 16;
         if (c0 < p.BN) {
           uint32_t v[16];
-          tmem_ld_32x16(acc_tmem + (uint32_t)c0, v);
-          tmem_ld_wait();
+          if (!(p.dbg_flags & 4)) {
+            tmem_ld_32x16(acc_tmem + (uint32_t)c0, v);
+            tmem_ld_wait();
+          }
           const int co0 = nb * p.BN + c0;
           const int valid = ok ? p.Cout - co0 : 0;     // < 16: channel tail (multiple of 8); <= 0: TMA clips the row / chunk
           float f[16];
@@ -239,16 +261,18 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           const uint32_t c16 = (uint32_t)(sub * 2);
+          if (!(p.dbg_flags & 2)) {
           st_shared_v4(srow + ((c16 ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
           st_shared_v4(srow + (((c16 + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
           if (p.out_act) {
             st_shared_v4(srow + act_off + ((c16 ^ sw) << 4), pa[0], pa[1], pa[2], pa[3]);
             st_shared_v4(srow + act_off + (((c16 + 1) ^ sw) << 4), pa[4], pa[5], pa[6], pa[7]);
           }
+          }
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 32 * PW_EPI_WARPS);
-        if (ew == 0 && lane == 0) {
+        if (ew == 0 && lane == 0 && !(p.dbg_flags & 1)) {
           const uint32_t src = stg_base + (uint32_t)buf * PW_STG_BYTES;
           tma_store_3d(&tmOut, src, nb * p.BN + b0, ti * 128, n);
           if (p.out_act) tma_store_3d(&tmAct, src + act_off, nb * p.BN + b0, ti * 128, n);
@@ -337,10 +361,18 @@ extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_samp
   }
   // two CTAs per SM while two accumulators of BN columns each fit twice into the 512 TMEM columns (BN <= 128),
   // else one; the operand ring takes what is left of the shared memory (2 .. 8 stages)
-  const int per_sm = BN <= 128 ? 2 : 1;
-  const int budget = (per_sm == 2 ? 110 : 220) * 1024;
   p.staging = (out_act ? 4 : 2) * PW_STG_BYTES;
-  int stages = (budget - pw_smem_bytes(BN, 0, p.staging)) / pw_stage_bytes(BN);
+  static const int dbg_flags = getenv("AST_PW_DBGFLAGS") ? atoi(getenv("AST_PW_DBGFLAGS")) : 0;
+  p.dbg_flags = dbg_flags;
+  // weights resident when they are shared by all images, one n-block covers Cout and they take <= 96 KB
+  const int ksteps = (Cin + 63) / 64;
+  static const int res_env = getenv("AST_PW_RESIDENT") ? atoi(getenv("AST_PW_RESIDENT")) : 1;
+  p.resident = (res_env && !per_sample_w && n_blocks == 1 && ksteps * pw_b_slot_bytes(BN) <= 96 * 1024) ? ksteps : 0;
+  const int stage_b = p.resident ? PW_A_BYTES : pw_stage_bytes(BN);
+  int per_sm = BN <= 128 ? 2 : 1;
+  int stages = (110 * 1024 - pw_smem_bytes(BN, 0, p.staging, p.resident)) / stage_b;
+  if (per_sm == 2 && stages < 2) per_sm = 1;       // staging + a two-stage ring do not fit twice: one CTA per SM
+  if (per_sm == 1) stages = (220 * 1024 - pw_smem_bytes(BN, 0, p.staging, p.resident)) / stage_b;
   stages = stages < 2 ? 2 : (stages > PW_MAX_STAGES ? PW_MAX_STAGES : stages);
   p.stages = stages;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const PwParams);
@@ -358,7 +390,7 @@ extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_samp
   }
   const int64_t max_ctas = (int64_t)sm_count * per_sm;
   const unsigned grid = (unsigned)(total < max_ctas ? total : max_ctas);
-  const int smem = pw_smem_bytes(BN, stages, p.staging);
+  const int smem = pw_smem_bytes(BN, stages, p.staging, p.resident);
   CUtensorMap tmOut, tmAct;
   {
     const uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)HW, (uint64_t)N};

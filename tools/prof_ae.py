@@ -12,6 +12,7 @@ ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--profile-eval", action="store_true", help="one eval-mode forward inside the profiler range")
 args = ap.parse_args()
 dev = torch.device("cuda")
 x = torch.rand(args.batch, 3, args.size, args.size, generator=torch.Generator().manual_seed(301)).to(dev)
@@ -58,6 +59,20 @@ def timeit(fn, steps):
     torch.cuda.synchronize()
     return a.elapsed_time(b) / steps, out
 
+
+if args.profile_eval:
+    step, ae = build()
+    ae.eval()
+    with torch.no_grad():
+        for _ in range(2):
+            ae(x)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        ae(x)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    print("ok")
+    sys.exit(0)
 
 if args.profile:
     step, ae = build()
