@@ -51,10 +51,14 @@ def _digest(path: str, extra: str) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ and link libast_b200.so.  Returns the library path."""
+    """Compile every .cu under csrc/ and link libast_b200.so.  Returns the library path.
+    AST_KERNEL_DEBUG=1 in the environment compiles the kernels' wait counters and bottleneck-elimination flags in
+    (AST_CONV_DEBUG / AST_CONV_DBGFLAGS / AST_PW_DBGFLAGS then work; the kernels are 15-40 % slower)."""
     nvcc = _nvcc()
     os.makedirs(BUILD_DIR, exist_ok=True)
     flags = list(NVCC_FLAGS)
+    if os.environ.get("AST_KERNEL_DEBUG", "0") not in ("", "0"):
+        flags += ["-DAST_KERNEL_DEBUG=1"]
     if verbose:
         flags += ["-Xptxas", "-v"]
     objs, jobs = [], []

@@ -11,7 +11,8 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libast_b200.so")
+# AST_B200_LIB: developer override for A/B runs against another build of the same ABI (tools/); never a fallback
+LIB_PATH = os.environ.get("AST_B200_LIB") or os.path.join(HERE, "libast_b200.so")
 
 # mirrors of the header constants
 ABI_VERSION = 2

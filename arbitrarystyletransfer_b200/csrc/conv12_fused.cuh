@@ -125,7 +125,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
 
   // Register budget per warpgroup (896 threads x 72 at launch): the control warps and the mid warps hand registers to the
   // epilogue warps, whose spills would otherwise share the shared-memory / L1 port with the MMA's operand reads
-  const int dflags = DBG ? p.dbg_flags : 0;
+  const int dflags = DBG ? kdbg_flags(p) : 0;
   if (warp < G_WARP_PROD0) {
     if (V & 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
@@ -166,7 +166,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       const uint64_t b2_desc0 = make_sdesc_k128(b2_base);
       constexpr uint32_t A2_SLOT16 = AW_SLOT >> 4, KH16 = (WA_W * KBLK * 2) >> 4;
       constexpr uint64_t B2_SLOT16 = G_B2_TILE >> 4;
-      const bool dbg = DBG && p.dbg != nullptr;
+      const bool dbg = DBG && kdbg_buf(p) != nullptr;
       long long w_a1 = 0, w_t1e = 0, w_a2 = 0, w_te = 0;
       auto issue_conv11 = [&](int i) {       // tile i of this pair: A1 stage / TMEM stage s = i & 1
         const int s = i & 1;
@@ -223,7 +223,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
         if (++as == G_NACC) { as = 0; aphase ^= 1u; }
       }
       if (dbg && lane == 0) {
-        long long* d = p.dbg + 8 * gridDim.x + 16 * blockIdx.x;
+        long long* d = kdbg_buf(p) + 8 * gridDim.x + 16 * blockIdx.x;
         d[0] = w_a1; d[1] = w_t1e; d[2] = w_a2; d[3] = w_te; d[4] = clock64() - t_begin;
       }
     }
@@ -240,7 +240,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       sh[c] = fp.normalise ? -fp.mean[c] * fp.rstd[c] : 0.f;
     }
     uint32_t uses = 0;
-    const bool dbg = DBG && p.dbg != nullptr;
+    const bool dbg = DBG && kdbg_buf(p) != nullptr;
     long long w_pf = 0, w_a1e = 0;
     const long long t_begin = clock64();
     TileCursor cur;
@@ -306,7 +306,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       if (lane == 0) mbar_arrive_cluster(a1full_l);
     }
     if (dbg && r0 == 0 && pset == 0) {
-      long long* d = p.dbg + 8 * gridDim.x + 16 * blockIdx.x;
+      long long* d = kdbg_buf(p) + 8 * gridDim.x + 16 * blockIdx.x;
       d[5] = w_pf; d[6] = w_a1e; d[7] = clock64() - t_begin;
     }
     if (uses) mbar_wait(a1empty(pset), (uses - 1u) & 1u);      // the last multicast release has landed
@@ -321,7 +321,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
     const uint32_t t1empty_l = mapa_shared(t1empty(0), 0), a2full_l = mapa_shared(a2full(0), 0);
     int sa = 0;
     uint32_t pa = 0;
-    const bool dbg = DBG && p.dbg != nullptr;
+    const bool dbg = DBG && kdbg_buf(p) != nullptr;
     long long w_t1f = 0, w_a2e = 0;
     const long long t_begin = clock64();
     TileCursor cur;
@@ -390,7 +390,7 @@ conv12_fused_pair_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid
       if (++sa == G_NA2) { sa = 0; pa ^= 1u; }
     }
     if (dbg && mw == 0 && lane == 0) {
-      long long* d = p.dbg + 8 * gridDim.x + 16 * blockIdx.x;
+      long long* d = kdbg_buf(p) + 8 * gridDim.x + 16 * blockIdx.x;
       d[8] = w_t1f; d[9] = w_a2e; d[10] = clock64() - t_begin;
     }
     if (mw == 0) {
@@ -488,8 +488,8 @@ int conv12_fused(const float* img, const float* w1, const float* b1, const float
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const FirstParams, const ConvParams);
   static const KernelFn kerns[5] = {conv12_fused_pair_kernel<0, false>, conv12_fused_pair_kernel<1, false>,
                                     conv12_fused_pair_kernel<2, false>, conv12_fused_pair_kernel<3, false>,
-                                    conv12_fused_pair_kernel<3, true>};
-  const int ki = (dbg_on || dbg_flags) ? 4 : variant;
+                                    conv12_fused_pair_kernel<3, AST_KERNEL_DEBUG != 0>};
+  const int ki = (AST_KERNEL_DEBUG && (dbg_on || dbg_flags)) ? 4 : variant;
   static bool attr_done[5] = {false, false, false, false, false};
   if (!attr_done[ki]) {
     AST_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));

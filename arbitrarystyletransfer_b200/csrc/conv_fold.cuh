@@ -113,7 +113,7 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
           const uint32_t c16 = (uint32_t)(cc * (CH / 8) + q) ^ (uint32_t)(lane & 7);
           st_shared_v4(wbuf + (uint32_t)lane * 128u + c16 * 16u, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
-        if (!(p.dbg_flags & 2)) {
+        if (!(kdbg_flags(p) & 2)) {
           for (int ri = 0; ri < nr; ++ri)
             for (int ci = 0; ci < nc; ++ci) {
               if (ri == 0 && ci == 0) continue;        // the pixel itself goes out with the TMA store
@@ -133,7 +133,7 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && !(p.dbg_flags & 2)) {
+      if (lane == 0 && !(kdbg_flags(p) & 2)) {
         tma_store_4d(&om->m[py * 2 + px], wbuf, cob * BN + choff, cur.twi * T2_W, cur.thi * T2_H + 4 * e, n);
         bulk_commit_group();
       }
@@ -141,7 +141,7 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
       continue;
     }
     uint32_t vnext[CH];
-    const bool skip_ld = (p.dbg_flags & 4) != 0;
+    const bool skip_ld = (kdbg_flags(p) & 4) != 0;
     if (g < NCH && !skip_ld) tmem_ld_cols(trow + g * CH, vnext);
 #pragma unroll 1
     for (int chunk = g; chunk < NCH && !skip_ld; chunk += NG) {
@@ -170,7 +170,7 @@ __device__ __forceinline__ void epilogue_fold(const ConvParams& p, uint32_t tmem
 #pragma unroll
         for (int i = 0; i < CH / 2; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
       }
-      if (in_img && !(p.dbg_flags & 2)) {
+      if (in_img && !(kdbg_flags(p) & 2)) {
         int rows[4], cols[4];
         const int nr = out_targets<AST_EPI_PLAIN>(2 * h + py, p.Ho, p.halo, rows);
         const int nc = out_targets<AST_EPI_PLAIN>(2 * w + px, p.Wo, p.halo, cols);
@@ -269,7 +269,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = px0; kw <= px0 + npx; ++kw) {
             if (p.prod_sleep_ns) mbar_wait_sleep(aempty(sa), pa ^ 1u, p.prod_sleep_ns); else mbar_wait(aempty(sa), pa ^ 1u);
-            if ((p.dbg_flags & 1) && a_filled) {
+            if ((kdbg_flags(p) & 1) && a_filled) {
               mbar_arrive(afull(sa));
             } else {
               mbar_expect_tx(afull(sa), A2_BYTES);
@@ -284,7 +284,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int px = px0; px < px0 + npx; ++px)
                   if (kw - px >= 0 && kw - px <= 1) cnt += 2;
               if (p.prod_sleep_ns) mbar_wait_sleep(bempty(sb), pb ^ 1u, p.prod_sleep_ns); else mbar_wait(bempty(sb), pb ^ 1u);
-              if ((p.dbg_flags & 1) && b_filled) {
+              if ((kdbg_flags(p) & 1) && b_filled) {
                 mbar_arrive(bfull(sb));
               } else {
                 mbar_expect_tx(bfull(sb), cnt * C::B_BYTES);

@@ -161,13 +161,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = 0; kw < 3; ++kw) {
             if (!wide || kw == 0) {
-              mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa, p.prod_sleep_ns);
+              mbar_wait_acc(aempty(sa), pa ^ 1u, kdbg_buf(p) != nullptr, dbg_pa, p.prod_sleep_ns);
               if (rank == 0) mbar_expect_tx(afull(sa), 2 * a_tx_bytes);
               tma_load_4d_2sm(a_base + sa * a_slot_bytes, &tmA, afull_l + 8u * sa, cb * KBLK, w0 + kw, h0, n);
               if (++sa == NA) { sa = 0; pa ^= 1u; }
             }
             if (!resident) {
-              mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb, p.prod_sleep_ns);
+              mbar_wait_acc(bempty(sb), pb ^ 1u, kdbg_buf(p) != nullptr, dbg_pb, p.prod_sleep_ns);
               if (rank == 0) mbar_expect_tx(bfull(sb), 2 * 3 * C::B_BYTES);
               for (int kh = 0; kh < 3; ++kh)
                 tma_load_3d_2sm(b_base + (sb * 3 + kh) * C::B_BYTES, &tmB, bfull_l + 8u * sb, cb * KBLK,
@@ -177,7 +177,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_pa; p.dbg[blockIdx.x * 8 + 1] = dbg_pb; }
+      if (kdbg_buf(p)) { kdbg_buf(p)[blockIdx.x * 8 + 0] = dbg_pa; kdbg_buf(p)[blockIdx.x * 8 + 1] = dbg_pb; }
       // drain: every multicast release aimed at this CTA has landed before it may exit
       for (int i = 0; i < NA; ++i) {
         mbar_wait(aempty(sa), pa ^ 1u);
@@ -206,7 +206,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       bool b_resident_ready = false;
       long long dbg_mt = 0, dbg_ma = 0, dbg_mb = 0;
       const long long dbg_m0 = clock64();
-      const bool dbg = p.dbg != nullptr;
+      const bool dbg = kdbg_buf(p) != nullptr;
       for (int q = pair0; q < p.num_tiles; q += npairs) {
         mbar_wait_acc(tempty(as), aphase ^ 1u, dbg, dbg_mt);
         tc_fence_after();
@@ -253,10 +253,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (++as == C::NACC) { as = 0; aphase ^= 1u; }
       }
-      if (p.dbg && lane == 0) {
-        p.dbg[blockIdx.x * 8 + 2] = dbg_ma + dbg_mb;
-        p.dbg[blockIdx.x * 8 + 3] = dbg_mt;
-        p.dbg[blockIdx.x * 8 + 6] = clock64() - dbg_m0;
+      if (kdbg_buf(p) && lane == 0) {
+        kdbg_buf(p)[blockIdx.x * 8 + 2] = dbg_ma + dbg_mb;
+        kdbg_buf(p)[blockIdx.x * 8 + 3] = dbg_mt;
+        kdbg_buf(p)[blockIdx.x * 8 + 6] = clock64() - dbg_m0;
       }
     }
   } else if (warp >= 4) {

@@ -89,6 +89,16 @@ struct ConvParams {
                      // slot, never refreshed; 2 = epilogue without global stores; 4 = epilogue without TMEM loads
 };
 
+// Debug instrumentation (wait counters, bottleneck-elimination flags) is compiled in only with -DAST_KERNEL_DEBUG=1
+// (AST_KERNEL_DEBUG=1 python -m arbitrarystyletransfer_b200._build): tested at run time, the flags cost the pointwise
+// kernel 40 % and the fused conv1_1 + conv1_2 kernel 15 % (register pressure, lost unrolling, maybe-uninitialised
+// values), so product builds fold them to constants.
+#ifndef AST_KERNEL_DEBUG
+#define AST_KERNEL_DEBUG 0
+#endif
+template <typename P> __device__ __forceinline__ int kdbg_flags(const P& p) { return AST_KERNEL_DEBUG ? p.dbg_flags : 0; }
+template <typename P> __device__ __forceinline__ long long* kdbg_buf(const P& p) { return AST_KERNEL_DEBUG ? p.dbg : nullptr; }
+
 constexpr int EPI_NCHW32 = 3;  // internal: last decoder layer, fp32 NCHW image out
 
 // wait + optional accounting of the cycles spent waiting (debug instrumentation)
@@ -222,7 +232,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
       nc = out_targets<EPI>(w, p.Wo, halo, cols);
     }
 
-    mbar_wait_acc(tfull_bar0 + 8u * as, aphase, p.dbg != nullptr, dbg_wait, p.epi_sleep_ns);
+    mbar_wait_acc(tfull_bar0 + 8u * as, aphase, kdbg_buf(p) != nullptr, dbg_wait, p.epi_sleep_ns);
     tc_fence_after();
     if (TS) {   // two staging buffers alternate: the stores issued two tiles ago have finished reading this one
       if (ew == 0 && lane == 0) bulk_wait_group_read1();
@@ -231,7 +241,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
     const uint32_t stg = TS ? staging + (ts_buf ? (uint32_t)(BN / 64) * (TILE_M * 128) : 0u) : 0u;
     const uint32_t trow = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
     uint32_t vnext[CH];
-    const bool skip_ld = (p.dbg_flags & 4) != 0;
+    const bool skip_ld = (kdbg_flags(p) & 4) != 0;
     if (g < NCH && !skip_ld) tmem_ld_cols(trow + g * CH, vnext);
 #pragma unroll 1
     for (int chunk = g; chunk < NCH && !skip_ld; chunk += NG) {
@@ -307,7 +317,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
             st_shared_v4(rowa + c16 * 16u, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
-        if (p.out && !(p.dbg_flags & 2)) {
+        if (p.out && !(kdbg_flags(p) & 2)) {
           for (int ri = 0; ri < nr; ++ri) {
             for (int ci = 0; ci < nc; ++ci) {
               if (TS && ri == 0 && ci == 0) continue;      // the pixel itself goes out with the TMA store
@@ -336,7 +346,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
     if (TS) {
       fence_proxy_async_smem();
       named_bar_sync(1, 128 * NG);
-      if (ew == 0 && lane == 0 && !(p.dbg_flags & 2)) {
+      if (ew == 0 && lane == 0 && !(kdbg_flags(p) & 2)) {
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b)
           tma_store_4d(tmOut, stg + (uint32_t)b * (TILE_M * 128), nb * BN + b * 64, twi * TW, thi * TH, n);
@@ -348,9 +358,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, uint32_t tmem
     if (as >= NACC) { as -= NACC; aphase ^= 1u; }
   }
   if (TS && ew == 0 && lane == 0) bulk_wait_group0();
-  if (p.dbg && ew == 0 && lane == 0) {
-    p.dbg[blockIdx.x * 8 + 4] = dbg_wait;               // epilogue warp 0: waiting for an accumulator
-    p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;     // epilogue warp 0: total loop time
+  if (kdbg_buf(p) && ew == 0 && lane == 0) {
+    kdbg_buf(p)[blockIdx.x * 8 + 4] = dbg_wait;               // epilogue warp 0: waiting for an accumulator
+    kdbg_buf(p)[blockIdx.x * 8 + 5] = clock64() - dbg_t0;     // epilogue warp 0: total loop time
   }
 }
 
@@ -573,8 +583,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int h0 = thi * T2_H, w0 = twi * T2_W;
         for (int cb = 0; cb < cblocks; ++cb) {
           for (int kw = 0; kw < 3; ++kw) {
-            mbar_wait_acc(aempty(sa), pa ^ 1u, p.dbg != nullptr, dbg_pa, p.prod_sleep_ns);
-            if ((p.dbg_flags & 1) && a_filled) {
+            mbar_wait_acc(aempty(sa), pa ^ 1u, kdbg_buf(p) != nullptr, dbg_pa, p.prod_sleep_ns);
+            if ((kdbg_flags(p) & 1) && a_filled) {
               mbar_arrive(afull(sa));
             } else {
               mbar_expect_tx(afull(sa), A2_BYTES);
@@ -584,8 +594,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (++sa == C::NA) { sa = 0; pa ^= 1u; }
             if (!resident) {
               if constexpr (C::GROUPED) {
-                mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb, p.prod_sleep_ns);
-                if ((p.dbg_flags & 1) && b_filled) {
+                mbar_wait_acc(bempty(sb), pb ^ 1u, kdbg_buf(p) != nullptr, dbg_pb, p.prod_sleep_ns);
+                if ((kdbg_flags(p) & 1) && b_filled) {
                   mbar_arrive(bfull(sb));
                 } else {
                   mbar_expect_tx(bfull(sb), 3 * C::B_BYTES);
@@ -597,7 +607,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (++sb == 3) { sb = 0; pb ^= 1u; }
               } else {
                 for (int kh = 0; kh < 3; ++kh) {
-                  mbar_wait_acc(bempty(sb), pb ^ 1u, p.dbg != nullptr, dbg_pb);
+                  mbar_wait_acc(bempty(sb), pb ^ 1u, kdbg_buf(p) != nullptr, dbg_pb);
                   mbar_expect_tx(bfull(sb), C::B_BYTES);
                   tma_load_3d(b_base + sb * C::B_BYTES, &tmB, bfull(sb), cb * KBLK, nb * BN, kh * 3 + kw);
                   if (++sb == C::NB) { sb = 0; pb ^= 1u; }
@@ -607,7 +617,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_pa; p.dbg[blockIdx.x * 8 + 1] = dbg_pb; }
+      if (kdbg_buf(p)) { kdbg_buf(p)[blockIdx.x * 8 + 0] = dbg_pa; kdbg_buf(p)[blockIdx.x * 8 + 1] = dbg_pb; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -628,7 +638,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       bool b_resident_ready = false;
       long long dbg_mt = 0, dbg_ma = 0, dbg_mb = 0;
       const long long dbg_m0 = clock64();
-      const bool dbg = p.dbg != nullptr;
+      const bool dbg = kdbg_buf(p) != nullptr;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait_acc(tempty(as), aphase ^ 1u, dbg, dbg_mt);
         tc_fence_after();
@@ -695,10 +705,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         __syncwarp();
         if (++as == C::NACC) { as = 0; aphase ^= 1u; }
       }
-      if (p.dbg && lane == 0) {
-        p.dbg[blockIdx.x * 8 + 2] = dbg_ma + dbg_mb;        // MMA warp: waiting for operands
-        p.dbg[blockIdx.x * 8 + 3] = dbg_mt;                 // MMA warp: waiting for a free accumulator
-        p.dbg[blockIdx.x * 8 + 6] = clock64() - dbg_m0;     // MMA warp: total loop time
+      if (kdbg_buf(p) && lane == 0) {
+        kdbg_buf(p)[blockIdx.x * 8 + 2] = dbg_ma + dbg_mb;        // MMA warp: waiting for operands
+        kdbg_buf(p)[blockIdx.x * 8 + 3] = dbg_mt;                 // MMA warp: waiting for a free accumulator
+        kdbg_buf(p)[blockIdx.x * 8 + 6] = clock64() - dbg_m0;     // MMA warp: total loop time
       }
     }
   } else if (warp >= 4) {
@@ -1168,7 +1178,7 @@ __device__ __forceinline__ void epilogue_first_store(const ConvParams& p, const 
   const long long dbg_t0 = clock64();
   for (int tile = blockIdx.x + tg * gridDim.x; tile < p.num_tiles; tile += F2_NG * gridDim.x, cur.next()) {
     const int twi = cur.twi, thi = cur.thi, n = cur.n;
-    mbar_wait_acc(tfull_bar0 + 8u * tg, aphase, p.dbg != nullptr, dbg_wait, p.epi_sleep_ns);
+    mbar_wait_acc(tfull_bar0 + 8u * tg, aphase, kdbg_buf(p) != nullptr, dbg_wait, p.epi_sleep_ns);
     tc_fence_after();
     // the previous store of this tile set has finished reading the staging buffer
     if (issuer && lane == 0) bulk_wait_group_read0();
@@ -1210,9 +1220,9 @@ __device__ __forceinline__ void epilogue_first_store(const ConvParams& p, const 
     aphase ^= 1u;
   }
   if (issuer && lane == 0) bulk_wait_group0();
-  if (p.dbg && ew == 0 && lane == 0) {
-    p.dbg[blockIdx.x * 8 + 4] = dbg_wait;
-    p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_t0;
+  if (kdbg_buf(p) && ew == 0 && lane == 0) {
+    kdbg_buf(p)[blockIdx.x * 8 + 4] = dbg_wait;
+    kdbg_buf(p)[blockIdx.x * 8 + 5] = clock64() - dbg_t0;
   }
 }
 

@@ -19,6 +19,9 @@
 // bandwidth, profiles/r1_ncu_pointwise_summary.csv.)
 #include <cstdlib>
 #include "tc.cuh"
+#ifndef AST_KERNEL_DEBUG
+#define AST_KERNEL_DEBUG 0
+#endif
 
 namespace ast {
 namespace tc {
@@ -64,7 +67,7 @@ __device__ __forceinline__ float hardswish(float x) {
 
 // F16: every 16-bit tensor of the call is fp16 (forward activations / weights), else bf16 (gradients, attention rows);
 // compile-time, so the epilogue's conversions carry no selects
-template <int TMEM_COLS, bool F16>
+template <int TMEM_COLS, bool F16, bool DBG>
 __global__ void __launch_bounds__(PW_THREADS)
 pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAct, const PwParams p) {
@@ -72,6 +75,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
+  const int dflags = DBG ? p.dbg_flags : 0;      // elimination flags live in a separate instantiation
   const int STAGE = p.resident ? PW_A_BYTES : pw_stage_bytes(p.BN);
   const int NS = p.stages;
   const int B_SLOT = pw_b_slot_bytes(p.BN);
@@ -212,7 +216,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int c0 = b0 + sub * 16;
         if (c0 < p.BN) {
           uint32_t v[16];
-          if (!(p.dbg_flags & 4)) {
+          if (!(dflags & 4)) {
             tmem_ld_32x16(acc_tmem + (uint32_t)c0, v);
             tmem_ld_wait();
           }
@@ -261,7 +265,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           const uint32_t c16 = (uint32_t)(sub * 2);
-          if (!(p.dbg_flags & 2)) {
+          if (!(dflags & 2)) {
           st_shared_v4(srow + ((c16 ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
           st_shared_v4(srow + (((c16 + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
           if (p.out_act) {
@@ -272,7 +276,7 @@ pw_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 32 * PW_EPI_WARPS);
-        if (ew == 0 && lane == 0 && !(p.dbg_flags & 1)) {
+        if (ew == 0 && lane == 0 && !(dflags & 1)) {
           const uint32_t src = stg_base + (uint32_t)buf * PW_STG_BYTES;
           tma_store_3d(&tmOut, src, nb * p.BN + b0, ti * 128, n);
           if (p.out_act) tma_store_3d(&tmAct, src + act_off, nb * p.BN + b0, ti * 128, n);
@@ -377,15 +381,25 @@ extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_samp
   p.stages = stages;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const PwParams);
   // first index: TMEM columns = two accumulators of the N block rounded up to a power of two
-  static const KernelFn kerns[4][2] = {{pw_conv_tc_kernel<64, false>, pw_conv_tc_kernel<64, true>},
-                                       {pw_conv_tc_kernel<128, false>, pw_conv_tc_kernel<128, true>},
-                                       {pw_conv_tc_kernel<256, false>, pw_conv_tc_kernel<256, true>},
-                                       {pw_conv_tc_kernel<512, false>, pw_conv_tc_kernel<512, true>}};
+  static const KernelFn kerns[4][2] = {{pw_conv_tc_kernel<64, false, false>, pw_conv_tc_kernel<64, true, false>},
+                                       {pw_conv_tc_kernel<128, false, false>, pw_conv_tc_kernel<128, true, false>},
+                                       {pw_conv_tc_kernel<256, false, false>, pw_conv_tc_kernel<256, true, false>},
+                                       {pw_conv_tc_kernel<512, false, false>, pw_conv_tc_kernel<512, true, false>}};
+#if AST_KERNEL_DEBUG
+  static const KernelFn kerns_dbg[4][2] = {{pw_conv_tc_kernel<64, false, true>, pw_conv_tc_kernel<64, true, true>},
+                                           {pw_conv_tc_kernel<128, false, true>, pw_conv_tc_kernel<128, true, true>},
+                                           {pw_conv_tc_kernel<256, false, true>, pw_conv_tc_kernel<256, true, true>},
+                                           {pw_conv_tc_kernel<512, false, true>, pw_conv_tc_kernel<512, true, true>}};
+#else
+  const KernelFn (*kerns_dbg)[2] = kerns;      // elimination flags need a build with AST_KERNEL_DEBUG=1
+#endif
   static bool attr_done = false;
   if (!attr_done) {
     for (int i = 0; i < 4; ++i)
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < 2; ++j) {
         AST_CUDA(cudaFuncSetAttribute(kerns[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        AST_CUDA(cudaFuncSetAttribute(kerns_dbg[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      }
     attr_done = true;
   }
   const int64_t max_ctas = (int64_t)sm_count * per_sm;
@@ -406,7 +420,7 @@ extern "C" int ast_pw_conv(const void* x, int ld_in, const void* w, int per_samp
     }
   }
   const int ki = BN <= 32 ? 0 : (BN <= 64 ? 1 : (BN <= 128 ? 2 : 3));
-  kerns[ki][p.f16 ? 1 : 0]<<<grid, PW_THREADS, smem, s>>>(tmA, tmB, tmOut, tmAct, p);
+  ((AST_KERNEL_DEBUG && dbg_flags) ? kerns_dbg : kerns)[ki][p.f16 ? 1 : 0]<<<grid, PW_THREADS, smem, s>>>(tmA, tmB, tmOut, tmAct, p);
   AST_CHECK_LAUNCH();
   return 0;
 }

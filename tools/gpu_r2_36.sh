@@ -1,9 +1,7 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_mobile.py tests/test_gpu_attn.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -n 4 | cut -c1-300
-for r in 0 1; do
-  AST_PW_RESIDENT=$r timeout 120 python tools/prof_pw.py 16 96 0 0 | sed "s/^/resident $r: /"
-  AST_PW_RESIDENT=$r timeout 120 python tools/prof_pw.py 40 240 1 1 | sed "s/^/resident $r: /"
-  AST_PW_RESIDENT=$r timeout 120 python tools/prof_pw.py 160 40 0 0 | sed "s/^/resident $r: /"
+for f in "" 8; do
+  for sh in "160 40 0 0" "96 16 0 0" "40 240 1 1" "16 96 0 0" "320 40 0 1 128"; do
+    AST_PW_DBGFLAGS=$f timeout 120 python tools/prof_pw.py $sh | sed "s/^/dbg '$f': /"
+  done
 done
 timeout 300 python tools/bench_pw.py 2>&1 | tail -n 60 > gpurun_out/bench_pw.txt; tail -1 gpurun_out/bench_pw.txt
-timeout 600 python tools/prof_ae.py --batch 32 --steps 5 2>&1 | tail -n 1
