@@ -13,7 +13,9 @@ python tools/ncu_family_traffic.py $G/r2_step_full_raw.csv conv3x3_pair_kernel "
 python tools/ncu_traffic.py $G/r2_step_full_raw.csv conv3x3_last_tn conv3x3_last_tn_kernel
 python tools/ncu_traffic.py $G/r2_step_full_raw.csv conv12_fused_pair_kernel conv12_fused_pair_kernel
 cp $G/layers.json $P/r2_layers_table.json
-cp $G/conv12_fused_breakdown.txt $P/r2_conv12_fused_breakdown.txt
+cp $G/conv12_fused_timing.txt $P/r2_conv12_fused_timing.txt
+cp $G/ae_small_batch.txt $P/r2_ae_step_vs_batch.txt
+cp $G/bench_dw.txt $P/r2_bench_depthwise_kernels.txt
 cp $G/bench_pw.txt $P/r2_bench_pointwise_kernels.txt
 cp $G/ae_b32.log $P/r2_ae_step_b32.json
 cp $G/smoke.log $P/r2_smoke.log

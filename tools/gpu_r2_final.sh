@@ -18,12 +18,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
   --log-file gpurun_out/ae_train_launches.csv python tools/prof_ae.py --batch 32 --profile > gpurun_out/ae_ncu.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
   --log-file gpurun_out/train_launches.csv python tools/prof_train.py --profile > gpurun_out/train_ncu.log 2>&1
-{
-for v in 0 3; do SUSTAINED=1 AST_CONV12_V=$v timeout 120 python tools/bench_conv12.py 2>&1 | tail -1; done
-for f in 2 6 64 128 256 454; do AST_CONV_DBGFLAGS=$f timeout 120 python tools/bench_conv12.py 2>&1 | tail -1; done
-AST_CONV_DEBUG=1 timeout 120 python tools/bench_conv12.py 2>&1 | grep "conv12 dbg" | tail -1
-} > gpurun_out/conv12_fused_breakdown.txt 2>&1
+# (the wait counters / elimination runs of the fused kernel need a build with AST_KERNEL_DEBUG=1: tools/gpu_r2_26.sh)
+for v in 0 3; do SUSTAINED=1 AST_CONV12_V=$v timeout 120 python tools/bench_conv12.py 2>&1 | tail -1; done > gpurun_out/conv12_fused_timing.txt 2>&1
 timeout 300 python tools/bench_pw.py > gpurun_out/bench_pw.txt 2>&1
 timeout 600 python tools/prof_ae.py --batch 32 --steps 5 > gpurun_out/ae_b32.log 2>&1
+timeout 600 python tools/ae_small_batch.py > gpurun_out/ae_small_batch.txt 2>&1
+timeout 300 python tools/bench_dw.py --n 32 > gpurun_out/bench_dw.txt 2>&1
 tail -n 3 gpurun_out/test_gpu_all.log; tail -n 3 gpurun_out/smoke.log | cut -c1-300; head -c 400 gpurun_out/bench.log; echo; head -c 300 gpurun_out/bench_ref.log; echo
 ls -la gpurun_out/r2_step_full_raw.csv gpurun_out/launches.csv
