@@ -8,6 +8,8 @@ ordinary fp32 ``.grad`` tensors on ordinary ``nn.Parameter``s).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -95,6 +97,26 @@ def conv_wgrad(dz_planar, x_planar3, N, H, W, cin, cout, w_like, b_like):
     return gw, gb
 
 
+def conv_wgrad_native(dz, dz_halo, x, N, H, W, cin, cout, w_like, b_like, need_b=True):
+    """(dW OIHW fp32, db fp32) of one 3x3 conv straight from the native tensors (K2wn, csrc/wgrad_mn.cu):
+    dz [N][H+2*dz_halo][W+2*dz_halo][cz] with a ZERO halo, x [N][H+2][W+2][cin] with the halo the conv saw."""
+    lib = L.load()
+    dev = dz.device
+    st = L.stream_ptr(dev)
+    dwpk = torch.empty((9, cout, cin), device=dev, dtype=torch.float32)
+    gb = torch.empty_like(b_like, dtype=torch.float32) if (b_like is not None and need_b) else None
+    L.check(lib.ast_conv3x3_wgrad_native(dz.data_ptr(), dz.shape[3], dz_halo, x.data_ptr(), dwpk.data_ptr(),
+                                         L.ptr(gb), N, H, W, cin, cout, st), "ast_conv3x3_wgrad_native")
+    gw = torch.empty_like(w_like, dtype=torch.float32, memory_format=torch.contiguous_format)
+    L.check(lib.ast_unpack_wgrad(dwpk.data_ptr(), gw.data_ptr(), None, None, cout, cin, 0, 0, st),
+            "ast_unpack_wgrad")
+    return gw, gb
+
+
+# AST_WGRAD_PLANAR=1: the round-1 weight-gradient path (channel-planar copies + one tap per work item), for A/B runs
+_WGRAD_PLANAR = os.environ.get("AST_WGRAD_PLANAR", "0") not in ("", "0")
+
+
 class DecoderFn(torch.autograd.Function):
     """img = decoder(x) for the classic mirrored decoder (models.py:598-628)."""
 
@@ -149,9 +171,13 @@ class DecoderFn(torch.autograd.Function):
             cz = dZ.shape[3]
             need_w, need_b = ctx.needs_input_grad[2 + 2 * i], ctx.needs_input_grad[3 + 2 * i]
             if need_w or need_b:
-                dzT = to_planar(dZ, N, cz, Hi, Wi, 2, False)
-                xT = to_planar(acts[i], N, cin, Hi, Wi, 1, True, nshift=3)
-                gw, gb = conv_wgrad(dzT, xT, N, Hi, Wi, cin, cout, params[2 * i], params[2 * i + 1])
+                if _WGRAD_PLANAR:
+                    dzT = to_planar(dZ, N, cz, Hi, Wi, 2, False)
+                    xT = to_planar(acts[i], N, cin, Hi, Wi, 1, True, nshift=3)
+                    gw, gb = conv_wgrad(dzT, xT, N, Hi, Wi, cin, cout, params[2 * i], params[2 * i + 1])
+                else:
+                    gw, gb = conv_wgrad_native(dZ, 2, acts[i], N, Hi, Wi, cin, cout, params[2 * i],
+                                               params[2 * i + 1], need_b)
                 grads[2 * i] = gw if need_w else None
                 grads[2 * i + 1] = gb if need_b else None
             if i == 0:

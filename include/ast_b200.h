@@ -319,6 +319,14 @@ int ast_native_to_planar(const void* native, void* planar, int N, int C, int H, 
 int ast_conv3x3_wgrad(const void* dz_planar, const void* x_planar3, float* dwpk, int N, int H, int W,
                       int Cin, int Cout, int wp, void* stream);
 
+/* K2wn: weight and bias gradient of a 3x3 conv straight from the native tensors (no planar copies): what autograd
+ * derives for nn.Conv2d.weight / .bias of the decoder convs (models.py:598-628) in train.py:287-300.
+ * dz: bf16 [N][H+2*dz_halo][W+2*dz_halo][cz], halo ZERO, channels >= Cout zero; x: bf16 [N][H+2][W+2][Cin] with the
+ * halo the forward conv saw.  dwpk [9][Cout][Cin] fp32 (overwritten) = sum_p dz[p][co] * x[p + tap][ci];
+ * db [Cout] fp32 (optional, overwritten) = sum_p dz[p][co].  cz % 8 == 0, Cin % 8 == 0, Cout <= cz <= 2048. */
+int ast_conv3x3_wgrad_native(const void* dz, int cz, int dz_halo, const void* x, float* dwpk, float* db, int N,
+                             int H, int W, int Cin, int Cout, void* stream);
+
 /* dwpk -> OIHW fp32 gradient (overwrite or accumulate); b_grad (optional) = row sums of dz_planar. */
 int ast_unpack_wgrad(const float* dwpk, float* w_grad, const void* dz_planar, float* b_grad, int Cout,
                      int Cin, int64_t ldq, int accumulate, void* stream);

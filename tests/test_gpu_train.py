@@ -60,6 +60,36 @@ def test_wgrad_gemm(shape):
     assert rel(gw.cpu(), w.grad) < 2e-3 and rel(gb.cpu(), b.grad) < 2e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 12, 20, 64, 128), (1, 16, 16, 128, 64), (3, 8, 24, 256, 256),
+                                   (2, 16, 16, 64, 3), (1, 40, 72, 64, 64), (2, 64, 64, 128, 256),
+                                   (1, 32, 32, 512, 256), (1, 9, 17, 16, 8), (1, 5, 130, 64, 64)])
+@pytest.mark.parametrize("dz_halo", [2, 1])
+def test_wgrad_native_gemm(shape, dz_halo):
+    """K2wn (csrc/wgrad_mn.cu): dW, db of a reflect-padded 3x3 conv straight from the native NHWC tensors (three kw
+    taps per CTA from one haloed X box) vs torch autograd: every patch geometry (bw = 16 / 32 / 64), ragged right /
+    bottom patches, several M / N blocks, Cout = 3 in a 64-channel dz, channel counts below one box."""
+    from arbitrarystyletransfer_b200 import _lib as L, engine as E, train_ops as T
+    N, H, W, cin, cout = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = bf16r(torch.randn(N, cin, H, W, generator=g))
+    dz = bf16r(torch.randn(N, cout, H, W, generator=g))
+    w = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    (F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w, b) * dz).sum().backward()
+    xin = E.nchw_to_native(x.cuda(), reflect=True)
+    cz = 64 if cout == 3 else cout
+    dzn = torch.zeros(N, H + 2 * dz_halo, W + 2 * dz_halo, cz, device="cuda", dtype=torch.bfloat16)
+    lib = L.load()
+    dzd = dz.cuda().contiguous()
+    L.check(lib.ast_nchw_to_native_ex(dzd.data_ptr(), dzn.data_ptr(), N, cout, H, W, cz, dz_halo, L.stream_ptr()))
+    gw, gb = T.conv_wgrad_native(dzn, dz_halo, xin, N, H, W, cin, cout, w.detach().cuda(), b.detach().cuda())
+    assert rel(gw.cpu(), w.grad) < 2e-3, f"dW rel {rel(gw.cpu(), w.grad)}"
+    assert rel(gb.cpu(), b.grad) < 2e-3, f"db rel {rel(gb.cpu(), b.grad)}"
+    # per-tap check: a wrong kw / kh assignment or a shifted window shows up as one bad tap
+    for t in range(9):
+        assert rel(gw.cpu()[:, :, t // 3, t % 3], w.grad[:, :, t // 3, t % 3]) < 3e-3, f"tap {t}"
+
+
 @pytest.mark.parametrize("cfg", [(2, 12, 20, 64, 64, False), (1, 16, 16, 128, 64, True), (2, 8, 24, 64, 3, False)])
 def test_dgrad_and_fold_single_layer(cfg):
     """One decoder link in isolation: v -> relu -> (upsample x2) -> ReflectionPad2d(1) -> conv.
