@@ -84,6 +84,7 @@ PROTOTYPES = {
     "ast_native_to_planar": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ast_unpack_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp]),
+    "ast_zero_halo": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     "ast_conv3x3_wgrad_native": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_set_act_format": (_i, [_i]),
     "ast_get_act_format": (_i, []),

@@ -259,6 +259,34 @@ __global__ void __launch_bounds__(256) planar_rowsum_kernel(const __nv_bfloat16*
   }
 }
 
+// Zero the halo ring (width hw) of a native tensor [N][H+2hw][W+2hw][C]: what a zero-padded conv reads around an
+// interior that its producer rewrites completely (replaces a memset of the whole tensor).
+__global__ void __launch_bounds__(kT) zero_halo_kernel(__nv_bfloat16* __restrict__ t, int N, int C, int H, int W, int hw) {
+  const int cv = C >> 3;
+  const int Hp = H + 2 * hw, Wp = W + 2 * hw;
+  const int64_t ring = (int64_t)2 * hw * Wp + (int64_t)2 * hw * H;   // pixels of the ring: full top / bottom rows + side columns
+  const int64_t total = (int64_t)N * ring * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    int64_t r = i / cv;
+    const int n = (int)(r / ring);
+    r -= (int64_t)n * ring;
+    int y, x;
+    if (r < (int64_t)2 * hw * Wp) {
+      const int row = (int)(r / Wp);
+      x = (int)(r - (int64_t)row * Wp);
+      y = row < hw ? row : H + row;               // rows hw .. 2hw-1 of the ring are the bottom rows H+hw .. H+2hw-1
+    } else {
+      r -= (int64_t)2 * hw * Wp;
+      const int row = (int)(r / (2 * hw));
+      const int c = (int)(r - (int64_t)row * 2 * hw);
+      y = hw + row;
+      x = c < hw ? c : W + c;
+    }
+    reinterpret_cast<uint4*>(t + (((int64_t)n * Hp + y) * Wp + x) * C)[v] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 static unsigned grid_for(int64_t total) {
   int64_t nb = (total + kT - 1) / kT;
   if (nb > 148 * 16) nb = 148 * 16;
@@ -275,6 +303,17 @@ extern "C" int ast_maxpool2_native(const void* in, void* out, int N, int C, int 
   if (C % 8 != 0) return AST_E_SHAPE;
   maxpool2_native_kernel<<<grid_for((int64_t)N * (H / 2) * (W / 2) * (C / 8)), kT, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), N, C, H, W);
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_zero_halo(void* native, int N, int C, int H, int W, int halo, void* stream) {
+  if (!native || N <= 0 || C <= 0 || H <= 0 || W <= 0 || halo < 1 || halo > 2) return AST_E_BADARG;
+  if (C % 8 != 0) return AST_E_SHAPE;
+  if (!aligned16(native)) return AST_E_ALIGN;
+  const int64_t ring = (int64_t)2 * halo * (W + 2 * halo) + (int64_t)2 * halo * H;
+  zero_halo_kernel<<<grid_for((int64_t)N * ring * (C / 8)), kT, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(native), N, C, H, W, halo);
   AST_CHECK_LAUNCH();
   return 0;
 }

@@ -74,12 +74,16 @@ def vgg_layer_plan(n_convs: int):
 
 
 def native_empty(N, H, W, Cc, device, zero_halo: bool):
-    """bf16 [N][H+2][W+2][C]; ``zero_halo`` buffers are zero-filled once and only ever written in
-    their interior, so the halo keeps VGG's zero padding."""
+    """bf16 [N][H+2][W+2][C]; ``zero_halo`` buffers get a zero halo ring (ast_zero_halo) and are only ever
+    written in their interior, so the halo keeps VGG's zero padding.  The interior is NOT initialised."""
     shape = (N, H + 2, W + 2, Cc)
+    t = torch.empty(shape, device=device, dtype=torch.bfloat16)
     if zero_halo:
-        return torch.zeros(shape, device=device, dtype=torch.bfloat16)
-    return torch.empty(shape, device=device, dtype=torch.bfloat16)
+        if Cc % 8:
+            return t.zero_()
+        # only the ring: every producer (conv epilogue, max-pool) rewrites the whole interior
+        L.check(L.load().ast_zero_halo(t.data_ptr(), N, Cc, H, W, 1, L.stream_ptr(t.device)), "ast_zero_halo")
+    return t
 
 
 def pack_conv_weight(w: torch.Tensor, flip: bool = False, cout_pad: int = 0) -> torch.Tensor:

@@ -9,6 +9,7 @@ ordinary fp32 ``.grad`` tensors on ordinary ``nn.Parameter``s).
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 
@@ -66,6 +67,24 @@ def pack_ex(w, flip, rows_pad=0, cols_pad=0, row_scale=None):
     L.check(lib.ast_pack_conv_weight_ex(w.data_ptr(), out.data_ptr(), co, ci, int(flip), R, Cc,
                                         L.ptr(row_scale), L.stream_ptr(w.device)),
             "ast_pack_conv_weight_ex")
+    return out
+
+
+_PACKED = {}
+
+
+def _packed_cached(p, kind, make):
+    """Packed bf16 form of a conv weight, re-made only when the parameter changes (same storage and autograd version
+    => same values): the VGG loss network is frozen in every training flow of the reference (train.py:55-56,
+    train_autoencoder.py:24-25), so its 2 x 9..16 pack launches per step disappear; a weight an optimiser updates
+    in place bumps ``_version`` and is re-packed.  Entries die with their parameter (weakref callback)."""
+    key = (id(p), kind)
+    ver = (p.data_ptr(), p._version, str(p.device))
+    hit = _PACKED.get(key)
+    if hit is not None and hit[0]() is p and hit[1] == ver:
+        return hit[2]
+    out = make()
+    _PACKED[key] = (weakref.ref(p, lambda _r, k=key: _PACKED.pop(k, None)), ver, out)
     return out
 
 
@@ -221,7 +240,8 @@ class EncoderFn(torch.autograd.Function):
                 E.conv3x3_first(img, wb[0].detach().float().contiguous(), wb[1], y, tap=tapbuf,
                                 tap_prerelu=(tap == "pre"))
             else:
-                E.conv3x3(x, E.pack_conv_weight(wb[2 * i]), wb[2 * i + 1], y, N=N, H=h, W=w, cin=cin,
+                E.conv3x3(x, _packed_cached(wb[2 * i], "fwd", lambda: E.pack_conv_weight(wb[2 * i])), wb[2 * i + 1], y,
+                          N=N, H=h, W=w, cin=cin,
                           cout=cout, relu=True, epilogue=L.EPI_PLAIN, halo=L.HALO_KEEP, tap=tapbuf,
                           tap_prerelu=(tap == "pre"))
             Ys.append(y)
@@ -234,6 +254,7 @@ class EncoderFn(torch.autograd.Function):
                                                 L.stream_ptr(dev)), "ast_maxpool2_native")
                 x, h, w = pz, h // 2, w // 2
         ctx.Ys, ctx.sizes, ctx.plan, ctx.N = Ys, sizes, plan, N
+        ctx.wb_objs = wb          # the parameter objects themselves: keys of the packed-weight cache in backward
         ctx.save_for_backward(*wb)
         return tuple(outs)
 
@@ -272,12 +293,13 @@ class EncoderFn(torch.autograd.Function):
                                          dZ.data_ptr(), N, cout, Hi, Wi, int(pooled), 1, st),
                     "ast_vgg_bwd_prep")
             if i > 0:
-                wflip = pack_ex(wb[2 * i], flip=True)
+                wflip = _packed_cached(ctx.wb_objs[2 * i], "flip", lambda: pack_ex(wb[2 * i], flip=True))
                 G = torch.empty((N, Hi + 2, Wi + 2, cin), device=dev, dtype=torch.bfloat16)
                 E.conv3x3(dZ, wflip, None, G, N=N, H=Hi, W=Wi, cin=cout, cout=cin, relu=False,
                           epilogue=L.EPI_PLAIN, halo=L.HALO_KEEP)
             else:
-                wflip = pack_ex(wb[0], flip=True, rows_pad=16, cols_pad=64, row_scale=_imagenet_rstd(dev))
+                wflip = _packed_cached(ctx.wb_objs[0], "flip0", lambda: pack_ex(wb[0], flip=True, rows_pad=16, cols_pad=64,
+                                                                                row_scale=_imagenet_rstd(dev)))
                 dimg = torch.empty(N, 3, Hi, Wi, device=dev, dtype=torch.float32)
                 E.conv3x3_last(dZ, None, wflip, None, dimg, False, impl=L.CONV_TC)
         ctx.Ys = None

@@ -288,6 +288,9 @@ int ast_pack_conv_weight_ex(const float* w_oihw, void* wpk, int Cout, int Cin, i
  * dst_halo (1 or 2); other channels and the halo are left untouched (caller zero-fills once). */
 int ast_nchw_to_native_ex(const float* nchw, void* native, int N, int C, int H, int W, int Cdst,
                           int dst_halo, void* stream);
+/* Zero the halo ring (width halo = 1 or 2) of a native tensor bf16 [N][H+2*halo][W+2*halo][C]: the zero padding of
+ * nn.Conv2d(.., padding=1) in VGG-19 (models.py:192-228) around an interior the producing kernel rewrites fully. */
+int ast_zero_halo(void* native, int N, int C, int H, int W, int halo, void* stream);
 /* interior of a native tensor with halo width src_halo -> NCHW fp32 */
 int ast_native_to_nchw_ex(const void* native, float* nchw, int N, int C, int H, int W, int src_halo,
                           void* stream);

@@ -90,6 +90,43 @@ def test_wgrad_native_gemm(shape, dz_halo):
         assert rel(gw.cpu()[:, :, t // 3, t % 3], w.grad[:, :, t // 3, t % 3]) < 3e-3, f"tap {t}"
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 5, 7, 1), (3, 64, 16, 16, 1), (1, 16, 9, 4, 2), (2, 24, 1, 1, 2)])
+def test_zero_halo_ring(shape):
+    """ast_zero_halo clears exactly the halo ring of a native tensor and nothing else."""
+    from arbitrarystyletransfer_b200 import _lib as L
+    N, Cc, H, W, hw = shape
+    t = torch.full((N, H + 2 * hw, W + 2 * hw, Cc), 3.0, device="cuda", dtype=torch.bfloat16)
+    L.check(L.load().ast_zero_halo(t.data_ptr(), N, Cc, H, W, hw, L.stream_ptr()))
+    want = torch.zeros_like(t)
+    want[:, hw:hw + H, hw:hw + W] = 3.0
+    assert torch.equal(t, want)
+
+
+def test_encoder_packed_weight_cache_follows_updates():
+    """EncoderFn packs the (normally frozen) VGG weights once; an in-place update must invalidate the cache."""
+    from arbitrarystyletransfer_b200 import models as M
+    torch.manual_seed(3)
+    enc = M.PretrainedEncoder(['relu_1', 'relu_3']).cuda()
+    img = torch.rand(1, 3, 32, 32, device="cuda", requires_grad=True)
+    a = [t.clone() for t in enc(img)]
+    b = [t.clone() for t in enc(img)]
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    with torch.no_grad():
+        for p in enc.parameters():
+            if p.dim() == 4:
+                p.mul_(0.5)
+    c = enc(img)
+    ref = M.PretrainedEncoder(['relu_1', 'relu_3']).cuda()
+    ref.load_state_dict(enc.state_dict())
+    d = ref(img)
+    assert not torch.equal(a[1], c[1])
+    assert all(torch.equal(x, y) for x, y in zip(c, d))
+    (c[1].sum()).backward()
+    g1 = img.grad.clone(); img.grad = None
+    (d[1].sum()).backward()
+    assert torch.equal(g1, img.grad)
+
+
 @pytest.mark.parametrize("cfg", [(2, 12, 20, 64, 64, False), (1, 16, 16, 128, 64, True), (2, 8, 24, 64, 3, False)])
 def test_dgrad_and_fold_single_layer(cfg):
     """One decoder link in isolation: v -> relu -> (upsample x2) -> ReflectionPad2d(1) -> conv.
