@@ -21,7 +21,8 @@
 // {64, bw, bh} boxes instead (A/B check of the shifted-start reads).
 // dZ's halo must be ZERO (it is: train_ops._zeros_native): patches that stick out of the image multiply X values
 // with zeros (TMA zero-fills out-of-tensor elements), so any H, W works.
-// Split-K over CTAs, fp32 red.global.add.v4 into dwpk [9][Cout][Cin] (zeroed here), bias gradient = column sums of dZ.
+// Split-K over CTAs, fp32 red.global.add.v4 into dwpk [9][Cout][Cin] (zeroed here); the bias gradient (column sums of
+// dZ) comes from the same dZ boxes times a constant box of ones.
 #include "tc.cuh"
 
 namespace ast {
@@ -32,7 +33,8 @@ constexpr int WN_ABOX = 64 * 128;          // {64 channels x 64 pixels} = 8 KB
 constexpr int WN_BSLOT = 9 * 1024;         // {64 channels x (bw + 2) * bh <= 72 pixels}
 constexpr int WN_MAX_STAGES = 6;
 constexpr int WN_SMEM_OPERANDS = 198 * 1024;
-constexpr int WN_SMEM = WN_SMEM_OPERANDS + (2 * WN_MAX_STAGES + 1) * 8 + 16 + 1024;
+constexpr int WN_ONES = 2048;              // 16 pixel rows x 128 B of bf16 1.0: the B operand of the bias-gradient MMAs
+constexpr int WN_SMEM = WN_SMEM_OPERANDS + WN_ONES + (2 * WN_MAX_STAGES + 1) * 8 + 16 + 1024;
 
 struct WnParams {
   int Cin, Cout, BN, a_boxes_last, b_boxes;   // a_boxes_last: 64-channel A boxes of the last M block (1 or 2)
@@ -41,6 +43,7 @@ struct WnParams {
   int chunks, split, sep;
   int stage_bytes, stages, b_off, b_slot;     // B region offset within a stage, bytes per 64-channel B slot
   float* dwpk;
+  float* db;                                  // optional [Cout]: column sums of dz (zeroed by the host)
 };
 
 __device__ __forceinline__ uint64_t wn_sdesc(uint32_t saddr, uint32_t lbo_bytes) {
@@ -66,13 +69,14 @@ wgrad3x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t bars = base + WN_SMEM_OPERANDS;
+  const uint32_t ones = base + WN_SMEM_OPERANDS;
+  const uint32_t bars = ones + WN_ONES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (WN_MAX_STAGES + s); };
   const uint32_t done_bar = bars + 8u * (2 * WN_MAX_STAGES);
   const uint32_t tmem_slot = bars + 8u * (2 * WN_MAX_STAGES + 1);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + WN_SMEM_OPERANDS + 8 * (2 * WN_MAX_STAGES + 1));
+      reinterpret_cast<volatile uint32_t*>(smem + WN_SMEM_OPERANDS + WN_ONES + 8 * (2 * WN_MAX_STAGES + 1));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
@@ -84,6 +88,14 @@ wgrad3x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int c1 = c0 + per < p.chunks ? c0 + per : p.chunks;
   const int nk = c1 > c0 ? c1 - c0 : 0;
   const int a_boxes = (mb == p.m_blocks - 1) ? p.a_boxes_last : 2;
+  // Bias gradient db[co] = sum_p dz[p][co]: the kh = 0 CTAs of the first N block multiply their dZ boxes with a constant
+  // box of ones as well (four N = 16 MMAs per patch into a fourth accumulator): no separate pass over dZ.
+  const bool do_db = p.db != nullptr && kh == 0 && nb == 0;
+  if (threadIdx.x >= 64) {
+    reinterpret_cast<uint4*>(smem + WN_SMEM_OPERANDS)[threadIdx.x - 64] =
+        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1) {
@@ -150,6 +162,9 @@ wgrad3x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint64_t b_desc0 = wn_sdesc(base + p.b_off, (uint32_t)p.b_slot);
       const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
       const uint32_t d1 = tmem_base + (uint32_t)p.BN, d2 = tmem_base + (uint32_t)(2 * p.BN);
+      const uint32_t d3 = tmem_base + (uint32_t)(3 * p.BN);
+      const uint32_t idesc_db = make_idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
+      const uint64_t ones_desc = wn_sdesc(ones, 0);
       int stage = 0;
       uint32_t soff = 0;               // stage * stage_bytes in 16-byte units (the address field never carries out)
       uint32_t phase = 0;
@@ -165,6 +180,7 @@ wgrad3x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             umma_bf16(tmem_base, ad + (uint64_t)(s * 128), bd + boff[s][0], idesc, acc);
             umma_bf16(d1, ad + (uint64_t)(s * 128), bd + boff[s][1], idesc, acc);
             umma_bf16(d2, ad + (uint64_t)(s * 128), bd + boff[s][2], idesc, acc);
+            if (do_db) umma_bf16(d3, ad + (uint64_t)(s * 128), ones_desc, idesc_db, acc);
           }
           umma_commit(empty_bar(stage));
         }
@@ -181,6 +197,12 @@ wgrad3x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const int co = mb * 128 + e * 32 + lane;
       const bool vec = (p.Cin & 3) == 0;
+      if (do_db) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(3 * p.BN), v);
+        tmem_ld_wait();
+        if (co < p.Cout) atomicAdd(p.db + co, __uint_as_float(v[0]));
+      }
       for (int kw = 0; kw < 3; ++kw) {
         float* orow = p.dwpk + ((int64_t)(kh * 3 + kw) * p.Cout + co) * p.Cin;
         for (int col = 0; col < p.BN; col += 16) {
@@ -210,40 +232,6 @@ wgrad3x3_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 }  // namespace tc
-
-// db[c] += sum over rows of dz[row][c] (bf16 rows of C channels; the zero halo rows add nothing).
-__global__ void __launch_bounds__(256) native_colsum_kernel(const __nv_bfloat16* __restrict__ dz, float* __restrict__ db,
-                                                            int64_t rows, int C, int Cvalid) {
-  __shared__ float red[256 * 8];
-  const int cv = C >> 3;
-  const int rl = 256 / cv;                       // row lanes per CTA
-  const int v = threadIdx.x % cv, r = threadIdx.x / cv;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  if (r < rl) {
-    for (int64_t row = (int64_t)blockIdx.x * rl + r; row < rows; row += (int64_t)gridDim.x * rl) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(dz + row * C) + v);
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[2 * j] += __uint_as_float(w[j] << 16);
-        acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = (r < rl) ? acc[j] : 0.f;
-  __syncthreads();
-  if (threadIdx.x < cv * 8) {
-    const int vv = threadIdx.x >> 3, j = threadIdx.x & 7;
-    float s = 0.f;
-    for (int rr = 0; rr < rl; ++rr) s += red[(rr * cv + vv) * 8 + j];
-    const int c = vv * 8 + j;
-    if (c < Cvalid) atomicAdd(db + c, s);
-  }
-}
-
 }  // namespace ast
 
 using namespace ast;
@@ -286,6 +274,8 @@ extern "C" int ast_conv3x3_wgrad_native(const void* dz, int cz, int dz_halo, con
   p.split = split;
 
   AST_CUDA(cudaMemsetAsync(dwpk, 0, sizeof(float) * 9 * (size_t)Cout * Cin, s));
+  if (db) AST_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, s));
+  p.db = db;
   CUtensorMap tmA, tmB;
   {
     const int Hp = H + 2 * dz_halo, Wp = W + 2 * dz_halo;
@@ -310,16 +300,5 @@ extern "C" int ast_conv3x3_wgrad_native(const void* dz, int cz, int dz_halo, con
   }
   wgrad3x3_mn_kernel<<<dim3((unsigned)(3 * split), p.m_blocks, n_blocks), WN_THREADS, WN_SMEM, s>>>(tmA, tmB, p);
   AST_CHECK_LAUNCH();
-  if (db) {
-    AST_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, s));
-    const int64_t rows = (int64_t)N * (H + 2 * dz_halo) * (W + 2 * dz_halo);
-    const int rl = 256 / (cz / 8);
-    if (rl < 1) return AST_E_SHAPE;
-    int64_t nb = (rows + (int64_t)rl * 16 - 1) / ((int64_t)rl * 16);
-    if (nb > 148 * 8) nb = 148 * 8;
-    if (nb < 1) nb = 1;
-    native_colsum_kernel<<<(unsigned)nb, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dz), db, rows, cz, Cout);
-    AST_CHECK_LAUNCH();
-  }
   return 0;
 }
