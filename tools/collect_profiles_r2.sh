@@ -17,7 +17,6 @@ cp $G/conv12_fused_timing.txt $P/r2_conv12_fused_timing.txt
 cp $G/ae_small_batch.txt $P/r2_ae_step_vs_batch.txt
 cp $G/bench_dw.txt $P/r2_bench_depthwise_kernels.txt
 cp $G/bench_wgrad.txt $P/r2_bench_wgrad_native.txt
-cp $G/sanitize_wgrad_native.log $P/r2_sanitize_wgrad_native.log
 cp $G/bench_pw.txt $P/r2_bench_pointwise_kernels.txt
 cp $G/ae_b32.log $P/r2_ae_step_b32.json
 cp $G/smoke.log $P/r2_smoke.log

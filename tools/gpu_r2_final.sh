@@ -21,7 +21,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 # (the wait counters / elimination runs of the fused kernel need a build with AST_KERNEL_DEBUG=1: tools/gpu_r2_26.sh)
 for v in 0 3; do SUSTAINED=1 AST_CONV12_V=$v timeout 120 python tools/bench_conv12.py 2>&1 | tail -1; done > gpurun_out/conv12_fused_timing.txt 2>&1
 timeout 300 python tools/bench_wgrad.py --step > gpurun_out/bench_wgrad.txt 2>&1
-timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_train.py -q -x -p no:cacheprovider -k "wgrad_native or zero_halo" 2>&1 | tail -4 > gpurun_out/sanitize_wgrad_native.log
 timeout 300 python tools/bench_pw.py > gpurun_out/bench_pw.txt 2>&1
 timeout 600 python tools/prof_ae.py --batch 32 --steps 5 > gpurun_out/ae_b32.log 2>&1
 timeout 600 python tools/ae_small_batch.py > gpurun_out/ae_small_batch.txt 2>&1
