@@ -57,6 +57,9 @@ def test_argument_errors_without_gpu(lib_path):
     assert lib.ast_hist_ws_bytes(4) >= 2 * 4 * 257 * 8
     assert lib.ast_hist_loss_fwd(None, None, 1, 1, 1, 1.0, 1.0, None, None, None, 0, None) == -1
     assert lib.ast_split3_rows(None, 8, None, 1, 8, 0, None) == -1
+    # round 2: the native-layout weight gradient (K2wn) and the halo-ring zeroing
+    assert lib.ast_conv3x3_wgrad_native(None, 64, 2, None, None, None, 1, 8, 8, 64, 64, None) == -1
+    assert lib.ast_zero_halo(None, 1, 8, 4, 4, 1, None) == -1
 
 
 def test_no_cpu_fallback():
@@ -89,3 +92,6 @@ def test_sass_is_blackwell_native(lib_path):
     for body in fused:
         assert "0x40004050" in body and "UTCHMMA.2CTA" in body
     assert any("USETMAXREG" in body for body in fused)        # the default variant rebalances registers per role
+    # K2wn: MN-major tcgen05 GEMM fed by 4-D TMA boxes, vector reductions into the packed gradient
+    wn = [p for p in parts if p.startswith("_ZN3ast2tc18wgrad3x3_mn_kernel")]
+    assert len(wn) == 1 and "UTCHMMA" in wn[0] and "UTMALDG.4D" in wn[0] and "REDG.E.ADD.F32x4" in wn[0]
