@@ -98,7 +98,7 @@ PROTOTYPES = {
     "ast_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _vp]),
     "ast_cvt_f16_to_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "ast_bn_stats": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
-    "ast_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _vp]),
+    "ast_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _vp, _vp]),
     "ast_affine_act": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _vp]),
     "ast_dw_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
     "ast_se_bn_combine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _vp]),

@@ -101,9 +101,10 @@ bn_stats_kernel(const AT* __restrict__ x, int ld, double* __restrict__ sums, int
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps,
-                                   float* __restrict__ stat, int C) {
+                                   float* __restrict__ stat, int C, long long* __restrict__ num_batches_tracked) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;   // nn.BatchNorm2d's counter (one thread: no race)
   const double mean = sums[c] / count;
   double var = sums[C + c] / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -848,10 +849,10 @@ extern "C" int ast_bn_stats(const void* x, int ld, double* sums, int N, int C, i
 
 extern "C" int ast_bn_finalize(const double* sums, double count, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps, float* stat,
-                               int C, void* stream) {
+                               int C, long long* num_batches_tracked, void* stream) {
   if (!sums || !gamma || !beta || !stat || C <= 0 || count <= 0) return AST_E_BADARG;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, gamma, beta, running_mean,
-                                                                        running_var, momentum, eps, stat, C);
+                                                                        running_var, momentum, eps, stat, C, num_batches_tracked);
   AST_CHECK_LAUNCH();
   return 0;
 }

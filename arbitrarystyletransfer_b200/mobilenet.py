@@ -280,9 +280,9 @@ def _bn_train_forward(a, bn):
     L.check(lib.ast_bn_finalize(sums.data_ptr(), float(N * H * W), bn.weight.data_ptr(), bn.bias.data_ptr(),
                                 bn.running_mean.data_ptr() if track else None,
                                 bn.running_var.data_ptr() if track else None, float(bn.momentum), float(bn.eps),
-                                stat.data_ptr(), Cc, _st(a)), "ast_bn_finalize")
-    if track and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+                                stat.data_ptr(), Cc,
+                                bn.num_batches_tracked.data_ptr() if track and bn.num_batches_tracked is not None else None,
+                                _st(a)), "ast_bn_finalize")   # the counter's += 1 rides in the same launch
     return stat
 
 
@@ -295,7 +295,7 @@ def _bn_eval_stat(bn, dev):
     Cc = rm.numel()
     stat = torch.empty(4, Cc, device=dev, dtype=torch.float32)
     L.check(lib.ast_bn_finalize(sums.data_ptr(), 1.0, bn.weight.data_ptr(), bn.bias.data_ptr(), None, None, 0.0,
-                                float(bn.eps), stat.data_ptr(), Cc, L.stream_ptr(dev)), "ast_bn_finalize")
+                                float(bn.eps), stat.data_ptr(), Cc, None, L.stream_ptr(dev)), "ast_bn_finalize")
     return stat
 
 
@@ -416,7 +416,15 @@ class _BlockFn(torch.autograd.Function):
         else:
             d_a3 = d_out
         d_u = pw_conv(d_a3, prep_weight(P["w2"], oup, hid, 1), None, 0, hid)
-        dW2 = torch.zeros_like(P["w2"], dtype=torch.float32)
+        # one zero fill for the block's three atomically accumulated weight gradients (segments 256-byte aligned)
+        names = ("w2", "wd") + (("w1",) if expand else ())
+        offs, tot = [], 0
+        for nm in names:
+            offs.append(tot)
+            tot += (P[nm].numel() + 63) // 64 * 64
+        flat = torch.zeros(tot, device=dev, dtype=torch.float32)
+        zg = {nm: flat[o:o + P[nm].numel()].view(P[nm].shape) for nm, o in zip(names, offs)}
+        dW2 = zg["w2"]
         _pw_wgrad(u, d_a3, dW2, 1, hid, a_is_act=True)                   # dW2[j][i] += sum u[p][i] d_a3[p][j]
         grads["w2"] = dW2
         # ---- SE, Hardswish and the depthwise norm ----
@@ -449,7 +457,7 @@ class _BlockFn(torch.autograd.Function):
                                      L.ptr(coef2), d_a2.data_ptr(), N, hid, HWo, st), "ast_dw_bwd_apply")
         # ---- depthwise conv ----
         dw_in = h1 if expand else x
-        dWd = torch.zeros_like(P["wd"], dtype=torch.float32)
+        dWd = zg["wd"]
         L.check(lib.ast_dw_conv_wgrad(d_a2.data_ptr(), dw_in.data_ptr(), dWd.data_ptr(), N, hid, H, W, k, stride,
                                       int(up2), st), "ast_dw_conv_wgrad")
         grads["wd"] = dWd
@@ -466,7 +474,7 @@ class _BlockFn(torch.autograd.Function):
                 d_a1, grads["g1"], grads["b1"] = _bn_backward(d_in, a1, stat1, ctx.frozen)
             else:
                 d_a1 = d_in
-            dW1 = torch.zeros_like(P["w1"], dtype=torch.float32)
+            dW1 = zg["w1"]
             _pw_wgrad(d_a1, x, dW1, inp, 1, b_is_act=True)               # dW1[i][j] += sum d_a1[p][i] x[p][j]
             grads["w1"] = dW1
             d_x = None

@@ -415,10 +415,11 @@ int ast_cvt_f16_to_bf16(const void* x, int64_t ld_x, void* out, int64_t ld_out, 
 
 /* sums[0][c] = sum x, sums[1][c] = sum x^2 over all N*HW rows. */
 int ast_bn_stats(const void* x, int ld, double* sums, int N, int C, int64_t HW, void* stream);
-/* sums -> stat; running_mean/var (nullable) updated like nn.BatchNorm2d (momentum, unbiased variance). */
+/* sums -> stat; running_mean/var (nullable) updated like nn.BatchNorm2d (momentum, unbiased variance);
+ * num_batches_tracked (nullable, device int64 scalar) += 1 as nn.BatchNorm2d.forward does in training mode. */
 int ast_bn_finalize(const double* sums, double count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, float* stat, int C,
-                    void* stream);
+                    long long* num_batches_tracked, void* stream);
 /* out = act(x*sc[c] + sh[c]) [* se[n][c]] [+ res]; pool[n][c] (optional) = sum over pixels of act(..)
  * (before the se factor).  sc/sh null = identity; act 0 none, 1 Hardswish; out may be null (pool only). */
 int ast_affine_act(const void* x, int ld_x, const float* sc, const float* sh, int act, const float* se,
