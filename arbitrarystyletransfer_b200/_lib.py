@@ -116,6 +116,7 @@ PROTOTYPES = {
     "ast_head_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_head_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ast_prep_weight": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "ast_prep_block_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ast_bgemm": (_i, [_vp, _i, _i, _i64, _vp, _i, _i, _i64, _vp, _i, _i64, _i64, _i, _i, _i, _i, _vp]),
     "ast_attn_softmax": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp]),
     "ast_attn_softmax_bwd": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _vp]),

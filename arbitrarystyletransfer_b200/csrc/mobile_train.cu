@@ -775,6 +775,36 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, void* __restrict
   }
 }
 
+// ---- all GEMM / depthwise forms of ONE DepthWiseConv block's weights in one launch (5 prep_weight launches -> 1):
+// pointwise weights w1 [hid][inp], w2 [oup][hid]: forward form (activation format, same layout) + data-gradient form
+// (bf16, transposed); depthwise weight wd [hid][k*k]: fp32 transposed [k*k][hid].
+struct PrepSeg {
+  const float* w;
+  void* out_f;      // pointwise: activation-format copy; depthwise: fp32 transposed
+  void* out_t;      // pointwise: bf16 transposed; depthwise: unused
+  int R, C;
+};
+struct PrepBlockArgs {
+  PrepSeg seg[3];   // w1 (may be empty: R = 0), wd, w2
+  int64_t off[4];
+};
+template <typename AT>
+__global__ void prep_block_weights_kernel(const PrepBlockArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.off[3]; i += (int64_t)gridDim.x * blockDim.x) {
+    const int sgi = i >= a.off[2] ? 2 : (i >= a.off[1] ? 1 : 0);
+    const PrepSeg& g = a.seg[sgi];
+    const int64_t j = i - a.off[sgi];
+    const int r = (int)(j / g.C), c = (int)(j - (int64_t)r * g.C);
+    const float v = g.w[j];
+    if (sgi == 1) {
+      reinterpret_cast<float*>(g.out_f)[(int64_t)c * g.R + r] = v;
+    } else {
+      H16<AT>::store1(g.out_f, j, v);
+      reinterpret_cast<__nv_bfloat16*>(g.out_t)[(int64_t)c * g.R + r] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 // ---- NCHW fp32 -> NHWC bf16 (row stride ld) --------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src,
                                                            uint16_t* __restrict__ dst, int ld, int C,
@@ -1079,6 +1109,26 @@ extern "C" int ast_prep_weight(const float* w, void* out, int R, int Cc, int mod
   int64_t nb = ((int64_t)R * Cc + 255) / 256;
   if (nb > 148 * 4) nb = 148 * 4;
   AST_ACT_DISPATCH(prep_weight_kernel<AT><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(w, out, R, Cc, mode));
+  AST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int ast_prep_block_weights(const float* w1, int R1, int C1, void* w1_f, void* w1_t, const float* wd, int Rd,
+                                      int Cd, float* wd_t, const float* w2, int R2, int C2, void* w2_f, void* w2_t,
+                                      void* stream) {
+  if (!wd || !wd_t || !w2 || !w2_f || !w2_t || Rd <= 0 || Cd <= 0 || R2 <= 0 || C2 <= 0) return AST_E_BADARG;
+  if (w1 && (!w1_f || !w1_t || R1 <= 0 || C1 <= 0)) return AST_E_BADARG;
+  PrepBlockArgs a = {};
+  a.seg[0] = PrepSeg{w1, w1_f, w1_t, w1 ? R1 : 0, w1 ? C1 : 1};
+  a.seg[1] = PrepSeg{wd, wd_t, nullptr, Rd, Cd};
+  a.seg[2] = PrepSeg{w2, w2_f, w2_t, R2, C2};
+  a.off[0] = 0;
+  a.off[1] = w1 ? (int64_t)R1 * C1 : 0;
+  a.off[2] = a.off[1] + (int64_t)Rd * Cd;
+  a.off[3] = a.off[2] + (int64_t)R2 * C2;
+  int64_t nb = (a.off[3] + 255) / 256;
+  if (nb > 148 * 4) nb = 148 * 4;
+  AST_ACT_DISPATCH(prep_block_weights_kernel<AT><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(a));
   AST_CHECK_LAUNCH();
   return 0;
 }

@@ -190,6 +190,32 @@ def prep_weight(w, rows, cols, mode):
     return out
 
 
+def prep_block_weights(w1, wd, w2, hid, inp, oup, kk):
+    """Every prepared form of one DepthWiseConv block's weights in ONE launch (ast_prep_block_weights): returns
+    (w1_f [hid][inp], w1_t [inp][hid], wd_t fp32 [k*k][hid], w2_f [oup][hid], w2_t [hid][oup]); ``w1`` may be None
+    (expand_ratio == 1).  ``*_f`` are the forward GEMM operands (activation format), ``*_t`` the bf16 transposed
+    operands of the data-gradient GEMMs."""
+    lib = L.load()
+
+    def f32(w):
+        w = w.detach()
+        return w if (w.dtype == torch.float32 and w.is_contiguous()) else w.float().contiguous()
+    wd, w2 = f32(wd), f32(w2)
+    dev = w2.device
+    w1_f = w1_t = None
+    if w1 is not None:
+        w1 = f32(w1)
+        w1_f = torch.empty((hid, inp), device=dev, dtype=BITS16)
+        w1_t = torch.empty((inp, hid), device=dev, dtype=BITS16)
+    wd_t = torch.empty((kk, hid), device=dev, dtype=torch.float32)
+    w2_f = torch.empty((oup, hid), device=dev, dtype=BITS16)
+    w2_t = torch.empty((hid, oup), device=dev, dtype=BITS16)
+    L.check(lib.ast_prep_block_weights(L.ptr(w1), hid, inp, L.ptr(w1_f), L.ptr(w1_t), wd.data_ptr(), hid, kk,
+                                       wd_t.data_ptr(), w2.data_ptr(), oup, hid, w2_f.data_ptr(), w2_t.data_ptr(),
+                                       _st(w2)), "ast_prep_block_weights")
+    return w1_f, w1_t, wd_t, w2_f, w2_t
+
+
 def nchw_to_nhwc(x, f16=False):
     """NCHW fp32 -> NHWC 16-bit: fp16 bit patterns (``f16``, forward activations) or bf16 (gradients, attention)."""
     lib = L.load()
@@ -361,10 +387,12 @@ class _BlockFn(torch.autograd.Function):
         frozen = norm and not mod.training       # eval-mode BatchNorm with gradients: running statistics, no update
         ctx.frozen = frozen
         a1 = stat1 = stat2 = stat3 = a3 = None
+        # all five prepared weight forms of the block (forward + data-gradient operands) in one launch
+        w1b, w1t, wd, w2b, w2t = prep_block_weights(P["w1"] if expand else None, P["wd"], P["w2"], hid, mod.inp, mod.oup,
+                                                    k * k)
         if expand:
             if up2:
                 raise L.AstError("the upsampled input is only supported for expand_ratio == 1 blocks")
-            w1b = prep_weight(P["w1"], hid, mod.inp, 3)
             if norm:
                 a1 = pw_conv(x, w1b, None, 0, hid, f16=act_is_f16())
                 stat1 = _bn_forward(a1, bns[0], frozen)
@@ -373,7 +401,6 @@ class _BlockFn(torch.autograd.Function):
                 a1, dw_in = pw_conv(x, w1b, None, 1, hid, want_raw=True, f16=act_is_f16())
         else:
             dw_in = x
-        wd = prep_weight(P["wd"], hid, k * k, 2)                       # fp32 [k*k][C]
         a2, pool = dw_conv(dw_in, wd, None, k, stride, up2=up2, act=0 if norm else 2, want_pool=not norm)
         Ho, Wo = a2.shape[1], a2.shape[2]
         if norm:
@@ -382,7 +409,6 @@ class _BlockFn(torch.autograd.Function):
         inv_hw = 1.0 / (Ho * Wo)
         s, sehid, sepre = se_fc(pool, inv_hw, P["se_w1"], P["se_b1"], P["se_w2"], P["se_b2"], save=True)
         u, _ = affine_act(a2, stat2[2] if norm else None, stat2[3] if norm else None, 1, se=s)
-        w2b = prep_weight(P["w2"], mod.oup, hid, 3)
         res = x if mod.identity else None
         if norm:
             a3 = pw_conv(u, w2b, None, 0, mod.oup, f16=act_is_f16())
@@ -393,7 +419,7 @@ class _BlockFn(torch.autograd.Function):
         ctx.mod, ctx.up2, ctx.geom = mod, up2, (N, H, W, Ho, Wo)
         ctx.n_params = len(params)
         ctx.save_for_backward(x, a1, dw_in if expand else None, a2, u, a3, s, sehid, sepre, pool, stat1, stat2,
-                              stat3, wd, *params)
+                              stat3, wd, w1t, w2t, *params)
         return out
 
     @staticmethod
@@ -402,8 +428,8 @@ class _BlockFn(torch.autograd.Function):
         mod, up2 = ctx.mod, ctx.up2
         N, H, W, Ho, Wo = ctx.geom
         saved = ctx.saved_tensors
-        x, a1, h1, a2, u, a3, s, sehid, sepre, pool, stat1, stat2, stat3, wd = saved[:14]
-        P = mod._unpack(saved[14:])
+        x, a1, h1, a2, u, a3, s, sehid, sepre, pool, stat1, stat2, stat3, wd, w1t, w2t = saved[:16]
+        P = mod._unpack(saved[16:])
         norm, expand = mod.use_norm, mod.expand
         hid, k, stride, inp, oup = mod.hidden, mod.k, mod.stride, mod.inp, mod.oup
         dev = x.device
@@ -415,7 +441,7 @@ class _BlockFn(torch.autograd.Function):
             d_a3, grads["g3"], grads["b3"] = _bn_backward(d_out, a3, stat3, ctx.frozen)
         else:
             d_a3 = d_out
-        d_u = pw_conv(d_a3, prep_weight(P["w2"], oup, hid, 1), None, 0, hid)
+        d_u = pw_conv(d_a3, w2t, None, 0, hid)
         # one zero fill for the block's three atomically accumulated weight gradients (segments 256-byte aligned)
         names = ("w2", "wd") + (("w1",) if expand else ())
         offs, tot = [], 0
@@ -479,7 +505,7 @@ class _BlockFn(torch.autograd.Function):
             grads["w1"] = dW1
             d_x = None
             if ctx.needs_input_grad[0]:
-                d_x = pw_conv(d_a1, prep_weight(P["w1"], hid, inp, 1), None, 0, inp,
+                d_x = pw_conv(d_a1, w1t, None, 0, inp,
                               residual=d_out if mod.identity else None)
         else:
             d_x = d_in if ctx.needs_input_grad[0] else None

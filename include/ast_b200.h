@@ -477,6 +477,13 @@ int ast_head_dgrad(const float* dY, const float* w, void* dx, int N, int H, int 
 /* fp32 [R][Cc] -> mode 0: bf16 [R][Cc]; 1: bf16 [Cc][R]; 2: fp32 [Cc][R]; 3: fp16 [R][Cc] (forward GEMM weights). */
 int ast_prep_weight(const float* w, void* out, int R, int Cc, int mode, void* stream);
 
+/* The five prepared forms of ONE DepthWiseConv block's weights (mobilenetv2.py:103-150) in one launch: pointwise
+ * w1 [R1][C1] (nullable: expand_ratio == 1 blocks) and w2 [R2][C2] -> activation-format copy (w*_f, same layout, the
+ * forward GEMM operand) + bf16 transposed copy (w*_t, the data-gradient GEMM operand); depthwise wd [Rd][Cd] ->
+ * fp32 transposed [Cd][Rd]. */
+int ast_prep_block_weights(const float* w1, int R1, int C1, void* w1_f, void* w1_t, const float* wd, int Rd, int Cd,
+                           float* wd_t, const float* w2, int R2, int C2, void* w2_f, void* w2_t, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K6  AdaAttN (models.py:70-115).  The layer's contractions -- Q K^T (:97),
  * P V and P V^2 (:101-103) and the five products of their backward pass -- run on one batched tcgen05 GEMM that
