@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AST_B200_LIB") or os.path.join(HERE, "libast_b200.so")
 
 # mirrors of the header constants
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_STYLES = 8
 F_CANONICAL, F_BIASED, F_BF16 = 0x1, 0x2, 0x4
 EPI_PLAIN, EPI_POOL2, EPI_UP2, EPI_UPFOLD = 0, 1, 2, 4

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 2
+#define AST_ABI_VERSION 3
 
 /* error codes (negative) */
 #define AST_E_BADARG   (-1)  /* null pointer / non-positive size */
